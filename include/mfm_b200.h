@@ -1,0 +1,170 @@
+/* mfm_b200 — C ABI of the B200-native Markovian-Flow-Matching hot path.
+ *
+ * Drop-in boundary for the data-parallel hot path of albcab/mfm.  The reference has no FFI of its
+ * own (it is pure Python/JAX); each entry point below replaces the jitted JAX computation cited
+ * next to it (paths relative to the reference repository).  A maintainer binds these from JAX
+ * with jax.ffi / from Python with ctypes.
+ *
+ * Conventions
+ *   - all array pointers are DEVICE pointers (float32 / uint32 / uint8), row-major [N, d];
+ *   - keys are raw jax.random legacy keys: uint32[2] (or uint32[N,2]) in device memory;
+ *   - every call enqueues work on `stream` and returns 0 on success or a negative MFM_ERR_* code;
+ *     mfm_last_error() returns a description.  Nothing is allocated inside a call: scratch comes
+ *     from the caller-provided workspace whose size the matching *_workspace_bytes() reports;
+ *   - mfm_ode_* / mfm_flow_mh_step poll a device counter once per Runge-Kutta iteration (the
+ *     adaptive step loop is data dependent), i.e. they synchronise `stream`; all other calls are
+ *     fully asynchronous.
+ *   - arithmetic type: float32 everywhere; dense contractions use error-compensated TF32
+ *     (3 tensor-core passes, fp32 accumulate) so results are fp32-accurate.
+ */
+#ifndef MFM_B200_H
+#define MFM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* mfm_stream_t; /* == cudaStream_t */
+
+enum { MFM_TARGET_GMM = 0, MFM_TARGET_PHI4 = 1, MFM_TARGET_PINES = 2, MFM_TARGET_GAUSS = 3 };
+
+/* Target descriptor: replaces the Python closure `logdensity_fn` that the reference passes to
+ * bblackjax.mcmc.mala.init/kernel (mala.py:51-54,86-93) and `dist.loglik/logprior/logprob`
+ * (distributions.py).  logprob_beta(x) = beta * loglik(x) + logprior(x)
+ * (exe_flow_matching.py:301). */
+typedef struct mfm_target {
+    int kind;            /* MFM_TARGET_* */
+    int dim;             /* d */
+    float beta;          /* tempering inverse temperature (1 = untempered) */
+    /* GMM (distributions.py:42-61): dim must be 2 */
+    int n_modes;
+    const float* modes;   /* [K,2] */
+    const float* stds;    /* [K,2] = sqrt(covs) */
+    const float* weights; /* [K] */
+    /* phi-four (distributions.py:114-160), Dirichlet(0) boundary */
+    float phi_a, phi_beta;
+    /* pines LGCP (distributions.py:231-307, cox_process_utils.py:98-165) */
+    const float* counts;  /* [d] flat bin counts */
+    const float* kinv;    /* [d,d] inverse Gram matrix (symmetric), fp32 */
+    const float* kinv_mu; /* [d] mu * rowsum(kinv) */
+    const float* kinv_diag; /* [d] diagonal of kinv */
+    float mu, log_norm, poisson_a;
+    /* independent Gaussian (distributions.py:80-97) */
+    float gauss_mean, gauss_std;
+} mfm_target_t;
+
+/* VectorFieldNet parameters (exe_flow_matching.py:56-90).  One flat fp32 parameter buffer; layer i
+ * (flax name Dense_i) has kernel [in_i, out_i] row-major at params + w_off[i] and bias [out_i] at
+ * params + b_off[i].  Layers: 0,1 time branch (2F->H->H), 2,3 x branch (d->H->H), 4 nn_t head
+ * (H->d), 5,6 joint (2H->H->H), 7 nn_xt head (H->d). */
+typedef struct mfm_field {
+    int dim, hidden, fourier_dim;
+    const float* params;     /* flat buffer */
+    long long w_off[8], b_off[8];
+    long long n_params;      /* total floats */
+    const float* omega;      /* [F] fourier_random (module attribute, :350-351) */
+    float grad_clip;         /* <=0: no clip; else clip grad logprob to +-grad_clip (:87-90) */
+} mfm_field_t;
+
+typedef struct mfm_ode_opts {
+    float rtol, atol;        /* multi_modal.py:205-206 */
+    int mxstep;              /* :207 */
+    int hutch;               /* 1: Hutchinson (Gaussian probe); 0: exact trace */
+    int n_times;             /* output grid size (2, or 5 for 4-mode, exe_flow_matching.py:347) */
+} mfm_ode_opts_t;
+
+const char* mfm_last_error(void);
+int mfm_version(void);
+
+/* ---- RNG: jax.random semantics (threefry2x32, legacy keys, x64 off) ------------------------ */
+/* jax.random.split(key, num) -> out uint32[num,2] */
+int mfm_threefry_split(const uint32_t* key, int num, uint32_t* out, mfm_stream_t stream);
+/* vmap(lambda k: split(k, num))(keys[n]) -> out uint32[n,num,2] */
+int mfm_threefry_split_batched(const uint32_t* keys, int n, int num, uint32_t* out, mfm_stream_t stream);
+/* jax.random.bits(key, (n,), uint32) */
+int mfm_threefry_bits(const uint32_t* key, long long n, uint32_t* out, mfm_stream_t stream);
+/* jax.random.uniform(key, (n,), float32, minval, maxval) */
+int mfm_threefry_uniform(const uint32_t* key, long long n, float minval, float maxval, float* out, mfm_stream_t stream);
+/* jax.random.normal(key, (n,), float32) */
+int mfm_threefry_normal(const uint32_t* key, long long n, float* out, mfm_stream_t stream);
+/* vmap(lambda k: uniform(k, (d,), float32, minval, maxval))(keys[n]) -> out [n,d] */
+int mfm_threefry_uniform_batched(const uint32_t* keys, int n, int d, float minval, float maxval, float* out, mfm_stream_t stream);
+/* vmap(lambda k: normal(k, (d,)))(keys[n]) -> out [n,d] */
+int mfm_threefry_normal_batched(const uint32_t* keys, int n, int d, float* out, mfm_stream_t stream);
+/* host-side threefry split (key management outside the device), same semantics */
+void mfm_host_threefry_split(const uint32_t key[2], int num, uint32_t* out);
+
+/* ---- dense contraction used by every layer (test hook) --------------------------------------
+ * C[M,N] = relu?(opA(A)[M,K] * opB(B)[K,N] + bias[N]); fp32 in/out, 3xTF32 on tensor cores.
+ * a_kmajor: A[m*lda+k] (else A[k*lda+m]);  b_nmajor: B[k*ldb+n] (else B[n*ldb+k]). */
+int mfm_gemm_tf32x3(int M, int N, int K, const float* A, long long lda, int a_kmajor, const float* B, long long ldb,
+                    int b_nmajor, const float* bias, int relu, float* C, long long ldc, mfm_stream_t stream);
+
+/* ---- targets -------------------------------------------------------------------------------- */
+size_t mfm_target_workspace_bytes(const mfm_target_t* t, int n);
+/* vmap(init)(positions, logprob_beta): mala.py:51-54, exe_flow_matching.py:316.
+ * loglik_out (optional) receives the untempered log-likelihood (exe_flow_matching.py:418). */
+int mfm_logdensity_and_grad(const mfm_target_t* t, int n, const float* x, float* logp, float* grad,
+                            float* loglik_out, void* ws, size_t ws_bytes, mfm_stream_t stream);
+
+/* ---- MALA (bblackjax/mcmc/mala.py:86-118 + diffusions.py:22-33 + proposal.py) --------------- */
+size_t mfm_mala_workspace_bytes(const mfm_target_t* t, int n);
+/* keys = split(rng_key, n); vmap(kernel)(keys, states, logprob_beta, step_size)
+ * (exe_flow_matching.py:303,313).  State arrays are updated IN PLACE.
+ * chain_offset/n_total: this rank holds chains [chain_offset, chain_offset+n) of an n_total-chain
+ * ensemble; per-chain keys are rows of split(rng_key, n_total) so sharded runs draw the same
+ * numbers as the single-GPU run.  per_chain_keys=1: rng_key is uint32[n,2], the already-split
+ * per-chain keys (what jax.vmap hands to bblackjax's kernel); chain_offset/n_total are ignored. */
+int mfm_mala_step(const mfm_target_t* t, const uint32_t* rng_key, int per_chain_keys, int n, int chain_offset, int n_total,
+                  float step_size, float* position, float* logdensity, float* logdensity_grad,
+                  float* acceptance_rate, uint8_t* is_accepted, float* proposed_position,
+                  float* proposed_weight, void* ws, size_t ws_bytes, mfm_stream_t stream);
+
+/* ---- CNF push / pull (exe_flow_matching.py:206-242, jax.experimental.ode.odeint) ------------ */
+size_t mfm_ode_workspace_bytes(const mfm_field_t* f, const mfm_target_t* t, const mfm_ode_opts_t* o, int n);
+/* direction +1: transform_and_logdet (u -> x, ldj);  -1: inverse_and_logdet (x -> u, ldj).
+ * hutch_keys uint32[n,2]: per-chain probe keys (ignored when !hutch).  stats (optional, device
+ * int32[4]): total accepted steps, total attempted steps, max attempted steps, field evals. */
+int mfm_ode_flow(const mfm_field_t* f, const mfm_target_t* t, const mfm_ode_opts_t* o, int direction, int n,
+                 const uint32_t* hutch_keys, const float* y0, float* y1, float* ldj, int* stats,
+                 void* ws, size_t ws_bytes, mfm_stream_t stream);
+/* single evaluation of (v, div v) at (x[n,d], t[n]) — test hook for VectorFieldNet parity */
+int mfm_field_eval(const mfm_field_t* f, const mfm_target_t* t, const mfm_ode_opts_t* o, int n,
+                   const float* x, const float* time, const float* z, float* v, float* div,
+                   void* ws, size_t ws_bytes, mfm_stream_t stream);
+
+/* ---- flow-MH step (exe_flow_matching.py:246-278) -------------------------------------------- */
+enum { MFM_FLOW_RW_MH = 0, MFM_FLOW_INDEP_MH = 1 };
+size_t mfm_flow_mh_workspace_bytes(const mfm_field_t* f, const mfm_target_t* t, const mfm_ode_opts_t* o, int n);
+int mfm_flow_mh_step(const mfm_field_t* f, const mfm_target_t* t, const mfm_ode_opts_t* o, int variant,
+                     const uint32_t* rng_key, int per_chain_keys, int n, int chain_offset, int n_total,
+                     float* position, float* logdensity, float* logdensity_grad,
+                     float* acceptance_rate, uint8_t* is_accepted, float* proposed_position,
+                     float* proposed_weight, int* stats, void* ws, size_t ws_bytes, mfm_stream_t stream);
+
+/* ---- flow-matching update (exe_flow_matching.py:151-179, 362-368, 129-137, 184) ------------- */
+size_t mfm_fm_workspace_bytes(const mfm_field_t* f, const mfm_target_t* t, int n);
+/* loss = sum |v(x_t, t) - (x - x0)|^2 and d loss / d params (flat, same layout as params).
+ * loss_out: device float[1].  grads are OVERWRITTEN (not accumulated). */
+int mfm_fm_loss_grad(const mfm_field_t* f, const mfm_target_t* t, const uint32_t* rng_key, int n,
+                     int chain_offset, int n_total, float sigma, const float* positions,
+                     float* loss_out, float* grads, void* ws, size_t ws_bytes, mfm_stream_t stream);
+/* same, from explicit (x_t, t, target) — test hook */
+int mfm_fm_loss_grad_from_batch(const mfm_field_t* f, const mfm_target_t* t, int n, const float* xt,
+                                const float* times, const float* target_v, float* loss_out, float* grads,
+                                void* ws, size_t ws_bytes, mfm_stream_t stream);
+
+/* optax.apply_if_finite(chain(adamw(lr_fn, b1, b2, eps, wd, mask=no-bias), clip(c)), max_err)
+ * opt_state: device int32[4] = {adam count, notfinite_count, total_notfinite, last_finite}.
+ * decay_mask: uint8[n_params] (1 = kernel, decayed; 0 = bias).  lr_base*(1-count/lr_total_steps). */
+int mfm_adamw_step(float* params, const float* grads, float* mu, float* nu, const uint8_t* decay_mask,
+                   long long n_params, int* opt_state, float lr_base, int lr_total_steps, float b1, float b2,
+                   float eps, float weight_decay, float clip, int max_consecutive_errors, mfm_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MFM_B200_H */

@@ -1,0 +1,121 @@
+// Shared device helpers for the MFM hot path (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#define MFM_OK 0
+#define MFM_ERR_ARG (-1)
+#define MFM_ERR_CUDA (-2)
+#define MFM_ERR_WORKSPACE (-3)
+#define MFM_ERR_UNSUPPORTED (-4)
+
+#define MFM_CUDA_CHECK(expr)                                  \
+    do {                                                      \
+        cudaError_t _e = (expr);                              \
+        if (_e != cudaSuccess) { mfm_set_last_error(_e, __FILE__, __LINE__); return MFM_ERR_CUDA; } \
+    } while (0)
+#define MFM_LAUNCH_CHECK() MFM_CUDA_CHECK(cudaGetLastError())
+
+void mfm_set_last_error(cudaError_t e, const char* file, int line);
+
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---------------------------------------------------------------------------------------------
+// threefry2x32-20 with JAX's key schedule (jax/_src/prng.py threefry2x32_p; Random123 KATs).
+// ---------------------------------------------------------------------------------------------
+struct u32x2 { uint32_t a, b; };
+
+__host__ __device__ __forceinline__ uint32_t mfm_rotl(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
+
+__host__ __device__ __forceinline__ u32x2 threefry2x32(uint32_t k0, uint32_t k1, uint32_t x0, uint32_t x1) {
+    const uint32_t k2 = k0 ^ k1 ^ 0x1BD11BDAu;
+    x0 += k0; x1 += k1;
+#define MFM_TF_R(r) { x0 += x1; x1 = mfm_rotl(x1, r); x1 ^= x0; }
+    MFM_TF_R(13) MFM_TF_R(15) MFM_TF_R(26) MFM_TF_R(6)
+    x0 += k1; x1 += k2 + 1u;
+    MFM_TF_R(17) MFM_TF_R(29) MFM_TF_R(16) MFM_TF_R(24)
+    x0 += k2; x1 += k0 + 2u;
+    MFM_TF_R(13) MFM_TF_R(15) MFM_TF_R(26) MFM_TF_R(6)
+    x0 += k0; x1 += k1 + 3u;
+    MFM_TF_R(17) MFM_TF_R(29) MFM_TF_R(16) MFM_TF_R(24)
+    x0 += k1; x1 += k2 + 4u;
+    MFM_TF_R(13) MFM_TF_R(15) MFM_TF_R(26) MFM_TF_R(6)
+    x0 += k2; x1 += k0 + 5u;
+#undef MFM_TF_R
+    u32x2 o; o.a = x0; o.b = x1; return o;
+}
+
+// Word `i` of jax's random_bits(key, 32, n) stream ("halves" layout, n padded to even):
+// counts split in halves (lo, hi); word i < half is o0 of block (i, i+half), else o1 of
+// block (i-half, i).  The padded count (odd n) is 0, not n.
+__host__ __device__ __forceinline__ uint32_t threefry_stream_word(uint32_t k0, uint32_t k1, uint32_t i, uint32_t n) {
+    const uint32_t half = (n + 1u) >> 1;
+    const bool first = i < half;
+    const uint32_t lo = first ? i : i - half;
+    uint32_t hi = lo + half;
+    if (hi >= n) hi = 0u;                      // odd-size pad element
+    const u32x2 o = threefry2x32(k0, k1, lo, hi);
+    return first ? o.a : o.b;
+}
+
+// key `j` of jax.random.split(key, num): words (2j, 2j+1) of the 2*num stream.
+__host__ __device__ __forceinline__ u32x2 threefry_split_key(uint32_t k0, uint32_t k1, uint32_t j, uint32_t num) {
+    u32x2 r;
+    r.a = threefry_stream_word(k0, k1, 2u * j, 2u * num);
+    r.b = threefry_stream_word(k0, k1, 2u * j + 1u, 2u * num);
+    return r;
+}
+
+// jax.random.uniform float32 in [0,1): mantissa fill then subtract one.
+__host__ __device__ __forceinline__ float bits_to_unit_float(uint32_t bits) {
+#ifdef __CUDA_ARCH__
+    return __uint_as_float((bits >> 9) | 0x3F800000u) - 1.0f;
+#else
+    union { uint32_t u; float f; } c; c.u = (bits >> 9) | 0x3F800000u; return c.f - 1.0f;
+#endif
+}
+
+// XLA ErfInv (f32): Giles' single-precision polynomial, w = -log1p(-x*x).
+__device__ __forceinline__ float xla_erfinv_f32(float x) {
+    float w = -log1pf(-x * x);
+    const bool lt = w < 5.0f;
+    w = lt ? w - 2.5f : sqrtf(w) - 3.0f;
+    float p = lt ? 2.81022636e-08f : -0.000200214257f;
+    p = (lt ? 3.43273939e-07f : 0.000100950558f) + p * w;
+    p = (lt ? -3.5233877e-06f : 0.00134934322f) + p * w;
+    p = (lt ? -4.39150654e-06f : -0.00367342844f) + p * w;
+    p = (lt ? 0.00021858087f : 0.00573950773f) + p * w;
+    p = (lt ? -0.00125372503f : -0.0076224613f) + p * w;
+    p = (lt ? -0.00417768164f : 0.00943887047f) + p * w;
+    p = (lt ? 0.246640727f : 1.00167406f) + p * w;
+    p = (lt ? 1.50140941f : 2.83297682f) + p * w;
+    const float r = p * x;
+    return fabsf(x) == 1.0f ? x * INFINITY : r;
+}
+
+// jax.random.normal float32 from 32 random bits:
+// u = max(lo, f*(1-lo)+lo) with lo = nextafter(-1,0); (1-lo) rounds to 2.0f in f32.
+__device__ __forceinline__ float bits_to_normal(uint32_t bits) {
+    const float lo = -0.99999994f;
+    float u = fmaxf(lo, bits_to_unit_float(bits) * 2.0f + lo);
+    return 1.41421354f * xla_erfinv_f32(u);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Block-wide sum; `red` is >= 32 floats of shared memory.  Result valid in all threads.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    float r = (lane < nw) ? red[lane] : 0.0f;
+    r = warp_sum(r);
+    return r;
+}

@@ -1,0 +1,44 @@
+// Internal (non-ABI) declarations shared between translation units.
+#pragma once
+#include "common.cuh"
+#include "../../include/mfm_b200.h"
+
+void mfm_set_last_error_msg(const char* msg);
+
+namespace mfm {
+
+// bump allocator over the caller's workspace (256-byte aligned slices)
+struct Workspace {
+    char* base; size_t size, off; bool ok;
+    Workspace(void* p, size_t n) : base((char*)p), size(n), off(0), ok(true) {}
+    template <class T> T* take(size_t count) {
+        size_t bytes = (count * sizeof(T) + 255) & ~(size_t)255;
+        if (base == nullptr || off + bytes > size) { ok = false; off += bytes; return nullptr; }
+        T* r = (T*)(base + off); off += bytes; return r;
+    }
+};
+inline size_t ws_slice(size_t count, size_t elt) { return (count * elt + 255) & ~(size_t)255; }
+
+int pines_n_tiles(int d);
+
+// grad_out[n,d] = beta*(c - a e^x) - (x-mu) K^-1 ; prior_partial[n, pines_n_tiles] = per-tile
+// sums of (x-mu).q  (logprior = -0.5*sum + log_norm).  n_rows_dev: optional active-row count.
+int pines_grad_gemm(const mfm_target_t& T, int n, const float* X, long long ldx, float beta,
+                    float* grad_out, long long ldg, float* prior_partial, const int* n_rows_dev,
+                    cudaStream_t st);
+// out[n,d] = Z K^-1 (Hessian-vector product of the prior is -Z K^-1)
+int pines_kinv_gemm(const mfm_target_t& T, int n, const float* Z, long long ldz, float* out, long long ldo,
+                    const int* n_rows_dev, cudaStream_t st);
+
+// value+grad of logprob_beta for any target; loglik_out optional; ws from target_ws_bytes
+size_t target_ws_bytes(const mfm_target_t& T, int n);
+int target_value_and_grad(const mfm_target_t& T, int n, const float* x, float* logp, float* grad,
+                          float* loglik_out, Workspace& ws, cudaStream_t st);
+
+// untempered grad logprob (+ optional Hessian-vector product with z / Hessian diagonal) for the
+// vector field; for pines hv excludes the constant -zK^-1 part when zkinv is supplied.
+// outputs: gc = clip(grad), hvc = 1[|grad|<clip] * (H z), hdc = 1[|grad|<clip] * diag(H)  (hvc/hdc optional)
+int target_field_terms(const mfm_target_t& T, int n, const float* x, const float* z, const float* zkinv, float clip,
+                       float* gc, float* hvc, float* hdc, const int* n_rows_dev, cudaStream_t st);
+
+}  // namespace mfm

@@ -1,0 +1,103 @@
+// jax.random-compatible generators (threefry2x32, legacy uint32[2] keys, x64 off).
+// Replaces the XLA threefry2x32 / erf_inv HLO behind every jax.random.* call on the hot path
+// (bblackjax/util.py:81, proposal.py:179, exe_flow_matching.py:142-166,212,265-275,303).
+#include "common.cuh"
+#include "../../include/mfm_b200.h"
+#include <stdio.h>
+#include <string.h>
+
+static thread_local char g_err[512] = "";
+void mfm_set_last_error(cudaError_t e, const char* file, int line) {
+    snprintf(g_err, sizeof(g_err), "CUDA error %d (%s) at %s:%d", (int)e, cudaGetErrorString(e), file, line);
+}
+void mfm_set_last_error_msg(const char* msg) { snprintf(g_err, sizeof(g_err), "%s", msg); }
+extern "C" const char* mfm_last_error(void) { return g_err; }
+extern "C" int mfm_version(void) { return 100; }
+
+namespace {
+
+__global__ void split_kernel(const uint32_t* __restrict__ keys, int n, int num, uint32_t* __restrict__ out) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= (long long)n * num) return;
+    const int c = (int)(i / num), j = (int)(i % num);
+    const u32x2 k = threefry_split_key(keys[2 * c], keys[2 * c + 1], (uint32_t)j, (uint32_t)num);
+    out[2 * i] = k.a; out[2 * i + 1] = k.b;
+}
+
+// MODE 0 bits, 1 uniform, 2 normal.  One thread per threefry block -> two stream words.
+template <int MODE>
+__global__ void stream_kernel(const uint32_t* __restrict__ keys, int nkeys, long long n, float minval, float maxval,
+                              void* __restrict__ out) {
+    const long long half = (n + 1) >> 1;
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= half * nkeys) return;
+    const int c = (int)(i / half);
+    const long long lo = i % half;
+    long long hi = lo + half;
+    const bool has_hi = hi < n;
+    const u32x2 o = threefry2x32(keys[2 * c], keys[2 * c + 1], (uint32_t)lo, has_hi ? (uint32_t)hi : 0u);
+    const long long base = (long long)c * n;
+    if (MODE == 0) {
+        uint32_t* p = (uint32_t*)out;
+        p[base + lo] = o.a; if (has_hi) p[base + hi] = o.b;
+    } else if (MODE == 1) {
+        float* p = (float*)out;
+        const float sc = maxval - minval;
+        p[base + lo] = fmaxf(minval, __fadd_rn(__fmul_rn(bits_to_unit_float(o.a), sc), minval));  // no FMA: mul then add as XLA
+        if (has_hi) p[base + hi] = fmaxf(minval, __fadd_rn(__fmul_rn(bits_to_unit_float(o.b), sc), minval));
+    } else {
+        float* p = (float*)out;
+        p[base + lo] = bits_to_normal(o.a);
+        if (has_hi) p[base + hi] = bits_to_normal(o.b);
+    }
+}
+
+template <int MODE>
+int launch_stream(const uint32_t* keys, int nkeys, long long n, float lo, float hi, void* out, cudaStream_t st) {
+    if (n <= 0 || nkeys <= 0) return MFM_OK;
+    if (n > 0xFFFFFFFFll) return MFM_ERR_UNSUPPORTED;
+    const long long work = ((n + 1) >> 1) * nkeys;
+    stream_kernel<MODE><<<ceil_div(work, 256), 256, 0, st>>>(keys, nkeys, n, lo, hi, out);
+    MFM_LAUNCH_CHECK();
+    return MFM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mfm_threefry_split(const uint32_t* key, int num, uint32_t* out, mfm_stream_t stream) {
+    return mfm_threefry_split_batched(key, 1, num, out, stream);
+}
+
+int mfm_threefry_split_batched(const uint32_t* keys, int n, int num, uint32_t* out, mfm_stream_t stream) {
+    if (n <= 0 || num <= 0) return MFM_OK;
+    split_kernel<<<ceil_div((long long)n * num, 256), 256, 0, stream>>>(keys, n, num, out);
+    MFM_LAUNCH_CHECK();
+    return MFM_OK;
+}
+
+int mfm_threefry_bits(const uint32_t* key, long long n, uint32_t* out, mfm_stream_t stream) {
+    return launch_stream<0>(key, 1, n, 0.f, 1.f, out, stream);
+}
+int mfm_threefry_uniform(const uint32_t* key, long long n, float minval, float maxval, float* out, mfm_stream_t stream) {
+    return launch_stream<1>(key, 1, n, minval, maxval, out, stream);
+}
+int mfm_threefry_normal(const uint32_t* key, long long n, float* out, mfm_stream_t stream) {
+    return launch_stream<2>(key, 1, n, 0.f, 1.f, out, stream);
+}
+int mfm_threefry_uniform_batched(const uint32_t* keys, int n, int d, float minval, float maxval, float* out, mfm_stream_t stream) {
+    return launch_stream<1>(keys, n, d, minval, maxval, out, stream);
+}
+int mfm_threefry_normal_batched(const uint32_t* keys, int n, int d, float* out, mfm_stream_t stream) {
+    return launch_stream<2>(keys, n, d, 0.f, 1.f, out, stream);
+}
+
+void mfm_host_threefry_split(const uint32_t key[2], int num, uint32_t* out) {
+    for (int j = 0; j < num; ++j) {
+        const u32x2 k = threefry_split_key(key[0], key[1], (uint32_t)j, (uint32_t)num);
+        out[2 * j] = k.a; out[2 * j + 1] = k.b;
+    }
+}
+
+}  // extern "C"

@@ -1,0 +1,223 @@
+// Target evaluation kernels: logprob_beta value+grad (mala.init), and the untempered
+// grad / Hessian terms the vector field needs.
+// Reference: distributions.py:58-67,131-160,299-307; cox_process_utils.py:98-115,142-165;
+// bblackjax/mcmc/mala.py:51-54; exe_flow_matching.py:301,316,351.
+#include "internal.h"
+#include "targets.cuh"
+#include "gemm_tf32x3.cuh"
+
+namespace mfm {
+
+// -------------------------------------------------------------------------------------------
+// small targets: one warp per chain
+// -------------------------------------------------------------------------------------------
+constexpr int EVAL_WARPS = 4;
+
+__global__ void small_value_grad_kernel(mfm_target_t T, int n, const float* __restrict__ x, float* __restrict__ logp,
+                                        float* __restrict__ grad, float* __restrict__ loglik_out) {
+    extern __shared__ float sm[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int c = blockIdx.x * EVAL_WARPS + w;
+    if (c >= n) return;
+    const int d = T.dim;
+    float* xs = sm + w * 2 * d;
+    float* gs = xs + d;
+    for (int i = lane; i < d; i += 32) xs[i] = x[(long long)c * d + i];
+    __syncwarp();
+    const float ll = small_target_loglik_grad(T, xs, gs, lane);
+    __syncwarp();
+    for (int i = lane; i < d; i += 32) grad[(long long)c * d + i] = T.beta * gs[i];
+    if (lane == 0) {
+        logp[c] = T.beta * ll;     // logprior == 0 for these targets
+        if (loglik_out) loglik_out[c] = ll;
+    }
+}
+
+// field terms for small targets: gc = clip(grad), hvc = inrange * (H z), hdc = inrange * diag(H)
+__global__ void small_field_terms_kernel(mfm_target_t T, int n, const int* __restrict__ n_rows_dev, float clip,
+                                         const float* __restrict__ x, const float* __restrict__ z,
+                                         float* __restrict__ gc, float* __restrict__ hvc, float* __restrict__ hdc) {
+    extern __shared__ float sm[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int c = blockIdx.x * EVAL_WARPS + w;
+    if (n_rows_dev) n = min(n, *n_rows_dev);
+    if (c >= n) return;
+    const int d = T.dim;
+    float* xs = sm + w * 5 * d;
+    float* gs = xs + d; float* zs = gs + d; float* hv = zs + d; float* hd = hv + d;
+    for (int i = lane; i < d; i += 32) {
+        xs[i] = x[(long long)c * d + i];
+        if (z) zs[i] = z[(long long)c * d + i];
+    }
+    __syncwarp();
+    small_target_loglik_grad(T, xs, gs, lane);
+    if (hvc || hdc) small_target_hess(T, xs, zs, hvc ? hv : nullptr, hdc ? hd : nullptr, lane);
+    __syncwarp();
+    for (int i = lane; i < d; i += 32) {
+        const float g = gs[i];
+        const bool in = !(clip > 0.0f) || (g > -clip && g < clip);
+        gc[(long long)c * d + i] = clip > 0.0f ? fminf(fmaxf(g, -clip), clip) : g;
+        if (hvc) hvc[(long long)c * d + i] = in ? hv[i] : 0.0f;
+        if (hdc) hdc[(long long)c * d + i] = in ? hd[i] : 0.0f;
+    }
+}
+
+// -------------------------------------------------------------------------------------------
+// pines: dense prior as a GEMM against K^-1 with fused epilogues
+// -------------------------------------------------------------------------------------------
+struct EpiPinesGrad {
+    static constexpr bool kRowSum = true;
+    const float* X; long long ldx;
+    const float* counts; const float* kinv_mu;
+    float mu, a, beta;
+    float* grad; long long ldg;
+    float* partial; int n_tiles;
+    __device__ __forceinline__ float operator()(int row, int col, float acc) const {
+        const float q = acc - kinv_mu[col];
+        const float xv = X[(long long)row * ldx + col];
+        grad[(long long)row * ldg + col] = beta * (counts[col] - a * expf(xv)) - q;
+        return (xv - mu) * q;
+    }
+    __device__ __forceinline__ void row_partial(int row, int tile, float s) const {
+        if (partial) partial[(long long)row * n_tiles + tile] = s;
+    }
+};
+
+struct EpiPinesField {
+    static constexpr bool kRowSum = false;
+    const float* X; long long ldx;
+    const float* counts; const float* kinv_mu; const float* kinv_diag;
+    const float* Z; const float* ZK;     // probe and Z K^-1 (hutch), or null
+    float a, clip;
+    float* gc; float* hvc; float* hdc; long long ld;
+    __device__ __forceinline__ float operator()(int row, int col, float acc) const {
+        const long long o = (long long)row * ld + col;
+        const float e = a * expf(X[(long long)row * ldx + col]);
+        const float g = counts[col] - e - (acc - kinv_mu[col]);
+        const bool in = !(clip > 0.0f) || (g > -clip && g < clip);
+        gc[o] = clip > 0.0f ? fminf(fmaxf(g, -clip), clip) : g;
+        if (hvc) hvc[o] = in ? (-e * Z[o] - ZK[o]) : 0.0f;
+        if (hdc) hdc[o] = in ? (-e - kinv_diag[col]) : 0.0f;
+        return 0.0f;
+    }
+    __device__ __forceinline__ void row_partial(int, int, float) const {}
+};
+
+int pines_n_tiles(int d) { return gemm_n_tiles(d); }
+
+int pines_grad_gemm(const mfm_target_t& T, int n, const float* X, long long ldx, float beta, float* grad_out,
+                    long long ldg, float* prior_partial, const int* n_rows_dev, cudaStream_t st) {
+    GemmShape p{n, T.dim, T.dim, X, ldx, T.kinv, (long long)T.dim, n_rows_dev};
+    EpiPinesGrad e{X, ldx, T.counts, T.kinv_mu, T.mu, T.poisson_a, beta, grad_out, ldg, prior_partial, gemm_n_tiles(T.dim)};
+    MFM_CUDA_CHECK((launch_gemm<true, true>(p, e, st)));
+    return MFM_OK;
+}
+
+int pines_kinv_gemm(const mfm_target_t& T, int n, const float* Z, long long ldz, float* out, long long ldo,
+                    const int* n_rows_dev, cudaStream_t st) {
+    GemmShape p{n, T.dim, T.dim, Z, ldz, T.kinv, (long long)T.dim, n_rows_dev};
+    EpiStd e{out, ldo, nullptr, nullptr, 0, nullptr, 0, 1.0f, 0};
+    MFM_CUDA_CHECK((launch_gemm<true, true>(p, e, st)));
+    return MFM_OK;
+}
+
+// loglik[n] = sum(x c - a e^x)   (cox_process_utils.py:98-115); one warp per chain
+__global__ void pines_loglik_kernel(mfm_target_t T, int n, const float* __restrict__ x, float* __restrict__ lik) {
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= n) return;
+    float s = 0.0f;
+    for (int i = lane; i < T.dim; i += 32) {
+        const float xv = x[(long long)c * T.dim + i];
+        s += xv * T.counts[i] - T.poisson_a * expf(xv);
+    }
+    s = warp_sum(s);
+    if (lane == 0) lik[c] = s;
+}
+
+__global__ void pines_finish_value_kernel(mfm_target_t T, int n, int n_tiles, const float* __restrict__ lik,
+                                          const float* __restrict__ partial, float* __restrict__ logp,
+                                          float* __restrict__ loglik_out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    float s = 0.0f;
+    for (int t = 0; t < n_tiles; ++t) s += partial[(long long)c * n_tiles + t];
+    logp[c] = T.beta * lik[c] + (-0.5f * s + T.log_norm);
+    if (loglik_out) loglik_out[c] = lik[c];
+}
+
+size_t target_ws_bytes(const mfm_target_t& T, int n) {
+    if (T.kind != MFM_TARGET_PINES) return 256;
+    return ws_slice((size_t)n * pines_n_tiles(T.dim), 4) + ws_slice(n, 4) + 256;
+}
+
+int target_value_and_grad(const mfm_target_t& T, int n, const float* x, float* logp, float* grad, float* loglik_out,
+                          Workspace& ws, cudaStream_t st) {
+    if (n <= 0) return MFM_OK;
+    if (T.kind == MFM_TARGET_PINES) {
+        const int nt = pines_n_tiles(T.dim);
+        float* partial = ws.take<float>((size_t)n * nt);
+        float* lik = ws.take<float>(n);
+        if (!ws.ok) { mfm_set_last_error_msg("workspace too small (target_value_and_grad)"); return MFM_ERR_WORKSPACE; }
+        pines_loglik_kernel<<<ceil_div(n, 8), 256, 0, st>>>(T, n, x, lik);
+        MFM_LAUNCH_CHECK();
+        int rc = pines_grad_gemm(T, n, x, T.dim, T.beta, grad, T.dim, partial, nullptr, st);
+        if (rc) return rc;
+        pines_finish_value_kernel<<<ceil_div(n, 256), 256, 0, st>>>(T, n, nt, lik, partial, logp, loglik_out);
+        MFM_LAUNCH_CHECK();
+        return MFM_OK;
+    }
+    if (T.kind == MFM_TARGET_GMM && T.dim != 2) { mfm_set_last_error_msg("GMM target requires dim == 2"); return MFM_ERR_ARG; }
+    const size_t smem = (size_t)EVAL_WARPS * 2 * T.dim * sizeof(float);
+    if (smem > 200 * 1024) { mfm_set_last_error_msg("dim too large for warp-per-chain target"); return MFM_ERR_UNSUPPORTED; }
+    if (smem > 48 * 1024) MFM_CUDA_CHECK(cudaFuncSetAttribute(small_value_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    small_value_grad_kernel<<<ceil_div(n, EVAL_WARPS), EVAL_WARPS * 32, smem, st>>>(T, n, x, logp, grad, loglik_out);
+    MFM_LAUNCH_CHECK();
+    return MFM_OK;
+}
+
+int target_field_terms(const mfm_target_t& T, int n, const float* x, const float* z, const float* zkinv, float clip,
+                       float* gc, float* hvc, float* hdc, const int* n_rows_dev, cudaStream_t st) {
+    if (n <= 0) return MFM_OK;
+    if (T.kind == MFM_TARGET_PINES) {
+        GemmShape p{n, T.dim, T.dim, x, (long long)T.dim, T.kinv, (long long)T.dim, n_rows_dev};
+        EpiPinesField e{x, (long long)T.dim, T.counts, T.kinv_mu, T.kinv_diag, z, zkinv, T.poisson_a, clip, gc, hvc, hdc, (long long)T.dim};
+        MFM_CUDA_CHECK((launch_gemm<true, true>(p, e, st)));
+        return MFM_OK;
+    }
+    const size_t smem = (size_t)EVAL_WARPS * 5 * T.dim * sizeof(float);
+    if (smem > 200 * 1024) { mfm_set_last_error_msg("dim too large for warp-per-chain target"); return MFM_ERR_UNSUPPORTED; }
+    if (smem > 48 * 1024) MFM_CUDA_CHECK(cudaFuncSetAttribute(small_field_terms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    small_field_terms_kernel<<<ceil_div(n, EVAL_WARPS), EVAL_WARPS * 32, smem, st>>>(T, n, n_rows_dev, clip, x, z, gc, hvc, hdc);
+    MFM_LAUNCH_CHECK();
+    return MFM_OK;
+}
+
+}  // namespace mfm
+
+extern "C" {
+
+int mfm_gemm_tf32x3(int M, int N, int K, const float* A, long long lda, int a_kmajor, const float* B, long long ldb,
+                    int b_nmajor, const float* bias, int relu, float* Cout, long long ldc, mfm_stream_t stream) {
+    using namespace mfm;
+    GemmShape p{M, N, K, A, lda, B, ldb, nullptr};
+    EpiStd e{Cout, ldc, bias, nullptr, 0, nullptr, 0, 1.0f, relu};
+    cudaError_t err;
+    if (a_kmajor && b_nmajor) err = launch_gemm<true, true>(p, e, stream);
+    else if (a_kmajor && !b_nmajor) err = launch_gemm<true, false>(p, e, stream);
+    else if (!a_kmajor && b_nmajor) err = launch_gemm<false, true>(p, e, stream);
+    else err = launch_gemm<false, false>(p, e, stream);
+    MFM_CUDA_CHECK(err);
+    return MFM_OK;
+}
+
+size_t mfm_target_workspace_bytes(const mfm_target_t* t, int n) { return mfm::target_ws_bytes(*t, n); }
+
+int mfm_logdensity_and_grad(const mfm_target_t* t, int n, const float* x, float* logp, float* grad, float* loglik_out,
+                            void* ws, size_t ws_bytes, mfm_stream_t stream) {
+    if (!t || !x || !logp || !grad || n < 0) { mfm_set_last_error_msg("null argument"); return MFM_ERR_ARG; }
+    mfm::Workspace w(ws, ws_bytes);
+    return mfm::target_value_and_grad(*t, n, x, logp, grad, loglik_out, w, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,151 @@
+"""Oracle: VectorFieldNet forward / JVP / exact divergence / FM loss + gradient.
+TEST INFRASTRUCTURE ONLY.
+
+Follows /root/reference/exe_flow_matching.py:56-90 (VectorFieldNet.__call__), :151-179
+(cond_flow_fn, flow_matching_loss) and :206-242 (divergence by jvp or trace(jacfwd)).
+flax.linen.Dense is restated as y = x @ kernel + bias with kernel [in, out]; modules are
+auto-named Dense_0..Dense_7 in construction order: 0,1 = time branch, 2,3 = x branch,
+4 = nn_t head, 5,6 = joint branch, 7 = nn_xt head.  Activation: relu only (all configs).
+relu'(0) = 0 as in jax.nn.relu's custom JVP.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import threefry as tf
+
+
+def init_params(rng: np.random.Generator, d, H, F=128, head_scale=0.0, dtype=np.float32):
+    """NOT the reference initialiser (flax lecun_normal through flax's RNG folding is a 'next'
+    row).  Gaussian fan-in init; head_scale=0 reproduces the reference's zero-init heads
+    (exe_flow_matching.py:81,86); head_scale>0 gives the 'trained-like' bench fixture."""
+    shapes = [(2 * F, H), (H, H), (d, H), (H, H), (H, d), (2 * H, H), (H, H), (H, d)]
+    p = {}
+    for i, (fi, fo) in enumerate(shapes):
+        scale = 1.0 / np.sqrt(fi)
+        if i in (4, 7):
+            scale *= head_scale
+        p[f"Dense_{i}"] = {
+            "kernel": (rng.standard_normal((fi, fo)) * scale).astype(dtype),
+            "bias": (rng.standard_normal(fo) * 0.01).astype(dtype),
+        }
+    return {"params": p}
+
+
+def _wb(params, i, dt):
+    q = params["params"][f"Dense_{i}"]
+    return q["kernel"].astype(dt), q["bias"].astype(dt)
+
+
+def fourier_features(t, omega, dt):
+    """exe_flow_matching.py:70-71.  t: [N] (per-chain time), omega: [F]."""
+    deg = dt.type(2 * np.pi) * omega.astype(dt)[None, :] * t.astype(dt)[:, None]
+    return np.concatenate([np.cos(deg), np.sin(deg)], axis=1)
+
+
+def forward(params, omega, x, t, grad_logprob, grad_clip=None, want_cache=False):
+    """v(x, t) batched: x [N,d], t [N] -> [N,d]."""
+    dt = x.dtype
+    ff = fourier_features(t, omega, dt)
+    W0, b0 = _wb(params, 0, dt); W1, b1 = _wb(params, 1, dt)
+    W2, b2 = _wb(params, 2, dt); W3, b3 = _wb(params, 3, dt)
+    W4, b4 = _wb(params, 4, dt); W5, b5 = _wb(params, 5, dt)
+    W6, b6 = _wb(params, 6, dt); W7, b7 = _wb(params, 7, dt)
+    h0 = np.maximum(ff @ W0 + b0, 0)
+    st = np.maximum(h0 @ W1 + b1, 0)
+    h2 = np.maximum(x @ W2 + b2, 0)
+    sx = np.maximum(h2 @ W3 + b3, 0)
+    gt = st @ W4 + b4
+    cat = np.concatenate([sx, st], axis=1)
+    h5 = np.maximum(cat @ W5 + b5, 0)
+    h6 = np.maximum(h5 @ W6 + b6, 0)
+    y = h6 @ W7 + b7
+    g = grad_logprob(x)
+    gc = np.clip(g, -grad_clip, grad_clip).astype(dt) if grad_clip else g
+    v = y + gt * gc
+    if want_cache:
+        return v, dict(ff=ff, h0=h0, st=st, h2=h2, sx=sx, gt=gt, cat=cat, h5=h5, h6=h6, g=g, gc=gc)
+    return v
+
+
+def jvp_x(params, cache, z, hvp, grad_clip=None):
+    """d/dx v(x,t) . z for a batch of tangents z [N,d] given the forward cache."""
+    dt = z.dtype
+    H = cache["sx"].shape[1]
+    W2, _ = _wb(params, 2, dt); W3, _ = _wb(params, 3, dt)
+    W5, _ = _wb(params, 5, dt); W6, _ = _wb(params, 6, dt); W7, _ = _wb(params, 7, dt)
+    d2 = (z @ W2) * (cache["h2"] > 0)
+    d3 = (d2 @ W3) * (cache["sx"] > 0)
+    d5 = (d3 @ W5[:H]) * (cache["h5"] > 0)
+    d6 = (d5 @ W6) * (cache["h6"] > 0)
+    dy = d6 @ W7
+    dg = hvp(z)
+    if grad_clip:
+        dg = dg * ((cache["g"] > -grad_clip) & (cache["g"] < grad_clip))
+    return dy + cache["gt"] * dg
+
+
+def field_and_div(params, omega, x, t, target, hutch_z=None, grad_clip=None):
+    """(v, div v) as the augmented field needs them (exe_flow_matching.py:208-218).
+    hutch_z [N,d]: Hutchinson probe (div = z.(Jz)); None: exact trace by d tangents."""
+    v, c = forward(params, omega, x, t, target.grad, grad_clip, want_cache=True)
+    if hutch_z is not None:
+        jz = jvp_x(params, c, hutch_z, lambda zz: target.hvp(x, zz), grad_clip)
+        return v, (hutch_z * jz).sum(1)
+    N, d = x.shape
+    div = np.zeros(N, x.dtype)
+    hd = target.hdiag(x)
+    if grad_clip:
+        hd = hd * ((c["g"] > -grad_clip) & (c["g"] < grad_clip))
+    for j in range(d):
+        e = np.zeros_like(x); e[:, j] = 1
+        jz = jvp_x(params, c, e, lambda zz: np.zeros_like(zz), None)
+        div += jz[:, j]
+    return v, div + (c["gt"] * hd).sum(1)
+
+
+def fm_batch(key, samples, ref_sampler, sigma):
+    """cond_flow_fn (exe_flow_matching.py:151-169), cond_flow=True, ot_cond_flow=False."""
+    N, d = samples.shape
+    dt = samples.dtype
+    key_time, key_ref, key_gauss, _ = tf.split(key, 4)
+    times = tf.uniform(key_time, (N, 1), dt)
+    ref = ref_sampler(tf.split(key_ref, N), dt)
+    eps = tf.normal(key_gauss, (N, d), dt)
+    xt = dt.type(sigma) * eps + times * samples + (dt.type(1) - times) * ref
+    target = samples - ref
+    return times[:, 0], xt, target
+
+
+def fm_loss_and_grad(params, omega, xt, times, target_v, grad_logprob, grad_clip=None):
+    """flow_matching_loss (exe_flow_matching.py:171-179) and its gradient w.r.t. params
+    (what jax.value_and_grad(loss_fn, argnums=2) returns, :364-365)."""
+    dt = xt.dtype
+    v, c = forward(params, omega, xt, times, grad_logprob, grad_clip, want_cache=True)
+    diff = v - target_v
+    loss = (diff * diff).sum()
+    H = c["sx"].shape[1]
+    W = [_wb(params, i, dt)[0] for i in range(8)]
+    delta = dt.type(2) * diff
+    G = {}
+
+    def put(i, a, dz):
+        G[f"Dense_{i}"] = {"kernel": a.T @ dz, "bias": dz.sum(0)}
+
+    put(7, c["h6"], delta)
+    d6 = (delta @ W[7].T) * (c["h6"] > 0)
+    put(6, c["h5"], d6)
+    d5 = (d6 @ W[6].T) * (c["h5"] > 0)
+    put(5, c["cat"], d5)
+    dcat = d5 @ W[5].T
+    dgt = delta * c["gc"]
+    put(4, c["st"], dgt)
+    dsx = dcat[:, :H] * (c["sx"] > 0)
+    dst = (dcat[:, H:] + dgt @ W[4].T) * (c["st"] > 0)
+    put(3, c["h2"], dsx)
+    d2 = (dsx @ W[3].T) * (c["h2"] > 0)
+    put(2, xt, d2)
+    put(1, c["h0"], dst)
+    d0 = (dst @ W[1].T) * (c["h0"] > 0)
+    put(0, c["ff"], d0)
+    return loss, {"params": G}
