@@ -158,7 +158,7 @@ int mfm_fm_loss_grad_from_batch(const mfm_field_t* f, const mfm_target_t* t, int
                                 void* ws, size_t ws_bytes, mfm_stream_t stream);
 
 /* optax.apply_if_finite(chain(adamw(lr_fn, b1, b2, eps, wd, mask=no-bias), clip(c)), max_err)
- * opt_state: device int32[4] = {adam count, notfinite_count, total_notfinite, last_finite}.
+ * opt_state: device int32[8] = {adam count, notfinite_count, total_notfinite, last_finite, scratch x4}.
  * decay_mask: uint8[n_params] (1 = kernel, decayed; 0 = bias).  lr_base*(1-count/lr_total_steps). */
 int mfm_adamw_step(float* params, const float* grads, float* mu, float* nu, const uint8_t* decay_mask,
                    long long n_params, int* opt_state, float lr_base, int lr_total_steps, float b1, float b2,

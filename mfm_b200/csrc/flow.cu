@@ -1,0 +1,673 @@
+// CNF push/pull with adaptive Dormand-Prince 5(4) and the flow-MH transition.
+//
+// Replaces, for a whole batch of chains at once:
+//   VectorFieldNet.__call__                      exe_flow_matching.py:56-90
+//   divergence by jvp (Hutchinson) / trace(jacfwd)  :211-217, :231-237
+//   transform_and_logdet / inverse_and_logdet    :206-242
+//   jax.experimental.ode.odeint (jax 0.4.26)     :345-349   [restated in oracle/ode.py]
+//   random_walk / indep metropolis_hastings      :246-278
+//
+// Layout: every per-chain quantity is SoA [n, d] / [n]; the augmented ODE state ravel((x, ldj)) is
+// kept as x[n,d] + ldj[n].  All chains advance in lock-step *iterations*; each chain carries its
+// own (t, dt, segment, step count) and is masked once finished — exactly the semantics of the
+// batched while_loop that jax.vmap produces.  Dense layers run on tensor cores (3xTF32).
+#include "internal.h"
+#include "gemm_tf32x3.cuh"
+
+namespace mfm {
+
+// ---------------------------------------------------------------------------------------------
+// Dormand-Prince coefficients (float32 roundings of the float64 literals, as jnp.array(..., f32))
+// ---------------------------------------------------------------------------------------------
+__constant__ float c_alpha[6] = {(float)(1.0 / 5), (float)(3.0 / 10), (float)(4.0 / 5), (float)(8.0 / 9), 1.0f, 1.0f};
+__constant__ float c_beta[6][6] = {
+    {(float)(1.0 / 5), 0, 0, 0, 0, 0},
+    {(float)(3.0 / 40), (float)(9.0 / 40), 0, 0, 0, 0},
+    {(float)(44.0 / 45), (float)(-56.0 / 15), (float)(32.0 / 9), 0, 0, 0},
+    {(float)(19372.0 / 6561), (float)(-25360.0 / 2187), (float)(64448.0 / 6561), (float)(-212.0 / 729), 0, 0},
+    {(float)(9017.0 / 3168), (float)(-355.0 / 33), (float)(46732.0 / 5247), (float)(49.0 / 176), (float)(-5103.0 / 18656), 0},
+    {(float)(35.0 / 384), 0, (float)(500.0 / 1113), (float)(125.0 / 192), (float)(-2187.0 / 6784), (float)(11.0 / 84)}};
+__constant__ float c_sol[7] = {(float)(35.0 / 384), 0, (float)(500.0 / 1113), (float)(125.0 / 192),
+                               (float)(-2187.0 / 6784), (float)(11.0 / 84), 0};
+__constant__ float c_err[7] = {(float)(35.0 / 384 - 1951.0 / 21600), 0, (float)(500.0 / 1113 - 22642.0 / 50085),
+                               (float)(125.0 / 192 - 451.0 / 720), (float)(-2187.0 / 6784 - -12231.0 / 42400),
+                               (float)(11.0 / 84 - 649.0 / 6300), (float)(-1.0 / 60.0)};
+__constant__ float c_mid[7] = {(float)(6025192743.0 / 30085553152.0 / 2), 0, (float)(51252292925.0 / 65400821598.0 / 2),
+                               (float)(-2691868925.0 / 45128329728.0 / 2), (float)(187940372067.0 / 1594534317056.0 / 2),
+                               (float)(-1776094331.0 / 19743644256.0 / 2), (float)(11237099.0 / 235043384.0 / 2)};
+
+// ---------------------------------------------------------------------------------------------
+// GEMM epilogues specific to the field
+// ---------------------------------------------------------------------------------------------
+// v = sgn * (acc + bias + gt * gc)          (exe_flow_matching.py:86-90)
+struct EpiFieldV {
+    static constexpr bool kRowSum = false;
+    float* V; long long ldv; const float* bias; const float* gt; const float* gc; long long ld; float sgn;
+    __device__ __forceinline__ float operator()(int row, int col, float acc) const {
+        const long long o = (long long)row * ld + col;
+        V[(long long)row * ldv + col] = sgn * (acc + bias[col] + gt[o] * gc[o]);
+        return 0.0f;
+    }
+    __device__ __forceinline__ void row_partial(int, int, float) const {}
+    __device__ __forceinline__ void at_z(int) {}
+};
+// Hutchinson: sum_col z * (acc + gt * hvc)    (:212-214)
+struct EpiFieldDiv {
+    static constexpr bool kRowSum = true;
+    const float* z; const float* gt; const float* hvc; long long ld; float* partial; int n_tiles;
+    __device__ __forceinline__ float operator()(int row, int col, float acc) const {
+        const long long o = (long long)row * ld + col;
+        return z[o] * (acc + gt[o] * hvc[o]);
+    }
+    __device__ __forceinline__ void row_partial(int row, int tile, float s) const { partial[(long long)row * n_tiles + tile] = s; }
+    __device__ __forceinline__ void at_z(int) {}
+};
+
+int dense(int n, int in, int out, const float* A, long long lda, const float* W, const float* bias, int relu,
+                 float* C, long long ldc, const float* mask, long long ldm, int mask_div, cudaStream_t st) {
+    GemmShape p{n, out, in, A, lda, W, (long long)out, nullptr};
+    EpiStd e{C, ldc, bias, mask, ldm, nullptr, 0, 1.0f, relu, mask_div};
+    MFM_CUDA_CHECK((launch_gemm<true, true>(p, e, st)));
+    return MFM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// elementwise helpers
+// ---------------------------------------------------------------------------------------------
+__global__ void fourier_kernel(int n, int F, const float* __restrict__ omega, const float* __restrict__ t,
+                               float* __restrict__ ff) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= (long long)n * F) return;
+    const int c = (int)(i / F), j = (int)(i % F);
+    // degt = 2*pi*fourier_random*t  (left to right, :70)
+    const float deg = __fmul_rn(__fmul_rn(6.28318530717958647692f, omega[j]), t[c]);
+    float sv, cv; sincosf(deg, &sv, &cv);
+    ff[(long long)c * 2 * F + j] = cv;
+    ff[(long long)c * 2 * F + F + j] = sv;
+}
+
+// out[i,:] = a[i,:] * (gate[i,:] > 0)
+__global__ void gate_kernel(long long total, int H, const float* __restrict__ a, const float* __restrict__ gate,
+                            long long ldg, float* __restrict__ out) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const long long r = i / H; const int c = (int)(i % H);
+    out[i] = gate[r * ldg + c] > 0.0f ? a[i] : 0.0f;
+}
+
+// exact path: tan[(i,j),:] = W2[j,:] * (h2[i,:] > 0)
+__global__ void basis_tangent_kernel(int n, int d, int H, const float* __restrict__ W2, const float* __restrict__ h2,
+                                     float* __restrict__ tan) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= (long long)n * d * H) return;
+    const int k = (int)(i % H); const long long r = i / H; const int j = (int)(r % d); const long long c = r / d;
+    tan[i] = h2[c * H + k] > 0.0f ? W2[(long long)j * H + k] : 0.0f;
+}
+
+// exact path: div_i = sum_j tan6[(i,j),:].W7[:,j] + sum_j gt[i,j]*hdc[i,j];  out = coef * div
+__global__ void exact_trace_kernel(int n, int d, int H, const float* __restrict__ tan6, const float* __restrict__ W7,
+                                   const float* __restrict__ gt, const float* __restrict__ hdc, float coef,
+                                   float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= n) return;
+    float s = 0.0f;
+    for (int j = 0; j < d; ++j) {
+        const float* row = tan6 + ((long long)c * d + j) * H;
+        for (int k = lane; k < H; k += 32) s += row[k] * W7[(long long)k * d + j];
+    }
+    for (int j = lane; j < d; j += 32) s += gt[(long long)c * d + j] * hdc[(long long)c * d + j];
+    s = warp_sum(s);
+    if (lane == 0) out[c] = coef * s;
+}
+
+__global__ void div_finish_kernel(int n, int n_tiles, const float* __restrict__ partial, float coef, float* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    float s = 0.0f;
+    for (int t = 0; t < n_tiles; ++t) s += partial[(long long)c * n_tiles + t];
+    out[c] = coef * s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// field evaluation
+// ---------------------------------------------------------------------------------------------
+size_t field_bufs_bytes(const mfm_field_t& F, const mfm_target_t& T, int n, bool hutch) {
+    const size_t H = F.hidden, d = F.dim, N = n;
+    size_t b = ws_slice(N * 2 * F.fourier_dim, 4) + ws_slice(N * H, 4) * 6 + ws_slice(N * 2 * H, 4) + ws_slice(N * d, 4) * 3;
+    if (hutch) b += ws_slice(N * H, 4) + ws_slice(N * d, 4) + ws_slice(N * gemm_n_tiles((int)d), 4);
+    else b += 2 * ws_slice(N * d * H, 4);
+    return b;
+}
+
+bool field_bufs_take(FieldBufs& B, Workspace& w, const mfm_field_t& F, int n, bool hutch) {
+    const size_t H = F.hidden, d = F.dim, N = n;
+    B.ff = w.take<float>(N * 2 * F.fourier_dim);
+    B.h0 = w.take<float>(N * H); B.h2 = w.take<float>(N * H); B.h5 = w.take<float>(N * H); B.h6 = w.take<float>(N * H);
+    B.ta = w.take<float>(N * H); B.tb = w.take<float>(N * H);
+    B.cat = w.take<float>(N * 2 * H);
+    B.gt = w.take<float>(N * d); B.gc = w.take<float>(N * d); B.hx = w.take<float>(N * d);
+    B.zw2 = B.zkinv = B.divpart = B.tan_a = B.tan_b = nullptr;
+    if (hutch) { B.zw2 = w.take<float>(N * H); B.zkinv = w.take<float>(N * d); B.divpart = w.take<float>(N * gemm_n_tiles((int)d)); }
+    else { B.tan_a = w.take<float>(N * d * H); B.tan_b = w.take<float>(N * d * H); }
+    return w.ok;
+}
+
+#define W_(i) (F.params + F.w_off[i])
+#define B_(i) (F.params + F.b_off[i])
+
+// per-solve constants of the Hutchinson estimator: z W2 and (pines) z K^-1
+static int field_prepare_probe(const mfm_field_t& F, const mfm_target_t& T, int n, const float* z, FieldBufs& B, cudaStream_t st) {
+    const int d = F.dim, H = F.hidden;
+    int rc = dense(n, d, H, z, d, W_(2), nullptr, 0, B.zw2, H, nullptr, 0, 1, st);
+    if (rc) return rc;
+    if (T.kind == MFM_TARGET_PINES) return pines_kinv_gemm(T, n, z, d, B.zkinv, d, nullptr, st);
+    return MFM_OK;
+}
+
+// out_v[n,d] = sgn * v(x, tfield);  out_l[n] = -sgn * div v   (z != null: Hutchinson; else exact)
+int field_eval(const mfm_field_t& F, const mfm_target_t& T, int n, const float* x, const float* tfield,
+                      const float* z, float sgn, float* out_v, float* out_l, FieldBufs& B, cudaStream_t st) {
+    const int d = F.dim, H = F.hidden, Fd = F.fourier_dim;
+    int rc;
+    fourier_kernel<<<ceil_div((long long)n * Fd, 256), 256, 0, st>>>(n, Fd, F.omega, tfield, B.ff);
+    MFM_LAUNCH_CHECK();
+    if ((rc = dense(n, 2 * Fd, H, B.ff, 2 * Fd, W_(0), B_(0), 1, B.h0, H, nullptr, 0, 1, st))) return rc;
+    if ((rc = dense(n, H, H, B.h0, H, W_(1), B_(1), 1, B.cat + H, 2 * H, nullptr, 0, 1, st))) return rc;       // s_t
+    if ((rc = dense(n, d, H, x, d, W_(2), B_(2), 1, B.h2, H, nullptr, 0, 1, st))) return rc;
+    if ((rc = dense(n, H, H, B.h2, H, W_(3), B_(3), 1, B.cat, 2 * H, nullptr, 0, 1, st))) return rc;           // s_x
+    if ((rc = dense(n, H, d, B.cat + H, 2 * H, W_(4), B_(4), 0, B.gt, d, nullptr, 0, 1, st))) return rc;       // nn_t
+    if ((rc = dense(n, 2 * H, H, B.cat, 2 * H, W_(5), B_(5), 1, B.h5, H, nullptr, 0, 1, st))) return rc;
+    if ((rc = dense(n, H, H, B.h5, H, W_(6), B_(6), 1, B.h6, H, nullptr, 0, 1, st))) return rc;
+    // untempered grad logprob (clipped) and the Hessian term of the divergence
+    mfm_target_t T1 = T; T1.beta = 1.0f;
+    const bool want_div = out_l != nullptr;
+    if ((rc = target_field_terms(T1, n, x, z, B.zkinv, F.grad_clip, B.gc, (want_div && z) ? B.hx : nullptr,
+                                 (want_div && !z) ? B.hx : nullptr, nullptr, st))) return rc;
+    {
+        GemmShape p{n, d, H, B.h6, (long long)H, W_(7), (long long)d, nullptr};
+        EpiFieldV e{out_v, (long long)d, B_(7), B.gt, B.gc, (long long)d, sgn};
+        MFM_CUDA_CHECK((launch_gemm<true, true>(p, e, st)));
+    }
+    if (!want_div) return MFM_OK;
+    if (z) {
+        gate_kernel<<<ceil_div((long long)n * H, 256), 256, 0, st>>>((long long)n * H, H, B.zw2, B.h2, H, B.ta);
+        MFM_LAUNCH_CHECK();
+        if ((rc = dense(n, H, H, B.ta, H, W_(3), nullptr, 0, B.tb, H, B.cat, 2 * H, 1, st))) return rc;
+        if ((rc = dense(n, H, H, B.tb, H, W_(5), nullptr, 0, B.ta, H, B.h5, H, 1, st))) return rc;   // first H rows of W5
+        if ((rc = dense(n, H, H, B.ta, H, W_(6), nullptr, 0, B.tb, H, B.h6, H, 1, st))) return rc;
+        GemmShape p{n, d, H, B.tb, (long long)H, W_(7), (long long)d, nullptr};
+        const int nt = gemm_n_tiles(d);
+        EpiFieldDiv e{z, B.gt, B.hx, (long long)d, B.divpart, nt};
+        MFM_CUDA_CHECK((launch_gemm<true, true>(p, e, st)));
+        div_finish_kernel<<<ceil_div(n, 256), 256, 0, st>>>(n, nt, B.divpart, -sgn, out_l);
+        MFM_LAUNCH_CHECK();
+    } else {
+        const long long rows = (long long)n * d;
+        if (rows > 0x7FFFFFFFll) { mfm_set_last_error_msg("exact divergence: n*d too large"); return MFM_ERR_UNSUPPORTED; }
+        basis_tangent_kernel<<<ceil_div(rows * H, 256), 256, 0, st>>>(n, d, H, W_(2), B.h2, B.tan_a);
+        MFM_LAUNCH_CHECK();
+        if ((rc = dense((int)rows, H, H, B.tan_a, H, W_(3), nullptr, 0, B.tan_b, H, B.cat, 2 * H, d, st))) return rc;
+        if ((rc = dense((int)rows, H, H, B.tan_b, H, W_(5), nullptr, 0, B.tan_a, H, B.h5, H, d, st))) return rc;
+        if ((rc = dense((int)rows, H, H, B.tan_a, H, W_(6), nullptr, 0, B.tan_b, H, B.h6, H, d, st))) return rc;
+        exact_trace_kernel<<<ceil_div(n, 8), 256, 0, st>>>(n, d, H, B.tan_b, W_(7), B.gt, B.hx, -sgn, out_l);
+        MFM_LAUNCH_CHECK();
+    }
+    return MFM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// adaptive Dopri5 (jax.experimental.ode semantics)
+// ---------------------------------------------------------------------------------------------
+struct OdeState {
+    float *yx, *yl;            // current state
+    float* kx[7]; float* kl[7];
+    float *xi, *tf;            // stage input / field time
+    float *t, *dt, *d1;        // per-chain time, step, ||f0/scale||
+    int *seg, *icount, *ntry;  // segment index, steps in segment, attempts
+    float *outx, *outl;        // interpolated output at the final time
+    int* counters;             // [0] chains still active, [1] accepted, [2] attempted, [3] max attempts
+};
+
+struct OdeTimes { int n_seg; float target[16]; };
+
+__global__ void ode_init_kernel(int n, int d, const float* __restrict__ y0, OdeState S, float t0, float sgn) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < (long long)n * d) { const float v = y0[i]; S.yx[i] = v; S.outx[i] = v; S.xi[i] = v; }
+    if (i < n) {
+        S.yl[i] = 0.0f; S.outl[i] = 0.0f; S.t[i] = t0; S.seg[i] = 0; S.icount[i] = 0; S.ntry[i] = 0;
+        S.tf[i] = sgn > 0 ? t0 : 1.0f - t0;
+    }
+    if (i < 4) S.counters[i] = 0;
+}
+
+// initial_step_size part 1: h0 and the trial point y0 + h0 f0
+__global__ void ode_h0_kernel(int n, int d, OdeState S, float rtol, float atol, float sgn) {
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= n) return;
+    const float* y = S.yx + (long long)c * d; const float* f = S.kx[0] + (long long)c * d;
+    float s0 = 0.0f, s1 = 0.0f;
+    for (int i = lane; i < d; i += 32) {
+        const float sc = atol + fabsf(y[i]) * rtol;
+        const float a = y[i] / sc, b = f[i] / sc;
+        s0 += a * a; s1 += b * b;
+    }
+    if (lane == 0) { const float sc = atol + fabsf(S.yl[c]) * rtol; const float a = S.yl[c] / sc, b = S.kl[0][c] / sc; s0 += a * a; s1 += b * b; }
+    const float d0 = sqrtf(warp_sum(s0)), d1 = sqrtf(warp_sum(s1));
+    const float h0 = (d0 < 1e-5f || d1 < 1e-5f) ? 1e-6f : 0.01f * d0 / d1;
+    float* xi = S.xi + (long long)c * d;
+    for (int i = lane; i < d; i += 32) xi[i] = y[i] + h0 * f[i];
+    if (lane == 0) {
+        S.dt[c] = h0; S.d1[c] = d1;
+        const float tt = S.t[c] + h0;
+        S.tf[c] = sgn > 0 ? tt : 1.0f - tt;
+    }
+}
+
+// initial_step_size part 2: d2, h1, dt = min(100 h0, h1)
+__global__ void ode_h1_kernel(int n, int d, OdeState S, float rtol, float atol) {
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= n) return;
+    const float* y = S.yx + (long long)c * d;
+    const float* f0 = S.kx[0] + (long long)c * d; const float* f1 = S.kx[1] + (long long)c * d;
+    float s2 = 0.0f;
+    for (int i = lane; i < d; i += 32) {
+        const float sc = atol + fabsf(y[i]) * rtol;
+        const float a = (f1[i] - f0[i]) / sc; s2 += a * a;
+    }
+    if (lane == 0) { const float sc = atol + fabsf(S.yl[c]) * rtol; const float a = (S.kl[1][c] - S.kl[0][c]) / sc; s2 += a * a; }
+    const float h0 = S.dt[c], d1 = S.d1[c];
+    const float d2 = sqrtf(warp_sum(s2)) / h0;
+    float h1;
+    if (d1 <= 1e-15f && d2 <= 1e-15f) h1 = fmaxf(1e-6f, h0 * 1e-3f);
+    else {
+        const float m = (isnan(d1) || isnan(d2)) ? NAN : fmaxf(d1, d2);
+        h1 = powf(0.01f / m, 0.2f);
+    }
+    float dt = (isnan(h1)) ? NAN : fminf(100.0f * h0, h1);
+    if (dt < 0.0f) dt = 0.0f;       // jnp.clip(., 0, hmax=inf)
+    if (lane == 0) S.dt[c] = dt;
+}
+
+// stage s in 1..6: xi = y + dt * sum_j beta[s-1][j] k_j ; field time t + alpha dt
+__global__ void ode_stage_kernel(int n, int d, int s, OdeState S, int n_seg, float sgn) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= (long long)n * d) return;
+    const int c = (int)(i / d);
+    if (S.seg[c] >= n_seg) return;            // finished chain: leave its stage input untouched
+    const float h = S.dt[c];
+    float acc = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) if (j < s) acc += c_beta[s - 1][j] * S.kx[j][i];
+    S.xi[i] = S.yx[i] + h * acc;
+    if (i % d == 0) {
+        const float ti = S.t[c] + h * c_alpha[s - 1];
+        S.tf[c] = sgn > 0 ? ti : 1.0f - ti;
+    }
+}
+
+__device__ __forceinline__ float fit_eval(float y0, float y1, float ymid, float dy0, float dy1, float h, float rel) {
+    // fit_4th_order_polynomial + polyval (jax/experimental/ode.py)
+    const float a = -2.f * h * dy0 + 2.f * h * dy1 - 8.f * y0 - 8.f * y1 + 16.f * ymid;
+    const float b = 5.f * h * dy0 - 3.f * h * dy1 + 18.f * y0 + 14.f * y1 - 32.f * ymid;
+    const float c = -4.f * h * dy0 + h * dy1 - 11.f * y0 - 5.f * y1 + 16.f * ymid;
+    const float dd = h * dy0;
+    return (((a * rel + b) * rel + c) * rel + dd) * rel + y0;
+}
+
+// error ratio, accept/reject, controller, FSAL, dense output.  One warp per chain.
+__global__ void ode_finish_kernel(int n, int d, OdeState S, OdeTimes TS, float rtol, float atol, int mxstep) {
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= n) return;
+    int seg = S.seg[c];
+    if (seg >= TS.n_seg) return;
+    const float tt = S.t[c], h = S.dt[c];
+    const long long o = (long long)c * d;
+    float sum = 0.0f;
+    for (int i = lane; i < d; i += 32) {
+        float ss = 0.0f, se = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 7; ++j) { const float k = S.kx[j][o + i]; ss += c_sol[j] * k; se += c_err[j] * k; }
+        const float y = S.yx[o + i];
+        const float y1 = h * ss + y;
+        const float r = (h * se) / (atol + rtol * fmaxf(fabsf(y), fabsf(y1)));
+        sum += r * r;
+    }
+    float ssl = 0.0f, sel = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 7; ++j) { const float k = S.kl[j][c]; ssl += c_sol[j] * k; sel += c_err[j] * k; }
+    const float yl = S.yl[c];
+    const float yl1 = h * ssl + yl;
+    if (lane == 0) { const float r = (h * sel) / (atol + rtol * fmaxf(fabsf(yl), fabsf(yl1))); sum += r * r; }
+    sum = warp_sum(sum);
+    const float ratio = sqrtf(sum / (float)(d + 1));
+    const bool accept = ratio <= 1.0f;                       // NaN -> reject
+    // optimal_step_size
+    float new_dt;
+    if (isnan(ratio)) new_dt = NAN;
+    else if (ratio == 0.0f) new_dt = h * 10.0f;
+    else {
+        const float dfac = ratio < 1.0f ? 1.0f : 0.2f;
+        const float fac = fminf(10.0f, fmaxf(powf(ratio, -0.2f) * 0.9f, dfac));
+        new_dt = h * fac;
+    }
+    if (new_dt < 0.0f) new_dt = 0.0f;
+    float t_new = tt;
+    if (accept) {
+        t_new = tt + h;
+        const float t_final = TS.target[TS.n_seg - 1];
+        const float rel = (t_final - tt) / (t_new - tt);
+        for (int i = lane; i < d; i += 32) {
+            float ss = 0.0f, sm = 0.0f;
+            float k0 = 0.f, k6 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 7; ++j) {
+                const float k = S.kx[j][o + i]; ss += c_sol[j] * k; sm += c_mid[j] * k;
+                if (j == 0) k0 = k; if (j == 6) k6 = k;
+            }
+            const float y = S.yx[o + i];
+            const float y1 = h * ss + y, ymid = y + h * sm;
+            S.outx[o + i] = fit_eval(y, y1, ymid, k0, k6, h, rel);
+            S.yx[o + i] = y1;
+            S.kx[0][o + i] = k6;                               // FSAL
+        }
+        if (lane == 0) {
+            float sm = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 7; ++j) sm += c_mid[j] * S.kl[j][c];
+            S.outl[c] = fit_eval(yl, yl1, yl + h * sm, S.kl[0][c], S.kl[6][c], h, rel);
+            S.yl[c] = yl1; S.kl[0][c] = S.kl[6][c]; S.t[c] = t_new;
+        }
+    }
+    if (lane == 0) {
+        int ic = S.icount[c] + 1;
+        const int ntry = S.ntry[c] + 1;
+        S.ntry[c] = ntry;
+        S.dt[c] = new_dt;
+        // advance over finished output segments: while !(t < target && i < mxstep && dt > 0)
+        while (seg < TS.n_seg && !(t_new < TS.target[seg] && ic < mxstep && new_dt > 0.0f)) { ++seg; ic = 0; }
+        S.seg[c] = seg; S.icount[c] = ic;
+        if (seg < TS.n_seg) atomicAdd(&S.counters[0], 1);
+        if (accept) atomicAdd(&S.counters[1], 1);
+        atomicAdd(&S.counters[2], 1);
+        atomicMax(&S.counters[3], ntry);
+    }
+}
+
+__global__ void copy_out_kernel(int n, int d, const float* __restrict__ sx, const float* __restrict__ sl,
+                                float* __restrict__ y1, float* __restrict__ ldj) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < (long long)n * d) y1[i] = sx[i];
+    if (i < n && ldj) ldj[i] = sl[i];
+}
+
+__global__ void write_stats_kernel(const int* __restrict__ counters, int n_eval, int* __restrict__ stats, int accumulate) {
+    if (threadIdx.x == 0) {
+        if (accumulate) { stats[0] += counters[1]; stats[1] += counters[2]; stats[2] = max(stats[2], counters[3]); stats[3] += n_eval; }
+        else { stats[0] = counters[1]; stats[1] = counters[2]; stats[2] = counters[3]; stats[3] = n_eval; }
+    }
+}
+
+static size_t ode_state_bytes(int n, int d) {
+    const size_t N = n, D = d;
+    return ws_slice(N * D, 4) * (1 + 7 + 1 + 1) + ws_slice(N, 4) * (1 + 7 + 1 + 3 + 1) + ws_slice(N, 4) * 3 + 256;
+}
+
+static bool ode_state_take(OdeState& S, Workspace& w, int n, int d) {
+    const size_t N = n, D = d;
+    S.yx = w.take<float>(N * D); S.xi = w.take<float>(N * D); S.outx = w.take<float>(N * D);
+    for (int j = 0; j < 7; ++j) S.kx[j] = w.take<float>(N * D);
+    S.yl = w.take<float>(N); S.outl = w.take<float>(N); S.tf = w.take<float>(N); S.t = w.take<float>(N);
+    S.dt = w.take<float>(N); S.d1 = w.take<float>(N);
+    for (int j = 0; j < 7; ++j) S.kl[j] = w.take<float>(N);
+    S.seg = w.take<int>(N); S.icount = w.take<int>(N); S.ntry = w.take<int>(N);
+    S.counters = w.take<int>(64);
+    return w.ok;
+}
+
+static int* host_flag() {
+    static thread_local int* p = nullptr;
+    if (!p) { if (cudaMallocHost(&p, 64) != cudaSuccess) p = nullptr; }
+    return p;
+}
+
+// Solve from y0 over [0,1]; direction +1: (v, -div); -1: (-v(x, 1-s), +div).
+static int ode_solve(const mfm_field_t& F, const mfm_target_t& T, const mfm_ode_opts_t& O, int direction, int n,
+                     const float* z, const float* y0, float* y1, float* ldj, int* stats, int stats_accumulate,
+                     OdeState& S, FieldBufs& B, cudaStream_t st) {
+    const int d = F.dim;
+    const float sgn = direction >= 0 ? 1.0f : -1.0f;
+    if (O.n_times < 2 || O.n_times > 17) { mfm_set_last_error_msg("n_times must be in [2,17]"); return MFM_ERR_ARG; }
+    OdeTimes TS; TS.n_seg = O.n_times - 1;
+    for (int k = 1; k < O.n_times; ++k) TS.target[k - 1] = (float)((double)k / (double)(O.n_times - 1));
+    int* hflag = host_flag();
+    if (!hflag) { mfm_set_last_error_msg("cudaMallocHost failed"); return MFM_ERR_CUDA; }
+    int rc;
+    const int gE = ceil_div((long long)n * d, 256), gW = ceil_div(n, 8);
+    ode_init_kernel<<<max(gE, 1), 256, 0, st>>>(n, d, y0, S, 0.0f, sgn);
+    MFM_LAUNCH_CHECK();
+    if (z && (rc = field_prepare_probe(F, T, n, z, B, st))) return rc;
+    int n_eval = 0;
+    if ((rc = field_eval(F, T, n, S.xi, S.tf, z, sgn, S.kx[0], S.kl[0], B, st))) return rc; ++n_eval;
+    ode_h0_kernel<<<gW, 256, 0, st>>>(n, d, S, O.rtol, O.atol, sgn);
+    MFM_LAUNCH_CHECK();
+    if ((rc = field_eval(F, T, n, S.xi, S.tf, z, sgn, S.kx[1], S.kl[1], B, st))) return rc; ++n_eval;
+    ode_h1_kernel<<<gW, 256, 0, st>>>(n, d, S, O.rtol, O.atol);
+    MFM_LAUNCH_CHECK();
+    const long long max_iter = (long long)TS.n_seg * (long long)O.mxstep + 2;
+    for (long long it = 0; it < max_iter; ++it) {
+        for (int s = 1; s <= 6; ++s) {
+            ode_stage_kernel<<<gE, 256, 0, st>>>(n, d, s, S, TS.n_seg, sgn);
+            MFM_LAUNCH_CHECK();
+            if ((rc = field_eval(F, T, n, S.xi, S.tf, z, sgn, S.kx[s], S.kl[s], B, st))) return rc; ++n_eval;
+        }
+        MFM_CUDA_CHECK(cudaMemsetAsync(S.counters, 0, sizeof(int), st));
+        ode_finish_kernel<<<gW, 256, 0, st>>>(n, d, S, TS, O.rtol, O.atol, O.mxstep);
+        MFM_LAUNCH_CHECK();
+        MFM_CUDA_CHECK(cudaMemcpyAsync(hflag, S.counters, sizeof(int), cudaMemcpyDeviceToHost, st));
+        MFM_CUDA_CHECK(cudaStreamSynchronize(st));
+        if (*hflag == 0) break;
+    }
+    copy_out_kernel<<<max(gE, 1), 256, 0, st>>>(n, d, S.outx, S.outl, y1, ldj);
+    MFM_LAUNCH_CHECK();
+    if (stats) { write_stats_kernel<<<1, 32, 0, st>>>(S.counters, n_eval, stats, stats_accumulate); MFM_LAUNCH_CHECK(); }
+    return MFM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// flow-MH kernels
+// ---------------------------------------------------------------------------------------------
+// key_gen, key_acc, key_hutch1, key_hutch2 = split(keys[c], 4)   (exe_flow_matching.py:247,265)
+__global__ void flow_keys_kernel(const uint32_t* __restrict__ rng_key, int n, int chain_offset, int n_total,
+                                 uint32_t* __restrict__ kgen, uint32_t* __restrict__ kacc, uint32_t* __restrict__ kh1,
+                                 uint32_t* __restrict__ kh2) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    u32x2 kc;
+    if (n_total > 0) kc = threefry_split_key(rng_key[0], rng_key[1], (uint32_t)(chain_offset + c), (uint32_t)n_total);
+    else { kc.a = rng_key[2 * c]; kc.b = rng_key[2 * c + 1]; }
+    uint32_t* outs[4] = {kgen, kacc, kh1, kh2};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const u32x2 k = threefry_split_key(kc.a, kc.b, (uint32_t)j, 4u);
+        outs[j][2 * c] = k.a; outs[j][2 * c + 1] = k.b;
+    }
+}
+
+// out = a + scale * eps   (:268)
+__global__ void axpy_kernel(long long total, const float* __restrict__ a, float scale, const float* __restrict__ eps,
+                            float* __restrict__ out) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < total) out[i] = a[i] + scale * eps[i];
+}
+
+// log N(x; mean, std) summed over the row (ref_dist.logprob, distributions.py:89-90)
+__global__ void gauss_logprob_kernel(int n, int d, const float* __restrict__ x, float mean, float std_, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= n) return;
+    const float var = std_ * std_;
+    float s = 0.0f;
+    for (int i = lane; i < d; i += 32) { const float df = x[(long long)c * d + i] - mean; s += -(logf(6.28318530717958647692f * var) + df * df / var) / 2.0f; }
+    s = warp_sum(s);
+    if (lane == 0) out[c] = s;
+}
+
+struct FlowAcceptArgs {
+    int variant;
+    const float *xp, *lp, *gp, *Vp, *V0, *logq_up, *logq_u0;
+    const uint32_t* kacc;
+    float *x, *l, *g, *acc_rate, *prop_pos, *prop_w; uint8_t* is_acc;
+};
+
+__global__ void flow_accept_kernel(int n, int d, FlowAcceptArgs A) {
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= n) return;
+    float la;
+    if (A.variant == MFM_FLOW_RW_MH) la = A.lp[c] - A.Vp[c] - A.l[c] - A.V0[c];                            // :271-274
+    else la = A.lp[c] - A.logq_up[c] - A.Vp[c] + A.logq_u0[c] - A.V0[c] - A.l[c];                         // :253-256
+    const float acc_prob = expf(la);
+    const float u = bits_to_unit_float(threefry2x32(A.kacc[2 * c], A.kacc[2 * c + 1], 0u, 0u).a);
+    const bool acc = u <= acc_prob;                                                                      // :257,275
+    for (int i = lane; i < d; i += 32) {
+        const float v = A.xp[(long long)c * d + i];
+        if (A.prop_pos) A.prop_pos[(long long)c * d + i] = v;
+        if (acc) { A.x[(long long)c * d + i] = v; A.g[(long long)c * d + i] = A.gp[(long long)c * d + i]; }
+    }
+    if (lane == 0) {
+        if (acc) A.l[c] = A.lp[c];
+        if (A.acc_rate) A.acc_rate[c] = acc_prob;
+        if (A.is_acc) A.is_acc[c] = acc ? 1 : 0;
+        if (A.prop_w) A.prop_w[c] = 0.0f;
+    }
+}
+
+}  // namespace mfm
+
+// =============================================================================================
+extern "C" {
+using namespace mfm;
+
+static int check_field(const mfm_field_t* f, const mfm_target_t* t, const mfm_ode_opts_t* o) {
+    if (!f || !t || !o) { mfm_set_last_error_msg("null descriptor"); return MFM_ERR_ARG; }
+    if (f->dim != t->dim) { mfm_set_last_error_msg("field.dim != target.dim"); return MFM_ERR_ARG; }
+    if (f->hidden <= 0 || f->fourier_dim <= 0 || !f->params || !f->omega) { mfm_set_last_error_msg("bad field descriptor"); return MFM_ERR_ARG; }
+    return MFM_OK;
+}
+
+size_t mfm_ode_workspace_bytes(const mfm_field_t* f, const mfm_target_t* t, const mfm_ode_opts_t* o, int n) {
+    return ode_state_bytes(n, f->dim) + field_bufs_bytes(*f, *t, n, o->hutch != 0) + ws_slice((size_t)n * f->dim, 4) + 1024;
+}
+
+int mfm_ode_flow(const mfm_field_t* f, const mfm_target_t* t, const mfm_ode_opts_t* o, int direction, int n,
+                 const uint32_t* hutch_keys, const float* y0, float* y1, float* ldj, int* stats, void* ws,
+                 size_t ws_bytes, mfm_stream_t stream) {
+    int rc = check_field(f, t, o);
+    if (rc) return rc;
+    if (n <= 0) return MFM_OK;
+    Workspace w(ws, ws_bytes);
+    OdeState S; FieldBufs B;
+    ode_state_take(S, w, n, f->dim);
+    field_bufs_take(B, w, *f, n, o->hutch != 0);
+    float* z = nullptr;
+    if (o->hutch) z = w.take<float>((size_t)n * f->dim);
+    if (!w.ok) { mfm_set_last_error_msg("workspace too small (mfm_ode_flow)"); return MFM_ERR_WORKSPACE; }
+    if (o->hutch) {
+        if (!hutch_keys) { mfm_set_last_error_msg("hutch_keys required"); return MFM_ERR_ARG; }
+        if ((rc = mfm_threefry_normal_batched(hutch_keys, n, f->dim, z, stream))) return rc;
+    }
+    return ode_solve(*f, *t, *o, direction, n, z, y0, y1, ldj, stats, 0, S, B, stream);
+}
+
+int mfm_field_eval(const mfm_field_t* f, const mfm_target_t* t, const mfm_ode_opts_t* o, int n, const float* x,
+                   const float* time, const float* z, float* v, float* div, void* ws, size_t ws_bytes,
+                   mfm_stream_t stream) {
+    int rc = check_field(f, t, o);
+    if (rc) return rc;
+    if (n <= 0) return MFM_OK;
+    Workspace w(ws, ws_bytes);
+    FieldBufs B;
+    const bool hutch = o->hutch != 0;
+    field_bufs_take(B, w, *f, n, hutch);
+    float* negdiv = w.take<float>(n);
+    if (!w.ok) { mfm_set_last_error_msg("workspace too small (mfm_field_eval)"); return MFM_ERR_WORKSPACE; }
+    if (hutch && !z) { mfm_set_last_error_msg("z required for hutch"); return MFM_ERR_ARG; }
+    if (hutch && (rc = field_prepare_probe(*f, *t, n, z, B, stream))) return rc;
+    // field_eval writes -sgn*div; evaluate with sgn=-1 on a negated... simpler: sgn=+1 then negate
+    if ((rc = field_eval(*f, *t, n, x, time, hutch ? z : nullptr, 1.0f, v, div ? negdiv : nullptr, B, stream))) return rc;
+    if (div) { axpy_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(n, negdiv, -2.0f, negdiv, div); MFM_LAUNCH_CHECK(); }
+    return MFM_OK;
+}
+
+size_t mfm_flow_mh_workspace_bytes(const mfm_field_t* f, const mfm_target_t* t, const mfm_ode_opts_t* o, int n) {
+    const size_t N = n, D = f->dim;
+    return mfm_ode_workspace_bytes(f, t, o, n) + ws_slice(N * D, 4) * 5 + ws_slice(N, 4) * 6 + ws_slice(N * 2, 4) * 4 +
+           target_ws_bytes(*t, n) + 1024;
+}
+
+int mfm_flow_mh_step(const mfm_field_t* f, const mfm_target_t* t, const mfm_ode_opts_t* o, int variant,
+                     const uint32_t* rng_key, int per_chain_keys, int n, int chain_offset, int n_total,
+                     float* position, float* logdensity, float* logdensity_grad, float* acceptance_rate,
+                     uint8_t* is_accepted, float* proposed_position, float* proposed_weight, int* stats, void* ws,
+                     size_t ws_bytes, mfm_stream_t stream) {
+    int rc = check_field(f, t, o);
+    if (rc) return rc;
+    if (!rng_key || !position || !logdensity || !logdensity_grad) { mfm_set_last_error_msg("null argument"); return MFM_ERR_ARG; }
+    if (n <= 0) return MFM_OK;
+    if (variant != MFM_FLOW_RW_MH && variant != MFM_FLOW_INDEP_MH) { mfm_set_last_error_msg("unknown flow-MH variant"); return MFM_ERR_ARG; }
+    if (per_chain_keys) { chain_offset = 0; n_total = 0; }
+    else if (n_total < chain_offset + n || chain_offset < 0) { mfm_set_last_error_msg("bad chain_offset/n_total"); return MFM_ERR_ARG; }
+    const int d = f->dim;
+    const size_t N = n, D = d;
+    Workspace w(ws, ws_bytes);
+    OdeState S; FieldBufs B;
+    ode_state_take(S, w, n, d);
+    field_bufs_take(B, w, *f, n, o->hutch != 0);
+    float* z = w.take<float>(N * D);
+    float* u0 = w.take<float>(N * D); float* up = w.take<float>(N * D); float* xp = w.take<float>(N * D);
+    float* gp = w.take<float>(N * D); float* eps = w.take<float>(N * D);
+    float* V0 = w.take<float>(N); float* Vp = w.take<float>(N); float* lp = w.take<float>(N);
+    float* lq_up = w.take<float>(N); float* lq_u0 = w.take<float>(N); w.take<float>(N);
+    uint32_t* kgen = w.take<uint32_t>(N * 2); uint32_t* kacc = w.take<uint32_t>(N * 2);
+    uint32_t* kh1 = w.take<uint32_t>(N * 2); uint32_t* kh2 = w.take<uint32_t>(N * 2);
+    Workspace wt((char*)ws + w.off, w.off <= ws_bytes ? ws_bytes - w.off : 0);
+    if (!w.ok) { mfm_set_last_error_msg("workspace too small (mfm_flow_mh_step)"); return MFM_ERR_WORKSPACE; }
+    const bool hutch = o->hutch != 0;
+
+    flow_keys_kernel<<<ceil_div(n, 128), 128, 0, stream>>>(rng_key, n, chain_offset, n_total, kgen, kacc, kh1, kh2);
+    MFM_LAUNCH_CHECK();
+    if ((rc = mfm_threefry_normal_batched(kgen, n, d, eps, stream))) return rc;
+    const long long tot = (long long)n * d;
+    if (variant == MFM_FLOW_RW_MH) {
+        // pull back the current position, random-walk in latent space, push forward
+        if (hutch && (rc = mfm_threefry_normal_batched(kh2, n, d, z, stream))) return rc;
+        if ((rc = ode_solve(*f, *t, *o, -1, n, hutch ? z : nullptr, position, u0, V0, stats, 0, S, B, stream))) return rc;
+        const float scale = 2.38f / sqrtf((float)d);                                     // :262
+        axpy_kernel<<<ceil_div(tot, 256), 256, 0, stream>>>(tot, u0, scale, eps, up);
+        MFM_LAUNCH_CHECK();
+        if (hutch && (rc = mfm_threefry_normal_batched(kh1, n, d, z, stream))) return rc;
+        if ((rc = ode_solve(*f, *t, *o, +1, n, hutch ? z : nullptr, up, xp, Vp, stats, 1, S, B, stream))) return rc;
+    } else {
+        // independent proposal from the reference distribution N(0, I) (stdgauss, :48-49,249)
+        MFM_CUDA_CHECK(cudaMemcpyAsync(up, eps, tot * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+        if (hutch && (rc = mfm_threefry_normal_batched(kh1, n, d, z, stream))) return rc;
+        if ((rc = ode_solve(*f, *t, *o, +1, n, hutch ? z : nullptr, up, xp, Vp, stats, 0, S, B, stream))) return rc;
+        if (hutch && (rc = mfm_threefry_normal_batched(kh2, n, d, z, stream))) return rc;
+        if ((rc = ode_solve(*f, *t, *o, -1, n, hutch ? z : nullptr, position, u0, V0, stats, 1, S, B, stream))) return rc;
+        gauss_logprob_kernel<<<ceil_div(n, 8), 256, 0, stream>>>(n, d, up, 0.0f, 1.0f, lq_up);
+        gauss_logprob_kernel<<<ceil_div(n, 8), 256, 0, stream>>>(n, d, u0, 0.0f, 1.0f, lq_u0);
+        MFM_LAUNCH_CHECK();
+    }
+    if ((rc = target_value_and_grad(*t, n, xp, lp, gp, nullptr, wt, stream))) return rc;
+    FlowAcceptArgs A{variant, xp, lp, gp, Vp, V0, lq_up, lq_u0, kacc, position, logdensity, logdensity_grad,
+                     acceptance_rate, proposed_position, proposed_weight, is_accepted};
+    flow_accept_kernel<<<ceil_div(n, 8), 256, 0, stream>>>(n, d, A);
+    MFM_LAUNCH_CHECK();
+    return MFM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,356 @@
+// Flow-matching update: conditional-flow batch, loss, gradient w.r.t. the MLP parameters, and the
+// fused AdamW -> clip -> apply_if_finite step.
+//
+// Replaces:
+//   cond_flow_fn / flow_matching_loss        exe_flow_matching.py:151-179
+//   jax.value_and_grad(loss_fn, argnums=2)   :364-365  (hand-written backward of VectorFieldNet)
+//   optax chain in create_train_state        :129-137, :184   [restated in oracle/optim.py]
+#include "internal.h"
+#include "gemm_tf32x3.cuh"
+
+namespace mfm {
+
+// ---------------------------------------------------------------------------------------------
+// batch generation:  t ~ U[0,1)^(N,1); x0_i = normal(split(key_ref,N)_i,(d,)); eps ~ N(0,I)^(N,d)
+// x_t = sigma*eps + t*x + (1-t)*x0 ; target = x - x0      (one warp per chain)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+fm_batch_kernel(const uint32_t* __restrict__ rng_key, int n, int chain_offset, int n_total, int d, float sigma,
+                const float* __restrict__ x, float* __restrict__ times, float* __restrict__ xt,
+                float* __restrict__ target) {
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= n) return;
+    const uint32_t gc = (uint32_t)(chain_offset + c);
+    // key_time, key_ref, key_gauss, key_ot = split(rng_key, 4)
+    const u32x2 k_time = threefry_split_key(rng_key[0], rng_key[1], 0u, 4u);
+    const u32x2 k_ref = threefry_split_key(rng_key[0], rng_key[1], 1u, 4u);
+    const u32x2 k_gauss = threefry_split_key(rng_key[0], rng_key[1], 2u, 4u);
+    const float t = bits_to_unit_float(threefry_stream_word(k_time.a, k_time.b, gc, (uint32_t)n_total));
+    const u32x2 k_row = threefry_split_key(k_ref.a, k_ref.b, gc, (uint32_t)n_total);
+    const uint32_t total = (uint32_t)n_total * (uint32_t)d;
+    const uint32_t half = ((uint32_t)d + 1u) >> 1;
+    const float omt = 1.0f - t;
+    for (uint32_t b = lane; b < half; b += 32) {
+        const uint32_t hi = b + half;
+        const bool has_hi = hi < (uint32_t)d;
+        const u32x2 o = threefry2x32(k_row.a, k_row.b, b, has_hi ? hi : 0u);
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            if (s == 1 && !has_hi) break;
+            const uint32_t j = s == 0 ? b : hi;
+            const float x0 = bits_to_normal(s == 0 ? o.a : o.b);
+            const float eps = bits_to_normal(threefry_stream_word(k_gauss.a, k_gauss.b, gc * (uint32_t)d + j, total));
+            const long long idx = (long long)c * d + j;
+            const float xv = x[idx];
+            // sigma*eps + t*x + (1-t)*x0, left to right (:167)
+            xt[idx] = __fadd_rn(__fadd_rn(__fmul_rn(sigma, eps), __fmul_rn(t, xv)), __fmul_rn(omt, x0));
+            target[idx] = xv - x0;                                         // :168
+        }
+    }
+    if (lane == 0) times[c] = t;
+}
+
+// diff = v - target; delta = 2*diff; dgt = delta*gc; per-block partial sums of diff^2
+__global__ void __launch_bounds__(256)
+fm_loss_delta_kernel(long long total, const float* __restrict__ v, const float* __restrict__ target,
+                     const float* __restrict__ gc, float* __restrict__ delta, float* __restrict__ dgt,
+                     float* __restrict__ block_partial) {
+    __shared__ float red[32];
+    float s = 0.0f;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const float df = v[i] - target[i];
+        s += df * df;
+        const float dl = 2.0f * df;
+        delta[i] = dl;
+        dgt[i] = dl * gc[i];
+    }
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) block_partial[blockIdx.x] = s;
+}
+
+__global__ void final_sum_kernel(int n, const float* __restrict__ partial, float* __restrict__ out) {
+    __shared__ float red[32];
+    float s = 0.0f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s += partial[i];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) out[0] = s;
+}
+
+// column sums of a [n, cols] matrix (bias gradients); 32 columns per block, fixed summation order
+__global__ void __launch_bounds__(256)
+colsum_kernel(int n, int cols, const float* __restrict__ a, long long lda, float* __restrict__ out) {
+    __shared__ float sm[8][33];
+    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    const int col = blockIdx.x * 32 + cx;
+    float s = 0.0f;
+    if (col < cols) for (int r = ry; r < n; r += 8) s += a[(long long)r * lda + col];
+    sm[ry][cx] = s;
+    __syncthreads();
+    if (ry == 0 && col < cols) {
+        float t = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += sm[k][cx];
+        out[col] = t;
+    }
+}
+
+// out[i] = sum_z partial[z*stride + i]
+__global__ void splitk_reduce_kernel(long long count, int splits, long long stride, const float* __restrict__ partial,
+                                     float* __restrict__ out) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    float s = 0.0f;
+    for (int z = 0; z < splits; ++z) s += partial[(long long)z * stride + i];
+    out[i] = s;
+}
+
+// dW[in,out] = A^T[in,n] * D[n,out]  (A stored [n,in], lda), split over the batch dimension.
+static int wgrad(int n, int in, int out, const float* A, long long lda, const float* D, long long ldd, float* dW,
+                 float* splitbuf, size_t splitbuf_floats, cudaStream_t st) {
+    const long long tiles = (long long)ceil_div(in, GBM) * ceil_div(out, GBN);
+    int splits = (int)((2 * 148 + tiles - 1) / tiles);            // aim for >= 2 CTAs per SM
+    const int max_splits = (n + 255) / 256;
+    if (splits > max_splits) splits = max_splits;
+    if (splits > 64) splits = 64;
+    while (splits > 1 && (size_t)splits * in * out > splitbuf_floats) --splits;
+    if (splits <= 1) {
+        GemmShape p{in, out, n, A, lda, D, ldd, nullptr};
+        EpiStd e{dW, (long long)out, nullptr, nullptr, 0, nullptr, 0, 1.0f, 0};
+        MFM_CUDA_CHECK((launch_gemm<false, true>(p, e, st)));
+        return MFM_OK;
+    }
+    int kper = (n + splits - 1) / splits;
+    kper = (kper + GBK - 1) / GBK * GBK;
+    GemmShape p{in, out, n, A, lda, D, ldd, nullptr, kper};
+    EpiStd e{splitbuf, (long long)out, nullptr, nullptr, 0, nullptr, 0, 1.0f, 0, 1, (long long)in * out};
+    MFM_CUDA_CHECK((launch_gemm<false, true>(p, e, st)));
+    const int nz = (n + kper - 1) / kper;
+    splitk_reduce_kernel<<<ceil_div((long long)in * out, 256), 256, 0, st>>>((long long)in * out, nz, (long long)in * out, splitbuf, dW);
+    MFM_LAUNCH_CHECK();
+    return MFM_OK;
+}
+
+// dX[n,in] = (D[n,out] * W^T) gated by mask, optionally + add       (W stored [in,out])
+static int dgrad(int n, int in, int out, const float* D, long long ldd, const float* W, float* dX, long long ldx,
+                 const float* mask, long long ldm, const float* add, long long ldadd, cudaStream_t st) {
+    GemmShape p{n, in, out, D, ldd, W, (long long)out, nullptr};
+    EpiStd e{dX, ldx, nullptr, mask, ldm, add, ldadd, 1.0f, 0};
+    MFM_CUDA_CHECK((launch_gemm<true, false>(p, e, st)));
+    return MFM_OK;
+}
+
+struct FmBufs {
+    FieldBufs B;
+    float *times, *xt, *target, *v, *delta, *dgt, *d6, *d5, *dcat, *d2, *d0, *blockpart, *splitbuf;
+    size_t splitbuf_floats;
+};
+
+static const int FM_LOSS_BLOCKS = 1024;
+
+static size_t fm_splitbuf_floats(const mfm_field_t& F) {
+    const size_t H = F.hidden, d = F.dim, Fd = F.fourier_dim;
+    size_t m = 2 * H * H;
+    if (d * H > m) m = d * H;
+    if (2 * Fd * H > m) m = 2 * Fd * H;
+    return m * 8;      // room for up to 8 batch slices of the largest layer (more for smaller ones)
+}
+
+static size_t fm_bytes(const mfm_field_t& F, const mfm_target_t& T, int n) {
+    const size_t H = F.hidden, d = F.dim, N = n;
+    return field_bufs_bytes(F, T, n, true) + ws_slice(N, 4) + ws_slice(N * d, 4) * 5 + ws_slice(N * H, 4) * 4 +
+           ws_slice(N * 2 * H, 4) + ws_slice(FM_LOSS_BLOCKS, 4) + ws_slice(fm_splitbuf_floats(F), 4) + 1024;
+}
+
+static bool fm_take(FmBufs& M, Workspace& w, const mfm_field_t& F, int n) {
+    const size_t H = F.hidden, d = F.dim, N = n;
+    field_bufs_take(M.B, w, F, n, true);
+    M.times = w.take<float>(N);
+    M.xt = w.take<float>(N * d); M.target = w.take<float>(N * d); M.v = w.take<float>(N * d);
+    M.delta = w.take<float>(N * d); M.dgt = w.take<float>(N * d);
+    M.d6 = w.take<float>(N * H); M.d5 = w.take<float>(N * H); M.d2 = w.take<float>(N * H); M.d0 = w.take<float>(N * H);
+    M.dcat = w.take<float>(N * 2 * H);
+    M.blockpart = w.take<float>(FM_LOSS_BLOCKS);
+    M.splitbuf_floats = fm_splitbuf_floats(F);
+    M.splitbuf = w.take<float>(M.splitbuf_floats);
+    return w.ok;
+}
+
+#define W_(i) (F.params + F.w_off[i])
+#define GW_(i) (grads + F.w_off[i])
+#define GB_(i) (grads + F.b_off[i])
+
+static int fm_forward_backward(const mfm_field_t& F, const mfm_target_t& T, int n, FmBufs& M, float* loss_out,
+                               float* grads, cudaStream_t st) {
+    const int d = F.dim, H = F.hidden, Fd = F.fourier_dim;
+    FieldBufs& B = M.B;
+    int rc;
+    MFM_CUDA_CHECK(cudaMemsetAsync(grads, 0, (size_t)F.n_params * sizeof(float), st));
+    if ((rc = field_eval(F, T, n, M.xt, M.times, nullptr, 1.0f, M.v, nullptr, B, st))) return rc;
+    const long long tot = (long long)n * d;
+    const int lb = (int)((tot + 255) / 256 < FM_LOSS_BLOCKS ? (tot + 255) / 256 : FM_LOSS_BLOCKS);
+    fm_loss_delta_kernel<<<lb, 256, 0, st>>>(tot, M.v, M.target, B.gc, M.delta, M.dgt, M.blockpart);
+    MFM_LAUNCH_CHECK();
+    final_sum_kernel<<<1, 256, 0, st>>>(lb, M.blockpart, loss_out);
+    MFM_LAUNCH_CHECK();
+    auto bias_grad = [&](const float* a, long long lda, int cols, float* out) -> int {
+        colsum_kernel<<<ceil_div(cols, 32), 256, 0, st>>>(n, cols, a, lda, out);
+        MFM_LAUNCH_CHECK();
+        return MFM_OK;
+    };
+    float* sb = M.splitbuf; const size_t sbf = M.splitbuf_floats;
+    // layer 7 (nn_xt head): y = h6 W7 + b7
+    if ((rc = wgrad(n, H, d, B.h6, H, M.delta, d, GW_(7), sb, sbf, st))) return rc;
+    if ((rc = bias_grad(M.delta, d, d, GB_(7)))) return rc;
+    if ((rc = dgrad(n, H, d, M.delta, d, W_(7), M.d6, H, B.h6, H, nullptr, 0, st))) return rc;
+    // layer 6
+    if ((rc = wgrad(n, H, H, B.h5, H, M.d6, H, GW_(6), sb, sbf, st))) return rc;
+    if ((rc = bias_grad(M.d6, H, H, GB_(6)))) return rc;
+    if ((rc = dgrad(n, H, H, M.d6, H, W_(6), M.d5, H, B.h5, H, nullptr, 0, st))) return rc;
+    // layer 5 (joint, input cat = [s_x | s_t])
+    if ((rc = wgrad(n, 2 * H, H, B.cat, 2 * H, M.d5, H, GW_(5), sb, sbf, st))) return rc;
+    if ((rc = bias_grad(M.d5, H, H, GB_(5)))) return rc;
+    // d s_x = (d5 W5[:H]^T) * relu'(s_x)
+    if ((rc = dgrad(n, H, H, M.d5, H, W_(5), M.dcat, 2 * H, B.cat, 2 * H, nullptr, 0, st))) return rc;
+    // d s_t (joint part) = d5 W5[H:]^T   (no gate yet)
+    if ((rc = dgrad(n, H, H, M.d5, H, W_(5) + (long long)H * H, M.dcat + H, 2 * H, nullptr, 0, nullptr, 0, st))) return rc;
+    // layer 4 (nn_t head): g_t = s_t W4 + b4, dL/dg_t = delta * clip(grad logprob)
+    if ((rc = wgrad(n, H, d, B.cat + H, 2 * H, M.dgt, d, GW_(4), sb, sbf, st))) return rc;
+    if ((rc = bias_grad(M.dgt, d, d, GB_(4)))) return rc;
+    // d s_t = (dgt W4^T + joint part) * relu'(s_t)   (in place)
+    if ((rc = dgrad(n, H, d, M.dgt, d, W_(4), M.dcat + H, 2 * H, B.cat + H, 2 * H, M.dcat + H, 2 * H, st))) return rc;
+    // layer 3 (x branch)
+    if ((rc = wgrad(n, H, H, B.h2, H, M.dcat, 2 * H, GW_(3), sb, sbf, st))) return rc;
+    if ((rc = bias_grad(M.dcat, 2 * H, H, GB_(3)))) return rc;
+    if ((rc = dgrad(n, H, H, M.dcat, 2 * H, W_(3), M.d2, H, B.h2, H, nullptr, 0, st))) return rc;
+    // layer 2
+    if ((rc = wgrad(n, d, H, M.xt, d, M.d2, H, GW_(2), sb, sbf, st))) return rc;
+    if ((rc = bias_grad(M.d2, H, H, GB_(2)))) return rc;
+    // layer 1 (time branch)
+    if ((rc = wgrad(n, H, H, B.h0, H, M.dcat + H, 2 * H, GW_(1), sb, sbf, st))) return rc;
+    if ((rc = bias_grad(M.dcat + H, 2 * H, H, GB_(1)))) return rc;
+    if ((rc = dgrad(n, H, H, M.dcat + H, 2 * H, W_(1), M.d0, H, B.h0, H, nullptr, 0, st))) return rc;
+    // layer 0
+    if ((rc = wgrad(n, 2 * Fd, H, B.ff, 2 * Fd, M.d0, H, GW_(0), sb, sbf, st))) return rc;
+    if ((rc = bias_grad(M.d0, H, H, GB_(0)))) return rc;
+    return MFM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// optimizer
+// ---------------------------------------------------------------------------------------------
+// scratch[0] = number of non-finite gradient entries
+__global__ void finite_check_kernel(long long n, const float* __restrict__ g, int* __restrict__ scratch) {
+    int bad = 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        bad |= !isfinite(g[i]);
+    bad = __any_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0 && bad) atomicAdd(scratch, 1);
+}
+
+// opt_state: [adam count, notfinite_count, total_notfinite, last_finite, scratch(nonfinite), apply flag]
+__global__ void opt_decide_kernel(int* __restrict__ st, int max_err) {
+    if (threadIdx.x != 0) return;
+    const bool finite = st[4] == 0;
+    const int nf = finite ? 0 : st[1] + 1;                 // notfinite_count
+    st[1] = nf;
+    if (!finite) st[2] += 1;                               // total_notfinite
+    st[3] = finite ? 1 : 0;                                // last_finite
+    st[5] = (finite || nf > max_err) ? 1 : 0;              // apply the inner update?
+}
+
+__global__ void __launch_bounds__(256)
+adamw_kernel(long long n, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ mu,
+             float* __restrict__ nu, const uint8_t* __restrict__ decay, const int* __restrict__ st, float lr_base,
+             int lr_total, float b1, float b2, float eps, float wd, float clip) {
+    if (st[5] == 0) return;                                // rejected update: params and moments untouched
+    const int count = st[0];
+    const float c1 = (float)(count + 1);
+    const float bc1 = 1.0f - powf(b1, c1), bc2 = 1.0f - powf(b2, c1);
+    int cc = count < 0 ? 0 : (count > lr_total ? lr_total : count);
+    const float lr = lr_base * (1.0f - (float)cc / (float)lr_total);       // linear decay to 0 (:189-198)
+    const float omb1 = 1.0f - b1, omb2 = 1.0f - b2;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float gi = g[i];
+        const float m = omb1 * gi + b1 * mu[i];
+        const float v = omb2 * gi * gi + b2 * nu[i];
+        mu[i] = m; nu[i] = v;
+        float u = (m / bc1) / (sqrtf(v / bc2) + eps);
+        const float pi = p[i];
+        if (decay[i]) u += wd * pi;
+        u = -lr * u;
+        u = fminf(fmaxf(u, -clip), clip);                  // optax.clip on the update
+        p[i] = pi + u;
+    }
+}
+
+__global__ void opt_advance_kernel(int* __restrict__ st) {
+    if (threadIdx.x == 0 && st[5]) st[0] += 1;
+}
+
+}  // namespace mfm
+
+extern "C" {
+using namespace mfm;
+
+size_t mfm_fm_workspace_bytes(const mfm_field_t* f, const mfm_target_t* t, int n) { return fm_bytes(*f, *t, n); }
+
+static int fm_check(const mfm_field_t* f, const mfm_target_t* t) {
+    if (!f || !t) { mfm_set_last_error_msg("null descriptor"); return MFM_ERR_ARG; }
+    if (f->dim != t->dim) { mfm_set_last_error_msg("field.dim != target.dim"); return MFM_ERR_ARG; }
+    return MFM_OK;
+}
+
+int mfm_fm_loss_grad(const mfm_field_t* f, const mfm_target_t* t, const uint32_t* rng_key, int n, int chain_offset,
+                     int n_total, float sigma, const float* positions, float* loss_out, float* grads, void* ws,
+                     size_t ws_bytes, mfm_stream_t stream) {
+    int rc = fm_check(f, t);
+    if (rc) return rc;
+    if (!rng_key || !positions || !loss_out || !grads) { mfm_set_last_error_msg("null argument"); return MFM_ERR_ARG; }
+    if (n <= 0) return MFM_OK;
+    if (n_total < chain_offset + n || chain_offset < 0) { mfm_set_last_error_msg("bad chain_offset/n_total"); return MFM_ERR_ARG; }
+    if ((long long)n_total * f->dim > 0xFFFFFFFFll) { mfm_set_last_error_msg("n_total*d exceeds the 32-bit counter space"); return MFM_ERR_UNSUPPORTED; }
+    Workspace w(ws, ws_bytes);
+    FmBufs M;
+    if (!fm_take(M, w, *f, n)) { mfm_set_last_error_msg("workspace too small (mfm_fm_loss_grad)"); return MFM_ERR_WORKSPACE; }
+    fm_batch_kernel<<<ceil_div(n, 8), 256, 0, stream>>>(rng_key, n, chain_offset, n_total, f->dim, sigma, positions,
+                                                         M.times, M.xt, M.target);
+    MFM_LAUNCH_CHECK();
+    return fm_forward_backward(*f, *t, n, M, loss_out, grads, stream);
+}
+
+int mfm_fm_loss_grad_from_batch(const mfm_field_t* f, const mfm_target_t* t, int n, const float* xt, const float* times,
+                                const float* target_v, float* loss_out, float* grads, void* ws, size_t ws_bytes,
+                                mfm_stream_t stream) {
+    int rc = fm_check(f, t);
+    if (rc) return rc;
+    if (!xt || !times || !target_v || !loss_out || !grads) { mfm_set_last_error_msg("null argument"); return MFM_ERR_ARG; }
+    if (n <= 0) return MFM_OK;
+    Workspace w(ws, ws_bytes);
+    FmBufs M;
+    if (!fm_take(M, w, *f, n)) { mfm_set_last_error_msg("workspace too small (mfm_fm_loss_grad_from_batch)"); return MFM_ERR_WORKSPACE; }
+    const size_t nd = (size_t)n * f->dim * sizeof(float);
+    MFM_CUDA_CHECK(cudaMemcpyAsync(M.xt, xt, nd, cudaMemcpyDeviceToDevice, stream));
+    MFM_CUDA_CHECK(cudaMemcpyAsync(M.target, target_v, nd, cudaMemcpyDeviceToDevice, stream));
+    MFM_CUDA_CHECK(cudaMemcpyAsync(M.times, times, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+    return fm_forward_backward(*f, *t, n, M, loss_out, grads, stream);
+}
+
+int mfm_adamw_step(float* params, const float* grads, float* mu, float* nu, const uint8_t* decay_mask, long long n_params,
+                   int* opt_state, float lr_base, int lr_total_steps, float b1, float b2, float eps, float weight_decay,
+                   float clip, int max_consecutive_errors, mfm_stream_t stream) {
+    if (!params || !grads || !mu || !nu || !decay_mask || !opt_state || n_params <= 0 || lr_total_steps <= 0) {
+        mfm_set_last_error_msg("bad argument (mfm_adamw_step)"); return MFM_ERR_ARG;
+    }
+    MFM_CUDA_CHECK(cudaMemsetAsync(opt_state + 4, 0, 2 * sizeof(int), stream));
+    const int blocks = (int)((n_params + 255) / 256 < 1184 ? (n_params + 255) / 256 : 1184);
+    finite_check_kernel<<<blocks, 256, 0, stream>>>(n_params, grads, opt_state + 4);
+    opt_decide_kernel<<<1, 32, 0, stream>>>(opt_state, max_consecutive_errors);
+    adamw_kernel<<<blocks, 256, 0, stream>>>(n_params, params, grads, mu, nu, decay_mask, opt_state, lr_base,
+                                             lr_total_steps, b1, b2, eps, weight_decay, clip);
+    opt_advance_kernel<<<1, 32, 0, stream>>>(opt_state);
+    MFM_LAUNCH_CHECK();
+    return MFM_OK;
+}
+
+}  // extern "C"

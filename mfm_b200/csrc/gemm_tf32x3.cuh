@@ -13,19 +13,23 @@
 
 namespace mfm {
 
-constexpr int GBM = 128, GBN = 128, GBK = 16, GSTAGES = 3, GTHREADS = 256;
+constexpr int GBM = 128, GBN = 64, GBK = 16, GSTAGES = 3, GTHREADS = 256;
+constexpr int G_MI = 2, G_NJ = 4;      // warp tile 32x32 = 2 (m16) x 4 (n8) MMA tiles; warps 4 (M) x 2 (N)
+constexpr int G_FLUSH = 2;             // k-tiles (x16) accumulated inside the tensor core before an RN flush
 // smem strides chosen so fragment loads are bank-conflict free (see DESIGN.md "GEMM").
-constexpr int LDS_K = GBK + 4;    // operand stored [rows][K]   (K contiguous)
-constexpr int LDS_MN = GBM + 8;   // operand stored [K][rows]   (M/N contiguous)
-constexpr int A_STAGE = (GBM * LDS_K > GBK * LDS_MN) ? GBM * LDS_K : GBK * LDS_MN;
-constexpr int B_STAGE = A_STAGE;
-constexpr int GEMM_SMEM_BYTES = GSTAGES * (A_STAGE + B_STAGE) * 4 + GBM * 4 * 4;
+constexpr int LDS_K = GBK + 4;         // operand stored [rows][K]   (K contiguous)
+constexpr int LDS_AM = GBM + 8;        // A stored [K][M]
+constexpr int LDS_BN = GBN + 8;        // B stored [K][N]
+constexpr int A_STAGE = (GBM * LDS_K > GBK * LDS_AM) ? GBM * LDS_K : GBK * LDS_AM;
+constexpr int B_STAGE = (GBN * LDS_K > GBK * LDS_BN) ? GBN * LDS_K : GBK * LDS_BN;
+constexpr int GEMM_SMEM_BYTES = GSTAGES * (A_STAGE + B_STAGE) * 4 + GBM * 2 * 4;
 
 struct GemmShape {
     int M, N, K;
     const float* A; long long lda;   // A_KMAJOR: A[m*lda + k]; else A[k*lda + m]
     const float* B; long long ldb;   // B_NMAJOR: B[k*ldb + n]; else B[n*ldb + k]
     const int* n_rows_dev;           // optional: device int, effective M (active rows); tiles beyond exit
+    int k_split = 0;                 // >0: gridDim.z slices of k_split values of k; epilogue gets slice via at_z()
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool pred) {
@@ -50,44 +54,32 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
 }
 
 // Load a [ROWS x GBK] operand tile.  KMAJ=true: global is [row][k] (k contiguous) -> smem [row][LDS_K].
-// KMAJ=false: global is [k][row] (row contiguous) -> smem [k][LDS_MN].
-template <bool KMAJ>
+// KMAJ=false: global is [k][row] (row contiguous) -> smem [k][LDS_R].
+template <bool KMAJ, int ROWS, int LDS_R>
 __device__ __forceinline__ void load_tile(float* s, const float* __restrict__ g, long long ld, int row0, int k0,
                                           int rows, int K, bool vec_ok) {
     const int tid = threadIdx.x;
-    if (KMAJ) {
-        // 128 rows x 16 k = 512 float4 chunks; 2 per thread
+    constexpr int CHUNKS = ROWS * GBK / 4;
 #pragma unroll
-        for (int it = 0; it < 2; ++it) {
-            const int c = tid + it * GTHREADS;
-            const int r = c >> 2, kk = (c & 3) * 4;
-            float* dst = s + r * LDS_K + kk;
-            const int gr = row0 + r, gk = k0 + kk;
-            const bool full = (gr < rows) && (gk + 3 < K);
-            if (vec_ok) {
-                const float* src = g + (long long)(full ? gr : 0) * ld + (full ? gk : 0);
-                if (full || gr >= rows || gk >= K) { cp_async16(dst, src, full); continue; }
-            }
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-                dst[e] = (gr < rows && gk + e < K) ? g[(long long)gr * ld + gk + e] : 0.0f;
+    for (int it = 0; it < (CHUNKS + GTHREADS - 1) / GTHREADS; ++it) {
+        const int c = tid + it * GTHREADS;
+        if (CHUNKS % GTHREADS != 0 && c >= CHUNKS) break;
+        int r, kk, nr, nk;          // chunk origin (row, k) and its extent along (row, k)
+        float* dst;
+        if (KMAJ) { r = c >> 2; kk = (c & 3) * 4; nr = 1; nk = 4; dst = s + r * LDS_K + kk; }
+        else      { kk = c / (ROWS / 4); r = (c % (ROWS / 4)) * 4; nr = 4; nk = 1; dst = s + kk * LDS_R + r; }
+        const int gr = row0 + r, gk = k0 + kk;
+        const bool full = (gr + nr <= rows) && (gk + nk <= K);
+        const bool none = (gr >= rows) || (gk >= K);
+        if (vec_ok && (full || none)) {
+            const float* src = full ? (KMAJ ? g + (long long)gr * ld + gk : g + (long long)gk * ld + gr) : g;
+            cp_async16(dst, src, full);
+            continue;
         }
-    } else {
-        // 16 k x 128 rows = 512 float4 chunks
 #pragma unroll
-        for (int it = 0; it < 2; ++it) {
-            const int c = tid + it * GTHREADS;
-            const int kk = c >> 5, r = (c & 31) * 4;
-            float* dst = s + kk * LDS_MN + r;
-            const int gk = k0 + kk, gr = row0 + r;
-            const bool full = (gk < K) && (gr + 3 < rows);
-            if (vec_ok) {
-                const float* src = g + (long long)(full ? gk : 0) * ld + (full ? gr : 0);
-                if (full || gk >= K || gr >= rows) { cp_async16(dst, src, full); continue; }
-            }
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-                dst[e] = (gk < K && gr + e < rows) ? g[(long long)gk * ld + gr + e] : 0.0f;
+        for (int e = 0; e < 4; ++e) {
+            const int er = KMAJ ? gr : gr + e, ek = KMAJ ? gk + e : gk;
+            dst[e] = (er < rows && ek < K) ? (KMAJ ? g[(long long)er * ld + ek] : g[(long long)ek * ld + er]) : 0.0f;
         }
     }
 }
@@ -96,37 +88,43 @@ __device__ __forceinline__ void load_tile(float* s, const float* __restrict__ g,
 //   __device__ float operator()(int row, int col, float acc) const;   // stores; returns row-sum contribution
 //   static constexpr bool kRowSum;                                     // if true: row_partial(row, ntile, sum)
 //   __device__ void row_partial(int row, int ntile, float s) const;
+//
+// Accumulation: the tensor core adds into its fp32 accumulator with truncation, which biases long
+// chains (measured ~K*2^-25 relative).  MMAs therefore accumulate only G_FLUSH k-tiles (32 values of
+// k, 12 MMAs) from zero and the partial is then added into fp32 registers with round-to-nearest.
 template <bool A_KMAJOR, bool B_NMAJOR, class Epi>
 __global__ void __launch_bounds__(GTHREADS, 2) gemm_tf32x3_kernel(GemmShape p, Epi epi) {
     extern __shared__ __align__(16) float gsm[];
     float* sA = gsm;
     float* sB = gsm + GSTAGES * A_STAGE;
-    float* sRed = gsm + GSTAGES * (A_STAGE + B_STAGE);   // [GBM][4]
+    float* sRed = gsm + GSTAGES * (A_STAGE + B_STAGE);   // [GBM][2]
 
     const int M = p.n_rows_dev ? min(*p.n_rows_dev, p.M) : p.M;
     const int m0 = blockIdx.y * GBM, n0 = blockIdx.x * GBN;
     if (m0 >= M) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = (warp >> 2) * 64, wn = (warp & 3) * 32;
+    const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
     const int g = lane >> 2, t = lane & 3;
 
     const bool a_vec = ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0) && (p.lda % 4 == 0);
     const bool b_vec = ((reinterpret_cast<uintptr_t>(p.B) & 15) == 0) && (p.ldb % 4 == 0);
 
-    float acc[4][4][4];
+    float acc[G_MI][G_NJ][4], part[G_MI][G_NJ][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < G_MI; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < G_NJ; ++j)
 #pragma unroll
-            for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.0f;
+            for (int e = 0; e < 4; ++e) { acc[i][j][e] = 0.0f; part[i][j][e] = 0.0f; }
 
-    const int KT = (p.K + GBK - 1) / GBK;
+    const int kz0 = p.k_split > 0 ? blockIdx.z * p.k_split : 0;
+    const int Kend = p.k_split > 0 ? min(p.K, kz0 + p.k_split) : p.K;
+    const int KT = (Kend - kz0 + GBK - 1) / GBK;
     auto issue = [&](int kt) {
         if (kt < KT) {
             const int s = kt % GSTAGES;
-            load_tile<A_KMAJOR>(sA + s * A_STAGE, p.A, p.lda, m0, kt * GBK, M, p.K, a_vec);
-            load_tile<!B_NMAJOR>(sB + s * B_STAGE, p.B, p.ldb, n0, kt * GBK, p.N, p.K, b_vec);
+            load_tile<A_KMAJOR, GBM, LDS_AM>(sA + s * A_STAGE, p.A, p.lda, m0, kz0 + kt * GBK, M, Kend, a_vec);
+            load_tile<!B_NMAJOR, GBN, LDS_BN>(sB + s * B_STAGE, p.B, p.ldb, n0, kz0 + kt * GBK, p.N, Kend, b_vec);
         }
         cp_async_commit();
     };
@@ -140,48 +138,57 @@ __global__ void __launch_bounds__(GTHREADS, 2) gemm_tf32x3_kernel(GemmShape p, E
         const float* b = sB + (kt % GSTAGES) * B_STAGE;
 #pragma unroll
         for (int ks = 0; ks < GBK; ks += 8) {
-            uint32_t ah[4][4], al[4][4], bh[4][2], bl[4][2];
+            uint32_t ah[G_MI][4], al[G_MI][4], bh[G_NJ][2], bl[G_NJ][2];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < G_MI; ++i) {
                 const int r = wm + i * 16 + g;
                 float v0, v1, v2, v3;
                 if (A_KMAJOR) {
                     v0 = a[r * LDS_K + ks + t];       v1 = a[(r + 8) * LDS_K + ks + t];
                     v2 = a[r * LDS_K + ks + t + 4];   v3 = a[(r + 8) * LDS_K + ks + t + 4];
                 } else {
-                    v0 = a[(ks + t) * LDS_MN + r];     v1 = a[(ks + t) * LDS_MN + r + 8];
-                    v2 = a[(ks + t + 4) * LDS_MN + r]; v3 = a[(ks + t + 4) * LDS_MN + r + 8];
+                    v0 = a[(ks + t) * LDS_AM + r];     v1 = a[(ks + t) * LDS_AM + r + 8];
+                    v2 = a[(ks + t + 4) * LDS_AM + r]; v3 = a[(ks + t + 4) * LDS_AM + r + 8];
                 }
                 split_tf32(v0, ah[i][0], al[i][0]); split_tf32(v1, ah[i][1], al[i][1]);
                 split_tf32(v2, ah[i][2], al[i][2]); split_tf32(v3, ah[i][3], al[i][3]);
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < G_NJ; ++j) {
                 const int c = wn + j * 8 + g;
                 float v0, v1;
-                if (B_NMAJOR) { v0 = b[(ks + t) * LDS_MN + c]; v1 = b[(ks + t + 4) * LDS_MN + c]; }
+                if (B_NMAJOR) { v0 = b[(ks + t) * LDS_BN + c]; v1 = b[(ks + t + 4) * LDS_BN + c]; }
                 else          { v0 = b[c * LDS_K + ks + t];    v1 = b[c * LDS_K + ks + t + 4]; }
                 split_tf32(v0, bh[j][0], bl[j][0]); split_tf32(v1, bh[j][1], bl[j][1]);
             }
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < G_MI; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    mma_tf32(acc[i][j], al[i], bh[j]);
-                    mma_tf32(acc[i][j], ah[i], bl[j]);
-                    mma_tf32(acc[i][j], ah[i], bh[j]);
+                for (int j = 0; j < G_NJ; ++j) {
+                    mma_tf32(part[i][j], al[i], bh[j]);
+                    mma_tf32(part[i][j], ah[i], bl[j]);
+                    mma_tf32(part[i][j], ah[i], bh[j]);
                 }
+        }
+        if ((kt % G_FLUSH) == G_FLUSH - 1 || kt == KT - 1) {
+#pragma unroll
+            for (int i = 0; i < G_MI; ++i)
+#pragma unroll
+                for (int j = 0; j < G_NJ; ++j)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) { acc[i][j][e] += part[i][j][e]; part[i][j][e] = 0.0f; }
         }
     }
     cp_async_wait<0>();
 
     // ---- epilogue ----
+    if (p.k_split > 0) epi.at_z(blockIdx.z);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < G_MI; ++i) {
         float rs0 = 0.0f, rs1 = 0.0f;
         const int r0 = m0 + wm + i * 16 + g, r1 = r0 + 8;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < G_NJ; ++j) {
             const int c0 = n0 + wn + j * 8 + 2 * t;
             if (r0 < M) {
                 if (c0 < p.N) rs0 += epi(r0, c0, acc[i][j][0]);
@@ -196,17 +203,14 @@ __global__ void __launch_bounds__(GTHREADS, 2) gemm_tf32x3_kernel(GemmShape p, E
             rs0 += __shfl_xor_sync(0xffffffffu, rs0, 1); rs0 += __shfl_xor_sync(0xffffffffu, rs0, 2);
             rs1 += __shfl_xor_sync(0xffffffffu, rs1, 1); rs1 += __shfl_xor_sync(0xffffffffu, rs1, 2);
             if (t == 0) {
-                sRed[(wm + i * 16 + g) * 4 + (warp & 3)] = rs0;
-                sRed[(wm + i * 16 + g + 8) * 4 + (warp & 3)] = rs1;
+                sRed[(wm + i * 16 + g) * 2 + (warp & 1)] = rs0;
+                sRed[(wm + i * 16 + g + 8) * 2 + (warp & 1)] = rs1;
             }
         }
     }
     if (Epi::kRowSum) {
         __syncthreads();
-        if (tid < GBM && m0 + tid < M) {
-            const float s = ((sRed[tid * 4 + 0] + sRed[tid * 4 + 1]) + sRed[tid * 4 + 2]) + sRed[tid * 4 + 3];
-            epi.row_partial(m0 + tid, blockIdx.x, s);
-        }
+        if (tid < GBM && m0 + tid < M) epi.row_partial(m0 + tid, blockIdx.x, sRed[tid * 2 + 0] + sRed[tid * 2 + 1]);
     }
 }
 
@@ -220,7 +224,7 @@ inline cudaError_t launch_gemm(const GemmShape& p, const Epi& epi, cudaStream_t 
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    dim3 grid((p.N + GBN - 1) / GBN, (p.M + GBM - 1) / GBM);
+    dim3 grid((p.N + GBN - 1) / GBN, (p.M + GBM - 1) / GBM, p.k_split > 0 ? (p.K + p.k_split - 1) / p.k_split : 1);
     kern<<<grid, GTHREADS, GEMM_SMEM_BYTES, st>>>(p, epi);
     return cudaGetLastError();
 }
@@ -232,15 +236,18 @@ struct EpiStd {
     static constexpr bool kRowSum = false;
     float* C; long long ldc;
     const float* bias;               // [N] or null
-    const float* mask; long long ldm; // out = mask[row,col] > 0 ? out : 0  (relu' gate) or null
+    const float* mask; long long ldm; // out = mask[row/mask_div,col] > 0 ? out : 0  (relu' gate) or null
     const float* add; long long ldadd; // out += add[row,col] or null
     float alpha; int relu;
+    int mask_div = 1;                  // rows of the mask are shared by mask_div consecutive output rows
+    long long c_zstride = 0;           // split-K: slice z writes to C + z*c_zstride
+    __device__ __forceinline__ void at_z(int z) { C += (long long)z * c_zstride; }
     __device__ __forceinline__ float operator()(int row, int col, float acc) const {
         float v = alpha * acc;
         if (bias) v += bias[col];
         if (add) v += add[(long long)row * ldadd + col];
         if (relu) v = fmaxf(v, 0.0f);
-        if (mask) v = mask[(long long)row * ldm + col] > 0.0f ? v : 0.0f;
+        if (mask) v = mask[(long long)(row / mask_div) * ldm + col] > 0.0f ? v : 0.0f;
         C[(long long)row * ldc + col] = v;
         return 0.0f;
     }

@@ -41,4 +41,19 @@ int target_value_and_grad(const mfm_target_t& T, int n, const float* x, float* l
 int target_field_terms(const mfm_target_t& T, int n, const float* x, const float* z, const float* zkinv, float clip,
                        float* gc, float* hvc, float* hdc, const int* n_rows_dev, cudaStream_t st);
 
+// ---- vector field (flow.cu) -------------------------------------------------------------------
+struct FieldBufs {
+    float *ff, *h0, *cat, *h2, *gt, *h5, *h6, *gc, *hx, *ta, *tb, *zw2, *zkinv, *divpart;
+    float *tan_a, *tan_b;   // exact path [n*d, H]
+};
+size_t field_bufs_bytes(const mfm_field_t& F, const mfm_target_t& T, int n, bool hutch);
+bool field_bufs_take(FieldBufs& B, Workspace& w, const mfm_field_t& F, int n, bool hutch);
+// C[n,out] = relu?(A[n,in] W[in,out] + bias) gated by mask (relu' of another activation)
+int dense(int n, int in, int out, const float* A, long long lda, const float* W, const float* bias, int relu,
+          float* C, long long ldc, const float* mask, long long ldm, int mask_div, cudaStream_t st);
+// out_v = sgn * v(x, t); out_l = -sgn * div v (optional; z != null -> Hutchinson, else exact trace).
+// Leaves the activations (ff, h0, cat=[s_x|s_t], h2, gt, h5, h6, gc) in B for a backward pass.
+int field_eval(const mfm_field_t& F, const mfm_target_t& T, int n, const float* x, const float* tfield,
+               const float* z, float sgn, float* out_v, float* out_l, FieldBufs& B, cudaStream_t st);
+
 }  // namespace mfm

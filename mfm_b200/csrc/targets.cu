@@ -81,6 +81,7 @@ struct EpiPinesGrad {
     __device__ __forceinline__ void row_partial(int row, int tile, float s) const {
         if (partial) partial[(long long)row * n_tiles + tile] = s;
     }
+    __device__ __forceinline__ void at_z(int) {}
 };
 
 struct EpiPinesField {
@@ -101,6 +102,7 @@ struct EpiPinesField {
         return 0.0f;
     }
     __device__ __forceinline__ void row_partial(int, int, float) const {}
+    __device__ __forceinline__ void at_z(int) {}
 };
 
 int pines_n_tiles(int d) { return gemm_n_tiles(d); }

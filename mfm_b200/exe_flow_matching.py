@@ -1,0 +1,291 @@
+"""Hot-path entry points — B200 drop-in for the reference's exe_flow_matching.py.
+
+Mirrors (same names, argument meaning, return structure):
+  VectorFieldNet            exe_flow_matching.py:56-90     (parameter container + apply)
+  create_train_state        :93-186   (FM loss, AdamW -> clip -> apply_if_finite)
+  create_learning_rate_fn   :189-198
+  create_train_data_gn      :201-318  -> (train_data_generator, init_fn, transform_and_logdet)
+  run                       :321-450  (hot loop incl. adaptive tempering; post-training metrics/plots
+                                        are out of scope)
+Everything numeric happens in CUDA kernels behind the C-ABI (include/mfm_b200.h).
+"""
+from __future__ import annotations
+
+import logging
+import time
+from types import SimpleNamespace
+from typing import Callable, NamedTuple, Optional
+
+import numpy as np
+import torch
+
+from . import _lib, random as mrandom
+from .bblackjax.mcmc.mala import MALAInfo, MALAState, init, mala_step
+from .distributions import DeviceLogDensity, Distribution, GaussianMixture, IndepGaussian
+
+logger = logging.getLogger(__name__)
+
+ref_dists = {
+    "stdgauss": lambda dim, device=None: IndepGaussian(dim, device=device),
+    "widegauss": lambda dim, device=None: IndepGaussian(dim, var=5.0, device=device),
+}
+
+
+# ------------------------------------------------------------------------------------------------
+# VectorFieldNet
+# ------------------------------------------------------------------------------------------------
+def layer_shapes(dim: int, hidden: int, fourier_dim: int):
+    """(in, out) of Dense_0..Dense_7 in flax construction order (exe_flow_matching.py:73-86)."""
+    F, H, d = fourier_dim, hidden, dim
+    return [(2 * F, H), (H, H), (d, H), (H, H), (H, d), (2 * H, H), (H, H), (H, d)]
+
+
+class VectorFieldParams:
+    """Flat fp32 parameter buffer + offsets; converts from/to the flax dict layout
+    {'params': {'Dense_i': {'kernel': [in,out], 'bias': [out]}}}."""
+
+    def __init__(self, dim, hidden, fourier_dim, device):
+        self.dim, self.hidden, self.fourier_dim = dim, hidden, fourier_dim
+        self.shapes = layer_shapes(dim, hidden, fourier_dim)
+        self.w_off, self.b_off = [], []
+        off = 0
+        for fi, fo in self.shapes:
+            self.w_off.append(off); off += fi * fo
+            off = (off + 3) // 4 * 4                      # 16-byte aligned slices
+            self.b_off.append(off); off += fo
+            off = (off + 3) // 4 * 4
+        self.n_params = off
+        self.device = torch.device(device)
+        self.flat = torch.zeros(off, dtype=torch.float32, device=self.device)
+        mask = torch.zeros(off, dtype=torch.uint8)
+        for (fi, fo), wo in zip(self.shapes, self.w_off):
+            mask[wo:wo + fi * fo] = 1                     # decay kernels only (decay_mask_fn, :116-127)
+        self.decay_mask = mask.to(self.device)
+
+    def kernel(self, i):
+        fi, fo = self.shapes[i]
+        return self.flat[self.w_off[i]:self.w_off[i] + fi * fo].view(fi, fo)
+
+    def bias(self, i):
+        return self.flat[self.b_off[i]:self.b_off[i] + self.shapes[i][1]]
+
+    def load_dict(self, params: dict):
+        p = params["params"]
+        for i in range(8):
+            self.kernel(i).copy_(torch.as_tensor(np.asarray(p[f"Dense_{i}"]["kernel"], np.float32)))
+            self.bias(i).copy_(torch.as_tensor(np.asarray(p[f"Dense_{i}"]["bias"], np.float32)))
+        return self
+
+    def to_dict(self, flat: Optional[torch.Tensor] = None) -> dict:
+        src = self.flat if flat is None else flat
+        out = {}
+        for i, (fi, fo) in enumerate(self.shapes):
+            out[f"Dense_{i}"] = {
+                "kernel": src[self.w_off[i]:self.w_off[i] + fi * fo].view(fi, fo).cpu().numpy().copy(),
+                "bias": src[self.b_off[i]:self.b_off[i] + fo].cpu().numpy().copy(),
+            }
+        return {"params": out}
+
+
+class VectorFieldNet:
+    """Device vector field v(x, t) = nn_xt + nn_t * clip(grad logprob(x)) (exe_flow_matching.py:56-90).
+
+    fourier_random is a module attribute (not a parameter), grad_logprob is fixed to the untempered
+    target (`jax.grad(dist.logprob)`, :351) and therefore given as the distribution itself."""
+
+    def __init__(self, fourier_random: torch.Tensor, dist: Distribution, hidden_x, hidden_t, hidden_xt,
+                 act_fn="relu", grad_clip: Optional[float] = None):
+        hs = list(hidden_x) + list(hidden_t) + list(hidden_xt)
+        if len(hidden_x) != 2 or len(hidden_t) != 2 or len(hidden_xt) != 2 or len(set(hs)) != 1:
+            raise NotImplementedError("the CUDA path implements the configured shape: three 2-layer branches of equal width")
+        if act_fn not in ("relu", torch.relu):
+            raise NotImplementedError("only relu (the reference default) is implemented on device")
+        self.dist = dist
+        self.hidden = hs[0]
+        self.fourier_random = fourier_random.to(torch.float32).contiguous()
+        self.grad_clip = float(grad_clip) if grad_clip else 0.0
+
+    def init(self, rng_key, x0=None, t0=None, head_scale: float = 0.0) -> VectorFieldParams:
+        """Parameter initialisation.  NOT flax's RNG-folded lecun_normal (a 'next' row): fan-in
+        scaled normals from jax.random-compatible streams; nn_t / nn_xt heads are zero-initialised as
+        in the reference (:81,86) unless head_scale > 0."""
+        P = VectorFieldParams(self.dist.dim, self.hidden, self.fourier_random.numel(), self.fourier_random.device)
+        keys = mrandom.split(rng_key, 8)
+        for i, (fi, fo) in enumerate(P.shapes):
+            scale = (1.0 / np.sqrt(fi)) * (head_scale if i in (4, 7) else 1.0)
+            if scale > 0:
+                P.kernel(i).copy_(mrandom.normal(keys[i], (fi, fo)) * scale)
+        return P
+
+    def field_desc(self, P: VectorFieldParams, flat: Optional[torch.Tensor] = None) -> _lib.FieldDesc:
+        d = _lib.FieldDesc()
+        d.dim, d.hidden, d.fourier_dim = P.dim, P.hidden, P.fourier_dim
+        d.params = (P.flat if flat is None else flat).data_ptr()
+        for i in range(8):
+            d.w_off[i], d.b_off[i] = P.w_off[i], P.b_off[i]
+        d.n_params = P.n_params
+        d.omega = self.fourier_random.data_ptr()
+        d.grad_clip = self.grad_clip
+        return d
+
+    def apply(self, P: VectorFieldParams, x: torch.Tensor, t: torch.Tensor, z: Optional[torch.Tensor] = None,
+              hutch: bool = False, want_div: bool = False):
+        """Batched model.apply(params, x, t): x [N,d], t [N] -> v [N,d] (and div v [N])."""
+        lib = _lib.load()
+        n, d = x.shape
+        t = t.to(torch.float32).reshape(-1).contiguous()
+        if t.numel() == 1:
+            t = t.expand(n).contiguous()
+        v = torch.empty_like(x)
+        div = torch.empty(n, dtype=torch.float32, device=x.device) if want_div else None
+        fd, td = self.field_desc(P), self.dist._desc(1.0)
+        od = _lib.OdeOpts(1e-5, 1e-5, 1000, 1 if hutch else 0, 2)
+        ws = _lib.workspace(lib.mfm_ode_workspace_bytes(fd, td, od, n), x.device, "ode")
+        _lib.check(lib.mfm_field_eval(fd, td, od, n, _lib.ptr(x.contiguous()), _lib.ptr(t),
+                                      _lib.ptr(z.contiguous()) if z is not None else None, _lib.ptr(v), _lib.ptr(div),
+                                      _lib.ptr(ws), ws.numel(), _lib.stream()))
+        return (v, div) if want_div else v
+
+
+# ------------------------------------------------------------------------------------------------
+# optimizer / train state
+# ------------------------------------------------------------------------------------------------
+def create_learning_rate_fn(num_train_steps: int, num_warmup_steps: int, learning_rate: float) -> Callable[[int], float]:
+    """Linear warmup then linear decay (exe_flow_matching.py:189-198).  optax.linear_schedule with
+    transition_steps<=0 is constant init_value and join_schedules switches at the boundary, so
+    warmup_steps=0 is pure decay lr*(1-step/num_train_steps)."""
+    if num_warmup_steps != 0:
+        raise NotImplementedError("the device optimizer implements warmup_steps=0 (every reference config)")
+
+    def schedule(step):
+        s = min(max(int(step), 0), num_train_steps)
+        return learning_rate * (1.0 - s / num_train_steps)
+
+    schedule.base, schedule.total = float(learning_rate), int(num_train_steps)
+    return schedule
+
+
+class TrainState:
+    """flax TrainState analogue: params + AdamW moments + counters, all on device."""
+
+    def __init__(self, model: VectorFieldNet, params: VectorFieldParams, lr_fn, args):
+        self.model, self.P, self.lr_fn, self.args = model, params, lr_fn, args
+        self.params = params
+        dev = params.flat.device
+        self.mu = torch.zeros_like(params.flat)
+        self.nu = torch.zeros_like(params.flat)
+        self.grads = torch.zeros_like(params.flat)
+        self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
+        # [adam count, notfinite_count, total_notfinite, last_finite, scratch x4]
+        self.opt_state = torch.tensor([0, 0, 0, 1, 0, 0, 0, 0], dtype=torch.int32, device=dev)
+        self.step = 0
+        self.ref_dist = ref_dists[args.ref_dist](params.dim, device=dev)
+
+    # loss_fn(rng_key, samples, params) of the reference (flow_matching_loss, :171-179)
+    def loss_and_grad(self, rng_key, positions, chain_offset=0, n_total=None):
+        lib = _lib.load()
+        a = self.args
+        if not a.cond_flow or a.ot_cond_flow:
+            raise NotImplementedError("device FM loss implements cond_flow=True, ot_cond_flow=False (reference defaults)")
+        n = positions.shape[0]
+        fd, td = self.model.field_desc(self.P), self.model.dist._desc(1.0)
+        ws = _lib.workspace(lib.mfm_fm_workspace_bytes(fd, td, n), positions.device, "fm")
+        _lib.check(lib.mfm_fm_loss_grad(fd, td, _lib.ptr(rng_key), n, chain_offset, n_total if n_total is not None else n,
+                                        float(a.sigma), _lib.ptr(positions.contiguous()), _lib.ptr(self.loss),
+                                        _lib.ptr(self.grads), _lib.ptr(ws), ws.numel(), _lib.stream()))
+        return self.loss, self.grads
+
+    def apply_gradients(self, grads=None):
+        lib = _lib.load()
+        a = self.args
+        g = self.grads if grads is None else grads
+        _lib.check(lib.mfm_adamw_step(_lib.ptr(self.P.flat), _lib.ptr(g), _lib.ptr(self.mu), _lib.ptr(self.nu),
+                                      _lib.ptr(self.P.decay_mask), self.P.n_params, _lib.ptr(self.opt_state),
+                                      self.lr_fn.base, self.lr_fn.total, a.adam_beta1, a.adam_beta2, a.adam_epsilon,
+                                      a.weight_decay, a.gradient_clip, 10, _lib.stream()))
+        self.step += 1
+        return self
+
+
+def create_train_state(model: VectorFieldNet, vector_field_param: VectorFieldParams, learning_rate_fn, args) -> TrainState:
+    return TrainState(model, vector_field_param, learning_rate_fn, args)
+
+
+# ------------------------------------------------------------------------------------------------
+# MALA / flow-MH data generator
+# ------------------------------------------------------------------------------------------------
+def create_train_data_gn(dist: Distribution, model: VectorFieldNet, ode_opts, args, chain_offset: int = 0,
+                         n_total: Optional[int] = None):
+    """Returns (train_data_generator, init_fn, transform_and_logdet) like the reference (:201-318).
+
+    ode_opts: SimpleNamespace(rtol, atol, mxstep, n_times).  chain_offset/n_total describe this
+    rank's shard of the ensemble (keys are rows of split(rng_key, n_total))."""
+    lib = _lib.load()
+    dim = dist.dim
+    opts = _lib.OdeOpts(float(ode_opts.rtol), float(ode_opts.atol), int(ode_opts.mxstep), 1 if args.hutchs else 0,
+                        int(ode_opts.n_times))
+    if args.num_importance_samples > 0:
+        raise NotImplementedError("conditional importance sampling is not on the configured hot path")
+    variant = _lib.FLOW_INDEP_MH if args.num_importance_samples < 0 else _lib.FLOW_RW_MH
+    m = args.mcmc_per_flow_steps
+    last_stats = {}
+
+    def _ode(direction, key, sample, P, stats=None):
+        """key: uint32[2] shared probe key (as the reference's un-vmapped call) or uint32[N,2]."""
+        single = sample.dim() == 1
+        x = (sample[None] if single else sample).contiguous()
+        n = x.shape[0]
+        keys = key if key.dim() == 2 else key[None].expand(n, 2).contiguous()
+        y1 = torch.empty_like(x)
+        ldj = torch.empty(n, dtype=torch.float32, device=x.device)
+        fd, td = model.field_desc(P), dist._desc(1.0)
+        ws = _lib.workspace(lib.mfm_ode_workspace_bytes(fd, td, opts, n), x.device, "ode")
+        _lib.check(lib.mfm_ode_flow(fd, td, opts, direction, n, _lib.ptr(keys.contiguous()), _lib.ptr(x), _lib.ptr(y1),
+                                    _lib.ptr(ldj), _lib.ptr(stats), _lib.ptr(ws), ws.numel(), _lib.stream()))
+        return (y1[0], ldj[0]) if single else (y1, ldj)
+
+    def transform_and_logdet(key, ref_sample, vector_field_param, stats=None):
+        return _ode(+1, key, ref_sample, vector_field_param, stats)
+
+    def inverse_and_logdet(key, target_sample, vector_field_param, stats=None):
+        return _ode(-1, key, target_sample, vector_field_param, stats)
+
+    def flow_step(rng_key, states: MALAState, logprob: DeviceLogDensity, P, per_chain_keys=False, inplace=False):
+        x, l, g = states
+        if not inplace:
+            x, l, g = x.clone(), l.clone(), g.clone()
+        n = x.shape[0]
+        dev = x.device
+        acc_rate = torch.empty(n, dtype=torch.float32, device=dev)
+        is_acc = torch.empty(n, dtype=torch.uint8, device=dev)
+        prop = torch.empty_like(x)
+        weight = torch.empty(n, dtype=torch.float32, device=dev)
+        stats = torch.zeros(4, dtype=torch.int32, device=dev)
+        fd, td = model.field_desc(P), logprob.desc()
+        ws = _lib.workspace(lib.mfm_flow_mh_workspace_bytes(fd, td, opts, n), dev, "flow")
+        _lib.check(lib.mfm_flow_mh_step(fd, td, opts, variant, _lib.ptr(rng_key.contiguous()), 1 if per_chain_keys else 0,
+                                        n, chain_offset, n_total if n_total is not None else n, _lib.ptr(x), _lib.ptr(l),
+                                        _lib.ptr(g), _lib.ptr(acc_rate), _lib.ptr(is_acc), _lib.ptr(prop), _lib.ptr(weight),
+                                        _lib.ptr(stats), _lib.ptr(ws), ws.numel(), _lib.stream()))
+        last_stats["ode"] = stats
+        return MALAState(x, l, g), MALAInfo(acc_rate, is_acc.bool(), prop, weight)
+
+    def train_data_generator(rng_key, states: MALAState, count: int, vector_field_param, beta: float = 1.0,
+                             inplace: bool = False):
+        logprob = dist.tempered(beta)
+        if 0 < m < 1:
+            is_flow = count % (int(1 / m) + 1) != 0          # roles inverted for fractional m (:304-309)
+        else:
+            is_flow = count % (int(m) + 1) == 0              # :311
+        if is_flow:
+            return flow_step(rng_key, states, logprob, vector_field_param, inplace=inplace)
+        return mala_step(logprob, rng_key, states, args.step_size, per_chain_keys=False, chain_offset=chain_offset,
+                         n_total=n_total, inplace=inplace)
+
+    def init_fn(init_positions, beta: float = 1.0):
+        return init(init_positions, dist.tempered(beta))
+
+    train_data_generator.flow_step = flow_step
+    train_data_generator.inverse_and_logdet = inverse_and_logdet
+    train_data_generator.last_stats = last_stats
+    return train_data_generator, init_fn, transform_and_logdet

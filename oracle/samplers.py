@@ -33,8 +33,9 @@ def mala_init(x, target, beta=1.0):
     return MALAState(x, l, g)
 
 
-def mala_step(keys, state, target, step_size, beta=1.0, noise=None):
-    """vmap(kernel)(keys, states).  keys: uint32 [N,2]."""
+def mala_step(keys, state, target, step_size, beta=1.0, noise=None, rng_dtype=None):
+    """vmap(kernel)(keys, states).  keys: uint32 [N,2].  rng_dtype: dtype of the random draws
+    (float32 = x64 off); arithmetic runs in state.position.dtype."""
     x, l, g = state
     dt = x.dtype
     N, d = x.shape
@@ -42,8 +43,9 @@ def mala_step(keys, state, target, step_size, beta=1.0, noise=None):
     ki = np.empty((N, 2), np.uint32); kr = np.empty((N, 2), np.uint32)
     for n in range(N):
         ki[n], kr[n] = tf.split(keys[n])
+    rdt = np.dtype(rng_dtype or dt)
     if noise is None:
-        noise = tf.vmap_normal(ki, d, dt)
+        noise = tf.vmap_normal(ki, d, rdt).astype(dt)
     xn = x + h * g + np.sqrt(dt.type(2) * h) * noise
     ln, gn = target.value_and_grad(xn, beta)
     quarter = dt.type(0.25 * (1.0 / float(step_size)))   # python-float arithmetic, mala.py:79
@@ -55,7 +57,7 @@ def mala_step(keys, state, target, step_size, beta=1.0, noise=None):
         delta = e_prev - e_new
         delta = np.where(np.isnan(delta), -np.inf, delta).astype(dt)
         p_accept = np.minimum(np.exp(delta), dt.type(1))
-        u = np.array([tf.uniform(kr[n], (), dt) for n in range(N)], dt)
+        u = np.array([tf.uniform(kr[n], (), rdt) for n in range(N)], dt)
         acc = u < p_accept
         weight = np.exp(ln + quarter * (th_prev * th_prev).sum(1))
     new = MALAState(np.where(acc[:, None], xn, x), np.where(acc, ln, l), np.where(acc[:, None], gn, g))
@@ -66,13 +68,14 @@ class Flow:
     """Bundles (params, omega, target, config) for the CNF push/pull."""
 
     def __init__(self, params, omega, target, hutch, rtol=1e-5, atol=1e-5, mxstep=1000,
-                 grad_clip=None, ts=(0.0, 1.0)):
+                 grad_clip=None, ts=(0.0, 1.0), rng_dtype=None):
+        self.rng_dtype = rng_dtype
         self.params, self.omega, self.target = params, omega, target
         self.hutch, self.rtol, self.atol, self.mxstep = hutch, rtol, atol, mxstep
         self.grad_clip, self.ts = grad_clip, ts
 
     def _probe(self, keys, d, dt):
-        return tf.vmap_normal(keys, d, dt) if self.hutch else None
+        return tf.vmap_normal(keys, d, np.dtype(self.rng_dtype or dt)).astype(dt) if self.hutch else None
 
     def transform_and_logdet(self, keys, u, stats=None, z=None):
         """forward ODE of (v(u,t), -div) from t=0 to 1 (exe_flow_matching.py:206-221)."""
@@ -120,14 +123,15 @@ def rw_flow_mh_step(keys, state, target, flow: Flow, beta=1.0, stats=None):
     key_gen, key_acc, key_h1, key_h2 = _split4(keys)
     s_inv, s_fwd = {}, {}
     u0, V0 = flow.inverse_and_logdet(key_h2, x, s_inv)
+    rdt = np.dtype(flow.rng_dtype or dt)
     scale = dt.type(2.38) / np.sqrt(dt.type(d))
-    up = u0 + scale * tf.vmap_normal(key_gen, d, dt)
+    up = u0 + scale * tf.vmap_normal(key_gen, d, rdt).astype(dt)
     xp, Vp = flow.transform_and_logdet(key_h1, up, s_fwd)
     lp, gp = target.value_and_grad(xp, beta)
     with np.errstate(over="ignore", invalid="ignore"):
         log_acc = lp - Vp - l - V0
         acc_prob = np.exp(log_acc)
-        u = np.array([tf.uniform(key_acc[n], (), dt) for n in range(N)], dt)
+        u = np.array([tf.uniform(key_acc[n], (), rdt) for n in range(N)], dt)
         acc = u <= acc_prob
     new = MALAState(np.where(acc[:, None], xp, x), np.where(acc, lp, l), np.where(acc[:, None], gp, g))
     if stats is not None:
@@ -141,14 +145,15 @@ def indep_flow_mh_step(keys, state, target, flow: Flow, ref, beta=1.0, stats=Non
     dt = x.dtype
     N, d = x.shape
     key_gen, key_acc, key_h1, key_h2 = _split4(keys)
-    up = ref.sample(key_gen, dt)
+    rdt = np.dtype(flow.rng_dtype or dt)
+    up = ref.sample(key_gen, rdt).astype(dt)
     xp, Vp = flow.transform_and_logdet(key_h1, up)
     u0, V0 = flow.inverse_and_logdet(key_h2, x)
     lp, gp = target.value_and_grad(xp, beta)
     with np.errstate(over="ignore", invalid="ignore"):
         log_acc = lp - ref.loglik(up) - Vp + ref.loglik(u0) - V0 - l
         acc_prob = np.exp(log_acc)
-        u = np.array([tf.uniform(key_acc[n], (), dt) for n in range(N)], dt)
+        u = np.array([tf.uniform(key_acc[n], (), rdt) for n in range(N)], dt)
         acc = u <= acc_prob
     new = MALAState(np.where(acc[:, None], xp, x), np.where(acc, lp, l), np.where(acc[:, None], gp, g))
     if stats is not None:

@@ -104,14 +104,16 @@ def field_and_div(params, omega, x, t, target, hutch_z=None, grad_clip=None):
     return v, div + (c["gt"] * hd).sum(1)
 
 
-def fm_batch(key, samples, ref_sampler, sigma):
-    """cond_flow_fn (exe_flow_matching.py:151-169), cond_flow=True, ot_cond_flow=False."""
+def fm_batch(key, samples, ref_sampler, sigma, rng_dtype=None):
+    """cond_flow_fn (exe_flow_matching.py:151-169), cond_flow=True, ot_cond_flow=False.
+    rng_dtype: dtype of the random draws (float32 = x64 off); arithmetic in samples.dtype."""
     N, d = samples.shape
     dt = samples.dtype
+    rdt = np.dtype(rng_dtype or dt)
     key_time, key_ref, key_gauss, _ = tf.split(key, 4)
-    times = tf.uniform(key_time, (N, 1), dt)
-    ref = ref_sampler(tf.split(key_ref, N), dt)
-    eps = tf.normal(key_gauss, (N, d), dt)
+    times = tf.uniform(key_time, (N, 1), rdt).astype(dt)
+    ref = ref_sampler(tf.split(key_ref, N), rdt).astype(dt)
+    eps = tf.normal(key_gauss, (N, d), rdt).astype(dt)
     xt = dt.type(sigma) * eps + times * samples + (dt.type(1) - times) * ref
     target = samples - ref
     return times[:, 0], xt, target

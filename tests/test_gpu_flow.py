@@ -1,0 +1,165 @@
+"""VectorFieldNet / divergence / adaptive Dopri5 / flow-MH vs the float64 oracle.
+
+Tolerances: field values and divergences 1e-4 relative (north_star); ODE outputs 5e-4 relative
+(the solver itself runs at rtol=atol=1e-5 and CUDA computes in float32, so step sequences may
+differ by a step); accept decisions identical outside a band around the threshold."""
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import samplers as OS, targets as OT, threefry as tf, vector_field as VF
+from tests.helpers import key_dev, make_targets, rel_err, to_dev
+
+pytestmark = pytest.mark.gpu
+
+CFG = {  # name: (hidden, hutch, n_times, grad_clip, n chains)
+    "4-mode": (128, False, 5, None, 24),
+    "gmm16": (128, True, 2, None, 24),
+    "phi-four": (128, False, 2, None, 12),
+    "pines": (1024, True, 2, 1.0, 6),
+}
+
+
+@pytest.fixture(scope="module")
+def setups(cuda, lib):
+    from mfm_b200 import exe_flow_matching as E
+    out = {}
+    for name, ot, dd in make_targets(cuda):
+        H, hutch, n_times, clip, n = CFG[name]
+        rng = np.random.default_rng(hash(name) % 1000)
+        params = VF.init_params(rng, ot.dim, H, 128, head_scale=0.5 if ot.dim < 100 else 0.2)
+        omega = rng.standard_normal(128).astype(np.float32)
+        model = E.VectorFieldNet(to_dev(omega, cuda), dd, [H, H], [H, H], [H, H], "relu", clip)
+        P = E.VectorFieldParams(ot.dim, H, 128, cuda).load_dict(params)
+        out[name] = SimpleNamespace(ot=ot, dd=dd, params=params, omega=omega, model=model, P=P, hutch=hutch,
+                                    n_times=n_times, clip=clip, n=n)
+    return out
+
+
+def _positions(s, n, seed=1):
+    x = s.ot.init_positions(tf.PRNGKey(seed), n, np.float32)
+    return x.astype(np.float64)
+
+
+@pytest.mark.parametrize("name", list(CFG))
+def test_field_and_divergence(cuda, setups, name):
+    s = setups[name]
+    n = s.n
+    x = _positions(s, n)
+    t = np.linspace(0.0, 1.3, n)
+    z = np.random.default_rng(5).standard_normal(x.shape) if s.hutch else None
+    v_ref, div_ref = VF.field_and_div(s.params, s.omega, x, t, s.ot, z, s.clip)
+    v, div = s.model.apply(s.P, to_dev(x, cuda), to_dev(t, cuda), to_dev(z, cuda) if s.hutch else None,
+                           hutch=s.hutch, want_div=True)
+    assert rel_err(v.cpu().numpy(), v_ref) < 1e-4, name
+    assert np.abs(div.cpu().numpy() - div_ref).max() < 1e-4 * max(np.abs(div_ref).max(), 1.0), name
+
+
+@pytest.mark.parametrize("name", list(CFG))
+def test_roundtrip_param_dict(cuda, setups, name):
+    s = setups[name]
+    back = s.P.to_dict()
+    for i in range(8):
+        assert np.array_equal(back["params"][f"Dense_{i}"]["kernel"], s.params["params"][f"Dense_{i}"]["kernel"])
+
+
+def _flow(s):
+    ts = np.linspace(0.0, 1.0, s.n_times)
+    return OS.Flow(s.params, s.omega, s.ot, s.hutch, 1e-5, 1e-5, 1000, s.clip, ts, rng_dtype=np.float32)
+
+
+def _gn(s, mcmc=10, nis=0, step=0.1):
+    from mfm_b200 import exe_flow_matching as E
+    args = SimpleNamespace(hutchs=s.hutch, num_importance_samples=nis, mcmc_per_flow_steps=mcmc, step_size=step)
+    opts = SimpleNamespace(rtol=1e-5, atol=1e-5, mxstep=1000, n_times=s.n_times)
+    return E.create_train_data_gn(s.dd, s.model, opts, args)
+
+
+@pytest.mark.parametrize("name", list(CFG))
+def test_push_pull_vs_oracle(cuda, setups, name):
+    s = setups[name]
+    n = s.n
+    gen, init_fn, transform_and_logdet = _gn(s)
+    flow = _flow(s)
+    keys = tf.split(tf.PRNGKey(77), n)
+    u = tf.vmap_normal(tf.split(tf.PRNGKey(4), n), s.ot.dim).astype(np.float64)
+    st_o = {}
+    x_ref, ldj_ref = flow.transform_and_logdet(keys, u, st_o)
+    stats = torch.zeros(4, dtype=torch.int32, device=cuda)
+    x, ldj = transform_and_logdet(key_dev(keys, cuda), to_dev(u, cuda), s.P, stats)
+    assert rel_err(x.cpu().numpy(), x_ref) < 5e-4, name
+    assert np.abs(ldj.cpu().numpy() - ldj_ref).max() < 5e-4 * max(np.abs(ldj_ref).max(), 1.0), name
+    acc, tried, mx, nev = stats.cpu().tolist()
+    assert abs(tried - int(st_o["n_try"].sum())) <= max(2, 0.1 * tried), (tried, st_o["n_try"].sum())
+    # inverse direction + round trip
+    u_ref, v0_ref = flow.inverse_and_logdet(keys, x_ref)
+    ub, v0 = gen.inverse_and_logdet(key_dev(keys, cuda), to_dev(x_ref, cuda), s.P)
+    assert rel_err(ub.cpu().numpy(), u_ref) < 5e-4, name
+    assert np.abs(v0.cpu().numpy() - v0_ref).max() < 5e-4 * max(np.abs(v0_ref).max(), 1.0), name
+    if not s.hutch:   # exact divergence: pull(push(u)) == u and the log-dets cancel
+        assert rel_err(ub.cpu().numpy(), u) < 1e-3
+        assert np.abs(v0.cpu().numpy() + ldj_ref).max() < 1e-3 * max(np.abs(ldj_ref).max(), 1.0)
+
+
+def test_identity_flow_zero_heads(cuda, setups):
+    """Reference initialisation (zero nn_t / nn_xt kernels, :81,86): v == bias, 7 growing steps."""
+    from mfm_b200 import exe_flow_matching as E
+    s = setups["phi-four"]
+    P = E.VectorFieldParams(64, 128, 128, cuda).load_dict(s.params)
+    P.kernel(4).zero_(); P.kernel(7).zero_(); P.bias(4).zero_(); P.bias(7).zero_()
+    gen, _, push = _gn(s)
+    u = to_dev(np.random.default_rng(0).standard_normal((8, 64)), cuda)
+    stats = torch.zeros(4, dtype=torch.int32, device=cuda)
+    x, ldj = push(key_dev(tf.split(tf.PRNGKey(1), 8), cuda), u, P, stats)
+    assert torch.allclose(x, u, atol=1e-6) and torch.all(ldj == 0)
+    assert stats.cpu().tolist()[2] == 7       # dt: 1e-6 * 10^k until t >= 1
+
+
+@pytest.mark.parametrize("name,nis", [("4-mode", 0), ("gmm16", 0), ("phi-four", 0), ("pines", 0), ("gmm16", -1)])
+def test_flow_mh_step(cuda, setups, name, nis):
+    from mfm_b200.bblackjax.mcmc import mala as M
+    s = setups[name]
+    n = s.n
+    gen, init_fn, _ = _gn(s, nis=nis)
+    flow = _flow(s)
+    x0 = _positions(s, n, seed=3)
+    beta = 0.7
+    st_d = init_fn(to_dev(x0, cuda), beta)
+    st_o = OS.mala_init(x0, s.ot, beta)
+    key = tf.PRNGKey(2024)
+    keys = tf.split(key, n)
+    dbg = {}
+    if nis < 0:
+        new_o, info_o = OS.indep_flow_mh_step(keys, st_o, s.ot, flow, OT.IndepGaussian(s.ot.dim), beta, dbg)
+    else:
+        new_o, info_o = OS.rw_flow_mh_step(keys, st_o, s.ot, flow, beta, dbg)
+    new_d, info_d = gen.flow_step(key_dev(key, cuda), st_d, s.dd.tempered(beta), s.P)
+    la = dbg["log_acc"]
+    prop = info_d.proposed_position.cpu().numpy()
+    assert rel_err(prop, info_o.proposed_position) < 1e-3, name
+    acc_d = info_d.is_accepted.cpu().numpy(); acc_o = info_o.is_accepted
+    with np.errstate(divide="ignore"):
+        band = np.abs(la - np.log(dbg["u"])) < 2e-3 * np.maximum(1.0, np.abs(la)) + 2e-3 * np.abs(st_o.logdensity)
+    assert ((acc_d == acc_o) | band).all(), name
+    with np.errstate(over="ignore", divide="ignore"):
+        la_d = np.log(info_d.acceptance_rate.cpu().numpy().astype(np.float64))
+    fin = np.isfinite(la) & np.isfinite(la_d) & (np.abs(la) < 80)
+    scale = np.maximum(1.0, np.abs(st_o.logdensity))
+    assert (np.abs(la_d[fin] - la[fin]) < 2e-3 * scale[fin]).all(), name
+    same = acc_d == acc_o
+    assert rel_err(new_d.position.cpu().numpy()[same], new_o.position[same]) < 1e-3
+    assert (info_d.proposed_weight == 0).all()
+
+
+def test_train_data_generator_dispatch(cuda, setups):
+    """count % (m+1) == 0 -> flow step, else MALA (exe_flow_matching.py:311-313)."""
+    s = setups["gmm16"]
+    gen, init_fn, _ = _gn(s, mcmc=2, step=0.2)
+    st = init_fn(to_dev(_positions(s, 16), cuda), 1.0)
+    key = key_dev(tf.PRNGKey(5), cuda)
+    _, info = gen(key, st, 1, s.P, 1.0)
+    assert (info.proposed_weight != 0).any()           # MALA info carries exp(...) weights
+    _, info = gen(key, st, 3, s.P, 1.0)
+    assert (info.proposed_weight == 0).all()           # flow-MH info has weight 0

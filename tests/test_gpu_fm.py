@@ -1,0 +1,118 @@
+"""Flow-matching loss / gradient / AdamW step vs the oracle (loss 1e-4 relative, north_star)."""
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import optim as OO, targets as OT, threefry as tf, vector_field as VF
+from tests.helpers import key_dev, make_targets, rel_err, to_dev
+from tests.test_gpu_flow import CFG
+
+pytestmark = pytest.mark.gpu
+
+
+def _args():
+    return SimpleNamespace(ref_dist="stdgauss", cond_flow=True, ot_cond_flow=False, sigma=1e-4, adam_beta1=0.9,
+                           adam_beta2=0.999, adam_epsilon=1e-8, weight_decay=1e-4, gradient_clip=1.0)
+
+
+@pytest.fixture(scope="module")
+def setups(cuda, lib):
+    from mfm_b200 import exe_flow_matching as E
+    out = {}
+    for name, ot, dd in make_targets(cuda):
+        H, hutch, n_times, clip, n = CFG[name]
+        rng = np.random.default_rng(11)
+        params = VF.init_params(rng, ot.dim, H, 128, head_scale=0.3)
+        omega = rng.standard_normal(128).astype(np.float32)
+        model = E.VectorFieldNet(to_dev(omega, cuda), dd, [H, H], [H, H], [H, H], "relu", clip)
+        P = E.VectorFieldParams(ot.dim, H, 128, cuda).load_dict(params)
+        lr = E.create_learning_rate_fn(1000, 0, 1e-3)
+        state = E.create_train_state(model, P, lr, _args())
+        out[name] = SimpleNamespace(ot=ot, dd=dd, params=params, omega=omega, model=model, P=P, clip=clip, state=state)
+    return out
+
+
+def _flat_grads(s, G):
+    parts = []
+    for i, (fi, fo) in enumerate(s.P.shapes):
+        parts.append((s.P.w_off[i], G["params"][f"Dense_{i}"]["kernel"].ravel()))
+        parts.append((s.P.b_off[i], G["params"][f"Dense_{i}"]["bias"].ravel()))
+    out = np.zeros(s.P.n_params)
+    for off, a in parts:
+        out[off:off + a.size] = a
+    return out
+
+
+@pytest.mark.parametrize("name,n", [("4-mode", 128), ("gmm16", 77), ("phi-four", 300), ("pines", 40)])
+def test_fm_loss_and_grad(cuda, setups, name, n):
+    s = setups[name]
+    x = s.ot.init_positions(tf.PRNGKey(8), n, np.float32).astype(np.float64)
+    key = tf.PRNGKey(31337)
+    times, xt, target = VF.fm_batch(key, x, OT.IndepGaussian(s.ot.dim).sample, 1e-4, rng_dtype=np.float32)
+    loss_ref, G = VF.fm_loss_and_grad(s.params, s.omega, xt, times, target, s.ot.grad, s.clip)
+    loss, grads = s.state.loss_and_grad(key_dev(key, cuda), to_dev(x, cuda))
+    assert abs(loss.item() - loss_ref) < 1e-4 * abs(loss_ref), (loss.item(), loss_ref)
+    g_ref = _flat_grads(s, G)
+    g = grads.cpu().numpy()
+    assert rel_err(g, g_ref) < 2e-4
+    for i in range(8):   # every layer individually (small layers must not hide behind big ones)
+        fi, fo = s.P.shapes[i]
+        sl = slice(s.P.w_off[i], s.P.w_off[i] + fi * fo)
+        assert rel_err(g[sl], g_ref[sl]) < 5e-4, (name, i)
+        sl = slice(s.P.b_off[i], s.P.b_off[i] + fo)
+        assert rel_err(g[sl], g_ref[sl]) < 5e-4, (name, "bias", i)
+
+
+def test_fm_sharded_batch_matches_full(cuda, setups):
+    """Rows [lo,hi) of an n_total ensemble see the same (t, x0, eps) as in the unsharded call, so the
+    shard losses/gradients add up to the full ones (the quantity the NCCL all-reduce sums)."""
+    s = setups["phi-four"]
+    n = 96
+    x = to_dev(s.ot.init_positions(tf.PRNGKey(8), n, np.float32), cuda)
+    key = key_dev(tf.PRNGKey(5), cuda)
+    loss, grads = s.state.loss_and_grad(key, x)
+    loss, grads = loss.clone(), grads.clone()
+    tot_l, tot_g = 0.0, torch.zeros_like(grads)
+    for lo, hi in ((0, 32), (32, 96)):
+        l, g = s.state.loss_and_grad(key, x[lo:hi].contiguous(), chain_offset=lo, n_total=n)
+        tot_l += l.item(); tot_g += g
+    assert abs(tot_l - loss.item()) < 1e-5 * abs(loss.item())
+    assert rel_err(tot_g.cpu().numpy(), grads.cpu().numpy()) < 1e-5
+
+
+def test_adamw_clip_apply_if_finite(cuda, setups):
+    from mfm_b200 import exe_flow_matching as E
+    s = setups["4-mode"]
+    P = E.VectorFieldParams(2, 128, 128, cuda).load_dict(s.params)
+    lr = E.create_learning_rate_fn(100, 0, 1e-3)
+    state = E.create_train_state(s.model, P, lr, _args())
+    params = {"params": {k: {n: a.copy() for n, a in v.items()} for k, v in s.params["params"].items()}}
+    opt = OO.AdamWClipIfFinite(params, OO.learning_rate_fn(100, 0, 1e-3))
+    rng = np.random.default_rng(0)
+    for it in range(5):
+        G = {"params": {k: {n: (rng.standard_normal(a.shape) * 10 ** rng.uniform(-6, 2)).astype(np.float32)
+                            for n, a in v.items()} for k, v in params["params"].items()}}
+        if it == 2:
+            G["params"]["Dense_3"]["kernel"][0, 0] = np.nan          # rejected update
+        if it == 3:
+            G["params"]["Dense_0"]["bias"][5] = np.inf
+        flat = torch.from_numpy(_flat_grads(SimpleNamespace(P=P), G).astype(np.float32)).to(cuda)
+        state.apply_gradients(flat)
+        params = opt.update(G, params)
+        got = P.to_dict()
+        for k in params["params"]:
+            for nme in ("kernel", "bias"):
+                np.testing.assert_allclose(got["params"][k][nme], params["params"][k][nme], rtol=2e-6, atol=1e-9)
+        st = state.opt_state.cpu().tolist()
+        assert st[0] == opt.count and st[1] == opt.notfinite_count and st[2] == opt.total_notfinite
+        assert st[3] == int(opt.last_finite)
+    assert opt.total_notfinite == 2 and opt.count == 3
+
+
+def test_lr_schedule_matches_oracle(lib):
+    from mfm_b200 import exe_flow_matching as E
+    a, b = E.create_learning_rate_fn(400, 0, 1e-3), OO.learning_rate_fn(400, 0, 1e-3)
+    for step in (0, 1, 57, 399, 400, 1000):
+        assert a(step) == pytest.approx(b(step), rel=1e-12, abs=1e-18)

@@ -27,8 +27,8 @@ def test_gemm_layouts(cuda, lib, M, N, K, akm, bnm):
     ref = np.maximum(A.astype(np.float64) @ B.astype(np.float64) + bias, 0)
     got = Cd.cpu().numpy()
     assert np.isfinite(got).all()
-    scale = np.sqrt(K) + 1
-    assert np.abs(got - ref).max() <= 2e-6 * scale, np.abs(got - ref).max()
+    # fp32-level: a few ulp of the largest output (3xTF32 drops only the lo*lo term, ~2^-22)
+    assert np.abs(got - ref).max() <= 2e-6 * max(np.abs(ref).max(), 1.0), np.abs(got - ref).max()
 
 
 def test_gemm_strided_views(cuda, lib):

@@ -38,7 +38,7 @@ def _check(name, ot, dd, cuda, n, beta, per_chain, steps=3):
                              st_d.logdensity.cpu().numpy().astype(np.float64),
                              st_d.logdensity_grad.cpu().numpy().astype(np.float64))
         noise = tf.vmap_normal(np.stack([tf.split(k)[0] for k in keys]), ot.dim, np.float32).astype(np.float64)
-        new_o, info_o, dbg = OS.mala_step(keys, st_in, ot, h, beta, noise=noise)
+        new_o, info_o, dbg = OS.mala_step(keys, st_in, ot, h, beta, noise=noise, rng_dtype=np.float32)
         if per_chain:
             st_d, info_d = kernel(key_dev(keys, cuda), st_d, fn, h)
         else:
