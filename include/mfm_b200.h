@@ -78,6 +78,8 @@ typedef struct mfm_ode_opts {
 
 const char* mfm_last_error(void);
 int mfm_version(void);
+/* number of CUDA kernels this library has launched in the calling process (diagnostics / bench) */
+unsigned long long mfm_launch_count(void);
 
 /* ---- RNG: jax.random semantics (threefry2x32, legacy keys, x64 off) ------------------------ */
 /* jax.random.split(key, num) -> out uint32[num,2] */

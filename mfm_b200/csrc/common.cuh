@@ -15,7 +15,10 @@
         cudaError_t _e = (expr);                              \
         if (_e != cudaSuccess) { mfm_set_last_error(_e, __FILE__, __LINE__); return MFM_ERR_CUDA; } \
     } while (0)
-#define MFM_LAUNCH_CHECK() MFM_CUDA_CHECK(cudaGetLastError())
+// every kernel launch site is followed by exactly one MFM_LAUNCH_CHECK (or goes through launch_gemm),
+// which also feeds the launch counter exposed as mfm_launch_count().
+extern unsigned long long g_mfm_launches;
+#define MFM_LAUNCH_CHECK() do { ++g_mfm_launches; MFM_CUDA_CHECK(cudaGetLastError()); } while (0)
 
 void mfm_set_last_error(cudaError_t e, const char* file, int line);
 

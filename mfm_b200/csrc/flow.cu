@@ -659,6 +659,7 @@ int mfm_flow_mh_step(const mfm_field_t* f, const mfm_target_t* t, const mfm_ode_
         if (hutch && (rc = mfm_threefry_normal_batched(kh2, n, d, z, stream))) return rc;
         if ((rc = ode_solve(*f, *t, *o, -1, n, hutch ? z : nullptr, position, u0, V0, stats, 1, S, B, stream))) return rc;
         gauss_logprob_kernel<<<ceil_div(n, 8), 256, 0, stream>>>(n, d, up, 0.0f, 1.0f, lq_up);
+        MFM_LAUNCH_CHECK();
         gauss_logprob_kernel<<<ceil_div(n, 8), 256, 0, stream>>>(n, d, u0, 0.0f, 1.0f, lq_u0);
         MFM_LAUNCH_CHECK();
     }

@@ -345,9 +345,12 @@ int mfm_adamw_step(float* params, const float* grads, float* mu, float* nu, cons
     MFM_CUDA_CHECK(cudaMemsetAsync(opt_state + 4, 0, 2 * sizeof(int), stream));
     const int blocks = (int)((n_params + 255) / 256 < 1184 ? (n_params + 255) / 256 : 1184);
     finite_check_kernel<<<blocks, 256, 0, stream>>>(n_params, grads, opt_state + 4);
+    MFM_LAUNCH_CHECK();
     opt_decide_kernel<<<1, 32, 0, stream>>>(opt_state, max_consecutive_errors);
+    MFM_LAUNCH_CHECK();
     adamw_kernel<<<blocks, 256, 0, stream>>>(n_params, params, grads, mu, nu, decay_mask, opt_state, lr_base,
                                              lr_total_steps, b1, b2, eps, weight_decay, clip);
+    MFM_LAUNCH_CHECK();
     opt_advance_kernel<<<1, 32, 0, stream>>>(opt_state);
     MFM_LAUNCH_CHECK();
     return MFM_OK;

@@ -226,6 +226,7 @@ inline cudaError_t launch_gemm(const GemmShape& p, const Epi& epi, cudaStream_t 
     }
     dim3 grid((p.N + GBN - 1) / GBN, (p.M + GBM - 1) / GBM, p.k_split > 0 ? (p.K + p.k_split - 1) / p.k_split : 1);
     kern<<<grid, GTHREADS, GEMM_SMEM_BYTES, st>>>(p, epi);
+    ++g_mfm_launches;
     return cudaGetLastError();
 }
 

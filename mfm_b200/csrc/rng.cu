@@ -13,6 +13,8 @@ void mfm_set_last_error(cudaError_t e, const char* file, int line) {
 void mfm_set_last_error_msg(const char* msg) { snprintf(g_err, sizeof(g_err), "%s", msg); }
 extern "C" const char* mfm_last_error(void) { return g_err; }
 extern "C" int mfm_version(void) { return 100; }
+unsigned long long g_mfm_launches = 0;
+extern "C" unsigned long long mfm_launch_count(void) { return g_mfm_launches; }
 
 namespace {
 

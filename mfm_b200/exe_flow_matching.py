@@ -289,3 +289,54 @@ def create_train_data_gn(dist: Distribution, model: VectorFieldNet, ode_opts, ar
     train_data_generator.inverse_and_logdet = inverse_and_logdet
     train_data_generator.last_stats = last_stats
     return train_data_generator, init_fn, transform_and_logdet
+
+
+# ------------------------------------------------------------------------------------------------
+# hot loop (exe_flow_matching.py:432-449)
+# ------------------------------------------------------------------------------------------------
+class HotLoop:
+    """One rank's share of the reference's training loop: every outer iteration
+        key_sample, key_train_gn, key_train_step = split(key_sample, 3)             (:433)
+        train_states, infos = train_data_generator(key_train_gn, states, count, params, beta)  (:438)
+        state, metrics = train_step(state, train_states.position, key_train_step)   (:439)
+    Chains are sharded over ranks (this rank holds [chain_offset, chain_offset+n) of n_total); the
+    only exchange is the SUM all-reduce of the flat FM gradient (and the scalar loss)."""
+
+    def __init__(self, dist, model, P, args, ode_opts, key_sample, positions, beta=1.0, chain_offset=0, n_total=None,
+                 process_group=None):
+        import torch.distributed as tdist
+        self.dist, self.model, self.P, self.args = dist, model, P, args
+        self.n = positions.shape[0]
+        self.n_total = n_total if n_total is not None else self.n
+        self.chain_offset = chain_offset
+        self.pg = process_group
+        self.world = tdist.get_world_size(process_group) if (tdist.is_available() and tdist.is_initialized()) else 1
+        self.lr_fn = create_learning_rate_fn(args.learning_iter, args.warmup_steps, args.learning_rate)
+        self.state = create_train_state(model, P, self.lr_fn, args)
+        self.gen, self.init_fn, self.transform_and_logdet = create_train_data_gn(
+            dist, model, ode_opts, args, chain_offset=chain_offset, n_total=self.n_total)
+        self.beta = float(beta)
+        self.key_sample = key_sample.clone()
+        self.states = self.init_fn(positions, self.beta)
+        self.count = 0
+        self.last_info = None
+
+    def reset_positions(self, positions):
+        self.states = self.init_fn(positions, self.beta)
+
+    def iteration(self):
+        import torch.distributed as tdist
+        self.count += 1
+        keys = mrandom.split(self.key_sample, 3)
+        self.key_sample, key_train_gn, key_train_step = keys[0], keys[1], keys[2]
+        self.states, self.last_info = self.gen(key_train_gn, self.states, self.count, self.P, self.beta, inplace=True)
+        loss, grads = self.state.loss_and_grad(key_train_step, self.states.position, self.chain_offset, self.n_total)
+        if self.world > 1:
+            tdist.all_reduce(grads, op=tdist.ReduceOp.SUM, group=self.pg)     # loss is a SUM over chains (:178)
+            tdist.all_reduce(loss, op=tdist.ReduceOp.SUM, group=self.pg)
+        self.state.apply_gradients()
+        return loss
+
+    def is_flow_iteration(self, count):
+        m = self.args.mcmc_per_flow_steps
+        return (count % (int(1 / m) + 1) != 0) if 0 < m < 1 else (count % (int(m) + 1) == 0)
