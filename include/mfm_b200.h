@@ -80,6 +80,9 @@ const char* mfm_last_error(void);
 int mfm_version(void);
 /* number of CUDA kernels this library has launched in the calling process (diagnostics / bench) */
 unsigned long long mfm_launch_count(void);
+/* dense-layer backend: 0 = auto (tcgen05/TMEM/TMA kernel when the shape is eligible), 1 = warp-level mma.sync
+ * kernel only.  Same 3xTF32 arithmetic either way; also selectable with the environment variable MFM_GEMM=mma. */
+void mfm_set_gemm_backend(int backend);
 
 /* ---- RNG: jax.random semantics (threefry2x32, legacy keys, x64 off) ------------------------ */
 /* jax.random.split(key, num) -> out uint32[num,2] */

@@ -121,7 +121,7 @@ static int wgrad(int n, int in, int out, const float* A, long long lda, const fl
         return MFM_OK;
     }
     int kper = (n + splits - 1) / splits;
-    kper = (kper + GBK - 1) / GBK * GBK;
+    kper = (kper + 31) / 32 * 32;                 // multiple of both kernels' k-tile (16 / 32)
     GemmShape p{in, out, n, A, lda, D, ldd, nullptr, kper};
     EpiStd e{splitbuf, (long long)out, nullptr, nullptr, 0, nullptr, 0, 1.0f, 0, 1, (long long)in * out};
     MFM_CUDA_CHECK((launch_gemm<false, true>(p, e, st)));

@@ -13,7 +13,7 @@
 // Operand layouts (all via TMA tensor maps built on the host):
 //   K-major  X[rows][K]  : 2-D map, box {32 k, rows}, canonical K-major SW128 (SBO = 1024 B)
 //   MN-major X[K][cols]  : 3-D map {32 cols, K, cols/32}, box {32, 32 k, blocks}: blocks of 32 columns,
-//                          canonical MN-major SW128 (LBO = 4096 B between column blocks, SBO = 1024 B)
+//                          canonical MN-major SW128_32B (LBO = 4096 B between column blocks, SBO = 512 B)
 #pragma once
 #include <cuda.h>
 #include "common.cuh"
@@ -78,10 +78,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// shared-memory matrix descriptor (sm_100 "version 1"), SWIZZLE_128B
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// shared-memory matrix descriptor (sm_100 "version 1").
+// K-major operands: SWIZZLE_128B (layout type 2; 8-row x 128-byte atoms, SBO = 1024 B).
+// MN-major tf32 operands must use SWIZZLE_128B_BASE32B (layout type 1; Swizzle<2,5,2>: 32-byte
+// granules, 4-row x 128-byte atoms) -- the only MN-major layout the tensor core accepts for 32-bit
+// types; TMA produces it with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  LBO = stride between 32-column
+// blocks (4096 B), SBO = stride between 4-row groups (512 B).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
     const uint32_t lo = ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
-    const uint32_t hi = ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+    const uint32_t hi = ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (layout_type << 29);
     return ((uint64_t)hi << 32) | lo;
 }
 
@@ -161,8 +166,10 @@ gemm_tc_kernel(const __grid_constant__ Maps maps, GemmShape p, Epi epi) {
                     const uint32_t ao = A_KMAJOR ? ks * 32 : ks * 1024;
                     const uint32_t bo = !B_NMAJOR ? ks * 32 : ks * 1024;
                     const uint32_t albo = A_KMAJOR ? 16 : 4096, blbo = !B_NMAJOR ? 16 : 4096;
-                    const uint64_t dah = make_desc(a_hi + ao, albo, 1024), dal = make_desc(a_lo + ao, albo, 1024);
-                    const uint64_t dbh = make_desc(b_hi + bo, blbo, 1024), dbl = make_desc(b_lo + bo, blbo, 1024);
+                    const uint32_t asbo = A_KMAJOR ? 1024 : 512, bsbo = !B_NMAJOR ? 1024 : 512;
+                    const uint32_t alt = A_KMAJOR ? 2 : 1, blt = !B_NMAJOR ? 2 : 1;
+                    const uint64_t dah = make_desc(a_hi + ao, albo, asbo, alt), dal = make_desc(a_lo + ao, albo, asbo, alt);
+                    const uint64_t dbh = make_desc(b_hi + bo, blbo, bsbo, blt), dbl = make_desc(b_lo + bo, blbo, bsbo, blt);
                     mma_tf32_ss(tmem_base, dal, dbh, idesc, (kt | ks) != 0);
                     mma_tf32_ss(tmem_base, dah, dbl, idesc, 1);
                     mma_tf32_ss(tmem_base, dah, dbh, idesc, 1);
@@ -282,7 +289,7 @@ inline bool make_map_mnmajor(CUtensorMap* m, const float* base, long long ld, in
     cuuint32_t box[3] = {32, 32, (cuuint32_t)box_blocks};
     cuuint32_t es[3] = {1, 1, 1};
     return encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+                       CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 template <bool A_KMAJOR, bool B_NMAJOR>

@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(GTHREADS, 2) gemm_tf32x3_kernel(GemmShape p, E
 }
 
 template <bool A_KMAJOR, bool B_NMAJOR, class Epi>
-inline cudaError_t launch_gemm(const GemmShape& p, const Epi& epi, cudaStream_t st) {
+inline cudaError_t launch_gemm_mma(const GemmShape& p, const Epi& epi, cudaStream_t st) {
     if (p.M <= 0 || p.N <= 0) return cudaSuccess;
     auto kern = gemm_tf32x3_kernel<A_KMAJOR, B_NMAJOR, Epi>;
     static bool configured = false;
@@ -255,4 +255,16 @@ struct EpiStd {
     __device__ __forceinline__ void row_partial(int, int, float) const {}
 };
 
+}  // namespace mfm
+
+// ---- dispatcher: tcgen05/TMEM/TMA kernel for large aligned problems, warp-level kernel otherwise ----
+#include "gemm_tcgen05.cuh"
+namespace mfm {
+int gemm_backend();          // 0 = auto (tcgen05 when eligible), 1 = force mma.sync   (env MFM_GEMM=mma)
+template <bool A_KMAJOR, bool B_NMAJOR, class Epi>
+inline cudaError_t launch_gemm(const GemmShape& p, const Epi& epi, cudaStream_t st) {
+    if (p.M <= 0 || p.N <= 0) return cudaSuccess;
+    if (gemm_backend() == 0 && tc::eligible<A_KMAJOR, B_NMAJOR>(p)) return tc::launch<A_KMAJOR, B_NMAJOR, Epi>(p, epi, st);
+    return launch_gemm_mma<A_KMAJOR, B_NMAJOR, Epi>(p, epi, st);
+}
 }  // namespace mfm

@@ -14,6 +14,15 @@ void mfm_set_last_error_msg(const char* msg) { snprintf(g_err, sizeof(g_err), "%
 extern "C" const char* mfm_last_error(void) { return g_err; }
 extern "C" int mfm_version(void) { return 100; }
 unsigned long long g_mfm_launches = 0;
+#include <stdlib.h>
+namespace mfm {
+static int g_backend = -1;
+int gemm_backend() {
+    if (g_backend < 0) { const char* e = getenv("MFM_GEMM"); g_backend = (e && strcmp(e, "mma") == 0) ? 1 : 0; }
+    return g_backend;
+}
+}
+extern "C" void mfm_set_gemm_backend(int b) { mfm::g_backend = b; }
 extern "C" unsigned long long mfm_launch_count(void) { return g_mfm_launches; }
 
 namespace {

@@ -8,7 +8,9 @@ from mfm_b200 import _lib
 pytestmark = pytest.mark.gpu
 
 SHAPES = [(128, 128, 16), (128, 128, 256), (300, 200, 100), (1, 2, 2), (129, 2, 130), (64, 1600, 1600),
-          (1000, 128, 2), (257, 1024, 1024), (5, 7, 3), (2048, 256, 64)]
+          (1000, 128, 2), (257, 1024, 1024), (5, 7, 3), (2048, 256, 64),
+          # tcgen05-eligible shapes (M>=128, N>=64, K>=32, 32-aligned MN-major dims), incl. ragged edges
+          (512, 512, 512), (130, 96, 40), (384, 320, 1600), (1024, 1600, 1024), (160, 64, 33 * 4)]
 
 
 @pytest.mark.parametrize("M,N,K", SHAPES)
@@ -47,3 +49,23 @@ def test_gemm_strided_views(cuda, lib):
     got = Cd.cpu().numpy()
     assert np.abs(got[:, 128:128 + N] - ref).max() < 5e-5
     assert (got[:, :128] == 0).all() and (got[:, 128 + N:] == 0).all()
+
+
+def test_gemm_backends_agree(cuda, lib):
+    """tcgen05 and mma.sync kernels implement the same 3xTF32 arithmetic."""
+    rng = np.random.default_rng(3)
+    M, N, K = 640, 768, 1024
+    A = torch.from_numpy(rng.standard_normal((M, K)).astype(np.float32)).to(cuda)
+    B = torch.from_numpy(rng.standard_normal((K, N)).astype(np.float32)).to(cuda)
+    outs = []
+    for backend in (0, 1):
+        lib.mfm_set_gemm_backend(backend)
+        C = torch.empty((M, N), dtype=torch.float32, device=cuda)
+        _lib.check(lib.mfm_gemm_tf32x3(M, N, K, A.data_ptr(), K, 1, B.data_ptr(), N, 1, None, 0, C.data_ptr(), N,
+                                       torch.cuda.current_stream().cuda_stream))
+        outs.append(C.cpu().numpy().astype(np.float64))
+    lib.mfm_set_gemm_backend(0)
+    ref = A.cpu().numpy().astype(np.float64) @ B.cpu().numpy().astype(np.float64)
+    e_tc, e_mma = np.abs(outs[0] - ref).max(), np.abs(outs[1] - ref).max()
+    scale = np.abs(ref).max()
+    assert e_tc < 3e-6 * scale and e_mma < 3e-6 * scale, (e_tc / scale, e_mma / scale)
