@@ -320,11 +320,12 @@ def main():
     if ode_stats:
         step_flops += n * (ode_stats[3] * fl["field"] + fl["logp"])
     step_tflops = step_flops * a.steps / (ms * 1e-3) / 1e12 * 1.0
-    roofline = {"bound": "tensor", "kernel": "gemm_tf32x3_kernel (3xTF32 dense layer, FM shape [n,1024]x[1024,1024])",
+    roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05/TMEM/TMA 3xTF32 dense layer, FM shape [n,1024]x[1024,1024])",
                 "achieved": gemm_tflops, "peak": peak_tf, "unit": "TFLOP/s", "frac": gemm_tflops / peak_tf,
                 "traffic": None, "peak_source": peak_src,
                 "note": "algorithmic fp32 FLOPs (2*M*N*K per launch); each is executed as 3 TF32 tensor-core MMAs, so the "
-                        "ceiling of this arithmetic is 1/6 of the bf16 peak",
+                        "ceiling of this arithmetic is 1/6 of the bf16 peak (kind::tf32 runs at half the bf16 rate, x3 passes)",
+                "frac_of_3xtf32_ceiling": gemm_tflops / (peak_tf / 6.0),
                 "whole_step_tflops_per_gpu": step_tflops,
                 "phase_ms": {"fm_loss_grad": ms_fm, "mala_iteration": ms_mala},
                 "phase_tflops": {"fm_loss_grad": n * fl["fm"] / (ms_fm * 1e-3) / 1e12,
