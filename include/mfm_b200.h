@@ -169,6 +169,13 @@ int mfm_adamw_step(float* params, const float* grads, float* mu, float* nu, cons
                    long long n_params, int* opt_state, float lr_base, int lr_total_steps, float b1, float b2,
                    float eps, float weight_decay, float clip, int max_consecutive_errors, mfm_stream_t stream);
 
+/* ---- adaptive tempering (exe_flow_matching.py:391-402) ---------------------------------------
+ * beta_out[0] = jaxopt.Bisection(ess_zero, lower=prev_beta, upper=1, maxiter=30, tol=1e-5).run().params with
+ * ess_zero(beta) = 1/sum(softmax(loglik*(beta-prev_beta))^2) - alpha*n.  logliks: ALL n chains of the ensemble
+ * (all-gather first when sharded); prev_beta, beta_out: device float[1]. */
+int mfm_tempering_beta(const float* logliks, int n, const float* prev_beta, float alpha, float* beta_out,
+                       mfm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -83,6 +83,7 @@ SIGNATURES = {
                                    C.c_void_p, C.c_size_t, _S]),
     "mfm_fm_loss_grad_from_batch": (C.c_int, [_FP, _PT, C.c_int, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p,
                                               C.c_void_p, C.c_size_t, _S]),
+    "mfm_tempering_beta": (C.c_int, [c_f32p, C.c_int, c_f32p, C.c_float, c_f32p, _S]),
     "mfm_adamw_step": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_u8p, C.c_longlong, c_i32p, C.c_float, C.c_int,
                                  C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, _S]),
 }

@@ -19,7 +19,7 @@ from typing import Callable, NamedTuple, Optional
 import numpy as np
 import torch
 
-from . import _lib, random as mrandom
+from . import _lib, parallel, random as mrandom
 from .bblackjax.mcmc.mala import MALAInfo, MALAState, init, mala_step
 from .distributions import DeviceLogDensity, Distribution, GaussianMixture, IndepGaussian
 
@@ -331,12 +331,78 @@ class HotLoop:
         self.key_sample, key_train_gn, key_train_step = keys[0], keys[1], keys[2]
         self.states, self.last_info = self.gen(key_train_gn, self.states, self.count, self.P, self.beta, inplace=True)
         loss, grads = self.state.loss_and_grad(key_train_step, self.states.position, self.chain_offset, self.n_total)
-        if self.world > 1:
-            tdist.all_reduce(grads, op=tdist.ReduceOp.SUM, group=self.pg)     # loss is a SUM over chains (:178)
-            tdist.all_reduce(loss, op=tdist.ReduceOp.SUM, group=self.pg)
+        parallel.allreduce_sum_([grads, loss], self.pg)                        # loss is a SUM over chains (:178)
         self.state.apply_gradients()
         return loss
+
+    # -- adaptive tempering (exe_flow_matching.py:391-417) ------------------------------------------
+    def next_beta(self, prev_beta: float, positions) -> float:
+        """beta_fn(prev_beta, vmap(dist.loglik)(positions)) on the whole ensemble."""
+        lib = _lib.load()
+        _, _, ll = self.dist.tempered(1.0).value_and_grad(positions, want_loglik=True)
+        ll = parallel.allgather_chains(ll, self.n_total, self.pg).contiguous()
+        prev = torch.tensor([prev_beta], dtype=torch.float32, device=ll.device)
+        out = torch.empty(1, dtype=torch.float32, device=ll.device)
+        _lib.check(lib.mfm_tempering_beta(_lib.ptr(ll), ll.shape[0], _lib.ptr(prev), float(self.args.alpha), _lib.ptr(out),
+                                          _lib.stream()))
+        return float(out.item())
+
+    def temper(self):
+        """beta_gen (:410-417): while beta < 1 pick the next beta and re-initialise (l, g) under it."""
+        if self.beta < 1.0:
+            self.beta = self.next_beta(self.beta, self.states.position)
+            self.states = self.init_fn(self.states.position, self.beta)
+        return self.beta
 
     def is_flow_iteration(self, count):
         m = self.args.mcmc_per_flow_steps
         return (count % (int(1 / m) + 1) != 0) if 0 < m < 1 else (count % (int(m) + 1) == 0)
+
+
+# ------------------------------------------------------------------------------------------------
+# run (exe_flow_matching.py:321-450): training loop.  Post-training sampling / KSD / MMD / plots are
+# out of scope (SURVEY 8(f)); the function returns the training summary instead of the metric table.
+# ------------------------------------------------------------------------------------------------
+def run(dist: Distribution, args, target_gn=None, device=None, log_every: int = 0):
+    logging.basicConfig(format="%(asctime)s - %(levelname)s - %(name)s - %(message)s", datefmt="%m/%d/%Y %H:%M:%S",
+                        level=logging.INFO)
+    dev = dist.device if device is None else torch.device(device)
+    if args.mcmc_per_flow_steps < 0:
+        raise NotImplementedError("use_real_samples (mcmc_per_flow_steps < 0) is not on the configured hot path")
+    rank, world = parallel.world_info()
+    n_total = args.num_chain
+    lo, hi = parallel.shard_range(n_total, rank, world)
+    iter_per_temp = max(args.anneal_iter // args.num_anneal_temp, 1)
+    # key_target, key_sample, key_init, key_dist, key_fourier, key_gen = split(PRNGKey(seed), 6)   (:333)
+    keys = mrandom.split(mrandom.PRNGKey(args.seed, dev), 6)
+    key_sample, key_init, key_dist, key_fourier = keys[1], keys[2], keys[3], keys[4]
+    dist.initialize_model(key_dist, n_total)                                                       # (:334)
+    positions = dist.init_params[lo:hi].contiguous()
+    fourier_random = args.fourier_std * mrandom.normal(key_fourier, (args.fourier_dim,))           # (:350)
+    model = VectorFieldNet(fourier_random, dist, args.hidden_x, args.hidden_t, args.hidden_xt, args.non_linearity,
+                           args.gradient_clip if args.dim > 128 else None)                         # (:351)
+    P = model.init(key_init)
+    ode_opts = SimpleNamespace(rtol=args.rtol, atol=args.atol, mxstep=int(args.mxstep),
+                               n_times=5 if args.example == "4-mode" else 2)                       # (:345-349)
+    logger.info(f"===== Starting training seed {args.seed} w/ {args.learning_iter} iterations =====")
+    loop = HotLoop(dist, model, P, args, ode_opts, key_sample, positions, beta=1.0, chain_offset=lo, n_total=n_total)
+    beta = loop.next_beta(0.0, positions)                                                          # (:426)
+    logger.info(f"Initial beta= {beta}")
+    loop.beta = beta
+    loop.reset_positions(positions)                                                                # (:431)
+    t0 = time.time()
+    history = []
+    for count in range(1, args.learning_iter + 1):                                                 # (:432-449)
+        loss = loop.iteration()
+        if count % iter_per_temp == 0:
+            loop.temper()
+        if log_every and (count % log_every == 0 or count == args.learning_iter):
+            acc = loop.last_info.acceptance_rate
+            history.append({"count": count, "loss": float(loss.item()), "learning_rate": loop.lr_fn(loop.state.step - 1),
+                            "acceptance avg.": float(acc.mean().item()), "acceptance std.": float(acc.std().item()),
+                            "beta": loop.beta, "train_time": time.time() - t0})
+            logger.info(str(history[-1]))
+    torch.cuda.synchronize()
+    train_time = time.time() - t0
+    logger.info(f"Final beta= {loop.beta}")
+    return {"train_time": train_time, "final_beta": loop.beta, "history": history, "loop": loop}

@@ -68,3 +68,32 @@ class AdamWClipIfFinite:
                 new[k][n] = (P[k][n] + u).astype(f32)
         self.count = c
         return {"params": new}
+
+
+def tempering_beta(prev_beta, logliks, alpha, maxiter=30, tol=1e-5, dtype=np.float32):
+    """beta_fn (exe_flow_matching.py:391-402) with jaxopt 0.8.3 Bisection restated (parity unpinned):
+    bracket sign from f(lower), f(upper) (0 when not bracketing, check_bracket=False); each iteration
+    evaluates the midpoint, moves the bracket, stops when |f(mid)| <= tol; returns the last midpoint."""
+    dt = np.dtype(dtype).type
+    ll = np.asarray(logliks, dtype)
+    n = ll.shape[0]
+
+    def ess_zero(beta):
+        logw = ll * dt(beta - prev_beta)
+        w = np.exp(logw - logw.max())
+        w = w / w.sum()
+        return dt(1.0) / (w * w).sum() - dt(alpha * n)
+
+    lo, hi = dt(prev_beta), dt(1.0)
+    flo, fhi = ess_zero(lo), ess_zero(hi)
+    sign = 1.0 if (flo < 0 and fhi >= 0) else (-1.0 if (flo > 0 and fhi <= 0) else 0.0)
+    mid, err, it = lo, np.inf, 0
+    while it < maxiter and err > tol:
+        mid = dt(0.5) * (hi + lo)
+        v = ess_zero(mid)
+        too_large = sign * v > 0
+        hi = mid if too_large else hi
+        lo = lo if too_large else mid
+        err = abs(v)
+        it += 1
+    return float(mid)

@@ -116,3 +116,32 @@ def test_lr_schedule_matches_oracle(lib):
     a, b = E.create_learning_rate_fn(400, 0, 1e-3), OO.learning_rate_fn(400, 0, 1e-3)
     for step in (0, 1, 57, 399, 400, 1000):
         assert a(step) == pytest.approx(b(step), rel=1e-12, abs=1e-18)
+
+
+def test_tempering_beta_matches_oracle(cuda, lib):
+    """beta_fn (exe_flow_matching.py:391-402): ESS-targeted bisection."""
+    from mfm_b200 import _lib
+    rng = np.random.default_rng(1)
+    for n, scale, prev in [(128, 50.0, 0.0), (1024, 5.0, 0.3), (65536, 200.0, 0.0), (128, 1e-3, 0.5)]:
+        ll = (rng.standard_normal(n) * scale - 100.0).astype(np.float32)
+        exp = OO.tempering_beta(prev, ll, 0.95)
+        out = torch.empty(1, dtype=torch.float32, device=cuda)
+        _lib.check(lib.mfm_tempering_beta(to_dev(ll, cuda).data_ptr(), n, torch.tensor([prev], device=cuda).data_ptr(), 0.95,
+                                          out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        got = out.item()
+        assert prev <= got <= 1.0
+        assert abs(got - exp) <= 2e-3 * max(exp, 1e-3), (n, scale, got, exp)
+
+
+def test_run_entry_point_small(cuda, lib):
+    """run() drives tempering + MALA + flow-MH + FM updates end to end (4-mode, few iterations)."""
+    from mfm_b200 import multi_modal as MM
+    args = MM.parser().parse_args(["--example", "4-mode", "--learning_iter", "6", "--mcmc_per_flow_steps", "2",
+                                   "--seed", "1", "--log_every", "1"])
+    dist = MM.build(args, device=cuda)
+    res = MM.run(dist, args, None, log_every=1)
+    assert len(res["history"]) == 6 and 0.0 < res["final_beta"] <= 1.0
+    assert all(np.isfinite(h["loss"]) for h in res["history"])
+    loop = res["loop"]
+    assert loop.state.opt_state.cpu().tolist()[0] == 6          # six applied AdamW updates
+    assert torch.isfinite(loop.states.position).all()
