@@ -43,7 +43,7 @@ def parse():
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", type=str, default="b200", choices=["b200", "reference"])
     p.add_argument("--chains", type=int, default=65536, help="total chains over all GPUs")
-    p.add_argument("--m", type=int, default=100, help="mcmc_per_flow_steps")
+    p.add_argument("--mcmc_per_flow_steps", dest="m", type=int, default=100)
     p.add_argument("--head_scale", type=float, default=0.1)
     p.add_argument("--warmup_unit", type=str, default="iteration", choices=["iteration", "cycle"],
                    help="a warm-up step is one outer iteration (default; >=3 of them touch every MALA/FM kernel, and "
