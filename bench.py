@@ -203,6 +203,10 @@ def main():
     a = parse()
     if a.impl == "reference":
         return run_reference(a)
+    # The contract is ONE JSON line on stdout: route everything else that libraries print to fd 1
+    # (e.g. NCCL's version banner) to stderr, and keep a private handle for the result line.
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
 
     import torch
     import torch.distributed as tdist
@@ -379,7 +383,8 @@ def main():
                 "ode_stats_last_flow_step": dict(zip(["accepted", "attempted", "max_attempts_per_chain", "field_evals"],
                                                      ode_stats)) if ode_stats else None,
                 "warmup_unit": a.warmup_unit}
-        print(json.dumps(line), flush=True)
+        real_stdout.write(json.dumps(line) + "\n")
+        real_stdout.flush()
     if world > 1:
         tdist.destroy_process_group()
 
