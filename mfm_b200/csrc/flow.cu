@@ -43,9 +43,11 @@ __constant__ float c_mid[7] = {(float)(6025192743.0 / 30085553152.0 / 2), 0, (fl
 struct EpiFieldV {
     static constexpr bool kRowSum = false;
     float* V; long long ldv; const float* bias; const float* gt; const float* gc; long long ld; float sgn;
+    const int* row_map;      // optional: compact row -> chain index of the output
     __device__ __forceinline__ float operator()(int row, int col, float acc) const {
         const long long o = (long long)row * ld + col;
-        V[(long long)row * ldv + col] = sgn * (acc + bias[col] + gt[o] * gc[o]);
+        const int orow = row_map ? row_map[row] : row;
+        V[(long long)orow * ldv + col] = sgn * (acc + bias[col] + gt[o] * gc[o]);
         return 0.0f;
     }
     __device__ __forceinline__ void row_partial(int, int, float) const {}
@@ -64,8 +66,9 @@ struct EpiFieldDiv {
 };
 
 int dense(int n, int in, int out, const float* A, long long lda, const float* W, const float* bias, int relu,
-                 float* C, long long ldc, const float* mask, long long ldm, int mask_div, cudaStream_t st) {
-    GemmShape p{n, out, in, A, lda, W, (long long)out, nullptr};
+                 float* C, long long ldc, const float* mask, long long ldm, int mask_div, cudaStream_t st,
+                 const int* n_rows_dev) {
+    GemmShape p{n, out, in, A, lda, W, (long long)out, n_rows_dev};
     EpiStd e{C, ldc, bias, mask, ldm, nullptr, 0, 1.0f, relu, mask_div};
     MFM_CUDA_CHECK((launch_gemm<true, true>(p, e, st)));
     return MFM_OK;
@@ -75,8 +78,9 @@ int dense(int n, int in, int out, const float* A, long long lda, const float* W,
 // elementwise helpers
 // ---------------------------------------------------------------------------------------------
 __global__ void fourier_kernel(int n, int F, const float* __restrict__ omega, const float* __restrict__ t,
-                               float* __restrict__ ff) {
+                               float* __restrict__ ff, const int* __restrict__ n_rows_dev) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (n_rows_dev) n = min(n, *n_rows_dev);
     if (i >= (long long)n * F) return;
     const int c = (int)(i / F), j = (int)(i % F);
     // degt = 2*pi*fourier_random*t  (left to right, :70)
@@ -88,8 +92,9 @@ __global__ void fourier_kernel(int n, int F, const float* __restrict__ omega, co
 
 // out[i,:] = a[i,:] * (gate[i,:] > 0)
 __global__ void gate_kernel(long long total, int H, const float* __restrict__ a, const float* __restrict__ gate,
-                            long long ldg, float* __restrict__ out) {
+                            long long ldg, float* __restrict__ out, const int* __restrict__ n_rows_dev) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (n_rows_dev) total = min(total, (long long)(*n_rows_dev) * H);
     if (i >= total) return;
     const long long r = i / H; const int c = (int)(i % H);
     out[i] = gate[r * ldg + c] > 0.0f ? a[i] : 0.0f;
@@ -97,8 +102,9 @@ __global__ void gate_kernel(long long total, int H, const float* __restrict__ a,
 
 // exact path: tan[(i,j),:] = W2[j,:] * (h2[i,:] > 0)
 __global__ void basis_tangent_kernel(int n, int d, int H, const float* __restrict__ W2, const float* __restrict__ h2,
-                                     float* __restrict__ tan) {
+                                     float* __restrict__ tan, const int* __restrict__ n_rows_dev) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (n_rows_dev) n = min(n, *n_rows_dev);
     if (i >= (long long)n * d * H) return;
     const int k = (int)(i % H); const long long r = i / H; const int j = (int)(r % d); const long long c = r / d;
     tan[i] = h2[c * H + k] > 0.0f ? W2[(long long)j * H + k] : 0.0f;
@@ -107,9 +113,11 @@ __global__ void basis_tangent_kernel(int n, int d, int H, const float* __restric
 // exact path: div_i = sum_j tan6[(i,j),:].W7[:,j] + sum_j gt[i,j]*hdc[i,j];  out = coef * div
 __global__ void exact_trace_kernel(int n, int d, int H, const float* __restrict__ tan6, const float* __restrict__ W7,
                                    const float* __restrict__ gt, const float* __restrict__ hdc, float coef,
-                                   float* __restrict__ out) {
+                                   float* __restrict__ out, const int* __restrict__ n_rows_dev,
+                                   const int* __restrict__ row_map) {
     const int lane = threadIdx.x & 31;
     const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (n_rows_dev) n = min(n, *n_rows_dev);
     if (c >= n) return;
     float s = 0.0f;
     for (int j = 0; j < d; ++j) {
@@ -118,15 +126,17 @@ __global__ void exact_trace_kernel(int n, int d, int H, const float* __restrict_
     }
     for (int j = lane; j < d; j += 32) s += gt[(long long)c * d + j] * hdc[(long long)c * d + j];
     s = warp_sum(s);
-    if (lane == 0) out[c] = coef * s;
+    if (lane == 0) out[row_map ? row_map[c] : c] = coef * s;
 }
 
-__global__ void div_finish_kernel(int n, int n_tiles, const float* __restrict__ partial, float coef, float* __restrict__ out) {
+__global__ void div_finish_kernel(int n, int n_tiles, const float* __restrict__ partial, float coef, float* __restrict__ out,
+                                  const int* __restrict__ n_rows_dev, const int* __restrict__ row_map) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n_rows_dev) n = min(n, *n_rows_dev);
     if (c >= n) return;
     float s = 0.0f;
     for (int t = 0; t < n_tiles; ++t) s += partial[(long long)c * n_tiles + t];
-    out[c] = coef * s;
+    out[row_map ? row_map[c] : c] = coef * s;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -159,7 +169,7 @@ bool field_bufs_take(FieldBufs& B, Workspace& w, const mfm_field_t& F, int n, bo
 // per-solve constants of the Hutchinson estimator: z W2 and (pines) z K^-1
 static int field_prepare_probe(const mfm_field_t& F, const mfm_target_t& T, int n, const float* z, FieldBufs& B, cudaStream_t st) {
     const int d = F.dim, H = F.hidden;
-    int rc = dense(n, d, H, z, d, W_(2), nullptr, 0, B.zw2, H, nullptr, 0, 1, st);
+    int rc = dense(n, d, H, z, d, W_(2), nullptr, 0, B.zw2, H, nullptr, 0, 1, st, nullptr);
     if (rc) return rc;
     if (T.kind == MFM_TARGET_PINES) return pines_kinv_gemm(T, n, z, d, B.zkinv, d, nullptr, st);
     return MFM_OK;
@@ -167,50 +177,52 @@ static int field_prepare_probe(const mfm_field_t& F, const mfm_target_t& T, int 
 
 // out_v[n,d] = sgn * v(x, tfield);  out_l[n] = -sgn * div v   (z != null: Hutchinson; else exact)
 int field_eval(const mfm_field_t& F, const mfm_target_t& T, int n, const float* x, const float* tfield,
-                      const float* z, float sgn, float* out_v, float* out_l, FieldBufs& B, cudaStream_t st) {
+               const float* z, float sgn, float* out_v, float* out_l, FieldBufs& B, cudaStream_t st,
+               const int* nr, const int* row_map) {
     const int d = F.dim, H = F.hidden, Fd = F.fourier_dim;
     int rc;
-    fourier_kernel<<<ceil_div((long long)n * Fd, 256), 256, 0, st>>>(n, Fd, F.omega, tfield, B.ff);
+    fourier_kernel<<<ceil_div((long long)n * Fd, 256), 256, 0, st>>>(n, Fd, F.omega, tfield, B.ff, nr);
     MFM_LAUNCH_CHECK();
-    if ((rc = dense(n, 2 * Fd, H, B.ff, 2 * Fd, W_(0), B_(0), 1, B.h0, H, nullptr, 0, 1, st))) return rc;
-    if ((rc = dense(n, H, H, B.h0, H, W_(1), B_(1), 1, B.cat + H, 2 * H, nullptr, 0, 1, st))) return rc;       // s_t
-    if ((rc = dense(n, d, H, x, d, W_(2), B_(2), 1, B.h2, H, nullptr, 0, 1, st))) return rc;
-    if ((rc = dense(n, H, H, B.h2, H, W_(3), B_(3), 1, B.cat, 2 * H, nullptr, 0, 1, st))) return rc;           // s_x
-    if ((rc = dense(n, H, d, B.cat + H, 2 * H, W_(4), B_(4), 0, B.gt, d, nullptr, 0, 1, st))) return rc;       // nn_t
-    if ((rc = dense(n, 2 * H, H, B.cat, 2 * H, W_(5), B_(5), 1, B.h5, H, nullptr, 0, 1, st))) return rc;
-    if ((rc = dense(n, H, H, B.h5, H, W_(6), B_(6), 1, B.h6, H, nullptr, 0, 1, st))) return rc;
+    if ((rc = dense(n, 2 * Fd, H, B.ff, 2 * Fd, W_(0), B_(0), 1, B.h0, H, nullptr, 0, 1, st, nr))) return rc;
+    if ((rc = dense(n, H, H, B.h0, H, W_(1), B_(1), 1, B.cat + H, 2 * H, nullptr, 0, 1, st, nr))) return rc;       // s_t
+    if ((rc = dense(n, d, H, x, d, W_(2), B_(2), 1, B.h2, H, nullptr, 0, 1, st, nr))) return rc;
+    if ((rc = dense(n, H, H, B.h2, H, W_(3), B_(3), 1, B.cat, 2 * H, nullptr, 0, 1, st, nr))) return rc;           // s_x
+    if ((rc = dense(n, H, d, B.cat + H, 2 * H, W_(4), B_(4), 0, B.gt, d, nullptr, 0, 1, st, nr))) return rc;       // nn_t
+    if ((rc = dense(n, 2 * H, H, B.cat, 2 * H, W_(5), B_(5), 1, B.h5, H, nullptr, 0, 1, st, nr))) return rc;
+    if ((rc = dense(n, H, H, B.h5, H, W_(6), B_(6), 1, B.h6, H, nullptr, 0, 1, st, nr))) return rc;
     // untempered grad logprob (clipped) and the Hessian term of the divergence
     mfm_target_t T1 = T; T1.beta = 1.0f;
     const bool want_div = out_l != nullptr;
     if ((rc = target_field_terms(T1, n, x, z, B.zkinv, F.grad_clip, B.gc, (want_div && z) ? B.hx : nullptr,
-                                 (want_div && !z) ? B.hx : nullptr, nullptr, st))) return rc;
+                                 (want_div && !z) ? B.hx : nullptr, nr, st))) return rc;
     {
-        GemmShape p{n, d, H, B.h6, (long long)H, W_(7), (long long)d, nullptr};
-        EpiFieldV e{out_v, (long long)d, B_(7), B.gt, B.gc, (long long)d, sgn};
+        GemmShape p{n, d, H, B.h6, (long long)H, W_(7), (long long)d, nr};
+        EpiFieldV e{out_v, (long long)d, B_(7), B.gt, B.gc, (long long)d, sgn, row_map};
         MFM_CUDA_CHECK((launch_gemm<true, true>(p, e, st)));
     }
     if (!want_div) return MFM_OK;
     if (z) {
-        gate_kernel<<<ceil_div((long long)n * H, 256), 256, 0, st>>>((long long)n * H, H, B.zw2, B.h2, H, B.ta);
+        gate_kernel<<<ceil_div((long long)n * H, 256), 256, 0, st>>>((long long)n * H, H, B.zw2, B.h2, H, B.ta, nr);
         MFM_LAUNCH_CHECK();
-        if ((rc = dense(n, H, H, B.ta, H, W_(3), nullptr, 0, B.tb, H, B.cat, 2 * H, 1, st))) return rc;
-        if ((rc = dense(n, H, H, B.tb, H, W_(5), nullptr, 0, B.ta, H, B.h5, H, 1, st))) return rc;   // first H rows of W5
-        if ((rc = dense(n, H, H, B.ta, H, W_(6), nullptr, 0, B.tb, H, B.h6, H, 1, st))) return rc;
-        GemmShape p{n, d, H, B.tb, (long long)H, W_(7), (long long)d, nullptr};
+        if ((rc = dense(n, H, H, B.ta, H, W_(3), nullptr, 0, B.tb, H, B.cat, 2 * H, 1, st, nr))) return rc;
+        if ((rc = dense(n, H, H, B.tb, H, W_(5), nullptr, 0, B.ta, H, B.h5, H, 1, st, nr))) return rc;   // first H rows of W5
+        if ((rc = dense(n, H, H, B.ta, H, W_(6), nullptr, 0, B.tb, H, B.h6, H, 1, st, nr))) return rc;
+        GemmShape p{n, d, H, B.tb, (long long)H, W_(7), (long long)d, nr};
         const int nt = gemm_n_tiles(d);
         EpiFieldDiv e{z, B.gt, B.hx, (long long)d, B.divpart, nt};
         MFM_CUDA_CHECK((launch_gemm<true, true>(p, e, st)));
-        div_finish_kernel<<<ceil_div(n, 256), 256, 0, st>>>(n, nt, B.divpart, -sgn, out_l);
+        div_finish_kernel<<<ceil_div(n, 256), 256, 0, st>>>(n, nt, B.divpart, -sgn, out_l, nr, row_map);
         MFM_LAUNCH_CHECK();
     } else {
         const long long rows = (long long)n * d;
         if (rows > 0x7FFFFFFFll) { mfm_set_last_error_msg("exact divergence: n*d too large"); return MFM_ERR_UNSUPPORTED; }
-        basis_tangent_kernel<<<ceil_div(rows * H, 256), 256, 0, st>>>(n, d, H, W_(2), B.h2, B.tan_a);
+        if (nr) { mfm_set_last_error_msg("internal: compaction is not used with the exact divergence"); return MFM_ERR_UNSUPPORTED; }
+        basis_tangent_kernel<<<ceil_div(rows * H, 256), 256, 0, st>>>(n, d, H, W_(2), B.h2, B.tan_a, nullptr);
         MFM_LAUNCH_CHECK();
-        if ((rc = dense((int)rows, H, H, B.tan_a, H, W_(3), nullptr, 0, B.tan_b, H, B.cat, 2 * H, d, st))) return rc;
-        if ((rc = dense((int)rows, H, H, B.tan_b, H, W_(5), nullptr, 0, B.tan_a, H, B.h5, H, d, st))) return rc;
-        if ((rc = dense((int)rows, H, H, B.tan_a, H, W_(6), nullptr, 0, B.tan_b, H, B.h6, H, d, st))) return rc;
-        exact_trace_kernel<<<ceil_div(n, 8), 256, 0, st>>>(n, d, H, B.tan_b, W_(7), B.gt, B.hx, -sgn, out_l);
+        if ((rc = dense((int)rows, H, H, B.tan_a, H, W_(3), nullptr, 0, B.tan_b, H, B.cat, 2 * H, d, st, nullptr))) return rc;
+        if ((rc = dense((int)rows, H, H, B.tan_b, H, W_(5), nullptr, 0, B.tan_a, H, B.h5, H, d, st, nullptr))) return rc;
+        if ((rc = dense((int)rows, H, H, B.tan_a, H, W_(6), nullptr, 0, B.tan_b, H, B.h6, H, d, st, nullptr))) return rc;
+        exact_trace_kernel<<<ceil_div(n, 8), 256, 0, st>>>(n, d, H, B.tan_b, W_(7), B.gt, B.hx, -sgn, out_l, nullptr, row_map);
         MFM_LAUNCH_CHECK();
     }
     return MFM_OK;
@@ -227,6 +239,10 @@ struct OdeState {
     int *seg, *icount, *ntry;  // segment index, steps in segment, attempts
     float *outx, *outl;        // interpolated output at the final time
     int* counters;             // [0] chains still active, [1] accepted, [2] attempted, [3] max attempts
+    // active-chain compaction (Hutchinson path): stage inputs and all field activations live in
+    // compact rows r < n_active, row r <-> chain idx[r]; finished chains cost nothing.
+    int* idx; int* n_active;   // n_active == &counters[8]
+    float *z_full, *zw2_full, *zkinv_full;   // per-solve probe constants in chain order
 };
 
 struct OdeTimes { int n_seg; float target[16]; };
@@ -291,21 +307,70 @@ __global__ void ode_h1_kernel(int n, int d, OdeState S, float rtol, float atol) 
     if (lane == 0) S.dt[c] = dt;
 }
 
-// stage s in 1..6: xi = y + dt * sum_j beta[s-1][j] k_j ; field time t + alpha dt
-__global__ void ode_stage_kernel(int n, int d, int s, OdeState S, int n_seg, float sgn) {
+// stage s in 1..6: xi = y + dt * sum_j beta[s-1][j] k_j ; field time t + alpha dt.
+// Writes compact row r (chain idx[r]) when idx != null.
+__global__ void ode_stage_kernel(int n, int d, int s, OdeState S, int n_seg, float sgn, const int* __restrict__ idx,
+                                 const int* __restrict__ n_active) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (idx) n = min(n, *n_active);
     if (i >= (long long)n * d) return;
-    const int c = (int)(i / d);
+    const int r = (int)(i / d), col = (int)(i % d);
+    const int c = idx ? idx[r] : r;
     if (S.seg[c] >= n_seg) return;            // finished chain: leave its stage input untouched
+    const long long o = (long long)c * d + col;
     const float h = S.dt[c];
     float acc = 0.0f;
 #pragma unroll
-    for (int j = 0; j < 6; ++j) if (j < s) acc += c_beta[s - 1][j] * S.kx[j][i];
-    S.xi[i] = S.yx[i] + h * acc;
-    if (i % d == 0) {
+    for (int j = 0; j < 6; ++j) if (j < s) acc += c_beta[s - 1][j] * S.kx[j][o];
+    S.xi[i] = S.yx[o] + h * acc;
+    if (col == 0) {
         const float ti = S.t[c] + h * c_alpha[s - 1];
-        S.tf[c] = sgn > 0 ? ti : 1.0f - ti;
+        S.tf[r] = sgn > 0 ? ti : 1.0f - ti;
     }
+}
+
+// deterministic stream compaction of the chains that are still integrating (single block)
+__global__ void __launch_bounds__(1024) ode_compact_kernel(int n, int n_seg, const int* __restrict__ seg, int* __restrict__ idx,
+                                                           int* __restrict__ n_active) {
+    __shared__ int wsum[32];
+    __shared__ int total;
+    const int per = (n + 1023) / 1024;
+    const int b = threadIdx.x * per, e = min(n, b + per);
+    int cnt = 0;
+    for (int c = b; c < e; ++c) cnt += seg[c] < n_seg;
+    // block exclusive scan of cnt
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        int v = wsum[lane], iv = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, iv, o); if (lane >= o) iv += u; }
+        wsum[lane] = iv - v;
+        if (lane == 31) total = iv;
+    }
+    __syncthreads();
+    int pos = wsum[w] + inc - cnt;
+    for (int c = b; c < e; ++c) if (seg[c] < n_seg) idx[pos++] = c;
+    if (threadIdx.x == 0) *n_active = total;
+}
+
+// gather the per-solve probe constants of the active chains into compact rows
+__global__ void ode_gather_probe_kernel(int n, int d, int H, const int* __restrict__ idx, const int* __restrict__ n_active,
+                                        const float* __restrict__ z_full, const float* __restrict__ zw2_full,
+                                        const float* __restrict__ zkinv_full, float* __restrict__ z, float* __restrict__ zw2,
+                                        float* __restrict__ zkinv) {
+    const int r = blockIdx.x;
+    if (r >= min(n, *n_active)) return;
+    const long long c = idx[r];
+    for (int i = threadIdx.x; i < d; i += blockDim.x) {
+        z[(long long)r * d + i] = z_full[c * d + i];
+        if (zkinv_full) zkinv[(long long)r * d + i] = zkinv_full[c * d + i];
+    }
+    for (int i = threadIdx.x; i < H; i += blockDim.x) zw2[(long long)r * H + i] = zw2_full[c * H + i];
 }
 
 __device__ __forceinline__ float fit_eval(float y0, float y1, float ymid, float dy0, float dy1, float h, float rel) {
@@ -411,13 +476,15 @@ __global__ void write_stats_kernel(const int* __restrict__ counters, int n_eval,
     }
 }
 
-static size_t ode_state_bytes(int n, int d) {
+static size_t ode_state_bytes(int n, int d, int H) {
     const size_t N = n, D = d;
-    return ws_slice(N * D, 4) * (1 + 7 + 1 + 1) + ws_slice(N, 4) * (1 + 7 + 1 + 3 + 1) + ws_slice(N, 4) * 3 + 256;
+    return ws_slice(N * D, 4) * (1 + 7 + 1 + 1 + 2) + ws_slice(N * H, 4) + ws_slice(N, 4) * (1 + 7 + 1 + 3 + 1) + ws_slice(N, 4) * 4 + 512;
 }
 
-static bool ode_state_take(OdeState& S, Workspace& w, int n, int d) {
+static bool ode_state_take(OdeState& S, Workspace& w, int n, int d, int H) {
     const size_t N = n, D = d;
+    S.z_full = w.take<float>(N * D); S.zkinv_full = w.take<float>(N * D); S.zw2_full = w.take<float>(N * H);
+    S.idx = w.take<int>(N);
     S.yx = w.take<float>(N * D); S.xi = w.take<float>(N * D); S.outx = w.take<float>(N * D);
     for (int j = 0; j < 7; ++j) S.kx[j] = w.take<float>(N * D);
     S.yl = w.take<float>(N); S.outl = w.take<float>(N); S.tf = w.take<float>(N); S.t = w.take<float>(N);
@@ -425,6 +492,7 @@ static bool ode_state_take(OdeState& S, Workspace& w, int n, int d) {
     for (int j = 0; j < 7; ++j) S.kl[j] = w.take<float>(N);
     S.seg = w.take<int>(N); S.icount = w.take<int>(N); S.ntry = w.take<int>(N);
     S.counters = w.take<int>(64);
+    S.n_active = S.counters ? S.counters + 8 : nullptr;
     return w.ok;
 }
 
@@ -435,10 +503,12 @@ static int* host_flag() {
 }
 
 // Solve from y0 over [0,1]; direction +1: (v, -div); -1: (-v(x, 1-s), +div).
+// z: Hutchinson probes in chain order (null -> exact trace).  With probes, the chains still
+// integrating are compacted to the leading rows every iteration so finished chains cost nothing.
 static int ode_solve(const mfm_field_t& F, const mfm_target_t& T, const mfm_ode_opts_t& O, int direction, int n,
                      const float* z, const float* y0, float* y1, float* ldj, int* stats, int stats_accumulate,
-                     OdeState& S, FieldBufs& B, cudaStream_t st) {
-    const int d = F.dim;
+                     OdeState& S, FieldBufs& B, float* z_compact, cudaStream_t st) {
+    const int d = F.dim, H = F.hidden;
     const float sgn = direction >= 0 ? 1.0f : -1.0f;
     if (O.n_times < 2 || O.n_times > 17) { mfm_set_last_error_msg("n_times must be in [2,17]"); return MFM_ERR_ARG; }
     OdeTimes TS; TS.n_seg = O.n_times - 1;
@@ -447,9 +517,18 @@ static int ode_solve(const mfm_field_t& F, const mfm_target_t& T, const mfm_ode_
     if (!hflag) { mfm_set_last_error_msg("cudaMallocHost failed"); return MFM_ERR_CUDA; }
     int rc;
     const int gE = ceil_div((long long)n * d, 256), gW = ceil_div(n, 8);
+    const bool compact = z != nullptr;
     ode_init_kernel<<<max(gE, 1), 256, 0, st>>>(n, d, y0, S, 0.0f, sgn);
     MFM_LAUNCH_CHECK();
-    if (z && (rc = field_prepare_probe(F, T, n, z, B, st))) return rc;
+    if (z) {
+        // per-solve constants z W2 and z K^-1 in chain order (B.zw2 / B.zkinv hold them until the first gather)
+        if ((rc = field_prepare_probe(F, T, n, z, B, st))) return rc;
+        if (compact) {
+            MFM_CUDA_CHECK(cudaMemcpyAsync(S.zw2_full, B.zw2, (size_t)n * H * 4, cudaMemcpyDeviceToDevice, st));
+            if (T.kind == MFM_TARGET_PINES)
+                MFM_CUDA_CHECK(cudaMemcpyAsync(S.zkinv_full, B.zkinv, (size_t)n * d * 4, cudaMemcpyDeviceToDevice, st));
+        }
+    }
     int n_eval = 0;
     if ((rc = field_eval(F, T, n, S.xi, S.tf, z, sgn, S.kx[0], S.kl[0], B, st))) return rc; ++n_eval;
     ode_h0_kernel<<<gW, 256, 0, st>>>(n, d, S, O.rtol, O.atol, sgn);
@@ -457,16 +536,31 @@ static int ode_solve(const mfm_field_t& F, const mfm_target_t& T, const mfm_ode_
     if ((rc = field_eval(F, T, n, S.xi, S.tf, z, sgn, S.kx[1], S.kl[1], B, st))) return rc; ++n_eval;
     ode_h1_kernel<<<gW, 256, 0, st>>>(n, d, S, O.rtol, O.atol);
     MFM_LAUNCH_CHECK();
+    const int* idx = nullptr; const int* nact = nullptr; const float* zc = z;
+    if (compact) {
+        ode_compact_kernel<<<1, 1024, 0, st>>>(n, TS.n_seg, S.seg, S.idx, S.n_active);
+        MFM_LAUNCH_CHECK();
+        idx = S.idx; nact = S.n_active; zc = z_compact;
+    }
     const long long max_iter = (long long)TS.n_seg * (long long)O.mxstep + 2;
     for (long long it = 0; it < max_iter; ++it) {
-        for (int s = 1; s <= 6; ++s) {
-            ode_stage_kernel<<<gE, 256, 0, st>>>(n, d, s, S, TS.n_seg, sgn);
+        if (compact) {
+            ode_gather_probe_kernel<<<n, 128, 0, st>>>(n, d, H, idx, nact, z, S.zw2_full,
+                                                       T.kind == MFM_TARGET_PINES ? S.zkinv_full : nullptr, z_compact, B.zw2, B.zkinv);
             MFM_LAUNCH_CHECK();
-            if ((rc = field_eval(F, T, n, S.xi, S.tf, z, sgn, S.kx[s], S.kl[s], B, st))) return rc; ++n_eval;
+        }
+        for (int s = 1; s <= 6; ++s) {
+            ode_stage_kernel<<<gE, 256, 0, st>>>(n, d, s, S, TS.n_seg, sgn, idx, nact);
+            MFM_LAUNCH_CHECK();
+            if ((rc = field_eval(F, T, n, S.xi, S.tf, zc, sgn, S.kx[s], S.kl[s], B, st, nact, idx))) return rc; ++n_eval;
         }
         MFM_CUDA_CHECK(cudaMemsetAsync(S.counters, 0, sizeof(int), st));
         ode_finish_kernel<<<gW, 256, 0, st>>>(n, d, S, TS, O.rtol, O.atol, O.mxstep);
         MFM_LAUNCH_CHECK();
+        if (compact) {
+            ode_compact_kernel<<<1, 1024, 0, st>>>(n, TS.n_seg, S.seg, S.idx, S.n_active);
+            MFM_LAUNCH_CHECK();
+        }
         MFM_CUDA_CHECK(cudaMemcpyAsync(hflag, S.counters, sizeof(int), cudaMemcpyDeviceToHost, st));
         MFM_CUDA_CHECK(cudaStreamSynchronize(st));
         if (*hflag == 0) break;
@@ -560,7 +654,7 @@ static int check_field(const mfm_field_t* f, const mfm_target_t* t, const mfm_od
 }
 
 size_t mfm_ode_workspace_bytes(const mfm_field_t* f, const mfm_target_t* t, const mfm_ode_opts_t* o, int n) {
-    return ode_state_bytes(n, f->dim) + field_bufs_bytes(*f, *t, n, o->hutch != 0) + ws_slice((size_t)n * f->dim, 4) + 1024;
+    return ode_state_bytes(n, f->dim, f->hidden) + field_bufs_bytes(*f, *t, n, o->hutch != 0) + 2 * ws_slice((size_t)n * f->dim, 4) + 1024;
 }
 
 int mfm_ode_flow(const mfm_field_t* f, const mfm_target_t* t, const mfm_ode_opts_t* o, int direction, int n,
@@ -571,16 +665,16 @@ int mfm_ode_flow(const mfm_field_t* f, const mfm_target_t* t, const mfm_ode_opts
     if (n <= 0) return MFM_OK;
     Workspace w(ws, ws_bytes);
     OdeState S; FieldBufs B;
-    ode_state_take(S, w, n, f->dim);
+    ode_state_take(S, w, n, f->dim, f->hidden);
     field_bufs_take(B, w, *f, n, o->hutch != 0);
-    float* z = nullptr;
-    if (o->hutch) z = w.take<float>((size_t)n * f->dim);
+    float* z = nullptr; float* zc = nullptr;
+    if (o->hutch) { z = w.take<float>((size_t)n * f->dim); zc = w.take<float>((size_t)n * f->dim); }
     if (!w.ok) { mfm_set_last_error_msg("workspace too small (mfm_ode_flow)"); return MFM_ERR_WORKSPACE; }
     if (o->hutch) {
         if (!hutch_keys) { mfm_set_last_error_msg("hutch_keys required"); return MFM_ERR_ARG; }
         if ((rc = mfm_threefry_normal_batched(hutch_keys, n, f->dim, z, stream))) return rc;
     }
-    return ode_solve(*f, *t, *o, direction, n, z, y0, y1, ldj, stats, 0, S, B, stream);
+    return ode_solve(*f, *t, *o, direction, n, z, y0, y1, ldj, stats, 0, S, B, zc, stream);
 }
 
 int mfm_field_eval(const mfm_field_t* f, const mfm_target_t* t, const mfm_ode_opts_t* o, int n, const float* x,
@@ -605,7 +699,7 @@ int mfm_field_eval(const mfm_field_t* f, const mfm_target_t* t, const mfm_ode_op
 
 size_t mfm_flow_mh_workspace_bytes(const mfm_field_t* f, const mfm_target_t* t, const mfm_ode_opts_t* o, int n) {
     const size_t N = n, D = f->dim;
-    return mfm_ode_workspace_bytes(f, t, o, n) + ws_slice(N * D, 4) * 5 + ws_slice(N, 4) * 6 + ws_slice(N * 2, 4) * 4 +
+    return mfm_ode_workspace_bytes(f, t, o, n) + ws_slice(N * D, 4) * 6 + ws_slice(N, 4) * 6 + ws_slice(N * 2, 4) * 4 +
            target_ws_bytes(*t, n) + 1024;
 }
 
@@ -625,9 +719,9 @@ int mfm_flow_mh_step(const mfm_field_t* f, const mfm_target_t* t, const mfm_ode_
     const size_t N = n, D = d;
     Workspace w(ws, ws_bytes);
     OdeState S; FieldBufs B;
-    ode_state_take(S, w, n, d);
+    ode_state_take(S, w, n, d, f->hidden);
     field_bufs_take(B, w, *f, n, o->hutch != 0);
-    float* z = w.take<float>(N * D);
+    float* z = w.take<float>(N * D); float* zc = w.take<float>(N * D);
     float* u0 = w.take<float>(N * D); float* up = w.take<float>(N * D); float* xp = w.take<float>(N * D);
     float* gp = w.take<float>(N * D); float* eps = w.take<float>(N * D);
     float* V0 = w.take<float>(N); float* Vp = w.take<float>(N); float* lp = w.take<float>(N);
@@ -645,19 +739,19 @@ int mfm_flow_mh_step(const mfm_field_t* f, const mfm_target_t* t, const mfm_ode_
     if (variant == MFM_FLOW_RW_MH) {
         // pull back the current position, random-walk in latent space, push forward
         if (hutch && (rc = mfm_threefry_normal_batched(kh2, n, d, z, stream))) return rc;
-        if ((rc = ode_solve(*f, *t, *o, -1, n, hutch ? z : nullptr, position, u0, V0, stats, 0, S, B, stream))) return rc;
+        if ((rc = ode_solve(*f, *t, *o, -1, n, hutch ? z : nullptr, position, u0, V0, stats, 0, S, B, zc, stream))) return rc;
         const float scale = 2.38f / sqrtf((float)d);                                     // :262
         axpy_kernel<<<ceil_div(tot, 256), 256, 0, stream>>>(tot, u0, scale, eps, up);
         MFM_LAUNCH_CHECK();
         if (hutch && (rc = mfm_threefry_normal_batched(kh1, n, d, z, stream))) return rc;
-        if ((rc = ode_solve(*f, *t, *o, +1, n, hutch ? z : nullptr, up, xp, Vp, stats, 1, S, B, stream))) return rc;
+        if ((rc = ode_solve(*f, *t, *o, +1, n, hutch ? z : nullptr, up, xp, Vp, stats, 1, S, B, zc, stream))) return rc;
     } else {
         // independent proposal from the reference distribution N(0, I) (stdgauss, :48-49,249)
         MFM_CUDA_CHECK(cudaMemcpyAsync(up, eps, tot * sizeof(float), cudaMemcpyDeviceToDevice, stream));
         if (hutch && (rc = mfm_threefry_normal_batched(kh1, n, d, z, stream))) return rc;
-        if ((rc = ode_solve(*f, *t, *o, +1, n, hutch ? z : nullptr, up, xp, Vp, stats, 0, S, B, stream))) return rc;
+        if ((rc = ode_solve(*f, *t, *o, +1, n, hutch ? z : nullptr, up, xp, Vp, stats, 0, S, B, zc, stream))) return rc;
         if (hutch && (rc = mfm_threefry_normal_batched(kh2, n, d, z, stream))) return rc;
-        if ((rc = ode_solve(*f, *t, *o, -1, n, hutch ? z : nullptr, position, u0, V0, stats, 1, S, B, stream))) return rc;
+        if ((rc = ode_solve(*f, *t, *o, -1, n, hutch ? z : nullptr, position, u0, V0, stats, 1, S, B, zc, stream))) return rc;
         gauss_logprob_kernel<<<ceil_div(n, 8), 256, 0, stream>>>(n, d, up, 0.0f, 1.0f, lq_up);
         MFM_LAUNCH_CHECK();
         gauss_logprob_kernel<<<ceil_div(n, 8), 256, 0, stream>>>(n, d, u0, 0.0f, 1.0f, lq_u0);

@@ -108,12 +108,22 @@ __global__ void splitk_reduce_kernel(long long count, int splits, long long stri
 // dW[in,out] = A^T[in,n] * D[n,out]  (A stored [n,in], lda), split over the batch dimension.
 static int wgrad(int n, int in, int out, const float* A, long long lda, const float* D, long long ldd, float* dW,
                  float* splitbuf, size_t splitbuf_floats, cudaStream_t st) {
-    const long long tiles = (long long)ceil_div(in, GBM) * ceil_div(out, GBN);
-    int splits = (int)((2 * 148 + tiles - 1) / tiles);            // aim for >= 2 CTAs per SM
-    const int max_splits = (n + 255) / 256;
-    if (splits > max_splits) splits = max_splits;
-    if (splits > 64) splits = 64;
-    while (splits > 1 && (size_t)splits * in * out > splitbuf_floats) --splits;
+    // wave-aware split of the batch (reduction) dimension: fill the 148 SMs with whole waves
+    GemmShape probe{in, out, n, A, lda, D, ldd, nullptr};
+    const bool use_tc = gemm_backend() == 0 && tc::eligible<false, true>(probe);
+    const long long tiles = use_tc ? (long long)ceil_div(in, tc::BM) * ceil_div(out, tc::BN)
+                                   : (long long)ceil_div(in, GBM) * ceil_div(out, GBN);
+    const int slots = use_tc ? 148 : 296;                          // resident CTAs per wave
+    int max_splits = n / 512;
+    if (max_splits > 64) max_splits = 64;
+    while (max_splits > 1 && (size_t)max_splits * in * out > splitbuf_floats) --max_splits;
+    int splits = 1; double best = 0.0;
+    for (int sp = 1; sp <= max_splits; ++sp) {
+        const long long ctas = tiles * sp;
+        const double eff = (double)ctas / (double)(((ctas + slots - 1) / slots) * slots);
+        if (eff > best + 1e-9) { best = eff; splits = sp; }
+        if (eff >= 0.92) { splits = sp; break; }
+    }
     if (splits <= 1) {
         GemmShape p{in, out, n, A, lda, D, ldd, nullptr};
         EpiStd e{dW, (long long)out, nullptr, nullptr, 0, nullptr, 0, 1.0f, 0};
@@ -153,7 +163,7 @@ static size_t fm_splitbuf_floats(const mfm_field_t& F) {
     size_t m = 2 * H * H;
     if (d * H > m) m = d * H;
     if (2 * Fd * H > m) m = 2 * Fd * H;
-    return m * 8;      // room for up to 8 batch slices of the largest layer (more for smaller ones)
+    return m * 16;     // room for 16 batch slices of the largest layer (more for smaller ones)
 }
 
 static size_t fm_bytes(const mfm_field_t& F, const mfm_target_t& T, int n) {

@@ -50,10 +50,14 @@ size_t field_bufs_bytes(const mfm_field_t& F, const mfm_target_t& T, int n, bool
 bool field_bufs_take(FieldBufs& B, Workspace& w, const mfm_field_t& F, int n, bool hutch);
 // C[n,out] = relu?(A[n,in] W[in,out] + bias) gated by mask (relu' of another activation)
 int dense(int n, int in, int out, const float* A, long long lda, const float* W, const float* bias, int relu,
-          float* C, long long ldc, const float* mask, long long ldm, int mask_div, cudaStream_t st);
+          float* C, long long ldc, const float* mask, long long ldm, int mask_div, cudaStream_t st,
+          const int* n_rows_dev = nullptr);
 // out_v = sgn * v(x, t); out_l = -sgn * div v (optional; z != null -> Hutchinson, else exact trace).
 // Leaves the activations (ff, h0, cat=[s_x|s_t], h2, gt, h5, h6, gc) in B for a backward pass.
+// n_rows_dev (optional): device count of leading rows that are live (compacted active chains);
+// row_map (optional): compact row -> chain index used when writing out_v / out_l.
 int field_eval(const mfm_field_t& F, const mfm_target_t& T, int n, const float* x, const float* tfield,
-               const float* z, float sgn, float* out_v, float* out_l, FieldBufs& B, cudaStream_t st);
+               const float* z, float sgn, float* out_v, float* out_l, FieldBufs& B, cudaStream_t st,
+               const int* n_rows_dev = nullptr, const int* row_map = nullptr);
 
 }  // namespace mfm

@@ -126,8 +126,9 @@ def test_tempering_beta_matches_oracle(cuda, lib):
         ll = (rng.standard_normal(n) * scale - 100.0).astype(np.float32)
         exp = OO.tempering_beta(prev, ll, 0.95)
         out = torch.empty(1, dtype=torch.float32, device=cuda)
-        _lib.check(lib.mfm_tempering_beta(to_dev(ll, cuda).data_ptr(), n, torch.tensor([prev], device=cuda).data_ptr(), 0.95,
-                                          out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        ll_d, prev_d = to_dev(ll, cuda), torch.tensor([prev], dtype=torch.float32, device=cuda)   # keep alive
+        _lib.check(lib.mfm_tempering_beta(ll_d.data_ptr(), n, prev_d.data_ptr(), 0.95, out.data_ptr(),
+                                          torch.cuda.current_stream().cuda_stream))
         got = out.item()
         assert prev <= got <= 1.0
         assert abs(got - exp) <= 2e-3 * max(exp, 1e-3), (n, scale, got, exp)
