@@ -77,22 +77,33 @@ __global__ void final_sum_kernel(int n, const float* __restrict__ partial, float
     if (threadIdx.x == 0) out[0] = s;
 }
 
-// column sums of a [n, cols] matrix (bias gradients); 32 columns per block, fixed summation order
+// column sums of a [n, cols] matrix (bias gradients).  Block (x, y): 32 columns x one slab of rows;
+// slab partials are then added in fixed order (deterministic, no atomics).
+constexpr int COLSUM_SLABS = 64;
 __global__ void __launch_bounds__(256)
-colsum_kernel(int n, int cols, const float* __restrict__ a, long long lda, float* __restrict__ out) {
+colsum_partial_kernel(int n, int cols, const float* __restrict__ a, long long lda, float* __restrict__ partial) {
     __shared__ float sm[8][33];
     const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
     const int col = blockIdx.x * 32 + cx;
+    const int per = (n + gridDim.y - 1) / gridDim.y;
+    const int r0 = blockIdx.y * per, r1 = min(n, r0 + per);
     float s = 0.0f;
-    if (col < cols) for (int r = ry; r < n; r += 8) s += a[(long long)r * lda + col];
+    if (col < cols) for (int r = r0 + ry; r < r1; r += 8) s += a[(long long)r * lda + col];
     sm[ry][cx] = s;
     __syncthreads();
     if (ry == 0 && col < cols) {
         float t = 0.0f;
 #pragma unroll
         for (int k = 0; k < 8; ++k) t += sm[k][cx];
-        out[col] = t;
+        partial[(long long)blockIdx.y * cols + col] = t;
     }
+}
+__global__ void colsum_final_kernel(int cols, int slabs, const float* __restrict__ partial, float* __restrict__ out) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= cols) return;
+    float t = 0.0f;
+    for (int z = 0; z < slabs; ++z) t += partial[(long long)z * cols + col];
+    out[col] = t;
 }
 
 // out[i] = sum_z partial[z*stride + i]
@@ -152,7 +163,7 @@ static int dgrad(int n, int in, int out, const float* D, long long ldd, const fl
 
 struct FmBufs {
     FieldBufs B;
-    float *times, *xt, *target, *v, *delta, *dgt, *d6, *d5, *dcat, *d2, *d0, *blockpart, *splitbuf;
+    float *times, *xt, *target, *v, *delta, *dgt, *d6, *d5, *dcat, *d2, *d0, *blockpart, *splitbuf, *colpart;
     size_t splitbuf_floats;
 };
 
@@ -169,7 +180,8 @@ static size_t fm_splitbuf_floats(const mfm_field_t& F) {
 static size_t fm_bytes(const mfm_field_t& F, const mfm_target_t& T, int n) {
     const size_t H = F.hidden, d = F.dim, N = n;
     return field_bufs_bytes(F, T, n, true) + ws_slice(N, 4) + ws_slice(N * d, 4) * 5 + ws_slice(N * H, 4) * 4 +
-           ws_slice(N * 2 * H, 4) + ws_slice(FM_LOSS_BLOCKS, 4) + ws_slice(fm_splitbuf_floats(F), 4) + 1024;
+           ws_slice(N * 2 * H, 4) + ws_slice(FM_LOSS_BLOCKS, 4) + ws_slice(fm_splitbuf_floats(F), 4) +
+           ws_slice((size_t)COLSUM_SLABS * (H > d ? H : d), 4) + 1024;
 }
 
 static bool fm_take(FmBufs& M, Workspace& w, const mfm_field_t& F, int n) {
@@ -181,6 +193,7 @@ static bool fm_take(FmBufs& M, Workspace& w, const mfm_field_t& F, int n) {
     M.d6 = w.take<float>(N * H); M.d5 = w.take<float>(N * H); M.d2 = w.take<float>(N * H); M.d0 = w.take<float>(N * H);
     M.dcat = w.take<float>(N * 2 * H);
     M.blockpart = w.take<float>(FM_LOSS_BLOCKS);
+    M.colpart = w.take<float>((size_t)COLSUM_SLABS * (H > d ? H : d));
     M.splitbuf_floats = fm_splitbuf_floats(F);
     M.splitbuf = w.take<float>(M.splitbuf_floats);
     return w.ok;
@@ -204,7 +217,10 @@ static int fm_forward_backward(const mfm_field_t& F, const mfm_target_t& T, int 
     final_sum_kernel<<<1, 256, 0, st>>>(lb, M.blockpart, loss_out);
     MFM_LAUNCH_CHECK();
     auto bias_grad = [&](const float* a, long long lda, int cols, float* out) -> int {
-        colsum_kernel<<<ceil_div(cols, 32), 256, 0, st>>>(n, cols, a, lda, out);
+        const int slabs = n >= 8 * COLSUM_SLABS ? COLSUM_SLABS : 1;
+        colsum_partial_kernel<<<dim3(ceil_div(cols, 32), slabs), 256, 0, st>>>(n, cols, a, lda, M.colpart);
+        MFM_LAUNCH_CHECK();
+        colsum_final_kernel<<<ceil_div(cols, 256), 256, 0, st>>>(cols, slabs, M.colpart, out);
         MFM_LAUNCH_CHECK();
         return MFM_OK;
     };

@@ -23,8 +23,9 @@ def test_gemm_layouts(cuda, lib, M, N, K, akm, bnm):
     Ad = torch.from_numpy(A if akm else np.ascontiguousarray(A.T)).to(cuda)
     Bd = torch.from_numpy(B if bnm else np.ascontiguousarray(B.T)).to(cuda)
     Cd = torch.full((M, N), float("nan"), dtype=torch.float32, device=cuda)
+    bias_d = torch.from_numpy(bias).to(cuda)      # keep alive across the asynchronous launch
     _lib.check(lib.mfm_gemm_tf32x3(M, N, K, Ad.data_ptr(), Ad.shape[1], akm, Bd.data_ptr(), Bd.shape[1], bnm,
-                                   torch.from_numpy(bias).to(cuda).data_ptr(), 1, Cd.data_ptr(), N,
+                                   bias_d.data_ptr(), 1, Cd.data_ptr(), N,
                                    torch.cuda.current_stream().cuda_stream))
     ref = np.maximum(A.astype(np.float64) @ B.astype(np.float64) + bias, 0)
     got = Cd.cpu().numpy()
