@@ -44,12 +44,18 @@ struct EpiFieldV {
     static constexpr bool kRowSum = false;
     float* V; long long ldv; const float* bias; const float* gt; const float* gc; long long ld; float sgn;
     const int* row_map;      // optional: compact row -> chain index of the output
-    __device__ __forceinline__ float operator()(int row, int col, float acc) const {
+    struct Aux { float bias, gt, gc; int orow; };
+    __device__ __forceinline__ Aux load(int row, int col) const {
         const long long o = (long long)row * ld + col;
-        const int orow = row_map ? row_map[row] : row;
-        V[(long long)orow * ldv + col] = sgn * (acc + bias[col] + gt[o] * gc[o]);
+        Aux a; a.bias = __ldg(bias + col); a.gt = __ldg(gt + o); a.gc = __ldg(gc + o);
+        a.orow = row_map ? __ldg(row_map + row) : row;
+        return a;
+    }
+    __device__ __forceinline__ float apply(int, int col, float acc, const Aux& a) const {
+        V[(long long)a.orow * ldv + col] = sgn * (acc + a.bias + a.gt * a.gc);
         return 0.0f;
     }
+    __device__ __forceinline__ float operator()(int row, int col, float acc) const { return apply(row, col, acc, load(row, col)); }
     __device__ __forceinline__ void row_partial(int, int, float) const {}
     __device__ __forceinline__ void at_z(int) {}
 };
@@ -57,10 +63,14 @@ struct EpiFieldV {
 struct EpiFieldDiv {
     static constexpr bool kRowSum = true;
     const float* z; const float* gt; const float* hvc; long long ld; float* partial; int n_tiles;
-    __device__ __forceinline__ float operator()(int row, int col, float acc) const {
+    struct Aux { float z, gt, hvc; };
+    __device__ __forceinline__ Aux load(int row, int col) const {
         const long long o = (long long)row * ld + col;
-        return z[o] * (acc + gt[o] * hvc[o]);
+        Aux a; a.z = __ldg(z + o); a.gt = __ldg(gt + o); a.hvc = __ldg(hvc + o);
+        return a;
     }
+    __device__ __forceinline__ float apply(int, int, float acc, const Aux& a) const { return a.z * (acc + a.gt * a.hvc); }
+    __device__ __forceinline__ float operator()(int row, int col, float acc) const { return apply(row, col, acc, load(row, col)); }
     __device__ __forceinline__ void row_partial(int row, int tile, float s) const { partial[(long long)row * n_tiles + tile] = s; }
     __device__ __forceinline__ void at_z(int) {}
 };

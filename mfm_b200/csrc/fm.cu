@@ -121,10 +121,11 @@ static int wgrad(int n, int in, int out, const float* A, long long lda, const fl
                  float* splitbuf, size_t splitbuf_floats, cudaStream_t st) {
     // wave-aware split of the batch (reduction) dimension: fill the 148 SMs with whole waves
     GemmShape probe{in, out, n, A, lda, D, ldd, nullptr};
-    const bool use_tc = gemm_backend() == 0 && tc::eligible<false, true>(probe);
-    const long long tiles = use_tc ? (long long)ceil_div(in, tc::BM) * ceil_div(out, tc::BN)
-                                   : (long long)ceil_div(in, GBM) * ceil_div(out, GBN);
-    const int slots = use_tc ? 148 : 296;                          // resident CTAs per wave
+    const int path = gemm_path<false, true>(probe);                // 2 = CTA pair, 1 = single CTA, 0 = mma.sync
+    const long long tiles = path == 2 ? (long long)ceil_div(in, 2 * tc2::BM) * ceil_div(out, tc2::BN)
+                          : path == 1 ? (long long)ceil_div(in, tc::BM) * ceil_div(out, tc::BN)
+                                      : (long long)ceil_div(in, GBM) * ceil_div(out, GBN);
+    const int slots = path == 2 ? 74 : (path == 1 ? 148 : 296);    // resident tiles per wave
     int max_splits = n / 512;
     if (max_splits > 64) max_splits = 64;
     while (max_splits > 1 && (size_t)max_splits * in * out > splitbuf_floats) --max_splits;

@@ -85,7 +85,10 @@ __device__ __forceinline__ void load_tile(float* s, const float* __restrict__ g,
 }
 
 // Epilogue functor contract:
-//   __device__ float operator()(int row, int col, float acc) const;   // stores; returns row-sum contribution
+//   struct Aux;  __device__ Aux load(int row, int col) const;          // every global read of the epilogue
+//   __device__ float apply(int row, int col, float acc, const Aux&) const;   // stores; returns row-sum contribution
+//   __device__ float operator()(int row, int col, float acc) const;   // = apply(row, col, acc, load(row, col))
+//   (the tcgen05 kernels issue the loads of several rows before the first store: memory-level parallelism)
 //   static constexpr bool kRowSum;                                     // if true: row_partial(row, ntile, sum)
 //   __device__ void row_partial(int row, int ntile, float s) const;
 //
@@ -243,28 +246,48 @@ struct EpiStd {
     int mask_div = 1;                  // rows of the mask are shared by mask_div consecutive output rows
     long long c_zstride = 0;           // split-K: slice z writes to C + z*c_zstride
     __device__ __forceinline__ void at_z(int z) { C += (long long)z * c_zstride; }
-    __device__ __forceinline__ float operator()(int row, int col, float acc) const {
-        float v = alpha * acc;
-        if (bias) v += bias[col];
-        if (add) v += add[(long long)row * ldadd + col];
+    struct Aux { float bias, add, mask; };
+    __device__ __forceinline__ Aux load(int row, int col) const {
+        Aux a;
+        a.bias = bias ? __ldg(bias + col) : 0.0f;
+        a.add = add ? add[(long long)row * ldadd + col] : 0.0f;      // may alias C (in-place accumulate): plain load
+        a.mask = mask ? __ldg(mask + (long long)(mask_div == 1 ? row : row / mask_div) * ldm + col) : 1.0f;
+        return a;
+    }
+    __device__ __forceinline__ float apply(int row, int col, float acc, const Aux& a) const {
+        float v = alpha * acc + a.bias + a.add;
         if (relu) v = fmaxf(v, 0.0f);
-        if (mask) v = mask[(long long)(row / mask_div) * ldm + col] > 0.0f ? v : 0.0f;
+        v = a.mask > 0.0f ? v : 0.0f;
         C[(long long)row * ldc + col] = v;
         return 0.0f;
     }
+    __device__ __forceinline__ float operator()(int row, int col, float acc) const { return apply(row, col, acc, load(row, col)); }
     __device__ __forceinline__ void row_partial(int, int, float) const {}
 };
 
 }  // namespace mfm
 
-// ---- dispatcher: tcgen05/TMEM/TMA kernel for large aligned problems, warp-level kernel otherwise ----
+// ---- dispatcher: CTA-pair tcgen05 kernel for large aligned problems, single-CTA tcgen05 kernel for
+// medium ones, warp-level kernel otherwise ----
 #include "gemm_tcgen05.cuh"
+#include "gemm_tcgen05_2sm.cuh"
 namespace mfm {
-int gemm_backend();          // 0 = auto (tcgen05 when eligible), 1 = force mma.sync   (env MFM_GEMM=mma)
+// 0 = auto, 1 = force mma.sync (env MFM_GEMM=mma), 2 = tcgen05 single-CTA only (env MFM_GEMM=tc1)
+int gemm_backend();
+template <bool A_KMAJOR, bool B_NMAJOR>
+inline int gemm_path(const GemmShape& p) {       // 2 = CTA pair, 1 = single CTA, 0 = mma.sync
+    const int be = gemm_backend();
+    if (be == 1) return 0;
+    if (be == 0 && tc2::eligible<A_KMAJOR, B_NMAJOR>(p)) return 2;
+    return tc::eligible<A_KMAJOR, B_NMAJOR>(p) ? 1 : 0;
+}
 template <bool A_KMAJOR, bool B_NMAJOR, class Epi>
 inline cudaError_t launch_gemm(const GemmShape& p, const Epi& epi, cudaStream_t st) {
     if (p.M <= 0 || p.N <= 0) return cudaSuccess;
-    if (gemm_backend() == 0 && tc::eligible<A_KMAJOR, B_NMAJOR>(p)) return tc::launch<A_KMAJOR, B_NMAJOR, Epi>(p, epi, st);
-    return launch_gemm_mma<A_KMAJOR, B_NMAJOR, Epi>(p, epi, st);
+    switch (gemm_path<A_KMAJOR, B_NMAJOR>(p)) {
+        case 2: return tc2::launch<A_KMAJOR, B_NMAJOR, Epi>(p, epi, st);
+        case 1: return tc::launch<A_KMAJOR, B_NMAJOR, Epi>(p, epi, st);
+        default: return launch_gemm_mma<A_KMAJOR, B_NMAJOR, Epi>(p, epi, st);
+    }
 }
 }  // namespace mfm

@@ -18,10 +18,21 @@ unsigned long long g_mfm_launches = 0;
 namespace mfm {
 static int g_backend = -1;
 int gemm_backend() {
-    if (g_backend < 0) { const char* e = getenv("MFM_GEMM"); g_backend = (e && strcmp(e, "mma") == 0) ? 1 : 0; }
+    if (g_backend < 0) {
+        const char* e = getenv("MFM_GEMM");
+        g_backend = (e && strcmp(e, "mma") == 0) ? 1 : ((e && strcmp(e, "tc1") == 0) ? 2 : 0);
+    }
     return g_backend;
 }
+namespace tc2 {
+static int g_raw_hi = -1;
+int gemm_raw_hi() {
+    if (g_raw_hi < 0) { const char* e = getenv("MFM_TC_RAWHI"); g_raw_hi = (e && e[0] == '0') ? 0 : 1; }
+    return g_raw_hi;
 }
+}
+}
+extern "C" void mfm_set_gemm_raw_hi(int v) { mfm::tc2::g_raw_hi = v ? 1 : 0; }
 extern "C" void mfm_set_gemm_backend(int b) { mfm::g_backend = b; }
 extern "C" unsigned long long mfm_launch_count(void) { return g_mfm_launches; }
 

@@ -72,12 +72,17 @@ struct EpiPinesGrad {
     float mu, a, beta;
     float* grad; long long ldg;
     float* partial; int n_tiles;
-    __device__ __forceinline__ float operator()(int row, int col, float acc) const {
-        const float q = acc - kinv_mu[col];
-        const float xv = X[(long long)row * ldx + col];
-        grad[(long long)row * ldg + col] = beta * (counts[col] - a * expf(xv)) - q;
-        return (xv - mu) * q;
+    struct Aux { float kinv_mu, x, counts; };
+    __device__ __forceinline__ Aux load(int row, int col) const {
+        Aux u; u.kinv_mu = __ldg(kinv_mu + col); u.x = __ldg(X + (long long)row * ldx + col); u.counts = __ldg(counts + col);
+        return u;
     }
+    __device__ __forceinline__ float apply(int row, int col, float acc, const Aux& u) const {
+        const float q = acc - u.kinv_mu;
+        grad[(long long)row * ldg + col] = beta * (u.counts - a * expf(u.x)) - q;
+        return (u.x - mu) * q;
+    }
+    __device__ __forceinline__ float operator()(int row, int col, float acc) const { return apply(row, col, acc, load(row, col)); }
     __device__ __forceinline__ void row_partial(int row, int tile, float s) const {
         if (partial) partial[(long long)row * n_tiles + tile] = s;
     }
@@ -91,16 +96,24 @@ struct EpiPinesField {
     const float* Z; const float* ZK;     // probe and Z K^-1 (hutch), or null
     float a, clip;
     float* gc; float* hvc; float* hdc; long long ld;
-    __device__ __forceinline__ float operator()(int row, int col, float acc) const {
+    struct Aux { float x, counts, kinv_mu, z, zk, kdiag; };
+    __device__ __forceinline__ Aux load(int row, int col) const {
         const long long o = (long long)row * ld + col;
-        const float e = a * expf(X[(long long)row * ldx + col]);
-        const float g = counts[col] - e - (acc - kinv_mu[col]);
+        Aux u; u.x = __ldg(X + (long long)row * ldx + col); u.counts = __ldg(counts + col); u.kinv_mu = __ldg(kinv_mu + col);
+        u.z = hvc ? __ldg(Z + o) : 0.0f; u.zk = hvc ? __ldg(ZK + o) : 0.0f; u.kdiag = hdc ? __ldg(kinv_diag + col) : 0.0f;
+        return u;
+    }
+    __device__ __forceinline__ float apply(int row, int col, float acc, const Aux& u) const {
+        const long long o = (long long)row * ld + col;
+        const float e = a * expf(u.x);
+        const float g = u.counts - e - (acc - u.kinv_mu);
         const bool in = !(clip > 0.0f) || (g > -clip && g < clip);
         gc[o] = clip > 0.0f ? fminf(fmaxf(g, -clip), clip) : g;
-        if (hvc) hvc[o] = in ? (-e * Z[o] - ZK[o]) : 0.0f;
-        if (hdc) hdc[o] = in ? (-e - kinv_diag[col]) : 0.0f;
+        if (hvc) hvc[o] = in ? (-e * u.z - u.zk) : 0.0f;
+        if (hdc) hdc[o] = in ? (-e - u.kdiag) : 0.0f;
         return 0.0f;
     }
+    __device__ __forceinline__ float operator()(int row, int col, float acc) const { return apply(row, col, acc, load(row, col)); }
     __device__ __forceinline__ void row_partial(int, int, float) const {}
     __device__ __forceinline__ void at_z(int) {}
 };
