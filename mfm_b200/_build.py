@@ -16,6 +16,8 @@ STAMP = os.path.join(HERE, ".libmfm_b200.stamp")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-diag-suppress", "550"]
+if os.environ.get("MFM_TC2_TIMELINE"):
+    FLAGS.append("-DMFM_TC2_TIMELINE")
 
 
 def _sources():

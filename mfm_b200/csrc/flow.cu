@@ -58,6 +58,22 @@ struct EpiFieldV {
     __device__ __forceinline__ float operator()(int row, int col, float acc) const { return apply(row, col, acc, load(row, col)); }
     __device__ __forceinline__ void row_partial(int, int, float) const {}
     __device__ __forceinline__ void at_z(int) {}
+    struct Col4 { float4 bias; };
+    struct Row4 { float4 gt, gc; int orow; };
+    bool vec_ok() const { return aligned16(V) && ldv % 4 == 0 && aligned16(bias) && aligned16(gt) && aligned16(gc) && ld % 4 == 0; }
+    __device__ __forceinline__ Col4 load_col4(int col) const { Col4 c; c.bias = ldg4(bias + col); return c; }
+    __device__ __forceinline__ Row4 load_row4(int row, int col) const {
+        const long long o = (long long)row * ld + col;
+        Row4 r; r.gt = ldg4(gt + o); r.gc = ldg4(gc + o); r.orow = row_map ? __ldg(row_map + row) : row;
+        return r;
+    }
+    __device__ __forceinline__ float apply4(int, int col, const float4& acc, const Col4& c, const Row4& r) const {
+        float4 v;
+        v.x = sgn * (acc.x + c.bias.x + r.gt.x * r.gc.x); v.y = sgn * (acc.y + c.bias.y + r.gt.y * r.gc.y);
+        v.z = sgn * (acc.z + c.bias.z + r.gt.z * r.gc.z); v.w = sgn * (acc.w + c.bias.w + r.gt.w * r.gc.w);
+        st4(V + (long long)r.orow * ldv + col, v);
+        return 0.0f;
+    }
 };
 // Hutchinson: sum_col z * (acc + gt * hvc)    (:212-214)
 struct EpiFieldDiv {
@@ -71,6 +87,19 @@ struct EpiFieldDiv {
     }
     __device__ __forceinline__ float apply(int, int, float acc, const Aux& a) const { return a.z * (acc + a.gt * a.hvc); }
     __device__ __forceinline__ float operator()(int row, int col, float acc) const { return apply(row, col, acc, load(row, col)); }
+    struct Col4 {};
+    struct Row4 { float4 z, gt, hvc; };
+    bool vec_ok() const { return aligned16(z) && aligned16(gt) && aligned16(hvc) && ld % 4 == 0; }
+    __device__ __forceinline__ Col4 load_col4(int) const { return Col4{}; }
+    __device__ __forceinline__ Row4 load_row4(int row, int col) const {
+        const long long o = (long long)row * ld + col;
+        Row4 r; r.z = ldg4(z + o); r.gt = ldg4(gt + o); r.hvc = ldg4(hvc + o);
+        return r;
+    }
+    __device__ __forceinline__ float apply4(int, int, const float4& acc, const Col4&, const Row4& r) const {
+        return ((r.z.x * (acc.x + r.gt.x * r.hvc.x) + r.z.y * (acc.y + r.gt.y * r.hvc.y)) +
+                (r.z.z * (acc.z + r.gt.z * r.hvc.z) + r.z.w * (acc.w + r.gt.w * r.hvc.w)));
+    }
     __device__ __forceinline__ void row_partial(int row, int tile, float s) const { partial[(long long)row * n_tiles + tile] = s; }
     __device__ __forceinline__ void at_z(int) {}
 };

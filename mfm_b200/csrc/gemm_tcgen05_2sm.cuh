@@ -37,6 +37,8 @@ constexpr int HI_BYTES = A_BYTES + B_BYTES; // 32 KB raw/hi tiles (written by TM
 constexpr int STAGE_BYTES = 2 * HI_BYTES;   // + lo twins
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int TMEM_COLS = 512;              // [0,256): hi*hi sums, [256,512): lo*hi + hi*lo sums
+constexpr uint32_t EPI_LD = 132;            // epilogue staging row pitch in floats (conflict-free float4 rows)
+static_assert(8 * 32 * EPI_LD * 4 <= STAGES * STAGE_BYTES, "epilogue staging must fit in the idle pipeline buffers");
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r;
@@ -75,6 +77,13 @@ __device__ __forceinline__ void mma_commit_2sm(uint64_t* bar) {
                  ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
 
+// optional timeline of one CTA pair (SM clock at 9 events), for tuning: flags bit 1
+#ifdef MFM_TC2_TIMELINE
+#define TC2_MARK(i) do { if (tl && blockIdx.x == 0 && blockIdx.y == gridDim.y / 2 && blockIdx.z == 0 && lane == 0) tl[i] = clock64(); } while (0)
+#else
+#define TC2_MARK(i) do { } while (0)
+#endif
+
 // instruction descriptor: D=f32, A=B=tf32, majors, N>>3 (runtime), M = 256
 __host__ __device__ constexpr uint32_t make_idesc_base(bool a_mn_major, bool b_mn_major) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
@@ -83,7 +92,7 @@ __host__ __device__ constexpr uint32_t make_idesc_base(bool a_mn_major, bool b_m
 
 template <bool A_KMAJOR, bool B_NMAJOR, class Epi>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
-gemm_tc2_kernel(const __grid_constant__ Maps maps, GemmShape p, Epi epi, int raw_hi) {
+gemm_tc2_kernel(const __grid_constant__ Maps maps, GemmShape p, Epi epi, int raw_hi, int vec, long long* tl) {
     extern __shared__ uint8_t smem_raw[];
     // identical carve-up in both CTAs (the dynamic window starts at the same offset in each)
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -107,6 +116,7 @@ gemm_tc2_kernel(const __grid_constant__ Maps maps, GemmShape p, Epi epi, int raw
     const int kz0 = p.k_split > 0 ? blockIdx.z * p.k_split : 0;
     const int Kend = p.k_split > 0 ? min(p.K, kz0 + p.k_split) : p.K;
     const int KT = (Kend - kz0 + BK - 1) / BK;
+    if (warp == 0) TC2_MARK(0);
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a) : "memory");
@@ -124,6 +134,7 @@ gemm_tc2_kernel(const __grid_constant__ Maps maps, GemmShape p, Epi epi, int raw
     cluster_sync_all();                     // barriers of both CTAs initialised before any remote arrive / multicast
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    if (warp == 0) TC2_MARK(1);
 
     if (warp == 0) {
         // ---------------- TMA producer (both CTAs) ----------------
@@ -149,6 +160,7 @@ gemm_tc2_kernel(const __grid_constant__ Maps maps, GemmShape p, Epi epi, int raw
                 const int s = kt % STAGES;
                 const uint32_t ph = (kt / STAGES) & 1;
                 mbar_wait(&split[s], ph);          // arrivals come from both CTAs (mbar_arrive_remote)
+                if (kt == 0) TC2_MARK(4);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES), b_hi = a_hi + A_BYTES;
                 const uint32_t a_lo = a_hi + HI_BYTES, b_lo = b_hi + HI_BYTES;
@@ -170,6 +182,7 @@ gemm_tc2_kernel(const __grid_constant__ Maps maps, GemmShape p, Epi epi, int raw
                 mma_commit_2sm(&empty[s]);
             }
             mma_commit_2sm(acc_full);
+            TC2_MARK(5);
         }
     } else if (warp >= SPLIT_WARP0) {
         // ---------------- splitters (both CTAs) ----------------
@@ -178,12 +191,15 @@ gemm_tc2_kernel(const __grid_constant__ Maps maps, GemmShape p, Epi epi, int raw
             const int s = kt % STAGES;
             const uint32_t ph = (kt / STAGES) & 1;
             mbar_wait(&full[s], ph);
-            float4* hi = (float4*)(smem + s * STAGE_BYTES);
-            float4* lo = (float4*)(smem + s * STAGE_BYTES + HI_BYTES);
+            if (kt == 0 && warp == SPLIT_WARP0) TC2_MARK(2);
+            const uint32_t hi = smem_u32(smem + s * STAGE_BYTES) + (uint32_t)t * 16u;   // explicit shared-space accesses
+            const uint32_t lo = hi + HI_BYTES;
             constexpr int PER = HI_BYTES / 16 / (SPLIT_WARPS * 32);    // 8 float4 per thread
+            constexpr uint32_t STEP = SPLIT_WARPS * 32 * 16;
             float4 v[PER];
 #pragma unroll
-            for (int i = 0; i < PER; ++i) v[i] = hi[t + i * SPLIT_WARPS * 32];
+            for (int i = 0; i < PER; ++i)
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[i].x), "=f"(v[i].y), "=f"(v[i].z), "=f"(v[i].w) : "r"(hi + i * STEP));
             if (raw_hi) {
                 // the tensor core ignores the 13 low mantissa bits of a tf32 operand: leave the raw
                 // fp32 tile in place (hi = trunc(x)) and store only lo = rn_tf32(x - trunc(x))
@@ -194,7 +210,7 @@ gemm_tc2_kernel(const __grid_constant__ Maps maps, GemmShape p, Epi epi, int raw
                     l.y = __uint_as_float(f2tf32(v[i].y - __uint_as_float(__float_as_uint(v[i].y) & 0xFFFFE000u)));
                     l.z = __uint_as_float(f2tf32(v[i].z - __uint_as_float(__float_as_uint(v[i].z) & 0xFFFFE000u)));
                     l.w = __uint_as_float(f2tf32(v[i].w - __uint_as_float(__float_as_uint(v[i].w) & 0xFFFFE000u)));
-                    lo[t + i * SPLIT_WARPS * 32] = l;
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(lo + i * STEP), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
                 }
             } else {
 #pragma unroll
@@ -205,72 +221,124 @@ gemm_tc2_kernel(const __grid_constant__ Maps maps, GemmShape p, Epi epi, int raw
                     split_tf32(v[i].y, hh, ll); h.y = __uint_as_float(hh); l.y = __uint_as_float(ll);
                     split_tf32(v[i].z, hh, ll); h.z = __uint_as_float(hh); l.z = __uint_as_float(ll);
                     split_tf32(v[i].w, hh, ll); h.w = __uint_as_float(hh); l.w = __uint_as_float(ll);
-                    hi[t + i * SPLIT_WARPS * 32] = h;
-                    lo[t + i * SPLIT_WARPS * 32] = l;
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(hi + i * STEP), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(lo + i * STEP), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor core
             __syncwarp();
             if (lane == 0) mbar_arrive_remote(&split[s], 0);
+            if (kt == 0 && warp == SPLIT_WARP0) TC2_MARK(3);
         }
         // ---------------- epilogue (each CTA drains its own 128 rows) ----------------
         mbar_wait(acc_full, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (warp == SPLIT_WARP0) TC2_MARK(6);
         if (p.k_split > 0) epi.at_z(blockIdx.z);
         const int ew = warp - SPLIT_WARP0;            // 0..7
         const int quad = warp & 3;                    // TMEM lane quadrant this warp may access
         const int chalf = ew >> 2;                    // column half (128 columns)
-        float* stg = (float*)smem + ew * (32 * 33);   // pipeline buffers are idle now
         const int row_base = m0 + quad * 32;
-        float rowacc[2] = {0.0f, 0.0f};
+        if (vec) {
+            // Warp block = 32 rows x 128 columns.  TMEM -> registers (main + cross) -> shared memory with a
+            // 132-float row pitch (conflict-free 16-byte stores); then one ROW per warp instruction:
+            // lane l owns columns 4l..4l+3, so every global access is a coalesced 512-byte float4 row
+            // segment and the column-only operands are read once per warp.
+            const uint32_t stg = smem_u32(smem) + (uint32_t)ew * (32u * EPI_LD * 4u);     // pipeline buffers are idle now
 #pragma unroll 1
-        for (int cc = 0; cc < 4; ++cc) {
-            const int col0 = chalf * 128 + cc * 32;
-            if (n0 + col0 >= p.N) break;
-            uint32_t r[32], r2[32];
-            tmem_ld32_nowait(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)col0, r);
-            tmem_ld32_nowait(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(BN + col0), r2);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            for (int cc = 0; cc < 4; ++cc) {
+                const int col0 = chalf * 128 + cc * 32;
+                if (n0 + col0 >= p.N) break;
+                uint32_t r[32], r2[32];
+                tmem_ld32_nowait(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)col0, r);
+                tmem_ld32_nowait(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(BN + col0), r2);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                const uint32_t dst = stg + ((uint32_t)lane * EPI_LD + (uint32_t)cc * 32u) * 4u;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(r[j]) + __uint_as_float(r2[j]);
+                for (int j = 0; j < 8; ++j)
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + j * 16),
+                                 "f"(__uint_as_float(r[4 * j]) + __uint_as_float(r2[4 * j])),
+                                 "f"(__uint_as_float(r[4 * j + 1]) + __uint_as_float(r2[4 * j + 1])),
+                                 "f"(__uint_as_float(r[4 * j + 2]) + __uint_as_float(r2[4 * j + 2])),
+                                 "f"(__uint_as_float(r[4 * j + 3]) + __uint_as_float(r2[4 * j + 3])) : "memory");
+            }
             __syncwarp();
-            const int col = n0 + col0 + lane;
+            const int col = n0 + chalf * 128 + 4 * lane;          // N % 4 == 0: the four columns are valid together
+            const bool cvalid = col < p.N;
+            typename Epi::Col4 ca;
+            if (cvalid) ca = epi.load_col4(col);
+            constexpr int RB = 4;                                  // rows whose global reads are issued together
 #pragma unroll 1
-            for (int r8 = 0; r8 < 32; r8 += 8) {
-                // all global reads of 8 rows first, then the stores: 8+ loads in flight per lane
-                typename Epi::Aux aux[8];
+            for (int r0 = 0; r0 < 32; r0 += RB) {
+                typename Epi::Row4 ra[RB];
+                float4 acc[RB];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int row = row_base + r8 + i;
-                    if (row < M && col < p.N) aux[i] = epi.load(row, col);
+                for (int i = 0; i < RB; ++i) {
+                    const int row = row_base + r0 + i;
+                    if (row < M && cvalid) ra[i] = epi.load_row4(row, col);
                 }
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int row = row_base + r8 + i;
+                for (int i = 0; i < RB; ++i)
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(acc[i].x), "=f"(acc[i].y), "=f"(acc[i].z), "=f"(acc[i].w)
+                                 : "r"(stg + ((uint32_t)(r0 + i) * EPI_LD + 4u * (uint32_t)lane) * 4u));
+#pragma unroll
+                for (int i = 0; i < RB; ++i) {
+                    const int row = row_base + r0 + i;
                     float c = 0.0f;
-                    if (row < M && col < p.N) c = epi.apply(row, col, stg[(r8 + i) * 33 + lane], aux[i]);
+                    if (row < M && cvalid) c = epi.apply4(row, col, acc[i], ca, ra[i]);
                     if (Epi::kRowSum) {
-                        c = warp_sum(c);
-                        if (lane == r8 + i) rowacc[cc >> 1] += c;
+                        // 64-column groups (lanes 0-15 / 16-31), as the mma.sync path's n-tiles
+                        c += __shfl_xor_sync(0xffffffffu, c, 8); c += __shfl_xor_sync(0xffffffffu, c, 4);
+                        c += __shfl_xor_sync(0xffffffffu, c, 2); c += __shfl_xor_sync(0xffffffffu, c, 1);
+                        const int gcol = n0 + chalf * 128 + (lane >> 4) * 64;
+                        if ((lane & 15) == 0 && row < M && gcol < p.N) epi.row_partial(row, gcol / GBN, c);
                     }
                 }
             }
-            __syncwarp();
-        }
-        if (Epi::kRowSum) {
-            const int row = row_base + lane;
-            if (row < M) {
+        } else {
+            float* stgf = (float*)smem + ew * (32 * 33);
+            float rowacc[2] = {0.0f, 0.0f};
+#pragma unroll 1
+            for (int cc = 0; cc < 4; ++cc) {
+                const int col0 = chalf * 128 + cc * 32;
+                if (n0 + col0 >= p.N) break;
+                uint32_t r[32], r2[32];
+                tmem_ld32_nowait(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)col0, r);
+                tmem_ld32_nowait(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(BN + col0), r2);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                    const int tile = (n0 + chalf * 128 + g * 64) / GBN;     // 64-column groups, as the mma.sync path
-                    if (n0 + chalf * 128 + g * 64 < p.N) epi.row_partial(row, tile, rowacc[g]);
+                for (int j = 0; j < 32; ++j) stgf[lane * 33 + j] = __uint_as_float(r[j]) + __uint_as_float(r2[j]);
+                __syncwarp();
+                const int col = n0 + col0 + lane;
+#pragma unroll 4
+                for (int rr = 0; rr < 32; ++rr) {
+                    const int row = row_base + rr;
+                    float c = 0.0f;
+                    if (row < M && col < p.N) c = epi(row, col, stgf[rr * 33 + lane]);
+                    if (Epi::kRowSum) {
+                        c = warp_sum(c);
+                        if (lane == rr) rowacc[cc >> 1] += c;
+                    }
+                }
+                __syncwarp();
+            }
+            if (Epi::kRowSum) {
+                const int row = row_base + lane;
+                if (row < M) {
+#pragma unroll
+                    for (int g = 0; g < 2; ++g) {
+                        const int tile = (n0 + chalf * 128 + g * 64) / GBN;     // 64-column groups, as the mma.sync path
+                        if (n0 + chalf * 128 + g * 64 < p.N) epi.row_partial(row, tile, rowacc[g]);
+                    }
                 }
             }
         }
     }
+    if (warp == SPLIT_WARP0) TC2_MARK(7);
     __syncwarp();
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     cluster_sync_all();                     // the peer's shared memory / TMEM stay alive until both are done
+    if (warp == 0) TC2_MARK(8);
     if (warp == 2) {
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
     }
@@ -283,6 +351,7 @@ inline bool eligible(const GemmShape& p) {
     return p.M >= 2 * BM;                   // smaller problems: single-CTA kernel
 }
 
+long long* gemm_timeline();                 // device buffer for the timeline of one CTA pair, or null (MFM_TC2_TIMELINE builds)
 int gemm_raw_hi();                          // 1: rely on the tensor core truncating tf32 operands (env MFM_TC_RAWHI)
 
 template <bool A_KMAJOR, bool B_NMAJOR, class Epi>
@@ -299,7 +368,8 @@ inline cudaError_t launch(const GemmShape& p, const Epi& epi, cudaStream_t st) {
         configured = true;
     }
     dim3 grid(2 * ((p.N + BN - 1) / BN), (p.M + 2 * BM - 1) / (2 * BM), p.k_split > 0 ? (p.K + p.k_split - 1) / p.k_split : 1);
-    kern<<<grid, THREADS, SMEM_BYTES, st>>>(maps, p, epi, gemm_raw_hi());
+    const int vec = (p.N % 4 == 0 && epi.vec_ok()) ? 1 : 0;         // float4 epilogue when everything is 16-byte aligned
+    kern<<<grid, THREADS, SMEM_BYTES, st>>>(maps, p, epi, gemm_raw_hi(), vec, gemm_timeline());
     ++g_mfm_launches;
     return cudaGetLastError();
 }

@@ -235,6 +235,17 @@ inline cudaError_t launch_gemm_mma(const GemmShape& p, const Epi& epi, cudaStrea
 
 inline int gemm_n_tiles(int N) { return (N + GBN - 1) / GBN; }
 
+// ---- helpers of the 4-column (float4) epilogue interface used by the CTA-pair kernel ------------
+//   struct Col4 / Row4;  Col4 load_col4(col): column-only reads (hoisted out of the row loop);
+//   Row4 load_row4(row, col): per-row reads;  float apply4(row, col, acc4, Col4, Row4): stores columns
+//   col..col+3 of one row and returns their row-sum contribution;  bool vec_ok() (host): every
+//   pointer 16-byte aligned and every leading dimension a multiple of 4.
+__host__ __device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float4 f4(float v) { return make_float4(v, v, v, v); }
+
 // ---- standard epilogue: C = mask(relu(alpha*acc + bias) ) (+ add) ----------------------------
 struct EpiStd {
     static constexpr bool kRowSum = false;
@@ -263,6 +274,30 @@ struct EpiStd {
     }
     __device__ __forceinline__ float operator()(int row, int col, float acc) const { return apply(row, col, acc, load(row, col)); }
     __device__ __forceinline__ void row_partial(int, int, float) const {}
+    // float4 interface
+    struct Col4 { float4 bias; };
+    struct Row4 { float4 add, mask; };
+    bool vec_ok() const {
+        return aligned16(C) && ldc % 4 == 0 && c_zstride % 4 == 0 && (!bias || aligned16(bias)) &&
+               (!mask || (aligned16(mask) && ldm % 4 == 0)) && (!add || (aligned16(add) && ldadd % 4 == 0));
+    }
+    __device__ __forceinline__ Col4 load_col4(int col) const { Col4 c; c.bias = bias ? ldg4(bias + col) : f4(0.0f); return c; }
+    __device__ __forceinline__ Row4 load_row4(int row, int col) const {
+        Row4 r;
+        r.add = add ? ld4(add + (long long)row * ldadd + col) : f4(0.0f);        // may alias C: plain load
+        r.mask = mask ? ldg4(mask + (long long)(mask_div == 1 ? row : row / mask_div) * ldm + col) : f4(1.0f);
+        return r;
+    }
+    __device__ __forceinline__ float apply4(int row, int col, const float4& acc, const Col4& c, const Row4& r) const {
+        float4 v;
+        v.x = alpha * acc.x + c.bias.x + r.add.x; v.y = alpha * acc.y + c.bias.y + r.add.y;
+        v.z = alpha * acc.z + c.bias.z + r.add.z; v.w = alpha * acc.w + c.bias.w + r.add.w;
+        if (relu) { v.x = fmaxf(v.x, 0.0f); v.y = fmaxf(v.y, 0.0f); v.z = fmaxf(v.z, 0.0f); v.w = fmaxf(v.w, 0.0f); }
+        v.x = r.mask.x > 0.0f ? v.x : 0.0f; v.y = r.mask.y > 0.0f ? v.y : 0.0f;
+        v.z = r.mask.z > 0.0f ? v.z : 0.0f; v.w = r.mask.w > 0.0f ? v.w : 0.0f;
+        st4(C + (long long)row * ldc + col, v);
+        return 0.0f;
+    }
 };
 
 }  // namespace mfm

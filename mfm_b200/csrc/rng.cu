@@ -33,6 +33,19 @@ int gemm_raw_hi() {
 }
 }
 extern "C" void mfm_set_gemm_raw_hi(int v) { mfm::tc2::g_raw_hi = v ? 1 : 0; }
+// tuning aid (not part of the ABI header): SM-clock timeline of one CTA pair of the last tc2 GEMM
+namespace mfm { namespace tc2 {
+static long long* g_timeline_buf = nullptr;
+static int g_timeline = 0;
+long long* gemm_timeline() { return g_timeline ? g_timeline_buf : nullptr; }
+} }
+extern "C" int mfm_debug_gemm_timeline(int enable, long long* out16) {
+    using namespace mfm::tc2;
+    if (!g_timeline_buf && cudaMalloc(&g_timeline_buf, 16 * sizeof(long long)) != cudaSuccess) return -1;
+    g_timeline = enable ? 1 : 0;
+    if (out16) return cudaMemcpy(out16, g_timeline_buf, 16 * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -1;
+    return 0;
+}
 extern "C" void mfm_set_gemm_backend(int b) { mfm::g_backend = b; }
 extern "C" unsigned long long mfm_launch_count(void) { return g_mfm_launches; }
 

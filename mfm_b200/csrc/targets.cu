@@ -83,6 +83,19 @@ struct EpiPinesGrad {
         return (u.x - mu) * q;
     }
     __device__ __forceinline__ float operator()(int row, int col, float acc) const { return apply(row, col, acc, load(row, col)); }
+    struct Col4 { float4 kinv_mu, counts; };
+    struct Row4 { float4 x; };
+    bool vec_ok() const { return aligned16(X) && ldx % 4 == 0 && aligned16(grad) && ldg % 4 == 0 && aligned16(counts) && aligned16(kinv_mu); }
+    __device__ __forceinline__ Col4 load_col4(int col) const { Col4 c; c.kinv_mu = ldg4(kinv_mu + col); c.counts = ldg4(counts + col); return c; }
+    __device__ __forceinline__ Row4 load_row4(int row, int col) const { Row4 r; r.x = ldg4(X + (long long)row * ldx + col); return r; }
+    __device__ __forceinline__ float apply4(int row, int col, const float4& acc, const Col4& c, const Row4& r) const {
+        const float4 q = make_float4(acc.x - c.kinv_mu.x, acc.y - c.kinv_mu.y, acc.z - c.kinv_mu.z, acc.w - c.kinv_mu.w);
+        float4 g;
+        g.x = beta * (c.counts.x - a * expf(r.x.x)) - q.x; g.y = beta * (c.counts.y - a * expf(r.x.y)) - q.y;
+        g.z = beta * (c.counts.z - a * expf(r.x.z)) - q.z; g.w = beta * (c.counts.w - a * expf(r.x.w)) - q.w;
+        st4(grad + (long long)row * ldg + col, g);
+        return ((r.x.x - mu) * q.x + (r.x.y - mu) * q.y) + ((r.x.z - mu) * q.z + (r.x.w - mu) * q.w);
+    }
     __device__ __forceinline__ void row_partial(int row, int tile, float s) const {
         if (partial) partial[(long long)row * n_tiles + tile] = s;
     }
@@ -114,6 +127,43 @@ struct EpiPinesField {
         return 0.0f;
     }
     __device__ __forceinline__ float operator()(int row, int col, float acc) const { return apply(row, col, acc, load(row, col)); }
+    struct Col4 { float4 counts, kinv_mu, kdiag; };
+    struct Row4 { float4 x, z, zk; };
+    bool vec_ok() const {
+        return aligned16(X) && ldx % 4 == 0 && ld % 4 == 0 && aligned16(counts) && aligned16(kinv_mu) && aligned16(gc) &&
+               (!hvc || (aligned16(hvc) && aligned16(Z) && aligned16(ZK))) && (!hdc || (aligned16(hdc) && aligned16(kinv_diag)));
+    }
+    __device__ __forceinline__ Col4 load_col4(int col) const {
+        Col4 c; c.counts = ldg4(counts + col); c.kinv_mu = ldg4(kinv_mu + col); c.kdiag = hdc ? ldg4(kinv_diag + col) : f4(0.0f);
+        return c;
+    }
+    __device__ __forceinline__ Row4 load_row4(int row, int col) const {
+        const long long o = (long long)row * ld + col;
+        Row4 r; r.x = ldg4(X + (long long)row * ldx + col);
+        r.z = hvc ? ldg4(Z + o) : f4(0.0f); r.zk = hvc ? ldg4(ZK + o) : f4(0.0f);
+        return r;
+    }
+    __device__ __forceinline__ void one(float acc, float x, float cnt, float kmu, float kd, float z, float zk,
+                                        float& g_out, float& hv_out, float& hd_out) const {
+        const float e = a * expf(x);
+        const float g = cnt - e - (acc - kmu);
+        const bool in = !(clip > 0.0f) || (g > -clip && g < clip);
+        g_out = clip > 0.0f ? fminf(fmaxf(g, -clip), clip) : g;
+        hv_out = in ? (-e * z - zk) : 0.0f;
+        hd_out = in ? (-e - kd) : 0.0f;
+    }
+    __device__ __forceinline__ float apply4(int row, int col, const float4& acc, const Col4& c, const Row4& r) const {
+        const long long o = (long long)row * ld + col;
+        float4 g, hv, hd;
+        one(acc.x, r.x.x, c.counts.x, c.kinv_mu.x, c.kdiag.x, r.z.x, r.zk.x, g.x, hv.x, hd.x);
+        one(acc.y, r.x.y, c.counts.y, c.kinv_mu.y, c.kdiag.y, r.z.y, r.zk.y, g.y, hv.y, hd.y);
+        one(acc.z, r.x.z, c.counts.z, c.kinv_mu.z, c.kdiag.z, r.z.z, r.zk.z, g.z, hv.z, hd.z);
+        one(acc.w, r.x.w, c.counts.w, c.kinv_mu.w, c.kdiag.w, r.z.w, r.zk.w, g.w, hv.w, hd.w);
+        st4(gc + o, g);
+        if (hvc) st4(hvc + o, hv);
+        if (hdc) st4(hdc + o, hd);
+        return 0.0f;
+    }
     __device__ __forceinline__ void row_partial(int, int, float) const {}
     __device__ __forceinline__ void at_z(int) {}
 };

@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--json", default=None)
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--timeline", action="store_true", help="needs a MFM_TC2_TIMELINE=1 build")
     ap.add_argument("--only", default=None, help="comma-separated shape labels")
     ap.add_argument("--kernels", default="pair,pair_rawhi,tc1,mma")
     args = ap.parse_args()
@@ -84,6 +85,17 @@ def main():
                 torch.cuda.synchronize()
                 ts.append(e0.elapsed_time(e1))
             ms = float(np.median(ts))
+            if args.timeline and name.startswith("pair"):
+                import ctypes
+                buf = (ctypes.c_longlong * 16)()
+                lib.mfm_debug_gemm_timeline(1, None)
+                run(lib, M, N, K, akm, bnm, A, B, bias, C, st)
+                torch.cuda.synchronize()
+                lib.mfm_debug_gemm_timeline(0, buf)
+                t = list(buf)
+                names = ["entry", "prologue done", "first TMA landed", "first split done", "first MMA issue",
+                         "last MMA issued", "accumulator ready", "epilogue done", "after final cluster sync"]
+                print("   timeline (SM clocks since entry): " + ", ".join(f"{nm}={t[i] - t[0]}" for i, nm in enumerate(names)))
             rec[name] = {"rel_err": err, "finite": finite, "ms": ms, "tflops": 2.0 * M * N * K / ms / 1e9}
             print(f"{label:12s} {name:10s} M={M} N={N} K={K} err={err:.2e} finite={finite} {ms:8.3f} ms "
                   f"{rec[name]['tflops']:7.1f} TFLOP/s", flush=True)
