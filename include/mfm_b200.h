@@ -80,9 +80,10 @@ const char* mfm_last_error(void);
 int mfm_version(void);
 /* number of CUDA kernels this library has launched in the calling process (diagnostics / bench) */
 unsigned long long mfm_launch_count(void);
-/* dense-layer backend: 0 = auto (tcgen05/TMEM/TMA kernels: CTA-pair cta_group::2 tiles when M >= 256, single-CTA
- * tiles when the shape is otherwise eligible), 1 = warp-level mma.sync kernel only, 2 = single-CTA tcgen05 only.
- * Same 3xTF32 arithmetic every way; also selectable with the environment variable MFM_GEMM=mma|tc1. */
+/* dense-layer backend: 0 = auto (tcgen05/TMEM/TMA kernels: persistent CTA-pair cta_group::2 kernel when M >= 256,
+ * single-CTA tiles when the shape is otherwise eligible), 1 = warp-level mma.sync kernel only, 2 = single-CTA tcgen05
+ * only, 3 = one-tile CTA-pair kernel (separate cross-term accumulators: 3x smaller accumulator-truncation bias, no
+ * epilogue overlap).  Same 3xTF32 arithmetic every way; environment variable MFM_GEMM=mma|tc1|tc2. */
 void mfm_set_gemm_backend(int backend);
 /* CTA-pair kernel operand split: 1 (default) = leave the raw fp32 tile as the hi operand (the tensor core ignores the
  * 13 low mantissa bits of a tf32 operand; measured on B200) and store only lo = rn_tf32(x - trunc(x)), which saves

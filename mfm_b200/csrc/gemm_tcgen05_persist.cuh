@@ -1,0 +1,318 @@
+// Persistent CTA-pair 3xTF32 GEMM: gemm_tcgen05_2sm.cuh's pair tile (256 x 256, cta_group::2, in-kernel
+// hi/lo split) with the epilogue of tile i overlapped with the main loop of tile i+1.
+//
+// Measured on B200 (scripts/gemm_bench.py --timeline) for the one-tile-per-pair kernel at K = 1024:
+// main loop 48.3 k clocks (1 510 clk per 32-wide k-block = 98 % of the kind::tf32 issue rate), but
+// 4.1 k prologue + pipeline fill, 1.3 k drain, 11.7 k epilogue (all SMs write C in lock-step, so the
+// phase is HBM-write bound) and 1.6 k teardown per tile: 28 % of the tile is not MMA.  Here one pair
+// per TPC stays resident and walks a static tile list:
+//   warp 0        TMA producer          (runs ahead across tiles; 3-stage ring, 64 KB per stage)
+//   warp 1        MMA issuer (leader)   accumulator buffer b = tile & 1 (TMEM columns b*256 .. +255)
+//   warp 2        TMEM allocator
+//   warps 4-11    splitters             hi (raw, truncated by the tensor core) / lo = rn_tf32(x - trunc x)
+//   warps 12-15   epilogue              drain buffer b while the MMAs fill buffer b^1
+// TMEM holds 512 columns, so two 256-column buffers leave no room for a separate cross-term
+// accumulator: lo*hi, hi*lo and hi*hi of a k-step accumulate into the same buffer.  The tensor core's
+// fp32 accumulator truncates on every add, so this costs accuracy: measured bias ~ 7.5e-9 * K relative
+// (separate accumulators: 2.5e-9 * K).  MFM_GEMM=tc2 selects the one-tile kernel when that matters.
+//
+// Epilogue: a warp owns 32 rows (its TMEM lane quadrant) x 256 columns, drained in 32-column chunks:
+// tcgen05.ld -> shared memory (36-float pitch) -> 8 steps of 4 rows x 128 bytes, float4 per lane, through
+// the functors' Col4/Row4 interface (gemm_tf32x3.cuh).  Buffer b is released (remote arrive on the
+// leader's acc_empty[b]) as soon as the last chunk has left TMEM.
+#pragma once
+#include "gemm_tcgen05_2sm.cuh"
+
+namespace mfm {
+namespace tc2p {
+
+using tc::smem_u32; using tc::mbar_init; using tc::mbar_expect_tx; using tc::mbar_wait; using tc::tma_load_2d;
+using tc::tma_load_3d; using tc::tmem_ld32_nowait; using tc::make_desc; using tc::Maps;
+using tc2::cluster_ctarank; using tc2::cluster_sync_all; using tc2::mbar_arrive_remote; using tc2::mma_tf32_ss_2sm;
+using tc2::mma_commit_2sm; using tc2::make_idesc_base;
+
+constexpr int BM = 128, BN = 256, BNH = BN / 2, BK = 32, STAGES = 3;
+constexpr int THREADS = 512;                // 16 warps
+constexpr int SPLIT_WARP0 = 4, SPLIT_WARPS = 8, EPI_WARP0 = 12, EPI_WARPS = 4;
+constexpr int A_BYTES = BM * BK * 4, B_BYTES = BNH * BK * 4;
+constexpr int HI_BYTES = A_BYTES + B_BYTES; // 32 KB
+constexpr int STAGE_BYTES = 2 * HI_BYTES;   // 64 KB
+constexpr uint32_t EPI_LD = 36;             // staging row pitch (floats): conflict-free float4 rows of a 32x32 chunk
+constexpr int EPI_STG_BYTES = EPI_WARPS * 32 * EPI_LD * 4;      // 18 KB
+constexpr int NBARS = 3 * STAGES + 4;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STG_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int TMEM_COLS = 512;
+static_assert(NBARS * 8 + 8 <= 256, "barrier area");
+
+struct Tiles {
+    int m_tiles, n_tiles, z_tiles, total;
+};
+__host__ __device__ inline Tiles make_tiles(int M, int N, int K, int k_split) {
+    Tiles t;
+    t.m_tiles = (M + 2 * BM - 1) / (2 * BM);
+    t.n_tiles = (N + BN - 1) / BN;
+    t.z_tiles = k_split > 0 ? (K + k_split - 1) / k_split : 1;
+    t.total = t.m_tiles * t.n_tiles * t.z_tiles;
+    return t;
+}
+
+template <bool A_KMAJOR, bool B_NMAJOR, class Epi>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+gemm_tc2p_kernel(const __grid_constant__ Maps maps, GemmShape p, Epi epi) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* stg_base = smem + STAGES * STAGE_BYTES;
+    uint64_t* bars = (uint64_t*)(stg_base + EPI_STG_BYTES);
+    uint64_t* full = bars;                      // own TMA landed                      (local)
+    uint64_t* split = bars + STAGES;            // lo tiles of BOTH CTAs ready          (leader's copy is used)
+    uint64_t* empty = bars + 2 * STAGES;        // MMAs done reading the stage          (multicast commit)
+    uint64_t* acc_full = bars + 3 * STAGES;     // [2] accumulator buffer complete      (multicast commit)
+    uint64_t* acc_empty = bars + 3 * STAGES + 2;// [2] buffer drained by BOTH CTAs      (leader's copy is used)
+    uint32_t* tmem_slot = (uint32_t*)(bars + NBARS);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int M = p.n_rows_dev ? min(*p.n_rows_dev, p.M) : p.M;
+    const Tiles T = make_tiles(M, p.N, p.K, p.k_split);
+    if (T.total == 0) return;                   // uniform over the grid
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.b) : "memory");
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&split[s], 2 * SPLIT_WARPS); mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 2 * EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    // tile t -> (z, row tile, column tile); column tiles vary fastest so concurrent pairs share A rows
+    auto tile_origin = [&](int t, int& m0p, int& n0, int& kz0, int& KT, int& neff, int& z) {
+        const int per_z = T.m_tiles * T.n_tiles;
+        z = t / per_z;
+        const int r = t - z * per_z;
+        m0p = (r / T.n_tiles) * (2 * BM);
+        n0 = (r % T.n_tiles) * BN;
+        kz0 = p.k_split > 0 ? z * p.k_split : 0;
+        const int Kend = p.k_split > 0 ? min(p.K, kz0 + p.k_split) : p.K;
+        KT = (Kend - kz0 + BK - 1) / BK;
+        const int nrem = p.N - n0;
+        neff = nrem >= BN ? BN : ((nrem + 63) / 64) * 64;
+    };
+
+    if (warp == 0) {
+        // ---------------- TMA producer (both CTAs) ----------------
+        if (lane == 0) {
+            uint32_t g = 0;                     // k-blocks issued so far (ring position)
+            for (int t = pair; t < T.total; t += n_pairs) {
+                int m0p, n0, kz0, KT, neff, z;
+                tile_origin(t, m0p, n0, kz0, KT, neff, z);
+                const int m0 = m0p + (int)rank * BM;
+                const int nb0 = n0 + (int)rank * (neff / 2);
+                for (int kt = 0; kt < KT; ++kt, ++g) {
+                    const uint32_t s = g % STAGES, ph = (g / STAGES) & 1;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    uint8_t* st = smem + s * STAGE_BYTES;
+                    mbar_expect_tx(&full[s], HI_BYTES);
+                    const int k0 = kz0 + kt * BK;
+                    if (A_KMAJOR) tma_load_2d(st, &maps.a, &full[s], k0, m0);
+                    else          tma_load_3d(st, &maps.a, &full[s], 0, k0, m0 / 32);
+                    if (!B_NMAJOR) tma_load_2d(st + A_BYTES, &maps.b, &full[s], k0, nb0);
+                    else           tma_load_3d(st + A_BYTES, &maps.b, &full[s], 0, k0, nb0 / 32);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------- MMA issuer (leader CTA only) ----------------
+        if (rank == 0 && lane == 0) {
+            uint32_t g = 0, i = 0;
+            for (int t = pair; t < T.total; t += n_pairs, ++i) {
+                int m0p, n0, kz0, KT, neff, z;
+                tile_origin(t, m0p, n0, kz0, KT, neff, z);
+                const uint32_t b = i & 1, u = i >> 1;
+                const uint32_t idesc = make_idesc_base(!A_KMAJOR, B_NMAJOR) | ((uint32_t)(neff >> 3) << 17);
+                const uint32_t acc = tmem_base + b * BN;
+                mbar_wait(&acc_empty[b], (u & 1) ^ 1);          // both CTAs have drained this buffer (tile i-2)
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (int kt = 0; kt < KT; ++kt, ++g) {
+                    const uint32_t s = g % STAGES, ph = (g / STAGES) & 1;
+                    mbar_wait(&split[s], ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES), b_hi = a_hi + A_BYTES;
+                    const uint32_t a_lo = a_hi + HI_BYTES, b_lo = b_hi + HI_BYTES;
+#pragma unroll
+                    for (int ks = 0; ks < BK / 8; ++ks) {
+                        const uint32_t ao = A_KMAJOR ? ks * 32 : ks * 1024;
+                        const uint32_t bo = !B_NMAJOR ? ks * 32 : ks * 1024;
+                        const uint32_t albo = A_KMAJOR ? 16 : 4096, blbo = !B_NMAJOR ? 16 : 4096;
+                        const uint32_t asbo = A_KMAJOR ? 1024 : 512, bsbo = !B_NMAJOR ? 1024 : 512;
+                        const uint32_t alt = A_KMAJOR ? 2 : 1, blt = !B_NMAJOR ? 2 : 1;
+                        const uint64_t dah = make_desc(a_hi + ao, albo, asbo, alt), dal = make_desc(a_lo + ao, albo, asbo, alt);
+                        const uint64_t dbh = make_desc(b_hi + bo, blbo, bsbo, blt), dbl = make_desc(b_lo + bo, blbo, bsbo, blt);
+                        mma_tf32_ss_2sm(acc, dal, dbh, idesc, (kt | ks) != 0);
+                        mma_tf32_ss_2sm(acc, dah, dbl, idesc, 1);
+                        mma_tf32_ss_2sm(acc, dah, dbh, idesc, 1);
+                    }
+                    mma_commit_2sm(&empty[s]);
+                }
+                mma_commit_2sm(&acc_full[b]);
+            }
+        }
+    } else if (warp >= SPLIT_WARP0 && warp < EPI_WARP0) {
+        // ---------------- splitters (both CTAs) ----------------
+        const int tix = threadIdx.x - SPLIT_WARP0 * 32;
+        uint32_t g = 0;
+        for (int t = pair; t < T.total; t += n_pairs) {
+            int m0p, n0, kz0, KT, neff, z;
+            tile_origin(t, m0p, n0, kz0, KT, neff, z);
+            for (int kt = 0; kt < KT; ++kt, ++g) {
+                const uint32_t s = g % STAGES, ph = (g / STAGES) & 1;
+                mbar_wait(&full[s], ph);
+                const uint32_t hi = smem_u32(smem + s * STAGE_BYTES) + (uint32_t)tix * 16u;
+                const uint32_t lo = hi + HI_BYTES;
+                constexpr int PER = HI_BYTES / 16 / (SPLIT_WARPS * 32);    // 8 float4 per thread
+                constexpr uint32_t STEP = SPLIT_WARPS * 32 * 16;
+                float4 v[PER];
+#pragma unroll
+                for (int k = 0; k < PER; ++k)
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[k].x), "=f"(v[k].y), "=f"(v[k].z), "=f"(v[k].w) : "r"(hi + k * STEP));
+                // hi = the raw fp32 tile (the tensor core ignores the 13 low mantissa bits); lo = rn_tf32(x - trunc(x))
+#pragma unroll
+                for (int k = 0; k < PER; ++k) {
+                    float4 l;
+                    l.x = __uint_as_float(f2tf32(v[k].x - __uint_as_float(__float_as_uint(v[k].x) & 0xFFFFE000u)));
+                    l.y = __uint_as_float(f2tf32(v[k].y - __uint_as_float(__float_as_uint(v[k].y) & 0xFFFFE000u)));
+                    l.z = __uint_as_float(f2tf32(v[k].z - __uint_as_float(__float_as_uint(v[k].z) & 0xFFFFE000u)));
+                    l.w = __uint_as_float(f2tf32(v[k].w - __uint_as_float(__float_as_uint(v[k].w) & 0xFFFFE000u)));
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(lo + k * STEP), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor core
+                __syncwarp();
+                if (lane == 0) mbar_arrive_remote(&split[s], 0);
+            }
+        }
+    } else if (warp >= EPI_WARP0) {
+        // ---------------- epilogue (each CTA drains its own 128 TMEM lanes) ----------------
+        const int ew = warp - EPI_WARP0;              // == warp & 3: the TMEM lane quadrant this warp may access
+        const uint32_t stg = smem_u32(stg_base) + (uint32_t)ew * (32u * EPI_LD * 4u);
+        const int rsub = lane >> 3, cpiece = (lane & 7) * 4;
+        constexpr int RB = sizeof(typename Epi::Row4) > 36 ? 2 : 4;     // steps whose global reads are issued together
+        uint32_t i = 0;
+        for (int t = pair; t < T.total; t += n_pairs, ++i) {
+            int m0p, n0, kz0, KT, neff, z;
+            tile_origin(t, m0p, n0, kz0, KT, neff, z);
+            const uint32_t b = i & 1, u = i >> 1;
+            Epi e = epi;
+            if (p.k_split > 0) e.at_z(z);
+            const int row_base = m0p + (int)rank * BM + ew * 32;
+            const int n_chunks = min(BN / 32, (p.N - n0 + 31) / 32);
+            mbar_wait(&acc_full[b], u & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            float rs[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) rs[k] = 0.0f;
+#pragma unroll 1
+            for (int cc = 0; cc < n_chunks; ++cc) {
+                const int col0 = cc * 32;
+                uint32_t r[32];
+                tmem_ld32_nowait(tmem_base + ((uint32_t)(ew * 32) << 16) + b * BN + (uint32_t)col0, r);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (cc == n_chunks - 1) {
+                    // the last chunk has left TMEM: hand the buffer back to the MMA issuer
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_remote(&acc_empty[b], 0);
+                }
+                const uint32_t dst = stg + (uint32_t)lane * (EPI_LD * 4u);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + j * 16), "f"(__uint_as_float(r[4 * j])),
+                                 "f"(__uint_as_float(r[4 * j + 1])), "f"(__uint_as_float(r[4 * j + 2])), "f"(__uint_as_float(r[4 * j + 3])) : "memory");
+                __syncwarp();
+                const int col = n0 + col0 + cpiece;           // N % 4 == 0: the four columns are valid together
+                const bool cvalid = col < p.N;
+                typename Epi::Col4 ca;
+                if (cvalid) ca = e.load_col4(col);
+#pragma unroll
+                for (int it0 = 0; it0 < 8; it0 += RB) {
+                    typename Epi::Row4 ra[RB];
+                    float4 acc[RB];
+#pragma unroll
+                    for (int k = 0; k < RB; ++k) {
+                        const int row = row_base + (it0 + k) * 4 + rsub;
+                        if (row < M && cvalid) ra[k] = e.load_row4(row, col);
+                    }
+#pragma unroll
+                    for (int k = 0; k < RB; ++k)
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(acc[k].x), "=f"(acc[k].y), "=f"(acc[k].z), "=f"(acc[k].w)
+                                     : "r"(stg + ((uint32_t)((it0 + k) * 4 + rsub) * EPI_LD + (uint32_t)cpiece) * 4u));
+#pragma unroll
+                    for (int k = 0; k < RB; ++k) {
+                        const int row = row_base + (it0 + k) * 4 + rsub;
+                        float c = 0.0f;
+                        if (row < M && cvalid) c = e.apply4(row, col, acc[k], ca, ra[k]);
+                        if (Epi::kRowSum) {
+                            c += __shfl_xor_sync(0xffffffffu, c, 4); c += __shfl_xor_sync(0xffffffffu, c, 2);
+                            c += __shfl_xor_sync(0xffffffffu, c, 1);
+                            rs[it0 + k] += c;               // 32-column sums; pairs of chunks make the 64-column groups
+                        }
+                    }
+                }
+                if (Epi::kRowSum && ((cc & 1) || cc == n_chunks - 1)) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int row = row_base + k * 4 + rsub;
+                        if ((lane & 7) == 0 && row < M) e.row_partial(row, (n0 + (cc & ~1) * 32) / GBN, rs[k]);
+                        rs[k] = 0.0f;
+                    }
+                }
+                __syncwarp();                                 // staging is reused by the next chunk
+            }
+        }
+    }
+    __syncwarp();
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();                     // the peer's shared memory / TMEM / barriers stay alive until both are done
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---- host side ----------------------------------------------------------------------------------
+template <bool A_KMAJOR, bool B_NMAJOR, class Epi>
+inline bool eligible(const GemmShape& p, const Epi& epi) {
+    return tc2::eligible<A_KMAJOR, B_NMAJOR>(p) && p.N % 4 == 0 && epi.vec_ok();
+}
+
+int sm_pairs();                             // number of TPC pairs to keep resident (74 on B200)
+
+template <bool A_KMAJOR, bool B_NMAJOR, class Epi>
+inline cudaError_t launch(const GemmShape& p, const Epi& epi, cudaStream_t st) {
+    Maps maps;
+    bool ok = A_KMAJOR ? tc::make_map_kmajor(&maps.a, p.A, p.lda, p.M, p.K, BM) : tc::make_map_mnmajor(&maps.a, p.A, p.lda, p.M, p.K, BM / 32);
+    ok = ok && (!B_NMAJOR ? tc::make_map_kmajor(&maps.b, p.B, p.ldb, p.N, p.K, BNH) : tc::make_map_mnmajor(&maps.b, p.B, p.ldb, p.N, p.K, BNH / 32));
+    if (!ok) return cudaErrorInvalidValue;
+    auto kern = gemm_tc2p_kernel<A_KMAJOR, B_NMAJOR, Epi>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const Tiles T = make_tiles(p.M, p.N, p.K, p.k_split);
+    const int pairs = T.total < sm_pairs() ? T.total : sm_pairs();
+    kern<<<dim3(2 * pairs), THREADS, SMEM_BYTES, st>>>(maps, p, epi);
+    ++g_mfm_launches;
+    return cudaGetLastError();
+}
+
+}  // namespace tc2p
+}  // namespace mfm

@@ -306,21 +306,28 @@ struct EpiStd {
 // medium ones, warp-level kernel otherwise ----
 #include "gemm_tcgen05.cuh"
 #include "gemm_tcgen05_2sm.cuh"
+#include "gemm_tcgen05_persist.cuh"
 namespace mfm {
-// 0 = auto, 1 = force mma.sync (env MFM_GEMM=mma), 2 = tcgen05 single-CTA only (env MFM_GEMM=tc1)
+// 0 = auto, 1 = force mma.sync (env MFM_GEMM=mma), 2 = tcgen05 single-CTA only (env MFM_GEMM=tc1),
+// 3 = no persistent kernel: one-tile CTA-pair kernel with separate cross-term accumulators (env MFM_GEMM=tc2)
 int gemm_backend();
 template <bool A_KMAJOR, bool B_NMAJOR>
 inline int gemm_path(const GemmShape& p) {       // 2 = CTA pair, 1 = single CTA, 0 = mma.sync
     const int be = gemm_backend();
     if (be == 1) return 0;
-    if (be == 0 && tc2::eligible<A_KMAJOR, B_NMAJOR>(p)) return 2;
+    if ((be == 0 || be == 3) && tc2::eligible<A_KMAJOR, B_NMAJOR>(p)) return 2;
     return tc::eligible<A_KMAJOR, B_NMAJOR>(p) ? 1 : 0;
 }
 template <bool A_KMAJOR, bool B_NMAJOR, class Epi>
 inline cudaError_t launch_gemm(const GemmShape& p, const Epi& epi, cudaStream_t st) {
     if (p.M <= 0 || p.N <= 0) return cudaSuccess;
     switch (gemm_path<A_KMAJOR, B_NMAJOR>(p)) {
-        case 2: return tc2::launch<A_KMAJOR, B_NMAJOR, Epi>(p, epi, st);
+        case 2:
+            // persistent (epilogue overlapped with the next tile's MMAs) unless the reduction is split:
+            // split-K tiles have long main loops (nothing to hide) and need the separate accumulators
+            if (gemm_backend() == 0 && p.k_split == 0 && tc2p::eligible<A_KMAJOR, B_NMAJOR>(p, epi))
+                return tc2p::launch<A_KMAJOR, B_NMAJOR, Epi>(p, epi, st);
+            return tc2::launch<A_KMAJOR, B_NMAJOR, Epi>(p, epi, st);
         case 1: return tc::launch<A_KMAJOR, B_NMAJOR, Epi>(p, epi, st);
         default: return launch_gemm_mma<A_KMAJOR, B_NMAJOR, Epi>(p, epi, st);
     }

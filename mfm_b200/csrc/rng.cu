@@ -20,9 +20,20 @@ static int g_backend = -1;
 int gemm_backend() {
     if (g_backend < 0) {
         const char* e = getenv("MFM_GEMM");
-        g_backend = (e && strcmp(e, "mma") == 0) ? 1 : ((e && strcmp(e, "tc1") == 0) ? 2 : 0);
+        g_backend = (e && strcmp(e, "mma") == 0) ? 1 : ((e && strcmp(e, "tc1") == 0) ? 2 : ((e && strcmp(e, "tc2") == 0) ? 3 : 0));
     }
     return g_backend;
+}
+namespace tc2p {
+int sm_pairs() {
+    static int pairs = 0;
+    if (pairs == 0) {
+        int dev = 0, sms = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 2) sms = 148;
+        pairs = sms / 2;
+    }
+    return pairs;
+}
 }
 namespace tc2 {
 static int g_raw_hi = -1;

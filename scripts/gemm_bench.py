@@ -1,8 +1,8 @@
 """GEMM microbenchmark + accuracy check for the three 3xTF32 dense-layer kernels (run on a B200).
 
 For every (shape, layout) of the pines hot path: max error against a float64 matmul, then CUDA-event
-timing (L2 flushed between launches) of the CTA-pair kernel (both operand-split modes), the
-single-CTA tcgen05 kernel and, for reference, the mma.sync kernel.
+timing (L2 flushed between launches) of the persistent CTA-pair kernel, the one-tile CTA-pair kernel,
+the single-CTA tcgen05 kernel and, for reference, the mma.sync kernel.
 usage: python scripts/gemm_bench.py [--quick] [--json out.json]
 """
 import argparse
@@ -28,8 +28,9 @@ def main():
     ap.add_argument("--json", default=None)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--timeline", action="store_true", help="needs a MFM_TC2_TIMELINE=1 build")
+    ap.add_argument("--sustained", type=float, default=0.0, help="also run each kernel back to back for this many seconds, sampling nvidia-smi clocks/power")
     ap.add_argument("--only", default=None, help="comma-separated shape labels")
-    ap.add_argument("--kernels", default="pair,pair_rawhi,tc1,mma")
+    ap.add_argument("--kernels", default="persist,pair,tc1,mma")
     args = ap.parse_args()
     lib = _lib.load()
     dev = torch.device("cuda:0")
@@ -67,7 +68,7 @@ def main():
         Bm = (B if bnm else B.t()).double()
         ref = torch.relu(Am @ Bm + bias.double())
         rec = {"label": label, "M": M, "N": N, "K": K, "akm": akm, "bnm": bnm}
-        for name, backend, raw in [("pair", 0, 0), ("pair_rawhi", 0, 1), ("tc1", 2, 0), ("mma", 1, 0)]:
+        for name, backend, raw in [("persist", 0, 1), ("pair", 3, 1), ("pair_rnsplit", 3, 0), ("tc1", 2, 0), ("mma", 1, 0)]:
             if name not in kernels or (name == "mma" and not args.quick and M * N * K > 2e11):
                 continue
             lib.mfm_set_gemm_backend(backend)
@@ -85,7 +86,7 @@ def main():
                 torch.cuda.synchronize()
                 ts.append(e0.elapsed_time(e1))
             ms = float(np.median(ts))
-            if args.timeline and name.startswith("pair"):
+            if args.timeline and name == "pair":
                 import ctypes
                 buf = (ctypes.c_longlong * 16)()
                 lib.mfm_debug_gemm_timeline(1, None)
@@ -97,6 +98,26 @@ def main():
                          "last MMA issued", "accumulator ready", "epilogue done", "after final cluster sync"]
                 print("   timeline (SM clocks since entry): " + ", ".join(f"{nm}={t[i] - t[0]}" for i, nm in enumerate(names)))
             rec[name] = {"rel_err": err, "finite": finite, "ms": ms, "tflops": 2.0 * M * N * K / ms / 1e9}
+            if args.sustained > 0:
+                import subprocess, time
+                mon = subprocess.Popen(["nvidia-smi", "--query-gpu=clocks.sm,power.draw,clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits",
+                                        "-lms", "100", "-i", "0"], stdout=subprocess.PIPE, text=True)
+                n_it = max(10, int(args.sustained * 1e3 / ms))
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize(); time.sleep(0.3)
+                e0.record()
+                for _ in range(n_it):
+                    run(lib, M, N, K, akm, bnm, A, B, bias, C, st)
+                e1.record(); torch.cuda.synchronize()
+                mon.terminate(); lines = mon.stdout.read().strip().splitlines()
+                vals = [l.split(",") for l in lines if l.count(",") == 2]
+                clk = [float(v[0]) for v in vals][3:]; pw = [float(v[1]) for v in vals][3:]
+                sms = e0.elapsed_time(e1) / n_it
+                rec[name]["sustained"] = {"ms": sms, "tflops": 2.0 * M * N * K / sms / 1e9, "sm_mhz_median": float(np.median(clk)) if clk else None,
+                                          "power_w_median": float(np.median(pw)) if pw else None}
+                print(f"      sustained {n_it} launches: {sms:8.3f} ms {2.0 * M * N * K / sms / 1e9:7.1f} TFLOP/s  sm_mhz median "
+                      f"{np.median(clk) if clk else -1:.0f} min {min(clk) if clk else -1:.0f}  power median {np.median(pw) if pw else -1:.0f} W  "
+                      f"power_cap_active {sum(1 for v in vals if 'Active' in v[2] and 'Not' not in v[2])}/{len(vals)}", flush=True)
             print(f"{label:12s} {name:10s} M={M} N={N} K={K} err={err:.2e} finite={finite} {ms:8.3f} ms "
                   f"{rec[name]['tflops']:7.1f} TFLOP/s", flush=True)
         out.append(rec)

@@ -10,12 +10,21 @@ pytestmark = pytest.mark.gpu
 SHAPES = [(128, 128, 16), (128, 128, 256), (300, 200, 100), (1, 2, 2), (129, 2, 130), (64, 1600, 1600),
           (1000, 128, 2), (257, 1024, 1024), (5, 7, 3), (2048, 256, 64),
           # tcgen05-eligible shapes (M>=128, N>=64, K>=32, 32-aligned MN-major dims), incl. ragged edges
-          (512, 512, 512), (130, 96, 40), (384, 320, 1600), (1024, 1600, 1024), (160, 64, 33 * 4)]
+          (512, 512, 512), (130, 96, 40), (384, 320, 1600), (1024, 1600, 1024), (160, 64, 33 * 4),
+          # many tiles per CTA pair (persistent kernel: both TMEM buffers and every ring phase), ragged M and N
+          (20000, 1088, 96), (40000 + 77, 512, 256)]
 
 
+# accumulator-truncation bias per unit of K (relative to the largest output), by dense-layer backend:
+#   0 auto: persistent CTA-pair kernel where eligible (hi*hi and both cross terms share one TMEM accumulator)
+#   3 one-tile CTA-pair kernel / single-CTA kernel (cross terms in their own accumulator); 1 mma.sync (flushed every 32 k)
+BIAS_PER_K = {0: 1.2e-8, 3: 2.5e-9, 1: 0.0}
+
+
+@pytest.mark.parametrize("backend", [0, 3])
 @pytest.mark.parametrize("M,N,K", SHAPES)
 @pytest.mark.parametrize("akm,bnm", [(1, 1), (1, 0), (0, 1), (0, 0)])
-def test_gemm_layouts(cuda, lib, M, N, K, akm, bnm):
+def test_gemm_layouts(cuda, lib, M, N, K, akm, bnm, backend):
     rng = np.random.default_rng(M * 7 + N * 3 + K)
     A = rng.standard_normal((M, K)).astype(np.float32)
     B = rng.standard_normal((K, N)).astype(np.float32)
@@ -24,16 +33,19 @@ def test_gemm_layouts(cuda, lib, M, N, K, akm, bnm):
     Bd = torch.from_numpy(B if bnm else np.ascontiguousarray(B.T)).to(cuda)
     Cd = torch.full((M, N), float("nan"), dtype=torch.float32, device=cuda)
     bias_d = torch.from_numpy(bias).to(cuda)      # keep alive across the asynchronous launch
-    _lib.check(lib.mfm_gemm_tf32x3(M, N, K, Ad.data_ptr(), Ad.shape[1], akm, Bd.data_ptr(), Bd.shape[1], bnm,
-                                   bias_d.data_ptr(), 1, Cd.data_ptr(), N,
-                                   torch.cuda.current_stream().cuda_stream))
+    lib.mfm_set_gemm_backend(backend)
+    try:
+        _lib.check(lib.mfm_gemm_tf32x3(M, N, K, Ad.data_ptr(), Ad.shape[1], akm, Bd.data_ptr(), Bd.shape[1], bnm,
+                                       bias_d.data_ptr(), 1, Cd.data_ptr(), N,
+                                       torch.cuda.current_stream().cuda_stream))
+        got = Cd.cpu().numpy()
+    finally:
+        lib.mfm_set_gemm_backend(0)
     ref = np.maximum(A.astype(np.float64) @ B.astype(np.float64) + bias, 0)
-    got = Cd.cpu().numpy()
     assert np.isfinite(got).all()
     # fp32-level: a few ulp of the largest output (3xTF32 drops only the lo*lo term, ~2^-22), plus the
-    # tensor core's truncating accumulator: the mma.sync kernel flushes every 32 k, the tcgen05 kernel
-    # accumulates the whole K in TMEM (measured bias <= 2.5e-9 * K relative)
-    tol = (2e-6 + 2.5e-9 * K) * max(np.abs(ref).max(), 1.0)
+    # tensor core's truncating fp32 accumulator over the whole K (the mma.sync kernel flushes every 32 k)
+    tol = (2e-6 + BIAS_PER_K[backend] * K) * max(np.abs(ref).max(), 1.0)
     assert np.abs(got - ref).max() <= tol, (np.abs(got - ref).max(), tol)
 
 
@@ -72,4 +84,4 @@ def test_gemm_backends_agree(cuda, lib):
     ref = A.cpu().numpy().astype(np.float64) @ B.cpu().numpy().astype(np.float64)
     e_tc, e_mma = np.abs(outs[0] - ref).max(), np.abs(outs[1] - ref).max()
     scale = np.abs(ref).max()
-    assert e_tc < (2e-6 + 2.5e-9 * K) * scale and e_mma < 2e-6 * scale, (e_tc / scale, e_mma / scale)
+    assert e_tc < (2e-6 + BIAS_PER_K[0] * K) * scale and e_mma < 2e-6 * scale, (e_tc / scale, e_mma / scale)
