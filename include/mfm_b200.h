@@ -90,6 +90,11 @@ void mfm_set_gemm_backend(int backend);
  * a third of the splitter's shared-memory traffic; 0 = hi = rn_tf32(x), lo = rn_tf32(x - hi).
  * Environment variable MFM_TC_RAWHI=0|1. */
 void mfm_set_gemm_raw_hi(int raw_hi);
+/* Cross terms of the persistent kernel when both operands are K-major (A[m][k], B[n][k]): 0 = two kind::tf32 MMAs per
+ * k-step (a_lo*b_hi, a_hi*b_lo: "3xTF32"); 1 = one kind::f16 MMA with K=16 over bf16 copies [a_lo | a] x [b | b_lo]
+ * built by the splitter warps (error ~2^-19 relative on terms that are 2^-11 of the product).
+ * Environment variable MFM_GEMM_CROSS=tf32|bf16. */
+void mfm_set_gemm_cross_bf16(int enable);
 
 /* ---- RNG: jax.random semantics (threefry2x32, legacy keys, x64 off) ------------------------ */
 /* jax.random.split(key, num) -> out uint32[num,2] */

@@ -104,12 +104,42 @@ struct EpiFieldDiv {
     __device__ __forceinline__ void at_z(int) {}
 };
 
-int dense(int n, int in, int out, const float* A, long long lda, const float* W, const float* bias, int relu,
+int dense(int n, int in, int out, const float* A, long long lda, const float* WT, long long ldwt, const float* bias, int relu,
                  float* C, long long ldc, const float* mask, long long ldm, int mask_div, cudaStream_t st,
                  const int* n_rows_dev) {
-    GemmShape p{n, out, in, A, lda, W, (long long)out, n_rows_dev};
+    GemmShape p{n, out, in, A, lda, WT, ldwt, n_rows_dev};
     EpiStd e{C, ldc, bias, mask, ldm, nullptr, 0, 1.0f, relu, mask_div};
-    MFM_CUDA_CHECK((launch_gemm<true, true>(p, e, st)));
+    MFM_CUDA_CHECK((launch_gemm<true, false>(p, e, st)));
+    return MFM_OK;
+}
+
+// out[c*rows + r] = in[r*cols + c]   (32x32 tiles through shared memory)
+__global__ void transpose_kernel(int rows, int cols, const float* __restrict__ in, float* __restrict__ out) {
+    __shared__ float tile[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        const int r = r0 + j, c = c0 + threadIdx.x;
+        tile[j][threadIdx.x] = (r < rows && c < cols) ? in[(long long)r * cols + c] : 0.0f;
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        const int c = c0 + j, r = r0 + threadIdx.x;
+        if (r < rows && c < cols) out[(long long)c * rows + r] = tile[threadIdx.x][j];
+    }
+}
+
+static void layer_dims(const mfm_field_t& F, int i, int& in, int& out) {
+    const int d = F.dim, H = F.hidden, Fd = F.fourier_dim;
+    const int ins[8] = {2 * Fd, H, d, H, H, 2 * H, H, H}, outs[8] = {H, H, H, H, d, H, H, d};
+    in = ins[i]; out = outs[i];
+}
+
+int field_prepare_weights(const mfm_field_t& F, FieldBufs& B, cudaStream_t st) {
+    for (int i = 0; i < 8; ++i) {
+        int in, out; layer_dims(F, i, in, out);
+        transpose_kernel<<<dim3(ceil_div(out, 32), ceil_div(in, 32)), dim3(32, 8), 0, st>>>(in, out, F.params + F.w_off[i], B.wt + F.w_off[i]);
+        MFM_LAUNCH_CHECK();
+    }
     return MFM_OK;
 }
 
@@ -186,7 +216,7 @@ size_t field_bufs_bytes(const mfm_field_t& F, const mfm_target_t& T, int n, bool
     size_t b = ws_slice(N * 2 * F.fourier_dim, 4) + ws_slice(N * H, 4) * 6 + ws_slice(N * 2 * H, 4) + ws_slice(N * d, 4) * 3;
     if (hutch) b += ws_slice(N * H, 4) + ws_slice(N * d, 4) + ws_slice(N * gemm_n_tiles((int)d), 4);
     else b += 2 * ws_slice(N * d * H, 4);
-    return b;
+    return b + ws_slice((size_t)F.n_params, 4);
 }
 
 bool field_bufs_take(FieldBufs& B, Workspace& w, const mfm_field_t& F, int n, bool hutch) {
@@ -199,16 +229,18 @@ bool field_bufs_take(FieldBufs& B, Workspace& w, const mfm_field_t& F, int n, bo
     B.zw2 = B.zkinv = B.divpart = B.tan_a = B.tan_b = nullptr;
     if (hutch) { B.zw2 = w.take<float>(N * H); B.zkinv = w.take<float>(N * d); B.divpart = w.take<float>(N * gemm_n_tiles((int)d)); }
     else { B.tan_a = w.take<float>(N * d * H); B.tan_b = w.take<float>(N * d * H); }
+    B.wt = w.take<float>((size_t)F.n_params);
     return w.ok;
 }
 
 #define W_(i) (F.params + F.w_off[i])
+#define WT_(i) (B.wt + F.w_off[i])
 #define B_(i) (F.params + F.b_off[i])
 
 // per-solve constants of the Hutchinson estimator: z W2 and (pines) z K^-1
 static int field_prepare_probe(const mfm_field_t& F, const mfm_target_t& T, int n, const float* z, FieldBufs& B, cudaStream_t st) {
     const int d = F.dim, H = F.hidden;
-    int rc = dense(n, d, H, z, d, W_(2), nullptr, 0, B.zw2, H, nullptr, 0, 1, st, nullptr);
+    int rc = dense(n, d, H, z, d, WT_(2), d, nullptr, 0, B.zw2, H, nullptr, 0, 1, st, nullptr);
     if (rc) return rc;
     if (T.kind == MFM_TARGET_PINES) return pines_kinv_gemm(T, n, z, d, B.zkinv, d, nullptr, st);
     return MFM_OK;
@@ -222,34 +254,34 @@ int field_eval(const mfm_field_t& F, const mfm_target_t& T, int n, const float* 
     int rc;
     fourier_kernel<<<ceil_div((long long)n * Fd, 256), 256, 0, st>>>(n, Fd, F.omega, tfield, B.ff, nr);
     MFM_LAUNCH_CHECK();
-    if ((rc = dense(n, 2 * Fd, H, B.ff, 2 * Fd, W_(0), B_(0), 1, B.h0, H, nullptr, 0, 1, st, nr))) return rc;
-    if ((rc = dense(n, H, H, B.h0, H, W_(1), B_(1), 1, B.cat + H, 2 * H, nullptr, 0, 1, st, nr))) return rc;       // s_t
-    if ((rc = dense(n, d, H, x, d, W_(2), B_(2), 1, B.h2, H, nullptr, 0, 1, st, nr))) return rc;
-    if ((rc = dense(n, H, H, B.h2, H, W_(3), B_(3), 1, B.cat, 2 * H, nullptr, 0, 1, st, nr))) return rc;           // s_x
-    if ((rc = dense(n, H, d, B.cat + H, 2 * H, W_(4), B_(4), 0, B.gt, d, nullptr, 0, 1, st, nr))) return rc;       // nn_t
-    if ((rc = dense(n, 2 * H, H, B.cat, 2 * H, W_(5), B_(5), 1, B.h5, H, nullptr, 0, 1, st, nr))) return rc;
-    if ((rc = dense(n, H, H, B.h5, H, W_(6), B_(6), 1, B.h6, H, nullptr, 0, 1, st, nr))) return rc;
+    if ((rc = dense(n, 2 * Fd, H, B.ff, 2 * Fd, WT_(0), 2 * Fd, B_(0), 1, B.h0, H, nullptr, 0, 1, st, nr))) return rc;
+    if ((rc = dense(n, H, H, B.h0, H, WT_(1), H, B_(1), 1, B.cat + H, 2 * H, nullptr, 0, 1, st, nr))) return rc;       // s_t
+    if ((rc = dense(n, d, H, x, d, WT_(2), d, B_(2), 1, B.h2, H, nullptr, 0, 1, st, nr))) return rc;
+    if ((rc = dense(n, H, H, B.h2, H, WT_(3), H, B_(3), 1, B.cat, 2 * H, nullptr, 0, 1, st, nr))) return rc;           // s_x
+    if ((rc = dense(n, H, d, B.cat + H, 2 * H, WT_(4), H, B_(4), 0, B.gt, d, nullptr, 0, 1, st, nr))) return rc;       // nn_t
+    if ((rc = dense(n, 2 * H, H, B.cat, 2 * H, WT_(5), 2 * H, B_(5), 1, B.h5, H, nullptr, 0, 1, st, nr))) return rc;
+    if ((rc = dense(n, H, H, B.h5, H, WT_(6), H, B_(6), 1, B.h6, H, nullptr, 0, 1, st, nr))) return rc;
     // untempered grad logprob (clipped) and the Hessian term of the divergence
     mfm_target_t T1 = T; T1.beta = 1.0f;
     const bool want_div = out_l != nullptr;
     if ((rc = target_field_terms(T1, n, x, z, B.zkinv, F.grad_clip, B.gc, (want_div && z) ? B.hx : nullptr,
                                  (want_div && !z) ? B.hx : nullptr, nr, st))) return rc;
     {
-        GemmShape p{n, d, H, B.h6, (long long)H, W_(7), (long long)d, nr};
+        GemmShape p{n, d, H, B.h6, (long long)H, WT_(7), (long long)H, nr};
         EpiFieldV e{out_v, (long long)d, B_(7), B.gt, B.gc, (long long)d, sgn, row_map};
-        MFM_CUDA_CHECK((launch_gemm<true, true>(p, e, st)));
+        MFM_CUDA_CHECK((launch_gemm<true, false>(p, e, st)));
     }
     if (!want_div) return MFM_OK;
     if (z) {
         gate_kernel<<<ceil_div((long long)n * H, 256), 256, 0, st>>>((long long)n * H, H, B.zw2, B.h2, H, B.ta, nr);
         MFM_LAUNCH_CHECK();
-        if ((rc = dense(n, H, H, B.ta, H, W_(3), nullptr, 0, B.tb, H, B.cat, 2 * H, 1, st, nr))) return rc;
-        if ((rc = dense(n, H, H, B.tb, H, W_(5), nullptr, 0, B.ta, H, B.h5, H, 1, st, nr))) return rc;   // first H rows of W5
-        if ((rc = dense(n, H, H, B.ta, H, W_(6), nullptr, 0, B.tb, H, B.h6, H, 1, st, nr))) return rc;
-        GemmShape p{n, d, H, B.tb, (long long)H, W_(7), (long long)d, nr};
+        if ((rc = dense(n, H, H, B.ta, H, WT_(3), H, nullptr, 0, B.tb, H, B.cat, 2 * H, 1, st, nr))) return rc;
+        if ((rc = dense(n, H, H, B.tb, H, WT_(5), 2 * H, nullptr, 0, B.ta, H, B.h5, H, 1, st, nr))) return rc;   // first H rows of W5
+        if ((rc = dense(n, H, H, B.ta, H, WT_(6), H, nullptr, 0, B.tb, H, B.h6, H, 1, st, nr))) return rc;
+        GemmShape p{n, d, H, B.tb, (long long)H, WT_(7), (long long)H, nr};
         const int nt = gemm_n_tiles(d);
         EpiFieldDiv e{z, B.gt, B.hx, (long long)d, B.divpart, nt};
-        MFM_CUDA_CHECK((launch_gemm<true, true>(p, e, st)));
+        MFM_CUDA_CHECK((launch_gemm<true, false>(p, e, st)));
         div_finish_kernel<<<ceil_div(n, 256), 256, 0, st>>>(n, nt, B.divpart, -sgn, out_l, nr, row_map);
         MFM_LAUNCH_CHECK();
     } else {
@@ -258,9 +290,9 @@ int field_eval(const mfm_field_t& F, const mfm_target_t& T, int n, const float* 
         if (nr) { mfm_set_last_error_msg("internal: compaction is not used with the exact divergence"); return MFM_ERR_UNSUPPORTED; }
         basis_tangent_kernel<<<ceil_div(rows * H, 256), 256, 0, st>>>(n, d, H, W_(2), B.h2, B.tan_a, nullptr);
         MFM_LAUNCH_CHECK();
-        if ((rc = dense((int)rows, H, H, B.tan_a, H, W_(3), nullptr, 0, B.tan_b, H, B.cat, 2 * H, d, st, nullptr))) return rc;
-        if ((rc = dense((int)rows, H, H, B.tan_b, H, W_(5), nullptr, 0, B.tan_a, H, B.h5, H, d, st, nullptr))) return rc;
-        if ((rc = dense((int)rows, H, H, B.tan_a, H, W_(6), nullptr, 0, B.tan_b, H, B.h6, H, d, st, nullptr))) return rc;
+        if ((rc = dense((int)rows, H, H, B.tan_a, H, WT_(3), H, nullptr, 0, B.tan_b, H, B.cat, 2 * H, d, st, nullptr))) return rc;
+        if ((rc = dense((int)rows, H, H, B.tan_b, H, WT_(5), 2 * H, nullptr, 0, B.tan_a, H, B.h5, H, d, st, nullptr))) return rc;
+        if ((rc = dense((int)rows, H, H, B.tan_a, H, WT_(6), H, nullptr, 0, B.tan_b, H, B.h6, H, d, st, nullptr))) return rc;
         exact_trace_kernel<<<ceil_div(n, 8), 256, 0, st>>>(n, d, H, B.tan_b, W_(7), B.gt, B.hx, -sgn, out_l, nullptr, row_map);
         MFM_LAUNCH_CHECK();
     }
@@ -709,6 +741,7 @@ int mfm_ode_flow(const mfm_field_t* f, const mfm_target_t* t, const mfm_ode_opts
     float* z = nullptr; float* zc = nullptr;
     if (o->hutch) { z = w.take<float>((size_t)n * f->dim); zc = w.take<float>((size_t)n * f->dim); }
     if (!w.ok) { mfm_set_last_error_msg("workspace too small (mfm_ode_flow)"); return MFM_ERR_WORKSPACE; }
+    if ((rc = field_prepare_weights(*f, B, stream))) return rc;
     if (o->hutch) {
         if (!hutch_keys) { mfm_set_last_error_msg("hutch_keys required"); return MFM_ERR_ARG; }
         if ((rc = mfm_threefry_normal_batched(hutch_keys, n, f->dim, z, stream))) return rc;
@@ -729,6 +762,7 @@ int mfm_field_eval(const mfm_field_t* f, const mfm_target_t* t, const mfm_ode_op
     float* negdiv = w.take<float>(n);
     if (!w.ok) { mfm_set_last_error_msg("workspace too small (mfm_field_eval)"); return MFM_ERR_WORKSPACE; }
     if (hutch && !z) { mfm_set_last_error_msg("z required for hutch"); return MFM_ERR_ARG; }
+    if ((rc = field_prepare_weights(*f, B, stream))) return rc;
     if (hutch && (rc = field_prepare_probe(*f, *t, n, z, B, stream))) return rc;
     // field_eval writes -sgn*div; evaluate with sgn=-1 on a negated... simpler: sgn=+1 then negate
     if ((rc = field_eval(*f, *t, n, x, time, hutch ? z : nullptr, 1.0f, v, div ? negdiv : nullptr, B, stream))) return rc;
@@ -771,6 +805,7 @@ int mfm_flow_mh_step(const mfm_field_t* f, const mfm_target_t* t, const mfm_ode_
     if (!w.ok) { mfm_set_last_error_msg("workspace too small (mfm_flow_mh_step)"); return MFM_ERR_WORKSPACE; }
     const bool hutch = o->hutch != 0;
 
+    if ((rc = field_prepare_weights(*f, B, stream))) return rc;
     flow_keys_kernel<<<ceil_div(n, 128), 128, 0, stream>>>(rng_key, n, chain_offset, n_total, kgen, kacc, kh1, kh2);
     MFM_LAUNCH_CHECK();
     if ((rc = mfm_threefry_normal_batched(kgen, n, d, eps, stream))) return rc;

@@ -210,6 +210,7 @@ static int fm_forward_backward(const mfm_field_t& F, const mfm_target_t& T, int 
     FieldBufs& B = M.B;
     int rc;
     MFM_CUDA_CHECK(cudaMemsetAsync(grads, 0, (size_t)F.n_params * sizeof(float), st));
+    if ((rc = field_prepare_weights(F, B, st))) return rc;
     if ((rc = field_eval(F, T, n, M.xt, M.times, nullptr, 1.0f, M.v, nullptr, B, st))) return rc;
     const long long tot = (long long)n * d;
     const int lb = (int)((tot + 255) / 256 < FM_LOSS_BLOCKS ? (tot + 255) / 256 : FM_LOSS_BLOCKS);

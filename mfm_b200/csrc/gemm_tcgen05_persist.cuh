@@ -56,9 +56,30 @@ __host__ __device__ inline Tiles make_tiles(int M, int N, int K, int k_split) {
     return t;
 }
 
-template <bool A_KMAJOR, bool B_NMAJOR, class Epi>
+__device__ __forceinline__ void mma_bf16_ss_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    const uint32_t z = 0;
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(z) : "memory");
+}
+// two floats -> packed bf16x2 (round to nearest even); `lo16` lands in the low half (first in memory)
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo16, float hi16) {
+    uint32_t r; asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi16), "f"(lo16)); return r;
+}
+__device__ __forceinline__ float tf32_trunc_rest(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+// XBF16 (K-major x K-major operands only): the two cross terms of a k-step are ONE kind::f16 MMA with
+// K = 16 over a bf16 tile the splitters build next to the raw fp32 tile:
+//     A' = [ bf16(a_lo[0..7]) | bf16(a[0..7]) ],   B' = [ bf16(b[0..7]) | bf16(b_lo[0..7]) ]
+//     A'.B' = sum_k a_lo b + a b_lo            (a_lo = a - trunc_tf32(a): what the hi*hi MMA dropped)
+// 16 bf16 are 32 bytes = 8 tf32, so the cross tile has the raw tile's byte geometry (128 rows x 128 B,
+// SWIZZLE_128B, +32 B per k-step): same descriptors, half the tensor-pipe time of two tf32 MMAs and a
+// third less MMA operand traffic.  bf16 keeps 8 bits of factors that are 2^-11 relative, so the cross
+// terms carry ~2^-19 relative error (unbiased, round-to-nearest): fp32-class like the rest.
+template <bool A_KMAJOR, bool B_NMAJOR, bool XBF16, class Epi>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 gemm_tc2p_kernel(const __grid_constant__ Maps maps, GemmShape p, Epi epi) {
+    static_assert(!XBF16 || (A_KMAJOR && !B_NMAJOR), "bf16 cross terms need K-major operands");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* stg_base = smem + STAGES * STAGE_BYTES;
@@ -139,6 +160,8 @@ gemm_tc2p_kernel(const __grid_constant__ Maps maps, GemmShape p, Epi epi) {
                 tile_origin(t, m0p, n0, kz0, KT, neff, z);
                 const uint32_t b = i & 1, u = i >> 1;
                 const uint32_t idesc = make_idesc_base(!A_KMAJOR, B_NMAJOR) | ((uint32_t)(neff >> 3) << 17);
+                // kind::f16: D = f32, A = B = bf16, both K-major, same M and N
+                const uint32_t idesc16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(neff >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
                 const uint32_t acc = tmem_base + b * BN;
                 mbar_wait(&acc_empty[b], (u & 1) ^ 1);          // both CTAs have drained this buffer (tile i-2)
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -157,9 +180,14 @@ gemm_tc2p_kernel(const __grid_constant__ Maps maps, GemmShape p, Epi epi) {
                         const uint32_t alt = A_KMAJOR ? 2 : 1, blt = !B_NMAJOR ? 2 : 1;
                         const uint64_t dah = make_desc(a_hi + ao, albo, asbo, alt), dal = make_desc(a_lo + ao, albo, asbo, alt);
                         const uint64_t dbh = make_desc(b_hi + bo, blbo, bsbo, blt), dbl = make_desc(b_lo + bo, blbo, bsbo, blt);
-                        mma_tf32_ss_2sm(acc, dal, dbh, idesc, (kt | ks) != 0);
-                        mma_tf32_ss_2sm(acc, dah, dbl, idesc, 1);
-                        mma_tf32_ss_2sm(acc, dah, dbh, idesc, 1);
+                        if (XBF16) {
+                            mma_tf32_ss_2sm(acc, dah, dbh, idesc, (kt | ks) != 0);
+                            mma_bf16_ss_2sm(acc, dal, dbl, idesc16, 1);      // "lo" region = the bf16 cross tiles
+                        } else {
+                            mma_tf32_ss_2sm(acc, dal, dbh, idesc, (kt | ks) != 0);
+                            mma_tf32_ss_2sm(acc, dah, dbl, idesc, 1);
+                            mma_tf32_ss_2sm(acc, dah, dbh, idesc, 1);
+                        }
                     }
                     mma_commit_2sm(&empty[s]);
                 }
@@ -184,6 +212,25 @@ gemm_tc2p_kernel(const __grid_constant__ Maps maps, GemmShape p, Epi epi) {
 #pragma unroll
                 for (int k = 0; k < PER; ++k)
                     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[k].x), "=f"(v[k].y), "=f"(v[k].z), "=f"(v[k].w) : "r"(hi + k * STEP));
+                if (XBF16) {
+                    // chunk P = tix + 256 k of the stage: k < 4 -> A rows, k >= 4 -> B rows; row r = (P % 1024) / 8,
+                    // physical 16-byte chunk pc = P % 8 holds logical chunk c = pc ^ (r % 8) (SWIZZLE_128B), i.e.
+                    // k-group g = c / 2, half h = c % 2.  Its 4 lo and 4 full values go to bytes 8h.. of logical
+                    // chunks 2g and 2g + 1 of the cross tile (A: lo first; B: full first) = physical pc^h, pc^h^1.
+#pragma unroll
+                    for (int k = 0; k < PER; ++k) {
+                        const uint32_t q = (uint32_t)tix + (uint32_t)(k & 3) * 256u;      // chunk within the A or B tile
+                        const uint32_t r = q >> 3, pc = q & 7u, h = (pc ^ r) & 1u;
+                        const uint32_t l0 = pack_bf16x2(tf32_trunc_rest(v[k].x), tf32_trunc_rest(v[k].y));
+                        const uint32_t l1 = pack_bf16x2(tf32_trunc_rest(v[k].z), tf32_trunc_rest(v[k].w));
+                        const uint32_t f0 = pack_bf16x2(v[k].x, v[k].y), f1 = pack_bf16x2(v[k].z, v[k].w);
+                        const bool is_b = k >= 4;
+                        const uint32_t row = smem_u32(smem + s * STAGE_BYTES) + HI_BYTES + (is_b ? A_BYTES : 0) + r * 128u + (h << 3);
+                        const uint32_t d0 = row + ((pc ^ h) << 4), d1 = row + ((pc ^ h ^ 1u) << 4);
+                        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(d0), "r"(is_b ? f0 : l0), "r"(is_b ? f1 : l1) : "memory");
+                        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(d1), "r"(is_b ? l0 : f0), "r"(is_b ? l1 : f1) : "memory");
+                    }
+                } else
                 // hi = the raw fp32 tile (the tensor core ignores the 13 low mantissa bits); lo = rn_tf32(x - trunc(x))
 #pragma unroll
                 for (int k = 0; k < PER; ++k) {
@@ -293,6 +340,7 @@ inline bool eligible(const GemmShape& p, const Epi& epi) {
 }
 
 int sm_pairs();                             // number of TPC pairs to keep resident (74 on B200)
+int gemm_cross_bf16();                      // 1: K-major x K-major GEMMs take their cross terms from one bf16 MMA (env MFM_GEMM_CROSS=tf32|bf16)
 
 template <bool A_KMAJOR, bool B_NMAJOR, class Epi>
 inline cudaError_t launch(const GemmShape& p, const Epi& epi, cudaStream_t st) {
@@ -300,10 +348,12 @@ inline cudaError_t launch(const GemmShape& p, const Epi& epi, cudaStream_t st) {
     bool ok = A_KMAJOR ? tc::make_map_kmajor(&maps.a, p.A, p.lda, p.M, p.K, BM) : tc::make_map_mnmajor(&maps.a, p.A, p.lda, p.M, p.K, BM / 32);
     ok = ok && (!B_NMAJOR ? tc::make_map_kmajor(&maps.b, p.B, p.ldb, p.N, p.K, BNH) : tc::make_map_mnmajor(&maps.b, p.B, p.ldb, p.N, p.K, BNH / 32));
     if (!ok) return cudaErrorInvalidValue;
-    auto kern = gemm_tc2p_kernel<A_KMAJOR, B_NMAJOR, Epi>;
+    constexpr bool KK = A_KMAJOR && !B_NMAJOR;
+    auto kern = (KK && gemm_cross_bf16()) ? gemm_tc2p_kernel<A_KMAJOR, B_NMAJOR, KK, Epi> : gemm_tc2p_kernel<A_KMAJOR, B_NMAJOR, false, Epi>;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc2p_kernel<A_KMAJOR, B_NMAJOR, false, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e == cudaSuccess && KK) e = cudaFuncSetAttribute(gemm_tc2p_kernel<A_KMAJOR, B_NMAJOR, KK, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess) return e;
         configured = true;
     }

@@ -45,11 +45,16 @@ int target_field_terms(const mfm_target_t& T, int n, const float* x, const float
 struct FieldBufs {
     float *ff, *h0, *cat, *h2, *gt, *h5, *h6, *gc, *hx, *ta, *tb, *zw2, *zkinv, *divpart;
     float *tan_a, *tan_b;   // exact path [n*d, H]
+    float* wt;              // transposed dense kernels: layer i at wt + F.w_off[i], stored [out][in] (K-major B operand)
 };
 size_t field_bufs_bytes(const mfm_field_t& F, const mfm_target_t& T, int n, bool hutch);
 bool field_bufs_take(FieldBufs& B, Workspace& w, const mfm_field_t& F, int n, bool hutch);
-// C[n,out] = relu?(A[n,in] W[in,out] + bias) gated by mask (relu' of another activation)
-int dense(int n, int in, int out, const float* A, long long lda, const float* W, const float* bias, int relu,
+// B.wt <- transposes of the eight dense kernels (once per ABI call: the parameters may have changed)
+int field_prepare_weights(const mfm_field_t& F, FieldBufs& B, cudaStream_t st);
+// C[n,out] = relu?(A[n,in] W[in,out] + bias) gated by mask (relu' of another activation).
+// WT = the kernel transposed, WT[o*ldwt + i]: both GEMM operands are K-major, which is what the
+// persistent tcgen05 kernel's bf16 cross-term path needs.
+int dense(int n, int in, int out, const float* A, long long lda, const float* WT, long long ldwt, const float* bias, int relu,
           float* C, long long ldc, const float* mask, long long ldm, int mask_div, cudaStream_t st,
           const int* n_rows_dev = nullptr);
 // out_v = sgn * v(x, t); out_l = -sgn * div v (optional; z != null -> Hutchinson, else exact trace).

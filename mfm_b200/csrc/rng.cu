@@ -25,6 +25,11 @@ int gemm_backend() {
     return g_backend;
 }
 namespace tc2p {
+static int g_cross_bf16 = -1;
+int gemm_cross_bf16() {
+    if (g_cross_bf16 < 0) { const char* e = getenv("MFM_GEMM_CROSS"); g_cross_bf16 = (e && strcmp(e, "tf32") == 0) ? 0 : 1; }
+    return g_cross_bf16;
+}
 int sm_pairs() {
     static int pairs = 0;
     if (pairs == 0) {
@@ -44,6 +49,7 @@ int gemm_raw_hi() {
 }
 }
 extern "C" void mfm_set_gemm_raw_hi(int v) { mfm::tc2::g_raw_hi = v ? 1 : 0; }
+extern "C" void mfm_set_gemm_cross_bf16(int v) { mfm::tc2p::g_cross_bf16 = v ? 1 : 0; }
 // tuning aid (not part of the ABI header): SM-clock timeline of one CTA pair of the last tc2 GEMM
 namespace mfm { namespace tc2 {
 static long long* g_timeline_buf = nullptr;

@@ -174,7 +174,7 @@ int pines_grad_gemm(const mfm_target_t& T, int n, const float* X, long long ldx,
                     long long ldg, float* prior_partial, const int* n_rows_dev, cudaStream_t st) {
     GemmShape p{n, T.dim, T.dim, X, ldx, T.kinv, (long long)T.dim, n_rows_dev};
     EpiPinesGrad e{X, ldx, T.counts, T.kinv_mu, T.mu, T.poisson_a, beta, grad_out, ldg, prior_partial, gemm_n_tiles(T.dim)};
-    MFM_CUDA_CHECK((launch_gemm<true, true>(p, e, st)));
+    MFM_CUDA_CHECK((launch_gemm<true, false>(p, e, st)   /* K^-1 is symmetric: read it as the K-major operand */));
     return MFM_OK;
 }
 
@@ -182,7 +182,7 @@ int pines_kinv_gemm(const mfm_target_t& T, int n, const float* Z, long long ldz,
                     const int* n_rows_dev, cudaStream_t st) {
     GemmShape p{n, T.dim, T.dim, Z, ldz, T.kinv, (long long)T.dim, n_rows_dev};
     EpiStd e{out, ldo, nullptr, nullptr, 0, nullptr, 0, 1.0f, 0};
-    MFM_CUDA_CHECK((launch_gemm<true, true>(p, e, st)));
+    MFM_CUDA_CHECK((launch_gemm<true, false>(p, e, st)   /* K^-1 is symmetric: read it as the K-major operand */));
     return MFM_OK;
 }
 
@@ -247,7 +247,7 @@ int target_field_terms(const mfm_target_t& T, int n, const float* x, const float
     if (T.kind == MFM_TARGET_PINES) {
         GemmShape p{n, T.dim, T.dim, x, (long long)T.dim, T.kinv, (long long)T.dim, n_rows_dev};
         EpiPinesField e{x, (long long)T.dim, T.counts, T.kinv_mu, T.kinv_diag, z, zkinv, T.poisson_a, clip, gc, hvc, hdc, (long long)T.dim};
-        MFM_CUDA_CHECK((launch_gemm<true, true>(p, e, st)));
+        MFM_CUDA_CHECK((launch_gemm<true, false>(p, e, st)   /* K^-1 is symmetric: read it as the K-major operand */));
         return MFM_OK;
     }
     const size_t smem = (size_t)EVAL_WARPS * 5 * T.dim * sizeof(float);

@@ -30,7 +30,7 @@ def main():
     ap.add_argument("--timeline", action="store_true", help="needs a MFM_TC2_TIMELINE=1 build")
     ap.add_argument("--sustained", type=float, default=0.0, help="also run each kernel back to back for this many seconds, sampling nvidia-smi clocks/power")
     ap.add_argument("--only", default=None, help="comma-separated shape labels")
-    ap.add_argument("--kernels", default="persist,pair,tc1,mma")
+    ap.add_argument("--kernels", default="persist,persist_bf16x,pair,tc1,mma")
     args = ap.parse_args()
     lib = _lib.load()
     dev = torch.device("cuda:0")
@@ -46,6 +46,9 @@ def main():
         (n, 1600, 1600, 1, 1, "pines Kinv"),
         (n, 1024, 1024, 1, 0, "dgrad H<-H"),
         (n, 1024, 1600, 1, 0, "dgrad H<-d"),
+        (n, 1600, 1600, 1, 0, "Kinv KxK"),
+        (n, 1024, 2048, 1, 0, "2H->H KxK"),
+        (n, 1024, 256, 1, 0, "2F->H KxK"),
         (1024, 1024, n, 0, 1, "wgrad HxH"),
         (1024, 1600, n, 0, 1, "wgrad Hxd"),
         (1600, 1024, n, 0, 1, "wgrad dxH"),
@@ -68,11 +71,14 @@ def main():
         Bm = (B if bnm else B.t()).double()
         ref = torch.relu(Am @ Bm + bias.double())
         rec = {"label": label, "M": M, "N": N, "K": K, "akm": akm, "bnm": bnm}
-        for name, backend, raw in [("persist", 0, 1), ("pair", 3, 1), ("pair_rnsplit", 3, 0), ("tc1", 2, 0), ("mma", 1, 0)]:
+        for name, backend, raw in [("persist", 0, 1), ("persist_bf16x", 0, 1), ("pair", 3, 1), ("pair_rnsplit", 3, 0), ("tc1", 2, 0), ("mma", 1, 0)]:
             if name not in kernels or (name == "mma" and not args.quick and M * N * K > 2e11):
+                continue
+            if name == "persist_bf16x" and not (akm == 1 and bnm == 0):
                 continue
             lib.mfm_set_gemm_backend(backend)
             lib.mfm_set_gemm_raw_hi(raw)
+            lib.mfm_set_gemm_cross_bf16(1 if name == "persist_bf16x" else 0)
             C.fill_(float("nan"))
             run(lib, M, N, K, akm, bnm, A, B, bias, C, st)
             torch.cuda.synchronize()
@@ -121,7 +127,7 @@ def main():
             print(f"{label:12s} {name:10s} M={M} N={N} K={K} err={err:.2e} finite={finite} {ms:8.3f} ms "
                   f"{rec[name]['tflops']:7.1f} TFLOP/s", flush=True)
         out.append(rec)
-    lib.mfm_set_gemm_backend(0); lib.mfm_set_gemm_raw_hi(0)
+    lib.mfm_set_gemm_backend(0); lib.mfm_set_gemm_raw_hi(1); lib.mfm_set_gemm_cross_bf16(0)
     if args.json:
         with open(args.json, "w") as fh:
             json.dump(out, fh, indent=1)

@@ -49,6 +49,30 @@ def test_gemm_layouts(cuda, lib, M, N, K, akm, bnm, backend):
     assert np.abs(got - ref).max() <= tol, (np.abs(got - ref).max(), tol)
 
 
+@pytest.mark.parametrize("M,N,K", [(512, 512, 512), (384, 320, 1600), (1024, 1600, 1024), (20000, 1088, 96), (40000 + 77, 512, 256),
+                                   (4096, 1024, 2048), (300, 200, 100)])
+def test_gemm_bf16_cross_terms(cuda, lib, M, N, K):
+    """K-major x K-major persistent kernel with the cross terms taken from one bf16 MMA per k-step."""
+    rng = np.random.default_rng(M + N + K)
+    A = rng.standard_normal((M, K)).astype(np.float32) * np.exp(rng.standard_normal((M, 1))).astype(np.float32)
+    Bt = rng.standard_normal((N, K)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+    Ad, Bd, bias_d = torch.from_numpy(A).to(cuda), torch.from_numpy(Bt).to(cuda), torch.from_numpy(bias).to(cuda)
+    Cd = torch.full((M, N), float("nan"), dtype=torch.float32, device=cuda)
+    lib.mfm_set_gemm_cross_bf16(1)
+    try:
+        _lib.check(lib.mfm_gemm_tf32x3(M, N, K, Ad.data_ptr(), K, 1, Bd.data_ptr(), K, 0, bias_d.data_ptr(), 0, Cd.data_ptr(), N,
+                                       torch.cuda.current_stream().cuda_stream))
+        got = Cd.cpu().numpy()
+    finally:
+        lib.mfm_set_gemm_cross_bf16(0)
+    ref = A.astype(np.float64) @ Bt.astype(np.float64).T + bias
+    # row-wise scale: the rows of A span two orders of magnitude
+    scale = np.maximum(np.abs(ref).max(axis=1, keepdims=True), 1.0)
+    err = (np.abs(got - ref) / scale).max()
+    assert np.isfinite(got).all() and err <= 3e-6 + 8e-9 * K, err
+
+
 def test_gemm_strided_views(cuda, lib):
     """ld > logical width (writing into a column block of a concatenated buffer)."""
     rng = np.random.default_rng(0)
