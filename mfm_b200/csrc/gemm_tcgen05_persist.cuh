@@ -252,6 +252,16 @@ gemm_tc2p_kernel(const __grid_constant__ Maps maps, GemmShape p, Epi epi) {
         const uint32_t stg = smem_u32(stg_base) + (uint32_t)ew * (32u * EPI_LD * 4u);
         const int rsub = lane >> 3, cpiece = (lane & 7) * 4;
         constexpr int RB = sizeof(typename Epi::Row4) > 36 ? 2 : 4;     // steps whose global reads are issued together
+        // per-row epilogue operands of tile t -> L2 (lane = row; one 128-byte line per 32-column chunk)
+        auto prefetch_tile = [&](int t) {
+            int m0p, n0, kz0, KT, neff, z;
+            tile_origin(t, m0p, n0, kz0, KT, neff, z);
+            const int row = m0p + (int)rank * BM + ew * 32 + lane;
+            const int n_chunks = min(BN / 32, (p.N - n0 + 31) / 32);
+            if (row < M)
+                for (int cc = 0; cc < n_chunks; ++cc) epi.prefetch_row(row, n0 + cc * 32);
+        };
+        if (pair < T.total) prefetch_tile(pair);
         uint32_t i = 0;
         for (int t = pair; t < T.total; t += n_pairs, ++i) {
             int m0p, n0, kz0, KT, neff, z;
@@ -261,6 +271,7 @@ gemm_tc2p_kernel(const __grid_constant__ Maps maps, GemmShape p, Epi epi) {
             if (p.k_split > 0) e.at_z(z);
             const int row_base = m0p + (int)rank * BM + ew * 32;
             const int n_chunks = min(BN / 32, (p.N - n0 + 31) / 32);
+            if (t + n_pairs < T.total) prefetch_tile(t + n_pairs);     // one tile ahead: lands during this tile's epilogue
             mbar_wait(&acc_full[b], u & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             float rs[8];

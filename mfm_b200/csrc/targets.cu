@@ -87,6 +87,7 @@ struct EpiPinesGrad {
     struct Row4 { float4 x; };
     bool vec_ok() const { return aligned16(X) && ldx % 4 == 0 && aligned16(grad) && ldg % 4 == 0 && aligned16(counts) && aligned16(kinv_mu); }
     __device__ __forceinline__ Col4 load_col4(int col) const { Col4 c; c.kinv_mu = ldg4(kinv_mu + col); c.counts = ldg4(counts + col); return c; }
+    __device__ __forceinline__ void prefetch_row(int row, int col) const { prefetch_l2(X + (long long)row * ldx + col); }
     __device__ __forceinline__ Row4 load_row4(int row, int col) const { Row4 r; r.x = ldg4(X + (long long)row * ldx + col); return r; }
     __device__ __forceinline__ float apply4(int row, int col, const float4& acc, const Col4& c, const Row4& r) const {
         const float4 q = make_float4(acc.x - c.kinv_mu.x, acc.y - c.kinv_mu.y, acc.z - c.kinv_mu.z, acc.w - c.kinv_mu.w);
@@ -136,6 +137,11 @@ struct EpiPinesField {
     __device__ __forceinline__ Col4 load_col4(int col) const {
         Col4 c; c.counts = ldg4(counts + col); c.kinv_mu = ldg4(kinv_mu + col); c.kdiag = hdc ? ldg4(kinv_diag + col) : f4(0.0f);
         return c;
+    }
+    __device__ __forceinline__ void prefetch_row(int row, int col) const {
+        const long long o = (long long)row * ld + col;
+        prefetch_l2(X + (long long)row * ldx + col);
+        if (hvc) { prefetch_l2(Z + o); prefetch_l2(ZK + o); }
     }
     __device__ __forceinline__ Row4 load_row4(int row, int col) const {
         const long long o = (long long)row * ld + col;

@@ -17,9 +17,10 @@ def load(path):
 
 def short(name):
     name = re.sub(r"^void ", "", name)
-    m = re.match(r"([\w:]+)<\(bool\)(\d), \(bool\)(\d), mfm::(\w+)>", name)
+    m = re.match(r"([\w:]+)<([^>]*?)mfm::(\w+)>", name)
     if m:
-        return f"{m.group(1).split('::')[-1]}<{m.group(2)},{m.group(3)},{m.group(4)}>"
+        flags = ",".join(re.findall(r"\b(\d)\b", m.group(2)))
+        return f"{m.group(1).split('::')[-1]}<{flags},{m.group(3)}>"
     return re.sub(r"\(.*", "", name).split("::")[-1][:48]
 
 
