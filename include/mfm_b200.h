@@ -120,6 +120,11 @@ void mfm_host_threefry_split(const uint32_t key[2], int num, uint32_t* out);
 int mfm_gemm_tf32x3(int M, int N, int K, const float* A, long long lda, int a_kmajor, const float* B, long long ldb,
                     int b_nmajor, const float* bias, int relu, float* C, long long ldc, mfm_stream_t stream);
 
+/* Backward-data form of a dense layer (test / benchmark hook of the fused epilogue):
+ * C[M,N] = (A[M,K] * Bt[N,K]^T + add[M,N]) where mask[M,N] > 0, else 0; add and mask optional; add may alias C. */
+int mfm_gemm_tf32x3_gated(int M, int N, int K, const float* A, long long lda, const float* Bt, long long ldb, const float* mask,
+                          long long ldm, const float* add, long long ldadd, float* C, long long ldc, mfm_stream_t stream);
+
 /* ---- targets -------------------------------------------------------------------------------- */
 size_t mfm_target_workspace_bytes(const mfm_target_t* t, int n);
 /* vmap(init)(positions, logprob_beta): mala.py:51-54, exe_flow_matching.py:316.

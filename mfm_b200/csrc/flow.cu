@@ -62,10 +62,6 @@ struct EpiFieldV {
     struct Row4 { float4 gt, gc; int orow; };
     bool vec_ok() const { return aligned16(V) && ldv % 4 == 0 && aligned16(bias) && aligned16(gt) && aligned16(gc) && ld % 4 == 0; }
     __device__ __forceinline__ Col4 load_col4(int col) const { Col4 c; c.bias = ldg4(bias + col); return c; }
-    __device__ __forceinline__ void prefetch_row(int row, int col) const {
-        const long long o = (long long)row * ld + col;
-        prefetch_l2(gt + o); prefetch_l2(gc + o);
-    }
     __device__ __forceinline__ Row4 load_row4(int row, int col) const {
         const long long o = (long long)row * ld + col;
         Row4 r; r.gt = ldg4(gt + o); r.gc = ldg4(gc + o); r.orow = row_map ? __ldg(row_map + row) : row;
@@ -95,10 +91,6 @@ struct EpiFieldDiv {
     struct Row4 { float4 z, gt, hvc; };
     bool vec_ok() const { return aligned16(z) && aligned16(gt) && aligned16(hvc) && ld % 4 == 0; }
     __device__ __forceinline__ Col4 load_col4(int) const { return Col4{}; }
-    __device__ __forceinline__ void prefetch_row(int row, int col) const {
-        const long long o = (long long)row * ld + col;
-        prefetch_l2(z + o); prefetch_l2(gt + o); prefetch_l2(hvc + o);
-    }
     __device__ __forceinline__ Row4 load_row4(int row, int col) const {
         const long long o = (long long)row * ld + col;
         Row4 r; r.z = ldg4(z + o); r.gt = ldg4(gt + o); r.hvc = ldg4(hvc + o);

@@ -10,16 +10,21 @@
 //   warp 1        MMA issuer (leader)   accumulator buffer b = tile & 1 (TMEM columns b*256 .. +255)
 //   warp 2        TMEM allocator
 //   warps 4-11    splitters             hi (raw, truncated by the tensor core) / lo = rn_tf32(x - trunc x)
-//   warps 12-15   epilogue              drain buffer b while the MMAs fill buffer b^1
+//   warps 12-19   epilogue              drain buffer b while the MMAs fill buffer b^1 (quadrant x column half)
 // TMEM holds 512 columns, so two 256-column buffers leave no room for a separate cross-term
 // accumulator: lo*hi, hi*lo and hi*hi of a k-step accumulate into the same buffer.  The tensor core's
 // fp32 accumulator truncates on every add, so this costs accuracy: measured bias ~ 7.5e-9 * K relative
 // (separate accumulators: 2.5e-9 * K).  MFM_GEMM=tc2 selects the one-tile kernel when that matters.
 //
-// Epilogue: a warp owns 32 rows (its TMEM lane quadrant) x 256 columns, drained in 32-column chunks:
-// tcgen05.ld -> shared memory (36-float pitch) -> 8 steps of 4 rows x 128 bytes, float4 per lane, through
+// Epilogue: a warp owns 32 rows (its TMEM lane quadrant) x 128 columns, drained in 32-column chunks:
+// tcgen05.ld -> shared memory (XOR-swizzled) -> 8 steps of 4 rows x 128 bytes, float4 per lane, through
 // the functors' Col4/Row4 interface (gemm_tf32x3.cuh).  Buffer b is released (remote arrive on the
-// leader's acc_empty[b]) as soon as the last chunk has left TMEM.
+// leader's acc_empty[b]) as soon as a warp's last chunk has left TMEM.
+// Measured (scripts/epi_bench.py --timeline): the shared-memory / L1 data pipe is ~90 % busy with MMA
+// operand reads and the splitters, so a global load issued by an epilogue warp returns after ~2.5 k clocks
+// whether it hits L2 or not (an L2 prefetch one tile ahead changed nothing and was removed); the epilogue
+// is bounded by loads in flight, hence 8 epilogue warps.  Per 256x256 tile at K = 1024: MMAs 41 k clocks,
+// epilogue 17 k (bias only) / 40 k (with a mask or residual operand).
 #pragma once
 #include "gemm_tcgen05_2sm.cuh"
 
@@ -32,13 +37,15 @@ using tc2::cluster_ctarank; using tc2::cluster_sync_all; using tc2::mbar_arrive_
 using tc2::mma_commit_2sm; using tc2::make_idesc_base;
 
 constexpr int BM = 128, BN = 256, BNH = BN / 2, BK = 32, STAGES = 3;
-constexpr int THREADS = 512;                // 16 warps
-constexpr int SPLIT_WARP0 = 4, SPLIT_WARPS = 8, EPI_WARP0 = 12, EPI_WARPS = 4;
+constexpr int THREADS = 640;                // 20 warps
+constexpr int SPLIT_WARP0 = 4, SPLIT_WARPS = 8, EPI_WARP0 = 12, EPI_WARPS = 8;
 constexpr int A_BYTES = BM * BK * 4, B_BYTES = BNH * BK * 4;
 constexpr int HI_BYTES = A_BYTES + B_BYTES; // 32 KB
 constexpr int STAGE_BYTES = 2 * HI_BYTES;   // 64 KB
-constexpr uint32_t EPI_LD = 36;             // staging row pitch (floats): conflict-free float4 rows of a 32x32 chunk
-constexpr int EPI_STG_BYTES = EPI_WARPS * 32 * EPI_LD * 4;      // 18 KB
+// epilogue staging: one 32x32 fp32 chunk per warp, 128-byte rows, 16-byte pieces XOR-swizzled by the row
+// (piece j of row r at r*128 + ((j ^ (r & 7)) << 4)): conflict-free for the row-per-lane float4 writes and
+// for the 4-rows-per-instruction float4 reads, with no padding (8 warps x 4 KB must fit beside the ring)
+constexpr int EPI_STG_BYTES = EPI_WARPS * 32 * 32 * 4;          // 32 KB
 constexpr int NBARS = 3 * STAGES + 4;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STG_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int TMEM_COLS = 512;
@@ -78,7 +85,14 @@ __device__ __forceinline__ float tf32_trunc_rest(float x) { return x - __uint_as
 // terms carry ~2^-19 relative error (unbiased, round-to-nearest): fp32-class like the rest.
 template <bool A_KMAJOR, bool B_NMAJOR, bool XBF16, class Epi>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
-gemm_tc2p_kernel(const __grid_constant__ Maps maps, GemmShape p, Epi epi) {
+gemm_tc2p_kernel(const __grid_constant__ Maps maps, GemmShape p, Epi epi, long long* tl) {
+#ifdef MFM_TC2_TIMELINE
+    // tuning aid: SM clock at 4 events of the first 16 tiles of pair 0's leader (MMA start / accumulator
+    // committed / epilogue start / epilogue end)
+#define TC2P_MARK(tile, ev) do { if (tl && blockIdx.x == 0 && (tile) < 16 && lane == 0) tl[(tile) * 4 + (ev)] = clock64(); } while (0)
+#else
+#define TC2P_MARK(tile, ev) do { } while (0)
+#endif
     static_assert(!XBF16 || (A_KMAJOR && !B_NMAJOR), "bf16 cross terms need K-major operands");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -165,6 +179,7 @@ gemm_tc2p_kernel(const __grid_constant__ Maps maps, GemmShape p, Epi epi) {
                 const uint32_t acc = tmem_base + b * BN;
                 mbar_wait(&acc_empty[b], (u & 1) ^ 1);          // both CTAs have drained this buffer (tile i-2)
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                TC2P_MARK(i, 0);
                 for (int kt = 0; kt < KT; ++kt, ++g) {
                     const uint32_t s = g % STAGES, ph = (g / STAGES) & 1;
                     mbar_wait(&split[s], ph);
@@ -192,6 +207,7 @@ gemm_tc2p_kernel(const __grid_constant__ Maps maps, GemmShape p, Epi epi) {
                     mma_commit_2sm(&empty[s]);
                 }
                 mma_commit_2sm(&acc_full[b]);
+                TC2P_MARK(i, 1);
             }
         }
     } else if (warp >= SPLIT_WARP0 && warp < EPI_WARP0) {
@@ -248,20 +264,12 @@ gemm_tc2p_kernel(const __grid_constant__ Maps maps, GemmShape p, Epi epi) {
         }
     } else if (warp >= EPI_WARP0) {
         // ---------------- epilogue (each CTA drains its own 128 TMEM lanes) ----------------
-        const int ew = warp - EPI_WARP0;              // == warp & 3: the TMEM lane quadrant this warp may access
-        const uint32_t stg = smem_u32(stg_base) + (uint32_t)ew * (32u * EPI_LD * 4u);
+        const int ew = warp - EPI_WARP0;              // 0..7
+        const int quad = ew & 3;                      // == warp & 3: the TMEM lane quadrant this warp may access
+        const int chalf = ew >> 2;                    // column half of the tile (4 chunks of 32 columns)
+        const uint32_t stg = smem_u32(stg_base) + (uint32_t)ew * (32u * 32u * 4u);
         const int rsub = lane >> 3, cpiece = (lane & 7) * 4;
-        constexpr int RB = sizeof(typename Epi::Row4) > 36 ? 2 : 4;     // steps whose global reads are issued together
-        // per-row epilogue operands of tile t -> L2 (lane = row; one 128-byte line per 32-column chunk)
-        auto prefetch_tile = [&](int t) {
-            int m0p, n0, kz0, KT, neff, z;
-            tile_origin(t, m0p, n0, kz0, KT, neff, z);
-            const int row = m0p + (int)rank * BM + ew * 32 + lane;
-            const int n_chunks = min(BN / 32, (p.N - n0 + 31) / 32);
-            if (row < M)
-                for (int cc = 0; cc < n_chunks; ++cc) epi.prefetch_row(row, n0 + cc * 32);
-        };
-        if (pair < T.total) prefetch_tile(pair);
+        constexpr int RB = 2;                         // steps whose global reads are issued together (register budget: 102)
         uint32_t i = 0;
         for (int t = pair; t < T.total; t += n_pairs, ++i) {
             int m0p, n0, kz0, KT, neff, z;
@@ -269,30 +277,37 @@ gemm_tc2p_kernel(const __grid_constant__ Maps maps, GemmShape p, Epi epi) {
             const uint32_t b = i & 1, u = i >> 1;
             Epi e = epi;
             if (p.k_split > 0) e.at_z(z);
-            const int row_base = m0p + (int)rank * BM + ew * 32;
-            const int n_chunks = min(BN / 32, (p.N - n0 + 31) / 32);
-            if (t + n_pairs < T.total) prefetch_tile(t + n_pairs);     // one tile ahead: lands during this tile's epilogue
+            const int row_base = m0p + (int)rank * BM + quad * 32;
+            const int n_chunks = min(BN / 32, (p.N - n0 + 31) / 32);     // chunks of the whole tile
+            const int cc_begin = chalf * 4, cc_end = min(n_chunks, chalf * 4 + 4);
             mbar_wait(&acc_full[b], u & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (ew == 0) TC2P_MARK(i, 2);
             float rs[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) rs[k] = 0.0f;
+            if (cc_begin >= cc_end) {
+                // nothing to drain in this column half (edge tile): still release the buffer
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive_remote(&acc_empty[b], 0);
+            }
 #pragma unroll 1
-            for (int cc = 0; cc < n_chunks; ++cc) {
+            for (int cc = cc_begin; cc < cc_end; ++cc) {
                 const int col0 = cc * 32;
                 uint32_t r[32];
-                tmem_ld32_nowait(tmem_base + ((uint32_t)(ew * 32) << 16) + b * BN + (uint32_t)col0, r);
+                tmem_ld32_nowait(tmem_base + ((uint32_t)(quad * 32) << 16) + b * BN + (uint32_t)col0, r);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (cc == n_chunks - 1) {
-                    // the last chunk has left TMEM: hand the buffer back to the MMA issuer
+                if (cc == cc_end - 1) {
+                    // this warp's last chunk has left TMEM: hand the buffer back to the MMA issuer
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) mbar_arrive_remote(&acc_empty[b], 0);
                 }
-                const uint32_t dst = stg + (uint32_t)lane * (EPI_LD * 4u);
+                const uint32_t dst = stg + (uint32_t)lane * 128u;
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
-                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + j * 16), "f"(__uint_as_float(r[4 * j])),
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (uint32_t)((j ^ (lane & 7)) << 4)), "f"(__uint_as_float(r[4 * j])),
                                  "f"(__uint_as_float(r[4 * j + 1])), "f"(__uint_as_float(r[4 * j + 2])), "f"(__uint_as_float(r[4 * j + 3])) : "memory");
                 __syncwarp();
                 const int col = n0 + col0 + cpiece;           // N % 4 == 0: the four columns are valid together
@@ -311,7 +326,7 @@ gemm_tc2p_kernel(const __grid_constant__ Maps maps, GemmShape p, Epi epi) {
 #pragma unroll
                     for (int k = 0; k < RB; ++k)
                         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(acc[k].x), "=f"(acc[k].y), "=f"(acc[k].z), "=f"(acc[k].w)
-                                     : "r"(stg + ((uint32_t)((it0 + k) * 4 + rsub) * EPI_LD + (uint32_t)cpiece) * 4u));
+                                     : "r"(stg + (uint32_t)((it0 + k) * 4 + rsub) * 128u + (uint32_t)((((lane & 7) ^ (((it0 + k) * 4 + rsub) & 7))) << 4)));
 #pragma unroll
                     for (int k = 0; k < RB; ++k) {
                         const int row = row_base + (it0 + k) * 4 + rsub;
@@ -324,7 +339,7 @@ gemm_tc2p_kernel(const __grid_constant__ Maps maps, GemmShape p, Epi epi) {
                         }
                     }
                 }
-                if (Epi::kRowSum && ((cc & 1) || cc == n_chunks - 1)) {
+                if (Epi::kRowSum && ((cc & 1) || cc == cc_end - 1)) {
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
                         const int row = row_base + k * 4 + rsub;
@@ -334,6 +349,7 @@ gemm_tc2p_kernel(const __grid_constant__ Maps maps, GemmShape p, Epi epi) {
                 }
                 __syncwarp();                                 // staging is reused by the next chunk
             }
+            if (ew == 0) TC2P_MARK(i, 3);
         }
     }
     __syncwarp();
@@ -370,7 +386,7 @@ inline cudaError_t launch(const GemmShape& p, const Epi& epi, cudaStream_t st) {
     }
     const Tiles T = make_tiles(p.M, p.N, p.K, p.k_split);
     const int pairs = T.total < sm_pairs() ? T.total : sm_pairs();
-    kern<<<dim3(2 * pairs), THREADS, SMEM_BYTES, st>>>(maps, p, epi);
+    kern<<<dim3(2 * pairs), THREADS, SMEM_BYTES, st>>>(maps, p, epi, tc2::gemm_timeline());
     ++g_mfm_launches;
     return cudaGetLastError();
 }

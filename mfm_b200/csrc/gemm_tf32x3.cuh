@@ -245,9 +245,6 @@ __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpre
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ float4 f4(float v) { return make_float4(v, v, v, v); }
-// pull the 128-byte line at p into L2 (no register, no dependency): used one tile ahead by the persistent
-// kernel's epilogue warps so their per-row operand reads are L2 hits instead of DRAM round trips
-__device__ __forceinline__ void prefetch_l2(const float* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // ---- standard epilogue: C = mask(relu(alpha*acc + bias) ) (+ add) ----------------------------
 struct EpiStd {
@@ -285,10 +282,6 @@ struct EpiStd {
                (!mask || (aligned16(mask) && ldm % 4 == 0)) && (!add || (aligned16(add) && ldadd % 4 == 0));
     }
     __device__ __forceinline__ Col4 load_col4(int col) const { Col4 c; c.bias = bias ? ldg4(bias + col) : f4(0.0f); return c; }
-    __device__ __forceinline__ void prefetch_row(int row, int col) const {
-        if (add) prefetch_l2(add + (long long)row * ldadd + col);
-        if (mask) prefetch_l2(mask + (long long)(mask_div == 1 ? row : row / mask_div) * ldm + col);
-    }
     __device__ __forceinline__ Row4 load_row4(int row, int col) const {
         Row4 r;
         r.add = add ? ld4(add + (long long)row * ldadd + col) : f4(0.0f);        // may alias C: plain load

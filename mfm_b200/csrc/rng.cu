@@ -58,9 +58,9 @@ long long* gemm_timeline() { return g_timeline ? g_timeline_buf : nullptr; }
 } }
 extern "C" int mfm_debug_gemm_timeline(int enable, long long* out16) {
     using namespace mfm::tc2;
-    if (!g_timeline_buf && cudaMalloc(&g_timeline_buf, 16 * sizeof(long long)) != cudaSuccess) return -1;
+    if (!g_timeline_buf && cudaMalloc(&g_timeline_buf, 64 * sizeof(long long)) != cudaSuccess) return -1;
     g_timeline = enable ? 1 : 0;
-    if (out16) return cudaMemcpy(out16, g_timeline_buf, 16 * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -1;
+    if (out16) return cudaMemcpy(out16, g_timeline_buf, 64 * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -1;
     return 0;
 }
 extern "C" void mfm_set_gemm_backend(int b) { mfm::g_backend = b; }

@@ -87,7 +87,6 @@ struct EpiPinesGrad {
     struct Row4 { float4 x; };
     bool vec_ok() const { return aligned16(X) && ldx % 4 == 0 && aligned16(grad) && ldg % 4 == 0 && aligned16(counts) && aligned16(kinv_mu); }
     __device__ __forceinline__ Col4 load_col4(int col) const { Col4 c; c.kinv_mu = ldg4(kinv_mu + col); c.counts = ldg4(counts + col); return c; }
-    __device__ __forceinline__ void prefetch_row(int row, int col) const { prefetch_l2(X + (long long)row * ldx + col); }
     __device__ __forceinline__ Row4 load_row4(int row, int col) const { Row4 r; r.x = ldg4(X + (long long)row * ldx + col); return r; }
     __device__ __forceinline__ float apply4(int row, int col, const float4& acc, const Col4& c, const Row4& r) const {
         const float4 q = make_float4(acc.x - c.kinv_mu.x, acc.y - c.kinv_mu.y, acc.z - c.kinv_mu.z, acc.w - c.kinv_mu.w);
@@ -137,11 +136,6 @@ struct EpiPinesField {
     __device__ __forceinline__ Col4 load_col4(int col) const {
         Col4 c; c.counts = ldg4(counts + col); c.kinv_mu = ldg4(kinv_mu + col); c.kdiag = hdc ? ldg4(kinv_diag + col) : f4(0.0f);
         return c;
-    }
-    __device__ __forceinline__ void prefetch_row(int row, int col) const {
-        const long long o = (long long)row * ld + col;
-        prefetch_l2(X + (long long)row * ldx + col);
-        if (hvc) { prefetch_l2(Z + o); prefetch_l2(ZK + o); }
     }
     __device__ __forceinline__ Row4 load_row4(int row, int col) const {
         const long long o = (long long)row * ld + col;
@@ -279,6 +273,15 @@ int mfm_gemm_tf32x3(int M, int N, int K, const float* A, long long lda, int a_km
     else if (!a_kmajor && b_nmajor) err = launch_gemm<false, true>(p, e, stream);
     else err = launch_gemm<false, false>(p, e, stream);
     MFM_CUDA_CHECK(err);
+    return MFM_OK;
+}
+
+int mfm_gemm_tf32x3_gated(int M, int N, int K, const float* A, long long lda, const float* Bt, long long ldb, const float* mask,
+                          long long ldm, const float* add, long long ldadd, float* Cout, long long ldc, mfm_stream_t stream) {
+    using namespace mfm;
+    GemmShape p{M, N, K, A, lda, Bt, ldb, nullptr};
+    EpiStd e{Cout, ldc, nullptr, mask, ldm, add, ldadd, 1.0f, 0};
+    MFM_CUDA_CHECK((launch_gemm<true, false>(p, e, stream)));
     return MFM_OK;
 }
 

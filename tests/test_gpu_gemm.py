@@ -73,6 +73,31 @@ def test_gemm_bf16_cross_terms(cuda, lib, M, N, K):
     assert np.isfinite(got).all() and err <= 3e-6 + 8e-9 * K, err
 
 
+@pytest.mark.parametrize("M,N,K", [(1024, 512, 256), (40000 + 77, 1024, 128), (700, 1600, 1024), (130, 96, 40)])
+@pytest.mark.parametrize("use_mask,use_add,inplace", [(1, 0, 0), (0, 1, 0), (1, 1, 1)])
+def test_gemm_gated_epilogue(cuda, lib, M, N, K, use_mask, use_add, inplace):
+    """Backward-data form: C = (A Bt^T + add) * [mask > 0]; add may alias C (in-place accumulate)."""
+    rng = np.random.default_rng(M + 3 * N + K + use_mask + 2 * use_add)
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    Bt = rng.standard_normal((N, K)).astype(np.float32)
+    mask = rng.standard_normal((M, N)).astype(np.float32)
+    add = rng.standard_normal((M, N)).astype(np.float32)
+    Ad, Bd = torch.from_numpy(A).to(cuda), torch.from_numpy(Bt).to(cuda)
+    md, ad = torch.from_numpy(mask).to(cuda), torch.from_numpy(add).to(cuda)
+    Cd = ad.clone() if inplace else torch.full((M, N), float("nan"), dtype=torch.float32, device=cuda)
+    add_ptr = (Cd if inplace else ad).data_ptr() if use_add else None
+    _lib.check(lib.mfm_gemm_tf32x3_gated(M, N, K, Ad.data_ptr(), K, Bd.data_ptr(), K, md.data_ptr() if use_mask else None, N,
+                                         add_ptr, N, Cd.data_ptr(), N, torch.cuda.current_stream().cuda_stream))
+    ref = A.astype(np.float64) @ Bt.astype(np.float64).T
+    if use_add:
+        ref = ref + add
+    if use_mask:
+        ref = np.where(mask > 0, ref, 0.0)
+    got = Cd.cpu().numpy()
+    assert np.isfinite(got).all()
+    assert np.abs(got - ref).max() <= (3e-6 + 1.2e-8 * K) * max(np.abs(ref).max(), 1.0)
+
+
 def test_gemm_strided_views(cuda, lib):
     """ld > logical width (writing into a column block of a concatenated buffer)."""
     rng = np.random.default_rng(0)
