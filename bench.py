@@ -307,6 +307,13 @@ def main():
     ms_fm = timed(lambda: loop.state.loss_and_grad(key_t, loop.states.position, off, n_total), 3)
     from mfm_b200.bblackjax.mcmc.mala import mala_step
     ms_mala = timed(lambda: mala_step(dist.tempered(1.0), key_t, loop.states, 0.01, False, off, n_total, inplace=True), 3)
+    # one whole MALA outer iteration (data generator + FM loss/grad + gradient all-reduce + AdamW), max over ranks
+    loop.count = 0
+    ms_iter = timed(loop.iteration, 5)
+    t_it = torch.tensor([ms_iter], dtype=torch.float64, device=dev)
+    if world > 1:
+        tdist.all_reduce(t_it, op=tdist.ReduceOp.MAX)
+    ms_iter = float(t_it.item())
     # dominant kernel: the persistent CTA-pair dense-layer GEMM, measured on the FM hidden-layer shape
     # [n,H] x [H,H] with K-major operands (how every forward / backward-data layer calls it): a burst of 10
     # launches and a sustained run of >= 1 s (the clocks settle under the 1 kW power cap), CUDA events on
@@ -343,7 +350,8 @@ def main():
                         "(split-K weight-gradient GEMMs still use 3 tf32 passes, ceiling 1/6)",
                 "frac_of_emulation_ceiling": gemm_tflops / (peak_tf / 4.0),
                 "whole_step_tflops_per_gpu": step_tflops,
-                "phase_ms": {"fm_loss_grad": ms_fm, "mala_iteration": ms_mala},
+                "phase_ms": {"fm_loss_grad": ms_fm, "mala_iteration": ms_mala, "outer_iteration_mala": ms_iter,
+                             "outer_iteration_flow": ms / a.steps - m * ms_iter},
                 "phase_tflops": {"fm_loss_grad": n * fl["fm"] / (ms_fm * 1e-3) / 1e12,
                                  "mala_iteration": n * fl["mala"] / (ms_mala * 1e-3) / 1e12},
                 "mala_state_gbs": n * (20 * D + 28) / (ms_mala * 1e-3) / 1e9}

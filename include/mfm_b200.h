@@ -174,6 +174,13 @@ size_t mfm_fm_workspace_bytes(const mfm_field_t* f, const mfm_target_t* t, int n
 int mfm_fm_loss_grad(const mfm_field_t* f, const mfm_target_t* t, const uint32_t* rng_key, int n,
                      int chain_offset, int n_total, float sigma, const float* positions,
                      float* loss_out, float* grads, void* ws, size_t ws_bytes, mfm_stream_t stream);
+/* The same computation in two calls so that the multi-GPU host can overlap the gradient all-reduce with the
+ * backward pass: part 1 = batch, forward, loss and the gradients of Dense_7..Dense_4, i.e. grads[w_off[4] .. n_params);
+ * part 2 = the gradients of Dense_3..Dense_0, grads[0 .. w_off[4]), from the activations part 1 left in `ws` (same
+ * arguments, same workspace, nothing else may use `ws` in between); part 0 = both (== mfm_fm_loss_grad). */
+int mfm_fm_loss_grad_part(const mfm_field_t* f, const mfm_target_t* t, const uint32_t* rng_key, int n, int chain_offset,
+                          int n_total, float sigma, const float* positions, float* loss_out, float* grads, void* ws,
+                          size_t ws_bytes, int part, mfm_stream_t stream);
 /* same, from explicit (x_t, t, target) — test hook */
 int mfm_fm_loss_grad_from_batch(const mfm_field_t* f, const mfm_target_t* t, int n, const float* xt,
                                 const float* times, const float* target_v, float* loss_out, float* grads,

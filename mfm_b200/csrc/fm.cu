@@ -204,20 +204,25 @@ static bool fm_take(FmBufs& M, Workspace& w, const mfm_field_t& F, int n) {
 #define GW_(i) (grads + F.w_off[i])
 #define GB_(i) (grads + F.b_off[i])
 
+// part 0: everything; part 1: forward, loss and the gradients of layers 7..4 (the tail [w_off[4], n_params) of
+// the flat buffer); part 2: the gradients of layers 3..0 (the head) from the activations part 1 left in
+// the workspace.  The split lets the host all-reduce the tail while part 2 runs.
 static int fm_forward_backward(const mfm_field_t& F, const mfm_target_t& T, int n, FmBufs& M, float* loss_out,
-                               float* grads, cudaStream_t st) {
+                               float* grads, cudaStream_t st, int part) {
     const int d = F.dim, H = F.hidden, Fd = F.fourier_dim;
     FieldBufs& B = M.B;
     int rc;
-    MFM_CUDA_CHECK(cudaMemsetAsync(grads, 0, (size_t)F.n_params * sizeof(float), st));
-    if ((rc = field_prepare_weights(F, B, st))) return rc;
-    if ((rc = field_eval(F, T, n, M.xt, M.times, nullptr, 1.0f, M.v, nullptr, B, st))) return rc;
-    const long long tot = (long long)n * d;
-    const int lb = (int)((tot + 255) / 256 < FM_LOSS_BLOCKS ? (tot + 255) / 256 : FM_LOSS_BLOCKS);
-    fm_loss_delta_kernel<<<lb, 256, 0, st>>>(tot, M.v, M.target, B.gc, M.delta, M.dgt, M.blockpart);
-    MFM_LAUNCH_CHECK();
-    final_sum_kernel<<<1, 256, 0, st>>>(lb, M.blockpart, loss_out);
-    MFM_LAUNCH_CHECK();
+    if (part != 2) {
+        MFM_CUDA_CHECK(cudaMemsetAsync(grads, 0, (size_t)F.n_params * sizeof(float), st));
+        if ((rc = field_prepare_weights(F, B, st))) return rc;
+        if ((rc = field_eval(F, T, n, M.xt, M.times, nullptr, 1.0f, M.v, nullptr, B, st))) return rc;
+        const long long tot = (long long)n * d;
+        const int lb = (int)((tot + 255) / 256 < FM_LOSS_BLOCKS ? (tot + 255) / 256 : FM_LOSS_BLOCKS);
+        fm_loss_delta_kernel<<<lb, 256, 0, st>>>(tot, M.v, M.target, B.gc, M.delta, M.dgt, M.blockpart);
+        MFM_LAUNCH_CHECK();
+        final_sum_kernel<<<1, 256, 0, st>>>(lb, M.blockpart, loss_out);
+        MFM_LAUNCH_CHECK();
+    }
     auto bias_grad = [&](const float* a, long long lda, int cols, float* out) -> int {
         const int slabs = n >= 8 * COLSUM_SLABS ? COLSUM_SLABS : 1;
         colsum_partial_kernel<<<dim3(ceil_div(cols, 32), slabs), 256, 0, st>>>(n, cols, a, lda, M.colpart);
@@ -227,6 +232,7 @@ static int fm_forward_backward(const mfm_field_t& F, const mfm_target_t& T, int 
         return MFM_OK;
     };
     float* sb = M.splitbuf; const size_t sbf = M.splitbuf_floats;
+    if (part != 2) {
     // layer 7 (nn_xt head): y = h6 W7 + b7
     if ((rc = wgrad(n, H, d, B.h6, H, M.delta, d, GW_(7), sb, sbf, st))) return rc;
     if ((rc = bias_grad(M.delta, d, d, GB_(7)))) return rc;
@@ -247,6 +253,8 @@ static int fm_forward_backward(const mfm_field_t& F, const mfm_target_t& T, int 
     if ((rc = bias_grad(M.dgt, d, d, GB_(4)))) return rc;
     // d s_t = (dgt W4^T + joint part) * relu'(s_t)   (in place)
     if ((rc = dgrad(n, H, d, M.dgt, d, W_(4), M.dcat + H, 2 * H, B.cat + H, 2 * H, M.dcat + H, 2 * H, st))) return rc;
+    }
+    if (part == 1) return MFM_OK;
     // layer 3 (x branch)
     if ((rc = wgrad(n, H, H, B.h2, H, M.dcat, 2 * H, GW_(3), sb, sbf, st))) return rc;
     if ((rc = bias_grad(M.dcat, 2 * H, H, GB_(3)))) return rc;
@@ -332,8 +340,15 @@ static int fm_check(const mfm_field_t* f, const mfm_target_t* t) {
 int mfm_fm_loss_grad(const mfm_field_t* f, const mfm_target_t* t, const uint32_t* rng_key, int n, int chain_offset,
                      int n_total, float sigma, const float* positions, float* loss_out, float* grads, void* ws,
                      size_t ws_bytes, mfm_stream_t stream) {
+    return mfm_fm_loss_grad_part(f, t, rng_key, n, chain_offset, n_total, sigma, positions, loss_out, grads, ws, ws_bytes, 0, stream);
+}
+
+int mfm_fm_loss_grad_part(const mfm_field_t* f, const mfm_target_t* t, const uint32_t* rng_key, int n, int chain_offset,
+                          int n_total, float sigma, const float* positions, float* loss_out, float* grads, void* ws,
+                          size_t ws_bytes, int part, mfm_stream_t stream) {
     int rc = fm_check(f, t);
     if (rc) return rc;
+    if (part < 0 || part > 2) { mfm_set_last_error_msg("part must be 0, 1 or 2"); return MFM_ERR_ARG; }
     if (!rng_key || !positions || !loss_out || !grads) { mfm_set_last_error_msg("null argument"); return MFM_ERR_ARG; }
     if (n <= 0) return MFM_OK;
     if (n_total < chain_offset + n || chain_offset < 0) { mfm_set_last_error_msg("bad chain_offset/n_total"); return MFM_ERR_ARG; }
@@ -341,10 +356,12 @@ int mfm_fm_loss_grad(const mfm_field_t* f, const mfm_target_t* t, const uint32_t
     Workspace w(ws, ws_bytes);
     FmBufs M;
     if (!fm_take(M, w, *f, n)) { mfm_set_last_error_msg("workspace too small (mfm_fm_loss_grad)"); return MFM_ERR_WORKSPACE; }
-    fm_batch_kernel<<<ceil_div(n, 8), 256, 0, stream>>>(rng_key, n, chain_offset, n_total, f->dim, sigma, positions,
-                                                         M.times, M.xt, M.target);
-    MFM_LAUNCH_CHECK();
-    return fm_forward_backward(*f, *t, n, M, loss_out, grads, stream);
+    if (part != 2) {
+        fm_batch_kernel<<<ceil_div(n, 8), 256, 0, stream>>>(rng_key, n, chain_offset, n_total, f->dim, sigma, positions,
+                                                             M.times, M.xt, M.target);
+        MFM_LAUNCH_CHECK();
+    }
+    return fm_forward_backward(*f, *t, n, M, loss_out, grads, stream, part);
 }
 
 int mfm_fm_loss_grad_from_batch(const mfm_field_t* f, const mfm_target_t* t, int n, const float* xt, const float* times,
@@ -361,7 +378,7 @@ int mfm_fm_loss_grad_from_batch(const mfm_field_t* f, const mfm_target_t* t, int
     MFM_CUDA_CHECK(cudaMemcpyAsync(M.xt, xt, nd, cudaMemcpyDeviceToDevice, stream));
     MFM_CUDA_CHECK(cudaMemcpyAsync(M.target, target_v, nd, cudaMemcpyDeviceToDevice, stream));
     MFM_CUDA_CHECK(cudaMemcpyAsync(M.times, times, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, stream));
-    return fm_forward_backward(*f, *t, n, M, loss_out, grads, stream);
+    return fm_forward_backward(*f, *t, n, M, loss_out, grads, stream, 0);
 }
 
 int mfm_adamw_step(float* params, const float* grads, float* mu, float* nu, const uint8_t* decay_mask, long long n_params,

@@ -111,6 +111,9 @@ gemm_tc2p_kernel(const __grid_constant__ Maps maps, GemmShape p, Epi epi, long l
     const Tiles T = make_tiles(M, p.N, p.K, p.k_split);
     if (T.total == 0) return;                   // uniform over the grid
     const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+#ifdef MFM_TC2_TIMELINE
+    if (tl && blockIdx.x == 0 && threadIdx.x == 0) tl[62] = clock64();
+#endif
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a) : "memory");
@@ -262,31 +265,40 @@ gemm_tc2p_kernel(const __grid_constant__ Maps maps, GemmShape p, Epi epi, long l
                 if (lane == 0) mbar_arrive_remote(&split[s], 0);
             }
         }
-    } else if (warp >= EPI_WARP0) {
+    }
+    if (warp >= SPLIT_WARP0) {
         // ---------------- epilogue (each CTA drains its own 128 TMEM lanes) ----------------
-        const int ew = warp - EPI_WARP0;              // 0..7
+        // Epilogue warps 12-19: (TMEM lane quadrant, column half) = 4 chunks of 32 columns per tile.  The
+        // splitter warps 4-11 have nothing left to do once the pair's LAST tile is split, so they take
+        // half of that tile's chunks: its epilogue is the only one no main loop hides.
+        const bool helper = warp < EPI_WARP0;
+        const int ew = helper ? warp - SPLIT_WARP0 : warp - EPI_WARP0;   // 0..7
         const int quad = ew & 3;                      // == warp & 3: the TMEM lane quadrant this warp may access
-        const int chalf = ew >> 2;                    // column half of the tile (4 chunks of 32 columns)
-        const uint32_t stg = smem_u32(stg_base) + (uint32_t)ew * (32u * 32u * 4u);
+        const int chalf = ew >> 2;                    // column half of the tile
+        // staging: the epilogue warps' own buffers; helpers use ring stage 0 (free: every MMA has completed)
+        const uint32_t stg = helper ? smem_u32(smem) + (uint32_t)ew * 4096u : smem_u32(stg_base) + (uint32_t)ew * 4096u;
         const int rsub = lane >> 3, cpiece = (lane & 7) * 4;
-        constexpr int RB = 2;                         // steps whose global reads are issued together (register budget: 102)
-        uint32_t i = 0;
-        for (int t = pair; t < T.total; t += n_pairs, ++i) {
+        constexpr int RB = sizeof(typename Epi::Row4) > 36 ? 2 : 4;   // steps whose global reads are issued together (register budget: 102)
+        const int n_mine = pair < T.total ? (T.total - 1 - pair) / n_pairs + 1 : 0;   // tiles of this pair
+        uint32_t i = helper ? (uint32_t)max(n_mine - 1, 0) : 0u;
+        for (int t = pair + (int)i * n_pairs; t < T.total; t += n_pairs, ++i) {
             int m0p, n0, kz0, KT, neff, z;
             tile_origin(t, m0p, n0, kz0, KT, neff, z);
             const uint32_t b = i & 1, u = i >> 1;
+            const bool last = (int)i == n_mine - 1;
             Epi e = epi;
             if (p.k_split > 0) e.at_z(z);
             const int row_base = m0p + (int)rank * BM + quad * 32;
             const int n_chunks = min(BN / 32, (p.N - n0 + 31) / 32);     // chunks of the whole tile
-            const int cc_begin = chalf * 4, cc_end = min(n_chunks, chalf * 4 + 4);
+            int cc_begin = chalf * 4, cc_end = min(n_chunks, chalf * 4 + 4);
+            if (last) { if (helper) cc_begin = min(cc_begin + 2, cc_end); else cc_end = min(cc_end, cc_begin + 2); }
             mbar_wait(&acc_full[b], u & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (ew == 0) TC2P_MARK(i, 2);
+            if (ew == 0 && !helper) TC2P_MARK(i, 2);
             float rs[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) rs[k] = 0.0f;
-            if (cc_begin >= cc_end) {
+            if (cc_begin >= cc_end && !helper) {
                 // nothing to drain in this column half (edge tile): still release the buffer
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
@@ -298,8 +310,9 @@ gemm_tc2p_kernel(const __grid_constant__ Maps maps, GemmShape p, Epi epi, long l
                 uint32_t r[32];
                 tmem_ld32_nowait(tmem_base + ((uint32_t)(quad * 32) << 16) + b * BN + (uint32_t)col0, r);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (cc == cc_end - 1) {
-                    // this warp's last chunk has left TMEM: hand the buffer back to the MMA issuer
+                if (cc == cc_end - 1 && !helper) {
+                    // this warp's last chunk has left TMEM: hand the buffer back to the MMA issuer (on the
+                    // pair's last tile nobody waits for it any more, so the helpers' chunks need no arrive)
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) mbar_arrive_remote(&acc_empty[b], 0);
@@ -349,12 +362,15 @@ gemm_tc2p_kernel(const __grid_constant__ Maps maps, GemmShape p, Epi epi, long l
                 }
                 __syncwarp();                                 // staging is reused by the next chunk
             }
-            if (ew == 0) TC2P_MARK(i, 3);
+            if (ew == 0 && !helper) TC2P_MARK(i, 3);
         }
     }
     __syncwarp();
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     cluster_sync_all();                     // the peer's shared memory / TMEM / barriers stay alive until both are done
+#ifdef MFM_TC2_TIMELINE
+    if (tl && blockIdx.x == 0 && threadIdx.x == 0) tl[63] = clock64();
+#endif
     if (warp == 2) {
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
     }

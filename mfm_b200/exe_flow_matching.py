@@ -182,7 +182,11 @@ class TrainState:
         self.ref_dist = ref_dists[args.ref_dist](params.dim, device=dev)
 
     # loss_fn(rng_key, samples, params) of the reference (flow_matching_loss, :171-179)
-    def loss_and_grad(self, rng_key, positions, chain_offset=0, n_total=None):
+    def loss_and_grad(self, rng_key, positions, chain_offset=0, n_total=None, group=None, allreduce=False):
+        """value_and_grad(loss_fn) on this rank's chains.  allreduce=True additionally sums loss and gradient
+        over the ranks of `group` (the loss is a SUM over chains, :178): the backward pass is issued in two
+        parts and the all-reduce of the first part's gradients (Dense_4..7, 60 % of the buffer) runs on
+        NCCL's stream while the second part computes."""
         lib = _lib.load()
         a = self.args
         if not a.cond_flow or a.ot_cond_flow:
@@ -190,9 +194,26 @@ class TrainState:
         n = positions.shape[0]
         fd, td = self.model.field_desc(self.P), self.model.dist._desc(1.0)
         ws = _lib.workspace(lib.mfm_fm_workspace_bytes(fd, td, n), positions.device, "fm")
-        _lib.check(lib.mfm_fm_loss_grad(fd, td, _lib.ptr(rng_key), n, chain_offset, n_total if n_total is not None else n,
-                                        float(a.sigma), _lib.ptr(positions.contiguous()), _lib.ptr(self.loss),
-                                        _lib.ptr(self.grads), _lib.ptr(ws), ws.numel(), _lib.stream()))
+        pos = positions.contiguous()
+
+        def part(k):
+            _lib.check(lib.mfm_fm_loss_grad_part(fd, td, _lib.ptr(rng_key), n, chain_offset, n_total if n_total is not None else n,
+                                                 float(a.sigma), _lib.ptr(pos), _lib.ptr(self.loss), _lib.ptr(self.grads),
+                                                 _lib.ptr(ws), ws.numel(), k, _lib.stream()))
+
+        _, world = parallel.world_info(group)
+        if not allreduce or world == 1:
+            part(0)
+            return self.loss, self.grads
+        import torch.distributed as tdist
+        split = self.P.w_off[4]
+        part(1)
+        h_tail = tdist.all_reduce(self.grads[split:], op=tdist.ReduceOp.SUM, group=group, async_op=True)
+        h_loss = tdist.all_reduce(self.loss, op=tdist.ReduceOp.SUM, group=group, async_op=True)
+        part(2)
+        h_head = tdist.all_reduce(self.grads[:split], op=tdist.ReduceOp.SUM, group=group, async_op=True)
+        for h in (h_tail, h_loss, h_head):
+            h.wait()
         return self.loss, self.grads
 
     def apply_gradients(self, grads=None):
@@ -330,8 +351,8 @@ class HotLoop:
         keys = mrandom.split(self.key_sample, 3)
         self.key_sample, key_train_gn, key_train_step = keys[0], keys[1], keys[2]
         self.states, self.last_info = self.gen(key_train_gn, self.states, self.count, self.P, self.beta, inplace=True)
-        loss, grads = self.state.loss_and_grad(key_train_step, self.states.position, self.chain_offset, self.n_total)
-        parallel.allreduce_sum_([grads, loss], self.pg)                        # loss is a SUM over chains (:178)
+        loss, grads = self.state.loss_and_grad(key_train_step, self.states.position, self.chain_offset, self.n_total,
+                                               group=self.pg, allreduce=True)  # loss is a SUM over chains (:178)
         self.state.apply_gradients()
         return loss
 

@@ -8,7 +8,7 @@ from mfm_b200 import _lib
 lib = _lib.load()
 dev = torch.device("cuda:0")
 st = torch.cuda.current_stream().cuda_stream
-n, H = 65536, 1024
+n, H = (int(sys.argv[sys.argv.index("--n") + 1]) if "--n" in sys.argv else 65536), 1024
 g = torch.Generator(device=dev); g.manual_seed(0)
 A = torch.randn(n, H, generator=g, device=dev); Bt = torch.randn(H, H, generator=g, device=dev) * 0.03
 mask = torch.randn(n, H, generator=g, device=dev); add = torch.randn(n, H, generator=g, device=dev)
@@ -28,7 +28,7 @@ for name, m, a in [("plain", None, None), ("mask", mask, None), ("add", None, ad
         e0.record(); run(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(2000):
+    for _ in range(2000 if n > 20000 else 10000):
         run()
     e1.record(); torch.cuda.synchronize()
     if "--timeline" in sys.argv:
@@ -39,4 +39,5 @@ for name, m, a in [("plain", None, None), ("mask", mask, None), ("add", None, ad
         print("   tile: mma_start acc_committed epi_start epi_end (SM clocks since first MMA)")
         for i in range(8):
             print("   ", i, [t[4 * i + k] - t0 for k in range(4)])
-    print(f"{name:9s} burst {np.median(ts):.3f} ms  sustained {e0.elapsed_time(e1) / 2000:.3f} ms  ({2.0 * n * H * H / (e0.elapsed_time(e1) / 2000) / 1e9:.0f} TFLOP/s)")
+        print("    kernel entry", t[62] - t0, "exit", t[63] - t0)
+    print(f"{name:9s} burst {np.median(ts):.3f} ms  sustained {e0.elapsed_time(e1) / (2000 if n > 20000 else 10000):.3f} ms  ({2.0 * n * H * H / (e0.elapsed_time(e1) / (2000 if n > 20000 else 10000)) / 1e9:.0f} TFLOP/s)")

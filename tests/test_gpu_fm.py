@@ -82,6 +82,31 @@ def test_fm_sharded_batch_matches_full(cuda, setups):
     assert rel_err(tot_g.cpu().numpy(), grads.cpu().numpy()) < 1e-5
 
 
+@pytest.mark.parametrize("name", ["phi-four", "pines"])
+def test_fm_two_part_backward_is_identical(cuda, lib, setups, name):
+    """mfm_fm_loss_grad_part 1 then 2 (the split the multi-GPU host uses to overlap the all-reduce) gives
+    bit-identical loss and gradients to the single call; part 1 alone already holds the Dense_4..7 slice."""
+    from mfm_b200 import _lib
+    s = setups[name]
+    n = 160
+    x = to_dev(s.ot.init_positions(tf.PRNGKey(3), n, np.float32), cuda)
+    key = key_dev(tf.PRNGKey(11), cuda)
+    loss, grads = s.state.loss_and_grad(key, x)
+    loss, grads = loss.clone(), grads.clone()
+    st = s.state
+    fd, td = st.model.field_desc(st.P), st.model.dist._desc(1.0)
+    ws = _lib.workspace(lib.mfm_fm_workspace_bytes(fd, td, n), cuda, "fm")
+    g2 = torch.full_like(grads, float("nan")); l2 = torch.zeros_like(loss)
+    split = st.P.w_off[4]
+    for part in (1, 2):
+        _lib.check(lib.mfm_fm_loss_grad_part(fd, td, _lib.ptr(key), n, 0, n, float(st.args.sigma), _lib.ptr(x), _lib.ptr(l2),
+                                             _lib.ptr(g2), _lib.ptr(ws), ws.numel(), part, _lib.stream()))
+        if part == 1:
+            assert torch.equal(g2[split:], grads[split:]) and torch.equal(l2, loss)
+            assert (g2[:split] == 0).all()
+    assert torch.equal(g2, grads)
+
+
 def test_adamw_clip_apply_if_finite(cuda, setups):
     from mfm_b200 import exe_flow_matching as E
     s = setups["4-mode"]
