@@ -95,6 +95,16 @@ void mfm_set_gemm_raw_hi(int raw_hi);
  * built by the splitter warps (error ~2^-19 relative on terms that are 2^-11 of the product).
  * Environment variable MFM_GEMM_CROSS=tf32|bf16. */
 void mfm_set_gemm_cross_bf16(int enable);
+/* Stream-K for the remainder round of the persistent kernel: when the tile count is not a multiple of the number of
+ * CTA pairs (74), the k-blocks of the last, partially filled round are cut into equal contiguous ranges over the pairs;
+ * partial accumulators go through an L2-resident per-stream scratch area the library allocates on first use (19.4 MB)
+ * and the pair that owns a tile's last k-range adds them, in a fixed order, before the epilogue functor runs.
+ * 1 (default) = on, 0 = whole tiles only.  Environment variable MFM_STREAMK=0|1. */
+void mfm_set_gemm_streamk(int enable);
+/* Host-only test hook: the work list the persistent kernel derives for an M x N x K problem on n_pairs CTA pairs, as
+ * rows of 7 ints (pair, tile, first k-block, end k-block, kind 0 whole / 1 contribution / 2 finishing part, first
+ * contributing pair, number of contributing pairs).  Returns the number of rows; writes at most `cap` of them. */
+int mfm_debug_gemm_plan(int M, int N, int K, int n_pairs, int streamk, int* rows, int cap);
 
 /* ---- RNG: jax.random semantics (threefry2x32, legacy keys, x64 off) ------------------------ */
 /* jax.random.split(key, num) -> out uint32[num,2] */
@@ -124,6 +134,11 @@ int mfm_gemm_tf32x3(int M, int N, int K, const float* A, long long lda, int a_km
  * C[M,N] = (A[M,K] * Bt[N,K]^T + add[M,N]) where mask[M,N] > 0, else 0; add and mask optional; add may alias C. */
 int mfm_gemm_tf32x3_gated(int M, int N, int K, const float* A, long long lda, const float* Bt, long long ldb, const float* mask,
                           long long ldm, const float* add, long long ldadd, float* C, long long ldc, mfm_stream_t stream);
+
+/* Dense layer over the first *n_rows_dev rows only (test hook of the ODE driver's active-chain compaction: the row count
+ * lives in device memory and every kernel reads it; rows beyond it are left untouched).  C = A[M,K] * Bt[N,K]^T + bias. */
+int mfm_gemm_tf32x3_rows(int M, int N, int K, const float* A, long long lda, const float* Bt, long long ldb, const float* bias,
+                         float* C, long long ldc, const int* n_rows_dev, mfm_stream_t stream);
 
 /* ---- targets -------------------------------------------------------------------------------- */
 size_t mfm_target_workspace_bytes(const mfm_target_t* t, int n);

@@ -18,6 +18,8 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-diag-suppress", "550"]
 if os.environ.get("MFM_TC2_TIMELINE"):
     FLAGS.append("-DMFM_TC2_TIMELINE")
+    if os.environ.get("MFM_TL_PAIR"):
+        FLAGS.append("-DMFM_TL_PAIR=" + os.environ["MFM_TL_PAIR"])
 
 
 def _sources():

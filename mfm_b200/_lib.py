@@ -57,8 +57,12 @@ SIGNATURES = {
     "mfm_set_gemm_backend": (None, [C.c_int]),
     "mfm_set_gemm_raw_hi": (None, [C.c_int]),
     "mfm_set_gemm_cross_bf16": (None, [C.c_int]),
+    "mfm_set_gemm_streamk": (None, [C.c_int]),
+    "mfm_debug_gemm_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int]),
     "mfm_gemm_tf32x3_gated": (C.c_int, [C.c_int, C.c_int, C.c_int, c_f32p, C.c_longlong, c_f32p, C.c_longlong, c_f32p, C.c_longlong,
                                         c_f32p, C.c_longlong, c_f32p, C.c_longlong, _S]),
+    "mfm_gemm_tf32x3_rows": (C.c_int, [C.c_int, C.c_int, C.c_int, c_f32p, C.c_longlong, c_f32p, C.c_longlong, c_f32p, c_f32p, C.c_longlong,
+                                       C.c_void_p, _S]),
     "mfm_threefry_split": (C.c_int, [c_u32p, C.c_int, c_u32p, _S]),
     "mfm_threefry_split_batched": (C.c_int, [c_u32p, C.c_int, C.c_int, c_u32p, _S]),
     "mfm_threefry_bits": (C.c_int, [c_u32p, C.c_longlong, c_u32p, _S]),

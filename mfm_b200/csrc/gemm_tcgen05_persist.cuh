@@ -49,7 +49,7 @@ constexpr int EPI_STG_BYTES = EPI_WARPS * 32 * 32 * 4;          // 32 KB
 constexpr int NBARS = 3 * STAGES + 4;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STG_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int TMEM_COLS = 512;
-static_assert(NBARS * 8 + 8 <= 256, "barrier area");
+static_assert(NBARS * 8 + 8 + 64 <= 256, "barrier area: barriers, TMEM slot, PairWork");
 
 struct Tiles {
     int m_tiles, n_tiles, z_tiles, total;
@@ -62,6 +62,85 @@ __host__ __device__ inline Tiles make_tiles(int M, int N, int K, int k_split) {
     t.total = t.m_tiles * t.n_tiles * t.z_tiles;
     return t;
 }
+
+// ---- work list of one CTA pair ---------------------------------------------------------------------
+// Rounds of whole tiles (pair p takes tiles p, p + P, ...) plus the REMAINDER round of rem < P tiles.
+// When the remainder is small (rem * 4 <= P: e.g. 8 192 chains x 1 600 columns = 224 tiles = 3 rounds + 2
+// tiles, or the few active chains at the end of an ODE solve) its rem * KT k-blocks are cut into
+// Pp = 4 * rem equal contiguous ranges (stream-K): the round then lasts a quarter of a tile time instead of
+// a whole one.  A pair's range covers at most the END of one tile and the BEGINNING of the next one:
+//   * the beginning (CONTRIB) is the pair's FIRST item: its accumulator is dumped to the pair's workspace
+//     slot (256 x 256 fp32, L2 resident) and flagged per 32 x 32 chunk.  Contributions wait for nothing,
+//     so there is no dependency chain between pairs (every pair of the grid is co-resident);
+//   * the end (FINISH) comes second: its epilogue adds, chunk by chunk and in pair order, the slots of the
+//     pairs that hold the tile's earlier k-ranges before the functor runs;
+//   * the whole tiles follow, so the fix-up epilogue (global loads at ~2.5 k clocks each) hides under
+//     their main loops like any other epilogue.
+// Summation order is fixed => results are deterministic.
+// Measured on B200 (scripts/streamk_bench.py, scripts/streamk_timeline.py): 1.04-1.17x on the layers it
+// applies to.  NOT applied to large remainders (54 tiles on 74 pairs): there the round is bounded by the
+// epilogue chain (dump 13 k + fix-up + 18 k epilogue clocks against 41 k of MMAs), the short items pay a
+// pipeline fill each and the dump / fix-up traffic slows the concurrent MMAs by 15 % - three orderings
+// (fix-up in the epilogue, remainder first; fix-up pre-loaded into TMEM with tcgen05.st, remainder last)
+// all came out 0.7-0.96x of whole tiles.
+enum { ITEM_FULL = 0, ITEM_CONTRIB = 1, ITEM_FINISH = 2 };
+struct Item { int tile, kb0, kb1, kind, c_first, c_count; };
+struct Sched {
+    int P, KT, n_full, rem, Pp, U, pair;
+    __host__ __device__ __forceinline__ int lo(int q) const { return (int)(((long long)q * U) / Pp); }
+    // this pair's share of the remainder: `head` (a CONTRIB item, runs first) and / or `last` (the part that
+    // reaches a tile's final k-block, runs last); returns bit 0 = head present, bit 1 = last present
+    __host__ __device__ __forceinline__ int tail(Item& head, Item& last) const {
+        if (Pp == 0 || pair >= Pp) return 0;
+        const int u0 = lo(pair), u1 = lo(pair + 1), base = n_full * P;
+        if (u1 <= u0) return 0;
+        const int ta = u0 / KT, tb = (u1 - 1) / KT;
+        int have = 0;
+        if (ta != tb || u1 - ta * KT < KT) {         // the range ends inside tile tb: contribution
+            head.tile = base + tb; head.kb0 = ta == tb ? u0 - ta * KT : 0; head.kb1 = u1 - tb * KT;
+            head.kind = ITEM_CONTRIB; head.c_first = 0; head.c_count = 0;
+            have |= 1;
+        }
+        if (ta != tb || u1 - ta * KT == KT) {        // the range reaches the end of tile ta
+            last.tile = base + ta; last.kb0 = u0 - ta * KT; last.kb1 = KT; last.kind = ITEM_FULL; last.c_first = 0; last.c_count = 0;
+            if (last.kb0 > 0) {                      // pairs q < pair whose ranges reach into this tile
+                last.kind = ITEM_FINISH;
+                int q = pair - 1;
+                while (q > 0 && lo(q) > ta * KT) --q;
+                last.c_first = q; last.c_count = pair - q;
+            }
+            have |= 2;
+        }
+        return have;
+    }
+    // number of whole tiles of this pair (without stream-K the remainder round is one more whole tile)
+    __host__ __device__ __forceinline__ int whole() const { return n_full + ((Pp == 0 && pair < rem) ? 1 : 0); }
+    // item `idx` of this pair; false past the end
+    __host__ __device__ __forceinline__ bool get(int idx, Item& it) const {
+        Item head, last;
+        const int have = tail(head, last), nh = have & 1, nl = (have >> 1) & 1, nw = whole();
+        if (idx < nh) { it = head; return true; }
+        if (idx < nh + nl) { it = last; return true; }
+        if (idx - nh - nl < nw) { it.tile = pair + (idx - nh - nl) * P; it.kb0 = 0; it.kb1 = KT; it.kind = ITEM_FULL; it.c_first = 0; it.c_count = 0; return true; }
+        return false;
+    }
+};
+// what the roles read (shared memory, written once in the prologue)
+struct PairWork { int n_head, n_tail, n_items, fix; Item head, last; };   // n_tail = n_head + (last present); fix: `last` needs a fix-up
+constexpr int SK_MAX_SPLIT = 4, SK_MIN_KB = 4;
+__host__ __device__ __forceinline__ Sched make_sched(int total, int n_pairs, int pair, int K, int k_split, bool streamk) {
+    Sched s;
+    s.P = n_pairs; s.pair = pair; s.KT = (K + BK - 1) / BK;
+    s.n_full = total / n_pairs; s.rem = total - s.n_full * n_pairs; s.Pp = 0; s.U = 0;
+    // small remainders only (see above): every remainder tile is cut SK_MAX_SPLIT ways and every range keeps >= SK_MIN_KB k-blocks
+    if (streamk && k_split == 0 && s.rem > 0 && s.rem * SK_MAX_SPLIT <= n_pairs && s.KT >= SK_MAX_SPLIT * SK_MIN_KB) {
+        s.Pp = s.rem * SK_MAX_SPLIT; s.U = s.rem * s.KT;
+    }
+    return s;
+}
+constexpr int SK_SLOT_FLOATS = 2 * BM * BN;     // one pair tile
+constexpr int SK_SLOT_FLAGS = 2 * 4 * (BN / 32);// (CTA, TMEM lane quadrant, 32-column chunk)
+static_assert(SK_SLOT_FLOATS == 256 * 256 && SK_SLOT_FLAGS == 64, "rng.cu::streamk_workspace sizes its buffers with these");
 
 __device__ __forceinline__ void mma_bf16_ss_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     const uint32_t z = 0;
@@ -85,13 +164,18 @@ __device__ __forceinline__ float tf32_trunc_rest(float x) { return x - __uint_as
 // terms carry ~2^-19 relative error (unbiased, round-to-nearest): fp32-class like the rest.
 template <bool A_KMAJOR, bool B_NMAJOR, bool XBF16, class Epi>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
-gemm_tc2p_kernel(const __grid_constant__ Maps maps, GemmShape p, Epi epi, long long* tl) {
+gemm_tc2p_kernel(const __grid_constant__ Maps maps, GemmShape p, Epi epi, long long* tl, float* sk_ws, unsigned* sk_flags, unsigned sk_epoch) {
 #ifdef MFM_TC2_TIMELINE
     // tuning aid: SM clock at 4 events of the first 16 tiles of pair 0's leader (MMA start / accumulator
     // committed / epilogue start / epilogue end)
-#define TC2P_MARK(tile, ev) do { if (tl && blockIdx.x == 0 && (tile) < 16 && lane == 0) tl[(tile) * 4 + (ev)] = clock64(); } while (0)
+#ifndef MFM_TL_PAIR
+#define MFM_TL_PAIR 0
+#endif
+#define TC2P_MARK(tile, ev) do { if (tl && blockIdx.x == 2 * MFM_TL_PAIR && (tile) < 12 && lane == 0) tl[(tile) * 4 + (ev)] = clock64(); } while (0)
+#define TC2P_MARKX(slot) do { if (tl && blockIdx.x == 2 * MFM_TL_PAIR && lane == 0) tl[slot] = clock64(); } while (0)
 #else
 #define TC2P_MARK(tile, ev) do { } while (0)
+#define TC2P_MARKX(slot) do { } while (0)
 #endif
     static_assert(!XBF16 || (A_KMAJOR && !B_NMAJOR), "bf16 cross terms need K-major operands");
     extern __shared__ uint8_t smem_raw[];
@@ -104,6 +188,7 @@ gemm_tc2p_kernel(const __grid_constant__ Maps maps, GemmShape p, Epi epi, long l
     uint64_t* acc_full = bars + 3 * STAGES;     // [2] accumulator buffer complete      (multicast commit)
     uint64_t* acc_empty = bars + 3 * STAGES + 2;// [2] buffer drained by BOTH CTAs      (leader's copy is used)
     uint32_t* tmem_slot = (uint32_t*)(bars + NBARS);
+    volatile PairWork* work = (volatile PairWork*)(bars + NBARS + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -112,7 +197,7 @@ gemm_tc2p_kernel(const __grid_constant__ Maps maps, GemmShape p, Epi epi, long l
     if (T.total == 0) return;                   // uniform over the grid
     const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
 #ifdef MFM_TC2_TIMELINE
-    if (tl && blockIdx.x == 0 && threadIdx.x == 0) tl[62] = clock64();
+    if (tl && blockIdx.x == 2 * MFM_TL_PAIR && threadIdx.x == 0) tl[62] = clock64();
 #endif
 
     if (warp == 0 && lane == 0) {
@@ -126,11 +211,26 @@ gemm_tc2p_kernel(const __grid_constant__ Maps maps, GemmShape p, Epi epi, long l
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
+    if (warp == 3 && lane == 0) {
+        const Sched S = make_sched(T.total, n_pairs, pair, p.K, p.k_split, sk_ws != nullptr);
+        Item head, last;
+        const int have = S.tail(head, last);
+        if (have & 1) { volatile Item* d = &work->head; d->tile = head.tile; d->kb0 = head.kb0; d->kb1 = head.kb1; d->kind = head.kind; d->c_first = 0; d->c_count = 0; }
+        if (have & 2) { volatile Item* d = &work->last; d->tile = last.tile; d->kb0 = last.kb0; d->kb1 = last.kb1; d->kind = last.kind; d->c_first = last.c_first; d->c_count = last.c_count; }
+        work->n_head = have & 1; work->n_tail = (have & 1) + ((have >> 1) & 1); work->n_items = (have & 1) + ((have >> 1) & 1) + S.whole();
+        work->fix = ((have & 2) && last.kind == ITEM_FINISH) ? 1 : 0;
+    }
     __syncwarp();
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     cluster_sync_all();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    // item i of this pair -> tile and k-block range (the list stays in shared memory: the epilogue has no registers to spare)
+    auto item_at = [&](int i, int& tile, int& kb0, int& kb1) {
+        const int j = i - work->n_tail;
+        if (j >= 0) { tile = pair + j * n_pairs; kb0 = 0; kb1 = (p.K + BK - 1) / BK; }
+        else { volatile const Item* w = i < work->n_head ? &work->head : &work->last; tile = w->tile; kb0 = w->kb0; kb1 = w->kb1; }
+    };
 
     // tile t -> (z, row tile, column tile); column tiles vary fastest so concurrent pairs share A rows
     auto tile_origin = [&](int t, int& m0p, int& n0, int& kz0, int& KT, int& neff, int& z) {
@@ -150,12 +250,14 @@ gemm_tc2p_kernel(const __grid_constant__ Maps maps, GemmShape p, Epi epi, long l
         // ---------------- TMA producer (both CTAs) ----------------
         if (lane == 0) {
             uint32_t g = 0;                     // k-blocks issued so far (ring position)
-            for (int t = pair; t < T.total; t += n_pairs) {
-                int m0p, n0, kz0, KT, neff, z;
-                tile_origin(t, m0p, n0, kz0, KT, neff, z);
+            for (int idx = 0; idx < work->n_items; ++idx) {
+                int tile, kt0, kt1, m0p, n0, kz0, KT, neff, z;
+                item_at(idx, tile, kt0, kt1);
+                tile_origin(tile, m0p, n0, kz0, KT, neff, z);
                 const int m0 = m0p + (int)rank * BM;
                 const int nb0 = n0 + (int)rank * (neff / 2);
-                for (int kt = 0; kt < KT; ++kt, ++g) {
+                if (p.k_split > 0) { kt0 = 0; kt1 = KT; }
+                for (int kt = kt0; kt < kt1; ++kt, ++g) {
                     const uint32_t s = g % STAGES, ph = (g / STAGES) & 1;
                     mbar_wait(&empty[s], ph ^ 1);
                     uint8_t* st = smem + s * STAGE_BYTES;
@@ -172,18 +274,20 @@ gemm_tc2p_kernel(const __grid_constant__ Maps maps, GemmShape p, Epi epi, long l
         // ---------------- MMA issuer (leader CTA only) ----------------
         if (rank == 0 && lane == 0) {
             uint32_t g = 0, i = 0;
-            for (int t = pair; t < T.total; t += n_pairs, ++i) {
-                int m0p, n0, kz0, KT, neff, z;
-                tile_origin(t, m0p, n0, kz0, KT, neff, z);
+            for (; (int)i < work->n_items; ++i) {
+                int tile, kt0, kt1, m0p, n0, kz0, KT, neff, z;
+                item_at((int)i, tile, kt0, kt1);
+                tile_origin(tile, m0p, n0, kz0, KT, neff, z);
+                if (p.k_split > 0) { kt0 = 0; kt1 = KT; }
                 const uint32_t b = i & 1, u = i >> 1;
                 const uint32_t idesc = make_idesc_base(!A_KMAJOR, B_NMAJOR) | ((uint32_t)(neff >> 3) << 17);
                 // kind::f16: D = f32, A = B = bf16, both K-major, same M and N
                 const uint32_t idesc16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(neff >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
                 const uint32_t acc = tmem_base + b * BN;
                 mbar_wait(&acc_empty[b], (u & 1) ^ 1);          // both CTAs have drained this buffer (tile i-2)
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 TC2P_MARK(i, 0);
-                for (int kt = 0; kt < KT; ++kt, ++g) {
+                for (int kt = kt0; kt < kt1; ++kt, ++g) {
                     const uint32_t s = g % STAGES, ph = (g / STAGES) & 1;
                     mbar_wait(&split[s], ph);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -199,10 +303,10 @@ gemm_tc2p_kernel(const __grid_constant__ Maps maps, GemmShape p, Epi epi, long l
                         const uint64_t dah = make_desc(a_hi + ao, albo, asbo, alt), dal = make_desc(a_lo + ao, albo, asbo, alt);
                         const uint64_t dbh = make_desc(b_hi + bo, blbo, bsbo, blt), dbl = make_desc(b_lo + bo, blbo, bsbo, blt);
                         if (XBF16) {
-                            mma_tf32_ss_2sm(acc, dah, dbh, idesc, (kt | ks) != 0);
+                            mma_tf32_ss_2sm(acc, dah, dbh, idesc, ((kt - kt0) | ks) != 0);
                             mma_bf16_ss_2sm(acc, dal, dbl, idesc16, 1);      // "lo" region = the bf16 cross tiles
                         } else {
-                            mma_tf32_ss_2sm(acc, dal, dbh, idesc, (kt | ks) != 0);
+                            mma_tf32_ss_2sm(acc, dal, dbh, idesc, ((kt - kt0) | ks) != 0);
                             mma_tf32_ss_2sm(acc, dah, dbl, idesc, 1);
                             mma_tf32_ss_2sm(acc, dah, dbh, idesc, 1);
                         }
@@ -217,10 +321,12 @@ gemm_tc2p_kernel(const __grid_constant__ Maps maps, GemmShape p, Epi epi, long l
         // ---------------- splitters (both CTAs) ----------------
         const int tix = threadIdx.x - SPLIT_WARP0 * 32;
         uint32_t g = 0;
-        for (int t = pair; t < T.total; t += n_pairs) {
-            int m0p, n0, kz0, KT, neff, z;
-            tile_origin(t, m0p, n0, kz0, KT, neff, z);
-            for (int kt = 0; kt < KT; ++kt, ++g) {
+        for (int idx = 0; idx < work->n_items; ++idx) {
+            int tile, kb0, kb1;
+            item_at(idx, tile, kb0, kb1);
+            int n_kb = kb1 - kb0;
+            if (p.k_split > 0) { int m0p, n0, kz0, KT, neff, z; tile_origin(tile, m0p, n0, kz0, KT, neff, z); n_kb = KT; }
+            for (int kt = 0; kt < n_kb; ++kt, ++g) {
                 const uint32_t s = g % STAGES, ph = (g / STAGES) & 1;
                 mbar_wait(&full[s], ph);
                 const uint32_t hi = smem_u32(smem + s * STAGE_BYTES) + (uint32_t)tix * 16u;
@@ -279,13 +385,69 @@ gemm_tc2p_kernel(const __grid_constant__ Maps maps, GemmShape p, Epi epi, long l
         const uint32_t stg = helper ? smem_u32(smem) + (uint32_t)ew * 4096u : smem_u32(stg_base) + (uint32_t)ew * 4096u;
         const int rsub = lane >> 3, cpiece = (lane & 7) * 4;
         constexpr int RB = sizeof(typename Epi::Row4) > 36 ? 2 : 4;   // steps whose global reads are issued together (register budget: 102)
-        const int n_mine = pair < T.total ? (T.total - 1 - pair) / n_pairs + 1 : 0;   // tiles of this pair
-        uint32_t i = helper ? (uint32_t)max(n_mine - 1, 0) : 0u;
-        for (int t = pair + (int)i * n_pairs; t < T.total; t += n_pairs, ++i) {
-            int m0p, n0, kz0, KT, neff, z;
-            tile_origin(t, m0p, n0, kz0, KT, neff, z);
+        if (work->n_head != 0 && (!helper || work->n_items == 1)) {
+            // ---- stream-K contribution (item 0, accumulator buffer 0): dump to this pair's slot, flag per chunk ----
+            int tile, kb0_, kb1_, m0p, n0, kz0, KT, neff, z;
+            item_at(0, tile, kb0_, kb1_);
+            tile_origin(tile, m0p, n0, kz0, KT, neff, z);
+            const int n_chunks = min(BN / 32, (p.N - n0 + 31) / 32);
+            int cc_begin = chalf * 4, cc_end = min(n_chunks, chalf * 4 + 4);
+            if (work->n_items == 1) { if (helper) cc_begin = min(cc_begin + 2, cc_end); else cc_end = min(cc_end, cc_begin + 2); }
+            mbar_wait(&acc_full[0], 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (ew == 0 && !helper) TC2P_MARKX(48);
+            if (cc_begin >= cc_end && !helper) {
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive_remote(&acc_empty[0], 0);
+            }
+#pragma unroll 1
+            for (int cc = cc_begin; cc < cc_end; ++cc) {
+                uint32_t r[32];
+                tmem_ld32_nowait(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(cc * 32), r);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (cc == cc_end - 1 && !helper) {
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_remote(&acc_empty[0], 0);
+                }
+                const uint32_t dst = stg + (uint32_t)lane * 128u;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (uint32_t)((j ^ (lane & 7)) << 4)), "f"(__uint_as_float(r[4 * j])),
+                                 "f"(__uint_as_float(r[4 * j + 1])), "f"(__uint_as_float(r[4 * j + 2])), "f"(__uint_as_float(r[4 * j + 3])) : "memory");
+                __syncwarp();
+                // this warp's 32 x 32 chunk goes to rows rank*128 + quad*32 .., columns cc*32 .. of the slot, moved like C
+                // itself (4 rows x 128 contiguous bytes per instruction)
+                float* dstp = sk_ws + (size_t)pair * SK_SLOT_FLOATS + (size_t)((int)rank * BM + quad * 32 + rsub) * BN + cc * 32 + cpiece;
+                const uint32_t sa = stg + (uint32_t)rsub * 128u;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    float4 v;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                                 : "r"(sa + (uint32_t)k * 512u + (uint32_t)(((lane & 7) ^ ((k * 4 + rsub) & 7)) << 4)));
+                    __stcg(reinterpret_cast<float4*>(dstp + (size_t)k * 4 * BN), v);
+                }
+            }
+            // one release for the warp's chunks: every lane's stores -> __syncwarp -> lane 0's fence -> the flags
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence();
+                for (int cc = cc_begin; cc < cc_end; ++cc)
+                    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(sk_flags + (size_t)pair * SK_SLOT_FLAGS + rank * 32u + (uint32_t)quad * 8u + (uint32_t)cc),
+                                 "r"(sk_epoch) : "memory");
+            }
+        }
+        if (ew == 0 && !helper) TC2P_MARKX(49);
+        // the finishing part and the whole tiles (helpers: the last item only, unless that was the contribution)
+        uint32_t i = (uint32_t)(helper ? max(work->n_items - 1, work->n_head) : work->n_head);
+        for (; (int)i < work->n_items; ++i) {
+            int tile, kb0_, kb1_, m0p, n0, kz0, KT, neff, z;
+            item_at((int)i, tile, kb0_, kb1_);
+            tile_origin(tile, m0p, n0, kz0, KT, neff, z);
             const uint32_t b = i & 1, u = i >> 1;
-            const bool last = (int)i == n_mine - 1;
+            const bool last = (int)i == work->n_items - 1;
+            const bool fix = work->fix != 0 && (int)i == work->n_head;      // stream-K FINISH item: add the earlier k-ranges
             Epi e = epi;
             if (p.k_split > 0) e.at_z(z);
             const int row_base = m0p + (int)rank * BM + quad * 32;
@@ -323,6 +485,36 @@ gemm_tc2p_kernel(const __grid_constant__ Maps maps, GemmShape p, Epi epi, long l
                     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (uint32_t)((j ^ (lane & 7)) << 4)), "f"(__uint_as_float(r[4 * j])),
                                  "f"(__uint_as_float(r[4 * j + 1])), "f"(__uint_as_float(r[4 * j + 2])), "f"(__uint_as_float(r[4 * j + 3])) : "memory");
                 __syncwarp();
+                if (fix) {
+                    // stream-K: add this chunk of the contributing pairs' slots into the staged accumulator, moved like C itself
+                    // (4 rows x 128 contiguous bytes per instruction; each lane updates exactly the pieces it reads back below)
+                    const int c_first = work->last.c_first, c_count = work->last.c_count;
+                    const uint32_t fidx = rank * 32u + (uint32_t)quad * 8u + (uint32_t)cc;
+                    if (lane < c_count) {                     // one lane per contributing pair
+                        const unsigned* fl = sk_flags + (size_t)(c_first + lane) * SK_SLOT_FLAGS + fidx;
+                        unsigned seen;
+                        do {
+                            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(fl) : "memory");
+                        } while (seen != sk_epoch);
+                    }
+                    __syncwarp();
+                    const size_t toff = (size_t)((int)rank * BM + quad * 32 + rsub) * BN + col0 + cpiece;
+                    const uint32_t sa = stg + (uint32_t)rsub * 128u;
+#pragma unroll 1
+                    for (int c = 0; c < c_count; ++c) {
+                        const float* srcp = sk_ws + (size_t)(c_first + c) * SK_SLOT_FLOATS + toff;
+                        float4 v[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) v[k] = __ldcg(reinterpret_cast<const float4*>(srcp + (size_t)k * 4 * BN));
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const uint32_t ad = sa + (uint32_t)k * 512u + (uint32_t)(((lane & 7) ^ ((k * 4 + rsub) & 7)) << 4);
+                            float4 w;
+                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w.x), "=f"(w.y), "=f"(w.z), "=f"(w.w) : "r"(ad));
+                            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(ad), "f"(w.x + v[k].x), "f"(w.y + v[k].y), "f"(w.z + v[k].z), "f"(w.w + v[k].w) : "memory");
+                        }
+                    }
+                }
                 const int col = n0 + col0 + cpiece;           // N % 4 == 0: the four columns are valid together
                 const bool cvalid = col < p.N;
                 typename Epi::Col4 ca;
@@ -369,7 +561,7 @@ gemm_tc2p_kernel(const __grid_constant__ Maps maps, GemmShape p, Epi epi, long l
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     cluster_sync_all();                     // the peer's shared memory / TMEM / barriers stay alive until both are done
 #ifdef MFM_TC2_TIMELINE
-    if (tl && blockIdx.x == 0 && threadIdx.x == 0) tl[63] = clock64();
+    if (tl && blockIdx.x == 2 * MFM_TL_PAIR && threadIdx.x == 0) tl[63] = clock64();
 #endif
     if (warp == 2) {
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
@@ -383,6 +575,9 @@ inline bool eligible(const GemmShape& p, const Epi& epi) {
 }
 
 int sm_pairs();                             // number of TPC pairs to keep resident (74 on B200)
+// per-stream stream-K scratch (SK slots of 256 KB + flags, allocated on first use) and the launch epoch the
+// flags are compared with; false when stream-K is switched off (env MFM_STREAMK=0 / mfm_set_gemm_streamk)
+bool streamk_workspace(cudaStream_t st, float** ws, unsigned** flags, unsigned* epoch);
 int gemm_cross_bf16();                      // 1: K-major x K-major GEMMs take their cross terms from one bf16 MMA (env MFM_GEMM_CROSS=tf32|bf16)
 
 template <bool A_KMAJOR, bool B_NMAJOR, class Epi>
@@ -401,8 +596,14 @@ inline cudaError_t launch(const GemmShape& p, const Epi& epi, cudaStream_t st) {
         configured = true;
     }
     const Tiles T = make_tiles(p.M, p.N, p.K, p.k_split);
-    const int pairs = T.total < sm_pairs() ? T.total : sm_pairs();
-    kern<<<dim3(2 * pairs), THREADS, SMEM_BYTES, st>>>(maps, p, epi, tc2::gemm_timeline());
+    // stream-K (small remainder round cut along K) needs the per-stream workspace and the whole grid resident; with a
+    // device-side row count the kernel decides by itself
+    float* sk_ws = nullptr; unsigned* sk_flags = nullptr; unsigned sk_epoch = 0;
+    const int rem = T.total % sm_pairs();
+    const bool sk = p.k_split == 0 && (p.K + BK - 1) / BK >= SK_MAX_SPLIT * SK_MIN_KB && (p.n_rows_dev || (rem != 0 && rem * SK_MAX_SPLIT <= sm_pairs())) &&
+                    streamk_workspace(st, &sk_ws, &sk_flags, &sk_epoch);
+    const int pairs = (sk || T.total >= sm_pairs()) ? sm_pairs() : T.total;
+    kern<<<dim3(2 * pairs), THREADS, SMEM_BYTES, st>>>(maps, p, epi, tc2::gemm_timeline(), sk_ws, sk_flags, sk_epoch);
     ++g_mfm_launches;
     return cudaGetLastError();
 }

@@ -30,6 +30,36 @@ int gemm_cross_bf16() {
     if (g_cross_bf16 < 0) { const char* e = getenv("MFM_GEMM_CROSS"); g_cross_bf16 = (e && strcmp(e, "tf32") == 0) ? 0 : 1; }
     return g_cross_bf16;
 }
+int sm_pairs();
+static int g_streamk = -1;
+constexpr int SK_SLOT_FLOATS = 256 * 256, SK_SLOT_FLAGS = 64;   // = gemm_tcgen05_persist.cuh (static_assert there)
+struct SkWs { cudaStream_t st; int dev; float* ws; unsigned* flags; unsigned epoch; };
+static SkWs g_skws[8];
+static int g_n_skws = 0;
+// One scratch area per (device, stream): GEMMs on one stream are ordered, so a slot is never rewritten
+// while an earlier launch still reads it.  Allocated on the first stream-K launch of the stream (the only
+// allocation the library makes; 19.4 MB + 19 KB).  Streams beyond the 8th run without stream-K.
+bool streamk_workspace(cudaStream_t st, float** ws, unsigned** flags, unsigned* epoch) {
+    if (g_streamk < 0) { const char* e = getenv("MFM_STREAMK"); g_streamk = (e && e[0] == '0') ? 0 : 1; }
+    if (!g_streamk) return false;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    SkWs* w = nullptr;
+    for (int i = 0; i < g_n_skws; ++i) if (g_skws[i].st == st && g_skws[i].dev == dev) { w = &g_skws[i]; break; }
+    if (!w) {
+        if (g_n_skws == 8) return false;
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return false;
+        SkWs n{st, dev, nullptr, nullptr, 0};
+        const size_t fbytes = (size_t)sm_pairs() * SK_SLOT_FLAGS * sizeof(unsigned);
+        if (cudaMalloc(&n.ws, (size_t)sm_pairs() * SK_SLOT_FLOATS * sizeof(float)) != cudaSuccess) { cudaGetLastError(); return false; }
+        if (cudaMalloc(&n.flags, fbytes) != cudaSuccess || cudaMemset(n.flags, 0, fbytes) != cudaSuccess) { cudaGetLastError(); cudaFree(n.ws); return false; }
+        g_skws[g_n_skws] = n;
+        w = &g_skws[g_n_skws++];
+    }
+    *ws = w->ws; *flags = w->flags; *epoch = ++w->epoch;
+    return true;
+}
 int sm_pairs() {
     static int pairs = 0;
     if (pairs == 0) {
@@ -50,6 +80,7 @@ int gemm_raw_hi() {
 }
 extern "C" void mfm_set_gemm_raw_hi(int v) { mfm::tc2::g_raw_hi = v ? 1 : 0; }
 extern "C" void mfm_set_gemm_cross_bf16(int v) { mfm::tc2p::g_cross_bf16 = v ? 1 : 0; }
+extern "C" void mfm_set_gemm_streamk(int v) { mfm::tc2p::g_streamk = v ? 1 : 0; }
 // tuning aid (not part of the ABI header): SM-clock timeline of one CTA pair of the last tc2 GEMM
 namespace mfm { namespace tc2 {
 static long long* g_timeline_buf = nullptr;

@@ -262,6 +262,21 @@ int target_field_terms(const mfm_target_t& T, int n, const float* x, const float
 
 extern "C" {
 
+/* Host-side copy of the persistent kernel's work list (gemm_tcgen05_persist.cuh::Sched), for tests without a GPU:
+ * rows of 7 ints (pair, tile, kb0, kb1, kind, c_first, c_count); returns the number of rows (<= cap written). */
+int mfm_debug_gemm_plan(int M, int N, int K, int n_pairs, int streamk, int* rows, int cap) {
+    using namespace mfm::tc2p;
+    const Tiles T = make_tiles(M, N, K, 0);
+    int n = 0;
+    for (int pair = 0; pair < n_pairs; ++pair) {
+        const Sched S = make_sched(T.total, n_pairs, pair, K, 0, streamk != 0);
+        Item it;
+        for (int idx = 0; S.get(idx, it); ++idx, ++n)
+            if (n < cap) { int* r = rows + 7 * n; r[0] = pair; r[1] = it.tile; r[2] = it.kb0; r[3] = it.kb1; r[4] = it.kind; r[5] = it.c_first; r[6] = it.c_count; }
+    }
+    return n;
+}
+
 int mfm_gemm_tf32x3(int M, int N, int K, const float* A, long long lda, int a_kmajor, const float* B, long long ldb,
                     int b_nmajor, const float* bias, int relu, float* Cout, long long ldc, mfm_stream_t stream) {
     using namespace mfm;
@@ -281,6 +296,15 @@ int mfm_gemm_tf32x3_gated(int M, int N, int K, const float* A, long long lda, co
     using namespace mfm;
     GemmShape p{M, N, K, A, lda, Bt, ldb, nullptr};
     EpiStd e{Cout, ldc, nullptr, mask, ldm, add, ldadd, 1.0f, 0};
+    MFM_CUDA_CHECK((launch_gemm<true, false>(p, e, stream)));
+    return MFM_OK;
+}
+
+int mfm_gemm_tf32x3_rows(int M, int N, int K, const float* A, long long lda, const float* Bt, long long ldb, const float* bias,
+                         float* Cout, long long ldc, const int* n_rows_dev, mfm_stream_t stream) {
+    using namespace mfm;
+    GemmShape p{M, N, K, A, lda, Bt, ldb, n_rows_dev};
+    EpiStd e{Cout, ldc, bias, nullptr, 0, nullptr, 0, 1.0f, 0};
     MFM_CUDA_CHECK((launch_gemm<true, false>(p, e, stream)));
     return MFM_OK;
 }

@@ -65,7 +65,7 @@ def test_gemm_bf16_cross_terms(cuda, lib, M, N, K):
                                        torch.cuda.current_stream().cuda_stream))
         got = Cd.cpu().numpy()
     finally:
-        lib.mfm_set_gemm_cross_bf16(0)
+        lib.mfm_set_gemm_cross_bf16(1)         # the library default
     ref = A.astype(np.float64) @ Bt.astype(np.float64).T + bias
     # row-wise scale: the rows of A span two orders of magnitude
     scale = np.maximum(np.abs(ref).max(axis=1, keepdims=True), 1.0)
@@ -96,6 +96,83 @@ def test_gemm_gated_epilogue(cuda, lib, M, N, K, use_mask, use_add, inplace):
     got = Cd.cpu().numpy()
     assert np.isfinite(got).all()
     assert np.abs(got - ref).max() <= (3e-6 + 1.2e-8 * K) * max(np.abs(ref).max(), 1.0)
+
+
+# shapes whose last round of 256 x 256 tiles is partially filled on 74 CTA pairs (tests/test_gemm_plan.py checks the
+# work lists on the host): two-item pairs, integer split factors, fewer tiles than pairs, ragged M / N / K
+STREAMK_SHAPES = [(8192, 1600, 1024), (1024, 1024, 1600), (4096 + 77, 1088, 520), (256, 256, 4096), (16384, 1600, 1600),
+                  (5000 - 256, 1600, 1600), (19200, 1024, 1024), (8192, 1024, 1024)]
+
+
+@pytest.mark.parametrize("M,N,K", STREAMK_SHAPES)
+def test_gemm_streamk_matches_whole_tiles(cuda, lib, M, N, K):
+    """Remainder round cut along K (partials through the L2 scratch, fixed summation order) vs whole tiles vs float64."""
+    rng = np.random.default_rng(M + 5 * N + K)
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    Bt = rng.standard_normal((N, K)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+    Ad, Bd, bias_d = torch.from_numpy(A).to(cuda), torch.from_numpy(Bt).to(cuda), torch.from_numpy(bias).to(cuda)
+    st = torch.cuda.current_stream().cuda_stream
+    outs = {}
+    try:
+        for mode in (1, 0, 1):
+            lib.mfm_set_gemm_streamk(mode)
+            for rep in range(2 if mode else 1):
+                Cd = torch.full((M, N), float("nan"), dtype=torch.float32, device=cuda)
+                _lib.check(lib.mfm_gemm_tf32x3(M, N, K, Ad.data_ptr(), K, 1, Bd.data_ptr(), K, 0, bias_d.data_ptr(), 1, Cd.data_ptr(), N, st))
+                outs.setdefault(mode, []).append(Cd.cpu().numpy())
+    finally:
+        lib.mfm_set_gemm_streamk(1)
+    ref = np.maximum(A.astype(np.float64) @ Bt.astype(np.float64).T + bias, 0)
+    scale = max(np.abs(ref).max(), 1.0)
+    for mode, lst in outs.items():
+        for got in lst:
+            assert np.isfinite(got).all()
+            assert np.abs(got - ref).max() <= (3e-6 + 8e-9 * K) * scale, (mode, np.abs(got - ref).max() / scale)
+    # deterministic: four launches (epochs 1, 2, then 3, 4 after a whole-tile launch) give the same bits
+    for got in outs[1][1:]:
+        assert np.array_equal(got, outs[1][0])
+    # the two differ by the accumulator-truncation bias (partials are added with round-to-nearest)
+    assert np.abs(outs[1][0] - outs[0][0]).max() <= (3e-6 + 8e-9 * K) * scale
+
+
+@pytest.mark.parametrize("M,N,K", [(8192, 1600, 1024), (1024, 1024, 1024)])
+def test_gemm_streamk_gated_epilogue(cuda, lib, M, N, K):
+    """Stream-K under the backward-data epilogue (mask and in-place residual operands are read by the finishing pair only)."""
+    rng = np.random.default_rng(M + N)
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    Bt = rng.standard_normal((N, K)).astype(np.float32)
+    mask = rng.standard_normal((M, N)).astype(np.float32)
+    add = rng.standard_normal((M, N)).astype(np.float32)
+    Ad, Bd, md = torch.from_numpy(A).to(cuda), torch.from_numpy(Bt).to(cuda), torch.from_numpy(mask).to(cuda)
+    Cd = torch.from_numpy(add).to(cuda)
+    lib.mfm_set_gemm_streamk(1)
+    _lib.check(lib.mfm_gemm_tf32x3_gated(M, N, K, Ad.data_ptr(), K, Bd.data_ptr(), K, md.data_ptr(), N, Cd.data_ptr(), N, Cd.data_ptr(), N,
+                                         torch.cuda.current_stream().cuda_stream))
+    ref = np.where(mask > 0, A.astype(np.float64) @ Bt.astype(np.float64).T + add, 0.0)
+    got = Cd.cpu().numpy()
+    assert np.isfinite(got).all()
+    assert np.abs(got - ref).max() <= (3e-6 + 1.2e-8 * K) * max(np.abs(ref).max(), 1.0)
+
+
+@pytest.mark.parametrize("rows", [8192, 5000, 4800, 700, 256, 1, 0])
+def test_gemm_streamk_device_row_count(cuda, lib, rows):
+    """Active-row count read on the device (ODE compaction): the kernel derives its work list from the live M."""
+    M, N, K = 9000, 1024, 1024
+    rng = np.random.default_rng(rows)
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    Bt = rng.standard_normal((N, K)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+    Ad, Bd, bias_d = torch.from_numpy(A).to(cuda), torch.from_numpy(Bt).to(cuda), torch.from_numpy(bias).to(cuda)
+    Cd = torch.full((M, N), -7.0, dtype=torch.float32, device=cuda)
+    nrows = torch.tensor([rows], dtype=torch.int32, device=cuda)
+    _lib.check(lib.mfm_gemm_tf32x3_rows(M, N, K, Ad.data_ptr(), K, Bd.data_ptr(), K, bias_d.data_ptr(), Cd.data_ptr(), N, nrows.data_ptr(),
+                                        torch.cuda.current_stream().cuda_stream))
+    got = Cd.cpu().numpy()
+    ref = A[:rows].astype(np.float64) @ Bt.astype(np.float64).T + bias
+    assert (got[rows:] == -7.0).all()
+    if rows:
+        assert np.abs(got[:rows] - ref).max() <= (3e-6 + 8e-9 * K) * np.abs(ref).max()
 
 
 def test_gemm_strided_views(cuda, lib):
