@@ -45,9 +45,9 @@ def parse():
     p.add_argument("--chains", type=int, default=65536, help="total chains over all GPUs")
     p.add_argument("--mcmc_per_flow_steps", dest="m", type=int, default=100)
     p.add_argument("--head_scale", type=float, default=0.1)
-    p.add_argument("--warmup_unit", type=str, default="iteration", choices=["iteration", "cycle"],
-                   help="a warm-up step is one outer iteration (default; >=3 of them touch every MALA/FM kernel, and "
-                        "one extra flow-MH iteration is always run untimed) or a full cycle")
+    p.add_argument("--warmup_unit", type=str, default="cycle", choices=["iteration", "cycle"],
+                   help="a warm-up step is one full cycle (default, = a timed step) or one outer iteration (>=3 of them touch every MALA/FM kernel, and "
+                        "one extra flow-MH iteration is then run untimed)")
     p.add_argument("--no_cpu_baseline", action="store_true")
     p.add_argument("--no_e2e", action="store_true")
     return p.parse_args()
@@ -270,6 +270,7 @@ def main():
         loop.count = saved
         # realign: the timed window must start right after a multiple of (m+1)
         loop.count = 0
+    loop.flush()
     sync()
 
     # ---- timed region --------------------------------------------------------------------------
@@ -280,6 +281,7 @@ def main():
     e0.record()
     for _ in range(a.steps):
         run_cycle()
+    loop.flush()                          # multi-rank runs pipeline the last AdamW update: it belongs to the timed work
     e1.record()
     sync()
     ms = e0.elapsed_time(e1)
@@ -304,12 +306,15 @@ def main():
 
     fl = flops_per_chain()
     key_t = mr.PRNGKey(99, dev)
+    loop.flush()
     ms_fm = timed(lambda: loop.state.loss_and_grad(key_t, loop.states.position, off, n_total), 3)
     from mfm_b200.bblackjax.mcmc.mala import mala_step
     ms_mala = timed(lambda: mala_step(dist.tempered(1.0), key_t, loop.states, 0.01, False, off, n_total, inplace=True), 3)
     # one whole MALA outer iteration (data generator + FM loss/grad + gradient all-reduce + AdamW), max over ranks
+    loop.flush()
     loop.count = 0
     ms_iter = timed(loop.iteration, 5)
+    loop.flush()
     t_it = torch.tensor([ms_iter], dtype=torch.float64, device=dev)
     if world > 1:
         tdist.all_reduce(t_it, op=tdist.ReduceOp.MAX)
@@ -374,6 +379,7 @@ def main():
             loss = None
             for _ in range(cyc):
                 loss = loop.iteration()
+            loop.flush()
             host_out.copy_(loop.states.position, non_blocking=True)   # D2H: new positions + loss
             host_loss.copy_(loss, non_blocking=True)
             torch.cuda.current_stream().synchronize()

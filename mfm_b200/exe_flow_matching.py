@@ -180,13 +180,18 @@ class TrainState:
         self.opt_state = torch.tensor([0, 0, 0, 1, 0, 0, 0, 0], dtype=torch.int32, device=dev)
         self.step = 0
         self.ref_dist = ref_dists[args.ref_dist](params.dim, device=dev)
+        self._pending = None      # gradient all-reduce handles of an update that has not been applied yet
+
 
     # loss_fn(rng_key, samples, params) of the reference (flow_matching_loss, :171-179)
-    def loss_and_grad(self, rng_key, positions, chain_offset=0, n_total=None, group=None, allreduce=False):
+    def loss_and_grad(self, rng_key, positions, chain_offset=0, n_total=None, group=None, allreduce=False, defer=False):
         """value_and_grad(loss_fn) on this rank's chains.  allreduce=True additionally sums loss and gradient
         over the ranks of `group` (the loss is a SUM over chains, :178): the backward pass is issued in two
         parts and the all-reduce of the first part's gradients (Dense_4..7, 60 % of the buffer) runs on
-        NCCL's stream while the second part computes."""
+        NCCL's stream while the second part computes.  defer=True returns once the LOSS is reduced and leaves
+        the gradient all-reduces in flight: `apply_pending()` waits for them and applies the update, which
+        lets the caller put parameter-independent work (the next MALA step) under the exchange."""
+        assert self._pending is None, "apply_pending() first: the gradient buffer is still being reduced"
         lib = _lib.load()
         a = self.args
         if not a.cond_flow or a.ot_cond_flow:
@@ -204,6 +209,8 @@ class TrainState:
         _, world = parallel.world_info(group)
         if not allreduce or world == 1:
             part(0)
+            if defer:
+                self._pending = ()
             return self.loss, self.grads
         import torch.distributed as tdist
         split = self.P.w_off[4]
@@ -212,9 +219,22 @@ class TrainState:
         h_loss = tdist.all_reduce(self.loss, op=tdist.ReduceOp.SUM, group=group, async_op=True)
         part(2)
         h_head = tdist.all_reduce(self.grads[:split], op=tdist.ReduceOp.SUM, group=group, async_op=True)
-        for h in (h_tail, h_loss, h_head):
+        h_loss.wait()
+        if defer:
+            self._pending = (h_tail, h_head)
+            return self.loss, self.grads
+        for h in (h_tail, h_head):
             h.wait()
         return self.loss, self.grads
+
+    def apply_pending(self):
+        """Finish a deferred update: wait (on the stream) for the gradient all-reduces, then AdamW."""
+        if self._pending is not None:
+            for h in self._pending:
+                h.wait()
+            self._pending = None
+            self.apply_gradients()
+        return self
 
     def apply_gradients(self, grads=None):
         lib = _lib.load()
@@ -324,7 +344,7 @@ class HotLoop:
     only exchange is the SUM all-reduce of the flat FM gradient (and the scalar loss)."""
 
     def __init__(self, dist, model, P, args, ode_opts, key_sample, positions, beta=1.0, chain_offset=0, n_total=None,
-                 process_group=None):
+                 process_group=None, pipeline=None):
         import torch.distributed as tdist
         self.dist, self.model, self.P, self.args = dist, model, P, args
         self.n = positions.shape[0]
@@ -332,6 +352,7 @@ class HotLoop:
         self.chain_offset = chain_offset
         self.pg = process_group
         self.world = tdist.get_world_size(process_group) if (tdist.is_available() and tdist.is_initialized()) else 1
+        self.pipeline = (self.world > 1) if pipeline is None else bool(pipeline)
         self.lr_fn = create_learning_rate_fn(args.learning_iter, args.warmup_steps, args.learning_rate)
         self.state = create_train_state(model, P, self.lr_fn, args)
         self.gen, self.init_fn, self.transform_and_logdet = create_train_data_gn(
@@ -346,15 +367,30 @@ class HotLoop:
         self.states = self.init_fn(positions, self.beta)
 
     def iteration(self):
-        import torch.distributed as tdist
+        """One outer iteration (exe_flow_matching.py:433-439): data generator, then train_step.
+
+        With several ranks the parameter update is pipelined: the gradient all-reduce of iteration k stays in
+        flight while iteration k+1's MALA step runs (a MALA step reads the target only, never the MLP), and AdamW
+        is applied right after it, before anything reads the parameters; a flow-MH iteration applies it first.
+        Same arithmetic in the same order as the unpipelined loop."""
         self.count += 1
         keys = mrandom.split(self.key_sample, 3)
         self.key_sample, key_train_gn, key_train_step = keys[0], keys[1], keys[2]
+        if self.is_flow_iteration(self.count):
+            self.state.apply_pending()          # the flow step integrates the CURRENT vector field
         self.states, self.last_info = self.gen(key_train_gn, self.states, self.count, self.P, self.beta, inplace=True)
+        self.state.apply_pending()
+        pipelined = self.pipeline
         loss, grads = self.state.loss_and_grad(key_train_step, self.states.position, self.chain_offset, self.n_total,
-                                               group=self.pg, allreduce=True)  # loss is a SUM over chains (:178)
-        self.state.apply_gradients()
+                                               group=self.pg, allreduce=True, defer=pipelined)  # loss is a SUM over chains (:178)
+        if not pipelined:
+            self.state.apply_gradients()
         return loss
+
+    def flush(self):
+        """Apply an update still in flight (call before reading parameters / optimizer state from outside)."""
+        self.state.apply_pending()
+        return self
 
     # -- adaptive tempering (exe_flow_matching.py:391-417) ------------------------------------------
     def next_beta(self, prev_beta: float, positions) -> float:
@@ -370,6 +406,7 @@ class HotLoop:
 
     def temper(self):
         """beta_gen (:410-417): while beta < 1 pick the next beta and re-initialise (l, g) under it."""
+        self.flush()
         if self.beta < 1.0:
             self.beta = self.next_beta(self.beta, self.states.position)
             self.states = self.init_fn(self.states.position, self.beta)
@@ -419,10 +456,11 @@ def run(dist: Distribution, args, target_gn=None, device=None, log_every: int = 
             loop.temper()
         if log_every and (count % log_every == 0 or count == args.learning_iter):
             acc = loop.last_info.acceptance_rate
-            history.append({"count": count, "loss": float(loss.item()), "learning_rate": loop.lr_fn(loop.state.step - 1),
+            history.append({"count": count, "loss": float(loss.item()), "learning_rate": loop.lr_fn(count - 1),
                             "acceptance avg.": float(acc.mean().item()), "acceptance std.": float(acc.std().item()),
                             "beta": loop.beta, "train_time": time.time() - t0})
             logger.info(str(history[-1]))
+    loop.flush()
     torch.cuda.synchronize()
     train_time = time.time() - t0
     logger.info(f"Final beta= {loop.beta}")

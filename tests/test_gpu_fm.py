@@ -171,3 +171,37 @@ def test_run_entry_point_small(cuda, lib):
     loop = res["loop"]
     assert loop.state.opt_state.cpu().tolist()[0] == 6          # six applied AdamW updates
     assert torch.isfinite(loop.states.position).all()
+
+
+def test_pipelined_update_is_identical(cuda, lib):
+    """HotLoop(pipeline=True) - the multi-rank schedule: AdamW applied after the NEXT MALA step, before a flow-MH
+    step - gives bit-identical chains, parameters and losses (a MALA step never reads the MLP)."""
+    from types import SimpleNamespace
+    from mfm_b200 import distributions as Dm, exe_flow_matching as E, random as mr
+    d, H, F, n, m = 64, 128, 128, 96, 2
+    args = SimpleNamespace(hutchs=False, num_importance_samples=0, mcmc_per_flow_steps=m, step_size=1e-4, ref_dist="stdgauss",
+                           cond_flow=True, ot_cond_flow=False, sigma=1e-4, adam_beta1=0.9, adam_beta2=0.999, adam_epsilon=1e-8,
+                           weight_decay=1e-4, gradient_clip=1.0, learning_iter=100, warmup_steps=0, learning_rate=1e-3)
+    opts = SimpleNamespace(rtol=1e-5, atol=1e-5, mxstep=1000, n_times=2)
+    rng = np.random.default_rng(3)
+    shapes = [(2 * F, H), (H, H), (d, H), (H, H), (H, d), (2 * H, H), (H, H), (H, d)]
+    params = {"params": {f"Dense_{i}": {"kernel": (rng.standard_normal(s) / np.sqrt(s[0]) * (0.1 if i in (4, 7) else 1.0)).astype(np.float32),
+                                        "bias": (rng.standard_normal(s[1]) * 0.01).astype(np.float32)} for i, s in enumerate(shapes)}}
+    omega = torch.from_numpy(rng.standard_normal(F).astype(np.float32)).to(cuda)
+    x0 = torch.from_numpy(rng.uniform(-1, 1, (n, d)).astype(np.float32)).to(cuda)
+    out = []
+    for pipe in (False, True):
+        dist = Dm.PhiFour(d, device=cuda)
+        model = E.VectorFieldNet(omega, dist, [H, H], [H, H], [H, H], "relu", None)
+        P = E.VectorFieldParams(d, H, F, cuda).load_dict(params)
+        loop = E.HotLoop(dist, model, P, args, opts, mr.PRNGKey(11, cuda), x0.clone(), pipeline=pipe)
+        losses = [float(loop.iteration().item()) for _ in range(2 * (m + 1) + 1)]      # two flow-MH iterations inside
+        if pipe:
+            assert loop.state._pending is not None
+            assert loop.state.opt_state.cpu().tolist()[0] == len(losses) - 1               # the last update is still in flight
+        loop.flush()
+        assert loop.state._pending is None and loop.state.opt_state.cpu().tolist()[0] == len(losses)
+        out.append((losses, loop.states.position.clone(), P.flat.clone(), loop.state.mu.clone()))
+    assert out[0][0] == out[1][0]
+    for a, b in zip(out[0][1:], out[1][1:]):
+        assert torch.equal(a, b)
