@@ -215,6 +215,18 @@ int mfm_adamw_step(float* params, const float* grads, float* mu, float* nu, cons
 int mfm_tempering_beta(const float* logliks, int n, const float* prev_beta, float alpha, float* beta_out,
                        mfm_stream_t stream);
 
+/* ---- final sampling: importance weights + multinomial resampling (exe_flow_matching.py:453-459) ------------
+ * log_weights[i] = logdensity[i] - ref_logdensity[i] - vols[i]   (:457);   weights[i] = exp(log_weights[i] - max)   (:458) */
+int mfm_importance_weights(const float* logdensity, const float* ref_logdensity, const float* vols, int n, float* log_weights,
+                           float* weights, mfm_stream_t stream);
+/* jax.random.choice(key, n_pop, (n_draw,), replace=True, p=p) -> idx_out int32[n_draw] (:459; p need not be normalised):
+ * p_cuml = cumsum(p) (sequential float32), r = p_cuml[-1] * (1 - uniform(key, (n_draw,))), idx = searchsorted(p_cuml, r). */
+size_t mfm_random_choice_workspace_bytes(int n_pop);
+int mfm_random_choice(const uint32_t* key, int n_pop, const float* p, int n_draw, int* idx_out, void* ws, size_t ws_bytes,
+                      mfm_stream_t stream);
+/* jnp.take(src[n_pop,d], idx[n_draw], axis=0) -> out[n_draw,d] */
+int mfm_gather_rows(const float* src, const int* idx, int n_pop, int n_draw, int d, float* out, mfm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -63,6 +63,10 @@ SIGNATURES = {
                                         c_f32p, C.c_longlong, c_f32p, C.c_longlong, _S]),
     "mfm_gemm_tf32x3_rows": (C.c_int, [C.c_int, C.c_int, C.c_int, c_f32p, C.c_longlong, c_f32p, C.c_longlong, c_f32p, c_f32p, C.c_longlong,
                                        C.c_void_p, _S]),
+    "mfm_importance_weights": (C.c_int, [c_f32p, c_f32p, c_f32p, C.c_int, c_f32p, c_f32p, _S]),
+    "mfm_random_choice_workspace_bytes": (C.c_size_t, [C.c_int]),
+    "mfm_random_choice": (C.c_int, [c_u32p, C.c_int, c_f32p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, _S]),
+    "mfm_gather_rows": (C.c_int, [c_f32p, C.c_void_p, C.c_int, C.c_int, C.c_int, c_f32p, _S]),
     "mfm_threefry_split": (C.c_int, [c_u32p, C.c_int, c_u32p, _S]),
     "mfm_threefry_split_batched": (C.c_int, [c_u32p, C.c_int, C.c_int, c_u32p, _S]),
     "mfm_threefry_bits": (C.c_int, [c_u32p, C.c_longlong, c_u32p, _S]),

@@ -418,10 +418,39 @@ class HotLoop:
 
 
 # ------------------------------------------------------------------------------------------------
-# run (exe_flow_matching.py:321-450): training loop.  Post-training sampling / KSD / MMD / plots are
-# out of scope; the function returns the training summary instead of the metric table.
+# final sampling + importance resampling (exe_flow_matching.py:389,453-459)
 # ------------------------------------------------------------------------------------------------
-def run(dist: Distribution, args, target_gn=None, device=None, log_every: int = 0):
+def sample_flow(key_gen, dist: Distribution, ref_dist, transform_and_logdet, vector_field_param, n_samples: int):
+    """The reference's post-training sampling, line for line:
+        u = vmap(ref_dist.sample_model)(split(key_gen, n))                       (:389,453)
+        key_hutch, key_choice = split(key_gen)                                   (:454; key_gen is reused as coded)
+        flow_samples, vols = vmap(lambda u: transform_and_logdet(key_hutch, u, params))(u)   (:455; ONE probe key for all rows)
+        log_weights = dist.logprob(flow_samples) - ref_dist.logprob(u) - vols    (:456-457)
+        weights = exp(log_weights - max(log_weights))                            (:458)
+        exact_samples = random.choice(key_choice, flow_samples, (n,), p=weights) (:459)
+    Returns a dict with u, flow_samples, vols, log_weights, weights, exact_samples, indices."""
+    lib = _lib.load()
+    u = ref_dist.sample_model(mrandom.split(key_gen, n_samples))
+    ks = mrandom.split(key_gen)
+    key_hutch, key_choice = ks[0].clone(), ks[1].clone()
+    flow_samples, vols = transform_and_logdet(key_hutch, u, vector_field_param)
+    samples_logdensity = dist.logprob(flow_samples).contiguous()
+    ref_logdensity = ref_dist.logprob(u).contiguous()
+    log_w = torch.empty(n_samples, dtype=torch.float32, device=u.device)
+    w = torch.empty_like(log_w)
+    _lib.check(lib.mfm_importance_weights(_lib.ptr(samples_logdensity), _lib.ptr(ref_logdensity), _lib.ptr(vols.contiguous()), n_samples,
+                                          _lib.ptr(log_w), _lib.ptr(w), _lib.stream()))
+    exact, idx = mrandom.choice(key_choice, flow_samples, (n_samples,), w, return_index=True)
+    return {"u": u, "flow_samples": flow_samples, "vols": vols, "samples_logdensity": samples_logdensity, "log_weights": log_w,
+            "weights": w, "exact_samples": exact, "indices": idx}
+
+
+# ------------------------------------------------------------------------------------------------
+# run (exe_flow_matching.py:321-469): training loop + final sampling / importance resampling.  KSD / MMD /
+# plots are out of scope (SURVEY 8(f)); the function returns the training summary, the flow and the resampled
+# ("exact") samples and their mean log-densities instead of the metric table.
+# ------------------------------------------------------------------------------------------------
+def run(dist: Distribution, args, target_gn=None, device=None, log_every: int = 0, final_sampling: bool = True):
     logging.basicConfig(format="%(asctime)s - %(levelname)s - %(name)s - %(message)s", datefmt="%m/%d/%Y %H:%M:%S",
                         level=logging.INFO)
     dev = dist.device if device is None else torch.device(device)
@@ -433,7 +462,7 @@ def run(dist: Distribution, args, target_gn=None, device=None, log_every: int = 
     iter_per_temp = max(args.anneal_iter // args.num_anneal_temp, 1)
     # key_target, key_sample, key_init, key_dist, key_fourier, key_gen = split(PRNGKey(seed), 6)   (:333)
     keys = mrandom.split(mrandom.PRNGKey(args.seed, dev), 6)
-    key_sample, key_init, key_dist, key_fourier = keys[1], keys[2], keys[3], keys[4]
+    key_sample, key_init, key_dist, key_fourier, key_gen = keys[1], keys[2], keys[3], keys[4], keys[5]
     dist.initialize_model(key_dist, n_total)                                                       # (:334)
     positions = dist.init_params[lo:hi].contiguous()
     fourier_random = args.fourier_std * mrandom.normal(key_fourier, (args.fourier_dim,))           # (:350)
@@ -464,4 +493,12 @@ def run(dist: Distribution, args, target_gn=None, device=None, log_every: int = 
     torch.cuda.synchronize()
     train_time = time.time() - t0
     logger.info(f"Final beta= {loop.beta}")
-    return {"train_time": train_time, "final_beta": loop.beta, "history": history, "loop": loop}
+    out = {"train_time": train_time, "final_beta": loop.beta, "history": history, "loop": loop}
+    if final_sampling:
+        # (:453-459, :463-469) every rank draws the same eval_iter * num_chain samples (the draw is not sharded)
+        fs = sample_flow(key_gen.clone(), dist, loop.state.ref_dist, loop.transform_and_logdet, P, args.eval_iter * n_total)
+        out.update(flow_samples=fs["flow_samples"], exact_samples=fs["exact_samples"], weights=fs["weights"],
+                   logpdf=float(fs["samples_logdensity"].mean().item()), logpdf_exact=float(dist.logprob(fs["exact_samples"]).mean().item()))
+        logger.info(f"Logpdf of flow samples= {out['logpdf']}")
+        logger.info(f"Logpdf of exact samples= {out['logpdf_exact']}")
+    return out

@@ -83,3 +83,23 @@ def normal(key: torch.Tensor, shape=()) -> torch.Tensor:
     out = torch.empty(n, dtype=torch.float32, device=key.device)
     _lib.check(lib.mfm_threefry_normal(_lib.ptr(key), n, _lib.ptr(out), _lib.stream()))
     return out.reshape(tuple(shape))
+
+
+def choice(key: torch.Tensor, a: torch.Tensor, shape, p: torch.Tensor, return_index: bool = False):
+    """jax.random.choice(key, a, shape, replace=True, p=p) along axis 0 (exe_flow_matching.py:459); p need not be
+    normalised.  a: [n_pop, ...] float32 (or an int n_pop: returns indices)."""
+    lib = _lib.load()
+    n_draw = int(math.prod(shape)) if len(shape) else 1
+    n_pop = int(a) if isinstance(a, int) else a.shape[0]
+    p = p.contiguous().float()
+    assert p.shape == (n_pop,), "p must have shape (a.shape[0],)"
+    idx = torch.empty(n_draw, dtype=torch.int32, device=p.device)
+    ws = _lib.workspace(lib.mfm_random_choice_workspace_bytes(n_pop), p.device, "choice")
+    _lib.check(lib.mfm_random_choice(_lib.ptr(key), n_pop, _lib.ptr(p), n_draw, _lib.ptr(idx), _lib.ptr(ws), ws.numel(), _lib.stream()))
+    if isinstance(a, int):
+        return idx.reshape(tuple(shape))
+    src = a.contiguous().float().reshape(n_pop, -1)
+    out = torch.empty((n_draw, src.shape[1]), dtype=torch.float32, device=src.device)
+    _lib.check(lib.mfm_gather_rows(_lib.ptr(src), _lib.ptr(idx), n_pop, n_draw, src.shape[1], _lib.ptr(out), _lib.stream()))
+    out = out.reshape(tuple(shape) + tuple(a.shape[1:]))
+    return (out, idx.reshape(tuple(shape))) if return_index else out
