@@ -12,6 +12,7 @@ Everything numeric happens in CUDA kernels behind the C-ABI (include/mfm_b200.h)
 from __future__ import annotations
 
 import logging
+import os
 import time
 from types import SimpleNamespace
 from typing import Callable, NamedTuple, Optional
@@ -344,7 +345,7 @@ class HotLoop:
     only exchange is the SUM all-reduce of the flat FM gradient (and the scalar loss)."""
 
     def __init__(self, dist, model, P, args, ode_opts, key_sample, positions, beta=1.0, chain_offset=0, n_total=None,
-                 process_group=None, pipeline=None):
+                 process_group=None, pipeline=None, graph=None):
         import torch.distributed as tdist
         self.dist, self.model, self.P, self.args = dist, model, P, args
         self.n = positions.shape[0]
@@ -353,6 +354,12 @@ class HotLoop:
         self.pg = process_group
         self.world = tdist.get_world_size(process_group) if (tdist.is_available() and tdist.is_initialized()) else 1
         self.pipeline = (self.world > 1) if pipeline is None else bool(pipeline)
+        # MALA + FM-update iterations replayed from a CUDA graph: the latency-bound reference shapes (128 chains x d=2 is
+        # 1 KB of state, ~60 launches per iteration) are otherwise bound by host launch overhead.  Off for big ensembles
+        # (nothing to gain) and for multi-rank runs (NCCL + pipelined update).
+        small = self.n * dist.dim <= (1 << 18)
+        self.graph = (small and self.world == 1 and not self.pipeline and os.environ.get("MFM_GRAPH", "1") != "0") if graph is None else bool(graph)
+        self._graph, self._graph_loss, self._eager_done = None, None, False
         self.lr_fn = create_learning_rate_fn(args.learning_iter, args.warmup_steps, args.learning_rate)
         self.state = create_train_state(model, P, self.lr_fn, args)
         self.gen, self.init_fn, self.transform_and_logdet = create_train_data_gn(
@@ -365,6 +372,33 @@ class HotLoop:
 
     def reset_positions(self, positions):
         self.states = self.init_fn(positions, self.beta)
+        self._graph = None                    # the captured iteration points at the old state arrays
+
+    def _mala_iteration_body(self):
+        keys = mrandom.split(self.key_sample, 3)
+        self.states, self.last_info = self.gen(keys[1], self.states, 1 if not self.is_flow_iteration(1) else 2, self.P, self.beta,
+                                               inplace=True)
+        loss, _ = self.state.loss_and_grad(keys[2], self.states.position, self.chain_offset, self.n_total)
+        self.state.apply_gradients()
+        self.key_sample.copy_(keys[0])
+        return loss
+
+    def _graph_iteration(self):
+        """MALA iteration through a CUDA graph: the first one runs eagerly (sizes every workspace), the second is captured,
+        every later one only replays.  Same kernels, same order, same buffers => bit-identical to the eager loop."""
+        if not self._eager_done:
+            self._eager_done = True
+            return self._mala_iteration_body()
+        if self._graph is None or self._graph_beta != self.beta:
+            g = torch.cuda.CUDAGraph()
+            step = self.state.step
+            with torch.cuda.graph(g):
+                self._graph_loss = self._mala_iteration_body()
+            self.state.step = step            # capture records launches, it does not run them
+            self._graph, self._graph_beta = g, self.beta
+        self._graph.replay()
+        self.state.step += 1
+        return self._graph_loss
 
     def iteration(self):
         """One outer iteration (exe_flow_matching.py:433-439): data generator, then train_step.
@@ -374,8 +408,10 @@ class HotLoop:
         is applied right after it, before anything reads the parameters; a flow-MH iteration applies it first.
         Same arithmetic in the same order as the unpipelined loop."""
         self.count += 1
+        if self.graph and not self.is_flow_iteration(self.count):
+            return self._graph_iteration()
         keys = mrandom.split(self.key_sample, 3)
-        self.key_sample, key_train_gn, key_train_step = keys[0], keys[1], keys[2]
+        self.key_sample, key_train_gn, key_train_step = keys[0].clone(), keys[1], keys[2]
         if self.is_flow_iteration(self.count):
             self.state.apply_pending()          # the flow step integrates the CURRENT vector field
         self.states, self.last_info = self.gen(key_train_gn, self.states, self.count, self.P, self.beta, inplace=True)
@@ -410,6 +446,7 @@ class HotLoop:
         if self.beta < 1.0:
             self.beta = self.next_beta(self.beta, self.states.position)
             self.states = self.init_fn(self.states.position, self.beta)
+            self._graph = None                # new state arrays, new temperature
         return self.beta
 
     def is_flow_iteration(self, count):

@@ -205,3 +205,42 @@ def test_pipelined_update_is_identical(cuda, lib):
     assert out[0][0] == out[1][0]
     for a, b in zip(out[0][1:], out[1][1:]):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("name", ["phi-four", "4-mode"])
+def test_graph_replayed_iterations_are_identical(cuda, lib, name):
+    """HotLoop(graph=True) replays the MALA + FM-update iteration from a CUDA graph (latency-bound reference shapes):
+    same kernels on the same buffers => bit-identical chains, parameters and losses, flow-MH iterations (eager) included."""
+    from types import SimpleNamespace
+    from mfm_b200 import distributions as Dm, exe_flow_matching as E, random as mr
+    from oracle import targets as OT
+    d, n, m, step = (64, 96, 3, 1e-4) if name == "phi-four" else (2, 128, 3, 0.2)
+    H, F = 128, 128
+    args = SimpleNamespace(hutchs=False, num_importance_samples=0, mcmc_per_flow_steps=m, step_size=step, ref_dist="stdgauss",
+                           cond_flow=True, ot_cond_flow=False, sigma=1e-4, adam_beta1=0.9, adam_beta2=0.999, adam_epsilon=1e-8,
+                           weight_decay=1e-4, gradient_clip=1.0, learning_iter=100, warmup_steps=0, learning_rate=1e-3)
+    opts = SimpleNamespace(rtol=1e-5, atol=1e-5, mxstep=1000, n_times=2)
+    rng = np.random.default_rng(5)
+    shapes = [(2 * F, H), (H, H), (d, H), (H, H), (H, d), (2 * H, H), (H, H), (H, d)]
+    params = {"params": {f"Dense_{i}": {"kernel": (rng.standard_normal(s) / np.sqrt(s[0]) * (0.002 if i in (4, 7) else 1.0)).astype(np.float32),
+                                        "bias": (rng.standard_normal(s[1]) * 0.01).astype(np.float32)} for i, s in enumerate(shapes)}}
+    omega = torch.from_numpy(rng.standard_normal(F).astype(np.float32)).to(cuda)
+    x0 = torch.from_numpy(rng.uniform(-1, 1, (n, d)).astype(np.float32)).to(cuda)
+    out = []
+    for graph in (False, True):
+        if name == "phi-four":
+            dist = Dm.PhiFour(d, device=cuda)
+        else:
+            t4 = OT.four_mode()
+            dist = Dm.GaussianMixture(t4.modes, t4.covs, t4.weights, device=cuda)
+        model = E.VectorFieldNet(omega, dist, [H, H], [H, H], [H, H], "relu", None)
+        P = E.VectorFieldParams(d, H, F, cuda).load_dict(params)
+        loop = E.HotLoop(dist, model, P, args, opts, mr.PRNGKey(21, cuda), x0.clone(), graph=graph)
+        losses = [float(loop.iteration().item()) for _ in range(3 * (m + 1) + 2)]
+        assert (loop._graph is not None) == graph
+        assert loop.state.step == len(losses) and loop.state.opt_state.cpu().tolist()[0] == len(losses)
+        out.append((losses, loop.states.position.clone(), loop.states.logdensity.clone(), P.flat.clone(), loop.key_sample.clone(),
+                    loop.last_info.acceptance_rate.clone()))
+    assert out[0][0] == out[1][0]
+    for a, b in zip(out[0][1:], out[1][1:]):
+        assert torch.equal(a, b)

@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from oracle import resample as OR, samplers as OS, targets as OT, threefry as tf, vector_field as VF
-from tests.helpers import key_dev, to_dev
+from tests.helpers import key_dev, to_dev, ulp_diff_f32
 
 pytestmark = pytest.mark.gpu
 
@@ -70,7 +70,7 @@ def test_sample_flow_matches_oracle(cuda, lib, hutch):
     got = E.sample_flow(key_dev(key, cuda), dd, ref_d, transform_and_logdet, P, n)
     flow = OS.Flow(params, omega, ot, hutch, 1e-5, 1e-5, 1000, None, tuple(np.linspace(0, 1, 5)), rng_dtype=np.float32)
     ref = OR.sample_flow(key, ot, OT.IndepGaussian(2), flow, n)
-    assert np.array_equal(got["u"].cpu().numpy(), ref["u"].astype(np.float32))
+    assert ulp_diff_f32(got["u"].cpu().numpy(), ref["u"].astype(np.float32)).max() <= 4      # normals: erf_inv to 4 ulp
     fs = got["flow_samples"].cpu().numpy()
     assert np.abs(fs - ref["flow_samples"]).max() <= 5e-4 * np.abs(ref["flow_samples"]).max()
     lw, lw_ref = got["log_weights"].cpu().numpy(), ref["log_weights"]
