@@ -169,6 +169,17 @@ __global__ void gate_kernel(long long total, int H, const float* __restrict__ a,
     out[i] = gate[r * ldg + c] > 0.0f ? a[i] : 0.0f;
 }
 
+// same, four columns per thread (H % 4 == 0, 16-byte aligned rows): HBM-bound, 12 B moved per element
+__global__ void gate4_kernel(long long total4, int H4, const float4* __restrict__ a, const float4* __restrict__ gate,
+                             long long ldg4, float4* __restrict__ out, const int* __restrict__ n_rows_dev) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (n_rows_dev) total4 = min(total4, (long long)(*n_rows_dev) * H4);
+    if (i >= total4) return;
+    const float4 g = ldg4 == H4 ? __ldg(gate + i) : __ldg(gate + (i / H4) * ldg4 + (i % H4));
+    const float4 v = __ldg(a + i);
+    out[i] = make_float4(g.x > 0.0f ? v.x : 0.0f, g.y > 0.0f ? v.y : 0.0f, g.z > 0.0f ? v.z : 0.0f, g.w > 0.0f ? v.w : 0.0f);
+}
+
 // exact path: tan[(i,j),:] = W2[j,:] * (h2[i,:] > 0)
 __global__ void basis_tangent_kernel(int n, int d, int H, const float* __restrict__ W2, const float* __restrict__ h2,
                                      float* __restrict__ tan, const int* __restrict__ n_rows_dev) {
@@ -273,7 +284,11 @@ int field_eval(const mfm_field_t& F, const mfm_target_t& T, int n, const float* 
     }
     if (!want_div) return MFM_OK;
     if (z) {
-        gate_kernel<<<ceil_div((long long)n * H, 256), 256, 0, st>>>((long long)n * H, H, B.zw2, B.h2, H, B.ta, nr);
+        if (H % 4 == 0 && ((reinterpret_cast<uintptr_t>(B.zw2) | reinterpret_cast<uintptr_t>(B.h2) | reinterpret_cast<uintptr_t>(B.ta)) & 15) == 0)
+            gate4_kernel<<<ceil_div((long long)n * (H / 4), 256), 256, 0, st>>>((long long)n * (H / 4), H / 4, reinterpret_cast<const float4*>(B.zw2),
+                                                                                reinterpret_cast<const float4*>(B.h2), H / 4, reinterpret_cast<float4*>(B.ta), nr);
+        else
+            gate_kernel<<<ceil_div((long long)n * H, 256), 256, 0, st>>>((long long)n * H, H, B.zw2, B.h2, H, B.ta, nr);
         MFM_LAUNCH_CHECK();
         if ((rc = dense(n, H, H, B.ta, H, WT_(3), H, nullptr, 0, B.tb, H, B.cat, 2 * H, 1, st, nr))) return rc;
         if ((rc = dense(n, H, H, B.tb, H, WT_(5), 2 * H, nullptr, 0, B.ta, H, B.h5, H, 1, st, nr))) return rc;   // first H rows of W5
@@ -394,6 +409,33 @@ __global__ void ode_stage_kernel(int n, int d, int s, OdeState S, int n_seg, flo
 #pragma unroll
     for (int j = 0; j < 6; ++j) if (j < s) acc += c_beta[s - 1][j] * S.kx[j][o];
     S.xi[i] = S.yx[o] + h * acc;
+    if (col == 0) {
+        const float ti = S.t[c] + h * c_alpha[s - 1];
+        S.tf[r] = sgn > 0 ? ti : 1.0f - ti;
+    }
+}
+
+// same, four columns per thread (d % 4 == 0): (s + 2) arrays of 4 B per element, HBM-bound
+__global__ void ode_stage4_kernel(int n, int d4, int s, OdeState S, int n_seg, float sgn, const int* __restrict__ idx,
+                                  const int* __restrict__ n_active) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (idx) n = min(n, *n_active);
+    if (i >= (long long)n * d4) return;
+    const int r = (int)(i / d4), col = (int)(i % d4);
+    const int c = idx ? idx[r] : r;
+    if (S.seg[c] >= n_seg) return;            // finished chain: leave its stage input untouched
+    const long long o = (long long)c * d4 + col;
+    const float h = S.dt[c];
+    float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll
+    for (int j = 0; j < 6; ++j)
+        if (j < s) {
+            const float b = c_beta[s - 1][j];
+            const float4 k = __ldg(reinterpret_cast<const float4*>(S.kx[j]) + o);
+            acc.x += b * k.x; acc.y += b * k.y; acc.z += b * k.z; acc.w += b * k.w;     // same order as the scalar kernel
+        }
+    const float4 y = __ldg(reinterpret_cast<const float4*>(S.yx) + o);
+    reinterpret_cast<float4*>(S.xi)[i] = make_float4(y.x + h * acc.x, y.y + h * acc.y, y.z + h * acc.z, y.w + h * acc.w);
     if (col == 0) {
         const float ti = S.t[c] + h * c_alpha[s - 1];
         S.tf[r] = sgn > 0 ? ti : 1.0f - ti;
@@ -614,6 +656,8 @@ static int ode_solve(const mfm_field_t& F, const mfm_target_t& T, const mfm_ode_
         idx = S.idx; nact = S.n_active; zc = z_compact;
     }
     const long long max_iter = (long long)TS.n_seg * (long long)O.mxstep + 2;
+    bool stage_vec = d % 4 == 0 && ((reinterpret_cast<uintptr_t>(S.yx) | reinterpret_cast<uintptr_t>(S.xi)) & 15) == 0;
+    for (int j = 0; j < 6; ++j) stage_vec = stage_vec && (reinterpret_cast<uintptr_t>(S.kx[j]) & 15) == 0;
     for (long long it = 0; it < max_iter; ++it) {
         if (compact) {
             ode_gather_probe_kernel<<<n, 128, 0, st>>>(n, d, H, idx, nact, z, S.zw2_full,
@@ -621,7 +665,8 @@ static int ode_solve(const mfm_field_t& F, const mfm_target_t& T, const mfm_ode_
             MFM_LAUNCH_CHECK();
         }
         for (int s = 1; s <= 6; ++s) {
-            ode_stage_kernel<<<gE, 256, 0, st>>>(n, d, s, S, TS.n_seg, sgn, idx, nact);
+            if (stage_vec) ode_stage4_kernel<<<ceil_div((long long)n * (d / 4), 256), 256, 0, st>>>(n, d / 4, s, S, TS.n_seg, sgn, idx, nact);
+            else ode_stage_kernel<<<gE, 256, 0, st>>>(n, d, s, S, TS.n_seg, sgn, idx, nact);
             MFM_LAUNCH_CHECK();
             if ((rc = field_eval(F, T, n, S.xi, S.tf, zc, sgn, S.kx[s], S.kl[s], B, st, nact, idx))) return rc; ++n_eval;
         }
