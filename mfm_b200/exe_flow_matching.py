@@ -411,7 +411,8 @@ class HotLoop:
         if self.graph and not self.is_flow_iteration(self.count):
             return self._graph_iteration()
         keys = mrandom.split(self.key_sample, 3)
-        self.key_sample, key_train_gn, key_train_step = keys[0].clone(), keys[1], keys[2]
+        self.key_sample.copy_(keys[0])          # in place: a captured graph reads this buffer
+        key_train_gn, key_train_step = keys[1], keys[2]
         if self.is_flow_iteration(self.count):
             self.state.apply_pending()          # the flow step integrates the CURRENT vector field
         self.states, self.last_info = self.gen(key_train_gn, self.states, self.count, self.P, self.beta, inplace=True)
