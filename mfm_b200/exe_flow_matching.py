@@ -395,9 +395,10 @@ class HotLoop:
             with torch.cuda.graph(g):
                 self._graph_loss = self._mala_iteration_body()
             self.state.step = step            # capture records launches, it does not run them
-            self._graph, self._graph_beta = g, self.beta
+            self._graph, self._graph_beta, self._graph_info = g, self.beta, self.last_info
         self._graph.replay()
         self.state.step += 1
+        self.last_info = self._graph_info     # the graph's output buffers (a flow-MH iteration in between replaced the reference)
         return self._graph_loss
 
     def iteration(self):
