@@ -409,7 +409,7 @@ class HotLoop:
         is applied right after it, before anything reads the parameters; a flow-MH iteration applies it first.
         Same arithmetic in the same order as the unpipelined loop."""
         self.count += 1
-        if self.graph and not self.is_flow_iteration(self.count):
+        if self.graph and self.beta >= 1.0 and not self.is_flow_iteration(self.count):   # while tempering the state arrays change every iteration
             return self._graph_iteration()
         keys = mrandom.split(self.key_sample, 3)
         self.key_sample.copy_(keys[0])          # in place: a captured graph reads this buffer
