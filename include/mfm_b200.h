@@ -227,6 +227,17 @@ int mfm_random_choice(const uint32_t* key, int n_pop, const float* p, int n_draw
 /* jnp.take(src[n_pop,d], idx[n_draw], axis=0) -> out[n_draw,d] */
 int mfm_gather_rows(const float* src, const int* idx, int n_pop, int n_draw, int d, float* out, mfm_stream_t stream);
 
+/* ---- evaluation metrics (mcmc_utils.py:28-85, :88-111; exe_flow_matching.py:463-488) ----------------------
+ * stein_disc(X, logprob_fn, beta): kernelised Stein discrepancy with the IMQ kernel (1 + |x-x'|^2)^beta, beta = -1/2 in
+ * every call.  X [T,d] samples, grad_logp [T,d] = grad log pi at the samples (mfm_logdensity_and_grad).
+ * out_uv = (U-statistic, V-statistic).  Pair values in float32, sums in float64 in a fixed order. */
+size_t mfm_pairwise_workspace_bytes(int t);
+int mfm_stein_disc(const float* X, const float* grad_logp, int T, int d, float beta, float* out_uv, void* ws, size_t ws_bytes,
+                   mfm_stream_t stream);
+/* max_mean_disc(X, Y): squared MMD with the Gaussian kernel exp(-|x-y|^2 / 2), X and Y [m,d]; out[0] =
+ * (sum k(X,X) - m)/(m^2 - m) - 2 sum k(X,Y)/m^2 + (sum k(Y,Y) - m)/(m^2 - m). */
+int mfm_max_mean_disc(const float* X, const float* Y, int m, int d, float* out, void* ws, size_t ws_bytes, mfm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

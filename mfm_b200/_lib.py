@@ -67,6 +67,9 @@ SIGNATURES = {
     "mfm_random_choice_workspace_bytes": (C.c_size_t, [C.c_int]),
     "mfm_random_choice": (C.c_int, [c_u32p, C.c_int, c_f32p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, _S]),
     "mfm_gather_rows": (C.c_int, [c_f32p, C.c_void_p, C.c_int, C.c_int, C.c_int, c_f32p, _S]),
+    "mfm_pairwise_workspace_bytes": (C.c_size_t, [C.c_int]),
+    "mfm_stein_disc": (C.c_int, [c_f32p, c_f32p, C.c_int, C.c_int, C.c_float, c_f32p, C.c_void_p, C.c_size_t, _S]),
+    "mfm_max_mean_disc": (C.c_int, [c_f32p, c_f32p, C.c_int, C.c_int, c_f32p, C.c_void_p, C.c_size_t, _S]),
     "mfm_threefry_split": (C.c_int, [c_u32p, C.c_int, c_u32p, _S]),
     "mfm_threefry_split_batched": (C.c_int, [c_u32p, C.c_int, C.c_int, c_u32p, _S]),
     "mfm_threefry_bits": (C.c_int, [c_u32p, C.c_longlong, c_u32p, _S]),

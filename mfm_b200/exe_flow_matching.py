@@ -485,9 +485,9 @@ def sample_flow(key_gen, dist: Distribution, ref_dist, transform_and_logdet, vec
 
 
 # ------------------------------------------------------------------------------------------------
-# run (exe_flow_matching.py:321-469): training loop + final sampling / importance resampling.  KSD / MMD /
-# plots are out of scope; the function returns the training summary, the flow and the resampled
-# ("exact") samples and their mean log-densities instead of the metric table.
+# run (exe_flow_matching.py:321-488): training loop, final sampling / importance resampling, metric table
+# (mean log-density, KSD U/V statistics, MMD against real samples when a target generator is given).  Plots and the
+# phi-four magnetisation histogram are out of scope; the function returns what the reference logs.
 # ------------------------------------------------------------------------------------------------
 def run(dist: Distribution, args, target_gn=None, device=None, log_every: int = 0, final_sampling: bool = True):
     logging.basicConfig(format="%(asctime)s - %(levelname)s - %(name)s - %(message)s", datefmt="%m/%d/%Y %H:%M:%S",
@@ -534,10 +534,30 @@ def run(dist: Distribution, args, target_gn=None, device=None, log_every: int = 
     logger.info(f"Final beta= {loop.beta}")
     out = {"train_time": train_time, "final_beta": loop.beta, "history": history, "loop": loop}
     if final_sampling:
-        # (:453-459, :463-469) every rank draws the same eval_iter * num_chain samples (the draw is not sharded)
+        # (:453-459) every rank draws the same eval_iter * num_chain samples (the draw is not sharded)
+        from .mcmc_utils import max_mean_disc, stein_disc
         fs = sample_flow(key_gen.clone(), dist, loop.state.ref_dist, loop.transform_and_logdet, P, args.eval_iter * n_total)
-        out.update(flow_samples=fs["flow_samples"], exact_samples=fs["exact_samples"], weights=fs["weights"],
-                   logpdf=float(fs["samples_logdensity"].mean().item()), logpdf_exact=float(dist.logprob(fs["exact_samples"]).mean().item()))
-        logger.info(f"Logpdf of flow samples= {out['logpdf']}")
-        logger.info(f"Logpdf of exact samples= {out['logpdf_exact']}")
+        flow_samples, exact_samples = fs["flow_samples"], fs["exact_samples"]
+        out.update(flow_samples=flow_samples, exact_samples=exact_samples, weights=fs["weights"])
+        # metric table (:463-488): mean log-density and kernelised Stein discrepancy of the flow and the resampled samples
+        logpdf = float(fs["samples_logdensity"].mean().item())
+        logger.info(f"Logpdf of flow samples= {logpdf}")
+        stein = [float(v.item()) for v in stein_disc(flow_samples, dist.logprob)]
+        logger.info(f"Stein U, V disc of flow samples= {stein[0]}, {stein[1]}")
+        logpdf_ = float(dist.logprob(exact_samples).mean().item())
+        logger.info(f"Logpdf of exact samples= {logpdf_}")
+        stein_ = [float(v.item()) for v in stein_disc(exact_samples, dist.logprob)]
+        logger.info(f"Stein U, V disc of exact samples= {stein_[0]}, {stein_[1]}")
+        data = [args.mcmc_per_flow_steps, args.learning_iter, train_time, logpdf, logpdf_, stein[0], stein_[0], stein[1], stein_[1]]
+        columns = ["mcmc/flow", "learn iter", "train time", "logpdf", "logpdf*", "KSD U-stat", "KSD U-stat*", "KSD V-stat", "KSD V-stat*"]
+        if target_gn is not None:
+            # real samples: vmap(target_gn)(split(key_target, n)) (:336); target_gn maps uint32[n,2] keys -> [n,d] here
+            real_samples = target_gn(mrandom.split(keys[0].clone(), args.eval_iter * n_total))
+            mmd = float(max_mean_disc(real_samples, flow_samples).item())
+            mmd_ = float(max_mean_disc(real_samples, exact_samples).item())
+            logger.info(f"Max mean disc of flow samples= {mmd}")
+            logger.info(f"Max mean disc of exact samples= {mmd_}")
+            data += [mmd, mmd_]
+            columns += ["MMD", "MMD*"]
+        out.update(logpdf=logpdf, logpdf_exact=logpdf_, table=dict(zip(columns, data)))
     return out
