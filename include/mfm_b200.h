@@ -101,6 +101,12 @@ void mfm_set_gemm_cross_bf16(int enable);
  * and the pair that owns a tile's last k-range adds them, in a fixed order, before the epilogue functor runs.
  * 1 (default) = on, 0 = whole tiles only.  Environment variable MFM_STREAMK=0|1. */
 void mfm_set_gemm_streamk(int enable);
+/* Pre-split B operand of the persistent kernel (test / benchmark hooks; the ABI entry points below do this themselves for
+ * the MLP weights, inside their workspace): mfm_gemm_presplit writes the bf16 cross mirror of n_floats (multiple of 8, both
+ * pointers 32-byte aligned) K-major fp32 values; mfm_gemm_register_mirror announces it for the calling thread's next GEMMs
+ * (base == NULL clears the registry). */
+int mfm_gemm_presplit(const float* src, float* mirror, long long n_floats, mfm_stream_t stream);
+void mfm_gemm_register_mirror(const float* base, long long n_floats, const float* mirror);
 /* Host-only test hook: the work list the persistent kernel derives for an M x N x K problem on n_pairs CTA pairs, as
  * rows of 7 ints (pair, tile, first k-block, end k-block, kind 0 whole / 1 contribution / 2 finishing part, first
  * contributing pair, number of contributing pairs).  Returns the number of rows; writes at most `cap` of them. */

@@ -134,13 +134,56 @@ static void layer_dims(const mfm_field_t& F, int i, int& in, int& out) {
     in = ins[i]; out = outs[i];
 }
 
+// 8 consecutive floats -> 16 bf16 in the same 32 bytes: [bf16(b0..b7) | bf16(rest0..rest7)], rest = b - trunc_tf32(b)
+// (what the tensor core drops from the raw fp32 tile): the B operand's cross tile of the persistent GEMM, ready for TMA
+__global__ void presplit_kernel(const float4* __restrict__ src, uint4* __restrict__ dst, long long n8) {
+    const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (g >= n8) return;
+    const float4 a = __ldg(src + 2 * g), c = __ldg(src + 2 * g + 1);
+    auto rest = [](float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); };
+    auto pack = [](float lo16, float hi16) { uint32_t r; asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi16), "f"(lo16)); return r; };
+    dst[2 * g] = make_uint4(pack(a.x, a.y), pack(a.z, a.w), pack(c.x, c.y), pack(c.z, c.w));
+    dst[2 * g + 1] = make_uint4(pack(rest(a.x), rest(a.y)), pack(rest(a.z), rest(a.w)), pack(rest(c.x), rest(c.y)), pack(rest(c.z), rest(c.w)));
+}
+int presplit_weights(const float* src, float* dst, long long n_floats, cudaStream_t st) {
+    const long long n8 = n_floats / 8;
+    presplit_kernel<<<ceil_div(n8, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(src), reinterpret_cast<uint4*>(dst), n8);
+    MFM_LAUNCH_CHECK();
+    return MFM_OK;
+}
+
+void field_register_mirrors(const mfm_field_t& F, const FieldBufs& B);
 int field_prepare_weights(const mfm_field_t& F, FieldBufs& B, cudaStream_t st) {
+    tc2p::clear_cross();
+    bool mirrors = B.wx != nullptr && B.wxo != nullptr && ((reinterpret_cast<uintptr_t>(F.params) | reinterpret_cast<uintptr_t>(B.wt)) & 31) == 0;
     for (int i = 0; i < 8; ++i) {
         int in, out; layer_dims(F, i, in, out);
         transpose_kernel<<<dim3(ceil_div(out, 32), ceil_div(in, 32)), dim3(32, 8), 0, st>>>(in, out, F.params + F.w_off[i], B.wt + F.w_off[i]);
         MFM_LAUNCH_CHECK();
+        mirrors = mirrors && in % 8 == 0 && out % 8 == 0 && F.w_off[i] % 8 == 0;
+    }
+    if (mirrors) {
+        // the dense kernels occupy [w_off[0], w_off[7] + in7*out7) of the flat buffer; biases in between (if any) are converted too, harmlessly
+        int in7, out7; layer_dims(F, 7, in7, out7);
+        const long long lo = F.w_off[0], hi = (long long)F.w_off[7] + (long long)in7 * out7;
+        int rc;
+        if ((rc = presplit_weights(B.wt + lo, B.wx + lo, hi - lo, st))) return rc;
+        if ((rc = presplit_weights(F.params + lo, B.wxo + lo, hi - lo, st))) return rc;
+        field_register_mirrors(F, B);
     }
     return MFM_OK;
+}
+
+// (re-)announce the mirrors field_prepare_weights built in this workspace (a later ABI call on the same workspace: FM part 2)
+void field_register_mirrors(const mfm_field_t& F, const FieldBufs& B) {
+    tc2p::clear_cross();
+    bool mirrors = B.wx != nullptr && B.wxo != nullptr && ((reinterpret_cast<uintptr_t>(F.params) | reinterpret_cast<uintptr_t>(B.wt)) & 31) == 0;
+    for (int i = 0; i < 8; ++i) { int in, out; layer_dims(F, i, in, out); mirrors = mirrors && in % 8 == 0 && out % 8 == 0 && F.w_off[i] % 8 == 0; }
+    if (!mirrors) return;
+    int in7, out7; layer_dims(F, 7, in7, out7);
+    const long long lo = F.w_off[0], hi = (long long)F.w_off[7] + (long long)in7 * out7;
+    tc2p::register_cross(B.wt + lo, (size_t)(hi - lo), B.wx + lo);
+    tc2p::register_cross(F.params + lo, (size_t)(hi - lo), B.wxo + lo);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -227,7 +270,7 @@ size_t field_bufs_bytes(const mfm_field_t& F, const mfm_target_t& T, int n, bool
     size_t b = ws_slice(N * 2 * F.fourier_dim, 4) + ws_slice(N * H, 4) * 6 + ws_slice(N * 2 * H, 4) + ws_slice(N * d, 4) * 3;
     if (hutch) b += ws_slice(N * H, 4) + ws_slice(N * d, 4) + ws_slice(N * gemm_n_tiles((int)d), 4);
     else b += 2 * ws_slice(N * d * H, 4);
-    return b + ws_slice((size_t)F.n_params, 4);
+    return b + 3 * ws_slice((size_t)F.n_params, 4);
 }
 
 bool field_bufs_take(FieldBufs& B, Workspace& w, const mfm_field_t& F, int n, bool hutch) {
@@ -241,6 +284,7 @@ bool field_bufs_take(FieldBufs& B, Workspace& w, const mfm_field_t& F, int n, bo
     if (hutch) { B.zw2 = w.take<float>(N * H); B.zkinv = w.take<float>(N * d); B.divpart = w.take<float>(N * gemm_n_tiles((int)d)); }
     else { B.tan_a = w.take<float>(N * d * H); B.tan_b = w.take<float>(N * d * H); }
     B.wt = w.take<float>((size_t)F.n_params);
+    B.wx = w.take<float>((size_t)F.n_params); B.wxo = w.take<float>((size_t)F.n_params);
     return w.ok;
 }
 
@@ -776,6 +820,7 @@ size_t mfm_ode_workspace_bytes(const mfm_field_t* f, const mfm_target_t* t, cons
 int mfm_ode_flow(const mfm_field_t* f, const mfm_target_t* t, const mfm_ode_opts_t* o, int direction, int n,
                  const uint32_t* hutch_keys, const float* y0, float* y1, float* ldj, int* stats, void* ws,
                  size_t ws_bytes, mfm_stream_t stream) {
+    mfm::CrossScope cross_scope;
     int rc = check_field(f, t, o);
     if (rc) return rc;
     if (n <= 0) return MFM_OK;
@@ -797,6 +842,7 @@ int mfm_ode_flow(const mfm_field_t* f, const mfm_target_t* t, const mfm_ode_opts
 int mfm_field_eval(const mfm_field_t* f, const mfm_target_t* t, const mfm_ode_opts_t* o, int n, const float* x,
                    const float* time, const float* z, float* v, float* div, void* ws, size_t ws_bytes,
                    mfm_stream_t stream) {
+    mfm::CrossScope cross_scope;
     int rc = check_field(f, t, o);
     if (rc) return rc;
     if (n <= 0) return MFM_OK;
@@ -826,6 +872,7 @@ int mfm_flow_mh_step(const mfm_field_t* f, const mfm_target_t* t, const mfm_ode_
                      float* position, float* logdensity, float* logdensity_grad, float* acceptance_rate,
                      uint8_t* is_accepted, float* proposed_position, float* proposed_weight, int* stats, void* ws,
                      size_t ws_bytes, mfm_stream_t stream) {
+    mfm::CrossScope cross_scope;
     int rc = check_field(f, t, o);
     if (rc) return rc;
     if (!rng_key || !position || !logdensity || !logdensity_grad) { mfm_set_last_error_msg("null argument"); return MFM_ERR_ARG; }

@@ -212,6 +212,7 @@ static int fm_forward_backward(const mfm_field_t& F, const mfm_target_t& T, int 
     const int d = F.dim, H = F.hidden, Fd = F.fourier_dim;
     FieldBufs& B = M.B;
     int rc;
+    if (part == 2) field_register_mirrors(F, B);      // built by part 1 in this workspace
     if (part != 2) {
         MFM_CUDA_CHECK(cudaMemsetAsync(grads, 0, (size_t)F.n_params * sizeof(float), st));
         if ((rc = field_prepare_weights(F, B, st))) return rc;
@@ -340,12 +341,14 @@ static int fm_check(const mfm_field_t* f, const mfm_target_t* t) {
 int mfm_fm_loss_grad(const mfm_field_t* f, const mfm_target_t* t, const uint32_t* rng_key, int n, int chain_offset,
                      int n_total, float sigma, const float* positions, float* loss_out, float* grads, void* ws,
                      size_t ws_bytes, mfm_stream_t stream) {
+    mfm::CrossScope cross_scope;
     return mfm_fm_loss_grad_part(f, t, rng_key, n, chain_offset, n_total, sigma, positions, loss_out, grads, ws, ws_bytes, 0, stream);
 }
 
 int mfm_fm_loss_grad_part(const mfm_field_t* f, const mfm_target_t* t, const uint32_t* rng_key, int n, int chain_offset,
                           int n_total, float sigma, const float* positions, float* loss_out, float* grads, void* ws,
                           size_t ws_bytes, int part, mfm_stream_t stream) {
+    mfm::CrossScope cross_scope;
     int rc = fm_check(f, t);
     if (rc) return rc;
     if (part < 0 || part > 2) { mfm_set_last_error_msg("part must be 0, 1 or 2"); return MFM_ERR_ARG; }
@@ -367,6 +370,7 @@ int mfm_fm_loss_grad_part(const mfm_field_t* f, const mfm_target_t* t, const uin
 int mfm_fm_loss_grad_from_batch(const mfm_field_t* f, const mfm_target_t* t, int n, const float* xt, const float* times,
                                 const float* target_v, float* loss_out, float* grads, void* ws, size_t ws_bytes,
                                 mfm_stream_t stream) {
+    mfm::CrossScope cross_scope;
     int rc = fm_check(f, t);
     if (rc) return rc;
     if (!xt || !times || !target_v || !loss_out || !grads) { mfm_set_last_error_msg("null argument"); return MFM_ERR_ARG; }

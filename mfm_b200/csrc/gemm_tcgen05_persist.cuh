@@ -162,9 +162,17 @@ __device__ __forceinline__ float tf32_trunc_rest(float x) { return x - __uint_as
 // SWIZZLE_128B, +32 B per k-step): same descriptors, half the tensor-pipe time of two tf32 MMAs and a
 // third less MMA operand traffic.  bf16 keeps 8 bits of factors that are 2^-11 relative, so the cross
 // terms carry ~2^-19 relative error (unbiased, round-to-nearest): fp32-class like the rest.
-template <bool A_KMAJOR, bool B_NMAJOR, bool XBF16, class Epi>
+//
+// BPRE: the B operand's cross tile [ bf16(b) | bf16(b_lo) ] comes PRE-SPLIT from global memory (maps.bx: a byte-congruent
+// mirror of B in which every 8 floats are replaced by 8 + 8 bf16, written once per parameter update by presplit_kernel)
+// and is loaded by TMA straight into the cross region; the splitter warps then only convert the A rows.  The dense layers'
+// B operand is a weight matrix that every CTA pair of every tile of every layer call would otherwise re-split: this
+// halves the splitters' shared-memory traffic (measured: LSU wavefronts 52 % + tensor-core reads 35 % of the pipe).
+struct Maps3 { CUtensorMap a, b, bx; };
+
+template <bool A_KMAJOR, bool B_NMAJOR, bool XBF16, bool BPRE, class Epi>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
-gemm_tc2p_kernel(const __grid_constant__ Maps maps, GemmShape p, Epi epi, long long* tl, float* sk_ws, unsigned* sk_flags, unsigned sk_epoch) {
+gemm_tc2p_kernel(const __grid_constant__ Maps3 maps, GemmShape p, Epi epi, long long* tl, float* sk_ws, unsigned* sk_flags, unsigned sk_epoch) {
 #ifdef MFM_TC2_TIMELINE
     // tuning aid: SM clock at 4 events of the first 16 tiles of pair 0's leader (MMA start / accumulator
     // committed / epilogue start / epilogue end)
@@ -178,6 +186,7 @@ gemm_tc2p_kernel(const __grid_constant__ Maps maps, GemmShape p, Epi epi, long l
 #define TC2P_MARKX(slot) do { } while (0)
 #endif
     static_assert(!XBF16 || (A_KMAJOR && !B_NMAJOR), "bf16 cross terms need K-major operands");
+    static_assert(!BPRE || XBF16, "a pre-split B operand is a bf16 cross tile");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* stg_base = smem + STAGES * STAGE_BYTES;
@@ -203,6 +212,7 @@ gemm_tc2p_kernel(const __grid_constant__ Maps maps, GemmShape p, Epi epi, long l
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.b) : "memory");
+        if (BPRE) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.bx) : "memory");
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&split[s], 2 * SPLIT_WARPS); mbar_init(&empty[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 2 * EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -261,12 +271,13 @@ gemm_tc2p_kernel(const __grid_constant__ Maps maps, GemmShape p, Epi epi, long l
                     const uint32_t s = g % STAGES, ph = (g / STAGES) & 1;
                     mbar_wait(&empty[s], ph ^ 1);
                     uint8_t* st = smem + s * STAGE_BYTES;
-                    mbar_expect_tx(&full[s], HI_BYTES);
+                    mbar_expect_tx(&full[s], HI_BYTES + (BPRE ? B_BYTES : 0));
                     const int k0 = kz0 + kt * BK;
                     if (A_KMAJOR) tma_load_2d(st, &maps.a, &full[s], k0, m0);
                     else          tma_load_3d(st, &maps.a, &full[s], 0, k0, m0 / 32);
                     if (!B_NMAJOR) tma_load_2d(st + A_BYTES, &maps.b, &full[s], k0, nb0);
                     else           tma_load_3d(st + A_BYTES, &maps.b, &full[s], 0, k0, nb0 / 32);
+                    if (BPRE) tma_load_2d(st + HI_BYTES + A_BYTES, &maps.bx, &full[s], k0, nb0);   // B cross half-tile, ready made
                 }
             }
         }
@@ -331,7 +342,7 @@ gemm_tc2p_kernel(const __grid_constant__ Maps maps, GemmShape p, Epi epi, long l
                 mbar_wait(&full[s], ph);
                 const uint32_t hi = smem_u32(smem + s * STAGE_BYTES) + (uint32_t)tix * 16u;
                 const uint32_t lo = hi + HI_BYTES;
-                constexpr int PER = HI_BYTES / 16 / (SPLIT_WARPS * 32);    // 8 float4 per thread
+                constexpr int PER = (BPRE ? A_BYTES : HI_BYTES) / 16 / (SPLIT_WARPS * 32);    // 8 float4 per thread (4: A rows only)
                 constexpr uint32_t STEP = SPLIT_WARPS * 32 * 16;
                 float4 v[PER];
 #pragma unroll
@@ -580,18 +591,27 @@ int sm_pairs();                             // number of TPC pairs to keep resid
 bool streamk_workspace(cudaStream_t st, float** ws, unsigned** flags, unsigned* epoch);
 int gemm_cross_bf16();                      // 1: K-major x K-major GEMMs take their cross terms from one bf16 MMA (env MFM_GEMM_CROSS=tf32|bf16)
 
+// pre-split mirrors of weight buffers registered for the duration of an ABI call (rng.cu): mirror pointer for `p`, or null
+const float* lookup_cross(const float* p);
+
 template <bool A_KMAJOR, bool B_NMAJOR, class Epi>
 inline cudaError_t launch(const GemmShape& p, const Epi& epi, cudaStream_t st) {
-    Maps maps;
+    Maps3 maps;
     bool ok = A_KMAJOR ? tc::make_map_kmajor(&maps.a, p.A, p.lda, p.M, p.K, BM) : tc::make_map_mnmajor(&maps.a, p.A, p.lda, p.M, p.K, BM / 32);
     ok = ok && (!B_NMAJOR ? tc::make_map_kmajor(&maps.b, p.B, p.ldb, p.N, p.K, BNH) : tc::make_map_mnmajor(&maps.b, p.B, p.ldb, p.N, p.K, BNH / 32));
     if (!ok) return cudaErrorInvalidValue;
     constexpr bool KK = A_KMAJOR && !B_NMAJOR;
-    auto kern = (KK && gemm_cross_bf16()) ? gemm_tc2p_kernel<A_KMAJOR, B_NMAJOR, KK, Epi> : gemm_tc2p_kernel<A_KMAJOR, B_NMAJOR, false, Epi>;
+    const bool xb = KK && gemm_cross_bf16();
+    const float* bx = (xb && p.K % 8 == 0 && p.ldb % 8 == 0) ? lookup_cross(p.B) : nullptr;
+    if (bx && !tc::make_map_kmajor(&maps.bx, bx, p.ldb, p.N, p.K, BNH)) return cudaErrorInvalidValue;
+    if (!bx) maps.bx = maps.b;
+    auto kern = bx ? gemm_tc2p_kernel<A_KMAJOR, B_NMAJOR, KK, KK, Epi>
+                   : (xb ? gemm_tc2p_kernel<A_KMAJOR, B_NMAJOR, KK, false, Epi> : gemm_tc2p_kernel<A_KMAJOR, B_NMAJOR, false, false, Epi>);
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc2p_kernel<A_KMAJOR, B_NMAJOR, false, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        if (e == cudaSuccess && KK) e = cudaFuncSetAttribute(gemm_tc2p_kernel<A_KMAJOR, B_NMAJOR, KK, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc2p_kernel<A_KMAJOR, B_NMAJOR, false, false, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e == cudaSuccess && KK) e = cudaFuncSetAttribute(gemm_tc2p_kernel<A_KMAJOR, B_NMAJOR, KK, false, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e == cudaSuccess && KK) e = cudaFuncSetAttribute(gemm_tc2p_kernel<A_KMAJOR, B_NMAJOR, KK, KK, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess) return e;
         configured = true;
     }

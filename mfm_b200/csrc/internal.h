@@ -46,11 +46,21 @@ struct FieldBufs {
     float *ff, *h0, *cat, *h2, *gt, *h5, *h6, *gc, *hx, *ta, *tb, *zw2, *zkinv, *divpart;
     float *tan_a, *tan_b;   // exact path [n*d, H]
     float* wt;              // transposed dense kernels: layer i at wt + F.w_off[i], stored [out][in] (K-major B operand)
+    float *wx, *wxo;        // pre-split bf16 cross mirrors of wt / of the parameters themselves (null: layer sizes not multiples of 8)
 };
+namespace tc2p {
+void register_cross(const float* base, size_t n_floats, const float* mirror);
+void clear_cross();
+}
+// dst mirrors src (n8 groups of 8 floats): group g -> 8 bf16 of the values | 8 bf16 of their tf32 truncation rests
+int presplit_weights(const float* src, float* dst, long long n_floats, cudaStream_t st);
+// clears the mirror registry when an ABI call that registered mirrors returns
+struct CrossScope { ~CrossScope() { tc2p::clear_cross(); } };
 size_t field_bufs_bytes(const mfm_field_t& F, const mfm_target_t& T, int n, bool hutch);
 bool field_bufs_take(FieldBufs& B, Workspace& w, const mfm_field_t& F, int n, bool hutch);
 // B.wt <- transposes of the eight dense kernels (once per ABI call: the parameters may have changed)
 int field_prepare_weights(const mfm_field_t& F, FieldBufs& B, cudaStream_t st);
+void field_register_mirrors(const mfm_field_t& F, const FieldBufs& B);
 // C[n,out] = relu?(A[n,in] W[in,out] + bias) gated by mask (relu' of another activation).
 // WT = the kernel transposed, WT[o*ldwt + i]: both GEMM operands are K-major, which is what the
 // persistent tcgen05 kernel's bf16 cross-term path needs.

@@ -31,6 +31,21 @@ int gemm_cross_bf16() {
     return g_cross_bf16;
 }
 int sm_pairs();
+// ---- pre-split weight mirrors (gemm_tcgen05_persist.cuh, BPRE) -------------------------------------------------------
+// [base, base + n_floats) -> mirror (same byte layout, every 8 floats replaced by 8 + 8 bf16).  Registered by the ABI call
+// that built the mirrors in ITS workspace and cleared when it returns (CrossScope), so no stale range survives a call.
+struct CrossRange { const float* base; size_t n; const float* mirror; };
+static thread_local CrossRange g_cross[8];
+static thread_local int g_n_cross = 0;
+void register_cross(const float* base, size_t n_floats, const float* mirror) {
+    if (g_n_cross < 8) g_cross[g_n_cross++] = CrossRange{base, n_floats, mirror};
+}
+void clear_cross() { g_n_cross = 0; }
+const float* lookup_cross(const float* p) {
+    for (int i = 0; i < g_n_cross; ++i)
+        if (p >= g_cross[i].base && p < g_cross[i].base + g_cross[i].n && ((p - g_cross[i].base) % 8) == 0) return g_cross[i].mirror + (p - g_cross[i].base);
+    return nullptr;
+}
 static int g_streamk = -1;
 constexpr int SK_SLOT_FLOATS = 256 * 256, SK_SLOT_FLAGS = 64;   // = gemm_tcgen05_persist.cuh (static_assert there)
 struct SkWs { cudaStream_t st; int dev; float* ws; unsigned* flags; unsigned epoch; };
@@ -81,6 +96,9 @@ int gemm_raw_hi() {
 extern "C" void mfm_set_gemm_raw_hi(int v) { mfm::tc2::g_raw_hi = v ? 1 : 0; }
 extern "C" void mfm_set_gemm_cross_bf16(int v) { mfm::tc2p::g_cross_bf16 = v ? 1 : 0; }
 extern "C" void mfm_set_gemm_streamk(int v) { mfm::tc2p::g_streamk = v ? 1 : 0; }
+extern "C" void mfm_gemm_register_mirror(const float* base, long long n_floats, const float* mirror) {
+    if (base && mirror && n_floats > 0) mfm::tc2p::register_cross(base, (size_t)n_floats, mirror); else mfm::tc2p::clear_cross();
+}
 // tuning aid (not part of the ABI header): SM-clock timeline of one CTA pair of the last tc2 GEMM
 namespace mfm { namespace tc2 {
 static long long* g_timeline_buf = nullptr;

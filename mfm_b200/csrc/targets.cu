@@ -300,6 +300,13 @@ int mfm_gemm_tf32x3_gated(int M, int N, int K, const float* A, long long lda, co
     return MFM_OK;
 }
 
+int mfm_gemm_presplit(const float* src, float* mirror, long long n_floats, mfm_stream_t stream) {
+    if (!src || !mirror || n_floats <= 0 || n_floats % 8 || ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(mirror)) & 31)) {
+        mfm_set_last_error_msg("bad argument (mfm_gemm_presplit)"); return MFM_ERR_ARG;
+    }
+    return mfm::presplit_weights(src, mirror, n_floats, stream);
+}
+
 int mfm_gemm_tf32x3_rows(int M, int N, int K, const float* A, long long lda, const float* Bt, long long ldb, const float* bias,
                          float* Cout, long long ldc, const int* n_rows_dev, mfm_stream_t stream) {
     using namespace mfm;

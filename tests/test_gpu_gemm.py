@@ -175,6 +175,39 @@ def test_gemm_streamk_device_row_count(cuda, lib, rows):
         assert np.abs(got[:rows] - ref).max() <= (3e-6 + 8e-9 * K) * np.abs(ref).max()
 
 
+@pytest.mark.parametrize("M,N,K", [(512, 512, 512), (8192, 1600, 1024), (4096 + 77, 1088, 520), (1024, 1024, 1600), (300, 256, 64)])
+def test_gemm_presplit_b_operand(cuda, lib, M, N, K):
+    """B operand's bf16 cross tile pre-split in global memory and loaded by TMA (what the MLP layers do with their weights):
+    the same bits reach the tensor core, so the result is bit-identical to splitting B in the kernel."""
+    rng = np.random.default_rng(M + N + K + 1)
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    Bt = (rng.standard_normal((N, K)) * np.exp(rng.standard_normal((N, 1)))).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+    Ad, Bd, bias_d = torch.from_numpy(A).to(cuda), torch.from_numpy(Bt).to(cuda), torch.from_numpy(bias).to(cuda)
+    mirror = torch.empty_like(Bd)
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.mfm_gemm_presplit(Bd.data_ptr(), mirror.data_ptr(), N * K, st))
+    # mirror layout: per 8 floats, 8 bf16 of the values then 8 bf16 of (value - tf32 truncation)
+    mb = mirror.view(torch.bfloat16).view(N, K // 8, 2, 8).float().cpu().numpy()
+    vals = Bt.reshape(N, K // 8, 8)
+    trunc = (vals.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+    assert np.array_equal(mb[:, :, 0], torch.from_numpy(vals).bfloat16().float().numpy())
+    assert np.array_equal(mb[:, :, 1], torch.from_numpy(vals - trunc).bfloat16().float().numpy())
+    outs = []
+    for use in (0, 1):
+        Cd = torch.full((M, N), float("nan"), dtype=torch.float32, device=cuda)
+        if use:
+            lib.mfm_gemm_register_mirror(Bd.data_ptr(), N * K, mirror.data_ptr())
+        try:
+            _lib.check(lib.mfm_gemm_tf32x3(M, N, K, Ad.data_ptr(), K, 1, Bd.data_ptr(), K, 0, bias_d.data_ptr(), 1, Cd.data_ptr(), N, st))
+            outs.append(Cd.cpu().numpy())
+        finally:
+            lib.mfm_gemm_register_mirror(None, 0, None)
+    ref = np.maximum(A.astype(np.float64) @ Bt.astype(np.float64).T + bias, 0)
+    assert np.abs(outs[1] - ref).max() <= (3e-6 + 8e-9 * K) * max(np.abs(ref).max(), 1.0)
+    assert np.array_equal(outs[0], outs[1])
+
+
 def test_gemm_strided_views(cuda, lib):
     """ld > logical width (writing into a column block of a concatenated buffer)."""
     rng = np.random.default_rng(0)
