@@ -84,7 +84,7 @@ class Flow:
             z = self._probe(keys, d, u.dtype)
 
         def aug(y, t):
-            v, div = vf.field_and_div(self.params, self.omega, y[:, :d], t, self.target, z, self.grad_clip)
+            v, div = vf.field_and_div(self.params, self.omega, np.ascontiguousarray(y[:, :d]), t, self.target, z, self.grad_clip)
             return np.concatenate([v, -div[:, None]], 1)
 
         y0 = np.concatenate([u, np.zeros((N, 1), u.dtype)], 1)
@@ -99,7 +99,7 @@ class Flow:
 
         def aug(y, s):
             t = x.dtype.type(1.0) - s
-            v, div = vf.field_and_div(self.params, self.omega, y[:, :d], t, self.target, z, self.grad_clip)
+            v, div = vf.field_and_div(self.params, self.omega, np.ascontiguousarray(y[:, :d]), t, self.target, z, self.grad_clip)
             return np.concatenate([-v, div[:, None]], 1)
 
         y0 = np.concatenate([x, np.zeros((N, 1), x.dtype)], 1)

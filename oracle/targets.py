@@ -248,11 +248,11 @@ class LogGaussianCoxPines(Target):
 
     def loglik(self, x):
         dt = x.dtype
-        return (x * self.counts.astype(dt) - dt.type(self.a) * np.exp(x)).sum(1)
+        return (x * self.counts.astype(dt, copy=False) - dt.type(self.a) * np.exp(x)).sum(1)
 
     def grad_loglik(self, x):
         dt = x.dtype
-        return self.counts.astype(dt)[None] - dt.type(self.a) * np.exp(x)
+        return self.counts.astype(dt, copy=False)[None] - dt.type(self.a) * np.exp(x)
 
     def hvp_loglik(self, x, z):
         return -x.dtype.type(self.a) * np.exp(x) * z
@@ -263,19 +263,19 @@ class LogGaussianCoxPines(Target):
     def logprior(self, x):
         dt = x.dtype
         # as coded: triangular solve against the Cholesky factor (cox_process_utils.py:162)
-        white = self._sl.solve_triangular(self.L.astype(dt), (x - dt.type(self.mu)).T, lower=True).T
+        white = self._sl.solve_triangular(self.L.astype(dt, copy=False), (x - dt.type(self.mu)).T, lower=True).T
         return dt.type(-0.5) * (white * white).sum(1) + dt.type(self.log_norm)
 
     def grad_logprior(self, x):
         dt = x.dtype
         r = (x - dt.type(self.mu)).T
-        w = self._sl.solve_triangular(self.L.astype(dt), r, lower=True)
-        return -self._sl.solve_triangular(self.L.astype(dt), w, lower=True, trans="T").T
+        w = self._sl.solve_triangular(self.L.astype(dt, copy=False), r, lower=True)
+        return -self._sl.solve_triangular(self.L.astype(dt, copy=False), w, lower=True, trans="T").T
 
     def hvp_logprior(self, x, z):
         dt = x.dtype
-        w = self._sl.solve_triangular(self.L.astype(dt), z.T, lower=True)
-        return -self._sl.solve_triangular(self.L.astype(dt), w, lower=True, trans="T").T
+        w = self._sl.solve_triangular(self.L.astype(dt, copy=False), z.T, lower=True)
+        return -self._sl.solve_triangular(self.L.astype(dt, copy=False), w, lower=True, trans="T").T
 
     def hdiag_logprior(self, x):
         return np.broadcast_to(-np.diag(self.Kinv).astype(x.dtype), x.shape).copy()
@@ -284,4 +284,4 @@ class LogGaussianCoxPines(Target):
         """distributions.py:312-314: mu + L @ normal(k,(d,))."""
         dt = np.dtype(dtype)
         eps = tf.vmap_normal(tf.split(key, n), self.dim, dt)
-        return (dt.type(self.mu) + eps @ self.L.astype(dt).T).astype(dt)
+        return (dt.type(self.mu) + eps @ self.L.astype(dt, copy=False).T).astype(dt)

@@ -32,9 +32,25 @@ def init_params(rng: np.random.Generator, d, H, F=128, head_scale=0.0, dtype=np.
     return {"params": p}
 
 
+_CAST = {}      # (id(array), dtype) -> (array, converted): the float32 -> float64 cast of 10 M weights per call dominated
+                # the oracle's field evaluation; the source array is kept alive in the entry so ids cannot be recycled
+
+
+def _cast(a, dt):
+    if a.dtype == dt:
+        return a
+    k = (id(a), np.dtype(dt).str)
+    hit = _CAST.get(k)
+    if hit is None or hit[0] is not a:
+        if len(_CAST) > 64:
+            _CAST.clear()
+        hit = _CAST[k] = (a, a.astype(dt))
+    return hit[1]
+
+
 def _wb(params, i, dt):
     q = params["params"][f"Dense_{i}"]
-    return q["kernel"].astype(dt), q["bias"].astype(dt)
+    return _cast(q["kernel"], dt), _cast(q["bias"], dt)
 
 
 def fourier_features(t, omega, dt):
