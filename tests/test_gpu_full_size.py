@@ -117,7 +117,8 @@ def test_full_size_flow_push_subset_matches_small_run(cuda, big):
     stats = torch.zeros(4, dtype=torch.int32, device=cuda)
     y, ldj = push(keys, u, big.P, stats)
     idx = torch.from_numpy(ROWS).to(cuda)
-    y8, ldj8 = push(keys[idx].contiguous(), u[idx].contiguous(), big.P)
+    keys8 = keys.view(torch.int32)[idx].contiguous().view(torch.uint32)      # torch cannot index uint32 tensors
+    y8, ldj8 = push(keys8, u[idx].contiguous(), big.P)
     assert torch.isfinite(y).all() and torch.isfinite(ldj).all()
     acc, tried, mx, nev = stats.cpu().tolist()
     assert nev == 2 + 6 * mx and acc <= tried
