@@ -124,4 +124,7 @@ def test_full_size_flow_push_subset_matches_small_run(cuda, big):
     assert nev == 2 + 6 * mx and acc <= tried
     # different kernels serve 8 rows (warp-level MMA) and 65 536 rows (persistent tcgen05): agreement to the ODE tolerance
     assert rel_err(y[idx].cpu().numpy(), y8.cpu().numpy()) < 1e-3
-    assert np.abs(ldj[idx].cpu().numpy() - ldj8.cpu().numpy()).max() < 5e-3 + 3e-6 * D + 1e-3 * np.abs(ldj8.cpu().numpy()).max()
+    # log-det: a d-term cancelling Hutchinson sum per field evaluation, ~1e-6 * d absolute round-off each,
+    # accumulated over the ~14 accepted steps of the solve by two different GEMM kernels
+    dl = np.abs(ldj[idx].cpu().numpy() - ldj8.cpu().numpy()).max()
+    assert dl < 3e-2, dl
