@@ -59,12 +59,13 @@ bool streamk_workspace(cudaStream_t st, float** ws, unsigned** flags, unsigned* 
     if (!g_streamk) return false;
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    // never inside a CUDA-graph capture: the launch epoch is a kernel argument, a replay would meet its own stale flags
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) { cudaGetLastError(); return false; }
     SkWs* w = nullptr;
     for (int i = 0; i < g_n_skws; ++i) if (g_skws[i].st == st && g_skws[i].dev == dev) { w = &g_skws[i]; break; }
     if (!w) {
         if (g_n_skws == 8) return false;
-        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-        if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return false;
         SkWs n{st, dev, nullptr, nullptr, 0};
         const size_t fbytes = (size_t)sm_pairs() * SK_SLOT_FLAGS * sizeof(unsigned);
         if (cudaMalloc(&n.ws, (size_t)sm_pairs() * SK_SLOT_FLOATS * sizeof(float)) != cudaSuccess) { cudaGetLastError(); return false; }
