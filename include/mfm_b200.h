@@ -202,6 +202,11 @@ int mfm_fm_loss_grad(const mfm_field_t* f, const mfm_target_t* t, const uint32_t
 int mfm_fm_loss_grad_part(const mfm_field_t* f, const mfm_target_t* t, const uint32_t* rng_key, int n, int chain_offset,
                           int n_total, float sigma, const float* positions, float* loss_out, float* grads, void* ws,
                           size_t ws_bytes, int part, mfm_stream_t stream);
+/* same with the NON-conditional batch, flow_fn (exe_flow_matching.py:139-147; the reference's --cond_flow switched off):
+ * key_time, key_ref = split(key); x_t = t x + (1 - (1-sigma) t) ref, target = x - (1-sigma) ref, ref = normal(key_ref, (N,d)). */
+int mfm_fm_loss_grad_uncond(const mfm_field_t* f, const mfm_target_t* t, const uint32_t* rng_key, int n, int chain_offset,
+                            int n_total, float sigma, const float* positions, float* loss_out, float* grads, void* ws,
+                            size_t ws_bytes, mfm_stream_t stream);
 /* same, from explicit (x_t, t, target) — test hook */
 int mfm_fm_loss_grad_from_batch(const mfm_field_t* f, const mfm_target_t* t, int n, const float* xt,
                                 const float* times, const float* target_v, float* loss_out, float* grads,

@@ -98,6 +98,8 @@ SIGNATURES = {
     "mfm_fm_workspace_bytes": (C.c_size_t, [_FP, _PT, C.c_int]),
     "mfm_fm_loss_grad": (C.c_int, [_FP, _PT, c_u32p, C.c_int, C.c_int, C.c_int, C.c_float, c_f32p, c_f32p, c_f32p,
                                    C.c_void_p, C.c_size_t, _S]),
+    "mfm_fm_loss_grad_uncond": (C.c_int, [_FP, _PT, c_u32p, C.c_int, C.c_int, C.c_int, C.c_float, c_f32p, c_f32p, c_f32p,
+                                   C.c_void_p, C.c_size_t, _S]),
     "mfm_fm_loss_grad_part": (C.c_int, [_FP, _PT, c_u32p, C.c_int, C.c_int, C.c_int, C.c_float, c_f32p, c_f32p, c_f32p,
                                         C.c_void_p, C.c_size_t, C.c_int, _S]),
     "mfm_fm_loss_grad_from_batch": (C.c_int, [_FP, _PT, C.c_int, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p,

@@ -51,6 +51,32 @@ fm_batch_kernel(const uint32_t* __restrict__ rng_key, int n, int chain_offset, i
     if (lane == 0) times[c] = t;
 }
 
+// Non-conditional variant, flow_fn (exe_flow_matching.py:139-147, --cond_flow off):
+//   key_time, key_ref = split(key);  t ~ U[0,1)^(N,1);  ref ~ N(0,I)^(N,d) (ONE draw for the whole batch)
+//   x_t = t*x + (1 - (1-sigma) t) * ref ;  target = x - (1-sigma) * ref      (one warp per chain)
+__global__ void __launch_bounds__(256)
+fm_batch_uncond_kernel(const uint32_t* __restrict__ rng_key, int n, int chain_offset, int n_total, int d, float sigma,
+                       const float* __restrict__ x, float* __restrict__ times, float* __restrict__ xt, float* __restrict__ target) {
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= n) return;
+    const uint32_t gc = (uint32_t)(chain_offset + c);
+    const u32x2 k_time = threefry_split_key(rng_key[0], rng_key[1], 0u, 2u);
+    const u32x2 k_ref = threefry_split_key(rng_key[0], rng_key[1], 1u, 2u);
+    const float t = bits_to_unit_float(threefry_stream_word(k_time.a, k_time.b, gc, (uint32_t)n_total));
+    const uint32_t total = (uint32_t)n_total * (uint32_t)d;
+    const float oms = 1.0f - sigma;
+    const float sds = 1.0f - oms * t;                                     // :144
+    for (int j = lane; j < d; j += 32) {
+        const float ref = bits_to_normal(threefry_stream_word(k_ref.a, k_ref.b, gc * (uint32_t)d + (uint32_t)j, total));
+        const long long idx = (long long)c * d + j;
+        const float xv = x[idx];
+        xt[idx] = __fadd_rn(__fmul_rn(t, xv), __fmul_rn(sds, ref));      // :145
+        target[idx] = xv - __fmul_rn(oms, ref);                          // :146
+    }
+    if (lane == 0) times[c] = t;
+}
+
 // diff = v - target; delta = 2*diff; dgt = delta*gc; per-block partial sums of diff^2
 __global__ void __launch_bounds__(256)
 fm_loss_delta_kernel(long long total, const float* __restrict__ v, const float* __restrict__ target,
@@ -365,6 +391,25 @@ int mfm_fm_loss_grad_part(const mfm_field_t* f, const mfm_target_t* t, const uin
         MFM_LAUNCH_CHECK();
     }
     return fm_forward_backward(*f, *t, n, M, loss_out, grads, stream, part);
+}
+
+int mfm_fm_loss_grad_uncond(const mfm_field_t* f, const mfm_target_t* t, const uint32_t* rng_key, int n, int chain_offset,
+                            int n_total, float sigma, const float* positions, float* loss_out, float* grads, void* ws,
+                            size_t ws_bytes, mfm_stream_t stream) {
+    mfm::CrossScope cross_scope;
+    int rc = fm_check(f, t);
+    if (rc) return rc;
+    if (!rng_key || !positions || !loss_out || !grads) { mfm_set_last_error_msg("null argument"); return MFM_ERR_ARG; }
+    if (n <= 0) return MFM_OK;
+    if (n_total < chain_offset + n || chain_offset < 0) { mfm_set_last_error_msg("bad chain_offset/n_total"); return MFM_ERR_ARG; }
+    if ((long long)n_total * f->dim > 0xFFFFFFFFll) { mfm_set_last_error_msg("n_total*d exceeds the 32-bit counter space"); return MFM_ERR_UNSUPPORTED; }
+    Workspace w(ws, ws_bytes);
+    FmBufs M;
+    if (!fm_take(M, w, *f, n)) { mfm_set_last_error_msg("workspace too small (mfm_fm_loss_grad_uncond)"); return MFM_ERR_WORKSPACE; }
+    fm_batch_uncond_kernel<<<ceil_div(n, 8), 256, 0, stream>>>(rng_key, n, chain_offset, n_total, f->dim, sigma, positions,
+                                                                M.times, M.xt, M.target);
+    MFM_LAUNCH_CHECK();
+    return fm_forward_backward(*f, *t, n, M, loss_out, grads, stream, 0);
 }
 
 int mfm_fm_loss_grad_from_batch(const mfm_field_t* f, const mfm_target_t* t, int n, const float* xt, const float* times,

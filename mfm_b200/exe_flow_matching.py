@@ -195,8 +195,8 @@ class TrainState:
         assert self._pending is None, "apply_pending() first: the gradient buffer is still being reduced"
         lib = _lib.load()
         a = self.args
-        if not a.cond_flow or a.ot_cond_flow:
-            raise NotImplementedError("device FM loss implements cond_flow=True, ot_cond_flow=False (reference defaults)")
+        if a.ot_cond_flow:
+            raise NotImplementedError("the optimal-transport coupling (ot_cond_flow, ott-jax Sinkhorn) is not on the configured hot path")
         n = positions.shape[0]
         fd, td = self.model.field_desc(self.P), self.model.dist._desc(1.0)
         ws = _lib.workspace(lib.mfm_fm_workspace_bytes(fd, td, n), positions.device, "fm")
@@ -208,6 +208,16 @@ class TrainState:
                                                  _lib.ptr(ws), ws.numel(), k, _lib.stream()))
 
         _, world = parallel.world_info(group)
+        if not a.cond_flow:
+            # flow_fn (:139-147): one ABI call; with several ranks the gradient is reduced in one piece
+            _lib.check(lib.mfm_fm_loss_grad_uncond(fd, td, _lib.ptr(rng_key), n, chain_offset, n_total if n_total is not None else n,
+                                                   float(a.sigma), _lib.ptr(pos), _lib.ptr(self.loss), _lib.ptr(self.grads),
+                                                   _lib.ptr(ws), ws.numel(), _lib.stream()))
+            if allreduce and world > 1:
+                parallel.allreduce_sum_([self.loss, self.grads], group)
+            if defer:
+                self._pending = ()
+            return self.loss, self.grads
         if not allreduce or world == 1:
             part(0)
             if defer:
@@ -345,7 +355,7 @@ class HotLoop:
     only exchange is the SUM all-reduce of the flat FM gradient (and the scalar loss)."""
 
     def __init__(self, dist, model, P, args, ode_opts, key_sample, positions, beta=1.0, chain_offset=0, n_total=None,
-                 process_group=None, pipeline=None, graph=None):
+                 process_group=None, pipeline=None, graph=None, real_sampler=None):
         import torch.distributed as tdist
         self.dist, self.model, self.P, self.args = dist, model, P, args
         self.n = positions.shape[0]
@@ -366,12 +376,19 @@ class HotLoop:
             dist, model, ode_opts, args, chain_offset=chain_offset, n_total=self.n_total)
         self.beta = float(beta)
         self.key_sample = key_sample.clone()
-        self.states = self.init_fn(positions, self.beta)
+        # use_real_samples (mcmc_per_flow_steps < 0, :328,382-386): the "data generator" draws from the target itself,
+        # real_sampler(uint32[n,2] keys) -> [n,d]; no chains, no log-densities
+        self.real_sampler = real_sampler
+        if real_sampler is not None:
+            self.graph = False
+            self.states = MALAState(positions, None, None)
+        else:
+            self.states = self.init_fn(positions, self.beta)
         self.count = 0
         self.last_info = None
 
     def reset_positions(self, positions):
-        self.states = self.init_fn(positions, self.beta)
+        self.states = MALAState(positions, None, None) if self.real_sampler is not None else self.init_fn(positions, self.beta)
         self._graph = None                    # the captured iteration points at the old state arrays
 
     def _mala_iteration_body(self):
@@ -414,9 +431,15 @@ class HotLoop:
         keys = mrandom.split(self.key_sample, 3)
         self.key_sample.copy_(keys[0])          # in place: a captured graph reads this buffer
         key_train_gn, key_train_step = keys[1], keys[2]
-        if self.is_flow_iteration(self.count):
-            self.state.apply_pending()          # the flow step integrates the CURRENT vector field
-        self.states, self.last_info = self.gen(key_train_gn, self.states, self.count, self.P, self.beta, inplace=True)
+        if self.real_sampler is not None:
+            # train_data_generator = lambda key, *_: vmap(target_gn)(split(key, n_chain))  (:383-385); this rank's rows
+            keys_n = mrandom.split(key_train_gn, self.n_total)[self.chain_offset:self.chain_offset + self.n].contiguous()
+            self.states = MALAState(self.real_sampler(keys_n).contiguous(), None, None)
+            self.last_info = MALAInfo(torch.full((self.n,), float("nan"), device=self.states.position.device), None, None, None)
+        else:
+            if self.is_flow_iteration(self.count):
+                self.state.apply_pending()          # the flow step integrates the CURRENT vector field
+            self.states, self.last_info = self.gen(key_train_gn, self.states, self.count, self.P, self.beta, inplace=True)
         self.state.apply_pending()
         pipelined = self.pipeline
         loss, grads = self.state.loss_and_grad(key_train_step, self.states.position, self.chain_offset, self.n_total,
@@ -445,6 +468,8 @@ class HotLoop:
     def temper(self):
         """beta_gen (:410-417): while beta < 1 pick the next beta and re-initialise (l, g) under it."""
         self.flush()
+        if self.real_sampler is not None:
+            return self.beta
         if self.beta < 1.0:
             self.beta = self.next_beta(self.beta, self.states.position)
             self.states = self.init_fn(self.states.position, self.beta)
@@ -453,6 +478,8 @@ class HotLoop:
 
     def is_flow_iteration(self, count):
         m = self.args.mcmc_per_flow_steps
+        if self.real_sampler is not None:
+            return False
         return (count % (int(1 / m) + 1) != 0) if 0 < m < 1 else (count % (int(m) + 1) == 0)
 
 
@@ -493,8 +520,9 @@ def run(dist: Distribution, args, target_gn=None, device=None, log_every: int = 
     logging.basicConfig(format="%(asctime)s - %(levelname)s - %(name)s - %(message)s", datefmt="%m/%d/%Y %H:%M:%S",
                         level=logging.INFO)
     dev = dist.device if device is None else torch.device(device)
-    if args.mcmc_per_flow_steps < 0:
-        raise NotImplementedError("use_real_samples (mcmc_per_flow_steps < 0) is not on the configured hot path")
+    use_real_samples = args.mcmc_per_flow_steps < 0                                                  # (:328)
+    if use_real_samples and target_gn is None:
+        raise ValueError("mcmc_per_flow_steps < 0 trains on real samples: a target generator (uint32[n,2] keys -> [n,d]) is required")
     rank, world = parallel.world_info()
     n_total = args.num_chain
     lo, hi = parallel.shard_range(n_total, rank, world)
@@ -511,11 +539,13 @@ def run(dist: Distribution, args, target_gn=None, device=None, log_every: int = 
     ode_opts = SimpleNamespace(rtol=args.rtol, atol=args.atol, mxstep=int(args.mxstep),
                                n_times=5 if args.example == "4-mode" else 2)                       # (:345-349)
     logger.info(f"===== Starting training seed {args.seed} w/ {args.learning_iter} iterations =====")
-    loop = HotLoop(dist, model, P, args, ode_opts, key_sample, positions, beta=1.0, chain_offset=lo, n_total=n_total)
-    beta = loop.next_beta(0.0, positions)                                                          # (:426)
-    logger.info(f"Initial beta= {beta}")
-    loop.beta = beta
-    loop.reset_positions(positions)                                                                # (:431)
+    loop = HotLoop(dist, model, P, args, ode_opts, key_sample, positions, beta=1.0, chain_offset=lo, n_total=n_total,
+                   real_sampler=target_gn if use_real_samples else None)
+    if not use_real_samples:
+        beta = loop.next_beta(0.0, positions)                                                      # (:426)
+        logger.info(f"Initial beta= {beta}")
+        loop.beta = beta
+        loop.reset_positions(positions)                                                            # (:431)
     t0 = time.time()
     history = []
     for count in range(1, args.learning_iter + 1):                                                 # (:432-449)
@@ -523,7 +553,7 @@ def run(dist: Distribution, args, target_gn=None, device=None, log_every: int = 
         if count % iter_per_temp == 0:
             loop.temper()
         if log_every and (count % log_every == 0 or count == args.learning_iter):
-            acc = loop.last_info.acceptance_rate
+            acc = loop.last_info.acceptance_rate if not use_real_samples else torch.full((1,), float("nan"))
             history.append({"count": count, "loss": float(loss.item()), "learning_rate": loop.lr_fn(count - 1),
                             "acceptance avg.": float(acc.mean().item()), "acceptance std.": float(acc.std().item()),
                             "beta": loop.beta, "train_time": time.time() - t0})

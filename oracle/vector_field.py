@@ -135,6 +135,20 @@ def fm_batch(key, samples, ref_sampler, sigma, rng_dtype=None):
     return times[:, 0], xt, target
 
 
+def fm_batch_uncond(key, samples, sigma, rng_dtype=None):
+    """flow_fn (exe_flow_matching.py:139-147), the --cond_flow-off variant: two-way key split, ONE [N,d] normal draw."""
+    N, d = samples.shape
+    dt = samples.dtype
+    rdt = np.dtype(rng_dtype or dt)
+    key_time, key_ref = tf.split(key)
+    times = tf.uniform(key_time, (N, 1), rdt).astype(dt)
+    ref = tf.normal(key_ref, (N, d), rdt).astype(dt)
+    sds = dt.type(1.0) - (dt.type(1.0) - dt.type(sigma)) * times
+    xt = times * samples + sds * ref
+    target = samples - (dt.type(1) - dt.type(sigma)) * ref
+    return times[:, 0], xt, target
+
+
 def fm_loss_and_grad(params, omega, xt, times, target_v, grad_logprob, grad_clip=None):
     """flow_matching_loss (exe_flow_matching.py:171-179) and its gradient w.r.t. params
     (what jax.value_and_grad(loss_fn, argnums=2) returns, :364-365)."""

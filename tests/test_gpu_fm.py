@@ -244,3 +244,50 @@ def test_graph_replayed_iterations_are_identical(cuda, lib, name):
     assert out[0][0] == out[1][0]
     for a, b in zip(out[0][1:], out[1][1:]):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("name,n", [("phi-four", 200), ("pines", 24)])
+def test_fm_loss_non_conditional_flow(cuda, setups, name, n):
+    """--cond_flow off: flow_fn (exe_flow_matching.py:139-147) instead of cond_flow_fn; sharded rows see the global draws."""
+    import copy
+    s = setups[name]
+    x = s.ot.init_positions(tf.PRNGKey(8), n, np.float32).astype(np.float64)
+    key = tf.PRNGKey(4242)
+    times, xt, target = VF.fm_batch_uncond(key, x, 1e-4, rng_dtype=np.float32)
+    loss_ref, G = VF.fm_loss_and_grad(s.params, s.omega, xt, times, target, s.ot.grad, s.clip)
+    state = copy.copy(s.state)
+    state.args = copy.copy(s.state.args); state.args.cond_flow = False
+    state.loss, state.grads = s.state.loss.clone(), s.state.grads.clone()
+    loss, grads = state.loss_and_grad(key_dev(key, cuda), to_dev(x, cuda))
+    assert abs(loss.item() - loss_ref) < 1e-4 * abs(loss_ref), (loss.item(), loss_ref)
+    assert rel_err(grads.cpu().numpy(), _flat_grads(s, G)) < 2e-4
+    full_l, full_g = loss.item(), grads.clone()
+    tot_l, tot_g = 0.0, torch.zeros_like(full_g)
+    for lo, hi in ((0, 8), (8, n)):
+        l, g = state.loss_and_grad(key_dev(key, cuda), to_dev(x[lo:hi], cuda), chain_offset=lo, n_total=n)
+        tot_l += l.item(); tot_g += g
+    assert abs(tot_l - full_l) < 1e-5 * abs(full_l) and rel_err(tot_g.cpu().numpy(), full_g.cpu().numpy()) < 2e-5
+
+
+def test_run_on_real_samples(cuda, lib):
+    """mcmc_per_flow_steps < 0 (use_real_samples, exe_flow_matching.py:328,382-386): the FM update trains on draws of the target."""
+    from mfm_b200 import multi_modal as MM, random as mr
+    args = MM.parser().parse_args(["--example", "4-mode", "--learning_iter", "5", "--mcmc_per_flow_steps", "-1", "--seed", "1",
+                                   "--eval_iter", "2", "--log_every", "1"])
+    dist = MM.build(args, device=cuda)
+    modes = torch.tensor(8.0 * np.array([[1, 1], [1, -1], [-1, 1], [-1, -1]]), dtype=torch.float32, device=cuda)
+
+    def target_gn(keys):
+        ks = mr.split(keys, 2)
+        comp = (mr.uniform(ks[:, 0].contiguous(), (1,))[:, 0] * 4).long().clamp(max=3)
+        return modes[comp] + mr.normal(ks[:, 1].contiguous(), (2,))
+
+    with pytest.raises(ValueError):
+        MM.run(dist, args, None)
+    res = MM.run(dist, args, target_gn, log_every=1)
+    assert len(res["history"]) == 5 and all(np.isfinite(h["loss"]) for h in res["history"])
+    loop = res["loop"]
+    assert loop.state.opt_state.cpu().tolist()[0] == 5 and loop.states.logdensity is None
+    # the last training batch is a draw of the target: every point sits near one of the four modes
+    d = (loop.states.position[:, None, :] - modes[None]).norm(dim=-1).min(dim=1).values
+    assert d.max().item() < 6.0 and "MMD" in res["table"]
