@@ -553,7 +553,7 @@ def run(dist: Distribution, args, target_gn=None, device=None, log_every: int = 
         if count % iter_per_temp == 0:
             loop.temper()
         if log_every and (count % log_every == 0 or count == args.learning_iter):
-            acc = loop.last_info.acceptance_rate if not use_real_samples else torch.full((1,), float("nan"))
+            acc = loop.last_info.acceptance_rate if not use_real_samples else torch.full((2,), float("nan"))
             history.append({"count": count, "loss": float(loss.item()), "learning_rate": loop.lr_fn(count - 1),
                             "acceptance avg.": float(acc.mean().item()), "acceptance std.": float(acc.std().item()),
                             "beta": loop.beta, "train_time": time.time() - t0})
