@@ -36,47 +36,30 @@ def build(args, device=None):
     raise Exception("Example not found.")
 
 
+# (flag, type, default) of the reference's command line (multi_modal.py:149-210), kept name for name so its command lines run
+_SCALARS = [
+    ("seed", int, None), ("dim", int, 64), ("num_modes", int, 16), ("example", str, "pines"), ("sigma", float, 1e-4),
+    ("fourier_dim", int, 128), ("fourier_std", float, 1.0), ("ref_dist", str, "stdgauss"), ("num_importance_samples", int, 0),
+    ("mcmc_per_flow_steps", float, 10), ("num_chain", int, 128), ("learning_iter", int, 400), ("eval_iter", int, 100),
+    ("alpha", float, 0.95), ("anneal_iter", int, 200), ("num_anneal_temp", int, 200), ("non_linearity", str, "relu"),
+    ("step_size", float, 0.2), ("learning_rate", float, 1e-3), ("weight_decay", float, 1e-4), ("adam_beta1", float, 0.9),
+    ("adam_beta2", float, 0.999), ("adam_epsilon", float, 1e-8), ("gradient_clip", float, 1.0), ("warmup_steps", int, 0),
+    ("rtol", float, 1e-5), ("atol", float, 1e-5), ("mxstep", float, 1_000), ("log_every", int, 100),
+]
+_SWITCHES = {"hutchs": False, "cond_flow": True, "ot_cond_flow": False}          # store_true flags and their defaults
+_LISTS = [("hidden_x", int, "+", [128, 128]), ("hidden_t", int, "+", [128, 128]), ("hidden_xt", int, "+", [128, 128]),
+          ("lim", float, 2, [-16, 16])]
+
+
 def parser():
-    p = argparse.ArgumentParser()
-    p.add_argument("--seed", type=int, default=None)
-    p.add_argument("--dim", type=int, default=64)
-    p.add_argument("--num_modes", type=int, default=16)
-    p.add_argument("--example", type=str, default="pines")
-    p.add_argument("--sigma", type=float, default=1e-4)
-    p.add_argument("--fourier_dim", type=int, default=128)
-    p.add_argument("--fourier_std", type=float, default=1.0)
-    p.add_argument("--hutchs", dest="hutchs", action="store_true")
-    p.set_defaults(hutchs=False)
-    p.add_argument("--ref_dist", type=str, default="stdgauss")
-    p.add_argument("--cond_flow", dest="cond_flow", action="store_true")
-    p.set_defaults(cond_flow=True)
-    p.add_argument("--ot_cond_flow", dest="ot_cond_flow", action="store_true")
-    p.set_defaults(ot_cond_flow=False)
-    p.add_argument("--num_importance_samples", type=int, default=0)
-    p.add_argument("--mcmc_per_flow_steps", type=float, default=10)
-    p.add_argument("--num_chain", type=int, default=128)
-    p.add_argument("--learning_iter", type=int, default=400)
-    p.add_argument("--eval_iter", type=int, default=100)
-    p.add_argument("--alpha", type=float, default=0.95)
-    p.add_argument("--anneal_iter", type=int, default=200)
-    p.add_argument("--num_anneal_temp", type=int, default=200)
-    p.add_argument("--non_linearity", type=str, default="relu")
-    p.add_argument("--hidden_x", type=int, nargs="+", default=[128, 128])
-    p.add_argument("--hidden_t", type=int, nargs="+", default=[128, 128])
-    p.add_argument("--hidden_xt", type=int, nargs="+", default=[128, 128])
-    p.add_argument("--step_size", type=float, default=0.2)
-    p.add_argument("--learning_rate", type=float, default=1e-3)
-    p.add_argument("--weight_decay", type=float, default=0.0001)
-    p.add_argument("--adam_beta1", type=float, default=0.9)
-    p.add_argument("--adam_beta2", type=float, default=0.999)
-    p.add_argument("--adam_epsilon", type=float, default=1e-8)
-    p.add_argument("--gradient_clip", type=float, default=1.0)
-    p.add_argument("--warmup_steps", type=int, default=0)
-    p.add_argument("--rtol", type=float, default=1e-5)
-    p.add_argument("--atol", type=float, default=1e-5)
-    p.add_argument("--mxstep", type=float, default=1_000)
-    p.add_argument("--lim", type=float, nargs=2, default=[-16, 16])
-    p.add_argument("--log_every", type=int, default=100)
+    p = argparse.ArgumentParser(description="Markovian flow matching on the B200 hot path (reference CLI)")
+    for name, typ, default in _SCALARS:
+        p.add_argument(f"--{name}", type=typ, default=default)
+    for name, default in _SWITCHES.items():
+        p.add_argument(f"--{name}", dest=name, action="store_true")
+    p.set_defaults(**_SWITCHES)
+    for name, typ, nargs, default in _LISTS:
+        p.add_argument(f"--{name}", type=typ, nargs=nargs, default=default)
     return p
 
 
