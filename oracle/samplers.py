@@ -161,12 +161,52 @@ def indep_flow_mh_step(keys, state, target, flow: Flow, ref, beta=1.0, stats=Non
     return new, MALAInfo(acc_prob, acc, xp, np.zeros(N, dt))
 
 
+def cis_flow_step(keys, state, target, flow: Flow, ref, n_is, beta=1.0, stats=None):
+    """conditional_importance_sampling (exe_flow_matching.py:280-296), vmapped over chains.  Per chain: pull the current
+    state back (its weight), push n_is fresh reference samples (each with its own probe key), draw ONE index from the
+    n_is + 1 normalised weights with jax.random.choice(key_choice, n_is + 1, p=norm_weights) - a scalar draw: one uniform,
+    r = p_cuml[-1] * (1 - u), searchsorted.  The gradient of an accepted sample is NOT recomputed (as coded: the new state
+    keeps prev_state.logdensity_grad).  Not yet built on the device: this is the round-2 oracle."""
+    from . import resample as R
+    x, l, g = state
+    dt = x.dtype
+    N, d = x.shape
+    rdt = np.dtype(flow.rng_dtype or dt)
+    key_sample, key_hutch_prev, key_hutch, key_choice = _split4(keys)
+    u_prev, vol_prev = flow.inverse_and_logdet(key_hutch_prev, x)
+    with np.errstate(over="ignore", invalid="ignore"):
+        prev_w = np.exp(l - ref.logprob(u_prev) - vol_prev)
+    new_x, new_l = x.copy(), l.copy()
+    acc = np.zeros(N, bool); rate = np.zeros(N, dt); prop = x.copy(); wsel = np.zeros(N, dt)
+    for n in range(N):                                   # the reference vmaps this body over chains
+        ks = tf.split(key_sample[n], n_is)
+        refs = ref.sample(ks, rdt).astype(dt)
+        kh = tf.split(key_hutch[n], n_is)
+        samples, vols = flow.transform_and_logdet(kh, refs)
+        ld = target.logprob(samples, beta)
+        with np.errstate(over="ignore", invalid="ignore"):
+            w = np.exp(ld - ref.logprob(refs) - vols)
+        tot = prev_w[n] + w.sum()
+        norm = np.concatenate([[prev_w[n]], w]) / tot
+        idx, _ = R.choice_indices(key_choice[n], n_is + 1, 1, norm.astype(rdt), rdt)
+        c = int(min(idx[0], n_is))
+        rate[n] = wsel[n] = norm[c]
+        if c > 0:
+            acc[n] = True
+            new_x[n], new_l[n], prop[n] = samples[c - 1], ld[c - 1], samples[c - 1]
+    if stats is not None:
+        stats.update(prev_weight=prev_w)
+    return MALAState(new_x, new_l, g.copy()), MALAInfo(rate, acc, prop, wsel)
+
+
 def train_data_generator(rng_key, states, count, target, flow, step_size, mcmc_per_flow_steps,
                          beta=1.0, num_importance_samples=0, ref=None):
     """exe_flow_matching.py:300-314 (integer mcmc_per_flow_steps >= 1 branch)."""
     N = states.position.shape[0]
     keys = tf.split(rng_key, N)
     if count % (int(mcmc_per_flow_steps) + 1) == 0:
+        if num_importance_samples > 0:
+            return cis_flow_step(keys, states, target, flow, ref, num_importance_samples, beta)
         if num_importance_samples < 0:
             return indep_flow_mh_step(keys, states, target, flow, ref, beta)
         return rw_flow_mh_step(keys, states, target, flow, beta)

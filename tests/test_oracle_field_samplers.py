@@ -198,3 +198,35 @@ def test_tempering_beta_bisection():
     flat = rng.standard_normal(512) * 1e-3
     b = OO.tempering_beta(0.25, flat, alpha, dtype=np.float64)
     assert abs(b - (1.0 - 2.0 ** -30 * 0.75)) < 1e-12
+
+
+def test_cis_flow_step_as_coded():
+    """conditional_importance_sampling (:280-296): weights, one categorical draw per chain, gradient carried over unchanged."""
+    params, omega, rng = _small(seed=6, d=2, head=0.2)
+    t, ref = OT.four_mode(), OT.IndepGaussian(2)
+    flow = OS.Flow(params, omega, t, hutch=False)
+    x = 8.0 + rng.standard_normal((4, 2))
+    st = OS.mala_init(x, t)
+    keys = tf.split(tf.PRNGKey(3), 4)
+    K = 5
+    stats = {}
+    new, info = OS.cis_flow_step(keys, st, t, flow, ref, K, stats=stats)
+    for n in range(4):
+        k_sample, k_hp, k_h, k_choice = tf.split(keys[n], 4)
+        u_prev, vol_prev = flow.inverse_and_logdet(None, x[n:n + 1])
+        pw = np.exp(st.logdensity[n] - ref.logprob(u_prev)[0] - vol_prev[0])
+        assert np.isclose(stats["prev_weight"][n], pw, rtol=1e-6)        # batched vs single-chain solve: BLAS summation order
+        refs = np.stack([tf.normal(k, (2,), np.float64) for k in tf.split(k_sample, K)])
+        samples, vols = flow.transform_and_logdet(None, refs)
+        w = np.exp(t.logprob(samples) - ref.logprob(refs) - vols)
+        norm = np.concatenate([[pw], w]) / (pw + w.sum())
+        u = float(tf.uniform(k_choice, (1,), np.float64)[0])
+        c = int(np.searchsorted(np.cumsum(norm), np.cumsum(norm)[-1] * (1 - u)))
+        assert bool(info.is_accepted[n]) == (c > 0)
+        assert np.isclose(info.acceptance_rate[n], norm[c], rtol=1e-6) and info.proposed_weight[n] == info.acceptance_rate[n]
+        expect = samples[c - 1] if c > 0 else x[n]
+        assert np.allclose(new.position[n], expect, atol=1e-9) and np.allclose(info.proposed_position[n], expect, atol=1e-9)
+    assert np.array_equal(new.logdensity_grad, st.logdensity_grad)        # as coded: not recomputed
+    # dispatch: num_importance_samples > 0 selects it on flow iterations
+    _, i_f = OS.train_data_generator(tf.PRNGKey(3), st, 3, t, flow, 0.2, 2, num_importance_samples=K, ref=ref)
+    assert (i_f.proposed_weight == i_f.acceptance_rate).all()
