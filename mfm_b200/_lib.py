@@ -58,6 +58,7 @@ SIGNATURES = {
     "mfm_set_gemm_raw_hi": (None, [C.c_int]),
     "mfm_set_gemm_cross_bf16": (None, [C.c_int]),
     "mfm_set_gemm_streamk": (None, [C.c_int]),
+    "mfm_set_gemm_split16": (None, [C.c_int]),
     "mfm_gemm_presplit": (C.c_int, [c_f32p, c_f32p, C.c_longlong, _S]),
     "mfm_gemm_register_mirror": (None, [c_f32p, C.c_longlong, c_f32p]),
     "mfm_debug_gemm_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int]),

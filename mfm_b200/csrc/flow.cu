@@ -145,7 +145,30 @@ __global__ void presplit_kernel(const float4* __restrict__ src, uint4* __restric
     dst[2 * g] = make_uint4(pack(a.x, a.y), pack(a.z, a.w), pack(c.x, c.y), pack(c.z, c.w));
     dst[2 * g + 1] = make_uint4(pack(rest(a.x), rest(a.y)), pack(rest(a.z), rest(a.w)), pack(rest(c.x), rest(c.y)), pack(rest(c.z), rest(c.w)));
 }
+// split16 layout of the experimental kernel (gemm_tcgen05_split16.cuh): 16 consecutive floats -> 16 hi | 16 lo bf16 parts
+__global__ void presplit16_kernel(const float4* __restrict__ src, uint4* __restrict__ dst, long long n16) {
+    const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (g >= n16) return;
+    float4 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = __ldg(src + 4 * g + j);
+    auto pack = [](float first, float second) { uint32_t r; asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(second), "f"(first)); return r; };
+    uint32_t hp[8], lp[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        hp[2 * j] = pack(v[j].x, v[j].y); hp[2 * j + 1] = pack(v[j].z, v[j].w);
+        lp[2 * j] = pack(v[j].x - __uint_as_float(hp[2 * j] << 16), v[j].y - __uint_as_float(hp[2 * j] & 0xFFFF0000u));
+        lp[2 * j + 1] = pack(v[j].z - __uint_as_float(hp[2 * j + 1] << 16), v[j].w - __uint_as_float(hp[2 * j + 1] & 0xFFFF0000u));
+    }
+    dst[4 * g] = make_uint4(hp[0], hp[1], hp[2], hp[3]); dst[4 * g + 1] = make_uint4(hp[4], hp[5], hp[6], hp[7]);
+    dst[4 * g + 2] = make_uint4(lp[0], lp[1], lp[2], lp[3]); dst[4 * g + 3] = make_uint4(lp[4], lp[5], lp[6], lp[7]);
+}
 int presplit_weights(const float* src, float* dst, long long n_floats, cudaStream_t st) {
+    if (tc2s::gemm_split16() && n_floats % 16 == 0) {
+        presplit16_kernel<<<ceil_div(n_floats / 16, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(src), reinterpret_cast<uint4*>(dst), n_floats / 16);
+        MFM_LAUNCH_CHECK();
+        return MFM_OK;
+    }
     const long long n8 = n_floats / 8;
     presplit_kernel<<<ceil_div(n8, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(src), reinterpret_cast<uint4*>(dst), n8);
     MFM_LAUNCH_CHECK();

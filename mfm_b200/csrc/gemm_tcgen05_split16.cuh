@@ -1,0 +1,458 @@
+// EXPERIMENTAL (opt-in, MFM_GEMM_SPLIT=bf16x3 / mfm_set_gemm_split16; never the default): "split16" variant of the
+// persistent CTA-pair dense-layer kernel - written at the end of round 1 WITHOUT a GPU run (the round's GPU budget was spent);
+// it compiles for sm_100a, its arithmetic is emulated in scripts/emulation_error_study.py, its test is
+// tests/test_gpu_gemm.py::test_gemm_split16 (skipped unless MFM_TEST_SPLIT16=1).  See DESIGN.md section 9, item 1.
+//
+// Arithmetic: both operands as two 2-byte parts, a = hi + lo with hi = rn(a), lo = rn(a - hi) (bf16; fp16 needs a
+// per-tensor scale and is only a template parameter so far), product = hi.hi' + hi.lo' + lo.hi' : THREE kind::f16 K = 16
+// MMAs per 16 k-values instead of today's two tf32 + two bf16 (4 slots) - 25 % fewer tensor-core slots, operand rounding
+// error 5e-6 of max |C| on the pines layers (today 1.3e-6): inside the 1e-4 parity bar, meant for the FM update.
+//
+// Layout ("split16"): every 16 consecutive fp32 of a K-major row are replaced, in the same 64 bytes, by 16 hi parts followed
+// by 16 lo parts.  A 32-wide k-block is still a 128-byte SWIZZLE_128B row [hi 0..15 | lo 0..15 | hi 16..31 | lo 16..31], so
+// TMA maps, row pitch and the +32-byte descriptor stepping of gemm_tcgen05_persist.cuh apply unchanged.  B (weights) arrives
+// pre-split from global memory (presplit16_kernel, once per parameter update); A is loaded raw and split IN PLACE by the
+// splitter warps (one 64-byte group per thread per k-block: half of today's shared-memory traffic, no cross region).
+// A stage is therefore 32 KB (A 16 KB + half of B 16 KB) and the ring has 6 stages in the same 192 KB.
+// Everything else - work list incl. stream-K, TMEM double buffering, 8 + 8 epilogue warps - is the persistent kernel's.
+#pragma once
+#include <cuda_fp16.h>
+#include "gemm_tcgen05_persist.cuh"
+
+namespace mfm {
+namespace tc2s {
+
+using namespace tc2p;       // tile constants, Sched / PairWork, Maps3, barrier + MMA helpers
+
+constexpr int S_STAGES = 6, S_STAGE_BYTES = HI_BYTES;          // 6 x 32 KB
+constexpr int S_NBARS = 3 * S_STAGES + 4;
+constexpr int S_SMEM_BYTES = S_STAGES * S_STAGE_BYTES + EPI_STG_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+static_assert(S_NBARS * 8 + 8 + 64 <= 256, "barrier area: barriers, TMEM slot, PairWork");
+static_assert(S_STAGE_BYTES == EPI_WARPS * 4096, "the helpers' staging is exactly ring stage 0");
+
+template <bool FP16> __device__ __forceinline__ uint32_t pack2(float first, float second) {   // `first` lands first in memory
+    uint32_t r;
+    if (FP16) asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(second), "f"(first));
+    else      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(second), "f"(first));
+    return r;
+}
+template <bool FP16> __device__ __forceinline__ float unpack_lo(uint32_t p) {
+    if (FP16) return __half2float(__ushort_as_half((unsigned short)(p & 0xFFFFu)));
+    return __uint_as_float(p << 16);
+}
+template <bool FP16> __device__ __forceinline__ float unpack_hi(uint32_t p) {
+    if (FP16) return __half2float(__ushort_as_half((unsigned short)(p >> 16)));
+    return __uint_as_float(p & 0xFFFF0000u);
+}
+
+template <bool FP16, class Epi>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+gemm_tc2s_kernel(const __grid_constant__ Maps3 maps, GemmShape p, Epi epi, long long* tl, float* sk_ws, unsigned* sk_flags, unsigned sk_epoch) {
+#ifdef MFM_TC2_TIMELINE
+    // tuning aid: SM clock at 4 events of the first 16 tiles of pair 0's leader (MMA start / accumulator
+    // committed / epilogue start / epilogue end)
+#ifndef MFM_TL_PAIR
+#define MFM_TL_PAIR 0
+#endif
+#define TC2P_MARK(tile, ev) do { if (tl && blockIdx.x == 2 * MFM_TL_PAIR && (tile) < 12 && lane == 0) tl[(tile) * 4 + (ev)] = clock64(); } while (0)
+#define TC2P_MARKX(slot) do { if (tl && blockIdx.x == 2 * MFM_TL_PAIR && lane == 0) tl[slot] = clock64(); } while (0)
+#else
+#define TC2P_MARK(tile, ev) do { } while (0)
+#define TC2P_MARKX(slot) do { } while (0)
+#endif
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* stg_base = smem + S_STAGES * S_STAGE_BYTES;
+    uint64_t* bars = (uint64_t*)(stg_base + EPI_STG_BYTES);
+    uint64_t* full = bars;                      // own TMA landed                      (local)
+    uint64_t* split = bars + S_STAGES;            // lo tiles of BOTH CTAs ready          (leader's copy is used)
+    uint64_t* empty = bars + 2 * S_STAGES;        // MMAs done reading the stage          (multicast commit)
+    uint64_t* acc_full = bars + 3 * S_STAGES;     // [2] accumulator buffer complete      (multicast commit)
+    uint64_t* acc_empty = bars + 3 * S_STAGES + 2;// [2] buffer drained by BOTH CTAs      (leader's copy is used)
+    uint32_t* tmem_slot = (uint32_t*)(bars + S_NBARS);
+    volatile PairWork* work = (volatile PairWork*)(bars + S_NBARS + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int M = p.n_rows_dev ? min(*p.n_rows_dev, p.M) : p.M;
+    const Tiles T = make_tiles(M, p.N, p.K, p.k_split);
+    if (T.total == 0) return;                   // uniform over the grid
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+#ifdef MFM_TC2_TIMELINE
+    if (tl && blockIdx.x == 2 * MFM_TL_PAIR && threadIdx.x == 0) tl[62] = clock64();
+#endif
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.b) : "memory");
+        for (int s = 0; s < S_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&split[s], 2 * SPLIT_WARPS); mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 2 * EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    if (warp == 3 && lane == 0) {
+        const Sched S = make_sched(T.total, n_pairs, pair, p.K, p.k_split, sk_ws != nullptr);
+        Item head, last;
+        const int have = S.tail(head, last);
+        if (have & 1) { volatile Item* d = &work->head; d->tile = head.tile; d->kb0 = head.kb0; d->kb1 = head.kb1; d->kind = head.kind; d->c_first = 0; d->c_count = 0; }
+        if (have & 2) { volatile Item* d = &work->last; d->tile = last.tile; d->kb0 = last.kb0; d->kb1 = last.kb1; d->kind = last.kind; d->c_first = last.c_first; d->c_count = last.c_count; }
+        work->n_head = have & 1; work->n_tail = (have & 1) + ((have >> 1) & 1); work->n_items = (have & 1) + ((have >> 1) & 1) + S.whole();
+        work->fix = ((have & 2) && last.kind == ITEM_FINISH) ? 1 : 0;
+    }
+    __syncwarp();
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    // item i of this pair -> tile and k-block range (the list stays in shared memory: the epilogue has no registers to spare)
+    auto item_at = [&](int i, int& tile, int& kb0, int& kb1) {
+        const int j = i - work->n_tail;
+        if (j >= 0) { tile = pair + j * n_pairs; kb0 = 0; kb1 = (p.K + BK - 1) / BK; }
+        else { volatile const Item* w = i < work->n_head ? &work->head : &work->last; tile = w->tile; kb0 = w->kb0; kb1 = w->kb1; }
+    };
+
+    // tile t -> (z, row tile, column tile); column tiles vary fastest so concurrent pairs share A rows
+    auto tile_origin = [&](int t, int& m0p, int& n0, int& kz0, int& KT, int& neff, int& z) {
+        const int per_z = T.m_tiles * T.n_tiles;
+        z = t / per_z;
+        const int r = t - z * per_z;
+        m0p = (r / T.n_tiles) * (2 * BM);
+        n0 = (r % T.n_tiles) * BN;
+        kz0 = p.k_split > 0 ? z * p.k_split : 0;
+        const int Kend = p.k_split > 0 ? min(p.K, kz0 + p.k_split) : p.K;
+        KT = (Kend - kz0 + BK - 1) / BK;
+        const int nrem = p.N - n0;
+        neff = nrem >= BN ? BN : ((nrem + 63) / 64) * 64;
+    };
+
+    if (warp == 0) {
+        // ---------------- TMA producer (both CTAs) ----------------
+        if (lane == 0) {
+            uint32_t g = 0;                     // k-blocks issued so far (ring position)
+            for (int idx = 0; idx < work->n_items; ++idx) {
+                int tile, kt0, kt1, m0p, n0, kz0, KT, neff, z;
+                item_at(idx, tile, kt0, kt1);
+                tile_origin(tile, m0p, n0, kz0, KT, neff, z);
+                const int m0 = m0p + (int)rank * BM;
+                const int nb0 = n0 + (int)rank * (neff / 2);
+                if (p.k_split > 0) { kt0 = 0; kt1 = KT; }
+                for (int kt = kt0; kt < kt1; ++kt, ++g) {
+                    const uint32_t s = g % S_STAGES, ph = (g / S_STAGES) & 1;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    uint8_t* st = smem + s * S_STAGE_BYTES;
+                    mbar_expect_tx(&full[s], HI_BYTES);
+                    const int k0 = kz0 + kt * BK;
+                    tma_load_2d(st, &maps.a, &full[s], k0, m0);                    // raw fp32 rows of A (split in place below)
+                    tma_load_2d(st + A_BYTES, &maps.b, &full[s], k0, nb0);         // B half-tile, pre-split [16 hi | 16 lo] per 16 k
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------- MMA issuer (leader CTA only) ----------------
+        if (rank == 0 && lane == 0) {
+            uint32_t g = 0, i = 0;
+            for (; (int)i < work->n_items; ++i) {
+                int tile, kt0, kt1, m0p, n0, kz0, KT, neff, z;
+                item_at((int)i, tile, kt0, kt1);
+                tile_origin(tile, m0p, n0, kz0, KT, neff, z);
+                if (p.k_split > 0) { kt0 = 0; kt1 = KT; }
+                const uint32_t b = i & 1, u = i >> 1;
+                // kind::f16: D = f32, A = B = bf16 (or fp16), both K-major, M = 256 per pair, N = neff
+                const uint32_t idesc16 = (1u << 4) | ((FP16 ? 0u : 1u) << 7) | ((FP16 ? 0u : 1u) << 10) | ((uint32_t)(neff >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+                const uint32_t acc = tmem_base + b * BN;
+                mbar_wait(&acc_empty[b], (u & 1) ^ 1);          // both CTAs have drained this buffer (tile i-2)
+                                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                TC2P_MARK(i, 0);
+                for (int kt = kt0; kt < kt1; ++kt, ++g) {
+                    const uint32_t s = g % S_STAGES, ph = (g / S_STAGES) & 1;
+                    mbar_wait(&split[s], ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_t = smem_u32(smem + s * S_STAGE_BYTES), b_t = a_t + A_BYTES;
+                    // a 128-byte row of either tile = [hi(k 0..15) | lo(k 0..15) | hi(k 16..31) | lo(k 16..31)], 32 bytes each:
+                    // per 16 k-values three K = 16 MMAs  hi.hi' + hi.lo' + lo.hi'
+#pragma unroll
+                    for (int gq = 0; gq < 2; ++gq) {
+                        const uint64_t dah = make_desc(a_t + gq * 64, 16, 1024, 2), dal = make_desc(a_t + gq * 64 + 32, 16, 1024, 2);
+                        const uint64_t dbh = make_desc(b_t + gq * 64, 16, 1024, 2), dbl = make_desc(b_t + gq * 64 + 32, 16, 1024, 2);
+                        mma_bf16_ss_2sm(acc, dah, dbh, idesc16, ((kt - kt0) | gq) != 0);
+                        mma_bf16_ss_2sm(acc, dah, dbl, idesc16, 1);
+                        mma_bf16_ss_2sm(acc, dal, dbh, idesc16, 1);
+                    }
+                    mma_commit_2sm(&empty[s]);
+                }
+                mma_commit_2sm(&acc_full[b]);
+                TC2P_MARK(i, 1);
+            }
+        }
+    } else if (warp >= SPLIT_WARP0 && warp < EPI_WARP0) {
+        // ---------------- splitters (both CTAs) ----------------
+        const int tix = threadIdx.x - SPLIT_WARP0 * 32;
+        uint32_t g = 0;
+        for (int idx = 0; idx < work->n_items; ++idx) {
+            int tile, kb0, kb1;
+            item_at(idx, tile, kb0, kb1);
+            int n_kb = kb1 - kb0;
+            if (p.k_split > 0) { int m0p, n0, kz0, KT, neff, z; tile_origin(tile, m0p, n0, kz0, KT, neff, z); n_kb = KT; }
+            for (int kt = 0; kt < n_kb; ++kt, ++g) {
+                const uint32_t s = g % S_STAGES, ph = (g / S_STAGES) & 1;
+                mbar_wait(&full[s], ph);
+                // in-place split of the A tile: thread (row r, half hq) owns the 16 floats k = 16 hq .. 16 hq + 15 of row r,
+                // i.e. logical 16-byte chunks 4 hq .. 4 hq + 3 (physical chunk = logical ^ (r & 7), SWIZZLE_128B), and replaces
+                // them by 16 hi | 16 lo two-byte parts (hi = rn(a), lo = rn(a - hi)).  256 threads x 64 bytes = the 16 KB tile.
+                {
+                    const uint32_t r = (uint32_t)tix >> 1, hq = (uint32_t)tix & 1u;
+                    const uint32_t rowa = smem_u32(smem + s * S_STAGE_BYTES) + r * 128u;
+                    float4 v[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[j].x), "=f"(v[j].y), "=f"(v[j].z), "=f"(v[j].w)
+                                     : "r"(rowa + (((4u * hq + (uint32_t)j) ^ (r & 7u)) << 4)));
+                    uint32_t hp[8], lp[8];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        hp[2 * j] = pack2<FP16>(v[j].x, v[j].y); hp[2 * j + 1] = pack2<FP16>(v[j].z, v[j].w);
+                        lp[2 * j] = pack2<FP16>(v[j].x - unpack_lo<FP16>(hp[2 * j]), v[j].y - unpack_hi<FP16>(hp[2 * j]));
+                        lp[2 * j + 1] = pack2<FP16>(v[j].z - unpack_lo<FP16>(hp[2 * j + 1]), v[j].w - unpack_hi<FP16>(hp[2 * j + 1]));
+                    }
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowa + (((4u * hq + (uint32_t)j) ^ (r & 7u)) << 4)),
+                                     "r"(hp[4 * j]), "r"(hp[4 * j + 1]), "r"(hp[4 * j + 2]), "r"(hp[4 * j + 3]) : "memory");
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowa + (((4u * hq + 2u + (uint32_t)j) ^ (r & 7u)) << 4)),
+                                     "r"(lp[4 * j]), "r"(lp[4 * j + 1]), "r"(lp[4 * j + 2]), "r"(lp[4 * j + 3]) : "memory");
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor core
+                __syncwarp();
+                if (lane == 0) mbar_arrive_remote(&split[s], 0);
+            }
+        }
+    }
+    if (warp >= SPLIT_WARP0) {
+        // ---------------- epilogue (each CTA drains its own 128 TMEM lanes) ----------------
+        // Epilogue warps 12-19: (TMEM lane quadrant, column half) = 4 chunks of 32 columns per tile.  The
+        // splitter warps 4-11 have nothing left to do once the pair's LAST tile is split, so they take
+        // half of that tile's chunks: its epilogue is the only one no main loop hides.
+        const bool helper = warp < EPI_WARP0;
+        const int ew = helper ? warp - SPLIT_WARP0 : warp - EPI_WARP0;   // 0..7
+        const int quad = ew & 3;                      // == warp & 3: the TMEM lane quadrant this warp may access
+        const int chalf = ew >> 2;                    // column half of the tile
+        // staging: the epilogue warps' own buffers; helpers use ring stage 0 (free: every MMA has completed)
+        const uint32_t stg = helper ? smem_u32(smem) + (uint32_t)ew * 4096u : smem_u32(stg_base) + (uint32_t)ew * 4096u;
+        const int rsub = lane >> 3, cpiece = (lane & 7) * 4;
+        constexpr int RB = sizeof(typename Epi::Row4) > 36 ? 2 : 4;   // steps whose global reads are issued together (register budget: 102)
+        if (work->n_head != 0 && (!helper || work->n_items == 1)) {
+            // ---- stream-K contribution (item 0, accumulator buffer 0): dump to this pair's slot, flag per chunk ----
+            int tile, kb0_, kb1_, m0p, n0, kz0, KT, neff, z;
+            item_at(0, tile, kb0_, kb1_);
+            tile_origin(tile, m0p, n0, kz0, KT, neff, z);
+            const int n_chunks = min(BN / 32, (p.N - n0 + 31) / 32);
+            int cc_begin = chalf * 4, cc_end = min(n_chunks, chalf * 4 + 4);
+            if (work->n_items == 1) { if (helper) cc_begin = min(cc_begin + 2, cc_end); else cc_end = min(cc_end, cc_begin + 2); }
+            mbar_wait(&acc_full[0], 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (ew == 0 && !helper) TC2P_MARKX(48);
+            if (cc_begin >= cc_end && !helper) {
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive_remote(&acc_empty[0], 0);
+            }
+#pragma unroll 1
+            for (int cc = cc_begin; cc < cc_end; ++cc) {
+                uint32_t r[32];
+                tmem_ld32_nowait(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(cc * 32), r);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (cc == cc_end - 1 && !helper) {
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_remote(&acc_empty[0], 0);
+                }
+                const uint32_t dst = stg + (uint32_t)lane * 128u;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (uint32_t)((j ^ (lane & 7)) << 4)), "f"(__uint_as_float(r[4 * j])),
+                                 "f"(__uint_as_float(r[4 * j + 1])), "f"(__uint_as_float(r[4 * j + 2])), "f"(__uint_as_float(r[4 * j + 3])) : "memory");
+                __syncwarp();
+                // this warp's 32 x 32 chunk goes to rows rank*128 + quad*32 .., columns cc*32 .. of the slot, moved like C
+                // itself (4 rows x 128 contiguous bytes per instruction)
+                float* dstp = sk_ws + (size_t)pair * SK_SLOT_FLOATS + (size_t)((int)rank * BM + quad * 32 + rsub) * BN + cc * 32 + cpiece;
+                const uint32_t sa = stg + (uint32_t)rsub * 128u;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    float4 v;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                                 : "r"(sa + (uint32_t)k * 512u + (uint32_t)(((lane & 7) ^ ((k * 4 + rsub) & 7)) << 4)));
+                    __stcg(reinterpret_cast<float4*>(dstp + (size_t)k * 4 * BN), v);
+                }
+            }
+            // one release for the warp's chunks: every lane's stores -> __syncwarp -> lane 0's fence -> the flags
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence();
+                for (int cc = cc_begin; cc < cc_end; ++cc)
+                    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(sk_flags + (size_t)pair * SK_SLOT_FLAGS + rank * 32u + (uint32_t)quad * 8u + (uint32_t)cc),
+                                 "r"(sk_epoch) : "memory");
+            }
+        }
+        if (ew == 0 && !helper) TC2P_MARKX(49);
+        // the finishing part and the whole tiles (helpers: the last item only, unless that was the contribution)
+        uint32_t i = (uint32_t)(helper ? max(work->n_items - 1, work->n_head) : work->n_head);
+        for (; (int)i < work->n_items; ++i) {
+            int tile, kb0_, kb1_, m0p, n0, kz0, KT, neff, z;
+            item_at((int)i, tile, kb0_, kb1_);
+            tile_origin(tile, m0p, n0, kz0, KT, neff, z);
+            const uint32_t b = i & 1, u = i >> 1;
+            const bool last = (int)i == work->n_items - 1;
+            const bool fix = work->fix != 0 && (int)i == work->n_head;      // stream-K FINISH item: add the earlier k-ranges
+            Epi e = epi;
+            if (p.k_split > 0) e.at_z(z);
+            const int row_base = m0p + (int)rank * BM + quad * 32;
+            const int n_chunks = min(BN / 32, (p.N - n0 + 31) / 32);     // chunks of the whole tile
+            int cc_begin = chalf * 4, cc_end = min(n_chunks, chalf * 4 + 4);
+            if (last) { if (helper) cc_begin = min(cc_begin + 2, cc_end); else cc_end = min(cc_end, cc_begin + 2); }
+            mbar_wait(&acc_full[b], u & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (ew == 0 && !helper) TC2P_MARK(i, 2);
+            float rs[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) rs[k] = 0.0f;
+            if (cc_begin >= cc_end && !helper) {
+                // nothing to drain in this column half (edge tile): still release the buffer
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive_remote(&acc_empty[b], 0);
+            }
+#pragma unroll 1
+            for (int cc = cc_begin; cc < cc_end; ++cc) {
+                const int col0 = cc * 32;
+                uint32_t r[32];
+                tmem_ld32_nowait(tmem_base + ((uint32_t)(quad * 32) << 16) + b * BN + (uint32_t)col0, r);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (cc == cc_end - 1 && !helper) {
+                    // this warp's last chunk has left TMEM: hand the buffer back to the MMA issuer (on the
+                    // pair's last tile nobody waits for it any more, so the helpers' chunks need no arrive)
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_remote(&acc_empty[b], 0);
+                }
+                const uint32_t dst = stg + (uint32_t)lane * 128u;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (uint32_t)((j ^ (lane & 7)) << 4)), "f"(__uint_as_float(r[4 * j])),
+                                 "f"(__uint_as_float(r[4 * j + 1])), "f"(__uint_as_float(r[4 * j + 2])), "f"(__uint_as_float(r[4 * j + 3])) : "memory");
+                __syncwarp();
+                if (fix) {
+                    // stream-K: add this chunk of the contributing pairs' slots into the staged accumulator, moved like C itself
+                    // (4 rows x 128 contiguous bytes per instruction; each lane updates exactly the pieces it reads back below)
+                    const int c_first = work->last.c_first, c_count = work->last.c_count;
+                    const uint32_t fidx = rank * 32u + (uint32_t)quad * 8u + (uint32_t)cc;
+                    if (lane < c_count) {                     // one lane per contributing pair
+                        const unsigned* fl = sk_flags + (size_t)(c_first + lane) * SK_SLOT_FLAGS + fidx;
+                        unsigned seen;
+                        do {
+                            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(fl) : "memory");
+                        } while (seen != sk_epoch);
+                    }
+                    __syncwarp();
+                    const size_t toff = (size_t)((int)rank * BM + quad * 32 + rsub) * BN + col0 + cpiece;
+                    const uint32_t sa = stg + (uint32_t)rsub * 128u;
+#pragma unroll 1
+                    for (int c = 0; c < c_count; ++c) {
+                        const float* srcp = sk_ws + (size_t)(c_first + c) * SK_SLOT_FLOATS + toff;
+                        float4 v[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) v[k] = __ldcg(reinterpret_cast<const float4*>(srcp + (size_t)k * 4 * BN));
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const uint32_t ad = sa + (uint32_t)k * 512u + (uint32_t)(((lane & 7) ^ ((k * 4 + rsub) & 7)) << 4);
+                            float4 w;
+                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w.x), "=f"(w.y), "=f"(w.z), "=f"(w.w) : "r"(ad));
+                            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(ad), "f"(w.x + v[k].x), "f"(w.y + v[k].y), "f"(w.z + v[k].z), "f"(w.w + v[k].w) : "memory");
+                        }
+                    }
+                }
+                const int col = n0 + col0 + cpiece;           // N % 4 == 0: the four columns are valid together
+                const bool cvalid = col < p.N;
+                typename Epi::Col4 ca;
+                if (cvalid) ca = e.load_col4(col);
+#pragma unroll
+                for (int it0 = 0; it0 < 8; it0 += RB) {
+                    typename Epi::Row4 ra[RB];
+                    float4 acc[RB];
+#pragma unroll
+                    for (int k = 0; k < RB; ++k) {
+                        const int row = row_base + (it0 + k) * 4 + rsub;
+                        if (row < M && cvalid) ra[k] = e.load_row4(row, col);
+                    }
+#pragma unroll
+                    for (int k = 0; k < RB; ++k)
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(acc[k].x), "=f"(acc[k].y), "=f"(acc[k].z), "=f"(acc[k].w)
+                                     : "r"(stg + (uint32_t)((it0 + k) * 4 + rsub) * 128u + (uint32_t)((((lane & 7) ^ (((it0 + k) * 4 + rsub) & 7))) << 4)));
+#pragma unroll
+                    for (int k = 0; k < RB; ++k) {
+                        const int row = row_base + (it0 + k) * 4 + rsub;
+                        float c = 0.0f;
+                        if (row < M && cvalid) c = e.apply4(row, col, acc[k], ca, ra[k]);
+                        if (Epi::kRowSum) {
+                            c += __shfl_xor_sync(0xffffffffu, c, 4); c += __shfl_xor_sync(0xffffffffu, c, 2);
+                            c += __shfl_xor_sync(0xffffffffu, c, 1);
+                            rs[it0 + k] += c;               // 32-column sums; pairs of chunks make the 64-column groups
+                        }
+                    }
+                }
+                if (Epi::kRowSum && ((cc & 1) || cc == cc_end - 1)) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int row = row_base + k * 4 + rsub;
+                        if ((lane & 7) == 0 && row < M) e.row_partial(row, (n0 + (cc & ~1) * 32) / GBN, rs[k]);
+                        rs[k] = 0.0f;
+                    }
+                }
+                __syncwarp();                                 // staging is reused by the next chunk
+            }
+            if (ew == 0 && !helper) TC2P_MARK(i, 3);
+        }
+    }
+    __syncwarp();
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();                     // the peer's shared memory / TMEM / barriers stay alive until both are done
+#ifdef MFM_TC2_TIMELINE
+    if (tl && blockIdx.x == 2 * MFM_TL_PAIR && threadIdx.x == 0) tl[63] = clock64();
+#endif
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---- host side ----------------------------------------------------------------------------------
+int gemm_split16();                         // 1: route K-major x K-major EpiStd layers with a registered split16 mirror here (rng.cu)
+
+template <class Epi>
+inline cudaError_t launch(const GemmShape& p, const Epi& epi, const float* b_split16, cudaStream_t st) {
+    Maps3 maps;
+    bool ok = tc::make_map_kmajor(&maps.a, p.A, p.lda, p.M, p.K, BM) && tc::make_map_kmajor(&maps.b, b_split16, p.ldb, p.N, p.K, BNH);
+    if (!ok) return cudaErrorInvalidValue;
+    maps.bx = maps.b;
+    auto kern = gemm_tc2s_kernel<false, Epi>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S_SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const Tiles T = make_tiles(p.M, p.N, p.K, 0);
+    float* sk_ws = nullptr; unsigned* sk_flags = nullptr; unsigned sk_epoch = 0;
+    const int rem = T.total % sm_pairs();
+    const bool sk = (p.K + BK - 1) / BK >= SK_MAX_SPLIT * SK_MIN_KB && (p.n_rows_dev || (rem != 0 && rem * SK_MAX_SPLIT <= sm_pairs())) &&
+                    streamk_workspace(st, &sk_ws, &sk_flags, &sk_epoch);
+    const int pairs = (sk || T.total >= sm_pairs()) ? sm_pairs() : T.total;
+    kern<<<dim3(2 * pairs), THREADS, S_SMEM_BYTES, st>>>(maps, p, epi, tc2::gemm_timeline(), sk_ws, sk_flags, sk_epoch);
+    ++g_mfm_launches;
+    return cudaGetLastError();
+}
+
+}  // namespace tc2s
+}  // namespace mfm

@@ -307,7 +307,10 @@ struct EpiStd {
 #include "gemm_tcgen05.cuh"
 #include "gemm_tcgen05_2sm.cuh"
 #include "gemm_tcgen05_persist.cuh"
+#include "gemm_tcgen05_split16.cuh"
 namespace mfm {
+template <class Epi> struct Split16Epi { static constexpr bool value = false; };
+template <> struct Split16Epi<EpiStd> { static constexpr bool value = true; };     // the FM / forward dense layers only
 // 0 = auto, 1 = force mma.sync (env MFM_GEMM=mma), 2 = tcgen05 single-CTA only (env MFM_GEMM=tc1),
 // 3 = no persistent kernel: one-tile CTA-pair kernel with separate cross-term accumulators (env MFM_GEMM=tc2)
 int gemm_backend();
@@ -325,6 +328,14 @@ inline cudaError_t launch_gemm(const GemmShape& p, const Epi& epi, cudaStream_t 
         case 2:
             // persistent (epilogue overlapped with the next tile's MMAs) unless the reduction is split:
             // split-K tiles have long main loops (nothing to hide) and need the separate accumulators
+            if constexpr (A_KMAJOR && !B_NMAJOR && Split16Epi<Epi>::value) {
+                // experimental 3-slot operand split (off by default): needs the weight operand's split16 mirror
+                if (tc2s::gemm_split16() && gemm_backend() == 0 && p.k_split == 0 && p.K % 16 == 0 && p.ldb % 16 == 0 &&
+                    tc2p::eligible<A_KMAJOR, B_NMAJOR>(p, epi)) {
+                    const float* bx = tc2p::lookup_cross(p.B);
+                    if (bx && (reinterpret_cast<uintptr_t>(bx) & 63) == 0) return tc2s::launch<Epi>(p, epi, bx, st);
+                }
+            }
             if (gemm_backend() == 0 && p.k_split == 0 && tc2p::eligible<A_KMAJOR, B_NMAJOR>(p, epi))
                 return tc2p::launch<A_KMAJOR, B_NMAJOR, Epi>(p, epi, st);
             return tc2::launch<A_KMAJOR, B_NMAJOR, Epi>(p, epi, st);

@@ -46,6 +46,7 @@ const float* lookup_cross(const float* p) {
         if (p >= g_cross[i].base && p < g_cross[i].base + g_cross[i].n && ((p - g_cross[i].base) % 8) == 0) return g_cross[i].mirror + (p - g_cross[i].base);
     return nullptr;
 }
+static int g_split16 = -1;
 static int g_streamk = -1;
 constexpr int SK_SLOT_FLOATS = 256 * 256, SK_SLOT_FLAGS = 64;   // = gemm_tcgen05_persist.cuh (static_assert there)
 struct SkWs { cudaStream_t st; int dev; float* ws; unsigned* flags; unsigned epoch; };
@@ -76,6 +77,15 @@ bool streamk_workspace(cudaStream_t st, float** ws, unsigned** flags, unsigned* 
     *ws = w->ws; *flags = w->flags; *epoch = ++w->epoch;
     return true;
 }
+}   // namespace tc2p
+namespace tc2s {
+// EXPERIMENTAL split16 dense-layer kernel (gemm_tcgen05_split16.cuh): off unless MFM_GEMM_SPLIT=bf16x3 / mfm_set_gemm_split16(1)
+int gemm_split16() {
+    if (tc2p::g_split16 < 0) { const char* e = getenv("MFM_GEMM_SPLIT"); tc2p::g_split16 = (e && strcmp(e, "bf16x3") == 0) ? 1 : 0; }
+    return tc2p::g_split16;
+}
+}
+namespace tc2p {
 int sm_pairs() {
     static int pairs = 0;
     if (pairs == 0) {
@@ -97,6 +107,7 @@ int gemm_raw_hi() {
 extern "C" void mfm_set_gemm_raw_hi(int v) { mfm::tc2::g_raw_hi = v ? 1 : 0; }
 extern "C" void mfm_set_gemm_cross_bf16(int v) { mfm::tc2p::g_cross_bf16 = v ? 1 : 0; }
 extern "C" void mfm_set_gemm_streamk(int v) { mfm::tc2p::g_streamk = v ? 1 : 0; }
+extern "C" void mfm_set_gemm_split16(int v) { mfm::tc2p::g_split16 = v ? 1 : 0; }
 extern "C" void mfm_gemm_register_mirror(const float* base, long long n_floats, const float* mirror) {
     if (base && mirror && n_floats > 0) mfm::tc2p::register_cross(base, (size_t)n_floats, mirror); else mfm::tc2p::clear_cross();
 }
