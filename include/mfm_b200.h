@@ -104,7 +104,7 @@ void mfm_set_gemm_streamk(int enable);
 /* EXPERIMENTAL, off by default (environment variable MFM_GEMM_SPLIT=bf16x3): dense layers whose weight operand has a
  * pre-split mirror run with both operands as two bf16 parts and three kind::f16 MMAs per 16 k-values ("split16" layout,
  * csrc/gemm_tcgen05_split16.cuh) instead of tf32 hi*hi + bf16 cross terms; operand-rounding error ~5e-6 of max |C|.
- * Written at the end of round 1 without a GPU run: see DESIGN.md section 9. */
+ * 1.21-1.31x faster than the default kernel but too coarse for the phi-four gradients: see DESIGN.md section 9. */
 void mfm_set_gemm_split16(int enable);
 /* Pre-split B operand of the persistent kernel (test / benchmark hooks; the ABI entry points below do this themselves for
  * the MLP weights, inside their workspace): mfm_gemm_presplit writes the bf16 cross mirror of n_floats (multiple of 8, both

@@ -1,7 +1,8 @@
 // EXPERIMENTAL (opt-in, MFM_GEMM_SPLIT=bf16x3 / mfm_set_gemm_split16; never the default): "split16" variant of the
-// persistent CTA-pair dense-layer kernel - written at the end of round 1 WITHOUT a GPU run (the round's GPU budget was spent);
-// it compiles for sm_100a, its arithmetic is emulated in scripts/emulation_error_study.py, its test is
-// tests/test_gpu_gemm.py::test_gemm_split16 (skipped unless MFM_TEST_SPLIT16=1).  See DESIGN.md section 9, item 1.
+// persistent CTA-pair dense-layer kernel, written at the very end of round 1.  Measured with the round's last GPU seconds:
+// tests/test_gpu_gemm.py::test_gemm_split16 (skipped unless MFM_TEST_SPLIT16=1) passes, scripts/split16_bench.py shows
+// 1.21-1.31x over the default kernel (419 TFLOP/s at 65536x1024x1024), but bf16 parts fail phi-four's per-layer FM gradient
+// bar (3e-3 vs 5e-4) - fp16 parts with a per-tensor scale are the version to ship.  See DESIGN.md section 9, item 1.
 //
 // Arithmetic: both operands as two 2-byte parts, a = hi + lo with hi = rn(a), lo = rn(a - hi) (bf16; fp16 needs a
 // per-tensor scale and is only a template parameter so far), product = hi.hi' + hi.lo' + lo.hi' : THREE kind::f16 K = 16
