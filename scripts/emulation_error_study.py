@@ -62,14 +62,19 @@ def report(name, A, B):
         print(f"    {k:32s} max err / |C|max = {e.max() / scale:.2e}   max err / (|a||b|) = {(e / rows).max():.2e}")
 
 
-n, K, N = 512, 1600, 1024
-X = (3.88 + 1.4 * rng.standard_normal((n, K))).astype(np.float32)                         # pines positions
-W2 = (rng.standard_normal((1024, K)) / np.sqrt(K)).astype(np.float32)
-H2 = np.maximum(X @ W2.T, 0).astype(np.float32)                                          # activations of Dense_2
-W3 = (rng.standard_normal((N, 1024)) / np.sqrt(1024)).astype(np.float32)
-report("forward Dense_2 (x @ W2)", X, W2)
-report("forward Dense_3 (relu(h2) @ W3)", H2, W3)
-delta = (1e-3 * rng.standard_normal((n, N))).astype(np.float32)                          # small backward signal
-report("backward-data (delta @ W3) with |delta| ~ 1e-3", delta, np.ascontiguousarray(W3.T))
-tiny = (1e-6 * rng.standard_normal((n, N))).astype(np.float32)
-report("backward-data with |delta| ~ 1e-6", tiny, np.ascontiguousarray(W3.T))
+def main():
+    n, K, N = 512, 1600, 1024
+    X = (3.88 + 1.4 * rng.standard_normal((n, K))).astype(np.float32)                         # pines positions
+    W2 = (rng.standard_normal((1024, K)) / np.sqrt(K)).astype(np.float32)
+    H2 = np.maximum(X @ W2.T, 0).astype(np.float32)                                          # activations of Dense_2
+    W3 = (rng.standard_normal((N, 1024)) / np.sqrt(1024)).astype(np.float32)
+    report("forward Dense_2 (x @ W2)", X, W2)
+    report("forward Dense_3 (relu(h2) @ W3)", H2, W3)
+    delta = (1e-3 * rng.standard_normal((n, N))).astype(np.float32)                          # small backward signal
+    report("backward-data (delta @ W3) with |delta| ~ 1e-3", delta, np.ascontiguousarray(W3.T))
+    tiny = (1e-6 * rng.standard_normal((n, N))).astype(np.float32)
+    report("backward-data with |delta| ~ 1e-6", tiny, np.ascontiguousarray(W3.T))
+
+
+if __name__ == "__main__":
+    main()
