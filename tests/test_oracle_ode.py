@@ -76,3 +76,34 @@ def test_float32_solve_tracks_float64():
     A32 = A.astype(np.float32)
     f32 = OO.odeint_final(lambda y, t: y @ A32.T, y0.astype(np.float32), np.array([0.0, 1.0]), 1e-5, 1e-5, 1000)
     assert f32.dtype == np.float32 and np.abs(f32 - f64).max() <= 1e-4 * np.abs(f64).max()
+
+
+def test_agrees_with_scipy_rk45_on_a_nonlinear_field():
+    """Independent implementation of the same Dormand-Prince pair (scipy's RK45 uses its own controller and initial step):
+    both must land within the requested tolerance of each other on a smooth nonlinear field."""
+    from scipy.integrate import solve_ivp
+    rng = np.random.default_rng(3)
+    W = rng.standard_normal((5, 5)) * 0.7
+    y0 = rng.standard_normal((4, 5))
+
+    def f1(t, y):
+        return np.tanh(W @ y) * (1.0 + 0.5 * np.sin(4 * t)) - 0.3 * y
+
+    ours = OO.odeint_final(lambda y, t: np.tanh(y @ W.T) * (1.0 + 0.5 * np.sin(4 * t))[:, None] - 0.3 * y, y0,
+                           np.array([0.0, 1.0]), 1e-7, 1e-7, 1000)
+    for n in range(4):
+        ref = solve_ivp(f1, (0.0, 1.0), y0[n], method="RK45", rtol=1e-10, atol=1e-10).y[:, -1]
+        assert np.abs(ours[n] - ref).max() < 5e-6
+
+
+def test_erf_inv_restatement_matches_scipy():
+    """XLA's float32 ErfInv polynomial (Giles), as jax.random.normal uses it, against scipy's erfinv: the single-precision
+    approximation itself is good to ~3.5e-6 relative in the tails and 2e-7 absolute in the centre (bit-exactness against JAX is
+    pinned separately by the Sharp-Bits values in test_oracle_rng.py)."""
+    import scipy.special
+    from oracle import threefry as tf
+    x = np.linspace(-0.99999, 0.99999, 20001).astype(np.float32)
+    got = tf.erf_inv_f32(x).astype(np.float64)
+    ref = scipy.special.erfinv(x.astype(np.float64))
+    assert (np.abs(got - ref) <= 5e-6 * np.maximum(np.abs(ref), 0.1)).all()
+    assert np.abs(got - ref)[np.abs(x) < 0.9].max() <= 3e-7
