@@ -230,3 +230,26 @@ def test_cis_flow_step_as_coded():
     # dispatch: num_importance_samples > 0 selects it on flow iterations
     _, i_f = OS.train_data_generator(tf.PRNGKey(3), st, 3, t, flow, 0.2, 2, num_importance_samples=K, ref=ref)
     assert (i_f.proposed_weight == i_f.acceptance_rate).all()
+
+
+def test_adamw_restatement_matches_torch_adamw():
+    """optax.adamw (decoupled decay, bias-corrected moments, eps outside the root) against torch.optim.AdamW, an independent
+    implementation of the same update, for several steps with the schedule's learning rates (clip inactive: |update| << 1)."""
+    import torch
+    rng = np.random.default_rng(0)
+    p0 = {"params": {"Dense_0": {"kernel": rng.standard_normal((6, 5)).astype(np.float32), "bias": rng.standard_normal(5).astype(np.float32)}}}
+    lr_fn = OO.learning_rate_fn(100, 0, 1e-3)
+    opt = OO.AdamWClipIfFinite(p0, lr_fn, weight_decay=1e-2)
+    k = torch.nn.Parameter(torch.tensor(p0["params"]["Dense_0"]["kernel"]))
+    b = torch.nn.Parameter(torch.tensor(p0["params"]["Dense_0"]["bias"]))
+    topt = torch.optim.AdamW([{"params": [k], "weight_decay": 1e-2}, {"params": [b], "weight_decay": 0.0}], lr=1e-3, betas=(0.9, 0.999), eps=1e-8)
+    p = p0
+    for step in range(6):
+        g = {"params": {"Dense_0": {"kernel": rng.standard_normal((6, 5)).astype(np.float32), "bias": rng.standard_normal(5).astype(np.float32)}}}
+        p = opt.update(g, p)
+        for grp in topt.param_groups:
+            grp["lr"] = float(lr_fn(step))
+        k.grad = torch.tensor(g["params"]["Dense_0"]["kernel"]); b.grad = torch.tensor(g["params"]["Dense_0"]["bias"])
+        topt.step()
+        assert np.allclose(p["params"]["Dense_0"]["kernel"], k.detach().numpy(), rtol=2e-6, atol=2e-7)
+        assert np.allclose(p["params"]["Dense_0"]["bias"], b.detach().numpy(), rtol=2e-6, atol=2e-7)

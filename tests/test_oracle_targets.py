@@ -119,3 +119,11 @@ def test_initial_positions_follow_the_reference_recipes():
     g = OT.four_mode().init_positions(key, 4, np.float32)
     for i, k in enumerate(tf.split(key, 4)):            # distributions.py:69-71
         assert np.array_equal(g[i], tf.normal(k, (2,), np.float32))
+
+
+def test_pines_prior_is_the_multivariate_normal_density():
+    """unwhitened_prior_log_density (distributions.py:299-303) = log N(x; mu 1, K), checked against scipy's MVN on the real K."""
+    t = OT.LogGaussianCoxPines(1600)
+    x = t.init_positions(tf.PRNGKey(2), 2, np.float64)
+    ref = scipy.stats.multivariate_normal(mean=np.full(1600, t.mu), cov=t.K, allow_singular=False).logpdf(x)
+    assert np.allclose(t.logprior(x), ref, rtol=1e-10)
