@@ -129,6 +129,13 @@ def cpu_oracle_rate(m, head_scale, budget_s=20.0, n=None):
     one cycle  n*(m+1) / (m*t_mala_iter + t_flow_iter)."""
     from oracle import optim as OO, samplers as OS, targets as OT, threefry as tf, vector_field as VF
     cores = os.cpu_count() or 1
+    # torchrun exports OMP_NUM_THREADS=1 to every rank, and small-batch NumPy GEMMs do not always gain from threads (measured:
+    # a 16-chain flow iteration takes 29 s with 8 OpenBLAS threads and 6 s with 1 on a shared 8-core host).  Give the CPU its
+    # best shot: the thread count is set explicitly and calibrated below (1 vs all cores); `cores` reports what was used.
+    try:
+        from threadpoolctl import threadpool_limits
+    except Exception:
+        threadpool_limits = None
     n = n or 16
     ot = OT.LogGaussianCoxPines(D)
     params, omega = fixture_params(head_scale)
@@ -144,6 +151,31 @@ def cpu_oracle_rate(m, head_scale, budget_s=20.0, n=None):
         loss, G = VF.fm_loss_and_grad(params, omega, xt, times, target, ot.grad, 1.0)
         return opt.update(G, params)
 
+    def pick_threads(fn):
+        """faster of 1 / all cores for this phase (BLAS threads; 2 calls each after one warm-up call)"""
+        if threadpool_limits is None:
+            return cores
+        best = None
+        for cand in sorted({1, cores}):
+            threadpool_limits(limits=cand)
+            fn()
+            tc = time.perf_counter()
+            fn(); fn()
+            tc = time.perf_counter() - tc
+            if best is None or tc < best[0]:
+                best = (tc, cand)
+        threadpool_limits(limits=best[1])
+        return best[1]
+
+    def one_mala_fm():
+        nonlocal key, st, params
+        key, k1, k2 = tf.split(key, 3)
+        st, _, _ = OS.mala_step(tf.split(k1, n), st, ot, 0.01)
+        params = fm_update(k2, st.position, params); flow.params = params
+
+    zc = np.random.default_rng(1).standard_normal((n, D))
+    tcal = np.full(n, 0.5)
+    th_mala = pick_threads(one_mala_fm)
     # MALA + FM iterations
     t0 = time.perf_counter(); it = 0
     while it < 2 or (time.perf_counter() - t0 < 0.35 * budget_s and it < 50):
@@ -152,6 +184,8 @@ def cpu_oracle_rate(m, head_scale, budget_s=20.0, n=None):
         params = fm_update(k2, st.position, params); flow.params = params
         it += 1
     t_mala = (time.perf_counter() - t0) / it
+    th_flow = pick_threads(lambda: VF.field_and_div(params, omega, st.position, tcal, ot, zc, 1.0))
+    cores = max(th_mala, th_flow)
     # one flow-MH + FM iteration
     t0 = time.perf_counter()
     key, k1, k2 = tf.split(key, 3)
@@ -160,7 +194,7 @@ def cpu_oracle_rate(m, head_scale, budget_s=20.0, n=None):
     params = fm_update(k2, st.position, params)
     t_flow = time.perf_counter() - t0
     rate = n * (m + 1) / (m * t_mala + t_flow)
-    sample = (f"{n} chains (d=1600,H=1024), float64 NumPy oracle: {it} MALA+FM iterations ({t_mala*1e3:.0f} ms each) + "
+    sample = (f"{n} chains (d=1600,H=1024), float64 NumPy oracle, BLAS threads = faster of 1 / all {os.cpu_count()} cores per phase ({th_mala} for MALA+FM, {th_flow} for the flow): {it} MALA+FM iterations ({t_mala*1e3:.0f} ms each) + "
               f"1 flow-MH+FM iteration ({t_flow:.1f} s, {int(stats['inv']['n_try'].max())}+{int(stats['fwd']['n_try'].max())} "
               f"RK steps); cycle = {m}*t_mala + t_flow")
     return rate, cores, sample, m * t_mala + t_flow
