@@ -200,7 +200,8 @@ def cpu_oracle_rate(m, head_scale, budget_s=20.0, n=None):
     return rate, cores, sample, m * t_mala + t_flow
 
 
-REFERENCE_SAMPLE_CHAINS = 64     # the reference arm's sample (cpu_baseline inside the default run uses 16 chains to stay short)
+REFERENCE_SAMPLE_CHAINS = 128    # the reference arm's sample = the reference's own pines ensemble (multi_modal.py:90); the
+                                 # cpu_baseline object inside the default run uses 16 chains to stay short
 
 
 def run_reference(a):
@@ -221,7 +222,7 @@ def run_reference(a):
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "CPU oracle port (NumPy restatement of the reference; JAX/flax/optax cannot be installed in this "
-                    f"image); rate measured on a {n}-chain sample (the reference's own pines run has 128 chains) and reported per "
+                    f"image); rate measured on a {n}-chain sample (the size of the reference's own pines run) and reported per "
                     "chain-step, i.e. NOT extrapolated to 65536 chains' wall-clock; ms_per_step is the sample's cycle time",
             "wall_s": time.perf_counter() - t0}
     print(json.dumps(line), flush=True)
