@@ -1,19 +1,22 @@
 #!/usr/bin/env python
-"""bench.py — chain-steps/sec of the MFM hot path (MALA + flow-MH + FM update), pines 40x40.
+"""bench.py — chain-steps/sec of the MFM hot path (MALA + flow-MH + FM update).
 
 Contract: `python bench.py --gpus N --steps K --warmup W` (torchrun for N>1) prints ONE JSON line.
 
-Workload (BASELINE.json configs[4]): pines-shaped ensemble, 65 536 chains in
-total, sharded over the N GPUs (strong scaling: total work fixed), d=1600, H=1024, step 0.01,
-mcmc_per_flow_steps m, Hutchinson divergence, rtol=atol=1e-5, beta=1, synthetic positions
-mu + L eps, "trained-like" MLP fixture (all kernels ~ N(0, 1/fan_in), heads x0.1, numpy seed 0).
+Default workload = BASELINE.json configs[4]: pines-shaped ensemble, 65 536 chains in total,
+sharded over the N GPUs (strong scaling: total work fixed), d=1600, H=1024, step 0.01, mcmc_per_flow_steps m,
+Hutchinson divergence, rtol=atol=1e-5, beta=1, synthetic positions mu + L eps, "trained-like" MLP fixture (all
+kernels ~ N(0, 1/fan_in), heads x0.1, numpy seed 0).  `--config {4-mode,gaussian-mixture,phi-four,pines}` runs the
+reference's own four configurations (configs[0..3]) at THEIR shapes on one GPU with the same step definition.
 
-A STEP is one cycle-aligned block of (m+1) outer iterations of the reference loop
-(exe_flow_matching.py:432-449): m MALA iterations + 1 flow-MH iteration, EACH followed by one
-flow-matching AdamW update.  value = n_total * K * (m+1) / seconds  [chain-steps/s].
+A STEP is one cycle-aligned block of (m+1) outer iterations of the reference loop (exe_flow_matching.py:432-449):
+m MALA iterations + 1 flow-MH iteration, EACH followed by one flow-matching AdamW update.
+value = n_total * K * (m+1) / seconds  [chain-steps/s].
 
-`--impl reference` times the CPU oracle port of the same path (JAX is not installable here, see
-DESIGN.md) on the host cores, on a bounded sample of the workload.
+`--impl reference` times the CPU oracle port of the same path (JAX is not installable here) on the
+host cores.  Its step is a BOUNDED SAMPLE of the cycle (a few MALA+FM iterations + one flow-MH+FM iteration on a small
+ensemble); the line says what ran (`config.chains_total`, `sample`) and that the cycle rate is composed from the two
+measured phase times (`extrapolated: true`).  The `cpu_baseline` object of the default run is ONE such step.
 """
 from __future__ import annotations
 
@@ -31,9 +34,26 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "chain-steps/sec (MALA+flow-MH+FM update), pines 40x40"
 UNIT = "chain-steps/s"
-D, H, F = 1600, 1024, 128
+F = 128
+# name: chains, d, H, mcmc_per_flow_steps, step size, Hutchinson?, ODE grid, grad clip, CPU sample chains   
+CONFIGS = {
+    "4-mode": dict(n=128, d=2, H=128, m=10, step=0.2, hutch=False, n_times=5, clip=None, cpu_n=128,
+                   cite="BASELINE.json configs[0]: multi_modal.py --example 4-mode --mcmc_per_flow_steps 10"),
+    "gaussian-mixture": dict(n=128, d=2, H=128, m=100, step=0.2, hutch=True, n_times=2, clip=None, cpu_n=128,
+                             cite="BASELINE.json configs[1]: --example gaussian-mixture --mcmc_per_flow_steps 100 --hutchs (16 modes)"),
+    "phi-four": dict(n=1024, d=64, H=128, m=1000, step=1e-4, hutch=False, n_times=2, clip=None, cpu_n=8,
+                     cite="BASELINE.json configs[2]: --example phi-four --mcmc_per_flow_steps 1000 (exact trace)"),
+    "pines": dict(n=128, d=1600, H=1024, m=100, step=0.01, hutch=True, n_times=2, clip=1.0, cpu_n=16,
+                  cite="BASELINE.json configs[3]: --example pines --mcmc_per_flow_steps 100 --hutchs"),
+    "pines-scaling": dict(n=65536, d=1600, H=1024, m=100, step=0.01, hutch=True, n_times=2, clip=1.0, cpu_n=16,
+                          cite="BASELINE.json configs[4]: synthetic pines-shaped scaling run, 65536 chains over 1/2/4/8 GPUs"),
+}
+
+
+def metric_name(cfg):
+    shape = {"pines-scaling": "pines 40x40", "pines": "pines 40x40 (128 chains)"}.get(cfg, cfg)
+    return f"chain-steps/sec (MALA+flow-MH+FM update), {shape}"
 
 
 def parse():
@@ -42,28 +62,34 @@ def parse():
     p.add_argument("--steps", type=int, default=1)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", type=str, default="b200", choices=["b200", "reference"])
-    p.add_argument("--chains", type=int, default=65536, help="total chains over all GPUs")
-    p.add_argument("--mcmc_per_flow_steps", dest="m", type=int, default=100)
+    p.add_argument("--config", type=str, default="pines-scaling", choices=list(CONFIGS))
+    p.add_argument("--chains", type=int, default=None, help="total chains over all GPUs (default: the configuration's)")
+    p.add_argument("--mcmc_per_flow_steps", dest="m", type=int, default=None)
     p.add_argument("--head_scale", type=float, default=0.1)
     p.add_argument("--warmup_unit", type=str, default="cycle", choices=["iteration", "cycle"],
                    help="a warm-up step is one full cycle (default, = a timed step) or one outer iteration (>=3 of them touch every MALA/FM kernel, and "
                         "one extra flow-MH iteration is then run untimed)")
     p.add_argument("--no_cpu_baseline", action="store_true")
     p.add_argument("--no_e2e", action="store_true")
-    return p.parse_args()
+    a = p.parse_args()
+    c = CONFIGS[a.config]
+    a.chains = a.chains or c["n"]
+    a.m = a.m if a.m is not None else c["m"]
+    return a
 
 
-def args_ns(m, learning_iter=10000):
-    return SimpleNamespace(hutchs=True, num_importance_samples=0, mcmc_per_flow_steps=m, step_size=0.01,
+def args_ns(a, learning_iter=10000):
+    c = CONFIGS[a.config]
+    return SimpleNamespace(hutchs=c["hutch"], num_importance_samples=0, mcmc_per_flow_steps=a.m, step_size=c["step"],
                            ref_dist="stdgauss", cond_flow=True, ot_cond_flow=False, sigma=1e-4, adam_beta1=0.9,
                            adam_beta2=0.999, adam_epsilon=1e-8, weight_decay=1e-4, gradient_clip=1.0,
                            learning_iter=learning_iter, warmup_steps=0, learning_rate=1e-3)
 
 
-def fixture_params(head_scale):
+def fixture_params(d, H, head_scale):
     """Trained-like MLP fixture: fixed numpy seed, heads scaled down."""
     rng = np.random.default_rng(0)
-    shapes = [(2 * F, H), (H, H), (D, H), (H, H), (H, D), (2 * H, H), (H, H), (H, D)]
+    shapes = [(2 * F, H), (H, H), (d, H), (H, H), (H, d), (2 * H, H), (H, H), (H, d)]
     p = {}
     for i, (fi, fo) in enumerate(shapes):
         s = (1.0 / np.sqrt(fi)) * (head_scale if i in (4, 7) else 1.0)
@@ -74,12 +100,16 @@ def fixture_params(head_scale):
 
 
 # ------------------------------------------------------------------------------------------------
-# algorithmic work
+# algorithmic work per chain; 1 MAC = 2 flop
 # ------------------------------------------------------------------------------------------------
-def flops_per_chain():
-    P = 2 * F * H + 5 * H * H + 3 * D * H
-    T = 2 * D * H + 3 * H * H
-    return dict(mala=2 * D * D, fm=6 * P + 2 * D * D, field=2 * P + 2 * T + 2 * D * D, logp=2 * D * D)
+def flops_per_chain(cfg):
+    c = CONFIGS[cfg]
+    d, H = c["d"], c["H"]
+    P = 2 * F * H + 5 * H * H + 3 * d * H
+    T = 2 * d * H + 3 * H * H
+    dense_prior = 2 * d * d if d == 1600 else 0                   # pines: x K^-1 (GMM / phi-four: O(d), not counted)
+    field = 2 * P + dense_prior + ((2 * T + dense_prior) if c["hutch"] else 2 * d * (3 * H * H + H))
+    return dict(mala=dense_prior, fm=6 * P + dense_prior, field=field, logp=dense_prior)
 
 
 class ClockSampler:
@@ -121,87 +151,102 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU oracle timing (reference arm + cpu_baseline)
+# CPU oracle (the ONE CPU baseline definition, used by both `--impl reference` and `cpu_baseline`)
 # ------------------------------------------------------------------------------------------------
-def cpu_oracle_rate(m, head_scale, budget_s=20.0, n=None):
-    """chain-steps/s of the NumPy oracle (float64, as the reference runs with jax_enable_x64) on a
-    bounded sample: n chains, a few MALA+FM iterations and one flow-MH+FM iteration, combined into
-    one cycle  n*(m+1) / (m*t_mala_iter + t_flow_iter)."""
-    from oracle import optim as OO, samplers as OS, targets as OT, threefry as tf, vector_field as VF
-    cores = os.cpu_count() or 1
-    # torchrun exports OMP_NUM_THREADS=1 to every rank, and small-batch NumPy GEMMs do not always gain from threads (measured:
-    # a 16-chain flow iteration takes 29 s with 8 OpenBLAS threads and 6 s with 1 on a shared 8-core host).  Give the CPU its
-    # best shot: the thread count is set explicitly and calibrated below (1 vs all cores); `cores` reports what was used.
-    try:
-        from threadpoolctl import threadpool_limits
-    except Exception:
-        threadpool_limits = None
-    n = n or 16
-    ot = OT.LogGaussianCoxPines(D)
-    params, omega = fixture_params(head_scale)
-    ref = OT.IndepGaussian(D)
-    flow = OS.Flow(params, omega, ot, True, 1e-5, 1e-5, 1000, 1.0, (0.0, 1.0))
-    opt = OO.AdamWClipIfFinite(params, OO.learning_rate_fn(10000, 0, 1e-3))
-    x0 = ot.init_positions(tf.PRNGKey(1), n, np.float64)
-    st = OS.mala_init(x0, ot)
-    key = tf.PRNGKey(7)
+def oracle_target(cfg):
+    from oracle import targets as OT
+    return {"4-mode": OT.four_mode, "gaussian-mixture": OT.gmm16, "phi-four": lambda: OT.PhiFour(64),
+            "pines": lambda: OT.LogGaussianCoxPines(1600), "pines-scaling": lambda: OT.LogGaussianCoxPines(1600)}[cfg]()
 
-    def fm_update(key_step, pos, params):
-        times, xt, target = VF.fm_batch(key_step, pos, ref.sample, 1e-4)
-        loss, G = VF.fm_loss_and_grad(params, omega, xt, times, target, ot.grad, 1.0)
-        return opt.update(G, params)
 
-    def pick_threads(fn):
-        """faster of 1 / all cores for this phase (BLAS threads; 2 calls each after one warm-up call)"""
-        if threadpool_limits is None:
-            return cores
+class CpuSample:
+    """The NumPy oracle (float64, as the reference runs with jax_enable_x64) on a bounded sample of the workload:
+    `n` chains of the configuration's shape.  step() = `r` MALA+FM iterations + 1 flow-MH+FM iteration; the cycle rate
+    n (m+1) / (m t_mala + t_flow) is composed from the two measured phase times."""
+
+    def __init__(self, cfg, m, head_scale, n=None, r=2):
+        from oracle import optim as OO, samplers as OS, targets as OT, threefry as tf, vector_field as VF
+        self.OS, self.tf, self.VF = OS, tf, VF
+        c = CONFIGS[cfg]
+        self.cfg, self.c, self.m, self.r = cfg, c, m, r
+        self.n = n or c["cpu_n"]
+        self.ot = oracle_target(cfg)
+        self.params, self.omega = fixture_params(c["d"], c["H"], head_scale)
+        self.ref = OT.IndepGaussian(c["d"])
+        self.flow = OS.Flow(self.params, self.omega, self.ot, c["hutch"], 1e-5, 1e-5, 1000, c["clip"], np.linspace(0.0, 1.0, c["n_times"]))
+        self.opt = OO.AdamWClipIfFinite(self.params, OO.learning_rate_fn(10000, 0, 1e-3))
+        self.st = OS.mala_init(self.ot.init_positions(tf.PRNGKey(1), self.n, np.float64), self.ot)
+        self.key = tf.PRNGKey(7)
+        self.t_mala, self.t_flow, self.rk = [], [], None
+        # torchrun exports OMP_NUM_THREADS=1 to every rank and small-batch NumPy GEMMs do not always gain from threads:
+        # the BLAS thread count is set explicitly and calibrated per phase (1 vs all cores) so the CPU gets its best shot
+        try:
+            from threadpoolctl import threadpool_limits
+            self._limits = threadpool_limits
+        except Exception:
+            self._limits = None
+        self.cores_all = os.cpu_count() or 1
+        self.th_mala = self._pick(self._mala_fm)
+        zc = np.random.default_rng(1).standard_normal((self.n, c["d"]))
+        self.th_flow = self._pick(lambda: VF.field_and_div(self.params, self.omega, self.st.position, np.full(self.n, 0.5), self.ot,
+                                                           zc if c["hutch"] else None, c["clip"]))
+
+    def _pick(self, fn):
+        if self._limits is None:
+            return self.cores_all
         best = None
-        for cand in sorted({1, cores}):
-            threadpool_limits(limits=cand)
+        for cand in sorted({1, self.cores_all}):
+            self._limits(limits=cand)
             fn()
-            tc = time.perf_counter()
-            fn(); fn()
-            tc = time.perf_counter() - tc
+            tc = time.perf_counter(); fn(); fn(); tc = time.perf_counter() - tc
             if best is None or tc < best[0]:
                 best = (tc, cand)
-        threadpool_limits(limits=best[1])
         return best[1]
 
-    def one_mala_fm():
-        nonlocal key, st, params
-        key, k1, k2 = tf.split(key, 3)
-        st, _, _ = OS.mala_step(tf.split(k1, n), st, ot, 0.01)
-        params = fm_update(k2, st.position, params); flow.params = params
+    def _fm_update(self, key_step):
+        times, xt, target = self.VF.fm_batch(key_step, self.st.position, self.ref.sample, 1e-4)
+        _, G = self.VF.fm_loss_and_grad(self.params, self.omega, xt, times, target, self.ot.grad, self.c["clip"])
+        self.params = self.opt.update(G, self.params)
+        self.flow.params = self.params
 
-    zc = np.random.default_rng(1).standard_normal((n, D))
-    tcal = np.full(n, 0.5)
-    th_mala = pick_threads(one_mala_fm)
-    # MALA + FM iterations
-    t0 = time.perf_counter(); it = 0
-    while it < 2 or (time.perf_counter() - t0 < 0.35 * budget_s and it < 50):
-        key, k1, k2 = tf.split(key, 3)
-        st, _, _ = OS.mala_step(tf.split(k1, n), st, ot, 0.01)
-        params = fm_update(k2, st.position, params); flow.params = params
-        it += 1
-    t_mala = (time.perf_counter() - t0) / it
-    th_flow = pick_threads(lambda: VF.field_and_div(params, omega, st.position, tcal, ot, zc, 1.0))
-    cores = max(th_mala, th_flow)
-    # one flow-MH + FM iteration
-    t0 = time.perf_counter()
-    key, k1, k2 = tf.split(key, 3)
-    stats = {}
-    st, _ = OS.rw_flow_mh_step(tf.split(k1, n), st, ot, flow, 1.0, stats)
-    params = fm_update(k2, st.position, params)
-    t_flow = time.perf_counter() - t0
-    rate = n * (m + 1) / (m * t_mala + t_flow)
-    sample = (f"{n} chains (d=1600,H=1024), float64 NumPy oracle, BLAS threads = faster of 1 / all {os.cpu_count()} cores per phase ({th_mala} for MALA+FM, {th_flow} for the flow): {it} MALA+FM iterations ({t_mala*1e3:.0f} ms each) + "
-              f"1 flow-MH+FM iteration ({t_flow:.1f} s, {int(stats['inv']['n_try'].max())}+{int(stats['fwd']['n_try'].max())} "
-              f"RK steps); cycle = {m}*t_mala + t_flow")
-    return rate, cores, sample, m * t_mala + t_flow
+    def _mala_fm(self):
+        self.key, k1, k2 = self.tf.split(self.key, 3)
+        self.st, _, _ = self.OS.mala_step(self.tf.split(k1, self.n), self.st, self.ot, self.c["step"])
+        self._fm_update(k2)
 
+    def step(self):
+        if self._limits:
+            self._limits(limits=self.th_mala)
+        t0 = time.perf_counter()
+        for _ in range(self.r):
+            self._mala_fm()
+        self.t_mala.append((time.perf_counter() - t0) / self.r)
+        if self._limits:
+            self._limits(limits=self.th_flow)
+        t0 = time.perf_counter()
+        self.key, k1, k2 = self.tf.split(self.key, 3)
+        stats = {}
+        self.st, _ = self.OS.rw_flow_mh_step(self.tf.split(k1, self.n), self.st, self.ot, self.flow, 1.0, stats)
+        self._fm_update(k2)
+        self.t_flow.append(time.perf_counter() - t0)
+        self.rk = (int(stats["inv"]["n_try"].max()), int(stats["fwd"]["n_try"].max()))
 
-REFERENCE_SAMPLE_CHAINS = 128    # the reference arm's sample = the reference's own pines ensemble (multi_modal.py:90); the
-                                 # cpu_baseline object inside the default run uses 16 chains to stay short
+    def reset_timers(self):
+        self.t_mala, self.t_flow = [], []
+
+    def rate(self):
+        tm, tf_ = float(np.mean(self.t_mala)), float(np.mean(self.t_flow))
+        return self.n * (self.m + 1) / (self.m * tm + tf_), tm, tf_
+
+    def describe(self):
+        v, tm, tf_ = self.rate()
+        c = self.c
+        return (f"{self.n} chains (d={c['d']}, H={c['H']}), float64 NumPy oracle port; per step {self.r} MALA+FM iterations ({tm * 1e3:.1f} ms each, "
+                f"{self.th_mala} BLAS thread(s)) + 1 flow-MH+FM iteration ({tf_:.2f} s, {self.rk[0]}+{self.rk[1]} RK attempts, {self.th_flow} BLAS thread(s)); "
+                f"{len(self.t_flow)} step(s); cycle rate = n (m+1) / (m t_mala + t_flow), m = {self.m}; host has {self.cores_all} cores")
+
+    def cores(self):
+        return max(self.th_mala, self.th_flow)
 
 
 def run_reference(a):
@@ -209,33 +254,55 @@ def run_reference(a):
     if rank != 0:
         return
     t0 = time.perf_counter()
-    rates = []
-    n = REFERENCE_SAMPLE_CHAINS
-    for _ in range(max(1, min(a.steps, 2))):
-        rate, cores, sample, cyc = cpu_oracle_rate(a.m, a.head_scale, budget_s=15.0, n=n)
-        rates.append(rate)
-    v = float(np.mean(rates))
-    line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": 1e3 * n * (a.m + 1) / v, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "impl": "reference",
-            "config": workload_config(a, a.chains),
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+    cpu = CpuSample(a.config, a.m, a.head_scale)
+    for _ in range(a.warmup):
+        cpu.step()
+    cpu.reset_timers()
+    tw = time.perf_counter()
+    for _ in range(a.steps):
+        cpu.step()
+    wall_timed = time.perf_counter() - tw
+    v, tm, tf_ = cpu.rate()
+    cfg = workload_config(a, cpu.n)
+    cfg["workload"] = f"{cpu.n}-chain sample of: " + cfg["workload"]
+    cfg["sample_of_chains_total"] = a.chains
+    cfg["step_definition"] = f"SAMPLE step: {cpu.r} MALA+FM iterations + 1 flow-MH+FM iteration on {cpu.n} chains (not a full {a.m}+1 cycle)"
+    line = {"metric": metric_name(a.config), "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": 1e3 * wall_timed / max(a.steps, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "impl": "reference", "config": cfg, "extrapolated": True,
+            "sample_chains": cpu.n, "iterations_timed": {"mala_fm": cpu.r * a.steps, "flow_mh_fm": a.steps},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cpu.cores(), "kind": "port", "sample": cpu.describe()},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "note": "CPU oracle port (NumPy restatement of the reference; JAX/flax/optax cannot be installed in this "
-                    f"image); rate measured on a {n}-chain sample (the size of the reference's own pines run) and reported per "
-                    "chain-step, i.e. NOT extrapolated to 65536 chains' wall-clock; ms_per_step is the sample's cycle time",
+            "note": "CPU oracle port (NumPy restatement of the reference; JAX/flax/optax cannot be installed in this image). `value` is the "
+                    "per-chain cycle rate composed from the measured phase times of the sample (extrapolated: the sample does not run "
+                    f"{a.m} MALA iterations per flow iteration and holds {cpu.n} chains, not {a.chains}); ms_per_step is the measured wall time of one sample step",
             "wall_s": time.perf_counter() - t0}
     print(json.dumps(line), flush=True)
 
 
 def workload_config(a, n_total):
-    return {"workload": "pines-shaped scaling ensemble (BASELINE.json configs[4])", "chains_total": n_total, "dim": D,
-            "hidden": H, "fourier_dim": F, "mcmc_per_flow_steps": a.m, "step_size": 0.01, "divergence": "hutchinson",
-            "rtol": 1e-5, "atol": 1e-5, "beta": 1.0, "flow_step": "random-walk MH in latent space (reference default)",
+    c = CONFIGS[a.config]
+    big = n_total * c["d"] * 4 > 126e6
+    return {"workload": c["cite"], "name": a.config, "chains_total": n_total, "dim": c["d"], "hidden": c["H"], "fourier_dim": F,
+            "mcmc_per_flow_steps": a.m, "step_size": c["step"], "divergence": "hutchinson" if c["hutch"] else "exact trace",
+            "ode_grid": c["n_times"], "rtol": 1e-5, "atol": 1e-5, "beta": 1.0, "flow_step": "random-walk MH in latent space (reference default)",
             "mlp_params": f"trained-like fixture, heads x{a.head_scale}, numpy seed 0",
             "step_definition": f"{a.m} MALA + 1 flow-MH outer iterations, each followed by one FM AdamW update",
-            "l2": "inputs larger than L2 (state arrays 419 MB each at 65536 chains)",
+            "l2": (f"inputs larger than L2 (state arrays {n_total * c['d'] * 4 / 2**20:.0f} MiB each)" if big else
+                   "state smaller than L2 (the reference's own shape; latency-bound): every iteration rewrites the state and a cycle streams "
+                   "the parameter / optimizer buffers, no separate flush"),
             "parallelism": f"chains sharded over {a.gpus} GPU(s), FM-gradient all-reduce (NCCL)"}
+
+
+def device_dist(cfg, dev):
+    from mfm_b200 import distributions as Dm
+    from oracle import targets as OT          # constants of the two mixtures only (the fixture the tests use)
+    if cfg in ("pines", "pines-scaling"):
+        return Dm.LogGaussianCoxPines(1600, device=dev)
+    if cfg == "phi-four":
+        return Dm.PhiFour(64, device=dev)
+    ot = OT.four_mode() if cfg == "4-mode" else OT.gmm16()
+    return Dm.GaussianMixture(ot.modes, ot.covs, ot.weights, device=dev)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -250,7 +317,7 @@ def main():
 
     import torch
     import torch.distributed as tdist
-    from mfm_b200 import _lib, distributions as Dm, exe_flow_matching as E, random as mr
+    from mfm_b200 import _lib, exe_flow_matching as E, random as mr
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -261,28 +328,36 @@ def main():
         tdist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
 
+    c = CONFIGS[a.config]
+    D, H = c["d"], c["H"]
     n_total = a.chains
     assert n_total % world == 0
     n = n_total // world
     off = rank * n
     m = a.m
     cyc = m + 1
-    args = args_ns(m)
-    opts = SimpleNamespace(rtol=1e-5, atol=1e-5, mxstep=1000, n_times=2)
+    args = args_ns(a)
+    opts = SimpleNamespace(rtol=1e-5, atol=1e-5, mxstep=1000, n_times=c["n_times"])
 
-    dist = Dm.LogGaussianCoxPines(D, device=dev)
-    params, omega = fixture_params(a.head_scale)
-    model = E.VectorFieldNet(torch.from_numpy(omega).to(dev), dist, [H, H], [H, H], [H, H], "relu", 1.0)
+    dist = device_dist(a.config, dev)
+    params, omega = fixture_params(D, H, a.head_scale)
+    model = E.VectorFieldNet(torch.from_numpy(omega).to(dev), dist, [H, H], [H, H], [H, H], "relu", c["clip"])
     P = E.VectorFieldParams(D, H, F, dev).load_dict(params)
 
-    # synthetic positions mu + L eps for this rank's rows of split(key_dist, n_total)
+    # synthetic initial positions: this rank's rows of the configuration's own initialize_model (split(key_dist, n_total))
     key0 = mr.PRNGKey(1, dev)
     ks = mr.split(key0, 6)
     key_sample, key_dist = ks[1].clone(), ks[3].clone()
     rows = mr.split(key_dist, n_total)[off:off + n].contiguous()
-    eps = mr.normal(rows, (D,))
-    pos0 = (dist._mu_zero + eps @ dist._cholesky_gram.T).contiguous()
-    del eps, rows
+    if a.config in ("pines", "pines-scaling"):
+        eps = mr.normal(rows, (D,))
+        pos0 = (dist._mu_zero + eps @ dist._cholesky_gram.T).contiguous()          # mu + L eps (distributions.py:312-314)
+        del eps
+    elif a.config == "phi-four":
+        pos0 = (mr.uniform(rows, (D,)) * 2 - 1).contiguous()                      # distributions.py:162-164
+    else:
+        pos0 = mr.normal(rows, (D,)).contiguous()                                  # distributions.py:69-71
+    del rows
 
     loop = E.HotLoop(dist, model, P, args, opts, key_sample, pos0, beta=1.0, chain_offset=off, n_total=n_total)
 
@@ -304,10 +379,8 @@ def main():
         for _ in range(a.warmup):
             loop.iteration()              # MALA + FM update iterations
         # one untimed flow-MH iteration so the ODE kernels are warm too
-        saved = loop.count
         loop.count = cyc - 1
         loop.iteration()
-        loop.count = saved
         # realign: the timed window must start right after a multiple of (m+1)
         loop.count = 0
     loop.flush()
@@ -315,25 +388,30 @@ def main():
 
     # ---- timed region --------------------------------------------------------------------------
     sampler = ClockSampler(local) if rank == 0 else None
-    launches0 = lib.mfm_launch_count()
+    launches0 = lib.mfm_launch_count() + loop.replayed_launches
+    replays0 = loop.graph_replays
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    flow_stats = []                       # per timed step: the flow iteration's ODE statistics (device tensors, read after the sync)
     sync()
     e0.record()
     for _ in range(a.steps):
         run_cycle()
+        flow_stats.append(loop.gen.last_stats.get("ode"))
     loop.flush()                          # multi-rank runs pipeline the last AdamW update: it belongs to the timed work
     e1.record()
     sync()
     ms = e0.elapsed_time(e1)
-    launches = lib.mfm_launch_count() - launches0
+    launches = lib.mfm_launch_count() + loop.replayed_launches - launches0     # kernels launched directly + by CUDA-graph replays
+    graph_replays = loop.graph_replays - replays0
     clocks = sampler.stop() if sampler else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
     ms = float(t.item())
     value = n_total * a.steps * cyc / (ms / 1e3)
-    ode_stats = loop.gen.last_stats.get("ode")
-    ode_stats = ode_stats.cpu().tolist() if ode_stats is not None else None
+    stats_l = [s.cpu() for s in flow_stats if s is not None]
+    ode_stats = stats_l[-1][:4].tolist() if stats_l else None
+    chain_evals = [int(s[4:6].view(torch.int64).item()) for s in stats_l]          # rows ACTUALLY evaluated (compaction), per step
 
     # ---- per-phase timing (MALA iteration, FM update, flow iteration) for the roofline ------------
     def timed(fn, reps):
@@ -344,34 +422,34 @@ def main():
         s1.record(); torch.cuda.synchronize()
         return s0.elapsed_time(s1) / reps
 
-    fl = flops_per_chain()
+    fl = flops_per_chain(a.config)
     key_t = mr.PRNGKey(99, dev)
     loop.flush()
     ms_fm = timed(lambda: loop.state.loss_and_grad(key_t, loop.states.position, off, n_total), 3)
     from mfm_b200.bblackjax.mcmc.mala import mala_step
-    ms_mala = timed(lambda: mala_step(dist.tempered(1.0), key_t, loop.states, 0.01, False, off, n_total, inplace=True), 3)
+    ms_mala = timed(lambda: mala_step(dist.tempered(1.0), key_t, loop.states, c["step"], False, off, n_total, inplace=True), 3)
     # one whole MALA outer iteration (data generator + FM loss/grad + gradient all-reduce + AdamW), max over ranks
     loop.flush()
     loop.count = 0
-    ms_iter = timed(loop.iteration, 5)
+    ms_iter = timed(loop.iteration, min(5, m))
     loop.flush()
     t_it = torch.tensor([ms_iter], dtype=torch.float64, device=dev)
     if world > 1:
         tdist.all_reduce(t_it, op=tdist.ReduceOp.MAX)
     ms_iter = float(t_it.item())
-    # dominant kernel: the persistent CTA-pair dense-layer GEMM, measured on the FM hidden-layer shape
-    # [n,H] x [H,H] with K-major operands (how every forward / backward-data layer calls it): a burst of 10
-    # launches and a sustained run of >= 1 s (the clocks settle under the 1 kW power cap), CUDA events on
-    # the launching stream.
-    Ag = torch.randn(n, H, device=dev); Bg = torch.randn(H, H, device=dev); Cg = torch.empty(n, H, device=dev)
+    # dominant kernel: the dense-layer GEMM, measured on the FM hidden-layer shape [n,H] x [H,H] with K-major operands
+    # (how every forward / backward-data layer calls it): a burst of 10 launches and a sustained run of >= 1 s (the
+    # clocks settle under the 1 kW power cap), CUDA events on the launching stream.
+    gemm_info = lib.mfm_gemm_describe().decode() if hasattr(lib, "mfm_gemm_describe") else ""
+    Ag = torch.randn(n, H, device=dev); Bg = torch.randn(H, H, device=dev) / H ** 0.5; Cg = torch.empty(n, H, device=dev)
     st = torch.cuda.current_stream().cuda_stream
     gemm = lambda: _lib.check(lib.mfm_gemm_tf32x3(n, H, H, Ag.data_ptr(), H, 1, Bg.data_ptr(), H, 0, None, 0, Cg.data_ptr(), H, st))
-    # as the layers call it: the weight operand's bf16 cross tile pre-split once (per parameter update) and loaded by TMA
-    Bx = torch.empty_like(Bg)
+    # as the layers call it: the weight operand pre-split once (per parameter update) and loaded by TMA
+    Bx = torch.empty(2 * H * H, device=dev)
     _lib.check(lib.mfm_gemm_presplit(Bg.data_ptr(), Bx.data_ptr(), H * H, st))
     lib.mfm_gemm_register_mirror(Bg.data_ptr(), H * H, Bx.data_ptr())
     ms_gemm_burst = timed(gemm, 10)
-    ms_gemm = timed(gemm, max(10, int(1000.0 / ms_gemm_burst)))
+    ms_gemm = timed(gemm, max(10, min(20000, int(1000.0 / ms_gemm_burst))))
     lib.mfm_gemm_register_mirror(None, 0, None)
     gemm_tflops = 2.0 * n * H * H / (ms_gemm * 1e-3) / 1e12
     peaks = {}
@@ -381,25 +459,29 @@ def main():
         pass
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1590.0 if not peaks else peaks.get("bf16_tflops", 1590.0)))
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1590 (of fallback)"
-    step_flops = n * (cyc * fl["fm"] + m * fl["mala"])          # + flow iteration (data dependent), added below
-    if ode_stats:
-        step_flops += n * (ode_stats[3] * fl["field"] + fl["logp"])
-    step_tflops = step_flops * a.steps / (ms * 1e-3) / 1e12 * 1.0
-    # per-launch DRAM traffic of this kernel at n = 65536 from the committed ncu --set full capture
-    # (profiles/r01_ncu_pair_kernels.md: dram__bytes_read.sum + dram__bytes_write.sum); algorithmic bytes are
-    # A + C + W = 2 * n*H*4 + H*H*4.  Only quoted when the run has the profiled shape.
-    traffic = 501.6e6 if n == 65536 else None
+    # whole-step FLOPs from what was executed: FM updates and MALA steps on all n chains, field evaluations on the rows the
+    # ODE loop actually evaluated (finished chains are compacted away), read from the device counter of every timed step
+    step_flops = a.steps * n * (cyc * fl["fm"] + m * fl["mala"] + fl["logp"]) + sum(chain_evals) * fl["field"]
+    step_tflops = step_flops / (ms * 1e-3) / 1e12
+    # per-launch DRAM traffic of the dominant kernel: only from an ncu --set full capture of THIS round's kernel at THIS shape
+    # (profiles/r02_ncu_traffic.json, written by scripts/ncu_summary.py from the committed capture); otherwise null
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")))
+        if tr.get("rows") == n and tr.get("config") == a.config:
+            traffic = float(tr["dram_bytes_per_launch"])
+    except Exception:
+        pass
     roofline = {"bound": "tensor",
-                "kernel": "tc2p::gemm_tc2p_kernel (persistent CTA-pair tcgen05/TMEM/TMA dense layer, FM shape [n,1024]x[1024,1024], K-major operands)",
+                "kernel": f"dense-layer GEMM, FM shape [{n},{H}]x[{H},{H}], K-major operands; {gemm_info}",
                 "achieved": gemm_tflops, "peak": peak_tf, "unit": "TFLOP/s", "frac": gemm_tflops / peak_tf,
                 "traffic": traffic, "algorithmic_bytes": 2.0 * n * H * 4 + H * H * 4, "peak_source": peak_src,
                 "achieved_burst": 2.0 * n * H * H / (ms_gemm_burst * 1e-3) / 1e12,
-                "note": "algorithmic fp32 FLOPs (2*M*N*K per launch), sustained (>= 1 s of back-to-back launches, sw_power_cap active). "
-                        "fp32-accurate emulation: per k-step one kind::tf32 MMA (hi*hi) + one kind::f16 bf16 MMA with K=16 (both cross "
-                        "terms; the weight operand's cross tile is pre-split in global memory), i.e. 2 tf32-rate MMA slots per fp32 product => the ceiling of this arithmetic is 1/4 of the bf16 peak "
-                        "(split-K weight-gradient GEMMs still use 3 tf32 passes, ceiling 1/6)",
-                "frac_of_emulation_ceiling": gemm_tflops / (peak_tf / 4.0),
+                "note": "algorithmic fp32 FLOPs (2*M*N*K per launch) / mean launch time over a sustained run (>= 1 s of back-to-back launches, "
+                        "CUDA events). fp32-accurate products are emulated on the tensor cores, so the ceiling of the arithmetic is a fraction "
+                        "of the bf16 peak (see `kernel` / DESIGN.md 5.1)",
                 "whole_step_tflops_per_gpu": step_tflops,
+                "whole_step_flops_source": "executed work: n*(FM + MALA) per iteration + device-counted active chain-evaluations of the ODE loops",
                 "phase_ms": {"fm_loss_grad": ms_fm, "mala_iteration": ms_mala, "outer_iteration_mala": ms_iter,
                              "outer_iteration_flow": ms / a.steps - m * ms_iter},
                 "phase_tflops": {"fm_loss_grad": n * fl["fm"] / (ms_fm * 1e-3) / 1e12,
@@ -438,21 +520,25 @@ def main():
                "h2d_bytes_per_step": n * D * 4, "d2h_bytes_per_step": n * D * 4 + 4,
                "api": "HotLoop.reset_positions(init_fn) + (m+1) x HotLoop.iteration() per step, pinned host buffers"}
 
-    # ---- CPU baseline (rank 0, N=1 only) -------------------------------------------------------------
+    # ---- CPU baseline (rank 0, N=1 only): ONE sample step of the reference arm's definition ----------
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        rate, cores, sample, _ = cpu_oracle_rate(m, a.head_scale, budget_s=15.0)
-        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        cs = CpuSample(a.config, m, a.head_scale)
+        cs.step()
+        cpu = {"value": cs.rate()[0], "unit": UNIT, "cores": cs.cores(), "kind": "port", "sample": cs.describe()}
 
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        line = {"metric": metric_name(a.config), "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                "dtype": "f32 (dense layers: fp32 emulated on tensor cores, tf32 hi*hi + bf16 cross terms / 3xTF32, fp32 accumulate)", "data": "synthetic",
+                "dtype": "f32", "data": "synthetic",
                 "config": workload_config(a, n_total), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+                "graph_replays": int(graph_replays),
                 "roofline": roofline, "cpu_baseline": cpu,
                 "fm_iterations_per_s": a.steps * cyc / (ms / 1e3),
                 "ode_stats_last_flow_step": dict(zip(["accepted", "attempted", "max_attempts_per_chain", "field_evals"],
                                                      ode_stats)) if ode_stats else None,
+                "ode_chain_evals_per_step": chain_evals,
+                "arithmetic": "dense layers: fp32 products emulated on tensor cores (" + gemm_info + "), fp32 accumulate; everything else fp32",
                 "warmup_unit": a.warmup_unit}
         real_stdout.write(json.dumps(line) + "\n")
         real_stdout.flush()

@@ -67,6 +67,10 @@ typedef struct mfm_field {
     long long n_params;      /* total floats */
     const float* omega;      /* [F] fourier_random (module attribute, :350-351) */
     float grad_clip;         /* <=0: no clip; else clip grad logprob to +-grad_clip (:87-90) */
+    /* reference (base) distribution of the flow, ref_dists[args.ref_dist] (exe_flow_matching.py:48-54,149,244):
+     * IndepGaussian(dim, mean, var = ref_std^2); stdgauss = (0, 1), widegauss = (0, sqrt(5)).  Used by the conditional
+     * FM batch (x0 = mean + std * normal, :156) and by the independent / importance-sampling flow steps (:249-256,283-289). */
+    float ref_mean, ref_std;
 } mfm_field_t;
 
 typedef struct mfm_ode_opts {
@@ -175,7 +179,9 @@ int mfm_mala_step(const mfm_target_t* t, const uint32_t* rng_key, int per_chain_
 size_t mfm_ode_workspace_bytes(const mfm_field_t* f, const mfm_target_t* t, const mfm_ode_opts_t* o, int n);
 /* direction +1: transform_and_logdet (u -> x, ldj);  -1: inverse_and_logdet (x -> u, ldj).
  * hutch_keys uint32[n,2]: per-chain probe keys (ignored when !hutch).  stats (optional, device
- * int32[4]): total accepted steps, total attempted steps, max attempted steps, field evals. */
+ * int32[8], 8-byte aligned): total accepted steps, total attempted steps, max attempted steps per chain, field
+ * evaluations, then an int64 in [4..5]: chain-evaluations = rows actually evaluated summed over the field evaluations
+ * (finished chains are compacted away), [6..7] reserved. */
 int mfm_ode_flow(const mfm_field_t* f, const mfm_target_t* t, const mfm_ode_opts_t* o, int direction, int n,
                  const uint32_t* hutch_keys, const float* y0, float* y1, float* ldj, int* stats,
                  void* ws, size_t ws_bytes, mfm_stream_t stream);

@@ -35,6 +35,7 @@ class FieldDesc(C.Structure):
         ("dim", C.c_int), ("hidden", C.c_int), ("fourier_dim", C.c_int),
         ("params", c_f32p), ("w_off", C.c_longlong * 8), ("b_off", C.c_longlong * 8),
         ("n_params", C.c_longlong), ("omega", c_f32p), ("grad_clip", C.c_float),
+        ("ref_mean", C.c_float), ("ref_std", C.c_float),
     ]
 
 
@@ -154,13 +155,30 @@ def stream():
 
 
 _ws_cache: dict = {}
+_ws_generation = 0
+
+
+def workspace_generation() -> int:
+    """Bumped whenever a cached workspace is re-allocated: holders of raw pointers into one (a captured CUDA graph)
+    compare it with the value they saw and re-capture."""
+    return _ws_generation
 
 
 def workspace(nbytes: int, device, tag="default"):
-    """Grow-only scratch buffer per (device, tag)."""
+    """Grow-only scratch buffer per (device, tag).  Growing REPLACES the tensor; the old one stays alive in
+    `_ws_retired` while the generation counter tells graph holders to re-capture (a replay between the two would
+    otherwise touch freed memory)."""
+    global _ws_generation
     key = (str(device), tag)
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
+        if buf is not None:
+            _ws_retired.append(buf)
+            del _ws_retired[:-4]
+            _ws_generation += 1
         buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
         _ws_cache[key] = buf
     return buf
+
+
+_ws_retired: list = []

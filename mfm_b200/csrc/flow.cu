@@ -408,6 +408,7 @@ __global__ void ode_init_kernel(int n, int d, const float* __restrict__ y0, OdeS
         S.tf[i] = sgn > 0 ? t0 : 1.0f - t0;
     }
     if (i < 4) S.counters[i] = 0;
+    if (i == 0) { S.counters[10] = 0; S.counters[11] = 0; }      // 64-bit count of (chain, field evaluation) pairs of the RK loop
 }
 
 // initial_step_size part 1: h0 and the trial point y0 + h0 f0
@@ -511,7 +512,7 @@ __global__ void ode_stage4_kernel(int n, int d4, int s, OdeState S, int n_seg, f
 
 // deterministic stream compaction of the chains that are still integrating (single block)
 __global__ void __launch_bounds__(1024) ode_compact_kernel(int n, int n_seg, const int* __restrict__ seg, int* __restrict__ idx,
-                                                           int* __restrict__ n_active) {
+                                                           int* __restrict__ n_active, long long* __restrict__ chain_evals) {
     __shared__ int wsum[32];
     __shared__ int total;
     const int per = (n + 1023) / 1024;
@@ -535,7 +536,7 @@ __global__ void __launch_bounds__(1024) ode_compact_kernel(int n, int n_seg, con
     __syncthreads();
     int pos = wsum[w] + inc - cnt;
     for (int c = b; c < e; ++c) if (seg[c] < n_seg) idx[pos++] = c;
-    if (threadIdx.x == 0) *n_active = total;
+    if (threadIdx.x == 0) { *n_active = total; *chain_evals += 6ll * total; }    // the next RK iteration evaluates 6 stages on `total` rows
 }
 
 // gather the per-solve probe constants of the active chains into compact rows
@@ -649,10 +650,15 @@ __global__ void copy_out_kernel(int n, int d, const float* __restrict__ sx, cons
     if (i < n && ldj) ldj[i] = sl[i];
 }
 
-__global__ void write_stats_kernel(const int* __restrict__ counters, int n_eval, int* __restrict__ stats, int accumulate) {
+// stats: int32[8] = {accepted, attempted, max attempts per chain, field evaluations, chain-evaluations (int64 in [4..5]), 0, 0};
+// chain-evaluations = sum over field evaluations of the rows actually evaluated (active-chain compaction)
+__global__ void write_stats_kernel(const int* __restrict__ counters, int n_eval, long long host_chain_evals, int* __restrict__ stats,
+                                   int accumulate) {
     if (threadIdx.x == 0) {
-        if (accumulate) { stats[0] += counters[1]; stats[1] += counters[2]; stats[2] = max(stats[2], counters[3]); stats[3] += n_eval; }
-        else { stats[0] = counters[1]; stats[1] = counters[2]; stats[2] = counters[3]; stats[3] = n_eval; }
+        const long long ce = *reinterpret_cast<const long long*>(counters + 10) + host_chain_evals;
+        long long* out_ce = reinterpret_cast<long long*>(stats + 4);
+        if (accumulate) { stats[0] += counters[1]; stats[1] += counters[2]; stats[2] = max(stats[2], counters[3]); stats[3] += n_eval; *out_ce += ce; }
+        else { stats[0] = counters[1]; stats[1] = counters[2]; stats[2] = counters[3]; stats[3] = n_eval; *out_ce = ce; stats[6] = 0; stats[7] = 0; }
     }
 }
 
@@ -718,7 +724,7 @@ static int ode_solve(const mfm_field_t& F, const mfm_target_t& T, const mfm_ode_
     MFM_LAUNCH_CHECK();
     const int* idx = nullptr; const int* nact = nullptr; const float* zc = z;
     if (compact) {
-        ode_compact_kernel<<<1, 1024, 0, st>>>(n, TS.n_seg, S.seg, S.idx, S.n_active);
+        ode_compact_kernel<<<1, 1024, 0, st>>>(n, TS.n_seg, S.seg, S.idx, S.n_active, reinterpret_cast<long long*>(S.counters + 10));
         MFM_LAUNCH_CHECK();
         idx = S.idx; nact = S.n_active; zc = z_compact;
     }
@@ -741,7 +747,7 @@ static int ode_solve(const mfm_field_t& F, const mfm_target_t& T, const mfm_ode_
         ode_finish_kernel<<<gW, 256, 0, st>>>(n, d, S, TS, O.rtol, O.atol, O.mxstep);
         MFM_LAUNCH_CHECK();
         if (compact) {
-            ode_compact_kernel<<<1, 1024, 0, st>>>(n, TS.n_seg, S.seg, S.idx, S.n_active);
+            ode_compact_kernel<<<1, 1024, 0, st>>>(n, TS.n_seg, S.seg, S.idx, S.n_active, reinterpret_cast<long long*>(S.counters + 10));
             MFM_LAUNCH_CHECK();
         }
         MFM_CUDA_CHECK(cudaMemcpyAsync(hflag, S.counters, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -750,7 +756,12 @@ static int ode_solve(const mfm_field_t& F, const mfm_target_t& T, const mfm_ode_
     }
     copy_out_kernel<<<max(gE, 1), 256, 0, st>>>(n, d, S.outx, S.outl, y1, ldj);
     MFM_LAUNCH_CHECK();
-    if (stats) { write_stats_kernel<<<1, 32, 0, st>>>(S.counters, n_eval, stats, stats_accumulate); MFM_LAUNCH_CHECK(); }
+    if (stats) {
+        // rows evaluated outside the device count: the two evaluations of initial_step_size on all n rows, and without
+        // compaction (exact divergence) every evaluation runs on all n rows
+        const long long host_ce = compact ? 2ll * n : (long long)n * n_eval;
+        write_stats_kernel<<<1, 32, 0, st>>>(S.counters, n_eval, host_ce, stats, stats_accumulate); MFM_LAUNCH_CHECK();
+    }
     return MFM_OK;
 }
 
@@ -779,6 +790,11 @@ __global__ void axpy_kernel(long long total, const float* __restrict__ a, float 
                             float* __restrict__ out) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i < total) out[i] = a[i] + scale * eps[i];
+}
+// out = mean + std * eps   (ref_dist.sample_model, distributions.py:96-97)
+__global__ void ref_sample_kernel(long long total, float mean, float std_, const float* __restrict__ eps, float* __restrict__ out) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < total) out[i] = __fadd_rn(mean, __fmul_rn(std_, eps[i]));
 }
 
 // log N(x; mean, std) summed over the row (ref_dist.logprob, distributions.py:89-90)
@@ -833,6 +849,7 @@ static int check_field(const mfm_field_t* f, const mfm_target_t* t, const mfm_od
     if (!f || !t || !o) { mfm_set_last_error_msg("null descriptor"); return MFM_ERR_ARG; }
     if (f->dim != t->dim) { mfm_set_last_error_msg("field.dim != target.dim"); return MFM_ERR_ARG; }
     if (f->hidden <= 0 || f->fourier_dim <= 0 || !f->params || !f->omega) { mfm_set_last_error_msg("bad field descriptor"); return MFM_ERR_ARG; }
+    if (!(f->ref_std > 0.0f)) { mfm_set_last_error_msg("field.ref_std must be > 0 (reference distribution IndepGaussian(mean, std^2))"); return MFM_ERR_ARG; }
     return MFM_OK;
 }
 
@@ -935,15 +952,16 @@ int mfm_flow_mh_step(const mfm_field_t* f, const mfm_target_t* t, const mfm_ode_
         if (hutch && (rc = mfm_threefry_normal_batched(kh1, n, d, z, stream))) return rc;
         if ((rc = ode_solve(*f, *t, *o, +1, n, hutch ? z : nullptr, up, xp, Vp, stats, 1, S, B, zc, stream))) return rc;
     } else {
-        // independent proposal from the reference distribution N(0, I) (stdgauss, :48-49,249)
-        MFM_CUDA_CHECK(cudaMemcpyAsync(up, eps, tot * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+        // independent proposal from the reference distribution IndepGaussian(mean, std^2) (:48-49,249)
+        ref_sample_kernel<<<ceil_div(tot, 256), 256, 0, stream>>>(tot, f->ref_mean, f->ref_std, eps, up);
+        MFM_LAUNCH_CHECK();
         if (hutch && (rc = mfm_threefry_normal_batched(kh1, n, d, z, stream))) return rc;
         if ((rc = ode_solve(*f, *t, *o, +1, n, hutch ? z : nullptr, up, xp, Vp, stats, 0, S, B, zc, stream))) return rc;
         if (hutch && (rc = mfm_threefry_normal_batched(kh2, n, d, z, stream))) return rc;
         if ((rc = ode_solve(*f, *t, *o, -1, n, hutch ? z : nullptr, position, u0, V0, stats, 1, S, B, zc, stream))) return rc;
-        gauss_logprob_kernel<<<ceil_div(n, 8), 256, 0, stream>>>(n, d, up, 0.0f, 1.0f, lq_up);
+        gauss_logprob_kernel<<<ceil_div(n, 8), 256, 0, stream>>>(n, d, up, f->ref_mean, f->ref_std, lq_up);
         MFM_LAUNCH_CHECK();
-        gauss_logprob_kernel<<<ceil_div(n, 8), 256, 0, stream>>>(n, d, u0, 0.0f, 1.0f, lq_u0);
+        gauss_logprob_kernel<<<ceil_div(n, 8), 256, 0, stream>>>(n, d, u0, f->ref_mean, f->ref_std, lq_u0);
         MFM_LAUNCH_CHECK();
     }
     if ((rc = target_value_and_grad(*t, n, xp, lp, gp, nullptr, wt, stream))) return rc;

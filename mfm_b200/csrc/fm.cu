@@ -16,7 +16,7 @@ namespace mfm {
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 fm_batch_kernel(const uint32_t* __restrict__ rng_key, int n, int chain_offset, int n_total, int d, float sigma,
-                const float* __restrict__ x, float* __restrict__ times, float* __restrict__ xt,
+                float ref_mean, float ref_std, const float* __restrict__ x, float* __restrict__ times, float* __restrict__ xt,
                 float* __restrict__ target) {
     const int lane = threadIdx.x & 31;
     const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -39,7 +39,8 @@ fm_batch_kernel(const uint32_t* __restrict__ rng_key, int n, int chain_offset, i
         for (int s = 0; s < 2; ++s) {
             if (s == 1 && !has_hi) break;
             const uint32_t j = s == 0 ? b : hi;
-            const float x0 = bits_to_normal(s == 0 ? o.a : o.b);
+            // ref_dist.sample_model: mean + std * normal (distributions.py:96-97); exact identity for stdgauss (0, 1)
+            const float x0 = __fadd_rn(ref_mean, __fmul_rn(ref_std, bits_to_normal(s == 0 ? o.a : o.b)));
             const float eps = bits_to_normal(threefry_stream_word(k_gauss.a, k_gauss.b, gc * (uint32_t)d + j, total));
             const long long idx = (long long)c * d + j;
             const float xv = x[idx];
@@ -361,6 +362,7 @@ size_t mfm_fm_workspace_bytes(const mfm_field_t* f, const mfm_target_t* t, int n
 static int fm_check(const mfm_field_t* f, const mfm_target_t* t) {
     if (!f || !t) { mfm_set_last_error_msg("null descriptor"); return MFM_ERR_ARG; }
     if (f->dim != t->dim) { mfm_set_last_error_msg("field.dim != target.dim"); return MFM_ERR_ARG; }
+    if (!(f->ref_std > 0.0f)) { mfm_set_last_error_msg("field.ref_std must be > 0 (reference distribution IndepGaussian(mean, std^2))"); return MFM_ERR_ARG; }
     return MFM_OK;
 }
 
@@ -386,8 +388,8 @@ int mfm_fm_loss_grad_part(const mfm_field_t* f, const mfm_target_t* t, const uin
     FmBufs M;
     if (!fm_take(M, w, *f, n)) { mfm_set_last_error_msg("workspace too small (mfm_fm_loss_grad)"); return MFM_ERR_WORKSPACE; }
     if (part != 2) {
-        fm_batch_kernel<<<ceil_div(n, 8), 256, 0, stream>>>(rng_key, n, chain_offset, n_total, f->dim, sigma, positions,
-                                                             M.times, M.xt, M.target);
+        fm_batch_kernel<<<ceil_div(n, 8), 256, 0, stream>>>(rng_key, n, chain_offset, n_total, f->dim, sigma, f->ref_mean, f->ref_std,
+                                                             positions, M.times, M.xt, M.target);
         MFM_LAUNCH_CHECK();
     }
     return fm_forward_backward(*f, *t, n, M, loss_out, grads, stream, part);

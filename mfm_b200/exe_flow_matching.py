@@ -26,10 +26,28 @@ from .distributions import DeviceLogDensity, Distribution, GaussianMixture, Inde
 
 logger = logging.getLogger(__name__)
 
+def _broken_ref(name, why):
+    def make(dim, device=None):
+        raise TypeError(f"ref_dist='{name}' cannot be constructed in the reference either: {why}")
+    return make
+
+
+# exe_flow_matching.py:48-54.  'bimodal' and 'flat' fail at construction in the reference as coded (GaussianMixture(dim)
+# indexes an int, FlatDistribution() misses its argument); they raise here too.  'phifour' (PhiFourBase, a dense Gaussian)
+# is a §8(f) "next" row.
 ref_dists = {
     "stdgauss": lambda dim, device=None: IndepGaussian(dim, device=device),
     "widegauss": lambda dim, device=None: IndepGaussian(dim, var=5.0, device=device),
+    "bimodal": _broken_ref("bimodal", "GaussianMixture(dim) takes the modes, not a dimension (distributions.py:43-49)"),
+    "flat": _broken_ref("flat", "FlatDistribution() is called without its dim argument (exe_flow_matching.py:52)"),
 }
+
+
+def make_ref_dist(args, dim, device=None):
+    name = getattr(args, "ref_dist", "stdgauss")
+    if name not in ref_dists:
+        raise NotImplementedError(f"ref_dist='{name}' is not implemented on device (stdgauss, widegauss are)")
+    return ref_dists[name](dim, device=device)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -105,6 +123,15 @@ class VectorFieldNet:
         self.hidden = hs[0]
         self.fourier_random = fourier_random.to(torch.float32).contiguous()
         self.grad_clip = float(grad_clip) if grad_clip else 0.0
+        self.ref_mean, self.ref_std = 0.0, 1.0     # reference distribution of the flow (set_ref_dist)
+
+    def set_ref_dist(self, ref: IndepGaussian):
+        """ref_dists[args.ref_dist](dim) (:149,244): the kernels draw x0 / the independent proposal from it and evaluate
+        its log-density, so its parameters travel in the field descriptor."""
+        if not isinstance(ref, IndepGaussian):
+            raise NotImplementedError("the device kernels implement IndepGaussian reference distributions (stdgauss, widegauss)")
+        self.ref_mean, self.ref_std = float(ref.mean), float(ref.std)
+        return self
 
     def init(self, rng_key, x0=None, t0=None, head_scale: float = 0.0) -> VectorFieldParams:
         """Parameter initialisation.  NOT flax's RNG-folded lecun_normal (a 'next' row): fan-in
@@ -127,6 +154,7 @@ class VectorFieldNet:
         d.n_params = P.n_params
         d.omega = self.fourier_random.data_ptr()
         d.grad_clip = self.grad_clip
+        d.ref_mean, d.ref_std = self.ref_mean, self.ref_std
         return d
 
     def apply(self, P: VectorFieldParams, x: torch.Tensor, t: torch.Tensor, z: Optional[torch.Tensor] = None,
@@ -180,7 +208,8 @@ class TrainState:
         # [adam count, notfinite_count, total_notfinite, last_finite, scratch x4]
         self.opt_state = torch.tensor([0, 0, 0, 1, 0, 0, 0, 0], dtype=torch.int32, device=dev)
         self.step = 0
-        self.ref_dist = ref_dists[args.ref_dist](params.dim, device=dev)
+        self.ref_dist = make_ref_dist(args, params.dim, dev)                    # (:149)
+        model.set_ref_dist(self.ref_dist)
         self._pending = None      # gradient all-reduce handles of an update that has not been applied yet
 
 
@@ -274,6 +303,7 @@ def create_train_data_gn(dist: Distribution, model: VectorFieldNet, ode_opts, ar
     rank's shard of the ensemble (keys are rows of split(rng_key, n_total))."""
     lib = _lib.load()
     dim = dist.dim
+    model.set_ref_dist(make_ref_dist(args, dim, dist.device))                       # (:244)
     opts = _lib.OdeOpts(float(ode_opts.rtol), float(ode_opts.atol), int(ode_opts.mxstep), 1 if args.hutchs else 0,
                         int(ode_opts.n_times))
     if args.num_importance_samples > 0:
@@ -312,7 +342,7 @@ def create_train_data_gn(dist: Distribution, model: VectorFieldNet, ode_opts, ar
         is_acc = torch.empty(n, dtype=torch.uint8, device=dev)
         prop = torch.empty_like(x)
         weight = torch.empty(n, dtype=torch.float32, device=dev)
-        stats = torch.zeros(4, dtype=torch.int32, device=dev)
+        stats = torch.zeros(8, dtype=torch.int32, device=dev)
         fd, td = model.field_desc(P), logprob.desc()
         ws = _lib.workspace(lib.mfm_flow_mh_workspace_bytes(fd, td, opts, n), dev, "flow")
         _lib.check(lib.mfm_flow_mh_step(fd, td, opts, variant, _lib.ptr(rng_key.contiguous()), 1 if per_chain_keys else 0,
@@ -323,9 +353,13 @@ def create_train_data_gn(dist: Distribution, model: VectorFieldNet, ode_opts, ar
         return MALAState(x, l, g), MALAInfo(acc_rate, is_acc.bool(), prop, weight)
 
     def train_data_generator(rng_key, states: MALAState, count: int, vector_field_param, beta: float = 1.0,
-                             inplace: bool = False):
+                             inplace: bool = False, force: Optional[str] = None):
+        """force='mala' / 'flow' (not in the reference): the caller has already decided which branch of the `lax.cond`
+        (:304-313) this iteration takes (HotLoop's captured MALA iteration), so `count` is not consulted."""
         logprob = dist.tempered(beta)
-        if 0 < m < 1:
+        if force is not None:
+            is_flow = force == "flow"
+        elif 0 < m < 1:
             is_flow = count % (int(1 / m) + 1) != 0          # roles inverted for fractional m (:304-309)
         else:
             is_flow = count % (int(m) + 1) == 0              # :311
@@ -369,7 +403,8 @@ class HotLoop:
         # (nothing to gain) and for multi-rank runs (NCCL + pipelined update).
         small = self.n * dist.dim <= (1 << 18)
         self.graph = (small and self.world == 1 and not self.pipeline and os.environ.get("MFM_GRAPH", "1") != "0") if graph is None else bool(graph)
-        self._graph, self._graph_loss, self._eager_done = None, None, False
+        self._graph, self._graph_loss, self._eager_done, self._graph_ws_gen = None, None, False, -1
+        self.graph_replays, self.replayed_launches, self._graph_launches = 0, 0, 0   # diagnostics (bench.py's gpu_launches)
         self.lr_fn = create_learning_rate_fn(args.learning_iter, args.warmup_steps, args.learning_rate)
         self.state = create_train_state(model, P, self.lr_fn, args)
         self.gen, self.init_fn, self.transform_and_logdet = create_train_data_gn(
@@ -393,12 +428,22 @@ class HotLoop:
 
     def _mala_iteration_body(self):
         keys = mrandom.split(self.key_sample, 3)
-        self.states, self.last_info = self.gen(keys[1], self.states, 1 if not self.is_flow_iteration(1) else 2, self.P, self.beta,
-                                               inplace=True)
+        # only MALA iterations come here (iteration()): say so explicitly instead of encoding it in a fake count, which
+        # cannot be done for fractional mcmc_per_flow_steps (m = 0.5: counts 1 and 2 are both flow iterations)
+        self.states, self.last_info = self.gen(keys[1], self.states, self.count, self.P, self.beta, inplace=True, force="mala")
         loss, _ = self.state.loss_and_grad(keys[2], self.states.position, self.chain_offset, self.n_total)
         self.state.apply_gradients()
         self.key_sample.copy_(keys[0])
         return loss
+
+    def _mala_iteration_body_sizing(self):
+        """Make every workspace this iteration uses big enough BEFORE a capture (allocation is illegal inside one): the
+        size queries are host-only."""
+        lib = _lib.load()
+        fd, td = self.model.field_desc(self.P), self.dist._desc(1.0)
+        dev = self.states.position.device
+        _lib.workspace(lib.mfm_fm_workspace_bytes(fd, td, self.n), dev, "fm")
+        _lib.workspace(lib.mfm_mala_workspace_bytes(td, self.n), dev, "mala")
 
     def _graph_iteration(self):
         """MALA iteration through a CUDA graph: the first one runs eagerly (sizes every workspace), the second is captured,
@@ -406,14 +451,22 @@ class HotLoop:
         if not self._eager_done:
             self._eager_done = True
             return self._mala_iteration_body()
-        if self._graph is None or self._graph_beta != self.beta:
+        if self._graph is None or self._graph_beta != self.beta or self._graph_ws_gen != _lib.workspace_generation():
+            # (a workspace the captured kernels point into may have been re-allocated by a bigger request elsewhere:
+            #  the generation counter says so and the iteration is captured again against the live buffers)
+            self._mala_iteration_body_sizing()
             g = torch.cuda.CUDAGraph()
             step = self.state.step
+            l0 = _lib.load().mfm_launch_count()
             with torch.cuda.graph(g):
                 self._graph_loss = self._mala_iteration_body()
+            self._graph_launches = _lib.load().mfm_launch_count() - l0     # kernels one replay launches
             self.state.step = step            # capture records launches, it does not run them
             self._graph, self._graph_beta, self._graph_info = g, self.beta, self.last_info
+            self._graph_ws_gen = _lib.workspace_generation()
         self._graph.replay()
+        self.graph_replays += 1
+        self.replayed_launches += self._graph_launches
         self.state.step += 1
         self.last_info = self._graph_info     # the graph's output buffers (a flow-MH iteration in between replaced the reference)
         return self._graph_loss
@@ -526,7 +579,7 @@ def run(dist: Distribution, args, target_gn=None, device=None, log_every: int = 
     rank, world = parallel.world_info()
     n_total = args.num_chain
     lo, hi = parallel.shard_range(n_total, rank, world)
-    iter_per_temp = max(args.anneal_iter // args.num_anneal_temp, 1)
+    iter_per_temp = args.anneal_iter // args.num_anneal_temp                                       # (:331; 0 raises at `count % 0` as in the reference)
     # key_target, key_sample, key_init, key_dist, key_fourier, key_gen = split(PRNGKey(seed), 6)   (:333)
     keys = mrandom.split(mrandom.PRNGKey(args.seed, dev), 6)
     key_sample, key_init, key_dist, key_fourier, key_gen = keys[1], keys[2], keys[3], keys[4], keys[5]
@@ -555,7 +608,7 @@ def run(dist: Distribution, args, target_gn=None, device=None, log_every: int = 
         if log_every and (count % log_every == 0 or count == args.learning_iter):
             acc = loop.last_info.acceptance_rate if not use_real_samples else torch.full((2,), float("nan"))
             history.append({"count": count, "loss": float(loss.item()), "learning_rate": loop.lr_fn(count - 1),
-                            "acceptance avg.": float(acc.mean().item()), "acceptance std.": float(acc.std().item()),
+                            "acceptance avg.": float(acc.mean().item()), "acceptance std.": float(acc.std(unbiased=False).item()),  # jnp .std(): ddof=0
                             "beta": loop.beta, "train_time": time.time() - t0})
             logger.info(str(history[-1]))
     loop.flush()
@@ -566,6 +619,10 @@ def run(dist: Distribution, args, target_gn=None, device=None, log_every: int = 
     if final_sampling:
         # (:453-459) every rank draws the same eval_iter * num_chain samples (the draw is not sharded)
         from .mcmc_utils import max_mean_disc, stein_disc
+        # with a target generator the reference REBINDS key_gen: key_gen, key_loss = split(key_target) (:371), so the real
+        # samples and the final sampling both derive from split(key_target)[0]; without one key_gen is the 6th key of :333
+        if target_gn is not None:
+            key_gen = mrandom.split(keys[0].clone())[0].clone()
         fs = sample_flow(key_gen.clone(), dist, loop.state.ref_dist, loop.transform_and_logdet, P, args.eval_iter * n_total)
         flow_samples, exact_samples = fs["flow_samples"], fs["exact_samples"]
         out.update(flow_samples=flow_samples, exact_samples=exact_samples, weights=fs["weights"])
@@ -581,8 +638,9 @@ def run(dist: Distribution, args, target_gn=None, device=None, log_every: int = 
         data = [args.mcmc_per_flow_steps, args.learning_iter, train_time, logpdf, logpdf_, stein[0], stein_[0], stein[1], stein_[1]]
         columns = ["mcmc/flow", "learn iter", "train time", "logpdf", "logpdf*", "KSD U-stat", "KSD U-stat*", "KSD V-stat", "KSD V-stat*"]
         if target_gn is not None:
-            # real samples: vmap(target_gn)(split(key_target, n)) (:336); target_gn maps uint32[n,2] keys -> [n,d] here
-            real_samples = target_gn(mrandom.split(keys[0].clone(), args.eval_iter * n_total))
+            # real samples: vmap(target_gn)(split(key_gen, n_iter * n_chain)) with the rebound key_gen (:371-373);
+            # target_gn maps uint32[n,2] keys -> [n,d] here
+            real_samples = target_gn(mrandom.split(key_gen.clone(), args.eval_iter * n_total))
             mmd = float(max_mean_disc(real_samples, flow_samples).item())
             mmd_ = float(max_mean_disc(real_samples, exact_samples).item())
             logger.info(f"Max mean disc of flow samples= {mmd}")

@@ -135,7 +135,7 @@ def rw_flow_mh_step(keys, state, target, flow: Flow, beta=1.0, stats=None):
         acc = u <= acc_prob
     new = MALAState(np.where(acc[:, None], xp, x), np.where(acc, lp, l), np.where(acc[:, None], gp, g))
     if stats is not None:
-        stats.update(inv=s_inv, fwd=s_fwd, log_acc=log_acc, u=u, u0=u0, V0=V0, Vp=Vp)
+        stats.update(inv=s_inv, fwd=s_fwd, log_acc=log_acc, u=u, u0=u0, V0=V0, Vp=Vp, lp=lp)
     return new, MALAInfo(acc_prob, acc, xp, np.zeros(N, dt))
 
 
@@ -157,7 +157,7 @@ def indep_flow_mh_step(keys, state, target, flow: Flow, ref, beta=1.0, stats=Non
         acc = u <= acc_prob
     new = MALAState(np.where(acc[:, None], xp, x), np.where(acc, lp, l), np.where(acc[:, None], gp, g))
     if stats is not None:
-        stats.update(log_acc=log_acc, u=u)
+        stats.update(log_acc=log_acc, u=u, lp=lp)
     return new, MALAInfo(acc_prob, acc, xp, np.zeros(N, dt))
 
 

@@ -88,6 +88,22 @@ def _tol(got, ref64, ref32, floor, scale=None):
     return err, max(floor, 10.0 * ref)
 
 
+_MEASURED = {}
+
+
+def _record(name, nis, key, value):
+    """measured parity numbers, written to gpurun_out/r02_flow_mh_parity.json (quoted in DESIGN.md)"""
+    import json, os
+    _MEASURED.setdefault(f"{name}/{'indep' if nis < 0 else 'rw'}", {})[key] = value
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "r02_flow_mh_parity.json"), "w") as fh:
+            json.dump(_MEASURED, fh, indent=1, sort_keys=True)
+    except OSError:
+        pass
+
+
 def _gn(s, mcmc=10, nis=0, step=0.1):
     from mfm_b200 import exe_flow_matching as E
     args = SimpleNamespace(hutchs=s.hutch, num_importance_samples=nis, mcmc_per_flow_steps=mcmc, step_size=step)
@@ -106,7 +122,7 @@ def test_push_pull_vs_oracle(cuda, setups, name):
     st_o = {}
     x_ref, ldj_ref = flow.transform_and_logdet(keys, u, st_o)
     x32, ldj32 = flow.transform_and_logdet(keys, u.astype(np.float32))
-    stats = torch.zeros(4, dtype=torch.int32, device=cuda)
+    stats = torch.zeros(8, dtype=torch.int32, device=cuda)
     x, ldj = transform_and_logdet(key_dev(keys, cuda), to_dev(u, cuda), s.P, stats)
     # log-det: a d-term cancelling sum evaluated in float32 carries ~1e-6*d absolute round-off
     ldj_floor = 5e-3 + 3e-6 * s.ot.dim
@@ -114,7 +130,9 @@ def test_push_pull_vs_oracle(cuda, setups, name):
     assert err < tol, (name, err, tol)
     err, tol = _tol(ldj.cpu().numpy(), ldj_ref, ldj32, ldj_floor)
     assert err < tol, (name, err, tol)
-    acc, tried, mx, nev = stats.cpu().tolist()
+    acc, tried, mx, nev = stats.cpu().tolist()[:4]
+    chain_evals = int(stats[4:6].cpu().view(torch.int64).item())
+    assert 2 * n <= chain_evals <= n * nev
     assert abs(tried - int(st_o["n_try"].sum())) <= max(3, 0.15 * tried), (tried, st_o["n_try"].sum())
     assert nev == 2 + 6 * mx
     # inverse direction + round trip
@@ -140,7 +158,7 @@ def test_identity_flow_zero_heads(cuda, setups):
     P.kernel(4).zero_(); P.kernel(7).zero_(); P.bias(4).zero_(); P.bias(7).zero_()
     gen, _, push = _gn(s)
     u = to_dev(np.random.default_rng(0).standard_normal((8, 64)), cuda)
-    stats = torch.zeros(4, dtype=torch.int32, device=cuda)
+    stats = torch.zeros(8, dtype=torch.int32, device=cuda)
     x, ldj = push(key_dev(tf.split(tf.PRNGKey(1), 8), cuda), u, P, stats)
     assert torch.allclose(x, u, atol=1e-6) and torch.all(ldj == 0)
     assert stats.cpu().tolist()[2] == 7       # dt: 1e-6 * 10^k until t >= 1
@@ -173,17 +191,25 @@ def test_flow_mh_step(cuda, setups, name, nis):
     la32 = dbg32["log_acc"].astype(np.float64)
     err, tol = _tol(info_d.proposed_position.cpu().numpy(), info_o.proposed_position, info_32.proposed_position, 2e-3)
     assert err < tol, (name, err, tol)
-    # log acceptance ratio: float32 evaluation of l' - V' - l - V0 (|l| up to ~1e3) + ODE sensitivity
-    scale = np.maximum(1.0, np.abs(st_o.logdensity))
-    la_tol = 5e-3 * scale + 3e-6 * s.ot.dim + 10.0 * np.abs(la32 - la)
+    # log acceptance ratio l' - V' - l - V0 (:271-274).  Its float32 evaluation is exact to a few ulps of the largest
+    # term (|l| ~ 2e3 for pines / phi-four: 4 ulp = 1e-3) and the two log-dets carry the adaptive solve's own float32
+    # sensitivity, which the float32 ORACLE measures chain by chain (|la32 - la64|): the device must be that good (x4).
+    # No term proportional to |l|: a band of +-10 in log alpha would accept any decision.
+    l_mag = np.maximum(np.abs(st_o.logdensity), np.abs(dbg["lp"]) if "lp" in dbg else 0.0)
+    ulp = np.spacing(np.maximum(l_mag, 1.0).astype(np.float32)).astype(np.float64)
+    la_tol = np.maximum(1e-3, 4.0 * ulp) + 4.0 * np.abs(la32 - la)
     with np.errstate(over="ignore", divide="ignore"):
         la_d = np.log(info_d.acceptance_rate.cpu().numpy().astype(np.float64))
         logu = np.log(dbg["u"])
     fin = np.isfinite(la) & np.isfinite(la_d) & (np.abs(la) < 80)
-    assert (np.abs(la_d[fin] - la[fin]) < la_tol[fin]).all(), (name, np.abs(la_d[fin] - la[fin]).max())
+    la_err = np.abs(la_d[fin] - la[fin])
+    _record(name, nis, "log_alpha_abs_err_max", float(la_err.max()) if la_err.size else 0.0)
+    _record(name, nis, "log_alpha_abs_err_f32_oracle_max", float(np.abs(la32 - la)[fin].max()) if la_err.size else 0.0)
+    assert (la_err < la_tol[fin]).all(), (name, la_err.max(), la_tol[fin][np.argmax(la_err - la_tol[fin])])
     acc_d = info_d.is_accepted.cpu().numpy(); acc_o = info_o.is_accepted
     band = np.abs(la - logu) < la_tol
     assert ((acc_d == acc_o) | band).all(), name
+    _record(name, nis, "decision_flips", int((acc_d != acc_o).sum())); _record(name, nis, "chains", int(n))
     same = acc_d == acc_o
     err, tol = _tol(new_d.position.cpu().numpy()[same], new_o.position[same], new_o.position[same].astype(np.float32), tol)
     assert err < tol
@@ -200,3 +226,40 @@ def test_train_data_generator_dispatch(cuda, setups):
     assert (info.proposed_weight != 0).any()           # MALA info carries exp(...) weights
     _, info = gen(key, st, 3, s.P, 1.0)
     assert (info.proposed_weight == 0).all()           # flow-MH info has weight 0
+
+
+@pytest.mark.parametrize("name,n", [("phi-four", 256), ("pines", 96)])
+def test_flow_mh_decision_flip_rate(cuda, setups, name, n):
+    """Accept decisions of the flow-MH step against the float64 oracle on a larger ensemble, for the two targets whose
+    log-densities are ~2e3 (where a relative band would be vacuous): absolute log alpha error and the number of flipped
+    decisions are MEASURED and bounded.  A decision can only flip when the oracle's |log alpha - log u| is smaller than the
+    device's log alpha error, so the flip count is bounded by the chains inside that band."""
+    s = setups[name]
+    gen, init_fn, _ = _gn(s, nis=0)
+    flow = _flow(s)
+    x0 = _positions(s, n, seed=11)
+    beta = 1.0
+    st_d = init_fn(to_dev(x0, cuda), beta)
+    st_o = OS.mala_init(x0, s.ot, beta)
+    key = tf.PRNGKey(4242)
+    dbg = {}
+    new_o, info_o = OS.rw_flow_mh_step(tf.split(key, n), st_o, s.ot, flow, beta, dbg)
+    new_d, info_d = gen.flow_step(key_dev(key, cuda), st_d, s.dd.tempered(beta), s.P)
+    la = dbg["log_acc"]
+    with np.errstate(over="ignore", divide="ignore"):
+        la_d = np.log(info_d.acceptance_rate.cpu().numpy().astype(np.float64))
+        logu = np.log(dbg["u"])
+    fin = np.isfinite(la) & np.isfinite(la_d) & (np.abs(la) < 80)
+    err = np.abs(la_d - la)[fin]
+    acc_d = info_d.is_accepted.cpu().numpy(); acc_o = info_o.is_accepted
+    flips = int((acc_d != acc_o).sum())
+    tag = f"{name}-flip"
+    _record(tag, 0, "chains", n); _record(tag, 0, "log_alpha_abs_err_max", float(err.max()))
+    _record(tag, 0, "log_alpha_abs_err_median", float(np.median(err))); _record(tag, 0, "decision_flips", flips)
+    _record(tag, 0, "flip_rate", flips / n); _record(tag, 0, "oracle_accept_rate", float(acc_o.mean()))
+    # the bar VERDICT r01 set: |log alpha error| <= 5e-3 absolute on pines / phi-four
+    assert err.max() <= 5e-3, (name, err.max())
+    # every flipped decision must sit inside the error band around the threshold, and the rate stays below 1 %
+    band = np.abs(la - logu) <= 5e-3
+    assert ((acc_d == acc_o) | band).all(), name
+    assert flips <= max(1, n // 100), (name, flips)

@@ -114,13 +114,15 @@ def test_full_size_flow_push_subset_matches_small_run(cuda, big):
     _, _, push = E.create_train_data_gn(big.dd, big.model, opts, args)
     keys = big.mr.split(big.mr.PRNGKey(9, cuda), N)
     u = big.mr.normal(big.mr.split(big.mr.PRNGKey(10, cuda), N), (D,))
-    stats = torch.zeros(4, dtype=torch.int32, device=cuda)
+    stats = torch.zeros(8, dtype=torch.int32, device=cuda)
     y, ldj = push(keys, u, big.P, stats)
     idx = torch.from_numpy(ROWS).to(cuda)
     keys8 = keys.view(torch.int32)[idx].contiguous().view(torch.uint32)      # torch cannot index uint32 tensors
     y8, ldj8 = push(keys8, u[idx].contiguous(), big.P)
     assert torch.isfinite(y).all() and torch.isfinite(ldj).all()
-    acc, tried, mx, nev = stats.cpu().tolist()
+    acc, tried, mx, nev = stats.cpu().tolist()[:4]
+    chain_evals = int(stats[4:6].cpu().view(torch.int64).item())
+    assert 2 * N <= chain_evals <= N * nev
     assert nev == 2 + 6 * mx and acc <= tried
     # different kernels serve 8 rows (warp-level MMA) and 65 536 rows (persistent tcgen05): agreement to the ODE tolerance
     assert rel_err(y[idx].cpu().numpy(), y8.cpu().numpy()) < 1e-3

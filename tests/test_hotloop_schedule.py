@@ -20,8 +20,9 @@ def _loop(monkeypatch, m, pipeline, real_sampler=None):
     loop.states = E.MALAState(torch.zeros(4, 2), torch.zeros(4), torch.zeros(4, 2))
     monkeypatch.setattr(E.mrandom, "split", lambda key, num=2: torch.zeros((num, 2), dtype=torch.int64))
 
-    def gen(key, states, count, P, beta, inplace=False):
-        log.append(("flow" if loop.is_flow_iteration(count) else "mala", count))
+    def gen(key, states, count, P, beta, inplace=False, force=None):
+        kind = force if force is not None else ("flow" if loop.is_flow_iteration(count) else "mala")
+        log.append((kind, count))
         return states, SimpleNamespace(acceptance_rate=torch.zeros(4))
 
     pending = []
@@ -92,3 +93,19 @@ def test_real_samples_replace_the_generator(monkeypatch):
     assert drawn == [(4, 2), (4, 2)] and [e[0] for e in log] == ["grad", "adamw", "grad", "adamw"]
     assert loop.states.logdensity is None and torch.equal(loop.states.position, torch.ones(4, 2))
     assert loop.temper() == 1.0 and not loop.is_flow_iteration(3)
+
+
+def test_graph_path_runs_mala_for_fractional_m(monkeypatch):
+    """m = 0.5 inverts the roles (flow unless count % 3 == 0, exe_flow_matching.py:304-309): counts 1 and 2 are BOTH flow
+    iterations, so the captured MALA iteration cannot be selected through a fake count - it is forced explicitly.  The
+    graph machinery itself needs a GPU; here the eager first pass of the graph path is what is checked."""
+    from mfm_b200 import exe_flow_matching as E
+    loop, log = _loop(monkeypatch, m=0.5, pipeline=False)
+    loop.graph, loop._eager_done, loop._graph = True, False, None
+    loop.key_sample = torch.zeros(2, dtype=torch.int64)
+    loop.state.step = 0
+    for _ in range(3):
+        loop.iteration()
+    # counts 1, 2: flow (eager path); count 3: MALA through the graph path's eager first pass
+    assert [e for e in log if e[0] in ("mala", "flow")] == [("flow", 1), ("flow", 2), ("mala", 3)]
+    assert [e[0] for e in log] == ["flow", "grad", "adamw"] * 2 + ["mala", "grad", "adamw"]
