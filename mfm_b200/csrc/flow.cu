@@ -12,6 +12,8 @@
 // own (t, dt, segment, step count) and is masked once finished — exactly the semantics of the
 // batched while_loop that jax.vmap produces.  Dense layers run on tensor cores (3xTF32).
 #include "internal.h"
+#include <string.h>
+#include <stdlib.h>
 #include "gemm_tf32x3.cuh"
 
 namespace mfm {
@@ -106,9 +108,19 @@ struct EpiFieldDiv {
 
 int dense(int n, int in, int out, const float* A, long long lda, const float* WT, long long ldwt, const float* bias, int relu,
                  float* C, long long ldc, const float* mask, long long ldm, int mask_div, cudaStream_t st,
-                 const int* n_rows_dev) {
+                 const int* n_rows_dev, DenseAmax am) {
     GemmShape p{n, out, in, A, lda, WT, ldwt, n_rows_dev};
+    p.a_amax = am.a; p.a_amax2 = am.a2; p.a_bound = am.a_bound; p.a_split = am.a_split; p.a_scale_src = am.a_scale_src;
+    if (am.out_split && am.w_norm && (am.a || am.a_bound > 0.0f)) {
+        // C also leaves pre-split for the layer that consumes it (EpiStdS)
+        EpiStdS e{C, ldc, bias, mask, ldm, nullptr, 0, relu, mask_div, am.out_split, am.a, am.a2, am.a_bound, am.w_norm, am.bias_amax, am.add_bound, am.out_bound};
+        e.alt_amax = am.alt_amax; e.alt_w_norm = am.alt_w_norm; e.alt_bias = am.alt_bias;
+        e.amax_out = am.out;
+        MFM_CUDA_CHECK((launch_gemm<true, false>(p, e, st)));
+        return MFM_OK;
+    }
     EpiStd e{C, ldc, bias, mask, ldm, nullptr, 0, 1.0f, relu, mask_div};
+    e.amax_out = am.out;
     MFM_CUDA_CHECK((launch_gemm<true, false>(p, e, st)));
     return MFM_OK;
 }
@@ -125,6 +137,32 @@ __global__ void transpose_kernel(int rows, int cols, const float* __restrict__ i
     for (int j = threadIdx.y; j < 32; j += 8) {
         const int c = c0 + j, r = r0 + threadIdx.x;
         if (r < rows && c < cols) out[(long long)c * rows + r] = tile[threadIdx.x][j];
+    }
+}
+
+// operator norms of the dense kernels for the output bounds of the split-writing epilogue (EpiStdS): per layer the largest
+// absolute column sum (forward product x W), the largest absolute row sum (backward-data product d W^T) and max |bias|.
+// One warp per matrix row, coalesced: row sums of W [in][out] give the row norm, row sums of its transpose (wt, [out][in],
+// already built for the GEMMs) the column norm.  grid (8 layers, 2 kinds, WN_SLICES); slots zeroed by the caller.
+constexpr int WN_SLICES = 32;
+struct WeightDims { int in[8], out[8]; long long w_off[8], b_off[8]; };
+__global__ void __launch_bounds__(256) weight_norms_kernel(const float* __restrict__ params, const float* __restrict__ wt, WeightDims D,
+                                                           float* __restrict__ pool) {
+    const int layer = blockIdx.x, kind = blockIdx.y, slice = blockIdx.z;
+    const int rows = kind == 0 ? D.out[layer] : D.in[layer], cols = kind == 0 ? D.in[layer] : D.out[layer];
+    const float* W = (kind == 0 ? wt : params) + D.w_off[layer];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float m = 0.0f;
+    for (int r = slice * 8 + warp; r < rows; r += WN_SLICES * 8) {
+        float sum = 0.0f;
+        for (int c = lane; c < cols; c += 32) sum += fabsf(W[(long long)r * cols + c]);
+        m = fmaxf(m, warp_sum(sum));
+    }
+    amax_publish_warp(pool + (kind == 0 ? AM_WNORM_COL : AM_WNORM_ROW) + layer, m);
+    if (kind == 0 && slice == 0) {
+        float b = 0.0f;
+        for (int o = threadIdx.x; o < D.out[layer]; o += blockDim.x) b = fmaxf(b, fabsf(params[D.b_off[layer] + o]));
+        amax_publish_warp(pool + AM_BIAS + layer, b);
     }
 }
 
@@ -145,27 +183,23 @@ __global__ void presplit_kernel(const float4* __restrict__ src, uint4* __restric
     dst[2 * g] = make_uint4(pack(a.x, a.y), pack(a.z, a.w), pack(c.x, c.y), pack(c.z, c.w));
     dst[2 * g + 1] = make_uint4(pack(rest(a.x), rest(a.y)), pack(rest(a.z), rest(a.w)), pack(rest(c.x), rest(c.y)), pack(rest(c.z), rest(c.w)));
 }
-// split16 layout of the experimental kernel (gemm_tcgen05_split16.cuh): 16 consecutive floats -> 16 hi | 16 lo bf16 parts
-__global__ void presplit16_kernel(const float4* __restrict__ src, uint4* __restrict__ dst, long long n16) {
+// split16 layout of the scaled-fp16 kernel (gemm_tcgen05_h16.cuh): 16 consecutive floats -> 16 hi | 16 lo fp16 parts of the
+// values scaled by h16_scale(*amax) (the kernel derives the same power of two from the same slot)
+__global__ void presplit_h16_kernel(const float4* __restrict__ src, uint4* __restrict__ dst, long long n16, const float* __restrict__ amax) {
     const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (g >= n16) return;
+    const float sc = tc2h::h16_scale(*amax);
     float4 v[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) v[j] = __ldg(src + 4 * g + j);
-    auto pack = [](float first, float second) { uint32_t r; asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(second), "f"(first)); return r; };
     uint32_t hp[8], lp[8];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        hp[2 * j] = pack(v[j].x, v[j].y); hp[2 * j + 1] = pack(v[j].z, v[j].w);
-        lp[2 * j] = pack(v[j].x - __uint_as_float(hp[2 * j] << 16), v[j].y - __uint_as_float(hp[2 * j] & 0xFFFF0000u));
-        lp[2 * j + 1] = pack(v[j].z - __uint_as_float(hp[2 * j + 1] << 16), v[j].w - __uint_as_float(hp[2 * j + 1] & 0xFFFF0000u));
-    }
+    tc2h::split16(v, sc, hp, lp);
     dst[4 * g] = make_uint4(hp[0], hp[1], hp[2], hp[3]); dst[4 * g + 1] = make_uint4(hp[4], hp[5], hp[6], hp[7]);
     dst[4 * g + 2] = make_uint4(lp[0], lp[1], lp[2], lp[3]); dst[4 * g + 3] = make_uint4(lp[4], lp[5], lp[6], lp[7]);
 }
-int presplit_weights(const float* src, float* dst, long long n_floats, cudaStream_t st) {
-    if (tc2s::gemm_split16() && n_floats % 16 == 0) {
-        presplit16_kernel<<<ceil_div(n_floats / 16, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(src), reinterpret_cast<uint4*>(dst), n_floats / 16);
+int presplit_weights(const float* src, float* dst, long long n_floats, const float* amax, cudaStream_t st) {
+    if (tc2h::gemm_h16() && amax != nullptr && n_floats % 16 == 0) {
+        presplit_h16_kernel<<<ceil_div(n_floats / 16, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(src), reinterpret_cast<uint4*>(dst), n_floats / 16, amax);
         MFM_LAUNCH_CHECK();
         return MFM_OK;
     }
@@ -175,23 +209,40 @@ int presplit_weights(const float* src, float* dst, long long n_floats, cudaStrea
     return MFM_OK;
 }
 
-void field_register_mirrors(const mfm_field_t& F, const FieldBufs& B);
+// Mirrors of the dense kernels: the range [w_off[0], end of Dense_7) of the flat buffer (biases in between are converted too,
+// harmlessly).  h16 mirrors need 16-float groups and 64-byte aligned tiles, bf16-cross mirrors 8-float groups.
+static bool mirror_range(const mfm_field_t& F, const FieldBufs& B, bool& h16, long long& lo, long long& hi) {
+    if (B.wx == nullptr || B.wxo == nullptr) return false;
+    h16 = tc2h::gemm_h16() != 0 && B.amax != nullptr;
+    const int g = h16 ? 16 : 8;
+    if (((reinterpret_cast<uintptr_t>(F.params) | reinterpret_cast<uintptr_t>(B.wt)) & (h16 ? 63 : 31)) != 0) return false;
+    for (int i = 0; i < 8; ++i) { int in, out; layer_dims(F, i, in, out); if (in % g || out % g || F.w_off[i] % g) return false; }
+    int in7, out7; layer_dims(F, 7, in7, out7);
+    lo = F.w_off[0]; hi = (long long)F.w_off[7] + (long long)in7 * out7;
+    return true;
+}
+
 int field_prepare_weights(const mfm_field_t& F, FieldBufs& B, cudaStream_t st) {
-    tc2p::clear_cross();
-    bool mirrors = B.wx != nullptr && B.wxo != nullptr && ((reinterpret_cast<uintptr_t>(F.params) | reinterpret_cast<uintptr_t>(B.wt)) & 31) == 0;
+    tc2p::clear_cross(); tc2h::clear_mirrors_h16();
     for (int i = 0; i < 8; ++i) {
         int in, out; layer_dims(F, i, in, out);
         transpose_kernel<<<dim3(ceil_div(out, 32), ceil_div(in, 32)), dim3(32, 8), 0, st>>>(in, out, F.params + F.w_off[i], B.wt + F.w_off[i]);
         MFM_LAUNCH_CHECK();
-        mirrors = mirrors && in % 8 == 0 && out % 8 == 0 && F.w_off[i] % 8 == 0;
     }
-    if (mirrors) {
-        // the dense kernels occupy [w_off[0], w_off[7] + in7*out7) of the flat buffer; biases in between (if any) are converted too, harmlessly
-        int in7, out7; layer_dims(F, 7, in7, out7);
-        const long long lo = F.w_off[0], hi = (long long)F.w_off[7] + (long long)in7 * out7;
+    if (B.amax) {
+        // max |parameter|: the scale of both weight mirrors, and the bound of the exact path's basis tangents (entries of W2)
+        MFM_CUDA_CHECK(tc2h::launch_absmax(F.params, F.n_params, 1, (int)(F.n_params & ~3ll), nullptr, B.amax + AM_W, st));
+        MFM_CUDA_CHECK(cudaMemsetAsync(B.amax + AM_WNORM_COL, 0, 24 * sizeof(float), st));
+        WeightDims D;
+        for (int i = 0; i < 8; ++i) { layer_dims(F, i, D.in[i], D.out[i]); D.w_off[i] = F.w_off[i]; D.b_off[i] = F.b_off[i]; }
+        weight_norms_kernel<<<dim3(8, 2, WN_SLICES), 256, 0, st>>>(F.params, B.wt, D, B.amax);
+        MFM_LAUNCH_CHECK();
+    }
+    bool h16 = false; long long lo = 0, hi = 0;
+    if (mirror_range(F, B, h16, lo, hi)) {
         int rc;
-        if ((rc = presplit_weights(B.wt + lo, B.wx + lo, hi - lo, st))) return rc;
-        if ((rc = presplit_weights(F.params + lo, B.wxo + lo, hi - lo, st))) return rc;
+        if ((rc = presplit_weights(B.wt + lo, B.wx + lo, hi - lo, h16 ? B.amax + AM_W : nullptr, st))) return rc;
+        if ((rc = presplit_weights(F.params + lo, B.wxo + lo, hi - lo, h16 ? B.amax + AM_W : nullptr, st))) return rc;
         field_register_mirrors(F, B);
     }
     return MFM_OK;
@@ -199,22 +250,25 @@ int field_prepare_weights(const mfm_field_t& F, FieldBufs& B, cudaStream_t st) {
 
 // (re-)announce the mirrors field_prepare_weights built in this workspace (a later ABI call on the same workspace: FM part 2)
 void field_register_mirrors(const mfm_field_t& F, const FieldBufs& B) {
-    tc2p::clear_cross();
-    bool mirrors = B.wx != nullptr && B.wxo != nullptr && ((reinterpret_cast<uintptr_t>(F.params) | reinterpret_cast<uintptr_t>(B.wt)) & 31) == 0;
-    for (int i = 0; i < 8; ++i) { int in, out; layer_dims(F, i, in, out); mirrors = mirrors && in % 8 == 0 && out % 8 == 0 && F.w_off[i] % 8 == 0; }
-    if (!mirrors) return;
-    int in7, out7; layer_dims(F, 7, in7, out7);
-    const long long lo = F.w_off[0], hi = (long long)F.w_off[7] + (long long)in7 * out7;
-    tc2p::register_cross(B.wt + lo, (size_t)(hi - lo), B.wx + lo);
-    tc2p::register_cross(F.params + lo, (size_t)(hi - lo), B.wxo + lo);
+    tc2p::clear_cross(); tc2h::clear_mirrors_h16();
+    bool h16 = false; long long lo = 0, hi = 0;
+    if (!mirror_range(F, B, h16, lo, hi)) return;
+    if (h16) {
+        tc2h::register_mirror_h16(B.wt + lo, (size_t)(hi - lo), B.wx + lo, B.amax + AM_W);
+        tc2h::register_mirror_h16(F.params + lo, (size_t)(hi - lo), B.wxo + lo, B.amax + AM_W);
+    } else {
+        tc2p::register_cross(B.wt + lo, (size_t)(hi - lo), B.wx + lo);
+        tc2p::register_cross(F.params + lo, (size_t)(hi - lo), B.wxo + lo);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
 // elementwise helpers
 // ---------------------------------------------------------------------------------------------
 __global__ void fourier_kernel(int n, int F, const float* __restrict__ omega, const float* __restrict__ t,
-                               float* __restrict__ ff, const int* __restrict__ n_rows_dev) {
+                               float* __restrict__ ff, const int* __restrict__ n_rows_dev, float* __restrict__ ff_s, float* __restrict__ ff_bound) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i == 0 && ff_bound) *ff_bound = 1.0f;          // the slot the copy's scale derives from (consumer's a_scale_src)
     if (n_rows_dev) n = min(n, *n_rows_dev);
     if (i >= (long long)n * F) return;
     const int c = (int)(i / F), j = (int)(i % F);
@@ -223,27 +277,60 @@ __global__ void fourier_kernel(int n, int F, const float* __restrict__ omega, co
     float sv, cv; sincosf(deg, &sv, &cv);
     ff[(long long)c * 2 * F + j] = cv;
     ff[(long long)c * 2 * F + F + j] = sv;
+    if (ff_s) {
+        // pre-split copy for Dense_0 (split16 layout, scale 2^14 = h16_scale(1): |cos|, |sin| <= 1)
+        const float sc = 16384.0f;
+        __half* row = reinterpret_cast<__half*>(ff_s + (long long)c * 2 * F);
+        const float xc = cv * sc, xs = sv * sc;
+        const __half hc = __float2half_rn(xc), hs = __float2half_rn(xs);
+        const int jc = j, js = F + j;
+        row[2 * (jc & ~15) + (jc & 15)] = hc; row[2 * (jc & ~15) + 16 + (jc & 15)] = __float2half_rn(xc - __half2float(hc));
+        row[2 * (js & ~15) + (js & 15)] = hs; row[2 * (js & ~15) + 16 + (js & 15)] = __float2half_rn(xs - __half2float(hs));
+    }
 }
 
-// out[i,:] = a[i,:] * (gate[i,:] > 0)
+// out[i,:] = a[i,:] * (gate[i,:] > 0);  amax (optional): max |out| is folded into the slot (out feeds a scaled-fp16 GEMM)
 __global__ void gate_kernel(long long total, int H, const float* __restrict__ a, const float* __restrict__ gate,
-                            long long ldg, float* __restrict__ out, const int* __restrict__ n_rows_dev) {
+                            long long ldg, float* __restrict__ out, const int* __restrict__ n_rows_dev, float* __restrict__ amax) {
+    __shared__ float red[32];
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (n_rows_dev) total = min(total, (long long)(*n_rows_dev) * H);
-    if (i >= total) return;
-    const long long r = i / H; const int c = (int)(i % H);
-    out[i] = gate[r * ldg + c] > 0.0f ? a[i] : 0.0f;
+    float m = 0.0f;
+    if (i < total) {
+        const long long r = i / H; const int c = (int)(i % H);
+        const float v = gate[r * ldg + c] > 0.0f ? a[i] : 0.0f;
+        out[i] = v; m = fabsf(v);
+    }
+    if (amax) amax_publish_block(amax, m, red);
 }
 
-// same, four columns per thread (H % 4 == 0, 16-byte aligned rows): HBM-bound, 12 B moved per element
+// same, four columns per thread (H % 4 == 0, 16-byte aligned rows): HBM-bound, 12 B moved per element.
+// out_s (optional): pre-split copy of `out` scaled by h16_scale(*scale_src) - gating only zeroes entries, so the exact maximum
+// of `a` bounds the result.
 __global__ void gate4_kernel(long long total4, int H4, const float4* __restrict__ a, const float4* __restrict__ gate,
-                             long long ldg4, float4* __restrict__ out, const int* __restrict__ n_rows_dev) {
+                             long long ldg4, float4* __restrict__ out, const int* __restrict__ n_rows_dev, float* __restrict__ amax,
+                             float* __restrict__ out_s, const float* __restrict__ scale_src) {
+    __shared__ float red[32];
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (n_rows_dev) total4 = min(total4, (long long)(*n_rows_dev) * H4);
-    if (i >= total4) return;
-    const float4 g = ldg4 == H4 ? __ldg(gate + i) : __ldg(gate + (i / H4) * ldg4 + (i % H4));
-    const float4 v = __ldg(a + i);
-    out[i] = make_float4(g.x > 0.0f ? v.x : 0.0f, g.y > 0.0f ? v.y : 0.0f, g.z > 0.0f ? v.z : 0.0f, g.w > 0.0f ? v.w : 0.0f);
+    float m = 0.0f;
+    if (i < total4) {
+        const float4 g = ldg4 == H4 ? __ldg(gate + i) : __ldg(gate + (i / H4) * ldg4 + (i % H4));
+        const float4 v = __ldg(a + i);
+        const float4 o = make_float4(g.x > 0.0f ? v.x : 0.0f, g.y > 0.0f ? v.y : 0.0f, g.z > 0.0f ? v.z : 0.0f, g.w > 0.0f ? v.w : 0.0f);
+        out[i] = o; m = amax4(0.0f, o);
+        if (out_s) {
+            const float sc = tc2h::h16_scale(*scale_src);
+            const long long e = 4 * i;                                  // flat element index (rows are H4 * 4 wide, H % 16 == 0)
+            uint2 hp, lp;
+            split_pair(o.x * sc, o.y * sc, hp.x, lp.x);
+            split_pair(o.z * sc, o.w * sc, hp.y, lp.y);
+            char* gp = reinterpret_cast<char*>(out_s + (e & ~15ll)) + 2 * (int)(e & 15);
+            *reinterpret_cast<uint2*>(gp) = hp;
+            *reinterpret_cast<uint2*>(gp + 32) = lp;
+        }
+    }
+    if (amax) amax_publish_block(amax, m, red);
 }
 
 // exact path: tan[(i,j),:] = W2[j,:] * (h2[i,:] > 0)
@@ -293,7 +380,8 @@ size_t field_bufs_bytes(const mfm_field_t& F, const mfm_target_t& T, int n, bool
     size_t b = ws_slice(N * 2 * F.fourier_dim, 4) + ws_slice(N * H, 4) * 6 + ws_slice(N * 2 * H, 4) + ws_slice(N * d, 4) * 3;
     if (hutch) b += ws_slice(N * H, 4) + ws_slice(N * d, 4) + ws_slice(N * gemm_n_tiles((int)d), 4);
     else b += 2 * ws_slice(N * d * H, 4);
-    return b + 3 * ws_slice((size_t)F.n_params, 4);
+    b += ws_slice(N * 2 * F.fourier_dim, 4) + ws_slice(N * H, 4) * 6 + ws_slice(N * 2 * H, 4);      // pre-split copies (ff, h0, h2, h5, h6, ta, tb, cat)
+    return b + 3 * ws_slice((size_t)F.n_params, 4) + ws_slice(AM_POOL, 4);
 }
 
 bool field_bufs_take(FieldBufs& B, Workspace& w, const mfm_field_t& F, int n, bool hutch) {
@@ -308,6 +396,11 @@ bool field_bufs_take(FieldBufs& B, Workspace& w, const mfm_field_t& F, int n, bo
     else { B.tan_a = w.take<float>(N * d * H); B.tan_b = w.take<float>(N * d * H); }
     B.wt = w.take<float>((size_t)F.n_params);
     B.wx = w.take<float>((size_t)F.n_params); B.wxo = w.take<float>((size_t)F.n_params);
+    B.amax = w.take<float>(AM_POOL);
+    B.ff_s = w.take<float>(N * 2 * F.fourier_dim);
+    B.h0_s = w.take<float>(N * H); B.h2_s = w.take<float>(N * H); B.h5_s = w.take<float>(N * H); B.h6_s = w.take<float>(N * H);
+    B.ta_s = w.take<float>(N * H); B.tb_s = w.take<float>(N * H);
+    B.cat_s = w.take<float>(N * 2 * H);
     return w.ok;
 }
 
@@ -316,51 +409,110 @@ bool field_bufs_take(FieldBufs& B, Workspace& w, const mfm_field_t& F, int n, bo
 #define B_(i) (F.params + F.b_off[i])
 
 // per-solve constants of the Hutchinson estimator: z W2 and (pines) z K^-1
-static int field_prepare_probe(const mfm_field_t& F, const mfm_target_t& T, int n, const float* z, FieldBufs& B, cudaStream_t st) {
+static int field_prepare_probe(const mfm_field_t& F, const mfm_target_t& T, int n, const float* z, FieldBufs& B, cudaStream_t st,
+                               float z_bound) {
     const int d = F.dim, H = F.hidden;
-    int rc = dense(n, d, H, z, d, WT_(2), d, nullptr, 0, B.zw2, H, nullptr, 0, 1, st, nullptr);
+    DenseAmax am; am.a_bound = z_bound;
+    if (tc2h::gemm_h16() && B.amax) {       // exact max |z W2|: scales the gated tangent's pre-split copy in every field evaluation of the solve
+        MFM_CUDA_CHECK(cudaMemsetAsync(B.amax + AM_ZW2, 0, sizeof(float), st));
+        am.out = B.amax + AM_ZW2;
+    }
+    int rc = dense(n, d, H, z, d, WT_(2), d, nullptr, 0, B.zw2, H, nullptr, 0, 1, st, nullptr, am);
     if (rc) return rc;
-    if (T.kind == MFM_TARGET_PINES) return pines_kinv_gemm(T, n, z, d, B.zkinv, d, nullptr, st);
+    if (T.kind == MFM_TARGET_PINES) return pines_kinv_gemm(T, n, z, d, B.zkinv, d, nullptr, st, z_bound);
     return MFM_OK;
 }
+
+// |jax.random.normal| < 8 for float32 draws: the uniform is clipped to [nextafter(-1, 0), 1 - 2^-23] and sqrt(2) erfinv of
+// that is within +-5.5 - a host-known bound for the probes this library draws itself (caller-supplied probes get a reduction)
+static constexpr float NORMAL_BOUND = 8.0f;
 
 // out_v[n,d] = sgn * v(x, tfield);  out_l[n] = -sgn * div v   (z != null: Hutchinson; else exact)
 int field_eval(const mfm_field_t& F, const mfm_target_t& T, int n, const float* x, const float* tfield,
                const float* z, float sgn, float* out_v, float* out_l, FieldBufs& B, cudaStream_t st,
-               const int* nr, const int* row_map) {
+               const int* nr, const int* row_map, const float* x_amax) {
+    const float* zw2_amax = (tc2h::gemm_h16() && B.amax && z) ? B.amax + AM_ZW2 : nullptr;   // written by field_prepare_probe
     const int d = F.dim, H = F.hidden, Fd = F.fourier_dim;
     int rc;
-    fourier_kernel<<<ceil_div((long long)n * Fd, 256), 256, 0, st>>>(n, Fd, F.omega, tfield, B.ff, nr);
+    // tensor maxima for the scaled-fp16 GEMMs (AmaxSlot): this evaluation's slots start from zero; x gets one reduction
+    // when its producer did not track it (it feeds Dense_2 and, for pines, the K^-1 GEMM)
+    float* am = tc2h::gemm_h16() ? B.amax : nullptr;
+    auto slot = [&](int i) -> float* { return am ? am + i : nullptr; };
+    if (am) {
+        MFM_CUDA_CHECK(cudaMemsetAsync(am, 0, AM_EVAL_END * sizeof(float), st));
+        if (!x_amax && d % 16 == 0 && n >= 256) {
+            MFM_CUDA_CHECK(tc2h::launch_absmax(x, d, n, d, nr, am + AM_X, st));
+            x_amax = am + AM_X;
+        }
+    }
+    // pre-split copies: a layer's result leaves the epilogue in tensor-core format too (EpiStdS) and the consuming layer's TMA
+    // loads that copy (no splitter work, a quarter less shared-memory traffic in the consumer)
+    const bool sp = am != nullptr && B.h0_s != nullptr && H % 16 == 0 && (2 * Fd) % 16 == 0 && n >= 256 && ((reinterpret_cast<uintptr_t>(B.h0_s) | reinterpret_cast<uintptr_t>(B.cat_s)) & 63) == 0;
+    auto BD = [&](int i) -> float* { return am + AM_BOUND + i; };
+    auto WC = [&](int l) -> const float* { return am + AM_WNORM_COL + l; };
+    auto BA = [&](int l) -> const float* { return am + AM_BIAS + l; };
+    // (exact max of A [, second slot], host bound) -> exact max of C
+    auto A_ = [&](const float* a, const float* a2, float bound, float* out) { DenseAmax m; m.a = a; m.a2 = a2; m.a_bound = bound; m.out = out; return m; };
+    // ... A pre-split (copy, slot its scale came from)
+    auto IN_ = [&](DenseAmax m, const float* a_split, const float* src) { if (sp) { m.a_split = a_split; m.a_scale_src = src; } return m; };
+    // ... C pre-split too (copy, slot id of its bound, layer whose column norm / bias bound the product)
+    auto OUT_ = [&](DenseAmax m, float* c_split, int slot_id, int layer, bool has_bias) {
+        if (sp) { m.out_split = c_split; m.out_bound = BD(slot_id); m.w_norm = WC(layer); m.bias_amax = has_bias ? BA(layer) : nullptr; }
+        return m;
+    };
+    fourier_kernel<<<ceil_div((long long)n * Fd, 256), 256, 0, st>>>(n, Fd, F.omega, tfield, B.ff, nr, sp ? B.ff_s : nullptr, sp ? BD(AM_FF) : nullptr);
     MFM_LAUNCH_CHECK();
-    if ((rc = dense(n, 2 * Fd, H, B.ff, 2 * Fd, WT_(0), 2 * Fd, B_(0), 1, B.h0, H, nullptr, 0, 1, st, nr))) return rc;
-    if ((rc = dense(n, H, H, B.h0, H, WT_(1), H, B_(1), 1, B.cat + H, 2 * H, nullptr, 0, 1, st, nr))) return rc;       // s_t
-    if ((rc = dense(n, d, H, x, d, WT_(2), d, B_(2), 1, B.h2, H, nullptr, 0, 1, st, nr))) return rc;
-    if ((rc = dense(n, H, H, B.h2, H, WT_(3), H, B_(3), 1, B.cat, 2 * H, nullptr, 0, 1, st, nr))) return rc;           // s_x
-    if ((rc = dense(n, H, d, B.cat + H, 2 * H, WT_(4), H, B_(4), 0, B.gt, d, nullptr, 0, 1, st, nr))) return rc;       // nn_t
-    if ((rc = dense(n, 2 * H, H, B.cat, 2 * H, WT_(5), 2 * H, B_(5), 1, B.h5, H, nullptr, 0, 1, st, nr))) return rc;
-    if ((rc = dense(n, H, H, B.h5, H, WT_(6), H, B_(6), 1, B.h6, H, nullptr, 0, 1, st, nr))) return rc;
+    // first layers of the two branches (the exact maxima of h0 and h2 feed the COMMON scale of cat = [s_x | s_t])
+    if ((rc = dense(n, 2 * Fd, H, B.ff, 2 * Fd, WT_(0), 2 * Fd, B_(0), 1, B.h0, H, nullptr, 0, 1, st, nr,
+                    OUT_(IN_(A_(nullptr, nullptr, 1.0f, slot(AM_H0)), B.ff_s, BD(AM_FF)), B.h0_s, AM_H0, 0, true)))) return rc;      // |cos|, |sin| <= 1
+    if ((rc = dense(n, d, H, x, d, WT_(2), d, B_(2), 1, B.h2, H, nullptr, 0, 1, st, nr, OUT_(A_(x_amax, nullptr, 0, slot(AM_H2)), B.h2_s, AM_H2, 2, true)))) return rc;
+    {   // s_t and s_x: one scale for both halves of cat
+        DenseAmax mt = OUT_(IN_(A_(slot(AM_H0), nullptr, 0, slot(AM_ST)), B.h0_s, BD(AM_H0)), B.cat_s + H, AM_ST, 1, true);
+        DenseAmax mx = OUT_(IN_(A_(slot(AM_H2), nullptr, 0, slot(AM_SX)), B.h2_s, BD(AM_H2)), B.cat_s, AM_SX, 3, true);
+        if (sp) { mt.alt_amax = slot(AM_H2); mt.alt_w_norm = WC(3); mt.alt_bias = BA(3); mx.alt_amax = slot(AM_H0); mx.alt_w_norm = WC(1); mx.alt_bias = BA(1); }
+        if ((rc = dense(n, H, H, B.h0, H, WT_(1), H, B_(1), 1, B.cat + H, 2 * H, nullptr, 0, 1, st, nr, mt))) return rc;       // s_t
+        if ((rc = dense(n, H, H, B.h2, H, WT_(3), H, B_(3), 1, B.cat, 2 * H, nullptr, 0, 1, st, nr, mx))) return rc;           // s_x
+    }
+    if ((rc = dense(n, H, d, B.cat + H, 2 * H, WT_(4), H, B_(4), 0, B.gt, d, nullptr, 0, 1, st, nr, IN_(A_(slot(AM_ST), nullptr, 0, nullptr), B.cat_s + H, BD(AM_ST))))) return rc;       // nn_t
+    if ((rc = dense(n, 2 * H, H, B.cat, 2 * H, WT_(5), 2 * H, B_(5), 1, B.h5, H, nullptr, 0, 1, st, nr,
+                    OUT_(IN_(A_(slot(AM_SX), slot(AM_ST), 0, slot(AM_H5)), B.cat_s, BD(AM_SX)), B.h5_s, AM_H5, 5, true)))) return rc;
+    if ((rc = dense(n, H, H, B.h5, H, WT_(6), H, B_(6), 1, B.h6, H, nullptr, 0, 1, st, nr,
+                    OUT_(IN_(A_(slot(AM_H5), nullptr, 0, slot(AM_H6)), B.h5_s, BD(AM_H5)), B.h6_s, AM_H6, 6, true)))) return rc;
     // untempered grad logprob (clipped) and the Hessian term of the divergence
     mfm_target_t T1 = T; T1.beta = 1.0f;
     const bool want_div = out_l != nullptr;
     if ((rc = target_field_terms(T1, n, x, z, B.zkinv, F.grad_clip, B.gc, (want_div && z) ? B.hx : nullptr,
-                                 (want_div && !z) ? B.hx : nullptr, nr, st))) return rc;
+                                 (want_div && !z) ? B.hx : nullptr, nr, st, x_amax))) return rc;
     {
         GemmShape p{n, d, H, B.h6, (long long)H, WT_(7), (long long)H, nr};
+        p.a_amax = slot(AM_H6);
+        if (sp) { p.a_split = B.h6_s; p.a_scale_src = BD(AM_H6); }
         EpiFieldV e{out_v, (long long)d, B_(7), B.gt, B.gc, (long long)d, sgn, row_map};
         MFM_CUDA_CHECK((launch_gemm<true, false>(p, e, st)));
     }
     if (!want_div) return MFM_OK;
     if (z) {
+        // tangent of the probe through the x branch: z W2 (per-solve constant, its exact maximum in AM_ZW2 when the caller
+        // tracked it) gated by relu'(h2); gating only zeroes entries, so that maximum also scales the pre-split copy
+        const bool spt = sp && zw2_amax != nullptr;
         if (H % 4 == 0 && ((reinterpret_cast<uintptr_t>(B.zw2) | reinterpret_cast<uintptr_t>(B.h2) | reinterpret_cast<uintptr_t>(B.ta)) & 15) == 0)
             gate4_kernel<<<ceil_div((long long)n * (H / 4), 256), 256, 0, st>>>((long long)n * (H / 4), H / 4, reinterpret_cast<const float4*>(B.zw2),
-                                                                                reinterpret_cast<const float4*>(B.h2), H / 4, reinterpret_cast<float4*>(B.ta), nr);
+                                                                                reinterpret_cast<const float4*>(B.h2), H / 4, reinterpret_cast<float4*>(B.ta), nr, slot(AM_TA0),
+                                                                                spt ? B.ta_s : nullptr, zw2_amax);
         else
-            gate_kernel<<<ceil_div((long long)n * H, 256), 256, 0, st>>>((long long)n * H, H, B.zw2, B.h2, H, B.ta, nr);
+            gate_kernel<<<ceil_div((long long)n * H, 256), 256, 0, st>>>((long long)n * H, H, B.zw2, B.h2, H, B.ta, nr, slot(AM_TA0));
         MFM_LAUNCH_CHECK();
-        if ((rc = dense(n, H, H, B.ta, H, WT_(3), H, nullptr, 0, B.tb, H, B.cat, 2 * H, 1, st, nr))) return rc;
-        if ((rc = dense(n, H, H, B.tb, H, WT_(5), 2 * H, nullptr, 0, B.ta, H, B.h5, H, 1, st, nr))) return rc;   // first H rows of W5
-        if ((rc = dense(n, H, H, B.ta, H, WT_(6), H, nullptr, 0, B.tb, H, B.h6, H, 1, st, nr))) return rc;
+        const bool vec_gate = spt && H % 4 == 0 && ((reinterpret_cast<uintptr_t>(B.zw2) | reinterpret_cast<uintptr_t>(B.h2) | reinterpret_cast<uintptr_t>(B.ta)) & 15) == 0;
+        DenseAmax m1 = OUT_(A_(slot(AM_TA0), nullptr, 0, slot(AM_TB0)), B.tb_s, AM_TB0, 3, false);
+        if (vec_gate) { m1.a_split = B.ta_s; m1.a_scale_src = zw2_amax; }
+        if ((rc = dense(n, H, H, B.ta, H, WT_(3), H, nullptr, 0, B.tb, H, B.cat, 2 * H, 1, st, nr, m1))) return rc;
+        if ((rc = dense(n, H, H, B.tb, H, WT_(5), 2 * H, nullptr, 0, B.ta, H, B.h5, H, 1, st, nr,
+                        OUT_(IN_(A_(slot(AM_TB0), nullptr, 0, slot(AM_TA1)), B.tb_s, BD(AM_TB0)), B.ta_s, AM_TA1, 5, false)))) return rc;   // first H rows of W5
+        if ((rc = dense(n, H, H, B.ta, H, WT_(6), H, nullptr, 0, B.tb, H, B.h6, H, 1, st, nr,
+                        OUT_(IN_(A_(slot(AM_TA1), nullptr, 0, slot(AM_TB1)), B.ta_s, BD(AM_TA1)), B.tb_s, AM_TB1, 6, false)))) return rc;
         GemmShape p{n, d, H, B.tb, (long long)H, WT_(7), (long long)H, nr};
+        p.a_amax = slot(AM_TB1);
+        if (sp) { p.a_split = B.tb_s; p.a_scale_src = BD(AM_TB1); }
         const int nt = gemm_n_tiles(d);
         EpiFieldDiv e{z, B.gt, B.hx, (long long)d, B.divpart, nt};
         MFM_CUDA_CHECK((launch_gemm<true, false>(p, e, st)));
@@ -372,9 +524,10 @@ int field_eval(const mfm_field_t& F, const mfm_target_t& T, int n, const float* 
         if (nr) { mfm_set_last_error_msg("internal: compaction is not used with the exact divergence"); return MFM_ERR_UNSUPPORTED; }
         basis_tangent_kernel<<<ceil_div(rows * H, 256), 256, 0, st>>>(n, d, H, W_(2), B.h2, B.tan_a, nullptr);
         MFM_LAUNCH_CHECK();
-        if ((rc = dense((int)rows, H, H, B.tan_a, H, WT_(3), H, nullptr, 0, B.tan_b, H, B.cat, 2 * H, d, st, nullptr))) return rc;
-        if ((rc = dense((int)rows, H, H, B.tan_b, H, WT_(5), 2 * H, nullptr, 0, B.tan_a, H, B.h5, H, d, st, nullptr))) return rc;
-        if ((rc = dense((int)rows, H, H, B.tan_a, H, WT_(6), H, nullptr, 0, B.tan_b, H, B.h6, H, d, st, nullptr))) return rc;
+        // the basis tangents are entries of W2 or zero: max |parameter| bounds them
+        if ((rc = dense((int)rows, H, H, B.tan_a, H, WT_(3), H, nullptr, 0, B.tan_b, H, B.cat, 2 * H, d, st, nullptr, A_(slot(AM_W), nullptr, 0, slot(AM_TB0))))) return rc;
+        if ((rc = dense((int)rows, H, H, B.tan_b, H, WT_(5), 2 * H, nullptr, 0, B.tan_a, H, B.h5, H, d, st, nullptr, A_(slot(AM_TB0), nullptr, 0, slot(AM_TA1))))) return rc;
+        if ((rc = dense((int)rows, H, H, B.tan_a, H, WT_(6), H, nullptr, 0, B.tan_b, H, B.h6, H, d, st, nullptr, A_(slot(AM_TA1), nullptr, 0, nullptr)))) return rc;
         exact_trace_kernel<<<ceil_div(n, 8), 256, 0, st>>>(n, d, H, B.tan_b, W_(7), B.gt, B.hx, -sgn, out_l, nullptr, row_map);
         MFM_LAUNCH_CHECK();
     }
@@ -408,7 +561,7 @@ __global__ void ode_init_kernel(int n, int d, const float* __restrict__ y0, OdeS
         S.tf[i] = sgn > 0 ? t0 : 1.0f - t0;
     }
     if (i < 4) S.counters[i] = 0;
-    if (i == 0) { S.counters[10] = 0; S.counters[11] = 0; }      // 64-bit count of (chain, field evaluation) pairs of the RK loop
+    if (i == 0) { S.counters[10] = 0; S.counters[11] = 0; S.counters[12] = 0; }   // 64-bit count of (chain, field evaluation) pairs; loop iterations
 }
 
 // initial_step_size part 1: h0 and the trial point y0 + h0 f0
@@ -464,50 +617,62 @@ __global__ void ode_h1_kernel(int n, int d, OdeState S, float rtol, float atol) 
 // stage s in 1..6: xi = y + dt * sum_j beta[s-1][j] k_j ; field time t + alpha dt.
 // Writes compact row r (chain idx[r]) when idx != null.
 __global__ void ode_stage_kernel(int n, int d, int s, OdeState S, int n_seg, float sgn, const int* __restrict__ idx,
-                                 const int* __restrict__ n_active) {
+                                 const int* __restrict__ n_active, float* __restrict__ amax) {
+    __shared__ float red[32];
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (idx) n = min(n, *n_active);
-    if (i >= (long long)n * d) return;
-    const int r = (int)(i / d), col = (int)(i % d);
-    const int c = idx ? idx[r] : r;
-    if (S.seg[c] >= n_seg) return;            // finished chain: leave its stage input untouched
-    const long long o = (long long)c * d + col;
-    const float h = S.dt[c];
-    float acc = 0.0f;
+    float m = 0.0f;
+    if (i < (long long)n * d) {
+        const int r = (int)(i / d), col = (int)(i % d);
+        const int c = idx ? idx[r] : r;
+        if (S.seg[c] < n_seg) {                  // finished chain: leave its stage input untouched
+            const long long o = (long long)c * d + col;
+            const float h = S.dt[c];
+            float acc = 0.0f;
 #pragma unroll
-    for (int j = 0; j < 6; ++j) if (j < s) acc += c_beta[s - 1][j] * S.kx[j][o];
-    S.xi[i] = S.yx[o] + h * acc;
-    if (col == 0) {
-        const float ti = S.t[c] + h * c_alpha[s - 1];
-        S.tf[r] = sgn > 0 ? ti : 1.0f - ti;
+            for (int j = 0; j < 6; ++j) if (j < s) acc += c_beta[s - 1][j] * S.kx[j][o];
+            const float v = S.yx[o] + h * acc;
+            S.xi[i] = v; m = fabsf(v);
+            if (col == 0) {
+                const float ti = S.t[c] + h * c_alpha[s - 1];
+                S.tf[r] = sgn > 0 ? ti : 1.0f - ti;
+            }
+        }
     }
+    if (amax) amax_publish_block(amax, m, red);  // the stage input is the A operand of Dense_2 (and of the pines K^-1 GEMM)
 }
 
 // same, four columns per thread (d % 4 == 0): (s + 2) arrays of 4 B per element, HBM-bound
 __global__ void ode_stage4_kernel(int n, int d4, int s, OdeState S, int n_seg, float sgn, const int* __restrict__ idx,
-                                  const int* __restrict__ n_active) {
+                                  const int* __restrict__ n_active, float* __restrict__ amax) {
+    __shared__ float red[32];
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (idx) n = min(n, *n_active);
-    if (i >= (long long)n * d4) return;
-    const int r = (int)(i / d4), col = (int)(i % d4);
-    const int c = idx ? idx[r] : r;
-    if (S.seg[c] >= n_seg) return;            // finished chain: leave its stage input untouched
-    const long long o = (long long)c * d4 + col;
-    const float h = S.dt[c];
-    float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    float m = 0.0f;
+    if (i < (long long)n * d4) {
+        const int r = (int)(i / d4), col = (int)(i % d4);
+        const int c = idx ? idx[r] : r;
+        if (S.seg[c] < n_seg) {                  // finished chain: leave its stage input untouched
+            const long long o = (long long)c * d4 + col;
+            const float h = S.dt[c];
+            float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 #pragma unroll
-    for (int j = 0; j < 6; ++j)
-        if (j < s) {
-            const float b = c_beta[s - 1][j];
-            const float4 k = __ldg(reinterpret_cast<const float4*>(S.kx[j]) + o);
-            acc.x += b * k.x; acc.y += b * k.y; acc.z += b * k.z; acc.w += b * k.w;     // same order as the scalar kernel
+            for (int j = 0; j < 6; ++j)
+                if (j < s) {
+                    const float b = c_beta[s - 1][j];
+                    const float4 k = __ldg(reinterpret_cast<const float4*>(S.kx[j]) + o);
+                    acc.x += b * k.x; acc.y += b * k.y; acc.z += b * k.z; acc.w += b * k.w;     // same order as the scalar kernel
+                }
+            const float4 y = __ldg(reinterpret_cast<const float4*>(S.yx) + o);
+            const float4 v = make_float4(y.x + h * acc.x, y.y + h * acc.y, y.z + h * acc.z, y.w + h * acc.w);
+            reinterpret_cast<float4*>(S.xi)[i] = v; m = amax4(0.0f, v);
+            if (col == 0) {
+                const float ti = S.t[c] + h * c_alpha[s - 1];
+                S.tf[r] = sgn > 0 ? ti : 1.0f - ti;
+            }
         }
-    const float4 y = __ldg(reinterpret_cast<const float4*>(S.yx) + o);
-    reinterpret_cast<float4*>(S.xi)[i] = make_float4(y.x + h * acc.x, y.y + h * acc.y, y.z + h * acc.z, y.w + h * acc.w);
-    if (col == 0) {
-        const float ti = S.t[c] + h * c_alpha[s - 1];
-        S.tf[r] = sgn > 0 ? ti : 1.0f - ti;
     }
+    if (amax) amax_publish_block(amax, m, red);
 }
 
 // deterministic stream compaction of the chains that are still integrating (single block)
@@ -655,11 +820,97 @@ __global__ void copy_out_kernel(int n, int d, const float* __restrict__ sx, cons
 __global__ void write_stats_kernel(const int* __restrict__ counters, int n_eval, long long host_chain_evals, int* __restrict__ stats,
                                    int accumulate) {
     if (threadIdx.x == 0) {
+        // device-resident loop: n_eval < 0 carries -(evaluations before the loop), counters[12] the iterations the loop ran;
+        // host_chain_evals < 0 carries -n (every evaluation ran on all n rows: no compaction)
+        if (n_eval < 0) n_eval = -n_eval + 6 * counters[12];
+        if (host_chain_evals < 0) host_chain_evals = -host_chain_evals * n_eval;
         const long long ce = *reinterpret_cast<const long long*>(counters + 10) + host_chain_evals;
         long long* out_ce = reinterpret_cast<long long*>(stats + 4);
         if (accumulate) { stats[0] += counters[1]; stats[1] += counters[2]; stats[2] = max(stats[2], counters[3]); stats[3] += n_eval; *out_ce += ce; }
         else { stats[0] = counters[1]; stats[1] = counters[2]; stats[2] = counters[3]; stats[3] = n_eval; *out_ce = ce; stats[6] = 0; stats[7] = 0; }
     }
+}
+
+// ---- device-resident Runge-Kutta loop: CUDA-graph WHILE node -------------------------------------------------------------
+// condition of the next iteration: chains still integrating and the iteration budget (n_seg * mxstep + 2, as the host loop)
+__global__ void ode_loop_cond_kernel(cudaGraphConditionalHandle handle, int* __restrict__ counters, long long max_iter) {
+    if (threadIdx.x == 0) {
+        const int it = ++counters[12];
+        cudaGraphSetConditional(handle, (counters[0] > 0 && it < max_iter) ? 1u : 0u);
+    }
+}
+// everything the captured iteration depends on: descriptors by value (beta zeroed: the field uses the untempered target),
+// the buffers (workspace identity) and the GEMM switches.  An instantiated graph is reused while the key is unchanged - a
+// HotLoop calls with the same workspace and parameter buffer every time.
+struct OdeGraphKey {
+    mfm_field_t F; mfm_target_t T; mfm_ode_opts_t O; int direction, n, flags; const void *z, *z_compact, *ws, *fb;
+};
+struct OdeGraphEntry { OdeGraphKey key; cudaGraph_t graph; cudaGraphExec_t exec; int dev; long long max_iter; unsigned long long stamp; bool used; };
+static thread_local OdeGraphEntry g_ode_graphs[8];
+static thread_local unsigned long long g_ode_graph_stamp = 0;
+static int g_ode_graph_mode = -1;        // -1 unread, 0 never, 1 always, 2 auto (small ensembles)
+static bool ode_use_graph(long long elements) {
+    if (g_ode_graph_mode < 0) {
+        const char* e = getenv("MFM_ODE_GRAPH");
+        g_ode_graph_mode = (e && e[0] == '0') ? 0 : ((e && e[0] == '1') ? 1 : 2);
+    }
+    // big ensembles keep the host-driven loop: their iterations take tens of milliseconds (one poll each is free) and the
+    // persistent GEMM's stream-K remainder rounds are not capturable (a replay would meet its own stale flags)
+    return g_ode_graph_mode == 1 || (g_ode_graph_mode == 2 && elements <= (4ll << 20));
+}
+static cudaStream_t ode_capture_stream(int dev) {
+    static thread_local cudaStream_t s[16] = {};
+    if (dev < 0 || dev >= 16) return nullptr;
+    if (!s[dev] && cudaStreamCreateWithFlags(&s[dev], cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); s[dev] = nullptr; }
+    return s[dev];
+}
+template <class Body>
+static int ode_graph_launch(const OdeGraphKey& key, cudaStream_t st, int* counters, long long max_iter, Body&& body) {
+    int dev = 0;
+    MFM_CUDA_CHECK(cudaGetDevice(&dev));
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) { cudaGetLastError(); return MFM_ERR_UNSUPPORTED; }   // the caller is capturing: plain loop
+    OdeGraphEntry* e = nullptr; OdeGraphEntry* victim = &g_ode_graphs[0];
+    for (auto& g : g_ode_graphs) {
+        if (g.used && g.dev == dev && g.max_iter == max_iter && memcmp(&g.key, &key, sizeof(key)) == 0) { e = &g; break; }
+        if (!g.used || (victim->used && g.stamp < victim->stamp)) victim = &g;
+    }
+    if (!e) {
+        cudaStream_t cap = ode_capture_stream(dev);
+        if (!cap || !tc2h::amax_scratch_for(cap)) return MFM_ERR_UNSUPPORTED;
+        if (victim->used) {                 // an evicted graph may still be running
+            MFM_CUDA_CHECK(cudaDeviceSynchronize());
+            cudaGraphExecDestroy(victim->exec); cudaGraphDestroy(victim->graph); victim->used = false;
+        }
+        cudaGraph_t graph;
+        MFM_CUDA_CHECK(cudaGraphCreate(&graph, 0));
+        cudaGraphConditionalHandle handle;
+        MFM_CUDA_CHECK(cudaGraphConditionalHandleCreate(&handle, graph, 1, cudaGraphCondAssignDefault));
+        cudaGraphNodeParams np = {};
+        np.type = cudaGraphNodeTypeConditional;
+        np.conditional.handle = handle; np.conditional.type = cudaGraphCondTypeWhile; np.conditional.size = 1;
+        cudaGraphNode_t node;
+        MFM_CUDA_CHECK(cudaGraphAddNode(&node, graph, nullptr, 0, &np));
+        cudaGraph_t loop_body = np.conditional.phGraph_out[0];
+        MFM_CUDA_CHECK(cudaStreamBeginCaptureToGraph(cap, loop_body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+        int rc = body(cap);
+        if (rc == MFM_OK) {
+            ode_loop_cond_kernel<<<1, 32, 0, cap>>>(handle, counters, max_iter);
+            if (cudaGetLastError() != cudaSuccess) rc = MFM_ERR_CUDA;
+            ++g_mfm_launches;
+        }
+        cudaGraph_t captured = nullptr;
+        const cudaError_t ce = cudaStreamEndCapture(cap, &captured);
+        if (rc != MFM_OK || ce != cudaSuccess) { cudaGetLastError(); cudaGraphDestroy(graph); if (rc == MFM_OK) mfm_set_last_error(ce, __FILE__, __LINE__); return rc != MFM_OK ? rc : MFM_ERR_CUDA; }
+        cudaGraphExec_t exec;
+        const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+        if (ie != cudaSuccess) { cudaGetLastError(); cudaGraphDestroy(graph); mfm_set_last_error(ie, __FILE__, __LINE__); return MFM_ERR_CUDA; }
+        victim->key = key; victim->graph = graph; victim->exec = exec; victim->dev = dev; victim->max_iter = max_iter; victim->used = true;
+        e = victim;
+    }
+    e->stamp = ++g_ode_graph_stamp;
+    MFM_CUDA_CHECK(cudaGraphLaunch(e->exec, st));
+    return MFM_OK;
 }
 
 static size_t ode_state_bytes(int n, int d, int H) {
@@ -691,9 +942,10 @@ static int* host_flag() {
 // Solve from y0 over [0,1]; direction +1: (v, -div); -1: (-v(x, 1-s), +div).
 // z: Hutchinson probes in chain order (null -> exact trace).  With probes, the chains still
 // integrating are compacted to the leading rows every iteration so finished chains cost nothing.
+// z_bound: host-known bound on |z| (NORMAL_BOUND for probes drawn by this library), 0 = unknown.
 static int ode_solve(const mfm_field_t& F, const mfm_target_t& T, const mfm_ode_opts_t& O, int direction, int n,
                      const float* z, const float* y0, float* y1, float* ldj, int* stats, int stats_accumulate,
-                     OdeState& S, FieldBufs& B, float* z_compact, cudaStream_t st) {
+                     OdeState& S, FieldBufs& B, float* z_compact, cudaStream_t st, float z_bound = NORMAL_BOUND) {
     const int d = F.dim, H = F.hidden;
     const float sgn = direction >= 0 ? 1.0f : -1.0f;
     if (O.n_times < 2 || O.n_times > 17) { mfm_set_last_error_msg("n_times must be in [2,17]"); return MFM_ERR_ARG; }
@@ -708,7 +960,7 @@ static int ode_solve(const mfm_field_t& F, const mfm_target_t& T, const mfm_ode_
     MFM_LAUNCH_CHECK();
     if (z) {
         // per-solve constants z W2 and z K^-1 in chain order (B.zw2 / B.zkinv hold them until the first gather)
-        if ((rc = field_prepare_probe(F, T, n, z, B, st))) return rc;
+        if ((rc = field_prepare_probe(F, T, n, z, B, st, z_bound))) return rc;
         if (compact) {
             MFM_CUDA_CHECK(cudaMemcpyAsync(S.zw2_full, B.zw2, (size_t)n * H * 4, cudaMemcpyDeviceToDevice, st));
             if (T.kind == MFM_TARGET_PINES)
@@ -729,27 +981,51 @@ static int ode_solve(const mfm_field_t& F, const mfm_target_t& T, const mfm_ode_
         idx = S.idx; nact = S.n_active; zc = z_compact;
     }
     const long long max_iter = (long long)TS.n_seg * (long long)O.mxstep + 2;
+    // (the two evaluations above reduced max |xi| into AM_X themselves; the stage kernels keep folding into it)
+    float* x_amax = (tc2h::gemm_h16() && B.amax && d % 16 == 0 && n >= 256) ? B.amax + AM_X : nullptr;
     bool stage_vec = d % 4 == 0 && ((reinterpret_cast<uintptr_t>(S.yx) | reinterpret_cast<uintptr_t>(S.xi)) & 15) == 0;
     for (int j = 0; j < 6; ++j) stage_vec = stage_vec && (reinterpret_cast<uintptr_t>(S.kx[j]) & 15) == 0;
-    for (long long it = 0; it < max_iter; ++it) {
+    // one iteration of the lock-step Runge-Kutta loop, enqueued on `s`: 6 x (stage input, field evaluation), then the step
+    // controller; counters[0] = chains still integrating afterwards
+    auto rk_iteration = [&](cudaStream_t s) -> int {
+        int rc2;
         if (compact) {
-            ode_gather_probe_kernel<<<n, 128, 0, st>>>(n, d, H, idx, nact, z, S.zw2_full,
-                                                       T.kind == MFM_TARGET_PINES ? S.zkinv_full : nullptr, z_compact, B.zw2, B.zkinv);
+            ode_gather_probe_kernel<<<n, 128, 0, s>>>(n, d, H, idx, nact, z, S.zw2_full,
+                                                      T.kind == MFM_TARGET_PINES ? S.zkinv_full : nullptr, z_compact, B.zw2, B.zkinv);
             MFM_LAUNCH_CHECK();
         }
-        for (int s = 1; s <= 6; ++s) {
-            if (stage_vec) ode_stage4_kernel<<<ceil_div((long long)n * (d / 4), 256), 256, 0, st>>>(n, d / 4, s, S, TS.n_seg, sgn, idx, nact);
-            else ode_stage_kernel<<<gE, 256, 0, st>>>(n, d, s, S, TS.n_seg, sgn, idx, nact);
+        for (int sg = 1; sg <= 6; ++sg) {
+            // the stage input's maximum accumulates over the solve (never reset: a stale, larger maximum is safe)
+            if (stage_vec) ode_stage4_kernel<<<ceil_div((long long)n * (d / 4), 256), 256, 0, s>>>(n, d / 4, sg, S, TS.n_seg, sgn, idx, nact, x_amax);
+            else ode_stage_kernel<<<gE, 256, 0, s>>>(n, d, sg, S, TS.n_seg, sgn, idx, nact, x_amax);
             MFM_LAUNCH_CHECK();
-            if ((rc = field_eval(F, T, n, S.xi, S.tf, zc, sgn, S.kx[s], S.kl[s], B, st, nact, idx))) return rc; ++n_eval;
+            if ((rc2 = field_eval(F, T, n, S.xi, S.tf, zc, sgn, S.kx[sg], S.kl[sg], B, s, nact, idx, x_amax))) return rc2;
         }
-        MFM_CUDA_CHECK(cudaMemsetAsync(S.counters, 0, sizeof(int), st));
-        ode_finish_kernel<<<gW, 256, 0, st>>>(n, d, S, TS, O.rtol, O.atol, O.mxstep);
+        MFM_CUDA_CHECK(cudaMemsetAsync(S.counters, 0, sizeof(int), s));
+        ode_finish_kernel<<<gW, 256, 0, s>>>(n, d, S, TS, O.rtol, O.atol, O.mxstep);
         MFM_LAUNCH_CHECK();
         if (compact) {
-            ode_compact_kernel<<<1, 1024, 0, st>>>(n, TS.n_seg, S.seg, S.idx, S.n_active, reinterpret_cast<long long*>(S.counters + 10));
+            ode_compact_kernel<<<1, 1024, 0, s>>>(n, TS.n_seg, S.seg, S.idx, S.n_active, reinterpret_cast<long long*>(S.counters + 10));
             MFM_LAUNCH_CHECK();
         }
+        return MFM_OK;
+    };
+    bool looped_on_device = false;
+    if (ode_use_graph((long long)n * d)) {
+        // device-resident loop: the iteration above is the body of a CUDA-graph WHILE node whose condition a one-thread kernel
+        // sets from counters[0] - no host round trip per iteration and graph-internal launch latency between the ~100 kernels
+        OdeGraphKey key;
+        memset(&key, 0, sizeof(key));
+        key.F = F; key.T = T; key.T.beta = 0.0f; key.O = O; key.direction = direction; key.n = n; key.z = z; key.z_compact = z_compact;
+        key.ws = S.z_full; key.fb = B.ff; key.flags = tc2h::gemm_h16() * 16 + tc2h::split_groups() + 64 * gemm_backend();
+        rc = ode_graph_launch(key, st, S.counters, max_iter, rk_iteration);
+        if (rc == MFM_OK) looped_on_device = true;
+        else if (rc != MFM_ERR_UNSUPPORTED) return rc;
+    }
+    if (!looped_on_device)
+    for (long long it = 0; it < max_iter; ++it) {
+        if ((rc = rk_iteration(st))) return rc;
+        n_eval += 6;
         MFM_CUDA_CHECK(cudaMemcpyAsync(hflag, S.counters, sizeof(int), cudaMemcpyDeviceToHost, st));
         MFM_CUDA_CHECK(cudaStreamSynchronize(st));
         if (*hflag == 0) break;
@@ -759,8 +1035,9 @@ static int ode_solve(const mfm_field_t& F, const mfm_target_t& T, const mfm_ode_
     if (stats) {
         // rows evaluated outside the device count: the two evaluations of initial_step_size on all n rows, and without
         // compaction (exact divergence) every evaluation runs on all n rows
-        const long long host_ce = compact ? 2ll * n : (long long)n * n_eval;
-        write_stats_kernel<<<1, 32, 0, st>>>(S.counters, n_eval, host_ce, stats, stats_accumulate); MFM_LAUNCH_CHECK();
+        // (device-resident loop: the number of iterations lives in counters[12]; the kernel derives both figures from it)
+        const long long host_ce = compact ? 2ll * n : (looped_on_device ? -(long long)n : (long long)n * n_eval);
+        write_stats_kernel<<<1, 32, 0, st>>>(S.counters, looped_on_device ? -n_eval : n_eval, host_ce, stats, stats_accumulate); MFM_LAUNCH_CHECK();
     }
     return MFM_OK;
 }
@@ -894,7 +1171,7 @@ int mfm_field_eval(const mfm_field_t* f, const mfm_target_t* t, const mfm_ode_op
     if (!w.ok) { mfm_set_last_error_msg("workspace too small (mfm_field_eval)"); return MFM_ERR_WORKSPACE; }
     if (hutch && !z) { mfm_set_last_error_msg("z required for hutch"); return MFM_ERR_ARG; }
     if ((rc = field_prepare_weights(*f, B, stream))) return rc;
-    if (hutch && (rc = field_prepare_probe(*f, *t, n, z, B, stream))) return rc;
+    if (hutch && (rc = field_prepare_probe(*f, *t, n, z, B, stream, 0.0f))) return rc;    // caller's probes: no known bound
     // field_eval writes -sgn*div; evaluate with sgn=-1 on a negated... simpler: sgn=+1 then negate
     if ((rc = field_eval(*f, *t, n, x, time, hutch ? z : nullptr, 1.0f, v, div ? negdiv : nullptr, B, stream))) return rc;
     if (div) { axpy_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(n, negdiv, -2.0f, negdiv, div); MFM_LAUNCH_CHECK(); }

@@ -17,10 +17,11 @@ namespace mfm {
 __global__ void __launch_bounds__(256)
 fm_batch_kernel(const uint32_t* __restrict__ rng_key, int n, int chain_offset, int n_total, int d, float sigma,
                 float ref_mean, float ref_std, const float* __restrict__ x, float* __restrict__ times, float* __restrict__ xt,
-                float* __restrict__ target) {
+                float* __restrict__ target, float* __restrict__ xt_amax) {
     const int lane = threadIdx.x & 31;
     const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (c >= n) return;
+    if (c >= n) return;                                                    // whole warps leave together
+    float vm = 0.0f;
     const uint32_t gc = (uint32_t)(chain_offset + c);
     // key_time, key_ref, key_gauss, key_ot = split(rng_key, 4)
     const u32x2 k_time = threefry_split_key(rng_key[0], rng_key[1], 0u, 4u);
@@ -45,11 +46,13 @@ fm_batch_kernel(const uint32_t* __restrict__ rng_key, int n, int chain_offset, i
             const long long idx = (long long)c * d + j;
             const float xv = x[idx];
             // sigma*eps + t*x + (1-t)*x0, left to right (:167)
-            xt[idx] = __fadd_rn(__fadd_rn(__fmul_rn(sigma, eps), __fmul_rn(t, xv)), __fmul_rn(omt, x0));
+            const float xtv = __fadd_rn(__fadd_rn(__fmul_rn(sigma, eps), __fmul_rn(t, xv)), __fmul_rn(omt, x0));
+            xt[idx] = xtv; vm = fmaxf(vm, fabsf(xtv));
             target[idx] = xv - x0;                                         // :168
         }
     }
     if (lane == 0) times[c] = t;
+    if (xt_amax) amax_publish_warp(xt_amax, vm);                           // x_t is the A operand of Dense_2 / the K^-1 GEMM
 }
 
 // Non-conditional variant, flow_fn (exe_flow_matching.py:139-147, --cond_flow off):
@@ -57,10 +60,12 @@ fm_batch_kernel(const uint32_t* __restrict__ rng_key, int n, int chain_offset, i
 //   x_t = t*x + (1 - (1-sigma) t) * ref ;  target = x - (1-sigma) * ref      (one warp per chain)
 __global__ void __launch_bounds__(256)
 fm_batch_uncond_kernel(const uint32_t* __restrict__ rng_key, int n, int chain_offset, int n_total, int d, float sigma,
-                       const float* __restrict__ x, float* __restrict__ times, float* __restrict__ xt, float* __restrict__ target) {
+                       const float* __restrict__ x, float* __restrict__ times, float* __restrict__ xt, float* __restrict__ target,
+                       float* __restrict__ xt_amax) {
     const int lane = threadIdx.x & 31;
     const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= n) return;
+    float vm = 0.0f;
     const uint32_t gc = (uint32_t)(chain_offset + c);
     const u32x2 k_time = threefry_split_key(rng_key[0], rng_key[1], 0u, 2u);
     const u32x2 k_ref = threefry_split_key(rng_key[0], rng_key[1], 1u, 2u);
@@ -72,26 +77,30 @@ fm_batch_uncond_kernel(const uint32_t* __restrict__ rng_key, int n, int chain_of
         const float ref = bits_to_normal(threefry_stream_word(k_ref.a, k_ref.b, gc * (uint32_t)d + (uint32_t)j, total));
         const long long idx = (long long)c * d + j;
         const float xv = x[idx];
-        xt[idx] = __fadd_rn(__fmul_rn(t, xv), __fmul_rn(sds, ref));      // :145
+        const float xtv = __fadd_rn(__fmul_rn(t, xv), __fmul_rn(sds, ref));      // :145
+        xt[idx] = xtv; vm = fmaxf(vm, fabsf(xtv));
         target[idx] = xv - __fmul_rn(oms, ref);                          // :146
     }
     if (lane == 0) times[c] = t;
+    if (xt_amax) amax_publish_warp(xt_amax, vm);
 }
 
 // diff = v - target; delta = 2*diff; dgt = delta*gc; per-block partial sums of diff^2
 __global__ void __launch_bounds__(256)
 fm_loss_delta_kernel(long long total, const float* __restrict__ v, const float* __restrict__ target,
                      const float* __restrict__ gc, float* __restrict__ delta, float* __restrict__ dgt,
-                     float* __restrict__ block_partial) {
+                     float* __restrict__ block_partial, float* __restrict__ delta_amax, float* __restrict__ dgt_amax) {
     __shared__ float red[32];
-    float s = 0.0f;
+    float s = 0.0f, m0 = 0.0f, m1 = 0.0f;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const float df = v[i] - target[i];
         s += df * df;
         const float dl = 2.0f * df;
-        delta[i] = dl;
-        dgt[i] = dl * gc[i];
+        const float dg = dl * gc[i];
+        delta[i] = dl; dgt[i] = dg;
+        m0 = fmaxf(m0, fabsf(dl)); m1 = fmaxf(m1, fabsf(dg));
     }
+    if (delta_amax) { amax_publish_warp(delta_amax, m0); amax_publish_warp(dgt_amax, m1); }   // both are GEMM operands of the backward pass
     s = block_sum(s, red);
     if (threadIdx.x == 0) block_partial[blockIdx.x] = s;
 }
@@ -182,9 +191,18 @@ static int wgrad(int n, int in, int out, const float* A, long long lda, const fl
 
 // dX[n,in] = (D[n,out] * W^T) gated by mask, optionally + add       (W stored [in,out])
 static int dgrad(int n, int in, int out, const float* D, long long ldd, const float* W, float* dX, long long ldx,
-                 const float* mask, long long ldm, const float* add, long long ldadd, cudaStream_t st) {
+                 const float* mask, long long ldm, const float* add, long long ldadd, cudaStream_t st, DenseAmax am = DenseAmax()) {
     GemmShape p{n, in, out, D, ldd, W, (long long)out, nullptr};
+    p.a_amax = am.a; p.a_split = am.a_split; p.a_scale_src = am.a_scale_src;
+    if (am.out_split && am.w_norm && am.a) {
+        // dX also leaves pre-split for the backward-data layer that consumes it (EpiStdS; the bound uses the kernel's ROW norm)
+        EpiStdS e{dX, ldx, nullptr, mask, ldm, add, ldadd, 0, 1, am.out_split, am.a, nullptr, 0.0f, am.w_norm, nullptr, am.add_bound, am.out_bound};
+        e.amax_out = am.out;
+        MFM_CUDA_CHECK((launch_gemm<true, false>(p, e, st)));
+        return MFM_OK;
+    }
     EpiStd e{dX, ldx, nullptr, mask, ldm, add, ldadd, 1.0f, 0};
+    e.amax_out = am.out;
     MFM_CUDA_CHECK((launch_gemm<true, false>(p, e, st)));
     return MFM_OK;
 }
@@ -192,6 +210,7 @@ static int dgrad(int n, int in, int out, const float* D, long long ldd, const fl
 struct FmBufs {
     FieldBufs B;
     float *times, *xt, *target, *v, *delta, *dgt, *d6, *d5, *dcat, *d2, *d0, *blockpart, *splitbuf, *colpart;
+    float *d6_s, *d5_s, *dcat_s;      // pre-split copies of the back-propagated signals (A operands of the next backward-data layer)
     size_t splitbuf_floats;
 };
 
@@ -209,7 +228,7 @@ static size_t fm_bytes(const mfm_field_t& F, const mfm_target_t& T, int n) {
     const size_t H = F.hidden, d = F.dim, N = n;
     return field_bufs_bytes(F, T, n, true) + ws_slice(N, 4) + ws_slice(N * d, 4) * 5 + ws_slice(N * H, 4) * 4 +
            ws_slice(N * 2 * H, 4) + ws_slice(FM_LOSS_BLOCKS, 4) + ws_slice(fm_splitbuf_floats(F), 4) +
-           ws_slice((size_t)COLSUM_SLABS * (H > d ? H : d), 4) + 1024;
+           ws_slice((size_t)COLSUM_SLABS * (H > d ? H : d), 4) + ws_slice(N * H, 4) * 2 + ws_slice(N * 2 * H, 4) + 1024;
 }
 
 static bool fm_take(FmBufs& M, Workspace& w, const mfm_field_t& F, int n) {
@@ -224,6 +243,7 @@ static bool fm_take(FmBufs& M, Workspace& w, const mfm_field_t& F, int n) {
     M.colpart = w.take<float>((size_t)COLSUM_SLABS * (H > d ? H : d));
     M.splitbuf_floats = fm_splitbuf_floats(F);
     M.splitbuf = w.take<float>(M.splitbuf_floats);
+    M.d6_s = w.take<float>(N * H); M.d5_s = w.take<float>(N * H); M.dcat_s = w.take<float>(N * 2 * H);
     return w.ok;
 }
 
@@ -234,19 +254,23 @@ static bool fm_take(FmBufs& M, Workspace& w, const mfm_field_t& F, int n) {
 // part 0: everything; part 1: forward, loss and the gradients of layers 7..4 (the tail [w_off[4], n_params) of
 // the flat buffer); part 2: the gradients of layers 3..0 (the head) from the activations part 1 left in
 // the workspace.  The split lets the host all-reduce the tail while part 2 runs.
+// xt_amax: slot holding max |x_t| when the batch kernel tracked it (null: field_eval reduces it).
 static int fm_forward_backward(const mfm_field_t& F, const mfm_target_t& T, int n, FmBufs& M, float* loss_out,
-                               float* grads, cudaStream_t st, int part) {
+                               float* grads, cudaStream_t st, int part, const float* xt_amax = nullptr) {
     const int d = F.dim, H = F.hidden, Fd = F.fourier_dim;
     FieldBufs& B = M.B;
     int rc;
     if (part == 2) field_register_mirrors(F, B);      // built by part 1 in this workspace
+    // tensor maxima of the backward pass (AmaxSlot; null when the scaled-fp16 GEMM is off)
+    float* am = tc2h::gemm_h16() ? B.amax : nullptr;
+    auto slot = [&](int i) -> float* { return am ? am + i : nullptr; };
     if (part != 2) {
         MFM_CUDA_CHECK(cudaMemsetAsync(grads, 0, (size_t)F.n_params * sizeof(float), st));
         if ((rc = field_prepare_weights(F, B, st))) return rc;
-        if ((rc = field_eval(F, T, n, M.xt, M.times, nullptr, 1.0f, M.v, nullptr, B, st))) return rc;
+        if ((rc = field_eval(F, T, n, M.xt, M.times, nullptr, 1.0f, M.v, nullptr, B, st, nullptr, nullptr, xt_amax))) return rc;
         const long long tot = (long long)n * d;
         const int lb = (int)((tot + 255) / 256 < FM_LOSS_BLOCKS ? (tot + 255) / 256 : FM_LOSS_BLOCKS);
-        fm_loss_delta_kernel<<<lb, 256, 0, st>>>(tot, M.v, M.target, B.gc, M.delta, M.dgt, M.blockpart);
+        fm_loss_delta_kernel<<<lb, 256, 0, st>>>(tot, M.v, M.target, B.gc, M.delta, M.dgt, M.blockpart, slot(AM_DELTA), slot(AM_DGT));
         MFM_LAUNCH_CHECK();
         final_sum_kernel<<<1, 256, 0, st>>>(lb, M.blockpart, loss_out);
         MFM_LAUNCH_CHECK();
@@ -260,40 +284,53 @@ static int fm_forward_backward(const mfm_field_t& F, const mfm_target_t& T, int 
         return MFM_OK;
     };
     float* sb = M.splitbuf; const size_t sbf = M.splitbuf_floats;
+    // pre-split copies along the backward-data chain (as in field_eval): slot ids of the exact maxima / bounds, ROW norms of the kernels
+    const bool sp = am != nullptr && M.d6_s != nullptr && H % 16 == 0 && n >= 256;
+    auto BD = [&](int i) -> float* { return am + AM_BOUND + i; };
+    auto WR = [&](int l) -> const float* { return am + AM_WNORM_ROW + l; };
+    // (exact max of D, [D pre-split, slot of its scale]) -> exact max of dX [, dX pre-split, slot of its bound, layer, bound of `add`]
+    auto G_ = [&](const float* a, const float* a_split, const float* src, float* out, float* c_split, int slot_id, int layer, const float* add_bound) {
+        DenseAmax m; m.a = a; m.out = out;
+        if (sp && a_split) { m.a_split = a_split; m.a_scale_src = src; }
+        if (sp && c_split) { m.out_split = c_split; m.out_bound = BD(slot_id); m.w_norm = WR(layer); m.add_bound = add_bound; }
+        return m;
+    };
     if (part != 2) {
     // layer 7 (nn_xt head): y = h6 W7 + b7
     if ((rc = wgrad(n, H, d, B.h6, H, M.delta, d, GW_(7), sb, sbf, st))) return rc;
     if ((rc = bias_grad(M.delta, d, d, GB_(7)))) return rc;
-    if ((rc = dgrad(n, H, d, M.delta, d, W_(7), M.d6, H, B.h6, H, nullptr, 0, st))) return rc;
+    if ((rc = dgrad(n, H, d, M.delta, d, W_(7), M.d6, H, B.h6, H, nullptr, 0, st, G_(slot(AM_DELTA), nullptr, nullptr, slot(AM_D6), M.d6_s, AM_D6, 7, nullptr)))) return rc;
     // layer 6
     if ((rc = wgrad(n, H, H, B.h5, H, M.d6, H, GW_(6), sb, sbf, st))) return rc;
     if ((rc = bias_grad(M.d6, H, H, GB_(6)))) return rc;
-    if ((rc = dgrad(n, H, H, M.d6, H, W_(6), M.d5, H, B.h5, H, nullptr, 0, st))) return rc;
+    if ((rc = dgrad(n, H, H, M.d6, H, W_(6), M.d5, H, B.h5, H, nullptr, 0, st, G_(slot(AM_D6), M.d6_s, BD(AM_D6), slot(AM_D5), M.d5_s, AM_D5, 6, nullptr)))) return rc;
     // layer 5 (joint, input cat = [s_x | s_t])
     if ((rc = wgrad(n, 2 * H, H, B.cat, 2 * H, M.d5, H, GW_(5), sb, sbf, st))) return rc;
     if ((rc = bias_grad(M.d5, H, H, GB_(5)))) return rc;
     // d s_x = (d5 W5[:H]^T) * relu'(s_x)
-    if ((rc = dgrad(n, H, H, M.d5, H, W_(5), M.dcat, 2 * H, B.cat, 2 * H, nullptr, 0, st))) return rc;
-    // d s_t (joint part) = d5 W5[H:]^T   (no gate yet)
-    if ((rc = dgrad(n, H, H, M.d5, H, W_(5) + (long long)H * H, M.dcat + H, 2 * H, nullptr, 0, nullptr, 0, st))) return rc;
+    if ((rc = dgrad(n, H, H, M.d5, H, W_(5), M.dcat, 2 * H, B.cat, 2 * H, nullptr, 0, st, G_(slot(AM_D5), M.d5_s, BD(AM_D5), slot(AM_DCX), M.dcat_s, AM_DCX, 5, nullptr)))) return rc;
+    // d s_t (joint part) = d5 W5[H:]^T   (no gate yet; its bound enters the next layer's through `add`)
+    if ((rc = dgrad(n, H, H, M.d5, H, W_(5) + (long long)H * H, M.dcat + H, 2 * H, nullptr, 0, nullptr, 0, st,
+                    G_(slot(AM_D5), M.d5_s, BD(AM_D5), nullptr, M.dcat_s + H, AM_DCT0, 5, nullptr)))) return rc;
     // layer 4 (nn_t head): g_t = s_t W4 + b4, dL/dg_t = delta * clip(grad logprob)
     if ((rc = wgrad(n, H, d, B.cat + H, 2 * H, M.dgt, d, GW_(4), sb, sbf, st))) return rc;
     if ((rc = bias_grad(M.dgt, d, d, GB_(4)))) return rc;
     // d s_t = (dgt W4^T + joint part) * relu'(s_t)   (in place)
-    if ((rc = dgrad(n, H, d, M.dgt, d, W_(4), M.dcat + H, 2 * H, B.cat + H, 2 * H, M.dcat + H, 2 * H, st))) return rc;
+    if ((rc = dgrad(n, H, d, M.dgt, d, W_(4), M.dcat + H, 2 * H, B.cat + H, 2 * H, M.dcat + H, 2 * H, st,
+                    G_(slot(AM_DGT), nullptr, nullptr, slot(AM_DCT), M.dcat_s + H, AM_DCT, 4, sp ? BD(AM_DCT0) : nullptr)))) return rc;
     }
     if (part == 1) return MFM_OK;
     // layer 3 (x branch)
     if ((rc = wgrad(n, H, H, B.h2, H, M.dcat, 2 * H, GW_(3), sb, sbf, st))) return rc;
     if ((rc = bias_grad(M.dcat, 2 * H, H, GB_(3)))) return rc;
-    if ((rc = dgrad(n, H, H, M.dcat, 2 * H, W_(3), M.d2, H, B.h2, H, nullptr, 0, st))) return rc;
+    if ((rc = dgrad(n, H, H, M.dcat, 2 * H, W_(3), M.d2, H, B.h2, H, nullptr, 0, st, G_(slot(AM_DCX), M.dcat_s, BD(AM_DCX), slot(AM_D2), nullptr, 0, 0, nullptr)))) return rc;
     // layer 2
     if ((rc = wgrad(n, d, H, M.xt, d, M.d2, H, GW_(2), sb, sbf, st))) return rc;
     if ((rc = bias_grad(M.d2, H, H, GB_(2)))) return rc;
     // layer 1 (time branch)
     if ((rc = wgrad(n, H, H, B.h0, H, M.dcat + H, 2 * H, GW_(1), sb, sbf, st))) return rc;
     if ((rc = bias_grad(M.dcat + H, 2 * H, H, GB_(1)))) return rc;
-    if ((rc = dgrad(n, H, H, M.dcat + H, 2 * H, W_(1), M.d0, H, B.h0, H, nullptr, 0, st))) return rc;
+    if ((rc = dgrad(n, H, H, M.dcat + H, 2 * H, W_(1), M.d0, H, B.h0, H, nullptr, 0, st, G_(slot(AM_DCT), M.dcat_s + H, BD(AM_DCT), slot(AM_D0), nullptr, 0, 0, nullptr)))) return rc;
     // layer 0
     if ((rc = wgrad(n, 2 * Fd, H, B.ff, 2 * Fd, M.d0, H, GW_(0), sb, sbf, st))) return rc;
     if ((rc = bias_grad(M.d0, H, H, GB_(0)))) return rc;
@@ -387,12 +424,14 @@ int mfm_fm_loss_grad_part(const mfm_field_t* f, const mfm_target_t* t, const uin
     Workspace w(ws, ws_bytes);
     FmBufs M;
     if (!fm_take(M, w, *f, n)) { mfm_set_last_error_msg("workspace too small (mfm_fm_loss_grad)"); return MFM_ERR_WORKSPACE; }
+    float* xt_amax = mfm::tc2h::gemm_h16() ? M.B.amax + AM_X : nullptr;
     if (part != 2) {
+        MFM_CUDA_CHECK(cudaMemsetAsync(M.B.amax + AM_EVAL_END, 0, (AM_POOL - AM_EVAL_END) * sizeof(float), stream));   // this pass's maxima
         fm_batch_kernel<<<ceil_div(n, 8), 256, 0, stream>>>(rng_key, n, chain_offset, n_total, f->dim, sigma, f->ref_mean, f->ref_std,
-                                                             positions, M.times, M.xt, M.target);
+                                                             positions, M.times, M.xt, M.target, xt_amax);
         MFM_LAUNCH_CHECK();
     }
-    return fm_forward_backward(*f, *t, n, M, loss_out, grads, stream, part);
+    return fm_forward_backward(*f, *t, n, M, loss_out, grads, stream, part, xt_amax);
 }
 
 int mfm_fm_loss_grad_uncond(const mfm_field_t* f, const mfm_target_t* t, const uint32_t* rng_key, int n, int chain_offset,
@@ -408,10 +447,12 @@ int mfm_fm_loss_grad_uncond(const mfm_field_t* f, const mfm_target_t* t, const u
     Workspace w(ws, ws_bytes);
     FmBufs M;
     if (!fm_take(M, w, *f, n)) { mfm_set_last_error_msg("workspace too small (mfm_fm_loss_grad_uncond)"); return MFM_ERR_WORKSPACE; }
+    float* xt_amax = mfm::tc2h::gemm_h16() ? M.B.amax + AM_X : nullptr;
+    MFM_CUDA_CHECK(cudaMemsetAsync(M.B.amax + AM_EVAL_END, 0, (AM_POOL - AM_EVAL_END) * sizeof(float), stream));
     fm_batch_uncond_kernel<<<ceil_div(n, 8), 256, 0, stream>>>(rng_key, n, chain_offset, n_total, f->dim, sigma, positions,
-                                                                M.times, M.xt, M.target);
+                                                                M.times, M.xt, M.target, xt_amax);
     MFM_LAUNCH_CHECK();
-    return fm_forward_backward(*f, *t, n, M, loss_out, grads, stream, 0);
+    return fm_forward_backward(*f, *t, n, M, loss_out, grads, stream, 0, xt_amax);
 }
 
 int mfm_fm_loss_grad_from_batch(const mfm_field_t* f, const mfm_target_t* t, int n, const float* xt, const float* times,
@@ -429,7 +470,8 @@ int mfm_fm_loss_grad_from_batch(const mfm_field_t* f, const mfm_target_t* t, int
     MFM_CUDA_CHECK(cudaMemcpyAsync(M.xt, xt, nd, cudaMemcpyDeviceToDevice, stream));
     MFM_CUDA_CHECK(cudaMemcpyAsync(M.target, target_v, nd, cudaMemcpyDeviceToDevice, stream));
     MFM_CUDA_CHECK(cudaMemcpyAsync(M.times, times, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, stream));
-    return fm_forward_backward(*f, *t, n, M, loss_out, grads, stream, 0);
+    MFM_CUDA_CHECK(cudaMemsetAsync(M.B.amax + AM_EVAL_END, 0, (AM_POOL - AM_EVAL_END) * sizeof(float), stream));
+    return fm_forward_backward(*f, *t, n, M, loss_out, grads, stream, 0);     // the caller's x_t: field_eval reduces its maximum
 }
 
 int mfm_adamw_step(float* params, const float* grads, float* mu, float* nu, const uint8_t* decay_mask, long long n_params,

@@ -260,6 +260,7 @@ gemm_tc_kernel(const __grid_constant__ Maps maps, GemmShape p, Epi epi) {
                 }
             }
         }
+        epi_publish_amax(epi, epi_stored_max(epi, 0));
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();

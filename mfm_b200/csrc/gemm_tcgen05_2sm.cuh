@@ -333,6 +333,7 @@ gemm_tc2_kernel(const __grid_constant__ Maps maps, GemmShape p, Epi epi, int raw
                 }
             }
         }
+        epi_publish_amax(epi, epi_stored_max(epi, 0));
     }
     if (warp == SPLIT_WARP0) TC2_MARK(7);
     __syncwarp();

@@ -1,29 +1,41 @@
-// EXPERIMENTAL (opt-in, MFM_GEMM_SPLIT=bf16x3 / mfm_set_gemm_split16; never the default): "split16" variant of the
-// persistent CTA-pair dense-layer kernel, written at the very end of round 1.  Measured with the round's last GPU seconds:
-// tests/test_gpu_gemm.py::test_gemm_split16 (skipped unless MFM_TEST_SPLIT16=1) passes, scripts/split16_bench.py shows
-// 1.21-1.31x over the default kernel (419 TFLOP/s at 65536x1024x1024), but bf16 parts fail phi-four's per-layer FM gradient
-// bar (3e-3 vs 5e-4) - fp16 parts with a per-tensor scale are the version to ship.  See DESIGN.md section 9, item 1.
+// "h16" dense-layer kernel: fp32-accurate products from THREE fp16 tensor-core passes per 16 k-values.
 //
-// Arithmetic: both operands as two 2-byte parts, a = hi + lo with hi = rn(a), lo = rn(a - hi) (bf16; fp16 needs a
-// per-tensor scale and is only a template parameter so far), product = hi.hi' + hi.lo' + lo.hi' : THREE kind::f16 K = 16
-// MMAs per 16 k-values instead of today's two tf32 + two bf16 (4 slots) - 25 % fewer tensor-core slots, operand rounding
-// error 5e-6 of max |C| on the pines layers (today 1.3e-6): inside the 1e-4 parity bar, meant for the FM update.
+// Arithmetic.  Both operands are scaled by a per-tensor power of two and split into two fp16 parts,
+//     a * s_a = hi + lo,   hi = rn_fp16(a * s_a),   lo = rn_fp16(a * s_a - hi)        (22 significant bits)
+// and  a.b  ~  (hi.hi' + hi.lo' + lo.hi') / (s_a s_b):  three kind::f16 K = 16 MMAs per 16 k-values (the dropped lo.lo'
+// term is <= 2^-22 relative).  Against the tf32 + bf16-cross scheme of gemm_tcgen05_persist.cuh (one tf32 K = 8 MMA and one
+// bf16 K = 16 MMA per 8 k-values = 4 bf16-rate slots per 16 k) this needs 3 slots, i.e. the ceiling of the arithmetic moves
+// from 1/4 to 1/3 of the bf16 peak, and it is MORE accurate (operand rounding 2^-22 instead of bf16's 2^-8 on the cross
+// terms: measured max error / max |C| 8e-8 against 1.3e-6, profiles/r01_emulation_error_study.txt).
+//
+// Why the scale.  fp16 has 5 exponent bits: unscaled, hi is sub-normal below 6e-5 and lo below 0.1, which ruined
+// back-propagated signals of size 1e-6 (2e-2 relative error in the study).  With s chosen so that max |a| s lies in
+// [2^14, 2^15) every element down to 2^-18 of the tensor's maximum keeps all 22 bits and smaller ones an ABSOLUTE error of
+// 2^-25 / s (2^-40 of the maximum) - the normwise accuracy of fp32 for the whole tensor.  Powers of two make the scaling and
+// the un-scaling of the accumulator exact.  The maximum is exact, not estimated: every producer of a GEMM operand
+// (EpiStd epilogues, the element-wise kernels) folds max |value| into a device slot with one atomicMax per warp, the
+// consumer reads the slot (GemmShape::a_amax); tensors without a slot get one reduction pass (absmax_kernel).
 //
 // Layout ("split16"): every 16 consecutive fp32 of a K-major row are replaced, in the same 64 bytes, by 16 hi parts followed
 // by 16 lo parts.  A 32-wide k-block is still a 128-byte SWIZZLE_128B row [hi 0..15 | lo 0..15 | hi 16..31 | lo 16..31], so
-// TMA maps, row pitch and the +32-byte descriptor stepping of gemm_tcgen05_persist.cuh apply unchanged.  B (weights) arrives
-// pre-split from global memory (presplit16_kernel, once per parameter update); A is loaded raw and split IN PLACE by the
-// splitter warps (one 64-byte group per thread per k-block: half of today's shared-memory traffic, no cross region).
-// A stage is therefore 32 KB (A 16 KB + half of B 16 KB) and the ring has 6 stages in the same 192 KB.
+// TMA maps, row pitch and the +32-byte descriptor stepping of the persistent kernel apply unchanged.  The weight operand B
+// arrives pre-split from global memory when the caller registered a mirror (presplit_h16_kernel, once per parameter
+// update; BPRE) and is split in shared memory otherwise; A is loaded raw and split IN PLACE by the splitter warps (one
+// 64-byte group per thread per k-block, no cross region).  A stage is therefore 32 KB (A 16 KB + half of B 16 KB) and the
+// ring has 6 stages in the same 192 KB.  Shared-memory pipe per k-block and CTA: TMA 32 KB in, splitters 16 KB out + 16 KB in
+// (32 + 32 without a mirror), six MMAs x (4 KB of A + 4 KB of B, the pair's other half arrives by the cta_group::2
+// broadcast) = 112 KB against 768 clk x 128 B = 96 KB at the full tensor rate: the kernel is co-limited by the
+// shared-memory pipe at ~88 % of the 3-slot ceiling, which is what it measures.
 // Everything else - work list incl. stream-K, TMEM double buffering, 8 + 8 epilogue warps - is the persistent kernel's.
 #pragma once
 #include <cuda_fp16.h>
 #include "gemm_tcgen05_persist.cuh"
 
 namespace mfm {
-namespace tc2s {
+namespace tc2h {
 
 using namespace tc2p;       // tile constants, Sched / PairWork, Maps3, barrier + MMA helpers
+__device__ __forceinline__ void mma_f16_ss_2sm(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) { mma_bf16_ss_2sm(d, a, b, idesc, acc); }   // kind::f16: the descriptor says fp16
 
 constexpr int S_STAGES = 6, S_STAGE_BYTES = HI_BYTES;          // 6 x 32 KB
 constexpr int S_NBARS = 3 * S_STAGES + 4;
@@ -31,24 +43,80 @@ constexpr int S_SMEM_BYTES = S_STAGES * S_STAGE_BYTES + EPI_STG_BYTES + 1024 /*a
 static_assert(S_NBARS * 8 + 8 + 64 <= 256, "barrier area: barriers, TMEM slot, PairWork");
 static_assert(S_STAGE_BYTES == EPI_WARPS * 4096, "the helpers' staging is exactly ring stage 0");
 
-template <bool FP16> __device__ __forceinline__ uint32_t pack2(float first, float second) {   // `first` lands first in memory
-    uint32_t r;
-    if (FP16) asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(second), "f"(first));
-    else      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(second), "f"(first));
-    return r;
+// power of two s with amax * s in [2^14, 2^15) (fp16 max is 65504); 1 for a zero or non-finite maximum
+__host__ __device__ __forceinline__ uint32_t h16_scale_exp(float amax) {
+#ifdef __CUDA_ARCH__
+    const uint32_t b = __float_as_uint(amax) & 0x7FFFFFFFu;
+#else
+    union { float f; uint32_t u; } c; c.f = amax; const uint32_t b = c.u & 0x7FFFFFFFu;
+#endif
+    int e = (int)(b >> 23);
+    if (b == 0u || e == 255) return 127u;
+    if (e == 0) e = 1;
+    int se = 127 + 14 - (e - 127);
+    se = se < 2 ? 2 : (se > 252 ? 252 : se);
+    return (uint32_t)se;
 }
-template <bool FP16> __device__ __forceinline__ float unpack_lo(uint32_t p) {
-    if (FP16) return __half2float(__ushort_as_half((unsigned short)(p & 0xFFFFu)));
-    return __uint_as_float(p << 16);
-}
-template <bool FP16> __device__ __forceinline__ float unpack_hi(uint32_t p) {
-    if (FP16) return __half2float(__ushort_as_half((unsigned short)(p >> 16)));
-    return __uint_as_float(p & 0xFFFF0000u);
+__device__ __forceinline__ float h16_scale(float amax) { return __uint_as_float(h16_scale_exp(amax) << 23); }
+__device__ __forceinline__ float h16_inv_scale(float amax) { return __uint_as_float((254u - h16_scale_exp(amax)) << 23); }
+
+// what the kernel needs to know about the operands' magnitudes
+struct H16Scales {
+    const float* a_amax; const float* a_amax2;   // device: max |A| (the larger of the two when A spans two producers' outputs)
+    float a_bound;                               // > 0: a bound known on the host (Fourier features <= 1, normal draws <= 8)
+    const float* b_amax;                         // device: max |B| (the mirror was split with h16_scale of this value)
+    const float* a_scale_src;                    // APRE: device float the producer of the pre-split A derived its scale from
+    int cvt_unpack;                              // A/B switch of the splitter arithmetic (see split16)
+    int split_groups;                            // 1, 2 or 4: groups of splitter warps that take the stages in turn
+};
+__device__ __forceinline__ float h16_a_amax(const H16Scales& s) {
+    if (s.a_bound > 0.0f) return s.a_bound;
+    float m = *s.a_amax;
+    if (s.a_amax2) m = fmaxf(m, *s.a_amax2);
+    return m;
 }
 
-template <bool FP16, class Epi>
+__device__ __forceinline__ uint32_t pack_h2(float first, float second) {   // `first` lands first in memory
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(second), "f"(first));
+    return r;
+}
+__device__ __forceinline__ float h2_lo(uint32_t p) { return __half2float(__ushort_as_half((unsigned short)(p & 0xFFFFu))); }
+__device__ __forceinline__ float h2_hi(uint32_t p) { return __half2float(__ushort_as_half((unsigned short)(p >> 16))); }
+// x - h for the two fp16 halves h of `hp`, in ONE instruction each: sm_100's mixed-precision FMA (fma.rn.f32.f16 -> FHFMA)
+// multiplies the fp16 half by -1 and adds the fp32 value, so the hi parts never go back through the conversion unit.
+// The difference is exact (|x - h| is at most half an fp16 ulp of x and both share x's exponent range).
+__device__ __forceinline__ void sub_h2(uint32_t hp, float x0, float x1, float& d0, float& d1) {
+    unsigned short h0, h1;
+    asm("mov.b32 {%0, %1}, %2;" : "=h"(h0), "=h"(h1) : "r"(hp));
+    const unsigned short m1 = 0xBC00;       // -1.0
+    asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(d0) : "h"(h0), "h"(m1), "f"(x0));
+    asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(d1) : "h"(h1), "h"(m1), "f"(x1));
+}
+// 16 floats (4 float4, scaled by s) -> 8 words of hi parts, 8 words of lo parts: hi = rn_fp16(x s), lo = rn_fp16(x s - hi).
+// Per pair of values: 2 FMUL, 1 F2FP (pack hi), 2 FHFMA, 1 F2FP (pack lo).  Measured against two alternatives at
+// 65536 x 1024 x 1024 (scripts/h16_bench.py, sustained): converting hi back with cvt.f32.f16 (CVT_UNPACK, 2 more conversions and
+// 2 FADD per pair) 0.377 ms; rounding to 11 bits on the integer pipe instead (4 more integer ops per value) 0.396 ms - the
+// splitter warps are bound by issue slots, not by the conversion unit.
+template <bool CVT_UNPACK = false>
+__device__ __forceinline__ void split16(const float4 (&v)[4], float s, uint32_t (&hp)[8], uint32_t (&lp)[8]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float x = v[j].x * s, y = v[j].y * s, z = v[j].z * s, w = v[j].w * s;
+        hp[2 * j] = pack_h2(x, y); hp[2 * j + 1] = pack_h2(z, w);
+        float dx, dy, dz, dw;
+        if (CVT_UNPACK) {      // A/B variant (MFM_GEMM_H16=2)
+            dx = x - h2_lo(hp[2 * j]); dy = y - h2_hi(hp[2 * j]); dz = z - h2_lo(hp[2 * j + 1]); dw = w - h2_hi(hp[2 * j + 1]);
+        } else {
+            sub_h2(hp[2 * j], x, y, dx, dy); sub_h2(hp[2 * j + 1], z, w, dz, dw);
+        }
+        lp[2 * j] = pack_h2(dx, dy); lp[2 * j + 1] = pack_h2(dz, dw);
+    }
+}
+
+template <bool APRE, bool BPRE, class Epi>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
-gemm_tc2s_kernel(const __grid_constant__ Maps3 maps, GemmShape p, Epi epi, long long* tl, float* sk_ws, unsigned* sk_flags, unsigned sk_epoch) {
+gemm_tc2h_kernel(const __grid_constant__ Maps3 maps, GemmShape p, Epi epi, H16Scales sc, long long* tl, float* sk_ws, unsigned* sk_flags, unsigned sk_epoch) {
 #ifdef MFM_TC2_TIMELINE
     // tuning aid: SM clock at 4 events of the first 16 tiles of pair 0's leader (MMA start / accumulator
     // committed / epilogue start / epilogue end)
@@ -86,7 +154,10 @@ gemm_tc2s_kernel(const __grid_constant__ Maps3 maps, GemmShape p, Epi epi, long 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.b) : "memory");
-        for (int s = 0; s < S_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&split[s], 2 * SPLIT_WARPS); mbar_init(&empty[s], 1); }
+        // split[s]: the stage's operands are in tensor-core format in BOTH CTAs.  With everything pre-split (APRE and BPRE) one warp
+        // per CTA just forwards its own `full` to the leader; otherwise the splitter warps of the stage's group arrive
+        const uint32_t split_count = (APRE && BPRE) ? 2u : (uint32_t)(2 * SPLIT_WARPS / sc.split_groups);
+        for (int s = 0; s < S_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&split[s], split_count); mbar_init(&empty[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 2 * EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -146,8 +217,8 @@ gemm_tc2s_kernel(const __grid_constant__ Maps3 maps, GemmShape p, Epi epi, long 
                     uint8_t* st = smem + s * S_STAGE_BYTES;
                     mbar_expect_tx(&full[s], HI_BYTES);
                     const int k0 = kz0 + kt * BK;
-                    tma_load_2d(st, &maps.a, &full[s], k0, m0);                    // raw fp32 rows of A (split in place below)
-                    tma_load_2d(st + A_BYTES, &maps.b, &full[s], k0, nb0);         // B half-tile, pre-split [16 hi | 16 lo] per 16 k
+                    tma_load_2d(st, &maps.a, &full[s], k0, m0);                    // rows of A: raw fp32 (split in place below) or pre-split (APRE)
+                    tma_load_2d(st + A_BYTES, &maps.b, &full[s], k0, nb0);         // B half-tile: pre-split [16 hi | 16 lo] per 16 k (BPRE) or raw
                 }
             }
         }
@@ -161,8 +232,8 @@ gemm_tc2s_kernel(const __grid_constant__ Maps3 maps, GemmShape p, Epi epi, long 
                 tile_origin(tile, m0p, n0, kz0, KT, neff, z);
                 if (p.k_split > 0) { kt0 = 0; kt1 = KT; }
                 const uint32_t b = i & 1, u = i >> 1;
-                // kind::f16: D = f32, A = B = bf16 (or fp16), both K-major, M = 256 per pair, N = neff
-                const uint32_t idesc16 = (1u << 4) | ((FP16 ? 0u : 1u) << 7) | ((FP16 ? 0u : 1u) << 10) | ((uint32_t)(neff >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+                // kind::f16: D = f32 (bit 4), A = B = fp16 (format 0 in bits 7-9 / 10-12), both K-major, M = 256 per pair, N = neff
+                const uint32_t idesc16 = (1u << 4) | ((uint32_t)(neff >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
                 const uint32_t acc = tmem_base + b * BN;
                 mbar_wait(&acc_empty[b], (u & 1) ^ 1);          // both CTAs have drained this buffer (tile i-2)
                                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -178,9 +249,9 @@ gemm_tc2s_kernel(const __grid_constant__ Maps3 maps, GemmShape p, Epi epi, long 
                     for (int gq = 0; gq < 2; ++gq) {
                         const uint64_t dah = make_desc(a_t + gq * 64, 16, 1024, 2), dal = make_desc(a_t + gq * 64 + 32, 16, 1024, 2);
                         const uint64_t dbh = make_desc(b_t + gq * 64, 16, 1024, 2), dbl = make_desc(b_t + gq * 64 + 32, 16, 1024, 2);
-                        mma_bf16_ss_2sm(acc, dah, dbh, idesc16, ((kt - kt0) | gq) != 0);
-                        mma_bf16_ss_2sm(acc, dah, dbl, idesc16, 1);
-                        mma_bf16_ss_2sm(acc, dal, dbh, idesc16, 1);
+                        mma_f16_ss_2sm(acc, dah, dbh, idesc16, ((kt - kt0) | gq) != 0);
+                        mma_f16_ss_2sm(acc, dah, dbl, idesc16, 1);
+                        mma_f16_ss_2sm(acc, dal, dbh, idesc16, 1);
                     }
                     mma_commit_2sm(&empty[s]);
                 }
@@ -190,7 +261,15 @@ gemm_tc2s_kernel(const __grid_constant__ Maps3 maps, GemmShape p, Epi epi, long 
         }
     } else if (warp >= SPLIT_WARP0 && warp < EPI_WARP0) {
         // ---------------- splitters (both CTAs) ----------------
+        // The 8 warps work as `split_groups` groups that take the stages in turn (group = stage number mod groups): a group's
+        // threads each convert `split_groups` 64-byte units of the tile.  One stage costs a fixed latency (barrier wake-up,
+        // shared-memory round trip, fence.proxy.async, the remote arrive) plus the conversion work; two groups keep two stages in
+        // flight, so the fixed part overlaps and the splitters keep up with the 768-clock MMA time of a k-block.
+        const int G = (APRE && BPRE) ? 1 : sc.split_groups, per_group = SPLIT_WARPS * 32 / G;
         const int tix = threadIdx.x - SPLIT_WARP0 * 32;
+        const int grp = tix / per_group, tg = tix - grp * per_group;
+        // raw operands are scaled while they are split: A by the power of two of its maximum, B (no mirror) likewise
+        const float s_a = APRE ? 1.0f : h16_scale(h16_a_amax(sc)), s_b = BPRE ? 1.0f : h16_scale(*sc.b_amax);
         uint32_t g = 0;
         for (int idx = 0; idx < work->n_items; ++idx) {
             int tile, kb0, kb1;
@@ -198,26 +277,32 @@ gemm_tc2s_kernel(const __grid_constant__ Maps3 maps, GemmShape p, Epi epi, long 
             int n_kb = kb1 - kb0;
             if (p.k_split > 0) { int m0p, n0, kz0, KT, neff, z; tile_origin(tile, m0p, n0, kz0, KT, neff, z); n_kb = KT; }
             for (int kt = 0; kt < n_kb; ++kt, ++g) {
+                if ((int)(g % (uint32_t)G) != grp) continue;
                 const uint32_t s = g % S_STAGES, ph = (g / S_STAGES) & 1;
                 mbar_wait(&full[s], ph);
-                // in-place split of the A tile: thread (row r, half hq) owns the 16 floats k = 16 hq .. 16 hq + 15 of row r,
-                // i.e. logical 16-byte chunks 4 hq .. 4 hq + 3 (physical chunk = logical ^ (r & 7), SWIZZLE_128B), and replaces
-                // them by 16 hi | 16 lo two-byte parts (hi = rn(a), lo = rn(a - hi)).  256 threads x 64 bytes = the 16 KB tile.
-                {
-                    const uint32_t r = (uint32_t)tix >> 1, hq = (uint32_t)tix & 1u;
-                    const uint32_t rowa = smem_u32(smem + s * S_STAGE_BYTES) + r * 128u;
+                if (APRE && BPRE) {
+                    // nothing to convert: TMA delivered tensor-core format; one warp tells the leader that this CTA's half is in.
+                    // The other warps still WALK the stages: they become epilogue helpers of the pair's last tile afterwards, and
+                    // their parity wait on that tile's accumulator barrier is only unambiguous once the tile's own stages have
+                    // landed (the buffer's previous use is then complete) - starting early would read the wrong phase.
+                    if (warp == SPLIT_WARP0 && lane == 0) mbar_arrive_remote(&split[s], 0);
+                    continue;
+                }
+                // in-place split of the raw tile(s): unit (row r, half hq) = the 16 floats k = 16 hq .. 16 hq + 15 of row r, i.e.
+                // logical 16-byte chunks 4 hq .. 4 hq + 3 (physical chunk = logical ^ (r & 7), SWIZZLE_128B), replaced by
+                // 16 hi | 16 lo fp16 parts of the SCALED values.  Units 0..255: the A tile, 256..511: the B half-tile.
+#pragma unroll 1
+                for (int un = (APRE ? 256 : 0) + tg; un < (BPRE ? 256 : 512) && !(APRE && BPRE); un += per_group) {
+                    const int op = un >> 8;
+                    const uint32_t r = ((uint32_t)un & 255u) >> 1, hq = (uint32_t)un & 1u;
+                    const uint32_t rowa = smem_u32(smem + s * S_STAGE_BYTES) + (op ? A_BYTES : 0) + r * 128u;
                     float4 v[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
                         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[j].x), "=f"(v[j].y), "=f"(v[j].z), "=f"(v[j].w)
                                      : "r"(rowa + (((4u * hq + (uint32_t)j) ^ (r & 7u)) << 4)));
                     uint32_t hp[8], lp[8];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        hp[2 * j] = pack2<FP16>(v[j].x, v[j].y); hp[2 * j + 1] = pack2<FP16>(v[j].z, v[j].w);
-                        lp[2 * j] = pack2<FP16>(v[j].x - unpack_lo<FP16>(hp[2 * j]), v[j].y - unpack_hi<FP16>(hp[2 * j]));
-                        lp[2 * j + 1] = pack2<FP16>(v[j].z - unpack_lo<FP16>(hp[2 * j + 1]), v[j].w - unpack_hi<FP16>(hp[2 * j + 1]));
-                    }
+                    if (sc.cvt_unpack) split16<true>(v, op ? s_b : s_a, hp, lp); else split16<false>(v, op ? s_b : s_a, hp, lp);
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
                         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowa + (((4u * hq + (uint32_t)j) ^ (r & 7u)) << 4)),
@@ -245,6 +330,9 @@ gemm_tc2s_kernel(const __grid_constant__ Maps3 maps, GemmShape p, Epi epi, long 
         const uint32_t stg = helper ? smem_u32(smem) + (uint32_t)ew * 4096u : smem_u32(stg_base) + (uint32_t)ew * 4096u;
         const int rsub = lane >> 3, cpiece = (lane & 7) * 4;
         constexpr int RB = sizeof(typename Epi::Row4) > 36 ? 2 : 4;   // steps whose global reads are issued together (register budget: 102)
+        // exact un-scaling: the accumulator holds (s_a s_b) A.B; a pre-split A was scaled by its producer with the power of two of *a_scale_src
+        const float inv_s = h16_inv_scale(APRE ? *sc.a_scale_src : h16_a_amax(sc)) * h16_inv_scale(*sc.b_amax);
+        float vmax = 0.0f;                                            // max |value stored| by this thread (EpiStd::amax_out)
         if (work->n_head != 0 && (!helper || work->n_items == 1)) {
             // ---- stream-K contribution (item 0, accumulator buffer 0): dump to this pair's slot, flag per chunk ----
             int tile, kb0_, kb1_, m0p, n0, kz0, KT, neff, z;
@@ -396,6 +484,7 @@ gemm_tc2s_kernel(const __grid_constant__ Maps3 maps, GemmShape p, Epi epi, long 
                     for (int k = 0; k < RB; ++k) {
                         const int row = row_base + (it0 + k) * 4 + rsub;
                         float c = 0.0f;
+                        acc[k].x *= inv_s; acc[k].y *= inv_s; acc[k].z *= inv_s; acc[k].w *= inv_s;
                         if (row < M && cvalid) c = e.apply4(row, col, acc[k], ca, ra[k]);
                         if (Epi::kRowSum) {
                             c += __shfl_xor_sync(0xffffffffu, c, 4); c += __shfl_xor_sync(0xffffffffu, c, 2);
@@ -415,7 +504,9 @@ gemm_tc2s_kernel(const __grid_constant__ Maps3 maps, GemmShape p, Epi epi, long 
                 __syncwarp();                                 // staging is reused by the next chunk
             }
             if (ew == 0 && !helper) TC2P_MARK(i, 3);
+            vmax = fmaxf(vmax, epi_stored_max(e, 0));
         }
+        epi_publish_amax(epi, vmax);
     }
     __syncwarp();
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -429,18 +520,53 @@ gemm_tc2s_kernel(const __grid_constant__ Maps3 maps, GemmShape p, Epi epi, long 
 }
 
 // ---- host side ----------------------------------------------------------------------------------
-int gemm_split16();                         // 1: route K-major x K-major EpiStd layers with a registered split16 mirror here (rng.cu)
+int split_groups();                         // tuning switch (env MFM_H16_GROUPS=1|2|4, default 2)
+int gemm_h16();                             // 1 (default): K-major x K-major dense layers with 16-aligned K run here (env MFM_GEMM_H16=0|1)
+// per-stream scratch of 64 device floats for the maxima of operands nobody tracked (rng.cu)
+float* amax_scratch(cudaStream_t st);
+// pre-split mirror registered for the weight buffer that contains `p` (and the device slot holding its max |w|), or null
+const float* lookup_mirror_h16(const float* p, const float** amax);
+cudaError_t launch_absmax(const float* x, long long ld, int rows, int cols, const int* n_rows_dev, float* out, cudaStream_t st);
 
 template <class Epi>
-inline cudaError_t launch(const GemmShape& p, const Epi& epi, const float* b_split16, cudaStream_t st) {
+inline bool eligible(const GemmShape& p, const Epi& epi) {
+    return tc2p::eligible<true, false>(p, epi) && p.k_split == 0 && p.K % 16 == 0 && p.lda % 16 == 0 && p.ldb % 16 == 0 &&
+           ((reinterpret_cast<uintptr_t>(p.A) | reinterpret_cast<uintptr_t>(p.B)) & 63) == 0;
+}
+
+template <class Epi>
+inline cudaError_t launch(const GemmShape& p, const Epi& epi, cudaStream_t st) {
+    const bool apre = p.a_split != nullptr && p.a_scale_src != nullptr && (reinterpret_cast<uintptr_t>(p.a_split) & 63) == 0;
+    H16Scales sc{p.a_amax, p.a_amax2, p.a_bound, p.b_amax, apre ? p.a_scale_src : nullptr, gemm_h16() == 2 ? 1 : 0, split_groups()};
+    float* scratch = nullptr;
+    if (!apre && sc.a_bound <= 0.0f && !sc.a_amax) {
+        // nobody tracked this operand's maximum: one reduction pass over it (HBM-bound, ~10 % of the GEMM at 65 536 rows)
+        if (!(scratch = amax_scratch(st))) return cudaErrorMemoryAllocation;
+        cudaError_t e = launch_absmax(p.A, p.lda, p.M, p.K, p.n_rows_dev, scratch, st);
+        if (e != cudaSuccess) return e;
+        sc.a_amax = scratch; sc.a_amax2 = nullptr;
+    }
+    const float* b_amax = sc.b_amax;
+    const float* bx = (p.b_mirror && p.b_amax) ? p.b_mirror : lookup_mirror_h16(p.B, &b_amax);
+    if (!bx && !sc.b_amax) {
+        if (!scratch && !(scratch = amax_scratch(st))) return cudaErrorMemoryAllocation;
+        cudaError_t e = launch_absmax(p.B, p.ldb, p.N, p.K, nullptr, scratch + 1, st);
+        if (e != cudaSuccess) return e;
+        b_amax = scratch + 1;
+    }
+    sc.b_amax = b_amax;
     Maps3 maps;
-    bool ok = tc::make_map_kmajor(&maps.a, p.A, p.lda, p.M, p.K, BM) && tc::make_map_kmajor(&maps.b, b_split16, p.ldb, p.N, p.K, BNH);
+    bool ok = tc::make_map_kmajor(&maps.a, apre ? p.a_split : p.A, p.lda, p.M, p.K, BM) && tc::make_map_kmajor(&maps.b, bx ? bx : p.B, p.ldb, p.N, p.K, BNH);
     if (!ok) return cudaErrorInvalidValue;
     maps.bx = maps.b;
-    auto kern = gemm_tc2s_kernel<false, Epi>;
+    auto kern = apre ? (bx ? gemm_tc2h_kernel<true, true, Epi> : gemm_tc2h_kernel<true, false, Epi>)
+                     : (bx ? gemm_tc2h_kernel<false, true, Epi> : gemm_tc2h_kernel<false, false, Epi>);
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S_SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc2h_kernel<true, true, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, S_SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc2h_kernel<true, false, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, S_SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc2h_kernel<false, true, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, S_SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc2h_kernel<false, false, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, S_SMEM_BYTES);
         if (e != cudaSuccess) return e;
         configured = true;
     }
@@ -450,10 +576,10 @@ inline cudaError_t launch(const GemmShape& p, const Epi& epi, const float* b_spl
     const bool sk = (p.K + BK - 1) / BK >= SK_MAX_SPLIT * SK_MIN_KB && (p.n_rows_dev || (rem != 0 && rem * SK_MAX_SPLIT <= sm_pairs())) &&
                     streamk_workspace(st, &sk_ws, &sk_flags, &sk_epoch);
     const int pairs = (sk || T.total >= sm_pairs()) ? sm_pairs() : T.total;
-    kern<<<dim3(2 * pairs), THREADS, S_SMEM_BYTES, st>>>(maps, p, epi, tc2::gemm_timeline(), sk_ws, sk_flags, sk_epoch);
+    kern<<<dim3(2 * pairs), THREADS, S_SMEM_BYTES, st>>>(maps, p, epi, sc, tc2::gemm_timeline(), sk_ws, sk_flags, sk_epoch);
     ++g_mfm_launches;
     return cudaGetLastError();
 }
 
-}  // namespace tc2s
+}  // namespace tc2h
 }  // namespace mfm

@@ -396,6 +396,7 @@ gemm_tc2p_kernel(const __grid_constant__ Maps3 maps, GemmShape p, Epi epi, long 
         const uint32_t stg = helper ? smem_u32(smem) + (uint32_t)ew * 4096u : smem_u32(stg_base) + (uint32_t)ew * 4096u;
         const int rsub = lane >> 3, cpiece = (lane & 7) * 4;
         constexpr int RB = sizeof(typename Epi::Row4) > 36 ? 2 : 4;   // steps whose global reads are issued together (register budget: 102)
+        float vmax = 0.0f;                                            // max |value stored| by this thread (EpiStd::amax_out)
         if (work->n_head != 0 && (!helper || work->n_items == 1)) {
             // ---- stream-K contribution (item 0, accumulator buffer 0): dump to this pair's slot, flag per chunk ----
             int tile, kb0_, kb1_, m0p, n0, kz0, KT, neff, z;
@@ -566,7 +567,9 @@ gemm_tc2p_kernel(const __grid_constant__ Maps3 maps, GemmShape p, Epi epi, long 
                 __syncwarp();                                 // staging is reused by the next chunk
             }
             if (ew == 0 && !helper) TC2P_MARK(i, 3);
+            vmax = fmaxf(vmax, epi_stored_max(e, 0));
         }
+        epi_publish_amax(epi, vmax);
     }
     __syncwarp();
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

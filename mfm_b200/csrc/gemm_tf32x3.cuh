@@ -10,6 +10,7 @@
 // same arithmetic lives in gemm_tcgen05.cuh and is selected for large aligned shapes.
 #pragma once
 #include "common.cuh"
+#include <cuda_fp16.h>
 
 namespace mfm {
 
@@ -30,7 +31,32 @@ struct GemmShape {
     const float* B; long long ldb;   // B_NMAJOR: B[k*ldb + n]; else B[n*ldb + k]
     const int* n_rows_dev;           // optional: device int, effective M (active rows); tiles beyond exit
     int k_split = 0;                 // >0: gridDim.z slices of k_split values of k; epilogue gets slice via at_z()
+    // magnitudes of the operands for the scaled fp16 split of gemm_tcgen05_h16.cuh (ignored by the other kernels):
+    const float* a_amax = nullptr;   // device float: max |A| (maintained by A's producer), or null
+    const float* a_amax2 = nullptr;  // second slot when A spans two producers' outputs (the larger one counts)
+    float a_bound = 0.0f;            // > 0: bound on |A| known on the host (takes precedence)
+    const float* b_amax = nullptr;   // device float: max |B|, or null (weight mirrors carry their own)
+    const float* b_mirror = nullptr; // pre-split (split16, scaled fp16) copy of B made with h16_scale(*b_amax), or null: look one up
+    const float* a_split = nullptr;  // pre-split copy of A (same shape / leading dimension, written by A's producer), or null
+    const float* a_scale_src = nullptr; // device float: the copy was scaled by h16_scale(*a_scale_src) (the producer's bound on |A|)
 };
+
+// functors that track what they store expose `amax_out` (slot or null) and a per-thread running maximum `vmax`
+template <class E> __device__ __forceinline__ auto epi_stored_max(const E& e, int) -> decltype(e.vmax) { return e.vmax; }
+template <class E> __device__ __forceinline__ float epi_stored_max(const E&, long) { return 0.0f; }
+template <class E> __device__ __forceinline__ auto epi_amax_slot(const E& e, int) -> decltype(e.amax_out) { return e.amax_out; }
+template <class E> __device__ __forceinline__ float* epi_amax_slot(const E&, long) { return nullptr; }
+// call with whole warps (uniform branch on the slot)
+// the bound a split-writing functor scaled its copy with, published once per launch for the consumer (call from whole warps)
+template <class E> __device__ __forceinline__ auto epi_publish_bound(const E& e, int) -> decltype((void)e.bound_out) {
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (threadIdx.x & 31) == 0 && e.bound_out) *e.bound_out = e.out_bound();
+}
+template <class E> __device__ __forceinline__ void epi_publish_bound(const E&, long) {}
+template <class E> __device__ __forceinline__ void epi_publish_amax(const E& e, float vmax) {
+    float* slot = epi_amax_slot(e, 0);
+    if (slot != nullptr) amax_publish_warp(slot, vmax);
+    epi_publish_bound(e, 0);
+}
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool pred) {
     const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
@@ -215,6 +241,7 @@ __global__ void __launch_bounds__(GTHREADS, 2) gemm_tf32x3_kernel(GemmShape p, E
         __syncthreads();
         if (tid < GBM && m0 + tid < M) epi.row_partial(m0 + tid, blockIdx.x, sRed[tid * 2 + 0] + sRed[tid * 2 + 1]);
     }
+    epi_publish_amax(epi, epi_stored_max(epi, 0));
 }
 
 template <bool A_KMAJOR, bool B_NMAJOR, class Epi>
@@ -256,6 +283,8 @@ struct EpiStd {
     float alpha; int relu;
     int mask_div = 1;                  // rows of the mask are shared by mask_div consecutive output rows
     long long c_zstride = 0;           // split-K: slice z writes to C + z*c_zstride
+    float* amax_out = nullptr;         // optional device slot: max |C| (C is the A operand of a later h16 GEMM)
+    mutable float vmax = 0.0f;         // per-thread running maximum of what this copy of the functor stored
     __device__ __forceinline__ void at_z(int z) { C += (long long)z * c_zstride; }
     struct Aux { float bias, add, mask; };
     __device__ __forceinline__ Aux load(int row, int col) const {
@@ -270,6 +299,7 @@ struct EpiStd {
         if (relu) v = fmaxf(v, 0.0f);
         v = a.mask > 0.0f ? v : 0.0f;
         C[(long long)row * ldc + col] = v;
+        vmax = fmaxf(vmax, fabsf(v));
         return 0.0f;
     }
     __device__ __forceinline__ float operator()(int row, int col, float acc) const { return apply(row, col, acc, load(row, col)); }
@@ -296,6 +326,126 @@ struct EpiStd {
         v.x = r.mask.x > 0.0f ? v.x : 0.0f; v.y = r.mask.y > 0.0f ? v.y : 0.0f;
         v.z = r.mask.z > 0.0f ? v.z : 0.0f; v.w = r.mask.w > 0.0f ? v.w : 0.0f;
         st4(C + (long long)row * ldc + col, v);
+        vmax = amax4(vmax, v);
+        return 0.0f;
+    }
+};
+
+
+// ---- EpiStd that ALSO writes C as the pre-split A operand of the next scaled-fp16 GEMM ----------------------------------------
+// C is stored twice: as fp32 (masks, weight gradients and element-wise kernels read that) and, in `Cs`, in the split16 layout
+// of gemm_tcgen05_h16.cuh (every 16 consecutive floats of a row -> 16 hi | 16 lo fp16 parts of the SCALED values, same leading
+// dimension), so that the consuming GEMM's TMA delivers tensor-core format and its splitter warps have nothing to do - the
+// shared-memory pipe, which bounds that kernel, then carries 88 KB instead of 120 KB per k-block.
+// The scale must be known BEFORE the first element is written, i.e. before max |C| exists.  It comes from a bound instead:
+//     |C[m][n]| <= max |A| * max_n sum_k |B[n][k]| + max |bias| + bound(add)          (Hoelder; relu and masks only shrink)
+// with the EXACT maximum of A (tracked by A's producer), so the slack does not compound from layer to layer; the per-layer
+// operator norms are computed once per parameter update (weight_norms_kernel).  For a dense layer with K = 1024 inputs the
+// bound is ~2^7 above the true maximum, which leaves 11 octaves of full 22-bit precision below it (18 with an exact maximum)
+// and the same absolute floor; overflow is impossible by construction.  The bound is published in `bound_out` for the
+// consumer (GemmShape::a_scale_src) and the exact maximum of C still goes to `amax_out` for ITS bound.
+__device__ __forceinline__ uint32_t pack_h2_rn(float first, float second) {
+    uint32_t r; asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(second), "f"(first)); return r;
+}
+__device__ __forceinline__ void split_pair(float x, float y, uint32_t& hp, uint32_t& lp) {
+    hp = pack_h2_rn(x, y);
+    unsigned short h0, h1; asm("mov.b32 {%0, %1}, %2;" : "=h"(h0), "=h"(h1) : "r"(hp));
+    const unsigned short m1 = 0xBC00; float d0, d1;
+    asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(d0) : "h"(h0), "h"(m1), "f"(x));
+    asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(d1) : "h"(h1), "h"(m1), "f"(y));
+    lp = pack_h2_rn(d0, d1);
+}
+__host__ __device__ __forceinline__ uint32_t h16_scale_exp_(float amax) {     // == tc2h::h16_scale_exp (defined there for the kernel)
+#ifdef __CUDA_ARCH__
+    const uint32_t b = __float_as_uint(amax) & 0x7FFFFFFFu;
+#else
+    union { float f; uint32_t u; } c; c.f = amax; const uint32_t b = c.u & 0x7FFFFFFFu;
+#endif
+    int e = (int)(b >> 23);
+    if (b == 0u || e == 255) return 127u;
+    if (e == 0) e = 1;
+    int se = 127 + 14 - (e - 127);
+    se = se < 2 ? 2 : (se > 252 ? 252 : se);
+    return (uint32_t)se;
+}
+struct EpiStdS {
+    static constexpr bool kRowSum = false;
+    float* C; long long ldc;
+    const float* bias; const float* mask; long long ldm; const float* add; long long ldadd; int relu; int mask_div;
+    float* Cs;                         // split16 copy of C (leading dimension ldc)
+    const float* in_amax; const float* in_amax2; float in_bound;   // exact maximum of the A operand (as GemmShape)
+    const float* w_norm;               // device: max_n sum_k |B[n][k]|
+    const float* bias_amax;            // device or null
+    const float* add_bound;            // device or null: bound on |add|
+    float* bound_out;                  // device: receives the bound on |C| the copy was scaled with
+    // a second product whose result shares C's scale (the two halves of cat = [s_x | s_t] are ONE operand of Dense_5): the
+    // bound is the larger of the two layers' bounds, so both layers compute the same scale
+    const float* alt_amax = nullptr; const float* alt_w_norm = nullptr; const float* alt_bias = nullptr;
+    float* amax_out = nullptr;         // device or null: exact max |C|
+    mutable float vmax = 0.0f;
+    __device__ __forceinline__ void at_z(int) {}
+    __device__ __forceinline__ float out_bound() const {
+        float a = in_bound;
+        if (!(a > 0.0f)) { a = *in_amax; if (in_amax2) a = fmaxf(a, *in_amax2); }
+        float b = a * *w_norm;
+        if (bias_amax) b += *bias_amax;
+        if (add_bound) b += *add_bound;
+        if (alt_amax) b = fmaxf(b, *alt_amax * *alt_w_norm + (alt_bias ? *alt_bias : 0.0f));
+        return b;
+    }
+    __device__ __forceinline__ float out_scale() const { return __uint_as_float(h16_scale_exp_(out_bound()) << 23); }
+    struct Aux { float bias, add, mask, scale; };
+    __device__ __forceinline__ Aux load(int row, int col) const {
+        Aux a;
+        a.bias = bias ? __ldg(bias + col) : 0.0f;
+        a.add = add ? add[(long long)row * ldadd + col] : 0.0f;
+        a.mask = mask ? __ldg(mask + (long long)(mask_div == 1 ? row : row / mask_div) * ldm + col) : 1.0f;
+        a.scale = out_scale();
+        return a;
+    }
+    __device__ __forceinline__ float apply(int row, int col, float acc, const Aux& a) const {
+        float v = acc + a.bias + a.add;
+        if (relu) v = fmaxf(v, 0.0f);
+        v = a.mask > 0.0f ? v : 0.0f;
+        C[(long long)row * ldc + col] = v;
+        vmax = fmaxf(vmax, fabsf(v));
+        const float x = v * a.scale;
+        const __half h = __float2half_rn(x), l = __float2half_rn(x - __half2float(h));
+        __half* g = reinterpret_cast<__half*>(Cs + (long long)row * ldc + (col & ~15));
+        g[col & 15] = h; g[16 + (col & 15)] = l;
+        return 0.0f;
+    }
+    __device__ __forceinline__ float operator()(int row, int col, float acc) const { return apply(row, col, acc, load(row, col)); }
+    __device__ __forceinline__ void row_partial(int, int, float) const {}
+    struct Col4 { float4 bias; float scale; };
+    struct Row4 { float4 add, mask; };
+    bool vec_ok() const {
+        return aligned16(C) && ldc % 16 == 0 && (reinterpret_cast<uintptr_t>(Cs) & 63) == 0 && (!bias || aligned16(bias)) &&
+               (!mask || (aligned16(mask) && ldm % 4 == 0)) && (!add || (aligned16(add) && ldadd % 4 == 0));
+    }
+    __device__ __forceinline__ Col4 load_col4(int col) const { Col4 c; c.bias = bias ? ldg4(bias + col) : f4(0.0f); c.scale = out_scale(); return c; }
+    __device__ __forceinline__ Row4 load_row4(int row, int col) const {
+        Row4 r;
+        r.add = add ? ld4(add + (long long)row * ldadd + col) : f4(0.0f);        // may alias C: plain load
+        r.mask = mask ? ldg4(mask + (long long)(mask_div == 1 ? row : row / mask_div) * ldm + col) : f4(1.0f);
+        return r;
+    }
+    __device__ __forceinline__ float apply4(int row, int col, const float4& acc, const Col4& c, const Row4& r) const {
+        float4 v;
+        v.x = acc.x + c.bias.x + r.add.x; v.y = acc.y + c.bias.y + r.add.y;
+        v.z = acc.z + c.bias.z + r.add.z; v.w = acc.w + c.bias.w + r.add.w;
+        if (relu) { v.x = fmaxf(v.x, 0.0f); v.y = fmaxf(v.y, 0.0f); v.z = fmaxf(v.z, 0.0f); v.w = fmaxf(v.w, 0.0f); }
+        v.x = r.mask.x > 0.0f ? v.x : 0.0f; v.y = r.mask.y > 0.0f ? v.y : 0.0f;
+        v.z = r.mask.z > 0.0f ? v.z : 0.0f; v.w = r.mask.w > 0.0f ? v.w : 0.0f;
+        st4(C + (long long)row * ldc + col, v);
+        vmax = amax4(vmax, v);
+        // columns col..col+3 of the 16-group: hi parts at byte 2 (col % 16), lo parts 32 bytes further
+        uint2 hp, lp;
+        split_pair(v.x * c.scale, v.y * c.scale, hp.x, lp.x);
+        split_pair(v.z * c.scale, v.w * c.scale, hp.y, lp.y);
+        char* g = reinterpret_cast<char*>(Cs + (long long)row * ldc + (col & ~15)) + 2 * (col & 15);
+        *reinterpret_cast<uint2*>(g) = hp;
+        *reinterpret_cast<uint2*>(g + 32) = lp;
         return 0.0f;
     }
 };
@@ -307,10 +457,8 @@ struct EpiStd {
 #include "gemm_tcgen05.cuh"
 #include "gemm_tcgen05_2sm.cuh"
 #include "gemm_tcgen05_persist.cuh"
-#include "gemm_tcgen05_split16.cuh"
+#include "gemm_tcgen05_h16.cuh"
 namespace mfm {
-template <class Epi> struct Split16Epi { static constexpr bool value = false; };
-template <> struct Split16Epi<EpiStd> { static constexpr bool value = true; };     // the FM / forward dense layers only
 // 0 = auto, 1 = force mma.sync (env MFM_GEMM=mma), 2 = tcgen05 single-CTA only (env MFM_GEMM=tc1),
 // 3 = no persistent kernel: one-tile CTA-pair kernel with separate cross-term accumulators (env MFM_GEMM=tc2)
 int gemm_backend();
@@ -328,13 +476,9 @@ inline cudaError_t launch_gemm(const GemmShape& p, const Epi& epi, cudaStream_t 
         case 2:
             // persistent (epilogue overlapped with the next tile's MMAs) unless the reduction is split:
             // split-K tiles have long main loops (nothing to hide) and need the separate accumulators
-            if constexpr (A_KMAJOR && !B_NMAJOR && Split16Epi<Epi>::value) {
-                // experimental 3-slot operand split (off by default): needs the weight operand's split16 mirror
-                if (tc2s::gemm_split16() && gemm_backend() == 0 && p.k_split == 0 && p.K % 16 == 0 && p.ldb % 16 == 0 &&
-                    tc2p::eligible<A_KMAJOR, B_NMAJOR>(p, epi)) {
-                    const float* bx = tc2p::lookup_cross(p.B);
-                    if (bx && (reinterpret_cast<uintptr_t>(bx) & 63) == 0) return tc2s::launch<Epi>(p, epi, bx, st);
-                }
+            if constexpr (A_KMAJOR && !B_NMAJOR) {
+                // scaled fp16 split, three tensor-core passes (gemm_tcgen05_h16.cuh): every K-major x K-major layer with 16-aligned K
+                if (tc2h::gemm_h16() && gemm_backend() == 0 && tc2h::eligible(p, epi)) return tc2h::launch<Epi>(p, epi, st);
             }
             if (gemm_backend() == 0 && p.k_split == 0 && tc2p::eligible<A_KMAJOR, B_NMAJOR>(p, epi))
                 return tc2p::launch<A_KMAJOR, B_NMAJOR, Epi>(p, epi, st);

@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(256)
 pines_propose_kernel(mfm_target_t T, const uint32_t* __restrict__ rng_key, int n, int chain_offset, int n_total,
                      float h, float sq2h, const float* __restrict__ x, const float* __restrict__ g,
                      float* __restrict__ xprop, float* __restrict__ lik, float* __restrict__ sq_new_out,
-                     float* __restrict__ u_out) {
+                     float* __restrict__ u_out, float* __restrict__ xprop_amax) {
     const int lane = threadIdx.x & 31;
     const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= n) return;
@@ -133,13 +133,15 @@ pines_propose_kernel(mfm_target_t T, const uint32_t* __restrict__ rng_key, int n
     float* xp = xprop + (long long)c * d;
     const float sq = langevin_propose(ck.integrator, d, h, sq2h, x + (long long)c * d, g + (long long)c * d, xp, lane);
     __syncwarp();
-    float s = 0.0f;
+    float s = 0.0f, vm = 0.0f;
     for (int i = lane; i < d; i += 32) {
         const float xv = xp[i];
         s += xv * T.counts[i] - T.poisson_a * expf(xv);
+        vm = fmaxf(vm, fabsf(xv));
     }
     s = warp_sum(s);
     if (lane == 0) { lik[c] = s; sq_new_out[c] = sq; u_out[c] = scalar_uniform(ck.rmh); }
+    if (xprop_amax) amax_publish_warp(xprop_amax, vm);      // the proposal is the A operand of the K^-1 GEMM (scaled-fp16 split)
 }
 
 __global__ void __launch_bounds__(256)
@@ -165,7 +167,7 @@ extern "C" {
 size_t mfm_mala_workspace_bytes(const mfm_target_t* t, int n) {
     using namespace mfm;
     if (t->kind != MFM_TARGET_PINES) return 256;
-    return ws_slice((size_t)n * t->dim, 4) * 2 + ws_slice((size_t)n * pines_n_tiles(t->dim), 4) + 3 * ws_slice(n, 4) + 256;
+    return ws_slice((size_t)n * t->dim, 4) * 2 + ws_slice((size_t)n * pines_n_tiles(t->dim), 4) + 3 * ws_slice(n, 4) + ws_slice(64, 4) + 256;
 }
 
 int mfm_mala_step(const mfm_target_t* t, const uint32_t* rng_key, int per_chain_keys, int n, int chain_offset, int n_total, float step_size,
@@ -190,11 +192,13 @@ int mfm_mala_step(const mfm_target_t* t, const uint32_t* rng_key, int per_chain_
         float* gnew = w.take<float>((size_t)n * T.dim);
         float* partial = w.take<float>((size_t)n * nt);
         float* lik = w.take<float>(n); float* sqn = w.take<float>(n); float* u = w.take<float>(n);
+        float* xamax = w.take<float>(64);
         if (!w.ok) { mfm_set_last_error_msg("workspace too small (mfm_mala_step)"); return MFM_ERR_WORKSPACE; }
+        MFM_CUDA_CHECK(cudaMemsetAsync(xamax, 0, sizeof(float), stream));
         pines_propose_kernel<<<ceil_div(n, 8), 256, 0, stream>>>(T, rng_key, n, chain_offset, n_total, h, sq2h, position,
-                                                                  logdensity_grad, xprop, lik, sqn, u);
+                                                                  logdensity_grad, xprop, lik, sqn, u, xamax);
         MFM_LAUNCH_CHECK();
-        int rc = pines_grad_gemm(T, n, xprop, T.dim, T.beta, gnew, T.dim, partial, nullptr, stream);
+        int rc = pines_grad_gemm(T, n, xprop, T.dim, T.beta, gnew, T.dim, partial, nullptr, stream, xamax);
         if (rc) return rc;
         pines_mala_finalize_kernel<<<ceil_div(n, 8), 256, 0, stream>>>(T, n, nt, h, quarter, xprop, gnew, lik, partial, sqn, u, io);
         MFM_LAUNCH_CHECK();

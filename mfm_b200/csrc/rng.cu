@@ -14,117 +14,6 @@ void mfm_set_last_error_msg(const char* msg) { snprintf(g_err, sizeof(g_err), "%
 extern "C" const char* mfm_last_error(void) { return g_err; }
 extern "C" int mfm_version(void) { return 100; }
 unsigned long long g_mfm_launches = 0;
-#include <stdlib.h>
-namespace mfm {
-static int g_backend = -1;
-int gemm_backend() {
-    if (g_backend < 0) {
-        const char* e = getenv("MFM_GEMM");
-        g_backend = (e && strcmp(e, "mma") == 0) ? 1 : ((e && strcmp(e, "tc1") == 0) ? 2 : ((e && strcmp(e, "tc2") == 0) ? 3 : 0));
-    }
-    return g_backend;
-}
-namespace tc2p {
-static int g_cross_bf16 = -1;
-int gemm_cross_bf16() {
-    if (g_cross_bf16 < 0) { const char* e = getenv("MFM_GEMM_CROSS"); g_cross_bf16 = (e && strcmp(e, "tf32") == 0) ? 0 : 1; }
-    return g_cross_bf16;
-}
-int sm_pairs();
-// ---- pre-split weight mirrors (gemm_tcgen05_persist.cuh, BPRE) -------------------------------------------------------
-// [base, base + n_floats) -> mirror (same byte layout, every 8 floats replaced by 8 + 8 bf16).  Registered by the ABI call
-// that built the mirrors in ITS workspace and cleared when it returns (CrossScope), so no stale range survives a call.
-struct CrossRange { const float* base; size_t n; const float* mirror; };
-static thread_local CrossRange g_cross[8];
-static thread_local int g_n_cross = 0;
-void register_cross(const float* base, size_t n_floats, const float* mirror) {
-    if (g_n_cross < 8) g_cross[g_n_cross++] = CrossRange{base, n_floats, mirror};
-}
-void clear_cross() { g_n_cross = 0; }
-const float* lookup_cross(const float* p) {
-    for (int i = 0; i < g_n_cross; ++i)
-        if (p >= g_cross[i].base && p < g_cross[i].base + g_cross[i].n && ((p - g_cross[i].base) % 8) == 0) return g_cross[i].mirror + (p - g_cross[i].base);
-    return nullptr;
-}
-static int g_split16 = -1;
-static int g_streamk = -1;
-constexpr int SK_SLOT_FLOATS = 256 * 256, SK_SLOT_FLAGS = 64;   // = gemm_tcgen05_persist.cuh (static_assert there)
-struct SkWs { cudaStream_t st; int dev; float* ws; unsigned* flags; unsigned epoch; };
-static SkWs g_skws[8];
-static int g_n_skws = 0;
-// One scratch area per (device, stream): GEMMs on one stream are ordered, so a slot is never rewritten
-// while an earlier launch still reads it.  Allocated on the first stream-K launch of the stream (the only
-// allocation the library makes; 19.4 MB + 19 KB).  Streams beyond the 8th run without stream-K.
-bool streamk_workspace(cudaStream_t st, float** ws, unsigned** flags, unsigned* epoch) {
-    if (g_streamk < 0) { const char* e = getenv("MFM_STREAMK"); g_streamk = (e && e[0] == '0') ? 0 : 1; }
-    if (!g_streamk) return false;
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return false;
-    // never inside a CUDA-graph capture: the launch epoch is a kernel argument, a replay would meet its own stale flags
-    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) { cudaGetLastError(); return false; }
-    SkWs* w = nullptr;
-    for (int i = 0; i < g_n_skws; ++i) if (g_skws[i].st == st && g_skws[i].dev == dev) { w = &g_skws[i]; break; }
-    if (!w) {
-        if (g_n_skws == 8) return false;
-        SkWs n{st, dev, nullptr, nullptr, 0};
-        const size_t fbytes = (size_t)sm_pairs() * SK_SLOT_FLAGS * sizeof(unsigned);
-        if (cudaMalloc(&n.ws, (size_t)sm_pairs() * SK_SLOT_FLOATS * sizeof(float)) != cudaSuccess) { cudaGetLastError(); return false; }
-        if (cudaMalloc(&n.flags, fbytes) != cudaSuccess || cudaMemset(n.flags, 0, fbytes) != cudaSuccess) { cudaGetLastError(); cudaFree(n.ws); return false; }
-        g_skws[g_n_skws] = n;
-        w = &g_skws[g_n_skws++];
-    }
-    *ws = w->ws; *flags = w->flags; *epoch = ++w->epoch;
-    return true;
-}
-}   // namespace tc2p
-namespace tc2s {
-// EXPERIMENTAL split16 dense-layer kernel (gemm_tcgen05_split16.cuh): off unless MFM_GEMM_SPLIT=bf16x3 / mfm_set_gemm_split16(1)
-int gemm_split16() {
-    if (tc2p::g_split16 < 0) { const char* e = getenv("MFM_GEMM_SPLIT"); tc2p::g_split16 = (e && strcmp(e, "bf16x3") == 0) ? 1 : 0; }
-    return tc2p::g_split16;
-}
-}
-namespace tc2p {
-int sm_pairs() {
-    static int pairs = 0;
-    if (pairs == 0) {
-        int dev = 0, sms = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 2) sms = 148;
-        pairs = sms / 2;
-    }
-    return pairs;
-}
-}
-namespace tc2 {
-static int g_raw_hi = -1;
-int gemm_raw_hi() {
-    if (g_raw_hi < 0) { const char* e = getenv("MFM_TC_RAWHI"); g_raw_hi = (e && e[0] == '0') ? 0 : 1; }
-    return g_raw_hi;
-}
-}
-}
-extern "C" void mfm_set_gemm_raw_hi(int v) { mfm::tc2::g_raw_hi = v ? 1 : 0; }
-extern "C" void mfm_set_gemm_cross_bf16(int v) { mfm::tc2p::g_cross_bf16 = v ? 1 : 0; }
-extern "C" void mfm_set_gemm_streamk(int v) { mfm::tc2p::g_streamk = v ? 1 : 0; }
-extern "C" void mfm_set_gemm_split16(int v) { mfm::tc2p::g_split16 = v ? 1 : 0; }
-extern "C" void mfm_gemm_register_mirror(const float* base, long long n_floats, const float* mirror) {
-    if (base && mirror && n_floats > 0) mfm::tc2p::register_cross(base, (size_t)n_floats, mirror); else mfm::tc2p::clear_cross();
-}
-// tuning aid (not part of the ABI header): SM-clock timeline of one CTA pair of the last tc2 GEMM
-namespace mfm { namespace tc2 {
-static long long* g_timeline_buf = nullptr;
-static int g_timeline = 0;
-long long* gemm_timeline() { return g_timeline ? g_timeline_buf : nullptr; }
-} }
-extern "C" int mfm_debug_gemm_timeline(int enable, long long* out16) {
-    using namespace mfm::tc2;
-    if (!g_timeline_buf && cudaMalloc(&g_timeline_buf, 64 * sizeof(long long)) != cudaSuccess) return -1;
-    g_timeline = enable ? 1 : 0;
-    if (out16) return cudaMemcpy(out16, g_timeline_buf, 64 * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -1;
-    return 0;
-}
-extern "C" void mfm_set_gemm_backend(int b) { mfm::g_backend = b; }
 extern "C" unsigned long long mfm_launch_count(void) { return g_mfm_launches; }
 
 namespace {

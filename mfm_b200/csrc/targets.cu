@@ -170,17 +170,24 @@ struct EpiPinesField {
 
 int pines_n_tiles(int d) { return gemm_n_tiles(d); }
 
+// the constant K^-1 arrives pre-split (scaled fp16 parts + its maximum behind them) when the host built the mirror once
+static inline void kinv_mirror(const mfm_target_t& T, GemmShape& p) {
+    if (T.kinv_split && tc2h::gemm_h16()) { p.b_mirror = T.kinv_split; p.b_amax = T.kinv_split + (long long)T.dim * T.dim; }
+}
+
 int pines_grad_gemm(const mfm_target_t& T, int n, const float* X, long long ldx, float beta, float* grad_out,
-                    long long ldg, float* prior_partial, const int* n_rows_dev, cudaStream_t st) {
+                    long long ldg, float* prior_partial, const int* n_rows_dev, cudaStream_t st, const float* x_amax) {
     GemmShape p{n, T.dim, T.dim, X, ldx, T.kinv, (long long)T.dim, n_rows_dev};
+    p.a_amax = x_amax; kinv_mirror(T, p);
     EpiPinesGrad e{X, ldx, T.counts, T.kinv_mu, T.mu, T.poisson_a, beta, grad_out, ldg, prior_partial, gemm_n_tiles(T.dim)};
     MFM_CUDA_CHECK((launch_gemm<true, false>(p, e, st)   /* K^-1 is symmetric: read it as the K-major operand */));
     return MFM_OK;
 }
 
 int pines_kinv_gemm(const mfm_target_t& T, int n, const float* Z, long long ldz, float* out, long long ldo,
-                    const int* n_rows_dev, cudaStream_t st) {
+                    const int* n_rows_dev, cudaStream_t st, float z_bound) {
     GemmShape p{n, T.dim, T.dim, Z, ldz, T.kinv, (long long)T.dim, n_rows_dev};
+    p.a_bound = z_bound; kinv_mirror(T, p);
     EpiStd e{out, ldo, nullptr, nullptr, 0, nullptr, 0, 1.0f, 0};
     MFM_CUDA_CHECK((launch_gemm<true, false>(p, e, st)   /* K^-1 is symmetric: read it as the K-major operand */));
     return MFM_OK;
@@ -242,10 +249,11 @@ int target_value_and_grad(const mfm_target_t& T, int n, const float* x, float* l
 }
 
 int target_field_terms(const mfm_target_t& T, int n, const float* x, const float* z, const float* zkinv, float clip,
-                       float* gc, float* hvc, float* hdc, const int* n_rows_dev, cudaStream_t st) {
+                       float* gc, float* hvc, float* hdc, const int* n_rows_dev, cudaStream_t st, const float* x_amax) {
     if (n <= 0) return MFM_OK;
     if (T.kind == MFM_TARGET_PINES) {
         GemmShape p{n, T.dim, T.dim, x, (long long)T.dim, T.kinv, (long long)T.dim, n_rows_dev};
+        p.a_amax = x_amax; kinv_mirror(T, p);
         EpiPinesField e{x, (long long)T.dim, T.counts, T.kinv_mu, T.kinv_diag, z, zkinv, T.poisson_a, clip, gc, hvc, hdc, (long long)T.dim};
         MFM_CUDA_CHECK((launch_gemm<true, false>(p, e, st)   /* K^-1 is symmetric: read it as the K-major operand */));
         return MFM_OK;
@@ -301,10 +309,55 @@ int mfm_gemm_tf32x3_gated(int M, int N, int K, const float* A, long long lda, co
 }
 
 int mfm_gemm_presplit(const float* src, float* mirror, long long n_floats, mfm_stream_t stream) {
-    if (!src || !mirror || n_floats <= 0 || n_floats % 8 || ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(mirror)) & 31)) {
+    const bool h16 = mfm::tc2h::gemm_h16() != 0;
+    if (!src || !mirror || n_floats <= 0 || n_floats % (h16 ? 16 : 8) || ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(mirror)) & (h16 ? 63 : 31))) {
         mfm_set_last_error_msg("bad argument (mfm_gemm_presplit)"); return MFM_ERR_ARG;
     }
-    return mfm::presplit_weights(src, mirror, n_floats, stream);
+    float* amax = mirror + n_floats;          // the mirror buffer holds n_floats + 16 floats: max |src| lives behind the parts
+    if (h16) MFM_CUDA_CHECK(mfm::tc2h::launch_absmax(src, n_floats, 1, (int)n_floats, nullptr, amax, stream));
+    return mfm::presplit_weights(src, mirror, n_floats, h16 ? amax : nullptr, stream);
+}
+
+int mfm_absmax(const float* x, long long ld, int rows, int cols, float* out, mfm_stream_t stream) {
+    if (!x || !out || rows <= 0 || cols <= 0 || cols % 4 || ld % 4 || (reinterpret_cast<uintptr_t>(x) & 15)) { mfm_set_last_error_msg("bad argument (mfm_absmax)"); return MFM_ERR_ARG; }
+    MFM_CUDA_CHECK(mfm::tc2h::launch_absmax(x, ld, rows, cols, nullptr, out, stream));
+    return MFM_OK;
+}
+
+int mfm_gemm_dense(int M, int N, int K, const float* A, long long lda, const float* Bt, long long ldb, const float* bias, int relu,
+                   float* Cout, long long ldc, const float* a_amax, float* c_amax, const float* a_split, const float* a_scale_src,
+                   mfm_stream_t stream) {
+    using namespace mfm;
+    GemmShape p{M, N, K, A, lda, Bt, ldb, nullptr};
+    p.a_amax = a_amax; p.a_split = a_split; p.a_scale_src = a_scale_src;
+    EpiStd e{Cout, ldc, bias, nullptr, 0, nullptr, 0, 1.0f, relu};
+    e.amax_out = c_amax;
+    MFM_CUDA_CHECK((launch_gemm<true, false>(p, e, stream)));
+    return MFM_OK;
+}
+
+/* Test hook of the pre-split hand-over between two dense layers (not in the ABI header):
+ *   C1 = relu(A B1t^T + b1), written as fp32 AND pre-split (C1s) by the first layer's epilogue with the scale of its output bound;
+ *   C2 = C1 B2t^T, whose A operand is loaded pre-split.  slots: device float[4] = {max|A|, max|C1| (exact), bound(C1), -}. */
+int mfm_debug_dense_chain(int M, int K, int N1, int N2, const float* A, const float* B1t, const float* b1, const float* B2t,
+                          float* C1, float* C1s, float* C2, const float* wnorm1, const float* bias_amax, float* slots, mfm_stream_t stream) {
+    using namespace mfm;
+    MFM_CUDA_CHECK(tc2h::launch_absmax(A, K, M, K, nullptr, slots, stream));
+    MFM_CUDA_CHECK(cudaMemsetAsync(slots + 1, 0, 3 * sizeof(float), stream));
+    {
+        GemmShape p{M, N1, K, A, (long long)K, B1t, (long long)K, nullptr};
+        p.a_amax = slots;
+        EpiStdS e{C1, (long long)N1, b1, nullptr, 0, nullptr, 0, 1, 1, C1s, slots, nullptr, 0.0f, wnorm1, bias_amax, nullptr, slots + 2};
+        e.amax_out = slots + 1;
+        MFM_CUDA_CHECK((launch_gemm<true, false>(p, e, stream)));
+    }
+    {
+        GemmShape p{M, N2, N1, C1, (long long)N1, B2t, (long long)N1, nullptr};
+        p.a_amax = slots + 1; p.a_split = C1s; p.a_scale_src = slots + 2;
+        EpiStd e{C2, (long long)N2, nullptr, nullptr, 0, nullptr, 0, 1.0f, 0};
+        MFM_CUDA_CHECK((launch_gemm<true, false>(p, e, stream)));
+    }
+    return MFM_OK;
 }
 
 int mfm_gemm_tf32x3_rows(int M, int N, int K, const float* A, long long lda, const float* Bt, long long ldb, const float* bias,

@@ -199,10 +199,21 @@ class LogGaussianCoxPines(Distribution):
         self._kinv_mu = self._tensor(self._mu_zero * Kinv.sum(0))
         self._kinv_diag = self._tensor(np.diag(Kinv))
         self._cholesky_gram = self._tensor(L)
+        # K^-1 is the constant B operand of every pines GEMM: its scaled-fp16 split (include/mfm_b200.h, mfm_gemm_presplit) is
+        # made once here instead of in shared memory by every CTA of every call
+        self._kinv_split = None
+        if self.device.type == "cuda" and dim % 16 == 0:
+            lib = _lib.load()
+            if lib.mfm_gemm_h16_enabled():
+                m = torch.empty(dim * dim + 16, dtype=torch.float32, device=self.device)
+                with torch.cuda.device(self.device):
+                    _lib.check(lib.mfm_gemm_presplit(self._kinv.data_ptr(), m.data_ptr(), dim * dim, _lib.stream()))
+                self._kinv_split = m
 
     def _fill(self, d):
         d.counts, d.kinv = self._flat_bin_counts.data_ptr(), self._kinv.data_ptr()
         d.kinv_mu, d.kinv_diag = self._kinv_mu.data_ptr(), self._kinv_diag.data_ptr()
+        d.kinv_split = self._kinv_split.data_ptr() if self._kinv_split is not None else None
         d.mu, d.log_norm, d.poisson_a = self._mu_zero, self._log_norm, self._poisson_a
 
     def initialize_model(self, rng_key, n_chain):

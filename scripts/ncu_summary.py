@@ -24,11 +24,13 @@ def main():
     rows = list(csv.reader(out.splitlines()))
     h = rows[0]
     recs = [dict(zip(h, r)) for r in rows[2:]]
+    # every tensor-pipe metric the report holds (the name differs between ncu versions / chips; an empty row told us so in round 1)
+    extra = [c for c in h if ("pipe_tensor" in c or "tensor_op" in c or "inst_executed_pipe_uniform" in c) and c not in dict(KEYS)]
     names = [r["Kernel Name"].replace("void ", "").split("(")[0][:60] + " grid " + r.get("launch__grid_size", "") for r in recs]
     print("| metric | " + " | ".join(f"launch {i}" for i in range(len(recs))) + " |")
     print("|---|" + "---:|" * len(recs))
     print("| kernel | " + " | ".join(f"`{n}`" for n in names) + " |")
-    for k, label in KEYS:
+    for k, label in KEYS + [(c, c) for c in extra]:
         vals = []
         for r in recs:
             v = r.get(k, "")

@@ -60,12 +60,14 @@ def test_gemm_bf16_cross_terms(cuda, lib, M, N, K):
     Ad, Bd, bias_d = torch.from_numpy(A).to(cuda), torch.from_numpy(Bt).to(cuda), torch.from_numpy(bias).to(cuda)
     Cd = torch.full((M, N), float("nan"), dtype=torch.float32, device=cuda)
     lib.mfm_set_gemm_cross_bf16(1)
+    lib.mfm_set_gemm_h16(0)                     # this test is about the tf32 + bf16-cross kernel (the fallback of the h16 kernel)
     try:
         _lib.check(lib.mfm_gemm_tf32x3(M, N, K, Ad.data_ptr(), K, 1, Bd.data_ptr(), K, 0, bias_d.data_ptr(), 0, Cd.data_ptr(), N,
                                        torch.cuda.current_stream().cuda_stream))
         got = Cd.cpu().numpy()
     finally:
-        lib.mfm_set_gemm_cross_bf16(1)         # the library default
+        lib.mfm_set_gemm_cross_bf16(1)         # the library defaults
+        lib.mfm_set_gemm_h16(1)
     ref = A.astype(np.float64) @ Bt.astype(np.float64).T + bias
     # row-wise scale: the rows of A span two orders of magnitude
     scale = np.maximum(np.abs(ref).max(axis=1, keepdims=True), 1.0)
@@ -177,67 +179,95 @@ def test_gemm_streamk_device_row_count(cuda, lib, rows):
 
 @pytest.mark.parametrize("M,N,K", [(512, 512, 512), (8192, 1600, 1024), (4096 + 77, 1088, 520), (1024, 1024, 1600), (300, 256, 64)])
 def test_gemm_presplit_b_operand(cuda, lib, M, N, K):
-    """B operand's bf16 cross tile pre-split in global memory and loaded by TMA (what the MLP layers do with their weights):
+    """tf32 + bf16-cross kernel (h16 switched off): B operand's bf16 cross tile pre-split in global memory and loaded by TMA:
     the same bits reach the tensor core, so the result is bit-identical to splitting B in the kernel."""
     rng = np.random.default_rng(M + N + K + 1)
     A = rng.standard_normal((M, K)).astype(np.float32)
     Bt = (rng.standard_normal((N, K)) * np.exp(rng.standard_normal((N, 1)))).astype(np.float32)
     bias = rng.standard_normal(N).astype(np.float32)
     Ad, Bd, bias_d = torch.from_numpy(A).to(cuda), torch.from_numpy(Bt).to(cuda), torch.from_numpy(bias).to(cuda)
-    mirror = torch.empty_like(Bd)
+    mirror = torch.empty(N * K + 16, dtype=torch.float32, device=cuda)
     st = torch.cuda.current_stream().cuda_stream
-    _lib.check(lib.mfm_gemm_presplit(Bd.data_ptr(), mirror.data_ptr(), N * K, st))
-    # mirror layout: per 8 floats, 8 bf16 of the values then 8 bf16 of (value - tf32 truncation)
-    mb = mirror.view(torch.bfloat16).view(N, K // 8, 2, 8).float().cpu().numpy()
-    vals = Bt.reshape(N, K // 8, 8)
-    trunc = (vals.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
-    assert np.array_equal(mb[:, :, 0], torch.from_numpy(vals).bfloat16().float().numpy())
-    assert np.array_equal(mb[:, :, 1], torch.from_numpy(vals - trunc).bfloat16().float().numpy())
-    outs = []
-    for use in (0, 1):
-        Cd = torch.full((M, N), float("nan"), dtype=torch.float32, device=cuda)
-        if use:
-            lib.mfm_gemm_register_mirror(Bd.data_ptr(), N * K, mirror.data_ptr())
-        try:
-            _lib.check(lib.mfm_gemm_tf32x3(M, N, K, Ad.data_ptr(), K, 1, Bd.data_ptr(), K, 0, bias_d.data_ptr(), 1, Cd.data_ptr(), N, st))
-            outs.append(Cd.cpu().numpy())
-        finally:
-            lib.mfm_gemm_register_mirror(None, 0, None)
+    lib.mfm_set_gemm_h16(0)
+    try:
+        _lib.check(lib.mfm_gemm_presplit(Bd.data_ptr(), mirror.data_ptr(), N * K, st))
+        # mirror layout: per 8 floats, 8 bf16 of the values then 8 bf16 of (value - tf32 truncation)
+        mb = mirror[:N * K].view(torch.bfloat16).view(N, K // 8, 2, 8).float().cpu().numpy()
+        vals = Bt.reshape(N, K // 8, 8)
+        trunc = (vals.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+        assert np.array_equal(mb[:, :, 0], torch.from_numpy(vals).bfloat16().float().numpy())
+        assert np.array_equal(mb[:, :, 1], torch.from_numpy(vals - trunc).bfloat16().float().numpy())
+        outs = []
+        for use in (0, 1):
+            Cd = torch.full((M, N), float("nan"), dtype=torch.float32, device=cuda)
+            if use:
+                lib.mfm_gemm_register_mirror(Bd.data_ptr(), N * K, mirror.data_ptr())
+            try:
+                _lib.check(lib.mfm_gemm_tf32x3(M, N, K, Ad.data_ptr(), K, 1, Bd.data_ptr(), K, 0, bias_d.data_ptr(), 1, Cd.data_ptr(), N, st))
+                outs.append(Cd.cpu().numpy())
+            finally:
+                lib.mfm_gemm_register_mirror(None, 0, None)
+    finally:
+        lib.mfm_set_gemm_h16(1)
     ref = np.maximum(A.astype(np.float64) @ Bt.astype(np.float64).T + bias, 0)
     assert np.abs(outs[1] - ref).max() <= (3e-6 + 8e-9 * K) * max(np.abs(ref).max(), 1.0)
     assert np.array_equal(outs[0], outs[1])
 
 
-@pytest.mark.skipif(__import__("os").environ.get("MFM_TEST_SPLIT16") != "1",
-                    reason="experimental split16 kernel: written without a GPU run at the end of round 1 (DESIGN.md 9); set MFM_TEST_SPLIT16=1")
-@pytest.mark.parametrize("M,N,K", [(512, 512, 512), (8192, 1024, 1024), (8192, 1600, 1024), (4096 + 77, 1088, 528), (65536, 1024, 1024)])
-def test_gemm_split16(cuda, lib, M, N, K):
-    """Both operands as two bf16 parts, three kind::f16 MMAs per 16 k-values: operand-rounding error ~5e-6 of max |C|."""
+def _h16_split_ref(x, amax):
+    """numpy restatement of the scaled fp16 split (gemm_tcgen05_h16.cuh): s = 2^(14 - floor(log2 amax)), hi = fp16(x s), lo = fp16(x s - hi)"""
+    s = np.float32(2.0) ** np.float32(14 - np.floor(np.log2(np.float32(amax))))
+    xs = (x * s).astype(np.float32)
+    hi = xs.astype(np.float16)
+    return hi, (xs - hi.astype(np.float32)).astype(np.float16), s
+
+
+@pytest.mark.parametrize("M,N,K", [(512, 512, 512), (8192, 1024, 1024), (8192, 1600, 1024), (4096 + 77, 1088, 528), (65536, 1024, 1024),
+                                   (300, 256, 64)])
+@pytest.mark.parametrize("a_scale,b_scale", [(1.0, 1.0), (3e-7, 1.0), (2.5e4, 1e-3)])
+def test_gemm_h16(cuda, lib, M, N, K, a_scale, b_scale):
+    """Default dense-layer kernel: operands scaled per tensor and split into two fp16 parts, three kind::f16 MMAs per 16 k.
+    fp32-level accuracy for O(1) data, for back-propagation-sized (3e-7) and for large (2.5e4) operands alike - the per-tensor
+    power-of-two scale is what makes fp16's 5 exponent bits sufficient - with the weight operand pre-split or split in the
+    kernel, and with the maximum of A tracked by its producer or reduced on the fly."""
     rng = np.random.default_rng(M + N + K + 2)
-    A = rng.standard_normal((M, K)).astype(np.float32)
-    Bt = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
-    bias = rng.standard_normal(N).astype(np.float32)
+    A = (rng.standard_normal((M, K)) * a_scale).astype(np.float32)
+    Bt = (rng.standard_normal((N, K)) / np.sqrt(K) * b_scale).astype(np.float32)
+    bias = (rng.standard_normal(N) * a_scale * b_scale).astype(np.float32)
     Ad, Bd, bias_d = torch.from_numpy(A).to(cuda), torch.from_numpy(Bt).to(cuda), torch.from_numpy(bias).to(cuda)
-    mirror = torch.empty_like(Bd)
+    mirror = torch.empty(N * K + 16, dtype=torch.float32, device=cuda)
     st = torch.cuda.current_stream().cuda_stream
-    lib.mfm_set_gemm_split16(1)
+    ref = np.maximum(A.astype(np.float64) @ Bt.astype(np.float64).T + bias, 0)
+    tol = (1.5e-6 + 6e-9 * K) * np.abs(ref).max()
+    a_amax = torch.zeros(1, dtype=torch.float32, device=cuda)
+    _lib.check(lib.mfm_absmax(Ad.data_ptr(), K, M, K, a_amax.data_ptr(), st))
+    assert a_amax.item() == np.abs(A).max()
+    outs = {}
     try:
-        _lib.check(lib.mfm_gemm_presplit(Bd.data_ptr(), mirror.data_ptr(), N * K, st))
-        mb = mirror.view(torch.bfloat16).view(N, K // 16, 2, 16).float().cpu().numpy()
-        vals = torch.from_numpy(Bt.reshape(N, K // 16, 16))
-        hi = vals.bfloat16().float()
-        assert np.array_equal(mb[:, :, 0], hi.numpy()) and np.array_equal(mb[:, :, 1], (vals - hi).bfloat16().float().numpy())
-        lib.mfm_gemm_register_mirror(Bd.data_ptr(), N * K, mirror.data_ptr())
-        Cd = torch.full((M, N), float("nan"), dtype=torch.float32, device=cuda)
-        _lib.check(lib.mfm_gemm_tf32x3(M, N, K, Ad.data_ptr(), K, 1, Bd.data_ptr(), K, 0, bias_d.data_ptr(), 1, Cd.data_ptr(), N, st))
-        got = Cd.cpu().numpy()
+        for name, use_mirror, use_amax in [("kernel-split B, reduced max", 0, 0), ("mirror, tracked max", 1, 1), ("mirror, reduced max", 1, 0)]:
+            if use_mirror:
+                _lib.check(lib.mfm_gemm_presplit(Bd.data_ptr(), mirror.data_ptr(), N * K, st))
+                if K % 16 == 0 and name.startswith("mirror, tracked"):
+                    hi, lo, s = _h16_split_ref(Bt.reshape(N, K // 16, 16), np.abs(Bt).max())
+                    mb = mirror[:N * K].view(torch.float16).view(N, K // 16, 2, 16).cpu().numpy()
+                    assert np.array_equal(mb[:, :, 0], hi) and np.array_equal(mb[:, :, 1], lo)
+                    assert mirror[N * K].item() == np.abs(Bt).max()
+                lib.mfm_gemm_register_mirror(Bd.data_ptr(), N * K, mirror.data_ptr())
+            Cd = torch.full((M, N), float("nan"), dtype=torch.float32, device=cuda)
+            c_amax = torch.zeros(1, dtype=torch.float32, device=cuda)
+            _lib.check(lib.mfm_gemm_dense(M, N, K, Ad.data_ptr(), K, Bd.data_ptr(), K, bias_d.data_ptr(), 1, Cd.data_ptr(), N,
+                                          a_amax.data_ptr() if use_amax else None, c_amax.data_ptr(), None, None, st))
+            got = Cd.cpu().numpy()
+            lib.mfm_gemm_register_mirror(None, 0, None)
+            assert np.isfinite(got).all(), name
+            assert np.abs(got - ref).max() <= tol, (name, np.abs(got - ref).max(), tol)
+            assert c_amax.item() == got.max(), name          # the producer-side maximum the next layer would consume (relu: max = max |.|)
+            outs[name] = got
     finally:
         lib.mfm_gemm_register_mirror(None, 0, None)
-        lib.mfm_set_gemm_split16(0)
-    ref = np.maximum(A.astype(np.float64) @ Bt.astype(np.float64).T + bias, 0)
-    assert np.isfinite(got).all()
-    assert np.abs(got - ref).max() <= 2e-5 * max(np.abs(ref).max(), 1.0)
-
+    # the same parts reach the tensor core whichever way they were made
+    assert np.array_equal(outs["mirror, tracked max"], outs["mirror, reduced max"])
+    assert np.array_equal(outs["mirror, tracked max"], outs["kernel-split B, reduced max"])
 
 def test_gemm_strided_views(cuda, lib):
     """ld > logical width (writing into a column block of a concatenated buffer)."""
@@ -275,3 +305,52 @@ def test_gemm_backends_agree(cuda, lib):
     e_tc, e_mma = np.abs(outs[0] - ref).max(), np.abs(outs[1] - ref).max()
     scale = np.abs(ref).max()
     assert e_tc < (2e-6 + BIAS_PER_K[0] * K) * scale and e_mma < 2e-6 * scale, (e_tc / scale, e_mma / scale)
+
+
+@pytest.mark.parametrize("M,K,N1,N2", [(512, 512, 512, 256), (8192, 1024, 1024, 1600), (4096 + 77, 528, 1088, 512), (65536, 256, 1024, 1024)])
+@pytest.mark.parametrize("a_scale", [1.0, 2e-6])
+def test_gemm_presplit_handover(cuda, lib, M, K, N1, N2, a_scale):
+    """Two chained dense layers as the MLP runs them: the first epilogue writes its result as fp32 AND as the pre-split
+    (scaled fp16 hi | lo) A operand of the second, scaled by the power of two of its output BOUND
+    max|A| * max_n sum_k |B1[n][k]| + max|b1| (the exact maximum does not exist before the last tile is written); the second
+    layer's TMA loads that copy and nothing is split in shared memory.  Checks the copy bit for bit against a numpy restatement,
+    that the bound really bounds, and both results against float64."""
+    import ctypes
+    rng = np.random.default_rng(M + K + N1)
+    A = (rng.standard_normal((M, K)) * a_scale).astype(np.float32)
+    B1t = (rng.standard_normal((N1, K)) / np.sqrt(K)).astype(np.float32)
+    b1 = (rng.standard_normal(N1) * 0.1 * a_scale).astype(np.float32)
+    B2t = (rng.standard_normal((N2, N1)) / np.sqrt(N1)).astype(np.float32)
+    dev = lambda a: torch.from_numpy(a).to(cuda)
+    Ad, B1d, b1d, B2d = dev(A), dev(B1t), dev(b1), dev(B2t)
+    C1 = torch.full((M, N1), float("nan"), dtype=torch.float32, device=cuda)
+    C1s = torch.zeros((M, N1), dtype=torch.float32, device=cuda)
+    C2 = torch.full((M, N2), float("nan"), dtype=torch.float32, device=cuda)
+    wn = np.float32(np.abs(B1t).sum(axis=1, dtype=np.float32).max())
+    wnorm, bmax = dev(np.array([wn], np.float32)), dev(np.array([np.abs(b1).max()], np.float32))
+    slots = torch.zeros(4, dtype=torch.float32, device=cuda)
+    mirrors = []
+    try:
+        for Bd in (B1d, B2d):         # weight mirrors, as the MLP's layers have them
+            m = torch.empty(Bd.numel() + 16, dtype=torch.float32, device=cuda)
+            _lib.check(lib.mfm_gemm_presplit(Bd.data_ptr(), m.data_ptr(), Bd.numel(), torch.cuda.current_stream().cuda_stream))
+            lib.mfm_gemm_register_mirror(Bd.data_ptr(), Bd.numel(), m.data_ptr())
+            mirrors.append(m)
+        fn = lib.mfm_debug_dense_chain
+        fn.restype = ctypes.c_int
+        fn.argtypes = [ctypes.c_int] * 4 + [ctypes.c_void_p] * 10 + [ctypes.c_void_p]
+        _lib.check(fn(M, K, N1, N2, Ad.data_ptr(), B1d.data_ptr(), b1d.data_ptr(), B2d.data_ptr(), C1.data_ptr(), C1s.data_ptr(), C2.data_ptr(),
+                      wnorm.data_ptr(), bmax.data_ptr(), slots.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        c1, c2, sl = C1.cpu().numpy(), C2.cpu().numpy(), slots.cpu().numpy()
+    finally:
+        lib.mfm_gemm_register_mirror(None, 0, None)
+    ref1 = np.maximum(A.astype(np.float64) @ B1t.astype(np.float64).T + b1, 0)
+    assert np.abs(c1 - ref1).max() <= (1.5e-6 + 6e-9 * K) * np.abs(ref1).max()
+    assert sl[0] == np.abs(A).max() and sl[1] == c1.max()
+    assert sl[2] >= sl[1] and sl[2] <= 1.01 * (np.abs(A).max() * wn + np.abs(b1).max())          # a bound, and the one documented
+    hi, lo, s = _h16_split_ref(c1.reshape(M, N1 // 16, 16), sl[2])
+    got = C1s.view(torch.float16).view(M, N1 // 16, 2, 16).cpu().numpy()
+    assert np.array_equal(got[:, :, 0], hi) and np.array_equal(got[:, :, 1], lo)
+    assert np.isfinite(hi.astype(np.float32)).all()                                             # no overflow, by construction
+    ref2 = c1.astype(np.float64) @ B2t.astype(np.float64).T
+    assert np.abs(c2 - ref2).max() <= (1.5e-6 + 6e-9 * N1) * np.abs(ref2).max()
