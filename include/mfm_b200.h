@@ -11,9 +11,9 @@
  *   - every call enqueues work on `stream` and returns 0 on success or a negative MFM_ERR_* code;
  *     mfm_last_error() returns a description.  Nothing is allocated inside a call: scratch comes
  *     from the caller-provided workspace whose size the matching *_workspace_bytes() reports;
- *   - mfm_ode_* / mfm_flow_mh_step poll a device counter once per Runge-Kutta iteration (the
- *     adaptive step loop is data dependent), i.e. they synchronise `stream`; all other calls are
- *     fully asynchronous.
+ *   - mfm_ode_* / mfm_flow_*_step run a data-dependent loop (adaptive Runge-Kutta).  For small ensembles (n * d <= 4 Mi
+ *     elements; MFM_ODE_GRAPH=0|1 forces either way) the loop is a CUDA-graph WHILE node and the call is asynchronous like all
+ *     others; for large ones the host polls a device counter once per iteration, i.e. the call synchronises `stream`.
  *   - arithmetic type: float32 everywhere; dense contractions emulate fp32 products on the tensor cores (operands split
  *     into two 16-bit parts, three fp16 passes - or 3xTF32 for weight gradients - with fp32 accumulation): fp32-accurate results.
  */
@@ -29,7 +29,8 @@ extern "C" {
 
 typedef struct CUstream_st* mfm_stream_t; /* == cudaStream_t */
 
-enum { MFM_TARGET_GMM = 0, MFM_TARGET_PHI4 = 1, MFM_TARGET_PINES = 2, MFM_TARGET_GAUSS = 3 };
+enum { MFM_TARGET_GMM = 0, MFM_TARGET_PHI4 = 1, MFM_TARGET_PINES = 2, MFM_TARGET_GAUSS = 3, MFM_TARGET_PINES_WHITE = 4 };
+enum { MFM_ACT_RELU = 0, MFM_ACT_TANH = 1, MFM_ACT_ELU = 2, MFM_ACT_GELU = 3, MFM_ACT_SWISH = 4 };
 
 /* Target descriptor: replaces the Python closure `logdensity_fn` that the reference passes to
  * bblackjax.mcmc.mala.init/kernel (mala.py:51-54,86-93) and `dist.loglik/logprior/logprob`
@@ -53,6 +54,10 @@ typedef struct mfm_target {
     const float* kinv_diag; /* [d] diagonal of kinv */
     const float* kinv_split; /* optional: mfm_gemm_presplit mirror of kinv (d*d + 16 floats; constant for the whole run), or NULL */
     float mu, log_norm, poisson_a;
+    /* whitened pines (use_whitened=True, distributions.py:276-297; cox_process_utils.py:118-140): the state is the white noise e,
+     * latents f = L e + mu, loglik = Poisson(f), logprior = -|e|^2/2 + log_norm.  chol = L [d,d] row-major, chol_t = L^T,
+     * chol_sq_t = (L o L)^T (diagonal of the Hessian), mu_vec = mu * 1 [d]; counts / mu / poisson_a / log_norm as above. */
+    const float* chol; const float* chol_t; const float* chol_sq_t; const float* mu_vec;
     /* independent Gaussian (distributions.py:80-97) */
     float gauss_mean, gauss_std;
 } mfm_target_t;
@@ -72,6 +77,9 @@ typedef struct mfm_field {
      * IndepGaussian(dim, mean, var = ref_std^2); stdgauss = (0, 1), widegauss = (0, sqrt(5)).  Used by the conditional
      * FM batch (x0 = mean + std * normal, :156) and by the independent / importance-sampling flow steps (:249-256,283-289). */
     float ref_mean, ref_std;
+    /* activation of the six hidden layers, args.non_linearity (exe_flow_matching.py:40-46, multi_modal.py:181):
+     * MFM_ACT_RELU (0, the default of every configuration), TANH, ELU, GELU (jax.nn.gelu's default tanh approximation), SWISH */
+    int act;
 } mfm_field_t;
 
 typedef struct mfm_ode_opts {
@@ -136,19 +144,29 @@ int mfm_gemm_dense(int M, int N, int K, const float* A, long long lda, const flo
  * contributing pair, number of contributing pairs).  Returns the number of rows; writes at most `cap` of them. */
 int mfm_debug_gemm_plan(int M, int N, int K, int n_pairs, int streamk, int* rows, int cap);
 
-/* ---- RNG: jax.random semantics (threefry2x32, legacy keys, x64 off) ------------------------ */
+/* ---- RNG: jax.random semantics (threefry2x32, legacy keys) ----------------------------------
+ * Draw layout.  0 (default): float32 draws (32 random bits each) - the parity mode `north_star` names.  1: the layout of the
+ * reference AS SHIPPED, which sets jax_enable_x64 (multi_modal.py:14): every uniform / normal draw consumes 64 bits
+ * (random_bits(key, 64, shape): word i of the 2n-word stream is the high half, word n + i the low half), is transformed in
+ * float64 (mantissa fill of 52 bits; sqrt(2) erfinv(uniform(nextafter(-1, 0), 1))) and rounded to float32 once, because this
+ * library computes in float32.  The switch applies to EVERY draw the library makes (mfm_threefry_uniform / _normal, MALA noise
+ * and accept uniforms, the FM batch, Hutchinson probes, flow-MH proposals, resampling); keys and splits are unaffected.
+ * Environment variable MFM_RNG_X64=0|1. */
+void mfm_set_rng_x64(int enable);
+int mfm_rng_x64_enabled(void);
 /* jax.random.split(key, num) -> out uint32[num,2] */
 int mfm_threefry_split(const uint32_t* key, int num, uint32_t* out, mfm_stream_t stream);
 /* vmap(lambda k: split(k, num))(keys[n]) -> out uint32[n,num,2] */
 int mfm_threefry_split_batched(const uint32_t* keys, int n, int num, uint32_t* out, mfm_stream_t stream);
 /* jax.random.bits(key, (n,), uint32) */
 int mfm_threefry_bits(const uint32_t* key, long long n, uint32_t* out, mfm_stream_t stream);
-/* jax.random.uniform(key, (n,), float32, minval, maxval) */
-int mfm_threefry_uniform(const uint32_t* key, long long n, float minval, float maxval, float* out, mfm_stream_t stream);
+/* jax.random.uniform(key, (n,), minval, maxval): the bounds are rounded to float32 for float32 draws (as jax does) and used as
+ * float64 values for float64 draws */
+int mfm_threefry_uniform(const uint32_t* key, long long n, double minval, double maxval, float* out, mfm_stream_t stream);
 /* jax.random.normal(key, (n,), float32) */
 int mfm_threefry_normal(const uint32_t* key, long long n, float* out, mfm_stream_t stream);
 /* vmap(lambda k: uniform(k, (d,), float32, minval, maxval))(keys[n]) -> out [n,d] */
-int mfm_threefry_uniform_batched(const uint32_t* keys, int n, int d, float minval, float maxval, float* out, mfm_stream_t stream);
+int mfm_threefry_uniform_batched(const uint32_t* keys, int n, int d, double minval, double maxval, float* out, mfm_stream_t stream);
 /* vmap(lambda k: normal(k, (d,)))(keys[n]) -> out [n,d] */
 int mfm_threefry_normal_batched(const uint32_t* keys, int n, int d, float* out, mfm_stream_t stream);
 /* host-side threefry split (key management outside the device), same semantics */
@@ -214,6 +232,17 @@ int mfm_flow_mh_step(const mfm_field_t* f, const mfm_target_t* t, const mfm_ode_
                      float* acceptance_rate, uint8_t* is_accepted, float* proposed_position,
                      float* proposed_weight, int* stats, void* ws, size_t ws_bytes, mfm_stream_t stream);
 
+/* conditional_importance_sampling (exe_flow_matching.py:280-296; --num_importance_samples K > 0): per chain the current state is
+ * pulled back (weight exp(l - logq(u) - V)), K fresh reference samples are pushed through the flow with their own probe keys,
+ * and one of the K + 1 candidates is drawn with jax.random.choice(key_choice, K + 1, p = normalised weights).  As coded the
+ * gradient of the state is NOT recomputed (logdensity_grad is left untouched); acceptance_rate = proposed_weight = the chosen
+ * candidate's normalised weight, proposed_position = the chosen sample (the old position when candidate 0 wins). */
+size_t mfm_flow_cis_workspace_bytes(const mfm_field_t* f, const mfm_target_t* t, const mfm_ode_opts_t* o, int n, int n_is);
+int mfm_flow_cis_step(const mfm_field_t* f, const mfm_target_t* t, const mfm_ode_opts_t* o, int n_is, const uint32_t* rng_key,
+                      int per_chain_keys, int n, int chain_offset, int n_total, float* position, float* logdensity,
+                      float* acceptance_rate, uint8_t* is_accepted, float* proposed_position, float* proposed_weight, int* stats,
+                      void* ws, size_t ws_bytes, mfm_stream_t stream);
+
 /* ---- flow-matching update (exe_flow_matching.py:151-179, 362-368, 129-137, 184) ------------- */
 size_t mfm_fm_workspace_bytes(const mfm_field_t* f, const mfm_target_t* t, int n);
 /* loss = sum |v(x_t, t) - (x - x0)|^2 and d loss / d params (flat, same layout as params).
@@ -240,9 +269,10 @@ int mfm_fm_loss_grad_from_batch(const mfm_field_t* f, const mfm_target_t* t, int
 
 /* optax.apply_if_finite(chain(adamw(lr_fn, b1, b2, eps, wd, mask=no-bias), clip(c)), max_err)
  * opt_state: device int32[8] = {adam count, notfinite_count, total_notfinite, last_finite, scratch x4}.
- * decay_mask: uint8[n_params] (1 = kernel, decayed; 0 = bias).  lr_base*(1-count/lr_total_steps). */
+ * decay_mask: uint8[n_params] (1 = kernel, decayed; 0 = bias).  Learning rate (create_learning_rate_fn, :189-198): linear warm-up
+ * 0 -> lr_base over lr_warmup_steps, then linear decay to 0 at lr_total_steps (warm-up 0 = lr_base*(1-count/lr_total_steps)). */
 int mfm_adamw_step(float* params, const float* grads, float* mu, float* nu, const uint8_t* decay_mask,
-                   long long n_params, int* opt_state, float lr_base, int lr_total_steps, float b1, float b2,
+                   long long n_params, int* opt_state, float lr_base, int lr_total_steps, int lr_warmup_steps, float b1, float b2,
                    float eps, float weight_decay, float clip, int max_consecutive_errors, mfm_stream_t stream);
 
 /* ---- adaptive tempering (exe_flow_matching.py:391-402) ---------------------------------------

@@ -26,6 +26,7 @@ class TargetDesc(C.Structure):
         ("phi_a", C.c_float), ("phi_beta", C.c_float),
         ("counts", c_f32p), ("kinv", c_f32p), ("kinv_mu", c_f32p), ("kinv_diag", c_f32p), ("kinv_split", c_f32p),
         ("mu", C.c_float), ("log_norm", C.c_float), ("poisson_a", C.c_float),
+        ("chol", c_f32p), ("chol_t", c_f32p), ("chol_sq_t", c_f32p), ("mu_vec", c_f32p),
         ("gauss_mean", C.c_float), ("gauss_std", C.c_float),
     ]
 
@@ -35,7 +36,7 @@ class FieldDesc(C.Structure):
         ("dim", C.c_int), ("hidden", C.c_int), ("fourier_dim", C.c_int),
         ("params", c_f32p), ("w_off", C.c_longlong * 8), ("b_off", C.c_longlong * 8),
         ("n_params", C.c_longlong), ("omega", c_f32p), ("grad_clip", C.c_float),
-        ("ref_mean", C.c_float), ("ref_std", C.c_float),
+        ("ref_mean", C.c_float), ("ref_std", C.c_float), ("act", C.c_int),
     ]
 
 
@@ -44,7 +45,8 @@ class OdeOpts(C.Structure):
                 ("n_times", C.c_int)]
 
 
-TARGET_GMM, TARGET_PHI4, TARGET_PINES, TARGET_GAUSS = 0, 1, 2, 3
+TARGET_GMM, TARGET_PHI4, TARGET_PINES, TARGET_GAUSS, TARGET_PINES_WHITE = 0, 1, 2, 3, 4
+ACTIVATIONS = {"relu": 0, "tanh": 1, "elu": 2, "gelu": 3, "swish": 4}
 FLOW_RW_MH, FLOW_INDEP_MH = 0, 1
 
 _PT, _FP, _OP = C.POINTER(TargetDesc), C.POINTER(FieldDesc), C.POINTER(OdeOpts)
@@ -79,12 +81,14 @@ SIGNATURES = {
     "mfm_pairwise_workspace_bytes": (C.c_size_t, [C.c_int]),
     "mfm_stein_disc": (C.c_int, [c_f32p, c_f32p, C.c_int, C.c_int, C.c_float, c_f32p, C.c_void_p, C.c_size_t, _S]),
     "mfm_max_mean_disc": (C.c_int, [c_f32p, c_f32p, C.c_int, C.c_int, c_f32p, C.c_void_p, C.c_size_t, _S]),
+    "mfm_set_rng_x64": (None, [C.c_int]),
+    "mfm_rng_x64_enabled": (C.c_int, []),
     "mfm_threefry_split": (C.c_int, [c_u32p, C.c_int, c_u32p, _S]),
     "mfm_threefry_split_batched": (C.c_int, [c_u32p, C.c_int, C.c_int, c_u32p, _S]),
     "mfm_threefry_bits": (C.c_int, [c_u32p, C.c_longlong, c_u32p, _S]),
-    "mfm_threefry_uniform": (C.c_int, [c_u32p, C.c_longlong, C.c_float, C.c_float, c_f32p, _S]),
+    "mfm_threefry_uniform": (C.c_int, [c_u32p, C.c_longlong, C.c_double, C.c_double, c_f32p, _S]),
     "mfm_threefry_normal": (C.c_int, [c_u32p, C.c_longlong, c_f32p, _S]),
-    "mfm_threefry_uniform_batched": (C.c_int, [c_u32p, C.c_int, C.c_int, C.c_float, C.c_float, c_f32p, _S]),
+    "mfm_threefry_uniform_batched": (C.c_int, [c_u32p, C.c_int, C.c_int, C.c_double, C.c_double, c_f32p, _S]),
     "mfm_threefry_normal_batched": (C.c_int, [c_u32p, C.c_int, C.c_int, c_f32p, _S]),
     "mfm_host_threefry_split": (None, [C.POINTER(C.c_uint32), C.c_int, C.POINTER(C.c_uint32)]),
     "mfm_gemm_tf32x3": (C.c_int, [C.c_int, C.c_int, C.c_int, c_f32p, C.c_longlong, C.c_int, c_f32p, C.c_longlong,
@@ -102,6 +106,9 @@ SIGNATURES = {
     "mfm_flow_mh_workspace_bytes": (C.c_size_t, [_FP, _PT, _OP, C.c_int]),
     "mfm_flow_mh_step": (C.c_int, [_FP, _PT, _OP, C.c_int, c_u32p, C.c_int, C.c_int, C.c_int, C.c_int, c_f32p, c_f32p, c_f32p,
                                    c_f32p, c_u8p, c_f32p, c_f32p, c_i32p, C.c_void_p, C.c_size_t, _S]),
+    "mfm_flow_cis_workspace_bytes": (C.c_size_t, [_FP, _PT, _OP, C.c_int, C.c_int]),
+    "mfm_flow_cis_step": (C.c_int, [_FP, _PT, _OP, C.c_int, c_u32p, C.c_int, C.c_int, C.c_int, C.c_int, c_f32p, c_f32p,
+                                    c_f32p, c_u8p, c_f32p, c_f32p, c_i32p, C.c_void_p, C.c_size_t, _S]),
     "mfm_fm_workspace_bytes": (C.c_size_t, [_FP, _PT, C.c_int]),
     "mfm_fm_loss_grad": (C.c_int, [_FP, _PT, c_u32p, C.c_int, C.c_int, C.c_int, C.c_float, c_f32p, c_f32p, c_f32p,
                                    C.c_void_p, C.c_size_t, _S]),
@@ -112,7 +119,7 @@ SIGNATURES = {
     "mfm_fm_loss_grad_from_batch": (C.c_int, [_FP, _PT, C.c_int, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p,
                                               C.c_void_p, C.c_size_t, _S]),
     "mfm_tempering_beta": (C.c_int, [c_f32p, C.c_int, c_f32p, C.c_float, c_f32p, _S]),
-    "mfm_adamw_step": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_u8p, C.c_longlong, c_i32p, C.c_float, C.c_int,
+    "mfm_adamw_step": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_u8p, C.c_longlong, c_i32p, C.c_float, C.c_int, C.c_int,
                                  C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, _S]),
 }
 

@@ -79,21 +79,30 @@ __host__ __device__ __forceinline__ float bits_to_unit_float(uint32_t bits) {
 #endif
 }
 
-// XLA ErfInv (f32): Giles' single-precision polynomial, w = -log1p(-x*x).
+// XLA ErfInv (f32): Giles' single-precision polynomial in w = -log1p(-x*x), restated with XLA CPU's operation order
+// (xla/client/lib/math.cc ErfInv32 + elemental_ir_emitter EmitLog1p; third-party, restated from the published sources - unpinned):
+//   * every multiply and add rounds separately (XLA CPU does not contract to FMA without fast-math): __fmul_rn / __fadd_rn;
+//   * log1p(t) = (-0.5 t + 1) t for |t| < 1e-4, else log(1 + t) with the sum rounded to float32 first;
+//   * the logarithm itself is taken in double and rounded, i.e. correctly rounded logf - XLA's vectorised polynomial is within
+//     an ulp of that; oracle/threefry.py does the same, so device and oracle agree bit for bit.
+__device__ __forceinline__ float xla_log1p_f32(float t) {
+    if (fabsf(t) < 1e-4f) return __fmul_rn(__fadd_rn(__fmul_rn(-0.5f, t), 1.0f), t);
+    return (float)log((double)__fadd_rn(1.0f, t));
+}
 __device__ __forceinline__ float xla_erfinv_f32(float x) {
-    float w = -log1pf(-x * x);
+    float w = -xla_log1p_f32(-__fmul_rn(x, x));
     const bool lt = w < 5.0f;
-    w = lt ? w - 2.5f : sqrtf(w) - 3.0f;
+    w = lt ? __fadd_rn(w, -2.5f) : __fadd_rn(__fsqrt_rn(w), -3.0f);
     float p = lt ? 2.81022636e-08f : -0.000200214257f;
-    p = (lt ? 3.43273939e-07f : 0.000100950558f) + p * w;
-    p = (lt ? -3.5233877e-06f : 0.00134934322f) + p * w;
-    p = (lt ? -4.39150654e-06f : -0.00367342844f) + p * w;
-    p = (lt ? 0.00021858087f : 0.00573950773f) + p * w;
-    p = (lt ? -0.00125372503f : -0.0076224613f) + p * w;
-    p = (lt ? -0.00417768164f : 0.00943887047f) + p * w;
-    p = (lt ? 0.246640727f : 1.00167406f) + p * w;
-    p = (lt ? 1.50140941f : 2.83297682f) + p * w;
-    const float r = p * x;
+    p = __fadd_rn(lt ? 3.43273939e-07f : 0.000100950558f, __fmul_rn(p, w));
+    p = __fadd_rn(lt ? -3.5233877e-06f : 0.00134934322f, __fmul_rn(p, w));
+    p = __fadd_rn(lt ? -4.39150654e-06f : -0.00367342844f, __fmul_rn(p, w));
+    p = __fadd_rn(lt ? 0.00021858087f : 0.00573950773f, __fmul_rn(p, w));
+    p = __fadd_rn(lt ? -0.00125372503f : -0.0076224613f, __fmul_rn(p, w));
+    p = __fadd_rn(lt ? -0.00417768164f : 0.00943887047f, __fmul_rn(p, w));
+    p = __fadd_rn(lt ? 0.246640727f : 1.00167406f, __fmul_rn(p, w));
+    p = __fadd_rn(lt ? 1.50140941f : 2.83297682f, __fmul_rn(p, w));
+    const float r = __fmul_rn(p, x);
     return fabsf(x) == 1.0f ? x * INFINITY : r;
 }
 
@@ -101,8 +110,38 @@ __device__ __forceinline__ float xla_erfinv_f32(float x) {
 // u = max(lo, f*(1-lo)+lo) with lo = nextafter(-1,0); (1-lo) rounds to 2.0f in f32.
 __device__ __forceinline__ float bits_to_normal(uint32_t bits) {
     const float lo = -0.99999994f;
-    float u = fmaxf(lo, bits_to_unit_float(bits) * 2.0f + lo);
-    return 1.41421354f * xla_erfinv_f32(u);
+    float u = fmaxf(lo, __fadd_rn(__fmul_rn(bits_to_unit_float(bits), 2.0f), lo));
+    return __fmul_rn(1.41421354f, xla_erfinv_f32(u));
+}
+
+// ---- jax_enable_x64 (the reference as shipped, multi_modal.py:14): float64 draws ---------------------------------------------
+// random_bits(key, 64, (n,)) generates 2n words in the halves layout and pairs word i (high) with word n + i (low): exactly the
+// two outputs of ONE threefry block (i, n + i).  uniform: mantissa fill of the top 52 bits, minus one.  normal:
+// sqrt(2) erfinv(uniform(nextafter(-1, 0), 1)) in float64 (1 - nextafter(-1, 0) rounds to 2.0).  The library computes in
+// float32, so the draw is rounded once at the end; CUDA's double erfinv and XLA's differ by a few float64 ulps at most,
+// invisible after that rounding except on ties.
+__host__ __device__ __forceinline__ double bits64_to_unit_double(uint32_t hi, uint32_t lo) {
+    const unsigned long long b = ((((unsigned long long)hi << 32) | lo) >> 12) | 0x3FF0000000000000ull;
+#ifdef __CUDA_ARCH__
+    return __longlong_as_double((long long)b) - 1.0;
+#else
+    union { unsigned long long u; double f; } c; c.u = b; return c.f - 1.0;
+#endif
+}
+__device__ __forceinline__ float rng_uniform_at(uint32_t k0, uint32_t k1, uint32_t i, uint32_t n, int x64) {
+    if (!x64) return bits_to_unit_float(threefry_stream_word(k0, k1, i, n));
+    const u32x2 o = threefry2x32(k0, k1, i, n + i);
+    return (float)bits64_to_unit_double(o.a, o.b);
+}
+__device__ __forceinline__ float bits64_to_normal(uint32_t hi, uint32_t lo) {
+    const double lo_ = -0x1.fffffffffffffp-1;
+    const double u = fmax(lo_, bits64_to_unit_double(hi, lo) * 2.0 + lo_);
+    return (float)(0x1.6a09e667f3bcdp+0 * erfinv(u));
+}
+__device__ __forceinline__ float rng_normal_at(uint32_t k0, uint32_t k1, uint32_t i, uint32_t n, int x64) {
+    if (!x64) return bits_to_normal(threefry_stream_word(k0, k1, i, n));
+    const u32x2 o = threefry2x32(k0, k1, i, n + i);
+    return bits64_to_normal(o.a, o.b);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -115,12 +115,12 @@ int dense(int n, int in, int out, const float* A, long long lda, const float* WT
         // C also leaves pre-split for the layer that consumes it (EpiStdS)
         EpiStdS e{C, ldc, bias, mask, ldm, nullptr, 0, relu, mask_div, am.out_split, am.a, am.a2, am.a_bound, am.w_norm, am.bias_amax, am.add_bound, am.out_bound};
         e.alt_amax = am.alt_amax; e.alt_w_norm = am.alt_w_norm; e.alt_bias = am.alt_bias;
-        e.amax_out = am.out;
+        e.amax_out = am.out; e.dact = am.dact; e.lddact = am.lddact; e.mask_mul = am.mask_mul;
         MFM_CUDA_CHECK((launch_gemm<true, false>(p, e, st)));
         return MFM_OK;
     }
     EpiStd e{C, ldc, bias, mask, ldm, nullptr, 0, 1.0f, relu, mask_div};
-    e.amax_out = am.out;
+    e.amax_out = am.out; e.dact = am.dact; e.lddact = am.lddact; e.mask_mul = am.mask_mul;
     MFM_CUDA_CHECK((launch_gemm<true, false>(p, e, st)));
     return MFM_OK;
 }
@@ -291,14 +291,15 @@ __global__ void fourier_kernel(int n, int F, const float* __restrict__ omega, co
 
 // out[i,:] = a[i,:] * (gate[i,:] > 0);  amax (optional): max |out| is folded into the slot (out feeds a scaled-fp16 GEMM)
 __global__ void gate_kernel(long long total, int H, const float* __restrict__ a, const float* __restrict__ gate,
-                            long long ldg, float* __restrict__ out, const int* __restrict__ n_rows_dev, float* __restrict__ amax) {
+                            long long ldg, float* __restrict__ out, const int* __restrict__ n_rows_dev, float* __restrict__ amax, int mul) {
     __shared__ float red[32];
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (n_rows_dev) total = min(total, (long long)(*n_rows_dev) * H);
     float m = 0.0f;
     if (i < total) {
         const long long r = i / H; const int c = (int)(i % H);
-        const float v = gate[r * ldg + c] > 0.0f ? a[i] : 0.0f;
+        const float gv = gate[r * ldg + c];
+        const float v = mul ? a[i] * gv : (gv > 0.0f ? a[i] : 0.0f);      // mul: `gate` holds activation derivatives
         out[i] = v; m = fabsf(v);
     }
     if (amax) amax_publish_block(amax, m, red);
@@ -309,7 +310,7 @@ __global__ void gate_kernel(long long total, int H, const float* __restrict__ a,
 // of `a` bounds the result.
 __global__ void gate4_kernel(long long total4, int H4, const float4* __restrict__ a, const float4* __restrict__ gate,
                              long long ldg4, float4* __restrict__ out, const int* __restrict__ n_rows_dev, float* __restrict__ amax,
-                             float* __restrict__ out_s, const float* __restrict__ scale_src) {
+                             float* __restrict__ out_s, const float* __restrict__ scale_src, int mul) {
     __shared__ float red[32];
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (n_rows_dev) total4 = min(total4, (long long)(*n_rows_dev) * H4);
@@ -317,7 +318,8 @@ __global__ void gate4_kernel(long long total4, int H4, const float4* __restrict_
     if (i < total4) {
         const float4 g = ldg4 == H4 ? __ldg(gate + i) : __ldg(gate + (i / H4) * ldg4 + (i % H4));
         const float4 v = __ldg(a + i);
-        const float4 o = make_float4(g.x > 0.0f ? v.x : 0.0f, g.y > 0.0f ? v.y : 0.0f, g.z > 0.0f ? v.z : 0.0f, g.w > 0.0f ? v.w : 0.0f);
+        const float4 o = mul ? make_float4(v.x * g.x, v.y * g.y, v.z * g.z, v.w * g.w)
+                             : make_float4(g.x > 0.0f ? v.x : 0.0f, g.y > 0.0f ? v.y : 0.0f, g.z > 0.0f ? v.z : 0.0f, g.w > 0.0f ? v.w : 0.0f);
         out[i] = o; m = amax4(0.0f, o);
         if (out_s) {
             const float sc = tc2h::h16_scale(*scale_src);
@@ -335,12 +337,13 @@ __global__ void gate4_kernel(long long total4, int H4, const float4* __restrict_
 
 // exact path: tan[(i,j),:] = W2[j,:] * (h2[i,:] > 0)
 __global__ void basis_tangent_kernel(int n, int d, int H, const float* __restrict__ W2, const float* __restrict__ h2,
-                                     float* __restrict__ tan, const int* __restrict__ n_rows_dev) {
+                                     float* __restrict__ tan, const int* __restrict__ n_rows_dev, int mul) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (n_rows_dev) n = min(n, *n_rows_dev);
     if (i >= (long long)n * d * H) return;
     const int k = (int)(i % H); const long long r = i / H; const int j = (int)(r % d); const long long c = r / d;
-    tan[i] = h2[c * H + k] > 0.0f ? W2[(long long)j * H + k] : 0.0f;
+    const float gv = h2[c * H + k];                                   // the activation (relu) or its derivative (mul)
+    tan[i] = mul ? W2[(long long)j * H + k] * gv : (gv > 0.0f ? W2[(long long)j * H + k] : 0.0f);
 }
 
 // exact path: div_i = sum_j tan6[(i,j),:].W7[:,j] + sum_j gt[i,j]*hdc[i,j];  out = coef * div
@@ -381,10 +384,12 @@ size_t field_bufs_bytes(const mfm_field_t& F, const mfm_target_t& T, int n, bool
     if (hutch) b += ws_slice(N * H, 4) + ws_slice(N * d, 4) + ws_slice(N * gemm_n_tiles((int)d), 4);
     else b += 2 * ws_slice(N * d * H, 4);
     b += ws_slice(N * 2 * F.fourier_dim, 4) + ws_slice(N * H, 4) * 6 + ws_slice(N * 2 * H, 4);      // pre-split copies (ff, h0, h2, h5, h6, ta, tb, cat)
+    if (F.act != MFM_ACT_RELU) b += ws_slice(N * H, 4) * 4 + ws_slice(N * 2 * H, 4);                // activation derivatives
+    if (T.kind == MFM_TARGET_PINES_WHITE) b += 4 * ws_slice(N * d, 4);
     return b + 3 * ws_slice((size_t)F.n_params, 4) + ws_slice(AM_POOL, 4);
 }
 
-bool field_bufs_take(FieldBufs& B, Workspace& w, const mfm_field_t& F, int n, bool hutch) {
+bool field_bufs_take(FieldBufs& B, Workspace& w, const mfm_field_t& F, int n, bool hutch, const mfm_target_t* T) {
     const size_t H = F.hidden, d = F.dim, N = n;
     B.ff = w.take<float>(N * 2 * F.fourier_dim);
     B.h0 = w.take<float>(N * H); B.h2 = w.take<float>(N * H); B.h5 = w.take<float>(N * H); B.h6 = w.take<float>(N * H);
@@ -401,6 +406,13 @@ bool field_bufs_take(FieldBufs& B, Workspace& w, const mfm_field_t& F, int n, bo
     B.h0_s = w.take<float>(N * H); B.h2_s = w.take<float>(N * H); B.h5_s = w.take<float>(N * H); B.h6_s = w.take<float>(N * H);
     B.ta_s = w.take<float>(N * H); B.tb_s = w.take<float>(N * H);
     B.cat_s = w.take<float>(N * 2 * H);
+    B.dh0 = B.dh2 = B.dh5 = B.dh6 = B.dcat = nullptr;
+    if (F.act != MFM_ACT_RELU) {
+        B.dh0 = w.take<float>(N * H); B.dh2 = w.take<float>(N * H); B.dh5 = w.take<float>(N * H); B.dh6 = w.take<float>(N * H);
+        B.dcat = w.take<float>(N * 2 * H);
+    }
+    B.tscratch = nullptr;
+    if (T && T->kind == MFM_TARGET_PINES_WHITE) { B.tscratch = w.take<float>(N * d); w.take<float>(N * d); w.take<float>(N * d); w.take<float>(N * d); }
     return w.ok;
 }
 
@@ -460,29 +472,38 @@ int field_eval(const mfm_field_t& F, const mfm_target_t& T, int n, const float* 
         if (sp) { m.out_split = c_split; m.out_bound = BD(slot_id); m.w_norm = WC(layer); m.bias_amax = has_bias ? BA(layer) : nullptr; }
         return m;
     };
+    // activation (mfm_field_t::act): relu gates by the sign of the stored output; the others store act'(pre-activation) next
+    // to the output (D_) and every later gate multiplies by it (M_)
+    const int act = F.act + 1;                        // functor code: 1 relu, 2 tanh, 3 elu, 4 gelu, 5 swish
+    const bool dmul = F.act != MFM_ACT_RELU;
+    auto D_ = [&](DenseAmax m, float* dbuf, long long ld) { if (dmul) { m.dact = dbuf; m.lddact = ld; } return m; };
+    auto M_ = [&](DenseAmax m) { m.mask_mul = dmul ? 1 : 0; return m; };
+    const float* g_h2 = dmul ? B.dh2 : B.h2; const float* g_cat = dmul ? B.dcat : B.cat;
+    const float* g_h5 = dmul ? B.dh5 : B.h5; const float* g_h6 = dmul ? B.dh6 : B.h6;
     fourier_kernel<<<ceil_div((long long)n * Fd, 256), 256, 0, st>>>(n, Fd, F.omega, tfield, B.ff, nr, sp ? B.ff_s : nullptr, sp ? BD(AM_FF) : nullptr);
     MFM_LAUNCH_CHECK();
     // first layers of the two branches (the exact maxima of h0 and h2 feed the COMMON scale of cat = [s_x | s_t])
-    if ((rc = dense(n, 2 * Fd, H, B.ff, 2 * Fd, WT_(0), 2 * Fd, B_(0), 1, B.h0, H, nullptr, 0, 1, st, nr,
-                    OUT_(IN_(A_(nullptr, nullptr, 1.0f, slot(AM_H0)), B.ff_s, BD(AM_FF)), B.h0_s, AM_H0, 0, true)))) return rc;      // |cos|, |sin| <= 1
-    if ((rc = dense(n, d, H, x, d, WT_(2), d, B_(2), 1, B.h2, H, nullptr, 0, 1, st, nr, OUT_(A_(x_amax, nullptr, 0, slot(AM_H2)), B.h2_s, AM_H2, 2, true)))) return rc;
+    if ((rc = dense(n, 2 * Fd, H, B.ff, 2 * Fd, WT_(0), 2 * Fd, B_(0), act, B.h0, H, nullptr, 0, 1, st, nr,
+                    D_(OUT_(IN_(A_(nullptr, nullptr, 1.0f, slot(AM_H0)), B.ff_s, BD(AM_FF)), B.h0_s, AM_H0, 0, true), B.dh0, H)))) return rc;      // |cos|, |sin| <= 1
+    if ((rc = dense(n, d, H, x, d, WT_(2), d, B_(2), act, B.h2, H, nullptr, 0, 1, st, nr,
+                    D_(OUT_(A_(x_amax, nullptr, 0, slot(AM_H2)), B.h2_s, AM_H2, 2, true), B.dh2, H)))) return rc;
     {   // s_t and s_x: one scale for both halves of cat
         DenseAmax mt = OUT_(IN_(A_(slot(AM_H0), nullptr, 0, slot(AM_ST)), B.h0_s, BD(AM_H0)), B.cat_s + H, AM_ST, 1, true);
         DenseAmax mx = OUT_(IN_(A_(slot(AM_H2), nullptr, 0, slot(AM_SX)), B.h2_s, BD(AM_H2)), B.cat_s, AM_SX, 3, true);
         if (sp) { mt.alt_amax = slot(AM_H2); mt.alt_w_norm = WC(3); mt.alt_bias = BA(3); mx.alt_amax = slot(AM_H0); mx.alt_w_norm = WC(1); mx.alt_bias = BA(1); }
-        if ((rc = dense(n, H, H, B.h0, H, WT_(1), H, B_(1), 1, B.cat + H, 2 * H, nullptr, 0, 1, st, nr, mt))) return rc;       // s_t
-        if ((rc = dense(n, H, H, B.h2, H, WT_(3), H, B_(3), 1, B.cat, 2 * H, nullptr, 0, 1, st, nr, mx))) return rc;           // s_x
+        if ((rc = dense(n, H, H, B.h0, H, WT_(1), H, B_(1), act, B.cat + H, 2 * H, nullptr, 0, 1, st, nr, D_(mt, dmul ? B.dcat + H : nullptr, 2 * H)))) return rc;       // s_t
+        if ((rc = dense(n, H, H, B.h2, H, WT_(3), H, B_(3), act, B.cat, 2 * H, nullptr, 0, 1, st, nr, D_(mx, B.dcat, 2 * H)))) return rc;           // s_x
     }
     if ((rc = dense(n, H, d, B.cat + H, 2 * H, WT_(4), H, B_(4), 0, B.gt, d, nullptr, 0, 1, st, nr, IN_(A_(slot(AM_ST), nullptr, 0, nullptr), B.cat_s + H, BD(AM_ST))))) return rc;       // nn_t
-    if ((rc = dense(n, 2 * H, H, B.cat, 2 * H, WT_(5), 2 * H, B_(5), 1, B.h5, H, nullptr, 0, 1, st, nr,
-                    OUT_(IN_(A_(slot(AM_SX), slot(AM_ST), 0, slot(AM_H5)), B.cat_s, BD(AM_SX)), B.h5_s, AM_H5, 5, true)))) return rc;
-    if ((rc = dense(n, H, H, B.h5, H, WT_(6), H, B_(6), 1, B.h6, H, nullptr, 0, 1, st, nr,
-                    OUT_(IN_(A_(slot(AM_H5), nullptr, 0, slot(AM_H6)), B.h5_s, BD(AM_H5)), B.h6_s, AM_H6, 6, true)))) return rc;
+    if ((rc = dense(n, 2 * H, H, B.cat, 2 * H, WT_(5), 2 * H, B_(5), act, B.h5, H, nullptr, 0, 1, st, nr,
+                    D_(OUT_(IN_(A_(slot(AM_SX), slot(AM_ST), 0, slot(AM_H5)), B.cat_s, BD(AM_SX)), B.h5_s, AM_H5, 5, true), B.dh5, H)))) return rc;
+    if ((rc = dense(n, H, H, B.h5, H, WT_(6), H, B_(6), act, B.h6, H, nullptr, 0, 1, st, nr,
+                    D_(OUT_(IN_(A_(slot(AM_H5), nullptr, 0, slot(AM_H6)), B.h5_s, BD(AM_H5)), B.h6_s, AM_H6, 6, true), B.dh6, H)))) return rc;
     // untempered grad logprob (clipped) and the Hessian term of the divergence
     mfm_target_t T1 = T; T1.beta = 1.0f;
     const bool want_div = out_l != nullptr;
     if ((rc = target_field_terms(T1, n, x, z, B.zkinv, F.grad_clip, B.gc, (want_div && z) ? B.hx : nullptr,
-                                 (want_div && !z) ? B.hx : nullptr, nr, st, x_amax))) return rc;
+                                 (want_div && !z) ? B.hx : nullptr, nr, st, x_amax, B.tscratch))) return rc;
     {
         GemmShape p{n, d, H, B.h6, (long long)H, WT_(7), (long long)H, nr};
         p.a_amax = slot(AM_H6);
@@ -497,19 +518,19 @@ int field_eval(const mfm_field_t& F, const mfm_target_t& T, int n, const float* 
         const bool spt = sp && zw2_amax != nullptr;
         if (H % 4 == 0 && ((reinterpret_cast<uintptr_t>(B.zw2) | reinterpret_cast<uintptr_t>(B.h2) | reinterpret_cast<uintptr_t>(B.ta)) & 15) == 0)
             gate4_kernel<<<ceil_div((long long)n * (H / 4), 256), 256, 0, st>>>((long long)n * (H / 4), H / 4, reinterpret_cast<const float4*>(B.zw2),
-                                                                                reinterpret_cast<const float4*>(B.h2), H / 4, reinterpret_cast<float4*>(B.ta), nr, slot(AM_TA0),
-                                                                                spt ? B.ta_s : nullptr, zw2_amax);
+                                                                                reinterpret_cast<const float4*>(g_h2), H / 4, reinterpret_cast<float4*>(B.ta), nr, slot(AM_TA0),
+                                                                                spt ? B.ta_s : nullptr, zw2_amax, dmul ? 1 : 0);
         else
-            gate_kernel<<<ceil_div((long long)n * H, 256), 256, 0, st>>>((long long)n * H, H, B.zw2, B.h2, H, B.ta, nr, slot(AM_TA0));
+            gate_kernel<<<ceil_div((long long)n * H, 256), 256, 0, st>>>((long long)n * H, H, B.zw2, g_h2, H, B.ta, nr, slot(AM_TA0), dmul ? 1 : 0);
         MFM_LAUNCH_CHECK();
         const bool vec_gate = spt && H % 4 == 0 && ((reinterpret_cast<uintptr_t>(B.zw2) | reinterpret_cast<uintptr_t>(B.h2) | reinterpret_cast<uintptr_t>(B.ta)) & 15) == 0;
         DenseAmax m1 = OUT_(A_(slot(AM_TA0), nullptr, 0, slot(AM_TB0)), B.tb_s, AM_TB0, 3, false);
         if (vec_gate) { m1.a_split = B.ta_s; m1.a_scale_src = zw2_amax; }
-        if ((rc = dense(n, H, H, B.ta, H, WT_(3), H, nullptr, 0, B.tb, H, B.cat, 2 * H, 1, st, nr, m1))) return rc;
-        if ((rc = dense(n, H, H, B.tb, H, WT_(5), 2 * H, nullptr, 0, B.ta, H, B.h5, H, 1, st, nr,
-                        OUT_(IN_(A_(slot(AM_TB0), nullptr, 0, slot(AM_TA1)), B.tb_s, BD(AM_TB0)), B.ta_s, AM_TA1, 5, false)))) return rc;   // first H rows of W5
-        if ((rc = dense(n, H, H, B.ta, H, WT_(6), H, nullptr, 0, B.tb, H, B.h6, H, 1, st, nr,
-                        OUT_(IN_(A_(slot(AM_TA1), nullptr, 0, slot(AM_TB1)), B.ta_s, BD(AM_TA1)), B.tb_s, AM_TB1, 6, false)))) return rc;
+        if ((rc = dense(n, H, H, B.ta, H, WT_(3), H, nullptr, 0, B.tb, H, g_cat, 2 * H, 1, st, nr, M_(m1)))) return rc;
+        if ((rc = dense(n, H, H, B.tb, H, WT_(5), 2 * H, nullptr, 0, B.ta, H, g_h5, H, 1, st, nr,
+                        M_(OUT_(IN_(A_(slot(AM_TB0), nullptr, 0, slot(AM_TA1)), B.tb_s, BD(AM_TB0)), B.ta_s, AM_TA1, 5, false))))) return rc;   // first H rows of W5
+        if ((rc = dense(n, H, H, B.ta, H, WT_(6), H, nullptr, 0, B.tb, H, g_h6, H, 1, st, nr,
+                        M_(OUT_(IN_(A_(slot(AM_TA1), nullptr, 0, slot(AM_TB1)), B.ta_s, BD(AM_TA1)), B.tb_s, AM_TB1, 6, false))))) return rc;
         GemmShape p{n, d, H, B.tb, (long long)H, WT_(7), (long long)H, nr};
         p.a_amax = slot(AM_TB1);
         if (sp) { p.a_split = B.tb_s; p.a_scale_src = BD(AM_TB1); }
@@ -522,12 +543,13 @@ int field_eval(const mfm_field_t& F, const mfm_target_t& T, int n, const float* 
         const long long rows = (long long)n * d;
         if (rows > 0x7FFFFFFFll) { mfm_set_last_error_msg("exact divergence: n*d too large"); return MFM_ERR_UNSUPPORTED; }
         if (nr) { mfm_set_last_error_msg("internal: compaction is not used with the exact divergence"); return MFM_ERR_UNSUPPORTED; }
-        basis_tangent_kernel<<<ceil_div(rows * H, 256), 256, 0, st>>>(n, d, H, W_(2), B.h2, B.tan_a, nullptr);
+        basis_tangent_kernel<<<ceil_div(rows * H, 256), 256, 0, st>>>(n, d, H, W_(2), g_h2, B.tan_a, nullptr, dmul ? 1 : 0);
         MFM_LAUNCH_CHECK();
-        // the basis tangents are entries of W2 or zero: max |parameter| bounds them
-        if ((rc = dense((int)rows, H, H, B.tan_a, H, WT_(3), H, nullptr, 0, B.tan_b, H, B.cat, 2 * H, d, st, nullptr, A_(slot(AM_W), nullptr, 0, slot(AM_TB0))))) return rc;
-        if ((rc = dense((int)rows, H, H, B.tan_b, H, WT_(5), 2 * H, nullptr, 0, B.tan_a, H, B.h5, H, d, st, nullptr, A_(slot(AM_TB0), nullptr, 0, slot(AM_TA1))))) return rc;
-        if ((rc = dense((int)rows, H, H, B.tan_a, H, WT_(6), H, nullptr, 0, B.tan_b, H, B.h6, H, d, st, nullptr, A_(slot(AM_TA1), nullptr, 0, nullptr)))) return rc;
+        // the basis tangents are entries of W2 or zero (relu): max |parameter| bounds them; the other activations' derivatives
+        // reach 1.13 (gelu), so their tangents get an on-the-fly maximum instead
+        if ((rc = dense((int)rows, H, H, B.tan_a, H, WT_(3), H, nullptr, 0, B.tan_b, H, g_cat, 2 * H, d, st, nullptr, M_(A_(dmul ? nullptr : slot(AM_W), nullptr, 0, slot(AM_TB0)))))) return rc;
+        if ((rc = dense((int)rows, H, H, B.tan_b, H, WT_(5), 2 * H, nullptr, 0, B.tan_a, H, g_h5, H, d, st, nullptr, M_(A_(slot(AM_TB0), nullptr, 0, slot(AM_TA1)))))) return rc;
+        if ((rc = dense((int)rows, H, H, B.tan_a, H, WT_(6), H, nullptr, 0, B.tan_b, H, g_h6, H, d, st, nullptr, M_(A_(slot(AM_TA1), nullptr, 0, nullptr))))) return rc;
         exact_trace_kernel<<<ceil_div(n, 8), 256, 0, st>>>(n, d, H, B.tan_b, W_(7), B.gt, B.hx, -sgn, out_l, nullptr, row_map);
         MFM_LAUNCH_CHECK();
     }
@@ -1091,6 +1113,7 @@ struct FlowAcceptArgs {
     const float *xp, *lp, *gp, *Vp, *V0, *logq_up, *logq_u0;
     const uint32_t* kacc;
     float *x, *l, *g, *acc_rate, *prop_pos, *prop_w; uint8_t* is_acc;
+    int x64;
 };
 
 __global__ void flow_accept_kernel(int n, int d, FlowAcceptArgs A) {
@@ -1101,7 +1124,7 @@ __global__ void flow_accept_kernel(int n, int d, FlowAcceptArgs A) {
     if (A.variant == MFM_FLOW_RW_MH) la = A.lp[c] - A.Vp[c] - A.l[c] - A.V0[c];                            // :271-274
     else la = A.lp[c] - A.logq_up[c] - A.Vp[c] + A.logq_u0[c] - A.V0[c] - A.l[c];                         // :253-256
     const float acc_prob = expf(la);
-    const float u = bits_to_unit_float(threefry2x32(A.kacc[2 * c], A.kacc[2 * c + 1], 0u, 0u).a);
+    const float u = rng_uniform_at(A.kacc[2 * c], A.kacc[2 * c + 1], 0u, 1u, A.x64);
     const bool acc = u <= acc_prob;                                                                      // :257,275
     for (int i = lane; i < d; i += 32) {
         const float v = A.xp[(long long)c * d + i];
@@ -1116,6 +1139,82 @@ __global__ void flow_accept_kernel(int n, int d, FlowAcceptArgs A) {
     }
 }
 
+
+// ---- conditional importance sampling (exe_flow_matching.py:280-296) -------------------------------------------------------
+// key_sample, key_hutch_prev, key_hutch, key_choice = split(keys[c], 4); row (c, k) of the K fresh samples uses
+// split(key_sample, K)[k] for the reference draw and split(key_hutch, K)[k] for its Hutchinson probe  (:281,284,286)
+__global__ void cis_keys_kernel(const uint32_t* __restrict__ rng_key, int n, int chain_offset, int n_total, int K,
+                                uint32_t* __restrict__ kprev, uint32_t* __restrict__ kchoice, uint32_t* __restrict__ ksample,
+                                uint32_t* __restrict__ khutch) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= (long long)n * K) return;
+    const int c = (int)(i / K), k = (int)(i % K);
+    u32x2 kc;
+    if (n_total > 0) kc = threefry_split_key(rng_key[0], rng_key[1], (uint32_t)(chain_offset + c), (uint32_t)n_total);
+    else { kc.a = rng_key[2 * c]; kc.b = rng_key[2 * c + 1]; }
+    const u32x2 k_sample = threefry_split_key(kc.a, kc.b, 0u, 4u), k_hutch = threefry_split_key(kc.a, kc.b, 2u, 4u);
+    const u32x2 ks = threefry_split_key(k_sample.a, k_sample.b, (uint32_t)k, (uint32_t)K);
+    const u32x2 kh = threefry_split_key(k_hutch.a, k_hutch.b, (uint32_t)k, (uint32_t)K);
+    ksample[2 * i] = ks.a; ksample[2 * i + 1] = ks.b; khutch[2 * i] = kh.a; khutch[2 * i + 1] = kh.b;
+    if (k == 0) {
+        const u32x2 kp = threefry_split_key(kc.a, kc.b, 1u, 4u), kch = threefry_split_key(kc.a, kc.b, 3u, 4u);
+        kprev[2 * c] = kp.a; kprev[2 * c + 1] = kp.b; kchoice[2 * c] = kch.a; kchoice[2 * c + 1] = kch.b;
+    }
+}
+
+struct CisArgs {
+    int K;
+    const float *ld, *lq, *vol;            // [n*K] log-density, reference log-density and log-det of the fresh samples
+    const float *lq_prev, *vol_prev;       // [n] of the pulled-back current state
+    const float* samples;                  // [n*K, d]
+    const uint32_t* kchoice;               // [n, 2]
+    float* wbuf;                           // [n, K+1] scratch: normalised weights
+    float *x, *l, *acc_rate, *prop_pos, *prop_w; uint8_t* is_acc;
+    int x64;
+};
+// one warp per chain: weights, their normalisation, jax.random.choice(key_choice, K + 1, p = norm_weights) as cumsum ->
+// r = p_cuml[-1] (1 - uniform) -> searchsorted (sequential float32 sums), then the state / info update of :293-296.
+// As coded, an accepted sample keeps the PREVIOUS state's gradient.
+__global__ void cis_select_kernel(int n, int d, CisArgs A) {
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= n) return;
+    const int K = A.K;
+    float* w = A.wbuf + (long long)c * (K + 1);
+    if (lane == 0) w[0] = expf(A.l[c] - A.lq_prev[c] - A.vol_prev[c]);                       // prev_weight (:283)
+    for (int k = lane; k < K; k += 32) { const long long r = (long long)c * K + k; w[1 + k] = expf(A.ld[r] - A.lq[r] - A.vol[r]); }   // (:289)
+    __syncwarp();
+    int choice = 0; float wsel = 0.0f;
+    if (lane == 0) {
+        float wsum = 0.0f;
+        for (int k = 1; k <= K; ++k) wsum += w[k];                                            // weights.sum()
+        const float tot = w[0] + wsum;                                                         // (:290)
+        float cum = 0.0f;
+        for (int k = 0; k <= K; ++k) { w[k] = w[k] / tot; }                                    // norm_weights (:291)
+        float total = 0.0f;
+        for (int k = 0; k <= K; ++k) total += w[k];                                            // p_cuml[-1]
+        const float u = rng_uniform_at(A.kchoice[2 * c], A.kchoice[2 * c + 1], 0u, 1u, A.x64);
+        const float r = total * (1.0f - u);
+        choice = K + 1;
+        for (int k = 0; k <= K; ++k) { cum += w[k]; if (choice > K && cum >= r) choice = k; }   // searchsorted(p_cuml, r), side = left
+        if (choice > K) choice = K;                                                            // jnp indexing clamps
+        wsel = w[choice];
+    }
+    choice = __shfl_sync(0xffffffffu, choice, 0); wsel = __shfl_sync(0xffffffffu, wsel, 0);
+    const float* src = choice > 0 ? A.samples + ((long long)c * K + (choice - 1)) * d : nullptr;
+    for (int i = lane; i < d; i += 32) {
+        const float v = src ? src[i] : A.x[(long long)c * d + i];
+        if (A.prop_pos) A.prop_pos[(long long)c * d + i] = v;                                  // proposed_position: chosen sample or prev position
+        if (src) A.x[(long long)c * d + i] = v;
+    }
+    if (lane == 0) {
+        if (choice > 0) A.l[c] = A.ld[(long long)c * K + (choice - 1)];
+        if (A.acc_rate) A.acc_rate[c] = wsel;
+        if (A.is_acc) A.is_acc[c] = choice > 0 ? 1 : 0;
+        if (A.prop_w) A.prop_w[c] = wsel;
+    }
+}
+
 }  // namespace mfm
 
 // =============================================================================================
@@ -1126,6 +1225,7 @@ static int check_field(const mfm_field_t* f, const mfm_target_t* t, const mfm_od
     if (!f || !t || !o) { mfm_set_last_error_msg("null descriptor"); return MFM_ERR_ARG; }
     if (f->dim != t->dim) { mfm_set_last_error_msg("field.dim != target.dim"); return MFM_ERR_ARG; }
     if (f->hidden <= 0 || f->fourier_dim <= 0 || !f->params || !f->omega) { mfm_set_last_error_msg("bad field descriptor"); return MFM_ERR_ARG; }
+    if (f->act < MFM_ACT_RELU || f->act > MFM_ACT_SWISH) { mfm_set_last_error_msg("unknown activation (mfm_field_t::act)"); return MFM_ERR_ARG; }
     if (!(f->ref_std > 0.0f)) { mfm_set_last_error_msg("field.ref_std must be > 0 (reference distribution IndepGaussian(mean, std^2))"); return MFM_ERR_ARG; }
     return MFM_OK;
 }
@@ -1144,7 +1244,7 @@ int mfm_ode_flow(const mfm_field_t* f, const mfm_target_t* t, const mfm_ode_opts
     Workspace w(ws, ws_bytes);
     OdeState S; FieldBufs B;
     ode_state_take(S, w, n, f->dim, f->hidden);
-    field_bufs_take(B, w, *f, n, o->hutch != 0);
+    field_bufs_take(B, w, *f, n, o->hutch != 0, t);
     float* z = nullptr; float* zc = nullptr;
     if (o->hutch) { z = w.take<float>((size_t)n * f->dim); zc = w.take<float>((size_t)n * f->dim); }
     if (!w.ok) { mfm_set_last_error_msg("workspace too small (mfm_ode_flow)"); return MFM_ERR_WORKSPACE; }
@@ -1166,7 +1266,7 @@ int mfm_field_eval(const mfm_field_t* f, const mfm_target_t* t, const mfm_ode_op
     Workspace w(ws, ws_bytes);
     FieldBufs B;
     const bool hutch = o->hutch != 0;
-    field_bufs_take(B, w, *f, n, hutch);
+    field_bufs_take(B, w, *f, n, hutch, t);
     float* negdiv = w.take<float>(n);
     if (!w.ok) { mfm_set_last_error_msg("workspace too small (mfm_field_eval)"); return MFM_ERR_WORKSPACE; }
     if (hutch && !z) { mfm_set_last_error_msg("z required for hutch"); return MFM_ERR_ARG; }
@@ -1202,7 +1302,7 @@ int mfm_flow_mh_step(const mfm_field_t* f, const mfm_target_t* t, const mfm_ode_
     Workspace w(ws, ws_bytes);
     OdeState S; FieldBufs B;
     ode_state_take(S, w, n, d, f->hidden);
-    field_bufs_take(B, w, *f, n, o->hutch != 0);
+    field_bufs_take(B, w, *f, n, o->hutch != 0, t);
     float* z = w.take<float>(N * D); float* zc = w.take<float>(N * D);
     float* u0 = w.take<float>(N * D); float* up = w.take<float>(N * D); float* xp = w.take<float>(N * D);
     float* gp = w.take<float>(N * D); float* eps = w.take<float>(N * D);
@@ -1243,8 +1343,67 @@ int mfm_flow_mh_step(const mfm_field_t* f, const mfm_target_t* t, const mfm_ode_
     }
     if ((rc = target_value_and_grad(*t, n, xp, lp, gp, nullptr, wt, stream))) return rc;
     FlowAcceptArgs A{variant, xp, lp, gp, Vp, V0, lq_up, lq_u0, kacc, position, logdensity, logdensity_grad,
-                     acceptance_rate, proposed_position, proposed_weight, is_accepted};
+                     acceptance_rate, proposed_position, proposed_weight, is_accepted, rng_x64()};
     flow_accept_kernel<<<ceil_div(n, 8), 256, 0, stream>>>(n, d, A);
+    MFM_LAUNCH_CHECK();
+    return MFM_OK;
+}
+
+size_t mfm_flow_cis_workspace_bytes(const mfm_field_t* f, const mfm_target_t* t, const mfm_ode_opts_t* o, int n, int n_is) {
+    const size_t N = n, D = f->dim, M = (size_t)n * (n_is > 0 ? n_is : 1);
+    return mfm_ode_workspace_bytes(f, t, o, (int)M) + ws_slice(M * D, 4) * 5 + ws_slice(N * D, 4) * 2 + ws_slice(M, 4) * 4 + ws_slice(N, 4) * 3 +
+           ws_slice(M * 2, 4) * 2 + ws_slice(N * 2, 4) * 2 + ws_slice(N * (size_t)(n_is + 1), 4) + target_ws_bytes(*t, (int)M) + 2048;
+}
+
+int mfm_flow_cis_step(const mfm_field_t* f, const mfm_target_t* t, const mfm_ode_opts_t* o, int n_is, const uint32_t* rng_key,
+                      int per_chain_keys, int n, int chain_offset, int n_total, float* position, float* logdensity,
+                      float* acceptance_rate, uint8_t* is_accepted, float* proposed_position, float* proposed_weight, int* stats,
+                      void* ws, size_t ws_bytes, mfm_stream_t stream) {
+    mfm::CrossScope cross_scope;
+    int rc = check_field(f, t, o);
+    if (rc) return rc;
+    if (!rng_key || !position || !logdensity) { mfm_set_last_error_msg("null argument"); return MFM_ERR_ARG; }
+    if (n_is <= 0) { mfm_set_last_error_msg("num_importance_samples must be > 0 for conditional importance sampling"); return MFM_ERR_ARG; }
+    if (n <= 0) return MFM_OK;
+    if ((long long)n * n_is > 0x7FFFFFFFll) { mfm_set_last_error_msg("n * num_importance_samples too large"); return MFM_ERR_UNSUPPORTED; }
+    if (per_chain_keys) { chain_offset = 0; n_total = 0; }
+    else if (n_total < chain_offset + n || chain_offset < 0) { mfm_set_last_error_msg("bad chain_offset/n_total"); return MFM_ERR_ARG; }
+    const int d = f->dim, K = n_is, M = n * K;
+    const size_t N = n, D = d, MM = M;
+    const bool hutch = o->hutch != 0;
+    Workspace w(ws, ws_bytes);
+    OdeState S; FieldBufs B;
+    ode_state_take(S, w, M, d, f->hidden);
+    field_bufs_take(B, w, *f, M, hutch, t);
+    float* z = w.take<float>(MM * D); float* zc = w.take<float>(MM * D);
+    float* refs = w.take<float>(MM * D); float* samples = w.take<float>(MM * D); float* gscr = w.take<float>(MM * D);
+    float* u_prev = w.take<float>(N * D); w.take<float>(N * D);
+    float* vols = w.take<float>(MM); float* ld = w.take<float>(MM); float* lq = w.take<float>(MM); w.take<float>(MM);
+    float* vol_prev = w.take<float>(N); float* lq_prev = w.take<float>(N); w.take<float>(N);
+    uint32_t* ksample = w.take<uint32_t>(MM * 2); uint32_t* khutch = w.take<uint32_t>(MM * 2);
+    uint32_t* kprev = w.take<uint32_t>(N * 2); uint32_t* kchoice = w.take<uint32_t>(N * 2);
+    float* wbuf = w.take<float>(N * (size_t)(K + 1));
+    Workspace wt((char*)ws + w.off, w.off <= ws_bytes ? ws_bytes - w.off : 0);
+    if (!w.ok) { mfm_set_last_error_msg("workspace too small (mfm_flow_cis_step)"); return MFM_ERR_WORKSPACE; }
+    if ((rc = field_prepare_weights(*f, B, stream))) return rc;
+    cis_keys_kernel<<<ceil_div(M, 128), 128, 0, stream>>>(rng_key, n, chain_offset, n_total, K, kprev, kchoice, ksample, khutch);
+    MFM_LAUNCH_CHECK();
+    // pull the current state back: its weight (:282-283)
+    if (hutch && (rc = mfm_threefry_normal_batched(kprev, n, d, z, stream))) return rc;
+    if ((rc = ode_solve(*f, *t, *o, -1, n, hutch ? z : nullptr, position, u_prev, vol_prev, stats, 0, S, B, zc, stream))) return rc;
+    gauss_logprob_kernel<<<ceil_div(n, 8), 256, 0, stream>>>(n, d, u_prev, f->ref_mean, f->ref_std, lq_prev);
+    MFM_LAUNCH_CHECK();
+    // K fresh reference samples per chain, pushed forward with their own probe keys (:284-287)
+    if ((rc = mfm_threefry_normal_batched(ksample, M, d, gscr, stream))) return rc;
+    ref_sample_kernel<<<ceil_div((long long)M * d, 256), 256, 0, stream>>>((long long)M * d, f->ref_mean, f->ref_std, gscr, refs);
+    MFM_LAUNCH_CHECK();
+    if (hutch && (rc = mfm_threefry_normal_batched(khutch, M, d, z, stream))) return rc;
+    if ((rc = ode_solve(*f, *t, *o, +1, M, hutch ? z : nullptr, refs, samples, vols, stats, 1, S, B, zc, stream))) return rc;
+    if ((rc = target_value_and_grad(*t, M, samples, ld, gscr, nullptr, wt, stream))) return rc;      // logprob_beta of the samples (:288)
+    gauss_logprob_kernel<<<ceil_div(M, 8), 256, 0, stream>>>(M, d, refs, f->ref_mean, f->ref_std, lq);
+    MFM_LAUNCH_CHECK();
+    CisArgs A{K, ld, lq, vols, lq_prev, vol_prev, samples, kchoice, wbuf, position, logdensity, acceptance_rate, proposed_position, proposed_weight, is_accepted, rng_x64()};
+    cis_select_kernel<<<ceil_div(n, 8), 256, 0, stream>>>(n, d, A);
     MFM_LAUNCH_CHECK();
     return MFM_OK;
 }

@@ -17,7 +17,7 @@ namespace mfm {
 __global__ void __launch_bounds__(256)
 fm_batch_kernel(const uint32_t* __restrict__ rng_key, int n, int chain_offset, int n_total, int d, float sigma,
                 float ref_mean, float ref_std, const float* __restrict__ x, float* __restrict__ times, float* __restrict__ xt,
-                float* __restrict__ target, float* __restrict__ xt_amax) {
+                float* __restrict__ target, float* __restrict__ xt_amax, int x64) {
     const int lane = threadIdx.x & 31;
     const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= n) return;                                                    // whole warps leave together
@@ -27,7 +27,7 @@ fm_batch_kernel(const uint32_t* __restrict__ rng_key, int n, int chain_offset, i
     const u32x2 k_time = threefry_split_key(rng_key[0], rng_key[1], 0u, 4u);
     const u32x2 k_ref = threefry_split_key(rng_key[0], rng_key[1], 1u, 4u);
     const u32x2 k_gauss = threefry_split_key(rng_key[0], rng_key[1], 2u, 4u);
-    const float t = bits_to_unit_float(threefry_stream_word(k_time.a, k_time.b, gc, (uint32_t)n_total));
+    const float t = rng_uniform_at(k_time.a, k_time.b, gc, (uint32_t)n_total, x64);
     const u32x2 k_row = threefry_split_key(k_ref.a, k_ref.b, gc, (uint32_t)n_total);
     const uint32_t total = (uint32_t)n_total * (uint32_t)d;
     const uint32_t half = ((uint32_t)d + 1u) >> 1;
@@ -35,14 +35,16 @@ fm_batch_kernel(const uint32_t* __restrict__ rng_key, int n, int chain_offset, i
     for (uint32_t b = lane; b < half; b += 32) {
         const uint32_t hi = b + half;
         const bool has_hi = hi < (uint32_t)d;
-        const u32x2 o = threefry2x32(k_row.a, k_row.b, b, has_hi ? hi : 0u);
+        u32x2 o; o.a = o.b = 0u;
+        if (!x64) o = threefry2x32(k_row.a, k_row.b, b, has_hi ? hi : 0u);
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
             if (s == 1 && !has_hi) break;
             const uint32_t j = s == 0 ? b : hi;
             // ref_dist.sample_model: mean + std * normal (distributions.py:96-97); exact identity for stdgauss (0, 1)
-            const float x0 = __fadd_rn(ref_mean, __fmul_rn(ref_std, bits_to_normal(s == 0 ? o.a : o.b)));
-            const float eps = bits_to_normal(threefry_stream_word(k_gauss.a, k_gauss.b, gc * (uint32_t)d + j, total));
+            const float nrm = x64 ? rng_normal_at(k_row.a, k_row.b, j, (uint32_t)d, 1) : bits_to_normal(s == 0 ? o.a : o.b);
+            const float x0 = __fadd_rn(ref_mean, __fmul_rn(ref_std, nrm));
+            const float eps = rng_normal_at(k_gauss.a, k_gauss.b, gc * (uint32_t)d + j, total, x64);
             const long long idx = (long long)c * d + j;
             const float xv = x[idx];
             // sigma*eps + t*x + (1-t)*x0, left to right (:167)
@@ -61,7 +63,7 @@ fm_batch_kernel(const uint32_t* __restrict__ rng_key, int n, int chain_offset, i
 __global__ void __launch_bounds__(256)
 fm_batch_uncond_kernel(const uint32_t* __restrict__ rng_key, int n, int chain_offset, int n_total, int d, float sigma,
                        const float* __restrict__ x, float* __restrict__ times, float* __restrict__ xt, float* __restrict__ target,
-                       float* __restrict__ xt_amax) {
+                       float* __restrict__ xt_amax, int x64) {
     const int lane = threadIdx.x & 31;
     const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= n) return;
@@ -69,12 +71,12 @@ fm_batch_uncond_kernel(const uint32_t* __restrict__ rng_key, int n, int chain_of
     const uint32_t gc = (uint32_t)(chain_offset + c);
     const u32x2 k_time = threefry_split_key(rng_key[0], rng_key[1], 0u, 2u);
     const u32x2 k_ref = threefry_split_key(rng_key[0], rng_key[1], 1u, 2u);
-    const float t = bits_to_unit_float(threefry_stream_word(k_time.a, k_time.b, gc, (uint32_t)n_total));
+    const float t = rng_uniform_at(k_time.a, k_time.b, gc, (uint32_t)n_total, x64);
     const uint32_t total = (uint32_t)n_total * (uint32_t)d;
     const float oms = 1.0f - sigma;
     const float sds = 1.0f - oms * t;                                     // :144
     for (int j = lane; j < d; j += 32) {
-        const float ref = bits_to_normal(threefry_stream_word(k_ref.a, k_ref.b, gc * (uint32_t)d + (uint32_t)j, total));
+        const float ref = rng_normal_at(k_ref.a, k_ref.b, gc * (uint32_t)d + (uint32_t)j, total, x64);
         const long long idx = (long long)c * d + j;
         const float xv = x[idx];
         const float xtv = __fadd_rn(__fmul_rn(t, xv), __fmul_rn(sds, ref));      // :145
@@ -197,12 +199,12 @@ static int dgrad(int n, int in, int out, const float* D, long long ldd, const fl
     if (am.out_split && am.w_norm && am.a) {
         // dX also leaves pre-split for the backward-data layer that consumes it (EpiStdS; the bound uses the kernel's ROW norm)
         EpiStdS e{dX, ldx, nullptr, mask, ldm, add, ldadd, 0, 1, am.out_split, am.a, nullptr, 0.0f, am.w_norm, nullptr, am.add_bound, am.out_bound};
-        e.amax_out = am.out;
+        e.amax_out = am.out; e.mask_mul = am.mask_mul;
         MFM_CUDA_CHECK((launch_gemm<true, false>(p, e, st)));
         return MFM_OK;
     }
     EpiStd e{dX, ldx, nullptr, mask, ldm, add, ldadd, 1.0f, 0};
-    e.amax_out = am.out;
+    e.amax_out = am.out; e.mask_mul = am.mask_mul;
     MFM_CUDA_CHECK((launch_gemm<true, false>(p, e, st)));
     return MFM_OK;
 }
@@ -231,9 +233,9 @@ static size_t fm_bytes(const mfm_field_t& F, const mfm_target_t& T, int n) {
            ws_slice((size_t)COLSUM_SLABS * (H > d ? H : d), 4) + ws_slice(N * H, 4) * 2 + ws_slice(N * 2 * H, 4) + 1024;
 }
 
-static bool fm_take(FmBufs& M, Workspace& w, const mfm_field_t& F, int n) {
+static bool fm_take(FmBufs& M, Workspace& w, const mfm_field_t& F, int n, const mfm_target_t* T) {
     const size_t H = F.hidden, d = F.dim, N = n;
-    field_bufs_take(M.B, w, F, n, true);
+    field_bufs_take(M.B, w, F, n, true, T);
     M.times = w.take<float>(N);
     M.xt = w.take<float>(N * d); M.target = w.take<float>(N * d); M.v = w.take<float>(N * d);
     M.delta = w.take<float>(N * d); M.dgt = w.take<float>(N * d);
@@ -291,24 +293,28 @@ static int fm_forward_backward(const mfm_field_t& F, const mfm_target_t& T, int 
     // (exact max of D, [D pre-split, slot of its scale]) -> exact max of dX [, dX pre-split, slot of its bound, layer, bound of `add`]
     auto G_ = [&](const float* a, const float* a_split, const float* src, float* out, float* c_split, int slot_id, int layer, const float* add_bound) {
         DenseAmax m; m.a = a; m.out = out;
+        m.mask_mul = F.act != MFM_ACT_RELU ? 1 : 0;       // gates are activation derivatives (B.d*) instead of output signs
         if (sp && a_split) { m.a_split = a_split; m.a_scale_src = src; }
         if (sp && c_split) { m.out_split = c_split; m.out_bound = BD(slot_id); m.w_norm = WR(layer); m.add_bound = add_bound; }
         return m;
     };
+    const bool dmul = F.act != MFM_ACT_RELU;
+    const float* g_h0 = dmul ? B.dh0 : B.h0; const float* g_h2 = dmul ? B.dh2 : B.h2; const float* g_cat = dmul ? B.dcat : B.cat;
+    const float* g_h5 = dmul ? B.dh5 : B.h5; const float* g_h6 = dmul ? B.dh6 : B.h6;
     if (part != 2) {
     // layer 7 (nn_xt head): y = h6 W7 + b7
     if ((rc = wgrad(n, H, d, B.h6, H, M.delta, d, GW_(7), sb, sbf, st))) return rc;
     if ((rc = bias_grad(M.delta, d, d, GB_(7)))) return rc;
-    if ((rc = dgrad(n, H, d, M.delta, d, W_(7), M.d6, H, B.h6, H, nullptr, 0, st, G_(slot(AM_DELTA), nullptr, nullptr, slot(AM_D6), M.d6_s, AM_D6, 7, nullptr)))) return rc;
+    if ((rc = dgrad(n, H, d, M.delta, d, W_(7), M.d6, H, g_h6, H, nullptr, 0, st, G_(slot(AM_DELTA), nullptr, nullptr, slot(AM_D6), M.d6_s, AM_D6, 7, nullptr)))) return rc;
     // layer 6
     if ((rc = wgrad(n, H, H, B.h5, H, M.d6, H, GW_(6), sb, sbf, st))) return rc;
     if ((rc = bias_grad(M.d6, H, H, GB_(6)))) return rc;
-    if ((rc = dgrad(n, H, H, M.d6, H, W_(6), M.d5, H, B.h5, H, nullptr, 0, st, G_(slot(AM_D6), M.d6_s, BD(AM_D6), slot(AM_D5), M.d5_s, AM_D5, 6, nullptr)))) return rc;
+    if ((rc = dgrad(n, H, H, M.d6, H, W_(6), M.d5, H, g_h5, H, nullptr, 0, st, G_(slot(AM_D6), M.d6_s, BD(AM_D6), slot(AM_D5), M.d5_s, AM_D5, 6, nullptr)))) return rc;
     // layer 5 (joint, input cat = [s_x | s_t])
     if ((rc = wgrad(n, 2 * H, H, B.cat, 2 * H, M.d5, H, GW_(5), sb, sbf, st))) return rc;
     if ((rc = bias_grad(M.d5, H, H, GB_(5)))) return rc;
     // d s_x = (d5 W5[:H]^T) * relu'(s_x)
-    if ((rc = dgrad(n, H, H, M.d5, H, W_(5), M.dcat, 2 * H, B.cat, 2 * H, nullptr, 0, st, G_(slot(AM_D5), M.d5_s, BD(AM_D5), slot(AM_DCX), M.dcat_s, AM_DCX, 5, nullptr)))) return rc;
+    if ((rc = dgrad(n, H, H, M.d5, H, W_(5), M.dcat, 2 * H, g_cat, 2 * H, nullptr, 0, st, G_(slot(AM_D5), M.d5_s, BD(AM_D5), slot(AM_DCX), M.dcat_s, AM_DCX, 5, nullptr)))) return rc;
     // d s_t (joint part) = d5 W5[H:]^T   (no gate yet; its bound enters the next layer's through `add`)
     if ((rc = dgrad(n, H, H, M.d5, H, W_(5) + (long long)H * H, M.dcat + H, 2 * H, nullptr, 0, nullptr, 0, st,
                     G_(slot(AM_D5), M.d5_s, BD(AM_D5), nullptr, M.dcat_s + H, AM_DCT0, 5, nullptr)))) return rc;
@@ -316,21 +322,21 @@ static int fm_forward_backward(const mfm_field_t& F, const mfm_target_t& T, int 
     if ((rc = wgrad(n, H, d, B.cat + H, 2 * H, M.dgt, d, GW_(4), sb, sbf, st))) return rc;
     if ((rc = bias_grad(M.dgt, d, d, GB_(4)))) return rc;
     // d s_t = (dgt W4^T + joint part) * relu'(s_t)   (in place)
-    if ((rc = dgrad(n, H, d, M.dgt, d, W_(4), M.dcat + H, 2 * H, B.cat + H, 2 * H, M.dcat + H, 2 * H, st,
+    if ((rc = dgrad(n, H, d, M.dgt, d, W_(4), M.dcat + H, 2 * H, g_cat + H, 2 * H, M.dcat + H, 2 * H, st,
                     G_(slot(AM_DGT), nullptr, nullptr, slot(AM_DCT), M.dcat_s + H, AM_DCT, 4, sp ? BD(AM_DCT0) : nullptr)))) return rc;
     }
     if (part == 1) return MFM_OK;
     // layer 3 (x branch)
     if ((rc = wgrad(n, H, H, B.h2, H, M.dcat, 2 * H, GW_(3), sb, sbf, st))) return rc;
     if ((rc = bias_grad(M.dcat, 2 * H, H, GB_(3)))) return rc;
-    if ((rc = dgrad(n, H, H, M.dcat, 2 * H, W_(3), M.d2, H, B.h2, H, nullptr, 0, st, G_(slot(AM_DCX), M.dcat_s, BD(AM_DCX), slot(AM_D2), nullptr, 0, 0, nullptr)))) return rc;
+    if ((rc = dgrad(n, H, H, M.dcat, 2 * H, W_(3), M.d2, H, g_h2, H, nullptr, 0, st, G_(slot(AM_DCX), M.dcat_s, BD(AM_DCX), slot(AM_D2), nullptr, 0, 0, nullptr)))) return rc;
     // layer 2
     if ((rc = wgrad(n, d, H, M.xt, d, M.d2, H, GW_(2), sb, sbf, st))) return rc;
     if ((rc = bias_grad(M.d2, H, H, GB_(2)))) return rc;
     // layer 1 (time branch)
     if ((rc = wgrad(n, H, H, B.h0, H, M.dcat + H, 2 * H, GW_(1), sb, sbf, st))) return rc;
     if ((rc = bias_grad(M.dcat + H, 2 * H, H, GB_(1)))) return rc;
-    if ((rc = dgrad(n, H, H, M.dcat + H, 2 * H, W_(1), M.d0, H, B.h0, H, nullptr, 0, st, G_(slot(AM_DCT), M.dcat_s + H, BD(AM_DCT), slot(AM_D0), nullptr, 0, 0, nullptr)))) return rc;
+    if ((rc = dgrad(n, H, H, M.dcat + H, 2 * H, W_(1), M.d0, H, g_h0, H, nullptr, 0, st, G_(slot(AM_DCT), M.dcat_s + H, BD(AM_DCT), slot(AM_D0), nullptr, 0, 0, nullptr)))) return rc;
     // layer 0
     if ((rc = wgrad(n, 2 * Fd, H, B.ff, 2 * Fd, M.d0, H, GW_(0), sb, sbf, st))) return rc;
     if ((rc = bias_grad(M.d0, H, H, GB_(0)))) return rc;
@@ -363,13 +369,22 @@ __global__ void opt_decide_kernel(int* __restrict__ st, int max_err) {
 __global__ void __launch_bounds__(256)
 adamw_kernel(long long n, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ mu,
              float* __restrict__ nu, const uint8_t* __restrict__ decay, const int* __restrict__ st, float lr_base,
-             int lr_total, float b1, float b2, float eps, float wd, float clip) {
+             int lr_total, int lr_warmup, float b1, float b2, float eps, float wd, float clip) {
     if (st[5] == 0) return;                                // rejected update: params and moments untouched
     const int count = st[0];
     const float c1 = (float)(count + 1);
     const float bc1 = 1.0f - powf(b1, c1), bc2 = 1.0f - powf(b2, c1);
-    int cc = count < 0 ? 0 : (count > lr_total ? lr_total : count);
-    const float lr = lr_base * (1.0f - (float)cc / (float)lr_total);       // linear decay to 0 (:189-198)
+    // join_schedules([linear_schedule(0 -> lr, warmup), linear_schedule(lr -> 0, total - warmup)], [warmup])  (:189-198);
+    // optax.linear_schedule: (init - end) * (1 - clip(count, 0, steps) / steps) + end, the constant init for steps <= 0
+    float lr;
+    if (count < lr_warmup) {
+        const int cc = count < 0 ? 0 : count;
+        lr = (0.0f - lr_base) * (1.0f - (float)cc / (float)lr_warmup) + lr_base;
+    } else {
+        const int steps = lr_total - lr_warmup;
+        int cc = count - lr_warmup; cc = cc < 0 ? 0 : (cc > steps ? steps : cc);
+        lr = steps > 0 ? lr_base * (1.0f - (float)cc / (float)steps) : lr_base;
+    }
     const float omb1 = 1.0f - b1, omb2 = 1.0f - b2;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const float gi = g[i];
@@ -420,15 +435,15 @@ int mfm_fm_loss_grad_part(const mfm_field_t* f, const mfm_target_t* t, const uin
     if (!rng_key || !positions || !loss_out || !grads) { mfm_set_last_error_msg("null argument"); return MFM_ERR_ARG; }
     if (n <= 0) return MFM_OK;
     if (n_total < chain_offset + n || chain_offset < 0) { mfm_set_last_error_msg("bad chain_offset/n_total"); return MFM_ERR_ARG; }
-    if ((long long)n_total * f->dim > 0xFFFFFFFFll) { mfm_set_last_error_msg("n_total*d exceeds the 32-bit counter space"); return MFM_ERR_UNSUPPORTED; }
+    if ((long long)n_total * f->dim * (mfm::rng_x64() ? 2 : 1) > 0xFFFFFFFFll) { mfm_set_last_error_msg("n_total*d exceeds the 32-bit counter space"); return MFM_ERR_UNSUPPORTED; }
     Workspace w(ws, ws_bytes);
     FmBufs M;
-    if (!fm_take(M, w, *f, n)) { mfm_set_last_error_msg("workspace too small (mfm_fm_loss_grad)"); return MFM_ERR_WORKSPACE; }
+    if (!fm_take(M, w, *f, n, t)) { mfm_set_last_error_msg("workspace too small (mfm_fm_loss_grad)"); return MFM_ERR_WORKSPACE; }
     float* xt_amax = mfm::tc2h::gemm_h16() ? M.B.amax + AM_X : nullptr;
     if (part != 2) {
         MFM_CUDA_CHECK(cudaMemsetAsync(M.B.amax + AM_EVAL_END, 0, (AM_POOL - AM_EVAL_END) * sizeof(float), stream));   // this pass's maxima
         fm_batch_kernel<<<ceil_div(n, 8), 256, 0, stream>>>(rng_key, n, chain_offset, n_total, f->dim, sigma, f->ref_mean, f->ref_std,
-                                                             positions, M.times, M.xt, M.target, xt_amax);
+                                                             positions, M.times, M.xt, M.target, xt_amax, rng_x64());
         MFM_LAUNCH_CHECK();
     }
     return fm_forward_backward(*f, *t, n, M, loss_out, grads, stream, part, xt_amax);
@@ -443,14 +458,14 @@ int mfm_fm_loss_grad_uncond(const mfm_field_t* f, const mfm_target_t* t, const u
     if (!rng_key || !positions || !loss_out || !grads) { mfm_set_last_error_msg("null argument"); return MFM_ERR_ARG; }
     if (n <= 0) return MFM_OK;
     if (n_total < chain_offset + n || chain_offset < 0) { mfm_set_last_error_msg("bad chain_offset/n_total"); return MFM_ERR_ARG; }
-    if ((long long)n_total * f->dim > 0xFFFFFFFFll) { mfm_set_last_error_msg("n_total*d exceeds the 32-bit counter space"); return MFM_ERR_UNSUPPORTED; }
+    if ((long long)n_total * f->dim * (mfm::rng_x64() ? 2 : 1) > 0xFFFFFFFFll) { mfm_set_last_error_msg("n_total*d exceeds the 32-bit counter space"); return MFM_ERR_UNSUPPORTED; }
     Workspace w(ws, ws_bytes);
     FmBufs M;
-    if (!fm_take(M, w, *f, n)) { mfm_set_last_error_msg("workspace too small (mfm_fm_loss_grad_uncond)"); return MFM_ERR_WORKSPACE; }
+    if (!fm_take(M, w, *f, n, t)) { mfm_set_last_error_msg("workspace too small (mfm_fm_loss_grad_uncond)"); return MFM_ERR_WORKSPACE; }
     float* xt_amax = mfm::tc2h::gemm_h16() ? M.B.amax + AM_X : nullptr;
     MFM_CUDA_CHECK(cudaMemsetAsync(M.B.amax + AM_EVAL_END, 0, (AM_POOL - AM_EVAL_END) * sizeof(float), stream));
     fm_batch_uncond_kernel<<<ceil_div(n, 8), 256, 0, stream>>>(rng_key, n, chain_offset, n_total, f->dim, sigma, positions,
-                                                                M.times, M.xt, M.target, xt_amax);
+                                                                M.times, M.xt, M.target, xt_amax, rng_x64());
     MFM_LAUNCH_CHECK();
     return fm_forward_backward(*f, *t, n, M, loss_out, grads, stream, 0, xt_amax);
 }
@@ -465,7 +480,7 @@ int mfm_fm_loss_grad_from_batch(const mfm_field_t* f, const mfm_target_t* t, int
     if (n <= 0) return MFM_OK;
     Workspace w(ws, ws_bytes);
     FmBufs M;
-    if (!fm_take(M, w, *f, n)) { mfm_set_last_error_msg("workspace too small (mfm_fm_loss_grad_from_batch)"); return MFM_ERR_WORKSPACE; }
+    if (!fm_take(M, w, *f, n, t)) { mfm_set_last_error_msg("workspace too small (mfm_fm_loss_grad_from_batch)"); return MFM_ERR_WORKSPACE; }
     const size_t nd = (size_t)n * f->dim * sizeof(float);
     MFM_CUDA_CHECK(cudaMemcpyAsync(M.xt, xt, nd, cudaMemcpyDeviceToDevice, stream));
     MFM_CUDA_CHECK(cudaMemcpyAsync(M.target, target_v, nd, cudaMemcpyDeviceToDevice, stream));
@@ -475,9 +490,10 @@ int mfm_fm_loss_grad_from_batch(const mfm_field_t* f, const mfm_target_t* t, int
 }
 
 int mfm_adamw_step(float* params, const float* grads, float* mu, float* nu, const uint8_t* decay_mask, long long n_params,
-                   int* opt_state, float lr_base, int lr_total_steps, float b1, float b2, float eps, float weight_decay,
+                   int* opt_state, float lr_base, int lr_total_steps, int lr_warmup_steps, float b1, float b2, float eps, float weight_decay,
                    float clip, int max_consecutive_errors, mfm_stream_t stream) {
-    if (!params || !grads || !mu || !nu || !decay_mask || !opt_state || n_params <= 0 || lr_total_steps <= 0) {
+    if (!params || !grads || !mu || !nu || !decay_mask || !opt_state || n_params <= 0 || lr_total_steps <= 0 || lr_warmup_steps < 0 ||
+        lr_warmup_steps > lr_total_steps) {
         mfm_set_last_error_msg("bad argument (mfm_adamw_step)"); return MFM_ERR_ARG;
     }
     MFM_CUDA_CHECK(cudaMemsetAsync(opt_state + 4, 0, 2 * sizeof(int), stream));
@@ -487,7 +503,7 @@ int mfm_adamw_step(float* params, const float* grads, float* mu, float* nu, cons
     opt_decide_kernel<<<1, 32, 0, stream>>>(opt_state, max_consecutive_errors);
     MFM_LAUNCH_CHECK();
     adamw_kernel<<<blocks, 256, 0, stream>>>(n_params, params, grads, mu, nu, decay_mask, opt_state, lr_base,
-                                             lr_total_steps, b1, b2, eps, weight_decay, clip);
+                                             lr_total_steps, lr_warmup_steps, b1, b2, eps, weight_decay, clip);
     MFM_LAUNCH_CHECK();
     opt_advance_kernel<<<1, 32, 0, stream>>>(opt_state);
     MFM_LAUNCH_CHECK();

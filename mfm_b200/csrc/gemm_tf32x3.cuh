@@ -273,7 +273,28 @@ __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast
 __device__ __forceinline__ void st4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ float4 f4(float v) { return make_float4(v, v, v, v); }
 
-// ---- standard epilogue: C = mask(relu(alpha*acc + bias) ) (+ add) ----------------------------
+// ---- activations (exe_flow_matching.py:40-46 `non_lins`: jax.nn.tanh / elu / relu / gelu / swish) --------------------------
+// code: 0 none, 1 relu, 2 tanh, 3 elu (alpha = 1), 4 gelu (jax.nn.gelu default: tanh approximation), 5 swish (x sigmoid(x)).
+// Returns act(v) and its derivative at v (the backward pass and the forward-mode tangents multiply by it; relu keeps the
+// cheaper sign-of-the-output gate: relu'(0) = 0 as in jax.nn.relu's custom JVP).
+enum { ACT_NONE = 0, ACT_RELU = 1, ACT_TANH = 2, ACT_ELU = 3, ACT_GELU = 4, ACT_SWISH = 5 };
+__device__ __forceinline__ float act_fwd(int act, float v, float& dv) {
+    switch (act) {
+        case ACT_RELU: dv = v > 0.0f ? 1.0f : 0.0f; return fmaxf(v, 0.0f);
+        case ACT_TANH: { const float t = tanhf(v); dv = 1.0f - t * t; return t; }
+        case ACT_ELU: { const float e = expm1f(v); dv = v > 0.0f ? 1.0f : e + 1.0f; return v > 0.0f ? v : e; }
+        case ACT_GELU: {
+            const float c = 0.7978845608028654f, a = 0.044715f;
+            const float u = c * (v + a * v * v * v), t = tanhf(u);
+            dv = 0.5f * (1.0f + t) + 0.5f * v * (1.0f - t * t) * c * (1.0f + 3.0f * a * v * v);
+            return 0.5f * v * (1.0f + t);
+        }
+        case ACT_SWISH: { const float sg = 1.0f / (1.0f + expf(-v)); dv = sg + v * sg * (1.0f - sg); return v * sg; }
+        default: dv = 1.0f; return v;
+    }
+}
+
+// ---- standard epilogue: C = mask(act(alpha*acc + bias) ) (+ add) -----------------------------
 struct EpiStd {
     static constexpr bool kRowSum = false;
     float* C; long long ldc;
@@ -285,6 +306,8 @@ struct EpiStd {
     long long c_zstride = 0;           // split-K: slice z writes to C + z*c_zstride
     float* amax_out = nullptr;         // optional device slot: max |C| (C is the A operand of a later h16 GEMM)
     mutable float vmax = 0.0f;         // per-thread running maximum of what this copy of the functor stored
+    float* dact = nullptr; long long lddact = 0;   // optional: act'(pre-activation) is written here (activations other than relu)
+    int mask_mul = 0;                  // 1: out *= mask (the mask operand holds activation derivatives) instead of the > 0 gate
     __device__ __forceinline__ void at_z(int z) { C += (long long)z * c_zstride; }
     struct Aux { float bias, add, mask; };
     __device__ __forceinline__ Aux load(int row, int col) const {
@@ -296,8 +319,9 @@ struct EpiStd {
     }
     __device__ __forceinline__ float apply(int row, int col, float acc, const Aux& a) const {
         float v = alpha * acc + a.bias + a.add;
-        if (relu) v = fmaxf(v, 0.0f);
-        v = a.mask > 0.0f ? v : 0.0f;
+        if (relu == ACT_RELU) v = fmaxf(v, 0.0f);
+        else if (relu) { float dv; v = act_fwd(relu, v, dv); if (dact) dact[(long long)row * lddact + col] = dv; }
+        v = mask_mul ? v * a.mask : (a.mask > 0.0f ? v : 0.0f);
         C[(long long)row * ldc + col] = v;
         vmax = fmaxf(vmax, fabsf(v));
         return 0.0f;
@@ -322,9 +346,17 @@ struct EpiStd {
         float4 v;
         v.x = alpha * acc.x + c.bias.x + r.add.x; v.y = alpha * acc.y + c.bias.y + r.add.y;
         v.z = alpha * acc.z + c.bias.z + r.add.z; v.w = alpha * acc.w + c.bias.w + r.add.w;
-        if (relu) { v.x = fmaxf(v.x, 0.0f); v.y = fmaxf(v.y, 0.0f); v.z = fmaxf(v.z, 0.0f); v.w = fmaxf(v.w, 0.0f); }
-        v.x = r.mask.x > 0.0f ? v.x : 0.0f; v.y = r.mask.y > 0.0f ? v.y : 0.0f;
-        v.z = r.mask.z > 0.0f ? v.z : 0.0f; v.w = r.mask.w > 0.0f ? v.w : 0.0f;
+        if (relu == ACT_RELU) { v.x = fmaxf(v.x, 0.0f); v.y = fmaxf(v.y, 0.0f); v.z = fmaxf(v.z, 0.0f); v.w = fmaxf(v.w, 0.0f); }
+        else if (relu) {
+            float4 dv;
+            v.x = act_fwd(relu, v.x, dv.x); v.y = act_fwd(relu, v.y, dv.y); v.z = act_fwd(relu, v.z, dv.z); v.w = act_fwd(relu, v.w, dv.w);
+            if (dact) st4(dact + (long long)row * lddact + col, dv);
+        }
+        if (mask_mul) { v.x *= r.mask.x; v.y *= r.mask.y; v.z *= r.mask.z; v.w *= r.mask.w; }
+        else {
+            v.x = r.mask.x > 0.0f ? v.x : 0.0f; v.y = r.mask.y > 0.0f ? v.y : 0.0f;
+            v.z = r.mask.z > 0.0f ? v.z : 0.0f; v.w = r.mask.w > 0.0f ? v.w : 0.0f;
+        }
         st4(C + (long long)row * ldc + col, v);
         vmax = amax4(vmax, v);
         return 0.0f;
@@ -383,6 +415,8 @@ struct EpiStdS {
     const float* alt_amax = nullptr; const float* alt_w_norm = nullptr; const float* alt_bias = nullptr;
     float* amax_out = nullptr;         // device or null: exact max |C|
     mutable float vmax = 0.0f;
+    float* dact = nullptr; long long lddact = 0;   // as EpiStd: activation derivative output / multiplicative mask
+    int mask_mul = 0;
     __device__ __forceinline__ void at_z(int) {}
     __device__ __forceinline__ float out_bound() const {
         float a = in_bound;
@@ -405,8 +439,9 @@ struct EpiStdS {
     }
     __device__ __forceinline__ float apply(int row, int col, float acc, const Aux& a) const {
         float v = acc + a.bias + a.add;
-        if (relu) v = fmaxf(v, 0.0f);
-        v = a.mask > 0.0f ? v : 0.0f;
+        if (relu == ACT_RELU) v = fmaxf(v, 0.0f);
+        else if (relu) { float dv; v = act_fwd(relu, v, dv); if (dact) dact[(long long)row * lddact + col] = dv; }
+        v = mask_mul ? v * a.mask : (a.mask > 0.0f ? v : 0.0f);
         C[(long long)row * ldc + col] = v;
         vmax = fmaxf(vmax, fabsf(v));
         const float x = v * a.scale;
@@ -434,9 +469,17 @@ struct EpiStdS {
         float4 v;
         v.x = acc.x + c.bias.x + r.add.x; v.y = acc.y + c.bias.y + r.add.y;
         v.z = acc.z + c.bias.z + r.add.z; v.w = acc.w + c.bias.w + r.add.w;
-        if (relu) { v.x = fmaxf(v.x, 0.0f); v.y = fmaxf(v.y, 0.0f); v.z = fmaxf(v.z, 0.0f); v.w = fmaxf(v.w, 0.0f); }
-        v.x = r.mask.x > 0.0f ? v.x : 0.0f; v.y = r.mask.y > 0.0f ? v.y : 0.0f;
-        v.z = r.mask.z > 0.0f ? v.z : 0.0f; v.w = r.mask.w > 0.0f ? v.w : 0.0f;
+        if (relu == ACT_RELU) { v.x = fmaxf(v.x, 0.0f); v.y = fmaxf(v.y, 0.0f); v.z = fmaxf(v.z, 0.0f); v.w = fmaxf(v.w, 0.0f); }
+        else if (relu) {
+            float4 dv;
+            v.x = act_fwd(relu, v.x, dv.x); v.y = act_fwd(relu, v.y, dv.y); v.z = act_fwd(relu, v.z, dv.z); v.w = act_fwd(relu, v.w, dv.w);
+            if (dact) st4(dact + (long long)row * lddact + col, dv);
+        }
+        if (mask_mul) { v.x *= r.mask.x; v.y *= r.mask.y; v.z *= r.mask.z; v.w *= r.mask.w; }
+        else {
+            v.x = r.mask.x > 0.0f ? v.x : 0.0f; v.y = r.mask.y > 0.0f ? v.y : 0.0f;
+            v.z = r.mask.z > 0.0f ? v.z : 0.0f; v.w = r.mask.w > 0.0f ? v.w : 0.0f;
+        }
         st4(C + (long long)row * ldc + col, v);
         vmax = amax4(vmax, v);
         // columns col..col+3 of the 16-group: hi parts at byte 2 (col % 16), lo parts 32 bytes further

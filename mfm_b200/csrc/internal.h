@@ -39,7 +39,8 @@ int target_value_and_grad(const mfm_target_t& T, int n, const float* x, float* l
 // vector field; for pines hv excludes the constant -zK^-1 part when zkinv is supplied.
 // outputs: gc = clip(grad), hvc = 1[|grad|<clip] * (H z), hdc = 1[|grad|<clip] * diag(H)  (hvc/hdc optional)
 int target_field_terms(const mfm_target_t& T, int n, const float* x, const float* z, const float* zkinv, float clip,
-                       float* gc, float* hvc, float* hdc, const int* n_rows_dev, cudaStream_t st, const float* x_amax = nullptr);
+                       float* gc, float* hvc, float* hdc, const int* n_rows_dev, cudaStream_t st, const float* x_amax = nullptr,
+                       float* scratch = nullptr);
 
 // ---- vector field (flow.cu) -------------------------------------------------------------------
 // Slots of the per-workspace pool of tensor maxima (FieldBufs::amax, 64 floats): max |value| of every tensor that is the A
@@ -66,6 +67,10 @@ struct FieldBufs {
     // pre-split (split16, scaled fp16) copies written next to the fp32 tensors by their producers: the A operands of the
     // layers that consume them (null: the scaled-fp16 GEMM is off or the sizes are not multiples of 16)
     float *ff_s, *h0_s, *cat_s, *h2_s, *h5_s, *h6_s, *ta_s, *tb_s;
+    // activation derivatives at the pre-activations of h0, h2, cat = [s_x | s_t], h5, h6 (activations other than relu, whose
+    // derivative is read off the sign of the output): what the backward pass and the tangents multiply by
+    float *dh0, *dh2, *dcat, *dh5, *dh6;
+    float* tscratch;        // 4 x [n, d]: the whitened pines target's field terms (four GEMMs against the Cholesky factor)
 };
 namespace tc2p {
 void register_cross(const float* base, size_t n_floats, const float* mirror);
@@ -80,6 +85,7 @@ float* amax_scratch_for(cudaStream_t st);
 int split_groups();
 }
 int gemm_backend();
+int rng_x64();             // 1: float64-layout draws (jax_enable_x64), rounded to float32 (rng.cu)
 // dst mirrors src.  h16 kernel (default): groups of 16 floats -> 16 hi | 16 lo fp16 parts of the values scaled by
 // h16_scale(*amax); tf32 + bf16-cross kernel: groups of 8 floats -> 8 bf16 of the values | 8 bf16 of their tf32 truncation rests
 int presplit_weights(const float* src, float* dst, long long n_floats, const float* amax, cudaStream_t st);
@@ -93,13 +99,16 @@ struct DenseAmax {
     float* out_split = nullptr; float* out_bound = nullptr;                        // write C pre-split too; slot receiving its bound
     const float* w_norm = nullptr; const float* bias_amax = nullptr; const float* add_bound = nullptr;   // ingredients of that bound
     const float* alt_amax = nullptr; const float* alt_w_norm = nullptr; const float* alt_bias = nullptr; // a sibling layer sharing C's scale
+    float* dact = nullptr; long long lddact = 0;    // receives act'(pre-activation) (activations other than relu)
+    int mask_mul = 0;                               // the mask operand holds derivatives: multiply instead of the > 0 gate
 };
 size_t field_bufs_bytes(const mfm_field_t& F, const mfm_target_t& T, int n, bool hutch);
-bool field_bufs_take(FieldBufs& B, Workspace& w, const mfm_field_t& F, int n, bool hutch);
+bool field_bufs_take(FieldBufs& B, Workspace& w, const mfm_field_t& F, int n, bool hutch, const mfm_target_t* T = nullptr);
 // B.wt <- transposes of the eight dense kernels (once per ABI call: the parameters may have changed)
 int field_prepare_weights(const mfm_field_t& F, FieldBufs& B, cudaStream_t st);
 void field_register_mirrors(const mfm_field_t& F, const FieldBufs& B);
-// C[n,out] = relu?(A[n,in] W[in,out] + bias) gated by mask (relu' of another activation).
+// C[n,out] = act(A[n,in] W[in,out] + bias) gated by mask (relu' of another activation); `relu` = activation code of gemm_tf32x3.cuh
+// (0 none, 1 relu, 2 tanh, 3 elu, 4 gelu, 5 swish).
 // WT = the kernel transposed, WT[o*ldwt + i]: both GEMM operands are K-major, which is what the
 // persistent tcgen05 kernel's bf16 cross-term path needs.
 int dense(int n, int in, int out, const float* A, long long lda, const float* WT, long long ldwt, const float* bias, int relu,

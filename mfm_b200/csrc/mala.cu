@@ -28,30 +28,37 @@ __device__ __forceinline__ ChainKeys derive_chain_keys(const uint32_t* rng_key, 
 }
 
 // uniform(key, ()) : one-element stream, padded -> block (0,0), word o0
-__device__ __forceinline__ float scalar_uniform(u32x2 key) {
-    return bits_to_unit_float(threefry2x32(key.a, key.b, 0u, 0u).a);
+__device__ __forceinline__ float scalar_uniform(u32x2 key, int x64) {
+    return rng_uniform_at(key.a, key.b, 0u, 1u, x64);      // float32: block (0,0) word o0; float64 draws: block (0,1), both words
 }
 
 // Writes the proposal into xs (smem) and returns sum((x' - x - h g)^2) (warp-reduced).
 __device__ __forceinline__ float langevin_propose(u32x2 key, int d, float h, float sq2h, const float* __restrict__ x,
-                                                  const float* __restrict__ g, float* xs, int lane) {
+                                                  const float* __restrict__ g, float* xs, int lane, int x64) {
     const uint32_t half = ((uint32_t)d + 1u) >> 1;
     float sq = 0.0f;
     for (uint32_t b = lane; b < half; b += 32) {
         const uint32_t hi = b + half;
         const bool has_hi = hi < (uint32_t)d;
-        const u32x2 o = threefry2x32(key.a, key.b, b, has_hi ? hi : 0u);
+        float n_lo, n_hi = 0.0f;
+        if (x64) {          // float64 draws: element e is block (e, d + e)
+            n_lo = rng_normal_at(key.a, key.b, b, (uint32_t)d, 1);
+            if (has_hi) n_hi = rng_normal_at(key.a, key.b, hi, (uint32_t)d, 1);
+        } else {
+            const u32x2 o = threefry2x32(key.a, key.b, b, has_hi ? hi : 0u);
+            n_lo = bits_to_normal(o.a); n_hi = bits_to_normal(o.b);
+        }
         {
             const float xv = x[b], gv = g[b];
             // p + step_size*g + sqrt(2 step_size)*n, left to right as diffusions.py:25-30
-            const float xn = __fadd_rn(__fadd_rn(xv, __fmul_rn(h, gv)), __fmul_rn(sq2h, bits_to_normal(o.a)));
+            const float xn = __fadd_rn(__fadd_rn(xv, __fmul_rn(h, gv)), __fmul_rn(sq2h, n_lo));
             xs[b] = xn;
             const float th = __fadd_rn(__fadd_rn(xn, -xv), -__fmul_rn(h, gv));
             sq += th * th;
         }
         if (has_hi) {
             const float xv = x[hi], gv = g[hi];
-            const float xn = __fadd_rn(__fadd_rn(xv, __fmul_rn(h, gv)), __fmul_rn(sq2h, bits_to_normal(o.b)));
+            const float xn = __fadd_rn(__fadd_rn(xv, __fmul_rn(h, gv)), __fmul_rn(sq2h, n_hi));
             xs[hi] = xn;
             const float th = __fadd_rn(__fadd_rn(xn, -xv), -__fmul_rn(h, gv));
             sq += th * th;
@@ -101,7 +108,7 @@ __device__ __forceinline__ void mala_accept_select(const MalaIO& io, int c, int 
 
 __global__ void __launch_bounds__(MALA_WARPS * 32)
 mala_small_kernel(mfm_target_t T, const uint32_t* __restrict__ rng_key, int n, int chain_offset, int n_total, float h,
-                  float sq2h, float quarter, MalaIO io) {
+                  float sq2h, float quarter, MalaIO io, int x64) {
     extern __shared__ float sm[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int c = blockIdx.x * MALA_WARPS + w;
@@ -110,12 +117,12 @@ mala_small_kernel(mfm_target_t T, const uint32_t* __restrict__ rng_key, int n, i
     float* xs = sm + w * 2 * d;
     float* gs = xs + d;
     const ChainKeys ck = derive_chain_keys(rng_key, chain_offset + c, n_total);
-    const float sq_new = langevin_propose(ck.integrator, d, h, sq2h, io.x + (long long)c * d, io.g + (long long)c * d, xs, lane);
+    const float sq_new = langevin_propose(ck.integrator, d, h, sq2h, io.x + (long long)c * d, io.g + (long long)c * d, xs, lane, x64);
     __syncwarp();
     const float ll = small_target_loglik_grad(T, xs, gs, lane);
     __syncwarp();
     const float l_new = T.beta * ll;
-    const float u = scalar_uniform(ck.rmh);
+    const float u = scalar_uniform(ck.rmh, x64);
     mala_accept_select(io, c, d, h, quarter, u, io.l[c], sq_new, l_new, xs, gs, T.beta, lane);
 }
 
@@ -124,14 +131,14 @@ __global__ void __launch_bounds__(256)
 pines_propose_kernel(mfm_target_t T, const uint32_t* __restrict__ rng_key, int n, int chain_offset, int n_total,
                      float h, float sq2h, const float* __restrict__ x, const float* __restrict__ g,
                      float* __restrict__ xprop, float* __restrict__ lik, float* __restrict__ sq_new_out,
-                     float* __restrict__ u_out, float* __restrict__ xprop_amax) {
+                     float* __restrict__ u_out, float* __restrict__ xprop_amax, int x64) {
     const int lane = threadIdx.x & 31;
     const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= n) return;
     const int d = T.dim;
     const ChainKeys ck = derive_chain_keys(rng_key, chain_offset + c, n_total);
     float* xp = xprop + (long long)c * d;
-    const float sq = langevin_propose(ck.integrator, d, h, sq2h, x + (long long)c * d, g + (long long)c * d, xp, lane);
+    const float sq = langevin_propose(ck.integrator, d, h, sq2h, x + (long long)c * d, g + (long long)c * d, xp, lane, x64);
     __syncwarp();
     float s = 0.0f, vm = 0.0f;
     for (int i = lane; i < d; i += 32) {
@@ -140,8 +147,19 @@ pines_propose_kernel(mfm_target_t T, const uint32_t* __restrict__ rng_key, int n
         vm = fmaxf(vm, fabsf(xv));
     }
     s = warp_sum(s);
-    if (lane == 0) { lik[c] = s; sq_new_out[c] = sq; u_out[c] = scalar_uniform(ck.rmh); }
+    if (lane == 0) { lik[c] = s; sq_new_out[c] = sq; u_out[c] = scalar_uniform(ck.rmh, x64); }
     if (xprop_amax) amax_publish_warp(xprop_amax, vm);      // the proposal is the A operand of the K^-1 GEMM (scaled-fp16 split)
+}
+
+// whitened pines: the proposal's log-density and gradient come from target_value_and_grad (two GEMMs against the Cholesky factor)
+__global__ void __launch_bounds__(256)
+white_mala_finalize_kernel(int n, int d, float h, float quarter, const float* __restrict__ xprop, const float* __restrict__ gnew,
+                           const float* __restrict__ lnew, const float* __restrict__ sq_new, const float* __restrict__ u, MalaIO io) {
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= n) return;
+    MalaIO io2 = io; io2.prop_pos = nullptr;    // x' already lives in prop_pos (written by propose)
+    mala_accept_select(io2, c, d, h, quarter, u[c], io.l[c], sq_new[c], lnew[c], xprop + (long long)c * d, gnew + (long long)c * d, 1.0f, lane);
 }
 
 __global__ void __launch_bounds__(256)
@@ -166,6 +184,8 @@ extern "C" {
 
 size_t mfm_mala_workspace_bytes(const mfm_target_t* t, int n) {
     using namespace mfm;
+    if (t->kind == MFM_TARGET_PINES_WHITE)
+        return ws_slice((size_t)n * t->dim, 4) * 2 + 4 * ws_slice(n, 4) + ws_slice(64, 4) + target_ws_bytes(*t, n) + 512;
     if (t->kind != MFM_TARGET_PINES) return 256;
     return ws_slice((size_t)n * t->dim, 4) * 2 + ws_slice((size_t)n * pines_n_tiles(t->dim), 4) + 3 * ws_slice(n, 4) + ws_slice(64, 4) + 256;
 }
@@ -184,6 +204,26 @@ int mfm_mala_step(const mfm_target_t* t, const uint32_t* rng_key, int per_chain_
     const float sq2h = sqrtf(2.0f * h);                         // jnp.sqrt(2*step_size) in f32
     const float quarter = (float)(0.25 * (1.0 / (double)step_size));   // python-float arithmetic, mala.py:79
     MalaIO io{position, logdensity, logdensity_grad, acceptance_rate, is_accepted, proposed_position, proposed_weight};
+    if (T.kind == MFM_TARGET_PINES_WHITE) {
+        Workspace w(ws, ws_bytes);
+        float* xprop = proposed_position ? proposed_position : w.take<float>((size_t)n * T.dim);
+        if (proposed_position) w.take<float>((size_t)n * T.dim);
+        float* gnew = w.take<float>((size_t)n * T.dim);
+        float* lik = w.take<float>(n); float* sqn = w.take<float>(n); float* u = w.take<float>(n); float* lnew = w.take<float>(n);
+        float* xamax = w.take<float>(64);
+        Workspace wt((char*)ws + w.off, w.off <= ws_bytes ? ws_bytes - w.off : 0);
+        if (!w.ok) { mfm_set_last_error_msg("workspace too small (mfm_mala_step)"); return MFM_ERR_WORKSPACE; }
+        // (the propose kernel's Poisson sum over x' is the UNwhitened likelihood: unused here)
+        pines_propose_kernel<<<ceil_div(n, 8), 256, 0, stream>>>(T, rng_key, n, chain_offset, n_total, h, sq2h, position,
+                                                                  logdensity_grad, xprop, lik, sqn, u, nullptr, rng_x64());
+        MFM_LAUNCH_CHECK();
+        int rc = target_value_and_grad(T, n, xprop, lnew, gnew, nullptr, wt, stream);
+        if (rc) return rc;
+        white_mala_finalize_kernel<<<ceil_div(n, 8), 256, 0, stream>>>(n, T.dim, h, quarter, xprop, gnew, lnew, sqn, u, io);
+        MFM_LAUNCH_CHECK();
+        (void)xamax;
+        return MFM_OK;
+    }
     if (T.kind == MFM_TARGET_PINES) {
         Workspace w(ws, ws_bytes);
         const int nt = pines_n_tiles(T.dim);
@@ -196,7 +236,7 @@ int mfm_mala_step(const mfm_target_t* t, const uint32_t* rng_key, int per_chain_
         if (!w.ok) { mfm_set_last_error_msg("workspace too small (mfm_mala_step)"); return MFM_ERR_WORKSPACE; }
         MFM_CUDA_CHECK(cudaMemsetAsync(xamax, 0, sizeof(float), stream));
         pines_propose_kernel<<<ceil_div(n, 8), 256, 0, stream>>>(T, rng_key, n, chain_offset, n_total, h, sq2h, position,
-                                                                  logdensity_grad, xprop, lik, sqn, u, xamax);
+                                                                  logdensity_grad, xprop, lik, sqn, u, xamax, rng_x64());
         MFM_LAUNCH_CHECK();
         int rc = pines_grad_gemm(T, n, xprop, T.dim, T.beta, gnew, T.dim, partial, nullptr, stream, xamax);
         if (rc) return rc;
@@ -208,7 +248,7 @@ int mfm_mala_step(const mfm_target_t* t, const uint32_t* rng_key, int per_chain_
     const size_t smem = (size_t)MALA_WARPS * 2 * T.dim * sizeof(float);
     if (smem > 200 * 1024) { mfm_set_last_error_msg("dim too large for warp-per-chain MALA"); return MFM_ERR_UNSUPPORTED; }
     if (smem > 48 * 1024) MFM_CUDA_CHECK(cudaFuncSetAttribute(mala_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    mala_small_kernel<<<ceil_div(n, MALA_WARPS), MALA_WARPS * 32, smem, stream>>>(T, rng_key, n, chain_offset, n_total, h, sq2h, quarter, io);
+    mala_small_kernel<<<ceil_div(n, MALA_WARPS), MALA_WARPS * 32, smem, stream>>>(T, rng_key, n, chain_offset, n_total, h, sq2h, quarter, io, rng_x64());
     MFM_LAUNCH_CHECK();
     return MFM_OK;
 }

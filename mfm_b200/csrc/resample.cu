@@ -46,10 +46,10 @@ __global__ void __launch_bounds__(32) cumsum_seq_kernel(const float* __restrict_
 }
 
 __global__ void choice_kernel(const uint32_t* __restrict__ key, const float* __restrict__ cum, int n_pop, int n_draw,
-                              int* __restrict__ idx) {
+                              int* __restrict__ idx, int x64) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_draw) return;
-    const float u = bits_to_unit_float(threefry_stream_word(key[0], key[1], (uint32_t)i, (uint32_t)n_draw));
+    const float u = rng_uniform_at(key[0], key[1], (uint32_t)i, (uint32_t)n_draw, x64);
     const float r = cum[n_pop - 1] * (1.0f - u);
     int lo = 0, hi = n_pop;                                        // first index with cum[index] >= r
     while (lo < hi) {
@@ -92,7 +92,7 @@ int mfm_random_choice(const uint32_t* key, int n_pop, const float* p, int n_draw
     if (n_draw == 0) return MFM_OK;
     mfm::cumsum_seq_kernel<<<1, 32, 0, stream>>>(p, n_pop, cum);
     MFM_LAUNCH_CHECK();
-    mfm::choice_kernel<<<ceil_div(n_draw, 256), 256, 0, stream>>>(key, cum, n_pop, n_draw, idx_out);
+    mfm::choice_kernel<<<ceil_div(n_draw, 256), 256, 0, stream>>>(key, cum, n_pop, n_draw, idx_out, mfm::rng_x64());
     MFM_LAUNCH_CHECK();
     return MFM_OK;
 }

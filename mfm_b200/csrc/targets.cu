@@ -218,7 +218,63 @@ __global__ void pines_finish_value_kernel(mfm_target_t T, int n, int n_tiles, co
     if (loglik_out) loglik_out[c] = lik[c];
 }
 
+// ---- whitened pines (distributions.py:276-297): state e, latents f = L e + mu --------------------------------------------------
+// per row: lik = sum(f c - a e^f), r = beta (c - a e^f) (the loglik gradient w.r.t. f), prior = -|e|^2 / 2, neg_e = -e
+__global__ void __launch_bounds__(256)
+white_lik_kernel(mfm_target_t T, int n, const float* __restrict__ e, const float* __restrict__ f, float* __restrict__ r,
+                 float* __restrict__ neg_e, float* __restrict__ lik, float* __restrict__ prior) {
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= n) return;
+    float sl = 0.0f, sp = 0.0f;
+    for (int i = lane; i < T.dim; i += 32) {
+        const long long o = (long long)c * T.dim + i;
+        const float fv = f[o], ev = e[o], ex = T.poisson_a * expf(fv);
+        sl += fv * T.counts[i] - ex;
+        sp += ev * ev;
+        r[o] = T.beta * (T.counts[i] - ex);
+        neg_e[o] = -ev;
+    }
+    sl = warp_sum(sl); sp = warp_sum(sp);
+    if (lane == 0) { lik[c] = sl; prior[c] = -0.5f * sp; }
+}
+__global__ void white_finish_kernel(mfm_target_t T, int n, const float* __restrict__ lik, const float* __restrict__ prior,
+                                    float* __restrict__ logp, float* __restrict__ loglik_out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    logp[c] = T.beta * lik[c] + (prior[c] + T.log_norm);
+    if (loglik_out) loglik_out[c] = lik[c];
+}
+// field terms: g = (c - a e^f) L - e clipped; hv = -((a e^f o (z L^T)) L) - z; hd_j = -sum_i L_ij^2 a e^f_i - 1, both zeroed where g was clipped
+__global__ void white_weights_kernel(mfm_target_t T, long long total, const float* __restrict__ f, const float* __restrict__ q,
+                                     float* __restrict__ r, float* __restrict__ s) {
+    const long long o = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (o >= total) return;
+    const int i = (int)(o % T.dim);
+    const float ex = T.poisson_a * expf(f[o]);
+    r[o] = T.counts[i] - ex;
+    if (s) s[o] = q ? ex * q[o] : ex;
+}
+__global__ void white_field_finish_kernel(long long total, float clip, const float* __restrict__ g_lin, const float* __restrict__ e,
+                                          const float* __restrict__ h_lin, const float* __restrict__ z, float* __restrict__ gc,
+                                          float* __restrict__ hvc, float* __restrict__ hdc) {
+    const long long o = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (o >= total) return;
+    const float g = g_lin[o] - e[o];
+    const bool in = !(clip > 0.0f) || (g > -clip && g < clip);
+    gc[o] = clip > 0.0f ? fminf(fmaxf(g, -clip), clip) : g;
+    if (hvc) hvc[o] = in ? (-h_lin[o] - z[o]) : 0.0f;
+    if (hdc) hdc[o] = in ? (-h_lin[o] - 1.0f) : 0.0f;
+}
+static int white_gemm(int n, int d, const float* A, const float* Bt, const float* bias, const float* add, float* C, cudaStream_t st) {
+    GemmShape p{n, d, d, A, (long long)d, Bt, (long long)d, nullptr};
+    EpiStd e{C, (long long)d, bias, nullptr, 0, add, (long long)d, 1.0f, 0};
+    MFM_CUDA_CHECK((launch_gemm<true, false>(p, e, st)));
+    return MFM_OK;
+}
+
 size_t target_ws_bytes(const mfm_target_t& T, int n) {
+    if (T.kind == MFM_TARGET_PINES_WHITE) return 3 * ws_slice((size_t)n * T.dim, 4) + 2 * ws_slice(n, 4) + 256;
     if (T.kind != MFM_TARGET_PINES) return 256;
     return ws_slice((size_t)n * pines_n_tiles(T.dim), 4) + ws_slice(n, 4) + 256;
 }
@@ -226,6 +282,20 @@ size_t target_ws_bytes(const mfm_target_t& T, int n) {
 int target_value_and_grad(const mfm_target_t& T, int n, const float* x, float* logp, float* grad, float* loglik_out,
                           Workspace& ws, cudaStream_t st) {
     if (n <= 0) return MFM_OK;
+    if (T.kind == MFM_TARGET_PINES_WHITE) {
+        const int d = T.dim;
+        float* f = ws.take<float>((size_t)n * d); float* r = ws.take<float>((size_t)n * d); float* neg_e = ws.take<float>((size_t)n * d);
+        float* lik = ws.take<float>(n); float* prior = ws.take<float>(n);
+        if (!ws.ok) { mfm_set_last_error_msg("workspace too small (target_value_and_grad)"); return MFM_ERR_WORKSPACE; }
+        int rc;
+        if ((rc = white_gemm(n, d, x, T.chol, T.mu_vec, nullptr, f, st))) return rc;             // f = e L^T + mu   (cox_process_utils.py:137)
+        white_lik_kernel<<<ceil_div(n, 8), 256, 0, st>>>(T, n, x, f, r, neg_e, lik, prior);
+        MFM_LAUNCH_CHECK();
+        if ((rc = white_gemm(n, d, r, T.chol_t, nullptr, neg_e, grad, st))) return rc;           // grad = beta (c - a e^f) L - e
+        white_finish_kernel<<<ceil_div(n, 256), 256, 0, st>>>(T, n, lik, prior, logp, loglik_out);
+        MFM_LAUNCH_CHECK();
+        return MFM_OK;
+    }
     if (T.kind == MFM_TARGET_PINES) {
         const int nt = pines_n_tiles(T.dim);
         float* partial = ws.take<float>((size_t)n * nt);
@@ -249,8 +319,24 @@ int target_value_and_grad(const mfm_target_t& T, int n, const float* x, float* l
 }
 
 int target_field_terms(const mfm_target_t& T, int n, const float* x, const float* z, const float* zkinv, float clip,
-                       float* gc, float* hvc, float* hdc, const int* n_rows_dev, cudaStream_t st, const float* x_amax) {
+                       float* gc, float* hvc, float* hdc, const int* n_rows_dev, cudaStream_t st, const float* x_amax, float* scratch) {
     if (n <= 0) return MFM_OK;
+    if (T.kind == MFM_TARGET_PINES_WHITE) {
+        // scratch: 4 x [n, d] (f, r / g_lin, q / s, h_lin).  Rows beyond a device-side active count are computed too (harmless).
+        if (!scratch) { mfm_set_last_error_msg("internal: whitened pines field terms need scratch"); return MFM_ERR_ARG; }
+        const int d = T.dim; const long long tot = (long long)n * d; const size_t sl = ws_slice((size_t)tot, 4) / 4;
+        float* f = scratch; float* r = scratch + sl; float* q = scratch + 2 * sl; float* hl = scratch + 3 * sl;
+        int rc;
+        if ((rc = white_gemm(n, d, x, T.chol, T.mu_vec, nullptr, f, st))) return rc;
+        if (hvc && (rc = white_gemm(n, d, z, T.chol, nullptr, nullptr, q, st))) return rc;       // L z
+        white_weights_kernel<<<ceil_div(tot, 256), 256, 0, st>>>(T, tot, f, hvc ? q : nullptr, r, (hvc || hdc) ? q : nullptr);
+        MFM_LAUNCH_CHECK();
+        if ((hvc || hdc) && (rc = white_gemm(n, d, q, hvc ? T.chol_t : T.chol_sq_t, nullptr, nullptr, hl, st))) return rc;
+        if ((rc = white_gemm(n, d, r, T.chol_t, nullptr, nullptr, f, st))) return rc;            // (c - a e^f) L   (f is free now)
+        white_field_finish_kernel<<<ceil_div(tot, 256), 256, 0, st>>>(tot, clip, f, x, hl, z, gc, hvc, hdc);
+        MFM_LAUNCH_CHECK();
+        return MFM_OK;
+    }
     if (T.kind == MFM_TARGET_PINES) {
         GemmShape p{n, T.dim, T.dim, x, (long long)T.dim, T.kinv, (long long)T.dim, n_rows_dev};
         p.a_amax = x_amax; kinv_mirror(T, p);

@@ -164,15 +164,17 @@ def get_bin_counts(points: np.ndarray, n_bins: int) -> np.ndarray:
 
 
 class LogGaussianCoxPines(Distribution):
-    """distributions.py:231-314 (unwhitened parameterisation).  The dense Gaussian prior is applied
-    as x K^-1 (one GEMM) instead of two triangular solves against chol(K); K^-1 is formed once in
-    float64 on the host (cond(K) = 27.6)."""
+    """distributions.py:231-314.  Unwhitened parameterisation (what multi_modal.py constructs): the dense Gaussian prior is
+    applied as x K^-1 (one GEMM) instead of two triangular solves against chol(K); K^-1 is formed once in float64 on the host
+    (cond(K) = 27.6).  use_whitened=True (:276-297): the state is the white noise e, latents f = L e + mu - value and gradient
+    are two GEMMs against the Cholesky factor, the field's Hessian terms two more."""
     _kind = _lib.TARGET_PINES
 
     def __init__(self, dim, file_path=None, use_whitened=False, device=None):
         super().__init__(device)
-        if use_whitened:
-            raise NotImplementedError("whitened parameterisation is not on the reference's configured path")
+        self.use_whitened = bool(use_whitened)
+        if self.use_whitened:
+            self._kind = _lib.TARGET_PINES_WHITE
         self.dim = dim
         n = int(np.sqrt(dim))
         self._num_grid_per_dim = n
@@ -199,6 +201,11 @@ class LogGaussianCoxPines(Distribution):
         self._kinv_mu = self._tensor(self._mu_zero * Kinv.sum(0))
         self._kinv_diag = self._tensor(np.diag(Kinv))
         self._cholesky_gram = self._tensor(L)
+        if self.use_whitened:
+            self._log_norm = float(-0.5 * dim * np.log(2 * np.pi))              # _white_gaussian_log_normalizer (:267)
+            self._chol_t = self._tensor(L.T)
+            self._chol_sq_t = self._tensor((L * L).T)
+            self._mu_vec = self._tensor(np.full(dim, self._mu_zero))
         # K^-1 is the constant B operand of every pines GEMM: its scaled-fp16 split (include/mfm_b200.h, mfm_gemm_presplit) is
         # made once here instead of in shared memory by every CTA of every call
         self._kinv_split = None
@@ -214,6 +221,9 @@ class LogGaussianCoxPines(Distribution):
         d.counts, d.kinv = self._flat_bin_counts.data_ptr(), self._kinv.data_ptr()
         d.kinv_mu, d.kinv_diag = self._kinv_mu.data_ptr(), self._kinv_diag.data_ptr()
         d.kinv_split = self._kinv_split.data_ptr() if self._kinv_split is not None else None
+        if self.use_whitened:
+            d.chol, d.chol_t = self._cholesky_gram.data_ptr(), self._chol_t.data_ptr()
+            d.chol_sq_t, d.mu_vec = self._chol_sq_t.data_ptr(), self._mu_vec.data_ptr()
         d.mu, d.log_norm, d.poisson_a = self._mu_zero, self._log_norm, self._poisson_a
 
     def initialize_model(self, rng_key, n_chain):

@@ -117,8 +117,11 @@ class VectorFieldNet:
         hs = list(hidden_x) + list(hidden_t) + list(hidden_xt)
         if len(hidden_x) != 2 or len(hidden_t) != 2 or len(hidden_xt) != 2 or len(set(hs)) != 1:
             raise NotImplementedError("the CUDA path implements the configured shape: three 2-layer branches of equal width")
-        if act_fn not in ("relu", torch.relu):
-            raise NotImplementedError("only relu (the reference default) is implemented on device")
+        if act_fn is torch.relu:
+            act_fn = "relu"
+        if act_fn not in _lib.ACTIVATIONS:                       # non_lins (:40-46)
+            raise KeyError(f"unknown non_linearity {act_fn!r}: one of {sorted(_lib.ACTIVATIONS)}")
+        self.act = _lib.ACTIVATIONS[act_fn]
         self.dist = dist
         self.hidden = hs[0]
         self.fourier_random = fourier_random.to(torch.float32).contiguous()
@@ -155,6 +158,7 @@ class VectorFieldNet:
         d.omega = self.fourier_random.data_ptr()
         d.grad_clip = self.grad_clip
         d.ref_mean, d.ref_std = self.ref_mean, self.ref_std
+        d.act = self.act
         return d
 
     def apply(self, P: VectorFieldParams, x: torch.Tensor, t: torch.Tensor, z: Optional[torch.Tensor] = None,
@@ -180,17 +184,26 @@ class VectorFieldNet:
 # optimizer / train state
 # ------------------------------------------------------------------------------------------------
 def create_learning_rate_fn(num_train_steps: int, num_warmup_steps: int, learning_rate: float) -> Callable[[int], float]:
-    """Linear warmup then linear decay (exe_flow_matching.py:189-198).  optax.linear_schedule with
-    transition_steps<=0 is constant init_value and join_schedules switches at the boundary, so
-    warmup_steps=0 is pure decay lr*(1-step/num_train_steps)."""
-    if num_warmup_steps != 0:
-        raise NotImplementedError("the device optimizer implements warmup_steps=0 (every reference config)")
+    """Linear warmup then linear decay (exe_flow_matching.py:189-198): optax.join_schedules([linear_schedule(0 -> lr,
+    warmup), linear_schedule(lr -> 0, total - warmup)], [warmup]).  optax.linear_schedule with transition_steps <= 0 is the
+    constant init_value and join_schedules switches at the boundary, so warmup_steps = 0 is pure decay
+    lr * (1 - step / num_train_steps).  The device optimizer evaluates the same schedule from its own step counter."""
+    W, T = int(num_warmup_steps), int(num_train_steps)
+    if W < 0 or W > T:
+        raise ValueError("0 <= warmup_steps <= learning_iter")
+
+    def lin(init, end, steps):
+        if steps <= 0:
+            return lambda c: init
+        return lambda c: (init - end) * (1.0 - min(max(c, 0), steps) / steps) + end
+
+    warm, decay = lin(0.0, learning_rate, W), lin(learning_rate, 0.0, T - W)
 
     def schedule(step):
-        s = min(max(int(step), 0), num_train_steps)
-        return learning_rate * (1.0 - s / num_train_steps)
+        s = int(step)
+        return warm(s) if s < W else decay(s - W)
 
-    schedule.base, schedule.total = float(learning_rate), int(num_train_steps)
+    schedule.base, schedule.total, schedule.warmup = float(learning_rate), T, W
     return schedule
 
 
@@ -282,7 +295,7 @@ class TrainState:
         g = self.grads if grads is None else grads
         _lib.check(lib.mfm_adamw_step(_lib.ptr(self.P.flat), _lib.ptr(g), _lib.ptr(self.mu), _lib.ptr(self.nu),
                                       _lib.ptr(self.P.decay_mask), self.P.n_params, _lib.ptr(self.opt_state),
-                                      self.lr_fn.base, self.lr_fn.total, a.adam_beta1, a.adam_beta2, a.adam_epsilon,
+                                      self.lr_fn.base, self.lr_fn.total, self.lr_fn.warmup, a.adam_beta1, a.adam_beta2, a.adam_epsilon,
                                       a.weight_decay, a.gradient_clip, 10, _lib.stream()))
         self.step += 1
         return self
@@ -306,9 +319,8 @@ def create_train_data_gn(dist: Distribution, model: VectorFieldNet, ode_opts, ar
     model.set_ref_dist(make_ref_dist(args, dim, dist.device))                       # (:244)
     opts = _lib.OdeOpts(float(ode_opts.rtol), float(ode_opts.atol), int(ode_opts.mxstep), 1 if args.hutchs else 0,
                         int(ode_opts.n_times))
-    if args.num_importance_samples > 0:
-        raise NotImplementedError("conditional importance sampling is not on the configured hot path")
-    variant = _lib.FLOW_INDEP_MH if args.num_importance_samples < 0 else _lib.FLOW_RW_MH
+    n_is = int(args.num_importance_samples)                 # > 0: conditional importance sampling (:280-296, :298)
+    variant = _lib.FLOW_INDEP_MH if n_is < 0 else _lib.FLOW_RW_MH
     m = args.mcmc_per_flow_steps
     last_stats = {}
 
@@ -344,6 +356,14 @@ def create_train_data_gn(dist: Distribution, model: VectorFieldNet, ode_opts, ar
         weight = torch.empty(n, dtype=torch.float32, device=dev)
         stats = torch.zeros(8, dtype=torch.int32, device=dev)
         fd, td = model.field_desc(P), logprob.desc()
+        if n_is > 0:
+            ws = _lib.workspace(lib.mfm_flow_cis_workspace_bytes(fd, td, opts, n, n_is), dev, "flow")
+            _lib.check(lib.mfm_flow_cis_step(fd, td, opts, n_is, _lib.ptr(rng_key.contiguous()), 1 if per_chain_keys else 0, n, chain_offset,
+                                             n_total if n_total is not None else n, _lib.ptr(x), _lib.ptr(l), _lib.ptr(acc_rate),
+                                             _lib.ptr(is_acc), _lib.ptr(prop), _lib.ptr(weight), _lib.ptr(stats), _lib.ptr(ws), ws.numel(),
+                                             _lib.stream()))
+            last_stats["ode"] = stats
+            return MALAState(x, l, g), MALAInfo(acc_rate, is_acc.bool(), prop, weight)      # the gradient is kept, as coded (:295)
         ws = _lib.workspace(lib.mfm_flow_mh_workspace_bytes(fd, td, opts, n), dev, "flow")
         _lib.check(lib.mfm_flow_mh_step(fd, td, opts, variant, _lib.ptr(rng_key.contiguous()), 1 if per_chain_keys else 0,
                                         n, chain_offset, n_total if n_total is not None else n, _lib.ptr(x), _lib.ptr(l),

@@ -285,3 +285,46 @@ class LogGaussianCoxPines(Target):
         dt = np.dtype(dtype)
         eps = tf.vmap_normal(tf.split(key, n), self.dim, dt)
         return (dt.type(self.mu) + eps @ self.L.astype(dt, copy=False).T).astype(dt)
+
+
+class LogGaussianCoxPinesWhitened(LogGaussianCoxPines):
+    """use_whitened=True (distributions.py:276-297): the state is the white noise e; latents f = L e + mu
+    (cox_process_utils.get_latents_from_white, :118-140); loglik = Poisson log-likelihood of f; logprior = -|e|^2 / 2 -
+    d log(2 pi) / 2.  initialize_model is the SAME function as for the unwhitened target (mu + L eps, :312-314), as coded."""
+
+    def __init__(self, dim=1600, counts=None):
+        super().__init__(dim, counts)
+        self.log_norm = -0.5 * dim * np.log(2 * np.pi)
+
+    def _f(self, e):
+        dt = e.dtype
+        return e @ self.L.astype(dt, copy=False).T + dt.type(self.mu)
+
+    def loglik(self, e):
+        return LogGaussianCoxPines.loglik(self, self._f(e))
+
+    def grad_loglik(self, e):
+        return LogGaussianCoxPines.grad_loglik(self, self._f(e)) @ self.L.astype(e.dtype, copy=False)
+
+    def hvp_loglik(self, e, z):
+        dt = e.dtype
+        L = self.L.astype(dt, copy=False)
+        return -((dt.type(self.a) * np.exp(self._f(e))) * (z @ L.T)) @ L
+
+    def hdiag_loglik(self, e):
+        dt = e.dtype
+        L = self.L.astype(dt, copy=False)
+        return -(dt.type(self.a) * np.exp(self._f(e))) @ (L * L)
+
+    def logprior(self, e):
+        dt = e.dtype
+        return dt.type(-0.5) * (e * e).sum(1) + dt.type(self.log_norm)
+
+    def grad_logprior(self, e):
+        return -e
+
+    def hvp_logprior(self, e, z):
+        return -z
+
+    def hdiag_logprior(self, e):
+        return -np.ones_like(e)

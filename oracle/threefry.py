@@ -114,15 +114,28 @@ _W_GE5 = np.array([-0.000200214257, 0.000100950558, 0.00134934322, -0.0036734284
                   dtype=np.float32)
 
 
+def log1p_f32_xla(t):
+    """XLA CPU's float32 log1p (elemental_ir_emitter.cc EmitLog1p; third-party, restated - unpinned): (-0.5 t + 1) t for
+    |t| < 1e-4, else log(1 + t) with the sum rounded to float32 first.  The logarithm is evaluated in float64 and rounded
+    (= correctly rounded logf; XLA's vectorised polynomial is within an ulp of it) so that the CUDA path can reproduce it
+    bit for bit."""
+    t = np.asarray(t, np.float32)
+    small = ((np.float32(-0.5) * t).astype(np.float32) + np.float32(1.0)).astype(np.float32) * t
+    with np.errstate(divide="ignore", invalid="ignore"):
+        large = np.log((np.float32(1.0) + t).astype(np.float32).astype(np.float64)).astype(np.float32)
+    return np.where(np.abs(t) < np.float32(1e-4), small.astype(np.float32), large).astype(np.float32)
+
+
 def erf_inv_f32(x):
+    """every multiply and add rounds separately (XLA CPU does not contract to FMA)"""
     x = np.asarray(x, np.float32)
     with np.errstate(divide="ignore", invalid="ignore"):
-        w = -np.log1p(-x * x).astype(np.float32)
+        w = -log1p_f32_xla(-(x * x).astype(np.float32))
         lt = w < np.float32(5.0)
         w = np.where(lt, w - np.float32(2.5), np.sqrt(w) - np.float32(3.0)).astype(np.float32)
         p = np.where(lt, _W_LT5[0], _W_GE5[0]).astype(np.float32)
         for i in range(1, 9):
-            p = (np.where(lt, _W_LT5[i], _W_GE5[i]).astype(np.float32) + p * w).astype(np.float32)
+            p = (np.where(lt, _W_LT5[i], _W_GE5[i]).astype(np.float32) + (p * w).astype(np.float32)).astype(np.float32)
         res = (p * x).astype(np.float32)
         return np.where(np.abs(x) == 1, x * np.float32(np.inf), res).astype(np.float32)
 

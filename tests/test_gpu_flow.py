@@ -218,6 +218,39 @@ def test_flow_mh_step(cuda, setups, name, nis):
     assert (info_d.proposed_weight == 0).all()
 
 
+@pytest.mark.parametrize("name,K", [("gmm16", 4), ("4-mode", 3), ("gmm16", 7)])   # (as coded the weights are exp(log-density): they underflow to 0 / 0 for phi-four and pines, |l| ~ 2e3, in float64 too)
+def test_cis_flow_step(cuda, setups, name, K):
+    """conditional_importance_sampling (exe_flow_matching.py:280-296, --num_importance_samples K) against the oracle: K + 1
+    normalised weights per chain, the index drawn by jax.random.choice from one uniform, the state update (the gradient of the
+    previous state is kept, as coded) and the info fields."""
+    s = setups[name]
+    n = s.n
+    gen, init_fn, _ = _gn(s, nis=K)
+    flow = _flow(s)
+    x0 = _positions(s, n, seed=5)
+    beta = 0.8
+    st_d = init_fn(to_dev(x0, cuda), beta)
+    st_o = OS.mala_init(x0, s.ot, beta)
+    key = tf.PRNGKey(77)
+    new_o, info_o = OS.cis_flow_step(tf.split(key, n), st_o, s.ot, flow, OT.IndepGaussian(s.ot.dim), K, beta)
+    new_d, info_d = gen.flow_step(key_dev(key, cuda), st_d, s.dd.tempered(beta), s.P)
+    acc_d, acc_o = info_d.is_accepted.cpu().numpy(), info_o.is_accepted
+    w_d, w_o = info_d.acceptance_rate.cpu().numpy().astype(np.float64), info_o.acceptance_rate
+    same = (acc_d == acc_o) & (np.abs(w_d - w_o) <= 2e-2 * np.maximum(w_o, 1e-6))      # the same candidate was drawn
+    # a draw lands on the other side of a cumulative-weight boundary only when the ODE-level differences in the weights
+    # (~1e-2 relative, see test_flow_mh_decision_flip_rate) straddle r: at most one chain of the ensemble here
+    assert same.sum() >= n - 1, (name, same.sum(), n)
+    assert np.allclose(w_d[same], w_o[same], rtol=2e-2)
+    assert torch.equal(info_d.proposed_weight, info_d.acceptance_rate)
+    err, tol = _tol(new_d.position.cpu().numpy()[same], new_o.position[same], new_o.position[same].astype(np.float32), 2e-3)
+    assert err < tol, (name, err, tol)
+    err, tol = _tol(info_d.proposed_position.cpu().numpy()[same], info_o.proposed_position[same], info_o.proposed_position[same].astype(np.float32), 2e-3)
+    assert err < tol, (name, err, tol)
+    ld, lo = new_d.logdensity.cpu().numpy()[same], new_o.logdensity[same]
+    assert np.abs(ld - lo).max() <= 2e-3 * max(np.abs(lo).max(), 1.0)
+    assert torch.equal(new_d.logdensity_grad, st_d.logdensity_grad)                     # as coded: not recomputed
+
+
 def test_train_data_generator_dispatch(cuda, setups):
     """count % (m+1) == 0 -> flow step, else MALA (exe_flow_matching.py:311-313)."""
     s = setups["gmm16"]

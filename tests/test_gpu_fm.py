@@ -65,6 +65,53 @@ def test_fm_loss_and_grad(cuda, setups, name, n):
         assert rel_err(g[sl], g_ref[sl]) < 5e-4, (name, "bias", i)
 
 
+@pytest.mark.parametrize("act", ["tanh", "elu", "gelu", "swish"])
+@pytest.mark.parametrize("name,n", [("gmm16", 77), ("pines", 300)])
+def test_activations(cuda, setups, name, n, act):
+    """--non_linearity (exe_flow_matching.py:40-46, multi_modal.py:181): jax.nn.tanh / elu / gelu (tanh approximation) / swish.
+    Field value, Hutchinson divergence (forward-mode tangent through the activation derivatives) and the FM loss / gradient
+    (reverse mode through the same derivatives) against the float64 oracle; pines at 300 chains goes through the tcgen05
+    kernels incl. the pre-split hand-over, gmm16 through the warp-level ones."""
+    from mfm_b200 import exe_flow_matching as E
+    s = setups[name]
+    H = s.P.hidden
+    model = E.VectorFieldNet(to_dev(s.omega, cuda), s.dd, [H, H], [H, H], [H, H], act, s.clip)
+    state = E.create_train_state(model, s.P, E.create_learning_rate_fn(1000, 0, 1e-3), _args())
+    x = s.ot.init_positions(tf.PRNGKey(8), n, np.float32).astype(np.float64)
+    t = np.linspace(0.0, 1.2, n)
+    z = np.random.default_rng(5).standard_normal(x.shape)
+    v_ref, div_ref = VF.field_and_div(s.params, s.omega, x, t, s.ot, z, s.clip, act=act)
+    v, div = model.apply(s.P, to_dev(x, cuda), to_dev(t, cuda), to_dev(z, cuda), hutch=True, want_div=True)
+    assert rel_err(v.cpu().numpy(), v_ref) < 1e-4, (name, act)
+    assert np.abs(div.cpu().numpy() - div_ref).max() < 1e-4 * max(np.abs(div_ref).max(), 1.0), (name, act)
+    key = tf.PRNGKey(31337)
+    times, xt, target = VF.fm_batch(key, x, OT.IndepGaussian(s.ot.dim).sample, 1e-4, rng_dtype=np.float32)
+    loss_ref, G = VF.fm_loss_and_grad(s.params, s.omega, xt, times, target, s.ot.grad, s.clip, act=act)
+    loss, grads = state.loss_and_grad(key_dev(key, cuda), to_dev(x, cuda))
+    assert abs(loss.item() - loss_ref) < 1e-4 * abs(loss_ref), (loss.item(), loss_ref)
+    g_ref, g = _flat_grads(s, G), grads.cpu().numpy()
+    assert rel_err(g, g_ref) < 2e-4
+    for i in range(8):
+        fi, fo = s.P.shapes[i]
+        sl = slice(s.P.w_off[i], s.P.w_off[i] + fi * fo)
+        assert rel_err(g[sl], g_ref[sl]) < 5e-4, (name, act, i)
+
+
+def test_activation_exact_divergence(cuda, setups):
+    """trace(jacfwd) path (d tangents) with a smooth activation: phi-four's 64 basis tangents through tanh."""
+    from mfm_b200 import exe_flow_matching as E
+    s = setups["phi-four"]
+    H = s.P.hidden
+    model = E.VectorFieldNet(to_dev(s.omega, cuda), s.dd, [H, H], [H, H], [H, H], "tanh", s.clip)
+    n = 24
+    x = s.ot.init_positions(tf.PRNGKey(8), n, np.float32).astype(np.float64)
+    t = np.linspace(0.0, 1.0, n)
+    v_ref, div_ref = VF.field_and_div(s.params, s.omega, x, t, s.ot, None, s.clip, act="tanh")
+    v, div = model.apply(s.P, to_dev(x, cuda), to_dev(t, cuda), None, hutch=False, want_div=True)
+    assert rel_err(v.cpu().numpy(), v_ref) < 1e-4
+    assert np.abs(div.cpu().numpy() - div_ref).max() < 1e-4 * max(np.abs(div_ref).max(), 1.0)
+
+
 def test_fm_sharded_batch_matches_full(cuda, setups):
     """Rows [lo,hi) of an n_total ensemble see the same (t, x0, eps) as in the unsharded call, so the
     shard losses/gradients add up to the full ones (the quantity the NCCL all-reduce sums)."""
@@ -107,14 +154,17 @@ def test_fm_two_part_backward_is_identical(cuda, lib, setups, name):
     assert torch.equal(g2, grads)
 
 
-def test_adamw_clip_apply_if_finite(cuda, setups):
+@pytest.mark.parametrize("warmup", [0, 3])
+def test_adamw_clip_apply_if_finite(cuda, setups, warmup):
+    """warmup = 3: --warmup_steps (exe_flow_matching.py:189-198): the device optimizer evaluates the joined schedule itself; the first
+    step runs with learning rate 0, and a rejected update does not advance the schedule."""
     from mfm_b200 import exe_flow_matching as E
     s = setups["4-mode"]
     P = E.VectorFieldParams(2, 128, 128, cuda).load_dict(s.params)
-    lr = E.create_learning_rate_fn(100, 0, 1e-3)
+    lr = E.create_learning_rate_fn(100, warmup, 1e-3)
     state = E.create_train_state(s.model, P, lr, _args())
     params = {"params": {k: {n: a.copy() for n, a in v.items()} for k, v in s.params["params"].items()}}
-    opt = OO.AdamWClipIfFinite(params, OO.learning_rate_fn(100, 0, 1e-3))
+    opt = OO.AdamWClipIfFinite(params, OO.learning_rate_fn(100, warmup, 1e-3))
     rng = np.random.default_rng(0)
     for it in range(5):
         G = {"params": {k: {n: (rng.standard_normal(a.shape) * 10 ** rng.uniform(-6, 2)).astype(np.float32)
@@ -138,9 +188,11 @@ def test_adamw_clip_apply_if_finite(cuda, setups):
 
 def test_lr_schedule_matches_oracle(lib):
     from mfm_b200 import exe_flow_matching as E
-    a, b = E.create_learning_rate_fn(400, 0, 1e-3), OO.learning_rate_fn(400, 0, 1e-3)
-    for step in (0, 1, 57, 399, 400, 1000):
-        assert a(step) == pytest.approx(b(step), rel=1e-12, abs=1e-18)
+    for warm in (0, 1, 40, 400):
+        a, b = E.create_learning_rate_fn(400, warm, 1e-3), OO.learning_rate_fn(400, warm, 1e-3)
+        for step in (0, 1, 39, 40, 57, 399, 400, 1000):
+            assert a(step) == pytest.approx(b(step), rel=1e-12, abs=1e-18)
+    assert E.create_learning_rate_fn(400, 40, 1e-3)(20) == pytest.approx(0.5e-3)
 
 
 def test_tempering_beta_matches_oracle(cuda, lib):

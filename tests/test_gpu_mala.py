@@ -19,7 +19,7 @@ def targets(cuda, lib):
     return make_targets(cuda)
 
 
-def _check(name, ot, dd, cuda, n, beta, per_chain, steps=3):
+def _check(name, ot, dd, cuda, n, beta, per_chain, steps=3, rng_dtype=np.float32):
     from mfm_b200.bblackjax.mcmc import mala as M
     h = STEP[name]
     x0 = ot.init_positions(tf.PRNGKey(1), n, np.float32)
@@ -37,8 +37,8 @@ def _check(name, ot, dd, cuda, n, beta, per_chain, steps=3):
         st_in = OS.MALAState(st_d.position.cpu().numpy().astype(np.float64),
                              st_d.logdensity.cpu().numpy().astype(np.float64),
                              st_d.logdensity_grad.cpu().numpy().astype(np.float64))
-        noise = tf.vmap_normal(np.stack([tf.split(k)[0] for k in keys]), ot.dim, np.float32).astype(np.float64)
-        new_o, info_o, dbg = OS.mala_step(keys, st_in, ot, h, beta, noise=noise, rng_dtype=np.float32)
+        noise = tf.vmap_normal(np.stack([tf.split(k)[0] for k in keys]), ot.dim, rng_dtype).astype(np.float64)
+        new_o, info_o, dbg = OS.mala_step(keys, st_in, ot, h, beta, noise=noise, rng_dtype=rng_dtype)
         if per_chain:
             st_d, info_d = kernel(key_dev(keys, cuda), st_d, fn, h)
         else:
@@ -68,6 +68,19 @@ def _check(name, ot, dd, cuda, n, beta, per_chain, steps=3):
 def test_mala_small_targets(cuda, targets, per_chain):
     for name, ot, dd in targets[:3]:
         _check(name, ot, dd, cuda, 131, 1.0, per_chain)
+
+
+def test_mala_x64_draws(cuda, lib, targets):
+    """The reference as shipped runs with jax_enable_x64 (multi_modal.py:14): noise and accept uniforms are float64 draws
+    (64 bits each).  With mfm_set_rng_x64(1) the fused MALA kernels consume exactly those draws (rounded to float32)."""
+    lib.mfm_set_rng_x64(1)
+    try:
+        for name, ot, dd in targets[:3]:
+            _check(name, ot, dd, cuda, 67, 1.0, False, rng_dtype=np.float64)
+        name, ot, dd = targets[3]
+        _check(name, ot, dd, cuda, 5, 1.0, True, steps=2, rng_dtype=np.float64)
+    finally:
+        lib.mfm_set_rng_x64(0)
 
 
 def test_mala_tempered(cuda, targets):

@@ -253,3 +253,18 @@ def test_adamw_restatement_matches_torch_adamw():
         topt.step()
         assert np.allclose(p["params"]["Dense_0"]["kernel"], k.detach().numpy(), rtol=2e-6, atol=2e-7)
         assert np.allclose(p["params"]["Dense_0"]["bias"], b.detach().numpy(), rtol=2e-6, atol=2e-7)
+
+
+def test_activation_derivatives_by_finite_differences():
+    """oracle.vector_field.activation: (act, act') pairs of jax.nn.{relu, tanh, elu, gelu (tanh approximation), swish}."""
+    v = np.linspace(-4.0, 4.0, 401) + 1e-3
+    h = 1e-6
+    for name in ("relu", "tanh", "elu", "gelu", "swish"):
+        f, df = VF.activation(name, v)
+        fd = (VF.activation(name, v + h)[0] - VF.activation(name, v - h)[0]) / (2 * h)
+        assert np.abs(df - fd).max() < 1e-6, name
+    # definitions at known points: gelu(1) with the tanh approximation, swish(1) = sigmoid(1), elu(-1) = e^-1 - 1
+    one = np.array([1.0])
+    assert VF.activation("gelu", one)[0][0] == np.float64(0.5 * (1 + np.tanh(np.sqrt(2 / np.pi) * 1.044715)))
+    assert abs(VF.activation("swish", one)[0][0] - 1 / (1 + np.exp(-1.0))) < 1e-15
+    assert abs(VF.activation("elu", -one)[0][0] - (np.exp(-1.0) - 1)) < 1e-15

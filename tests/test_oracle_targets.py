@@ -127,3 +127,23 @@ def test_pines_prior_is_the_multivariate_normal_density():
     x = t.init_positions(tf.PRNGKey(2), 2, np.float64)
     ref = scipy.stats.multivariate_normal(mean=np.full(1600, t.mu), cov=t.K, allow_singular=False).logpdf(x)
     assert np.allclose(t.logprior(x), ref, rtol=1e-10)
+
+
+def test_whitened_pines_oracle_by_finite_differences():
+    """LogGaussianCoxPinesWhitened: analytic gradient / Hessian-vector product / Hessian diagonal of log-likelihood + log-prior in
+    the white-noise parameterisation (distributions.py:276-297), and its link to the unwhitened target: the two log-densities
+    differ by the constant log |det L| at corresponding points f = L e + mu."""
+    from oracle import targets as OT
+    t = OT.LogGaussianCoxPinesWhitened(1600)
+    u = OT.LogGaussianCoxPines(1600)
+    rng = np.random.default_rng(0)
+    e = rng.standard_normal((2, 1600)); z = rng.standard_normal((2, 1600))
+    h = 1e-5
+    g = t.grad(e)
+    assert abs(((t.logprob(e + h * z) - t.logprob(e - h * z)) / (2 * h) - (g * z).sum(1)) / (g * z).sum(1)).max() < 1e-6
+    hv = t.hvp(e, z)
+    assert np.abs(hv - (t.grad(e + h * z) - t.grad(e - h * z)) / (2 * h)).max() < 1e-6 * np.abs(hv).max()
+    ej = np.zeros((1, 1600)); ej[0, 7] = 1
+    assert abs(t.hdiag(e)[0, 7] - ((t.grad(e[:1] + h * ej) - t.grad(e[:1] - h * ej)) / (2 * h))[0, 7]) < 1e-6
+    f = e @ t.L.T + t.mu
+    assert np.allclose(t.logprob(e) - u.logprob(f), t.half_log_det, rtol=0, atol=1e-8)
