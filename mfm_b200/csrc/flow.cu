@@ -12,6 +12,7 @@
 // own (t, dt, segment, step count) and is masked once finished — exactly the semantics of the
 // batched while_loop that jax.vmap produces.  Dense layers run on tensor cores (3xTF32).
 #include "internal.h"
+#include <limits.h>
 #include <string.h>
 #include <stdlib.h>
 #include "gemm_tf32x3.cuh"
@@ -459,7 +460,8 @@ int field_eval(const mfm_field_t& F, const mfm_target_t& T, int n, const float* 
     }
     // pre-split copies: a layer's result leaves the epilogue in tensor-core format too (EpiStdS) and the consuming layer's TMA
     // loads that copy (no splitter work, a quarter less shared-memory traffic in the consumer)
-    const bool sp = am != nullptr && B.h0_s != nullptr && H % 16 == 0 && (2 * Fd) % 16 == 0 && n >= 256 && ((reinterpret_cast<uintptr_t>(B.h0_s) | reinterpret_cast<uintptr_t>(B.cat_s)) & 63) == 0;
+    static const bool no_split = getenv("MFM_H16_NOSPLIT") != nullptr;      // debug: every layer splits its own A operand
+    const bool sp = !no_split && am != nullptr && B.h0_s != nullptr && H % 16 == 0 && (2 * Fd) % 16 == 0 && n >= 256 && ((reinterpret_cast<uintptr_t>(B.h0_s) | reinterpret_cast<uintptr_t>(B.cat_s)) & 63) == 0;
     auto BD = [&](int i) -> float* { return am + AM_BOUND + i; };
     auto WC = [&](int l) -> const float* { return am + AM_WNORM_COL + l; };
     auto BA = [&](int l) -> const float* { return am + AM_BIAS + l; };
@@ -489,7 +491,9 @@ int field_eval(const mfm_field_t& F, const mfm_target_t& T, int n, const float* 
                     D_(OUT_(A_(x_amax, nullptr, 0, slot(AM_H2)), B.h2_s, AM_H2, 2, true), B.dh2, H)))) return rc;
     {   // s_t and s_x: one scale for both halves of cat
         DenseAmax mt = OUT_(IN_(A_(slot(AM_H0), nullptr, 0, slot(AM_ST)), B.h0_s, BD(AM_H0)), B.cat_s + H, AM_ST, 1, true);
-        DenseAmax mx = OUT_(IN_(A_(slot(AM_H2), nullptr, 0, slot(AM_SX)), B.h2_s, BD(AM_H2)), B.cat_s, AM_SX, 3, true);
+        // (h2's copy exists only when Dense_2 knew max |x|: dense() needs an input maximum to bound its output)
+        DenseAmax mx = OUT_(A_(slot(AM_H2), nullptr, 0, slot(AM_SX)), B.cat_s, AM_SX, 3, true);
+        if (x_amax) mx = IN_(mx, B.h2_s, BD(AM_H2));
         if (sp) { mt.alt_amax = slot(AM_H2); mt.alt_w_norm = WC(3); mt.alt_bias = BA(3); mx.alt_amax = slot(AM_H0); mx.alt_w_norm = WC(1); mx.alt_bias = BA(1); }
         if ((rc = dense(n, H, H, B.h0, H, WT_(1), H, B_(1), act, B.cat + H, 2 * H, nullptr, 0, 1, st, nr, D_(mt, dmul ? B.dcat + H : nullptr, 2 * H)))) return rc;       // s_t
         if ((rc = dense(n, H, H, B.h2, H, WT_(3), H, B_(3), act, B.cat, 2 * H, nullptr, 0, 1, st, nr, D_(mx, B.dcat, 2 * H)))) return rc;           // s_x
@@ -750,6 +754,11 @@ __device__ __forceinline__ float fit_eval(float y0, float y1, float ymid, float 
     return (((a * rel + b) * rel + c) * rel + dd) * rel + y0;
 }
 
+}  // namespace mfm
+#include "targets.cuh"
+#include "ode_small.cuh"      // the fused one-launch solve for the small reference shapes (uses the tableau and fit_eval above)
+namespace mfm {
+
 // error ratio, accept/reject, controller, FSAL, dense output.  One warp per chain.
 __global__ void ode_finish_kernel(int n, int d, OdeState S, OdeTimes TS, float rtol, float atol, int mxstep) {
     const int lane = threadIdx.x & 31;
@@ -844,7 +853,8 @@ __global__ void write_stats_kernel(const int* __restrict__ counters, int n_eval,
     if (threadIdx.x == 0) {
         // device-resident loop: n_eval < 0 carries -(evaluations before the loop), counters[12] the iterations the loop ran;
         // host_chain_evals < 0 carries -n (every evaluation ran on all n rows: no compaction)
-        if (n_eval < 0) n_eval = -n_eval + 6 * counters[12];
+        if (n_eval == INT_MIN) n_eval = 2 + 6 * counters[3];          // fused small-shape solve: as many lock-step iterations as the slowest chain took
+        else if (n_eval < 0) n_eval = -n_eval + 6 * counters[12];
         if (host_chain_evals < 0) host_chain_evals = -host_chain_evals * n_eval;
         const long long ce = *reinterpret_cast<const long long*>(counters + 10) + host_chain_evals;
         long long* out_ce = reinterpret_cast<long long*>(stats + 4);
@@ -870,6 +880,11 @@ struct OdeGraphKey {
 struct OdeGraphEntry { OdeGraphKey key; cudaGraph_t graph; cudaGraphExec_t exec; int dev; long long max_iter; unsigned long long stamp; bool used; };
 static thread_local OdeGraphEntry g_ode_graphs[8];
 static thread_local unsigned long long g_ode_graph_stamp = 0;
+static int g_ode_small = -1;             // fused one-launch solve for the small shapes (MFM_ODE_SMALL=0 switches it off)
+static bool ode_small_enabled() {
+    if (g_ode_small < 0) { const char* e = getenv("MFM_ODE_SMALL"); g_ode_small = (e && e[0] == '0') ? 0 : 1; }
+    return g_ode_small != 0;
+}
 static int g_ode_graph_mode = -1;        // -1 unread, 0 never, 1 always, 2 auto (small ensembles)
 static bool ode_use_graph(long long elements) {
     if (g_ode_graph_mode < 0) {
@@ -973,6 +988,23 @@ static int ode_solve(const mfm_field_t& F, const mfm_target_t& T, const mfm_ode_
     if (O.n_times < 2 || O.n_times > 17) { mfm_set_last_error_msg("n_times must be in [2,17]"); return MFM_ERR_ARG; }
     OdeTimes TS; TS.n_seg = O.n_times - 1;
     for (int k = 1; k < O.n_times; ++k) TS.target[k - 1] = (float)((double)k / (double)(O.n_times - 1));
+    if (ode_small_enabled() && small::eligible(F, T, n)) {
+        // the small reference shapes: the whole solve in ONE launch, 16 chains per CTA (ode_small.cuh)
+        small::Args A;
+        A.F = F; A.T = T; A.n = n; A.hutch = z != nullptr ? 1 : 0; A.n_seg = TS.n_seg;
+        for (int k = 0; k < 16; ++k) A.target[k] = k < TS.n_seg ? TS.target[k] : 0.0f;
+        A.rtol = O.rtol; A.atol = O.atol; A.mxstep = O.mxstep; A.sgn = sgn; A.y0 = y0; A.z = z; A.y1 = y1; A.ldj = ldj; A.counters = S.counters;
+        static bool configured = false;
+        if (!configured) {
+            MFM_CUDA_CHECK(cudaFuncSetAttribute(small::ode_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, small::SMEM_BYTES));
+            configured = true;
+        }
+        MFM_CUDA_CHECK(cudaMemsetAsync(S.counters, 0, 64 * sizeof(int), st));
+        small::ode_small_kernel<<<ceil_div(n, small::CH), small::NTHR, small::SMEM_BYTES, st>>>(A);
+        MFM_LAUNCH_CHECK();
+        if (stats) { write_stats_kernel<<<1, 32, 0, st>>>(S.counters, INT_MIN, 0, stats, stats_accumulate); MFM_LAUNCH_CHECK(); }
+        return MFM_OK;
+    }
     int* hflag = host_flag();
     if (!hflag) { mfm_set_last_error_msg("cudaMallocHost failed"); return MFM_ERR_CUDA; }
     int rc;
@@ -1229,6 +1261,8 @@ static int check_field(const mfm_field_t* f, const mfm_target_t* t, const mfm_od
     if (!(f->ref_std > 0.0f)) { mfm_set_last_error_msg("field.ref_std must be > 0 (reference distribution IndepGaussian(mean, std^2))"); return MFM_ERR_ARG; }
     return MFM_OK;
 }
+
+void mfm_debug_set_ode_small(int v) { g_ode_small = v ? 1 : 0; }      // test hook (not in the ABI header): fused small-shape solve on / off
 
 size_t mfm_ode_workspace_bytes(const mfm_field_t* f, const mfm_target_t* t, const mfm_ode_opts_t* o, int n) {
     return ode_state_bytes(n, f->dim, f->hidden) + field_bufs_bytes(*f, *t, n, o->hutch != 0) + 2 * ws_slice((size_t)n * f->dim, 4) + 1024;

@@ -223,7 +223,7 @@ def _h16_split_ref(x, amax):
 
 
 @pytest.mark.parametrize("M,N,K", [(512, 512, 512), (8192, 1024, 1024), (8192, 1600, 1024), (4096 + 77, 1088, 528), (65536, 1024, 1024),
-                                   (300, 256, 64)])
+                                   (300, 256, 64), (333, 128, 128), (333, 128, 256), (1024, 128, 128), (65536, 128, 128)])
 @pytest.mark.parametrize("a_scale,b_scale", [(1.0, 1.0), (3e-7, 1.0), (2.5e4, 1e-3)])
 def test_gemm_h16(cuda, lib, M, N, K, a_scale, b_scale):
     """Default dense-layer kernel: operands scaled per tensor and split into two fp16 parts, three kind::f16 MMAs per 16 k.
@@ -307,7 +307,8 @@ def test_gemm_backends_agree(cuda, lib):
     assert e_tc < (2e-6 + BIAS_PER_K[0] * K) * scale and e_mma < 2e-6 * scale, (e_tc / scale, e_mma / scale)
 
 
-@pytest.mark.parametrize("M,K,N1,N2", [(512, 512, 512, 256), (8192, 1024, 1024, 1600), (4096 + 77, 528, 1088, 512), (65536, 256, 1024, 1024)])
+@pytest.mark.parametrize("M,K,N1,N2", [(512, 512, 512, 256), (8192, 1024, 1024, 1600), (4096 + 77, 528, 1088, 512), (65536, 256, 1024, 1024),
+                                       (333, 256, 128, 128), (1024, 128, 128, 128)])
 @pytest.mark.parametrize("a_scale", [1.0, 2e-6])
 def test_gemm_presplit_handover(cuda, lib, M, K, N1, N2, a_scale):
     """Two chained dense layers as the MLP runs them: the first epilogue writes its result as fp32 AND as the pre-split
