@@ -439,9 +439,9 @@ int mfm_fm_loss_grad_part(const mfm_field_t* f, const mfm_target_t* t, const uin
     Workspace w(ws, ws_bytes);
     FmBufs M;
     if (!fm_take(M, w, *f, n, t)) { mfm_set_last_error_msg("workspace too small (mfm_fm_loss_grad)"); return MFM_ERR_WORKSPACE; }
-    float* xt_amax = mfm::tc2h::gemm_h16() ? M.B.amax + AM_X : nullptr;
+    float* xt_amax = (mfm::tc2h::gemm_h16() && M.B.amax) ? M.B.amax + AM_X : nullptr;
     if (part != 2) {
-        MFM_CUDA_CHECK(cudaMemsetAsync(M.B.amax + AM_EVAL_END, 0, (AM_POOL - AM_EVAL_END) * sizeof(float), stream));   // this pass's maxima
+        if (M.B.amax) MFM_CUDA_CHECK(cudaMemsetAsync(M.B.amax + AM_EVAL_END, 0, (AM_POOL - AM_EVAL_END) * sizeof(float), stream));   // this pass's maxima
         fm_batch_kernel<<<ceil_div(n, 8), 256, 0, stream>>>(rng_key, n, chain_offset, n_total, f->dim, sigma, f->ref_mean, f->ref_std,
                                                              positions, M.times, M.xt, M.target, xt_amax, rng_x64());
         MFM_LAUNCH_CHECK();
@@ -462,8 +462,8 @@ int mfm_fm_loss_grad_uncond(const mfm_field_t* f, const mfm_target_t* t, const u
     Workspace w(ws, ws_bytes);
     FmBufs M;
     if (!fm_take(M, w, *f, n, t)) { mfm_set_last_error_msg("workspace too small (mfm_fm_loss_grad_uncond)"); return MFM_ERR_WORKSPACE; }
-    float* xt_amax = mfm::tc2h::gemm_h16() ? M.B.amax + AM_X : nullptr;
-    MFM_CUDA_CHECK(cudaMemsetAsync(M.B.amax + AM_EVAL_END, 0, (AM_POOL - AM_EVAL_END) * sizeof(float), stream));
+    float* xt_amax = (mfm::tc2h::gemm_h16() && M.B.amax) ? M.B.amax + AM_X : nullptr;
+    if (M.B.amax) MFM_CUDA_CHECK(cudaMemsetAsync(M.B.amax + AM_EVAL_END, 0, (AM_POOL - AM_EVAL_END) * sizeof(float), stream));
     fm_batch_uncond_kernel<<<ceil_div(n, 8), 256, 0, stream>>>(rng_key, n, chain_offset, n_total, f->dim, sigma, positions,
                                                                 M.times, M.xt, M.target, xt_amax, rng_x64());
     MFM_LAUNCH_CHECK();
@@ -485,7 +485,7 @@ int mfm_fm_loss_grad_from_batch(const mfm_field_t* f, const mfm_target_t* t, int
     MFM_CUDA_CHECK(cudaMemcpyAsync(M.xt, xt, nd, cudaMemcpyDeviceToDevice, stream));
     MFM_CUDA_CHECK(cudaMemcpyAsync(M.target, target_v, nd, cudaMemcpyDeviceToDevice, stream));
     MFM_CUDA_CHECK(cudaMemcpyAsync(M.times, times, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, stream));
-    MFM_CUDA_CHECK(cudaMemsetAsync(M.B.amax + AM_EVAL_END, 0, (AM_POOL - AM_EVAL_END) * sizeof(float), stream));
+    if (M.B.amax) MFM_CUDA_CHECK(cudaMemsetAsync(M.B.amax + AM_EVAL_END, 0, (AM_POOL - AM_EVAL_END) * sizeof(float), stream));
     return fm_forward_backward(*f, *t, n, M, loss_out, grads, stream, 0);     // the caller's x_t: field_eval reduces its maximum
 }
 

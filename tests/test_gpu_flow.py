@@ -65,6 +65,21 @@ def test_field_and_divergence(cuda, setups, name):
     assert np.abs(div.cpu().numpy() - div_ref).max() < 1e-4 * max(np.abs(div_ref).max(), 1.0), name
 
 
+@pytest.mark.parametrize("name,n", [("4-mode", 333), ("gmm16", 333), ("gmm16", 512), ("phi-four", 300)])
+def test_field_and_divergence_tensor_core_rows(cuda, setups, name, n):
+    """>= 256 rows: the dense layers run on the tcgen05 kernel and hand their outputs over pre-split (d = 2: max |x| is not
+    tracked, Dense_2 writes no copy and Dense_3 must split h2 itself; d = 16: Dense_2 runs on mma.sync and writes the copy from
+    its scalar epilogue; 333 / 300 rows: a partial last tile)."""
+    s = setups[name]
+    x = _positions(s, n, seed=3)
+    t = np.linspace(0.0, 1.0, n)
+    z = np.random.default_rng(6).standard_normal(x.shape) if s.hutch else None
+    v_ref, div_ref = VF.field_and_div(s.params, s.omega, x, t, s.ot, z, s.clip)
+    v, div = s.model.apply(s.P, to_dev(x, cuda), to_dev(t, cuda), to_dev(z, cuda) if s.hutch else None, hutch=s.hutch, want_div=True)
+    assert rel_err(v.cpu().numpy(), v_ref) < 1e-4, name
+    assert np.abs(div.cpu().numpy() - div_ref).max() < 1e-4 * max(np.abs(div_ref).max(), 1.0), name
+
+
 @pytest.mark.parametrize("name", list(CFG))
 def test_roundtrip_param_dict(cuda, setups, name):
     s = setups[name]
