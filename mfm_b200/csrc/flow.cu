@@ -112,17 +112,24 @@ int dense(int n, int in, int out, const float* A, long long lda, const float* WT
                  const int* n_rows_dev, DenseAmax am) {
     GemmShape p{n, out, in, A, lda, WT, ldwt, n_rows_dev};
     p.a_amax = am.a; p.a_amax2 = am.a2; p.a_bound = am.a_bound; p.a_split = am.a_split; p.a_scale_src = am.a_scale_src;
+    const bool general = relu > ACT_RELU || am.dact != nullptr || am.mask_mul != 0;     // activations other than relu: the ACT = true functors
     if (am.out_split && am.w_norm && (am.a || am.a_bound > 0.0f)) {
         // C also leaves pre-split for the layer that consumes it (EpiStdS)
-        EpiStdS e{C, ldc, bias, mask, ldm, nullptr, 0, relu, mask_div, am.out_split, am.a, am.a2, am.a_bound, am.w_norm, am.bias_amax, am.add_bound, am.out_bound};
-        e.alt_amax = am.alt_amax; e.alt_w_norm = am.alt_w_norm; e.alt_bias = am.alt_bias;
-        e.amax_out = am.out; e.dact = am.dact; e.lddact = am.lddact; e.mask_mul = am.mask_mul;
-        MFM_CUDA_CHECK((launch_gemm<true, false>(p, e, st)));
+        auto run = [&](auto e) -> cudaError_t {
+            e.alt_amax = am.alt_amax; e.alt_w_norm = am.alt_w_norm; e.alt_bias = am.alt_bias;
+            e.amax_out = am.out; e.dact = am.dact; e.lddact = am.lddact; e.mask_mul = am.mask_mul;
+            return launch_gemm<true, false>(p, e, st);
+        };
+        if (general) MFM_CUDA_CHECK(run(EpiStdSA{C, ldc, bias, mask, ldm, nullptr, 0, relu, mask_div, am.out_split, am.a, am.a2, am.a_bound, am.w_norm, am.bias_amax, am.add_bound, am.out_bound}));
+        else MFM_CUDA_CHECK(run(EpiStdS{C, ldc, bias, mask, ldm, nullptr, 0, relu, mask_div, am.out_split, am.a, am.a2, am.a_bound, am.w_norm, am.bias_amax, am.add_bound, am.out_bound}));
         return MFM_OK;
     }
-    EpiStd e{C, ldc, bias, mask, ldm, nullptr, 0, 1.0f, relu, mask_div};
-    e.amax_out = am.out; e.dact = am.dact; e.lddact = am.lddact; e.mask_mul = am.mask_mul;
-    MFM_CUDA_CHECK((launch_gemm<true, false>(p, e, st)));
+    auto run = [&](auto e) -> cudaError_t {
+        e.amax_out = am.out; e.dact = am.dact; e.lddact = am.lddact; e.mask_mul = am.mask_mul;
+        return launch_gemm<true, false>(p, e, st);
+    };
+    if (general) MFM_CUDA_CHECK(run(EpiStdA{C, ldc, bias, mask, ldm, nullptr, 0, 1.0f, relu, mask_div}));
+    else MFM_CUDA_CHECK(run(EpiStd{C, ldc, bias, mask, ldm, nullptr, 0, 1.0f, relu, mask_div}));
     return MFM_OK;
 }
 

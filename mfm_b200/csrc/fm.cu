@@ -7,6 +7,7 @@
 //   optax chain in create_train_state        :129-137, :184   [restated in oracle/optim.py]
 #include "internal.h"
 #include "gemm_tf32x3.cuh"
+#include "gemm_tcgen05_wgrad16.cuh"
 
 namespace mfm {
 
@@ -154,12 +155,18 @@ __global__ void splitk_reduce_kernel(long long count, int splits, long long stri
     out[i] = s;
 }
 
-// dW[in,out] = A^T[in,n] * D[n,out]  (A stored [n,in], lda), split over the batch dimension.
+// split16 copies of a weight gradient's two operands and the device floats their scales came from (all four or none)
+struct WgradSplit { const float* a_s = nullptr; const float* a_src = nullptr; const float* g_s = nullptr; const float* g_src = nullptr; };
+
+// dW[in,out] = A^T[in,n] * D[n,out]  (A stored [n,in], lda), split over the batch dimension.  With the operands' split16
+// copies at hand (ws) the product runs on three fp16 tensor-core passes (gemm_tcgen05_wgrad16.cuh), else on 3xTF32.
 static int wgrad(int n, int in, int out, const float* A, long long lda, const float* D, long long ldd, float* dW,
-                 float* splitbuf, size_t splitbuf_floats, cudaStream_t st) {
-    // wave-aware split of the batch (reduction) dimension: fill the 148 SMs with whole waves
+                 float* splitbuf, size_t splitbuf_floats, cudaStream_t st, WgradSplit ws = WgradSplit()) {
     GemmShape probe{in, out, n, A, lda, D, ldd, nullptr};
-    const int path = gemm_path<false, true>(probe);                // 2 = CTA pair, 1 = single CTA, 0 = mma.sync
+    GemmShape p16{in, out, n, ws.a_s, lda, ws.g_s, ldd, nullptr};
+    const bool h16w = ws.a_s && ws.a_src && ws.g_s && ws.g_src && tc2w::eligible(p16);
+    // wave-aware split of the batch (reduction) dimension: fill the 148 SMs with whole waves
+    const int path = h16w ? 2 : gemm_path<false, true>(probe);     // 2 = CTA pair, 1 = single CTA, 0 = mma.sync
     const long long tiles = path == 2 ? (long long)ceil_div(in, 2 * tc2::BM) * ceil_div(out, tc2::BN)
                           : path == 1 ? (long long)ceil_div(in, tc::BM) * ceil_div(out, tc::BN)
                                       : (long long)ceil_div(in, GBM) * ceil_div(out, GBN);
@@ -175,16 +182,16 @@ static int wgrad(int n, int in, int out, const float* A, long long lda, const fl
         if (eff >= 0.92) { splits = sp; break; }
     }
     if (splits <= 1) {
-        GemmShape p{in, out, n, A, lda, D, ldd, nullptr};
         EpiStd e{dW, (long long)out, nullptr, nullptr, 0, nullptr, 0, 1.0f, 0};
-        MFM_CUDA_CHECK((launch_gemm<false, true>(p, e, st)));
+        if (h16w) MFM_CUDA_CHECK((tc2w::launch(p16, e, ws.a_src, ws.g_src, st)));
+        else MFM_CUDA_CHECK((launch_gemm<false, true>(probe, e, st)));
         return MFM_OK;
     }
     int kper = (n + splits - 1) / splits;
-    kper = (kper + 31) / 32 * 32;                 // multiple of both kernels' k-tile (16 / 32)
-    GemmShape p{in, out, n, A, lda, D, ldd, nullptr, kper};
+    kper = (kper + 63) / 64 * 64;                 // multiple of every kernel's k-tile (16 / 32 / 64)
     EpiStd e{splitbuf, (long long)out, nullptr, nullptr, 0, nullptr, 0, 1.0f, 0, 1, (long long)in * out};
-    MFM_CUDA_CHECK((launch_gemm<false, true>(p, e, st)));
+    if (h16w) { p16.k_split = kper; MFM_CUDA_CHECK((tc2w::launch(p16, e, ws.a_src, ws.g_src, st))); }
+    else { probe.k_split = kper; MFM_CUDA_CHECK((launch_gemm<false, true>(probe, e, st))); }
     const int nz = (n + kper - 1) / kper;
     splitk_reduce_kernel<<<ceil_div((long long)in * out, 256), 256, 0, st>>>((long long)in * out, nz, (long long)in * out, splitbuf, dW);
     MFM_LAUNCH_CHECK();
@@ -196,16 +203,17 @@ static int dgrad(int n, int in, int out, const float* D, long long ldd, const fl
                  const float* mask, long long ldm, const float* add, long long ldadd, cudaStream_t st, DenseAmax am = DenseAmax()) {
     GemmShape p{n, in, out, D, ldd, W, (long long)out, nullptr};
     p.a_amax = am.a; p.a_split = am.a_split; p.a_scale_src = am.a_scale_src;
+    const bool general = am.mask_mul != 0;      // gates are activation derivatives: the ACT = true functors
     if (am.out_split && am.w_norm && am.a) {
         // dX also leaves pre-split for the backward-data layer that consumes it (EpiStdS; the bound uses the kernel's ROW norm)
-        EpiStdS e{dX, ldx, nullptr, mask, ldm, add, ldadd, 0, 1, am.out_split, am.a, nullptr, 0.0f, am.w_norm, nullptr, am.add_bound, am.out_bound};
-        e.amax_out = am.out; e.mask_mul = am.mask_mul;
-        MFM_CUDA_CHECK((launch_gemm<true, false>(p, e, st)));
+        auto run = [&](auto e) -> cudaError_t { e.amax_out = am.out; e.mask_mul = am.mask_mul; return launch_gemm<true, false>(p, e, st); };
+        if (general) MFM_CUDA_CHECK(run(EpiStdSA{dX, ldx, nullptr, mask, ldm, add, ldadd, 0, 1, am.out_split, am.a, nullptr, 0.0f, am.w_norm, nullptr, am.add_bound, am.out_bound}));
+        else MFM_CUDA_CHECK(run(EpiStdS{dX, ldx, nullptr, mask, ldm, add, ldadd, 0, 1, am.out_split, am.a, nullptr, 0.0f, am.w_norm, nullptr, am.add_bound, am.out_bound}));
         return MFM_OK;
     }
-    EpiStd e{dX, ldx, nullptr, mask, ldm, add, ldadd, 1.0f, 0};
-    e.amax_out = am.out; e.mask_mul = am.mask_mul;
-    MFM_CUDA_CHECK((launch_gemm<true, false>(p, e, st)));
+    auto run = [&](auto e) -> cudaError_t { e.amax_out = am.out; e.mask_mul = am.mask_mul; return launch_gemm<true, false>(p, e, st); };
+    if (general) MFM_CUDA_CHECK(run(EpiStdA{dX, ldx, nullptr, mask, ldm, add, ldadd, 1.0f, 0}));
+    else MFM_CUDA_CHECK(run(EpiStd{dX, ldx, nullptr, mask, ldm, add, ldadd, 1.0f, 0}));
     return MFM_OK;
 }
 
@@ -213,6 +221,7 @@ struct FmBufs {
     FieldBufs B;
     float *times, *xt, *target, *v, *delta, *dgt, *d6, *d5, *dcat, *d2, *d0, *blockpart, *splitbuf, *colpart;
     float *d6_s, *d5_s, *dcat_s;      // pre-split copies of the back-propagated signals (A operands of the next backward-data layer)
+    float *d2_s, *d0_s, *xt_s, *delta_s, *dgt_s;   // ... and of the tensors only the weight gradients read in that form
     size_t splitbuf_floats;
 };
 
@@ -230,7 +239,7 @@ static size_t fm_bytes(const mfm_field_t& F, const mfm_target_t& T, int n) {
     const size_t H = F.hidden, d = F.dim, N = n;
     return field_bufs_bytes(F, T, n, true) + ws_slice(N, 4) + ws_slice(N * d, 4) * 5 + ws_slice(N * H, 4) * 4 +
            ws_slice(N * 2 * H, 4) + ws_slice(FM_LOSS_BLOCKS, 4) + ws_slice(fm_splitbuf_floats(F), 4) +
-           ws_slice((size_t)COLSUM_SLABS * (H > d ? H : d), 4) + ws_slice(N * H, 4) * 2 + ws_slice(N * 2 * H, 4) + 1024;
+           ws_slice((size_t)COLSUM_SLABS * (H > d ? H : d), 4) + ws_slice(N * H, 4) * 4 + ws_slice(N * 2 * H, 4) + ws_slice(N * d, 4) * 3 + 1024;
 }
 
 static bool fm_take(FmBufs& M, Workspace& w, const mfm_field_t& F, int n, const mfm_target_t* T) {
@@ -246,6 +255,8 @@ static bool fm_take(FmBufs& M, Workspace& w, const mfm_field_t& F, int n, const 
     M.splitbuf_floats = fm_splitbuf_floats(F);
     M.splitbuf = w.take<float>(M.splitbuf_floats);
     M.d6_s = w.take<float>(N * H); M.d5_s = w.take<float>(N * H); M.dcat_s = w.take<float>(N * 2 * H);
+    M.d2_s = w.take<float>(N * H); M.d0_s = w.take<float>(N * H);
+    M.xt_s = w.take<float>(N * d); M.delta_s = w.take<float>(N * d); M.dgt_s = w.take<float>(N * d);
     return w.ok;
 }
 
@@ -266,6 +277,14 @@ static int fm_forward_backward(const mfm_field_t& F, const mfm_target_t& T, int 
     // tensor maxima of the backward pass (AmaxSlot; null when the scaled-fp16 GEMM is off)
     float* am = tc2h::gemm_h16() ? B.amax : nullptr;
     auto slot = [&](int i) -> float* { return am ? am + i : nullptr; };
+    // weight gradients from the split16 copies (gemm_tcgen05_wgrad16.cuh): same conditions as the copies' producers
+    static const bool no_wsplit = getenv("MFM_H16_NOWGRAD") != nullptr;
+    static const bool no_split = getenv("MFM_H16_NOSPLIT") != nullptr;
+    const bool wsp = !no_wsplit && !no_split && am != nullptr && M.d6_s != nullptr && B.h0_s != nullptr && H % 16 == 0 && (2 * Fd) % 16 == 0 && n >= 256 &&
+                     ((reinterpret_cast<uintptr_t>(B.h0_s) | reinterpret_cast<uintptr_t>(B.cat_s)) & 63) == 0;
+    const bool wspd = wsp && d % 16 == 0;      // the [n, d] operands have copies too
+    // max |x_t|: the batch kernel's slot, or the one field_eval reduces into when d is a multiple of 16 (else untracked: no h2 copy)
+    const float* xa_src = xt_amax ? xt_amax : (d % 16 == 0 ? slot(AM_X) : nullptr);
     if (part != 2) {
         MFM_CUDA_CHECK(cudaMemsetAsync(grads, 0, (size_t)F.n_params * sizeof(float), st));
         if ((rc = field_prepare_weights(F, B, st))) return rc;
@@ -276,6 +295,13 @@ static int fm_forward_backward(const mfm_field_t& F, const mfm_target_t& T, int 
         MFM_LAUNCH_CHECK();
         final_sum_kernel<<<1, 256, 0, st>>>(lb, M.blockpart, loss_out);
         MFM_LAUNCH_CHECK();
+        // split16 copies of the [n, d] operands of the weight gradients of layers 2, 7 and 4 (their maxima are exact only now:
+        // one element-wise pass each, 8 B per element)
+        if (wspd) {
+            if ((rc = presplit_weights(M.xt, M.xt_s, tot, xa_src, st))) return rc;
+            if ((rc = presplit_weights(M.delta, M.delta_s, tot, slot(AM_DELTA), st))) return rc;
+            if ((rc = presplit_weights(M.dgt, M.dgt_s, tot, slot(AM_DGT), st))) return rc;
+        }
     }
     auto bias_grad = [&](const float* a, long long lda, int cols, float* out) -> int {
         const int slabs = n >= 8 * COLSUM_SLABS ? COLSUM_SLABS : 1;
@@ -301,17 +327,20 @@ static int fm_forward_backward(const mfm_field_t& F, const mfm_target_t& T, int 
     const bool dmul = F.act != MFM_ACT_RELU;
     const float* g_h0 = dmul ? B.dh0 : B.h0; const float* g_h2 = dmul ? B.dh2 : B.h2; const float* g_cat = dmul ? B.dcat : B.cat;
     const float* g_h5 = dmul ? B.dh5 : B.h5; const float* g_h6 = dmul ? B.dh6 : B.h6;
+    auto WS_ = [&](bool on, const float* a_s, const float* a_src, const float* g_s, const float* g_src) {
+        WgradSplit w; if (on) { w.a_s = a_s; w.a_src = a_src; w.g_s = g_s; w.g_src = g_src; } return w;
+    };
     if (part != 2) {
     // layer 7 (nn_xt head): y = h6 W7 + b7
-    if ((rc = wgrad(n, H, d, B.h6, H, M.delta, d, GW_(7), sb, sbf, st))) return rc;
+    if ((rc = wgrad(n, H, d, B.h6, H, M.delta, d, GW_(7), sb, sbf, st, WS_(wspd, B.h6_s, BD(AM_H6), M.delta_s, slot(AM_DELTA))))) return rc;
     if ((rc = bias_grad(M.delta, d, d, GB_(7)))) return rc;
     if ((rc = dgrad(n, H, d, M.delta, d, W_(7), M.d6, H, g_h6, H, nullptr, 0, st, G_(slot(AM_DELTA), nullptr, nullptr, slot(AM_D6), M.d6_s, AM_D6, 7, nullptr)))) return rc;
     // layer 6
-    if ((rc = wgrad(n, H, H, B.h5, H, M.d6, H, GW_(6), sb, sbf, st))) return rc;
+    if ((rc = wgrad(n, H, H, B.h5, H, M.d6, H, GW_(6), sb, sbf, st, WS_(wsp, B.h5_s, BD(AM_H5), M.d6_s, BD(AM_D6))))) return rc;
     if ((rc = bias_grad(M.d6, H, H, GB_(6)))) return rc;
     if ((rc = dgrad(n, H, H, M.d6, H, W_(6), M.d5, H, g_h5, H, nullptr, 0, st, G_(slot(AM_D6), M.d6_s, BD(AM_D6), slot(AM_D5), M.d5_s, AM_D5, 6, nullptr)))) return rc;
     // layer 5 (joint, input cat = [s_x | s_t])
-    if ((rc = wgrad(n, 2 * H, H, B.cat, 2 * H, M.d5, H, GW_(5), sb, sbf, st))) return rc;
+    if ((rc = wgrad(n, 2 * H, H, B.cat, 2 * H, M.d5, H, GW_(5), sb, sbf, st, WS_(wsp, B.cat_s, BD(AM_SX), M.d5_s, BD(AM_D5))))) return rc;
     if ((rc = bias_grad(M.d5, H, H, GB_(5)))) return rc;
     // d s_x = (d5 W5[:H]^T) * relu'(s_x)
     if ((rc = dgrad(n, H, H, M.d5, H, W_(5), M.dcat, 2 * H, g_cat, 2 * H, nullptr, 0, st, G_(slot(AM_D5), M.d5_s, BD(AM_D5), slot(AM_DCX), M.dcat_s, AM_DCX, 5, nullptr)))) return rc;
@@ -319,7 +348,7 @@ static int fm_forward_backward(const mfm_field_t& F, const mfm_target_t& T, int 
     if ((rc = dgrad(n, H, H, M.d5, H, W_(5) + (long long)H * H, M.dcat + H, 2 * H, nullptr, 0, nullptr, 0, st,
                     G_(slot(AM_D5), M.d5_s, BD(AM_D5), nullptr, M.dcat_s + H, AM_DCT0, 5, nullptr)))) return rc;
     // layer 4 (nn_t head): g_t = s_t W4 + b4, dL/dg_t = delta * clip(grad logprob)
-    if ((rc = wgrad(n, H, d, B.cat + H, 2 * H, M.dgt, d, GW_(4), sb, sbf, st))) return rc;
+    if ((rc = wgrad(n, H, d, B.cat + H, 2 * H, M.dgt, d, GW_(4), sb, sbf, st, WS_(wspd, B.cat_s + H, BD(AM_ST), M.dgt_s, slot(AM_DGT))))) return rc;
     if ((rc = bias_grad(M.dgt, d, d, GB_(4)))) return rc;
     // d s_t = (dgt W4^T + joint part) * relu'(s_t)   (in place)
     if ((rc = dgrad(n, H, d, M.dgt, d, W_(4), M.dcat + H, 2 * H, g_cat + H, 2 * H, M.dcat + H, 2 * H, st,
@@ -327,18 +356,18 @@ static int fm_forward_backward(const mfm_field_t& F, const mfm_target_t& T, int 
     }
     if (part == 1) return MFM_OK;
     // layer 3 (x branch)
-    if ((rc = wgrad(n, H, H, B.h2, H, M.dcat, 2 * H, GW_(3), sb, sbf, st))) return rc;
+    if ((rc = wgrad(n, H, H, B.h2, H, M.dcat, 2 * H, GW_(3), sb, sbf, st, WS_(wsp && xa_src, B.h2_s, BD(AM_H2), M.dcat_s, BD(AM_DCX))))) return rc;
     if ((rc = bias_grad(M.dcat, 2 * H, H, GB_(3)))) return rc;
-    if ((rc = dgrad(n, H, H, M.dcat, 2 * H, W_(3), M.d2, H, g_h2, H, nullptr, 0, st, G_(slot(AM_DCX), M.dcat_s, BD(AM_DCX), slot(AM_D2), nullptr, 0, 0, nullptr)))) return rc;
+    if ((rc = dgrad(n, H, H, M.dcat, 2 * H, W_(3), M.d2, H, g_h2, H, nullptr, 0, st, G_(slot(AM_DCX), M.dcat_s, BD(AM_DCX), slot(AM_D2), wsp ? M.d2_s : nullptr, AM_D2, 3, nullptr)))) return rc;
     // layer 2
-    if ((rc = wgrad(n, d, H, M.xt, d, M.d2, H, GW_(2), sb, sbf, st))) return rc;
+    if ((rc = wgrad(n, d, H, M.xt, d, M.d2, H, GW_(2), sb, sbf, st, WS_(wspd && xa_src, M.xt_s, xa_src, M.d2_s, BD(AM_D2))))) return rc;
     if ((rc = bias_grad(M.d2, H, H, GB_(2)))) return rc;
     // layer 1 (time branch)
-    if ((rc = wgrad(n, H, H, B.h0, H, M.dcat + H, 2 * H, GW_(1), sb, sbf, st))) return rc;
+    if ((rc = wgrad(n, H, H, B.h0, H, M.dcat + H, 2 * H, GW_(1), sb, sbf, st, WS_(wsp, B.h0_s, BD(AM_H0), M.dcat_s + H, BD(AM_DCT))))) return rc;
     if ((rc = bias_grad(M.dcat + H, 2 * H, H, GB_(1)))) return rc;
-    if ((rc = dgrad(n, H, H, M.dcat + H, 2 * H, W_(1), M.d0, H, g_h0, H, nullptr, 0, st, G_(slot(AM_DCT), M.dcat_s + H, BD(AM_DCT), slot(AM_D0), nullptr, 0, 0, nullptr)))) return rc;
+    if ((rc = dgrad(n, H, H, M.dcat + H, 2 * H, W_(1), M.d0, H, g_h0, H, nullptr, 0, st, G_(slot(AM_DCT), M.dcat_s + H, BD(AM_DCT), slot(AM_D0), wsp ? M.d0_s : nullptr, AM_D0, 1, nullptr)))) return rc;
     // layer 0
-    if ((rc = wgrad(n, 2 * Fd, H, B.ff, 2 * Fd, M.d0, H, GW_(0), sb, sbf, st))) return rc;
+    if ((rc = wgrad(n, 2 * Fd, H, B.ff, 2 * Fd, M.d0, H, GW_(0), sb, sbf, st, WS_(wsp, B.ff_s, BD(AM_FF), M.d0_s, BD(AM_D0))))) return rc;
     if ((rc = bias_grad(M.d0, H, H, GB_(0)))) return rc;
     return MFM_OK;
 }
@@ -511,3 +540,26 @@ int mfm_adamw_step(float* params, const float* grads, float* mu, float* nu, cons
 }
 
 }  // extern "C"
+
+/* Test hook of the scaled-fp16 weight-gradient kernel (not in the ABI header): dW[in,out] = A^T G with A [n,in], G [n,out];
+ * a_s / g_s: scratch for the split16 copies (same sizes), slots: device float[2] receiving max|A|, max|G|;
+ * use_split = 0 runs the 3xTF32 path on the fp32 operands instead. */
+extern "C" int mfm_debug_wgrad16(int n, int in, int out, const float* A, const float* G, float* dW, float* a_s, float* g_s, float* slots,
+                                 float* splitbuf, long long splitbuf_floats, int use_split, mfm_stream_t stream) {
+    using namespace mfm;
+    WgradSplit ws;
+    if (use_split) {
+        if (in % 16 || out % 16) { mfm_set_last_error_msg("mfm_debug_wgrad16: in / out must be multiples of 16"); return MFM_ERR_ARG; }
+        if (use_split == 1) {            // (2: the copies are already there - timing runs)
+            MFM_CUDA_CHECK(tc2h::launch_absmax(A, in, n, in, nullptr, slots, stream));
+            MFM_CUDA_CHECK(tc2h::launch_absmax(G, out, n, out, nullptr, slots + 1, stream));
+            int rc;
+            if ((rc = presplit_weights(A, a_s, (long long)n * in, slots, stream))) return rc;
+            if ((rc = presplit_weights(G, g_s, (long long)n * out, slots + 1, stream))) return rc;
+        }
+        ws.a_s = a_s; ws.a_src = slots; ws.g_s = g_s; ws.g_src = slots + 1;
+        GemmShape p16{in, out, n, a_s, (long long)in, g_s, (long long)out, nullptr};
+        if (!tc2w::eligible(p16)) { mfm_set_last_error_msg("mfm_debug_wgrad16: shape not eligible for the fp16 kernel"); return MFM_ERR_UNSUPPORTED; }
+    }
+    return wgrad(n, in, out, A, in, G, out, dW, splitbuf, (size_t)splitbuf_floats, stream, ws);
+}

@@ -295,7 +295,11 @@ __device__ __forceinline__ float act_fwd(int act, float v, float& dv) {
 }
 
 // ---- standard epilogue: C = mask(act(alpha*acc + bias) ) (+ add) -----------------------------
-struct EpiStd {
+// ACT = false: relu / no activation and sign-of-the-output gates only (the default configuration: nothing of the general
+// activations' code - transcendental functions, derivative stores, multiplicative gates - reaches the kernels' epilogues, which
+// sit at the register cap); ACT = true: every activation of act_fwd.
+template <bool ACT>
+struct EpiStdT {
     static constexpr bool kRowSum = false;
     float* C; long long ldc;
     const float* bias;               // [N] or null
@@ -319,9 +323,14 @@ struct EpiStd {
     }
     __device__ __forceinline__ float apply(int row, int col, float acc, const Aux& a) const {
         float v = alpha * acc + a.bias + a.add;
-        if (relu == ACT_RELU) v = fmaxf(v, 0.0f);
-        else if (relu) { float dv; v = act_fwd(relu, v, dv); if (dact) dact[(long long)row * lddact + col] = dv; }
-        v = mask_mul ? v * a.mask : (a.mask > 0.0f ? v : 0.0f);
+        if constexpr (ACT) {
+            if (relu == ACT_RELU) v = fmaxf(v, 0.0f);
+            else if (relu) { float dv; v = act_fwd(relu, v, dv); if (dact) dact[(long long)row * lddact + col] = dv; }
+            v = mask_mul ? v * a.mask : (a.mask > 0.0f ? v : 0.0f);
+        } else {
+            if (relu) v = fmaxf(v, 0.0f);
+            v = a.mask > 0.0f ? v : 0.0f;
+        }
         C[(long long)row * ldc + col] = v;
         vmax = fmaxf(vmax, fabsf(v));
         return 0.0f;
@@ -346,13 +355,15 @@ struct EpiStd {
         float4 v;
         v.x = alpha * acc.x + c.bias.x + r.add.x; v.y = alpha * acc.y + c.bias.y + r.add.y;
         v.z = alpha * acc.z + c.bias.z + r.add.z; v.w = alpha * acc.w + c.bias.w + r.add.w;
-        if (relu == ACT_RELU) { v.x = fmaxf(v.x, 0.0f); v.y = fmaxf(v.y, 0.0f); v.z = fmaxf(v.z, 0.0f); v.w = fmaxf(v.w, 0.0f); }
-        else if (relu) {
-            float4 dv;
-            v.x = act_fwd(relu, v.x, dv.x); v.y = act_fwd(relu, v.y, dv.y); v.z = act_fwd(relu, v.z, dv.z); v.w = act_fwd(relu, v.w, dv.w);
-            if (dact) st4(dact + (long long)row * lddact + col, dv);
-        }
-        if (mask_mul) { v.x *= r.mask.x; v.y *= r.mask.y; v.z *= r.mask.z; v.w *= r.mask.w; }
+        if constexpr (ACT) {
+            if (relu == ACT_RELU) { v.x = fmaxf(v.x, 0.0f); v.y = fmaxf(v.y, 0.0f); v.z = fmaxf(v.z, 0.0f); v.w = fmaxf(v.w, 0.0f); }
+            else if (relu) {
+                float4 dv;
+                v.x = act_fwd(relu, v.x, dv.x); v.y = act_fwd(relu, v.y, dv.y); v.z = act_fwd(relu, v.z, dv.z); v.w = act_fwd(relu, v.w, dv.w);
+                if (dact) st4(dact + (long long)row * lddact + col, dv);
+            }
+        } else if (relu) { v.x = fmaxf(v.x, 0.0f); v.y = fmaxf(v.y, 0.0f); v.z = fmaxf(v.z, 0.0f); v.w = fmaxf(v.w, 0.0f); }
+        if (ACT && mask_mul) { v.x *= r.mask.x; v.y *= r.mask.y; v.z *= r.mask.z; v.w *= r.mask.w; }
         else {
             v.x = r.mask.x > 0.0f ? v.x : 0.0f; v.y = r.mask.y > 0.0f ? v.y : 0.0f;
             v.z = r.mask.z > 0.0f ? v.z : 0.0f; v.w = r.mask.w > 0.0f ? v.w : 0.0f;
@@ -362,6 +373,8 @@ struct EpiStd {
         return 0.0f;
     }
 };
+using EpiStd = EpiStdT<false>;
+using EpiStdA = EpiStdT<true>;
 
 
 // ---- EpiStd that ALSO writes C as the pre-split A operand of the next scaled-fp16 GEMM ----------------------------------------
@@ -400,7 +413,8 @@ __host__ __device__ __forceinline__ uint32_t h16_scale_exp_(float amax) {     //
     se = se < 2 ? 2 : (se > 252 ? 252 : se);
     return (uint32_t)se;
 }
-struct EpiStdS {
+template <bool ACT>
+struct EpiStdST {
     static constexpr bool kRowSum = false;
     float* C; long long ldc;
     const float* bias; const float* mask; long long ldm; const float* add; long long ldadd; int relu; int mask_div;
@@ -439,9 +453,14 @@ struct EpiStdS {
     }
     __device__ __forceinline__ float apply(int row, int col, float acc, const Aux& a) const {
         float v = acc + a.bias + a.add;
-        if (relu == ACT_RELU) v = fmaxf(v, 0.0f);
-        else if (relu) { float dv; v = act_fwd(relu, v, dv); if (dact) dact[(long long)row * lddact + col] = dv; }
-        v = mask_mul ? v * a.mask : (a.mask > 0.0f ? v : 0.0f);
+        if constexpr (ACT) {
+            if (relu == ACT_RELU) v = fmaxf(v, 0.0f);
+            else if (relu) { float dv; v = act_fwd(relu, v, dv); if (dact) dact[(long long)row * lddact + col] = dv; }
+            v = mask_mul ? v * a.mask : (a.mask > 0.0f ? v : 0.0f);
+        } else {
+            if (relu) v = fmaxf(v, 0.0f);
+            v = a.mask > 0.0f ? v : 0.0f;
+        }
         C[(long long)row * ldc + col] = v;
         vmax = fmaxf(vmax, fabsf(v));
         const float x = v * a.scale;
@@ -469,13 +488,15 @@ struct EpiStdS {
         float4 v;
         v.x = acc.x + c.bias.x + r.add.x; v.y = acc.y + c.bias.y + r.add.y;
         v.z = acc.z + c.bias.z + r.add.z; v.w = acc.w + c.bias.w + r.add.w;
-        if (relu == ACT_RELU) { v.x = fmaxf(v.x, 0.0f); v.y = fmaxf(v.y, 0.0f); v.z = fmaxf(v.z, 0.0f); v.w = fmaxf(v.w, 0.0f); }
-        else if (relu) {
-            float4 dv;
-            v.x = act_fwd(relu, v.x, dv.x); v.y = act_fwd(relu, v.y, dv.y); v.z = act_fwd(relu, v.z, dv.z); v.w = act_fwd(relu, v.w, dv.w);
-            if (dact) st4(dact + (long long)row * lddact + col, dv);
-        }
-        if (mask_mul) { v.x *= r.mask.x; v.y *= r.mask.y; v.z *= r.mask.z; v.w *= r.mask.w; }
+        if constexpr (ACT) {
+            if (relu == ACT_RELU) { v.x = fmaxf(v.x, 0.0f); v.y = fmaxf(v.y, 0.0f); v.z = fmaxf(v.z, 0.0f); v.w = fmaxf(v.w, 0.0f); }
+            else if (relu) {
+                float4 dv;
+                v.x = act_fwd(relu, v.x, dv.x); v.y = act_fwd(relu, v.y, dv.y); v.z = act_fwd(relu, v.z, dv.z); v.w = act_fwd(relu, v.w, dv.w);
+                if (dact) st4(dact + (long long)row * lddact + col, dv);
+            }
+        } else if (relu) { v.x = fmaxf(v.x, 0.0f); v.y = fmaxf(v.y, 0.0f); v.z = fmaxf(v.z, 0.0f); v.w = fmaxf(v.w, 0.0f); }
+        if (ACT && mask_mul) { v.x *= r.mask.x; v.y *= r.mask.y; v.z *= r.mask.z; v.w *= r.mask.w; }
         else {
             v.x = r.mask.x > 0.0f ? v.x : 0.0f; v.y = r.mask.y > 0.0f ? v.y : 0.0f;
             v.z = r.mask.z > 0.0f ? v.z : 0.0f; v.w = r.mask.w > 0.0f ? v.w : 0.0f;
@@ -492,6 +513,8 @@ struct EpiStdS {
         return 0.0f;
     }
 };
+using EpiStdS = EpiStdST<false>;
+using EpiStdSA = EpiStdST<true>;
 
 }  // namespace mfm
 

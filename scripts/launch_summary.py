@@ -1,51 +1,35 @@
-"""Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list: per-kernel totals and the
-kernel sequence of one FM update / one MALA iteration / the flow-MH iteration.
-usage: python scripts/launch_summary.py gpurun_out/launches.csv [--phase]"""
-import collections
-import csv
-import re
-import sys
-
-
+"""Summarise an ncu launch list (--metrics gpu__time_duration.sum --csv): per kernel count, total, mean, share.
+usage: python scripts/launch_summary.py gpurun_out/launches.csv [other.csv to compare]"""
+import csv, re, sys, collections
 def load(path):
-    lines = [l for l in open(path) if not l.startswith("==")]
     rows = []
-    for x in csv.DictReader(lines):
-        rows.append((int(x["ID"]), x["Kernel Name"], x["Grid Size"], float(x["Metric Value"])))
+    with open(path, newline="") as fh:
+        lines = [l for l in fh if not l.startswith("==")]
+    rd = csv.DictReader(lines)
+    for r in rd:
+        if r.get("Metric Name") != "gpu__time_duration.sum": continue
+        v = float(r["Metric Value"].replace(",", "")); u = r["Metric Unit"]
+        us = v / 1000.0 if u in ("ns", "nsecond") else (v if u in ("us", "usecond") else v * 1000.0)
+        name = r["Kernel Name"]
+        rows.append((name, us))
     return rows
-
-
-def short(name):
-    name = re.sub(r"^void ", "", name)
-    m = re.match(r"([\w:]+)<([^>]*?)mfm::(\w+)>", name)
-    if m:
-        flags = ",".join(re.findall(r"\b(\d)\b", m.group(2)))
-        return f"{m.group(1).split('::')[-1]}<{flags},{m.group(3)}>"
-    return re.sub(r"\(.*", "", name).split("::")[-1][:48]
-
-
-def table(rows, title):
+def short(n):
+    n = re.sub(r"\(.*$", "", n)                      # drop the argument list
+    n = n.replace("mfm::", "").replace("(bool)", "")
+    return n[:110]
+def summarise(rows):
     agg = collections.OrderedDict()
-    for _, k, _, t in rows:
-        a = agg.setdefault(short(k), [0, 0.0]); a[0] += 1; a[1] += t
-    tot = sum(v[1] for v in agg.values())
-    print(f"\n{title}: {len(rows)} launches, {tot / 1e6:.2f} ms")
-    print("| kernel | launches | total ms | share | avg us |\n|---|---:|---:|---:|---:|")
-    for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-        print(f"| `{k}` | {v[0]} | {v[1] / 1e6:.2f} | {100 * v[1] / tot:.1f}% | {v[1] / v[0] / 1e3:.1f} |")
-
-
-def main():
-    rows = load(sys.argv[1])
-    table(rows, "all launches")
-    fm = [i for i, r in enumerate(rows) if "fm_batch" in r[1]]
-    if len(fm) >= 2 and "--phase" in sys.argv:
-        # last complete outer iteration = FM update followed by the data generator of the next one
-        table(rows[fm[-2]:fm[-1]], "one FM update + the following data-generator call (last complete pair)")
-        gaps = [fm[i + 1] - fm[i] for i in range(len(fm) - 1)]
-        big = max(range(len(gaps)), key=lambda i: gaps[i])
-        table(rows[fm[big]:fm[big + 1]], "the FM update followed by the flow-MH iteration")
-
-
-if __name__ == "__main__":
-    main()
+    for n, us in rows:
+        a = agg.setdefault(short(n), [0, 0.0]); a[0] += 1; a[1] += us
+    return agg
+a = summarise(load(sys.argv[1]))
+b = summarise(load(sys.argv[2])) if len(sys.argv) > 2 else None
+tot = sum(v[1] for v in a.values())
+print(f"# {sys.argv[1]}: {sum(v[0] for v in a.values())} launches, {tot / 1000:.2f} ms of kernel time (serialised, cold-cache ncu replay: shares, not absolutes)")
+print("| kernel | launches | total ms | mean us | share |" + (" other: launches | mean us |" if b else ""))
+print("|---|---:|---:|---:|---:|" + ("---:|---:|" if b else ""))
+for k, (c, t) in sorted(a.items(), key=lambda kv: -kv[1][1]):
+    extra = ""
+    if b is not None:
+        o = b.get(k); extra = f" {o[0]} | {o[1] / o[0]:.1f} |" if o else " - | - |"
+    print(f"| `{k}` | {c} | {t / 1000:.3f} | {t / c:.1f} | {100 * t / tot:.1f} % |{extra}")

@@ -355,3 +355,38 @@ def test_gemm_presplit_handover(cuda, lib, M, K, N1, N2, a_scale):
     assert np.isfinite(hi.astype(np.float32)).all()                                             # no overflow, by construction
     ref2 = c1.astype(np.float64) @ B2t.astype(np.float64).T
     assert np.abs(c2 - ref2).max() <= (1.5e-6 + 6e-9 * N1) * np.abs(ref2).max()
+
+
+@pytest.mark.parametrize("n,inn,out", [(512, 256, 128), (4096, 1024, 1024), (8192, 1600, 1024), (8192 + 77, 1024, 1600), (65536, 2048, 1024),
+                                       (65536, 256, 1024), (1000, 272, 144)])
+@pytest.mark.parametrize("scales", [(1.0, 1.0), (1.0, 3e-7)])
+def test_wgrad_fp16_parts(cuda, lib, n, inn, out, scales):
+    """Weight gradient dW = A^T G from the split16 copies of both operands (csrc/gemm_tcgen05_wgrad16.cuh: MN-major fp16 tiles
+    picked out of the K-major copies by a 4-D TMA map, three tensor-core passes, split-K over the batch) against float64, and
+    against the 3xTF32 kernel it replaces.  Back-propagated signals are tiny (1 / (n d) factors): the second scale set."""
+    import ctypes
+    rng = np.random.default_rng(n + inn + out)
+    A = (np.maximum(rng.standard_normal((n, inn)), 0) * scales[0]).astype(np.float32)       # activations: half zeros
+    G = (rng.standard_normal((n, out)) * scales[1]).astype(np.float32)
+    G[rng.random((n, out)) < 0.3] = 0.0
+    dev = lambda a: torch.from_numpy(a).to(cuda)
+    Ad, Gd = dev(A), dev(G)
+    a_s, g_s = torch.empty_like(Ad), torch.empty_like(Gd)
+    slots = torch.zeros(2, dtype=torch.float32, device=cuda)
+    sb = torch.empty(16 * inn * out, dtype=torch.float32, device=cuda)
+    fn = lib.mfm_debug_wgrad16
+    fn.restype = ctypes.c_int
+    fn.argtypes = [ctypes.c_int] * 3 + [ctypes.c_void_p] * 7 + [ctypes.c_longlong, ctypes.c_int, ctypes.c_void_p]
+    res = {}
+    for use in (1, 0):
+        dW = torch.full((inn, out), float("nan"), dtype=torch.float32, device=cuda)
+        _lib.check(fn(n, inn, out, Ad.data_ptr(), Gd.data_ptr(), dW.data_ptr(), a_s.data_ptr(), g_s.data_ptr(), slots.data_ptr(),
+                      sb.data_ptr(), sb.numel(), use, torch.cuda.current_stream().cuda_stream))
+        res[use] = dW.cpu().numpy()
+    ref = (Ad.double().T @ Gd.double()).cpu().numpy()
+    scale = np.abs(ref).max()
+    e16, e32 = np.abs(res[1] - ref).max() / scale, np.abs(res[0] - ref).max() / scale
+    assert np.isfinite(res[1]).all()
+    # operand rounding 2^-22 per part pair, plus the accumulator's truncation (2.5e-9 per accumulated k, main and cross kept apart)
+    assert e16 <= 1e-6 + 2.5e-9 * min(n, 8192), (e16, e32)
+    assert e16 <= max(2.0 * e32, 2.5e-6), (e16, e32)      # (small shapes: the 3xTF32 reference runs on mma.sync, which rounds to nearest)
