@@ -199,16 +199,31 @@ static int wgrad(int n, int in, int out, const float* A, long long lda, const fl
 }
 
 // dX[n,in] = (D[n,out] * W^T) gated by mask, optionally + add       (W stored [in,out])
+// cs_part (optional): [ceil(n / 32)][in] scratch; when the product runs on the scaled-fp16 kernel its epilogue also leaves the
+// per-32-row column sums of dX there (*cs_done = true) - dX is the back-propagated signal whose column sum is a bias gradient
 static int dgrad(int n, int in, int out, const float* D, long long ldd, const float* W, float* dX, long long ldx,
-                 const float* mask, long long ldm, const float* add, long long ldadd, cudaStream_t st, DenseAmax am = DenseAmax()) {
+                 const float* mask, long long ldm, const float* add, long long ldadd, cudaStream_t st, DenseAmax am = DenseAmax(),
+                 float* cs_part = nullptr, bool* cs_done = nullptr) {
     GemmShape p{n, in, out, D, ldd, W, (long long)out, nullptr};
     p.a_amax = am.a; p.a_split = am.a_split; p.a_scale_src = am.a_scale_src;
     const bool general = am.mask_mul != 0;      // gates are activation derivatives: the ACT = true functors
+    if (cs_done) *cs_done = false;
     if (am.out_split && am.w_norm && am.a) {
         // dX also leaves pre-split for the backward-data layer that consumes it (EpiStdS; the bound uses the kernel's ROW norm)
-        auto run = [&](auto e) -> cudaError_t { e.amax_out = am.out; e.mask_mul = am.mask_mul; return launch_gemm<true, false>(p, e, st); };
+        auto run = [&](auto e) -> cudaError_t {
+            e.amax_out = am.out; e.mask_mul = am.mask_mul;
+            if constexpr (decltype(e)::kColSum) { e.colsum_part = cs_part; e.ldcs = in; }
+            return launch_gemm<true, false>(p, e, st);
+        };
         if (general) MFM_CUDA_CHECK(run(EpiStdSA{dX, ldx, nullptr, mask, ldm, add, ldadd, 0, 1, am.out_split, am.a, nullptr, 0.0f, am.w_norm, nullptr, am.add_bound, am.out_bound}));
-        else MFM_CUDA_CHECK(run(EpiStdS{dX, ldx, nullptr, mask, ldm, add, ldadd, 0, 1, am.out_split, am.a, nullptr, 0.0f, am.w_norm, nullptr, am.add_bound, am.out_bound}));
+        else {
+            EpiStdST<false, true> ec{dX, ldx, nullptr, mask, ldm, add, ldadd, 0, 1, am.out_split, am.a, nullptr, 0.0f, am.w_norm, nullptr, am.add_bound, am.out_bound};
+            if (cs_part && cs_done && tc2h::gemm_h16() && gemm_backend() == 0 && gemm_path<true, false>(p) == 2 && tc2h::eligible(p, ec)) {
+                MFM_CUDA_CHECK(run(ec));
+                *cs_done = true;
+            } else
+                MFM_CUDA_CHECK(run(EpiStdS{dX, ldx, nullptr, mask, ldm, add, ldadd, 0, 1, am.out_split, am.a, nullptr, 0.0f, am.w_norm, nullptr, am.add_bound, am.out_bound}));
+        }
         return MFM_OK;
     }
     auto run = [&](auto e) -> cudaError_t { e.amax_out = am.out; e.mask_mul = am.mask_mul; return launch_gemm<true, false>(p, e, st); };
@@ -221,6 +236,7 @@ struct FmBufs {
     FieldBufs B;
     float *times, *xt, *target, *v, *delta, *dgt, *d6, *d5, *dcat, *d2, *d0, *blockpart, *splitbuf, *colpart;
     float *d6_s, *d5_s, *dcat_s;      // pre-split copies of the back-propagated signals (A operands of the next backward-data layer)
+    float* cspart;                    // [ceil(n / 32)][H] column-sum partials written by the backward-data epilogues
     float *d2_s, *d0_s, *xt_s, *delta_s, *dgt_s;   // ... and of the tensors only the weight gradients read in that form
     size_t splitbuf_floats;
 };
@@ -239,7 +255,7 @@ static size_t fm_bytes(const mfm_field_t& F, const mfm_target_t& T, int n) {
     const size_t H = F.hidden, d = F.dim, N = n;
     return field_bufs_bytes(F, T, n, true) + ws_slice(N, 4) + ws_slice(N * d, 4) * 5 + ws_slice(N * H, 4) * 4 +
            ws_slice(N * 2 * H, 4) + ws_slice(FM_LOSS_BLOCKS, 4) + ws_slice(fm_splitbuf_floats(F), 4) +
-           ws_slice((size_t)COLSUM_SLABS * (H > d ? H : d), 4) + ws_slice(N * H, 4) * 4 + ws_slice(N * 2 * H, 4) + ws_slice(N * d, 4) * 3 + 1024;
+           ws_slice((size_t)COLSUM_SLABS * (H > d ? H : d), 4) + ws_slice(N * H, 4) * 4 + ws_slice(N * 2 * H, 4) + ws_slice(N * d, 4) * 3 + ws_slice(((N + 31) / 32) * H, 4) + 1024;
 }
 
 static bool fm_take(FmBufs& M, Workspace& w, const mfm_field_t& F, int n, const mfm_target_t* T) {
@@ -257,6 +273,7 @@ static bool fm_take(FmBufs& M, Workspace& w, const mfm_field_t& F, int n, const 
     M.d6_s = w.take<float>(N * H); M.d5_s = w.take<float>(N * H); M.dcat_s = w.take<float>(N * 2 * H);
     M.d2_s = w.take<float>(N * H); M.d0_s = w.take<float>(N * H);
     M.xt_s = w.take<float>(N * d); M.delta_s = w.take<float>(N * d); M.dgt_s = w.take<float>(N * d);
+    M.cspart = w.take<float>(((N + 31) / 32) * H);
     return w.ok;
 }
 
@@ -311,6 +328,17 @@ static int fm_forward_backward(const mfm_field_t& F, const mfm_target_t& T, int 
         MFM_LAUNCH_CHECK();
         return MFM_OK;
     };
+    // ... or from the per-32-row partials a backward-data epilogue left in M.cspart (cs == true), else from the tensor itself
+    auto bias_grad_cs = [&](bool cs, const float* a, long long lda, int cols, float* out) -> int {
+        if (!cs) return bias_grad(a, lda, cols, out);
+        const int nb = (n + 31) / 32, slabs = nb >= 8 * COLSUM_SLABS ? COLSUM_SLABS : 1;
+        colsum_partial_kernel<<<dim3(ceil_div(cols, 32), slabs), 256, 0, st>>>(nb, cols, M.cspart, cols, M.colpart);
+        MFM_LAUNCH_CHECK();
+        colsum_final_kernel<<<ceil_div(cols, 256), 256, 0, st>>>(cols, slabs, M.colpart, out);
+        MFM_LAUNCH_CHECK();
+        return MFM_OK;
+    };
+    bool cs6 = false, cs5 = false, csx = false, cst = false, cs2 = false, cs0 = false;
     float* sb = M.splitbuf; const size_t sbf = M.splitbuf_floats;
     // pre-split copies along the backward-data chain (as in field_eval): slot ids of the exact maxima / bounds, ROW norms of the kernels
     const bool sp = am != nullptr && M.d6_s != nullptr && H % 16 == 0 && n >= 256;
@@ -334,16 +362,17 @@ static int fm_forward_backward(const mfm_field_t& F, const mfm_target_t& T, int 
     // layer 7 (nn_xt head): y = h6 W7 + b7
     if ((rc = wgrad(n, H, d, B.h6, H, M.delta, d, GW_(7), sb, sbf, st, WS_(wspd, B.h6_s, BD(AM_H6), M.delta_s, slot(AM_DELTA))))) return rc;
     if ((rc = bias_grad(M.delta, d, d, GB_(7)))) return rc;
-    if ((rc = dgrad(n, H, d, M.delta, d, W_(7), M.d6, H, g_h6, H, nullptr, 0, st, G_(slot(AM_DELTA), nullptr, nullptr, slot(AM_D6), M.d6_s, AM_D6, 7, nullptr)))) return rc;
+    if ((rc = dgrad(n, H, d, M.delta, d, W_(7), M.d6, H, g_h6, H, nullptr, 0, st, G_(slot(AM_DELTA), nullptr, nullptr, slot(AM_D6), M.d6_s, AM_D6, 7, nullptr), M.cspart, &cs6))) return rc;
+    if ((rc = bias_grad_cs(cs6, M.d6, H, H, GB_(6)))) return rc;        // bias gradients: column sums of the signal just written
     // layer 6
     if ((rc = wgrad(n, H, H, B.h5, H, M.d6, H, GW_(6), sb, sbf, st, WS_(wsp, B.h5_s, BD(AM_H5), M.d6_s, BD(AM_D6))))) return rc;
-    if ((rc = bias_grad(M.d6, H, H, GB_(6)))) return rc;
-    if ((rc = dgrad(n, H, H, M.d6, H, W_(6), M.d5, H, g_h5, H, nullptr, 0, st, G_(slot(AM_D6), M.d6_s, BD(AM_D6), slot(AM_D5), M.d5_s, AM_D5, 6, nullptr)))) return rc;
+    if ((rc = dgrad(n, H, H, M.d6, H, W_(6), M.d5, H, g_h5, H, nullptr, 0, st, G_(slot(AM_D6), M.d6_s, BD(AM_D6), slot(AM_D5), M.d5_s, AM_D5, 6, nullptr), M.cspart, &cs5))) return rc;
+    if ((rc = bias_grad_cs(cs5, M.d5, H, H, GB_(5)))) return rc;
     // layer 5 (joint, input cat = [s_x | s_t])
     if ((rc = wgrad(n, 2 * H, H, B.cat, 2 * H, M.d5, H, GW_(5), sb, sbf, st, WS_(wsp, B.cat_s, BD(AM_SX), M.d5_s, BD(AM_D5))))) return rc;
-    if ((rc = bias_grad(M.d5, H, H, GB_(5)))) return rc;
     // d s_x = (d5 W5[:H]^T) * relu'(s_x)
-    if ((rc = dgrad(n, H, H, M.d5, H, W_(5), M.dcat, 2 * H, g_cat, 2 * H, nullptr, 0, st, G_(slot(AM_D5), M.d5_s, BD(AM_D5), slot(AM_DCX), M.dcat_s, AM_DCX, 5, nullptr)))) return rc;
+    if ((rc = dgrad(n, H, H, M.d5, H, W_(5), M.dcat, 2 * H, g_cat, 2 * H, nullptr, 0, st, G_(slot(AM_D5), M.d5_s, BD(AM_D5), slot(AM_DCX), M.dcat_s, AM_DCX, 5, nullptr), M.cspart, &csx))) return rc;
+    if ((rc = bias_grad_cs(csx, M.dcat, 2 * H, H, GB_(3)))) return rc;  // (layer 3's bias; its slot lies in the head of the flat buffer, which nobody reads before part 2 ends)
     // d s_t (joint part) = d5 W5[H:]^T   (no gate yet; its bound enters the next layer's through `add`)
     if ((rc = dgrad(n, H, H, M.d5, H, W_(5) + (long long)H * H, M.dcat + H, 2 * H, nullptr, 0, nullptr, 0, st,
                     G_(slot(AM_D5), M.d5_s, BD(AM_D5), nullptr, M.dcat_s + H, AM_DCT0, 5, nullptr)))) return rc;
@@ -352,23 +381,22 @@ static int fm_forward_backward(const mfm_field_t& F, const mfm_target_t& T, int 
     if ((rc = bias_grad(M.dgt, d, d, GB_(4)))) return rc;
     // d s_t = (dgt W4^T + joint part) * relu'(s_t)   (in place)
     if ((rc = dgrad(n, H, d, M.dgt, d, W_(4), M.dcat + H, 2 * H, g_cat + H, 2 * H, M.dcat + H, 2 * H, st,
-                    G_(slot(AM_DGT), nullptr, nullptr, slot(AM_DCT), M.dcat_s + H, AM_DCT, 4, sp ? BD(AM_DCT0) : nullptr)))) return rc;
+                    G_(slot(AM_DGT), nullptr, nullptr, slot(AM_DCT), M.dcat_s + H, AM_DCT, 4, sp ? BD(AM_DCT0) : nullptr), M.cspart, &cst))) return rc;
+    if ((rc = bias_grad_cs(cst, M.dcat + H, 2 * H, H, GB_(1)))) return rc;
     }
     if (part == 1) return MFM_OK;
     // layer 3 (x branch)
     if ((rc = wgrad(n, H, H, B.h2, H, M.dcat, 2 * H, GW_(3), sb, sbf, st, WS_(wsp && xa_src, B.h2_s, BD(AM_H2), M.dcat_s, BD(AM_DCX))))) return rc;
-    if ((rc = bias_grad(M.dcat, 2 * H, H, GB_(3)))) return rc;
-    if ((rc = dgrad(n, H, H, M.dcat, 2 * H, W_(3), M.d2, H, g_h2, H, nullptr, 0, st, G_(slot(AM_DCX), M.dcat_s, BD(AM_DCX), slot(AM_D2), wsp ? M.d2_s : nullptr, AM_D2, 3, nullptr)))) return rc;
+    if ((rc = dgrad(n, H, H, M.dcat, 2 * H, W_(3), M.d2, H, g_h2, H, nullptr, 0, st, G_(slot(AM_DCX), M.dcat_s, BD(AM_DCX), slot(AM_D2), wsp ? M.d2_s : nullptr, AM_D2, 3, nullptr), M.cspart, &cs2))) return rc;
+    if ((rc = bias_grad_cs(cs2, M.d2, H, H, GB_(2)))) return rc;
     // layer 2
     if ((rc = wgrad(n, d, H, M.xt, d, M.d2, H, GW_(2), sb, sbf, st, WS_(wspd && xa_src, M.xt_s, xa_src, M.d2_s, BD(AM_D2))))) return rc;
-    if ((rc = bias_grad(M.d2, H, H, GB_(2)))) return rc;
     // layer 1 (time branch)
     if ((rc = wgrad(n, H, H, B.h0, H, M.dcat + H, 2 * H, GW_(1), sb, sbf, st, WS_(wsp, B.h0_s, BD(AM_H0), M.dcat_s + H, BD(AM_DCT))))) return rc;
-    if ((rc = bias_grad(M.dcat + H, 2 * H, H, GB_(1)))) return rc;
-    if ((rc = dgrad(n, H, H, M.dcat + H, 2 * H, W_(1), M.d0, H, g_h0, H, nullptr, 0, st, G_(slot(AM_DCT), M.dcat_s + H, BD(AM_DCT), slot(AM_D0), wsp ? M.d0_s : nullptr, AM_D0, 1, nullptr)))) return rc;
+    if ((rc = dgrad(n, H, H, M.dcat + H, 2 * H, W_(1), M.d0, H, g_h0, H, nullptr, 0, st, G_(slot(AM_DCT), M.dcat_s + H, BD(AM_DCT), slot(AM_D0), wsp ? M.d0_s : nullptr, AM_D0, 1, nullptr), M.cspart, &cs0))) return rc;
+    if ((rc = bias_grad_cs(cs0, M.d0, H, H, GB_(0)))) return rc;
     // layer 0
     if ((rc = wgrad(n, 2 * Fd, H, B.ff, 2 * Fd, M.d0, H, GW_(0), sb, sbf, st, WS_(wsp, B.ff_s, BD(AM_FF), M.d0_s, BD(AM_D0))))) return rc;
-    if ((rc = bias_grad(M.d0, H, H, GB_(0)))) return rc;
     return MFM_OK;
 }
 

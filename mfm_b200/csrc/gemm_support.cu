@@ -169,7 +169,8 @@ extern "C" void mfm_gemm_register_mirror(const float* base, long long n_floats, 
 extern "C" const char* mfm_gemm_describe(void) {
     if (mfm::tc2h::gemm_h16())
         return "K-major layers: operands scaled by a per-tensor power of two and split into 2 fp16 parts, 3 kind::f16 tcgen05 MMAs per 16 k "
-               "(ceiling 1/3 of the bf16 peak); weight gradients: 3xTF32 (ceiling 1/6); unaligned / tiny shapes: tf32 + bf16-cross or mma.sync 3xTF32";
+               "(ceiling 1/3 of the bf16 peak); weight gradients: the same three passes on MN-major tiles of the operands' pre-split copies; "
+               "unaligned / tiny shapes: 3xTF32 (tcgen05 or mma.sync)";
     return "K-major layers: tf32 hi*hi + bf16 cross terms, 2 tcgen05 MMAs per 8 k (ceiling 1/4 of the bf16 peak); weight gradients: 3xTF32";
 }
 // tuning aid (not part of the ABI header): SM-clock timeline of one CTA pair of the last tc2 GEMM

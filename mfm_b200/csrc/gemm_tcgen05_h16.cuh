@@ -493,6 +493,17 @@ gemm_tc2h_kernel(const __grid_constant__ Maps3 maps, GemmShape p, Epi epi, H16Sc
                         }
                     }
                 }
+                if constexpr (epi_has_colsum<Epi>::value) {
+                    // column sums of this 32-row x 32-column chunk: the four row groups of a column piece live 8 lanes apart
+                    float4 s4 = e.cs;
+                    s4.x += __shfl_xor_sync(0xffffffffu, s4.x, 8); s4.y += __shfl_xor_sync(0xffffffffu, s4.y, 8);
+                    s4.z += __shfl_xor_sync(0xffffffffu, s4.z, 8); s4.w += __shfl_xor_sync(0xffffffffu, s4.w, 8);
+                    s4.x += __shfl_xor_sync(0xffffffffu, s4.x, 16); s4.y += __shfl_xor_sync(0xffffffffu, s4.y, 16);
+                    s4.z += __shfl_xor_sync(0xffffffffu, s4.z, 16); s4.w += __shfl_xor_sync(0xffffffffu, s4.w, 16);
+                    if (rsub == 0 && cvalid && row_base < M && e.colsum_part)
+                        *reinterpret_cast<float4*>(e.colsum_part + (long long)(row_base >> 5) * e.ldcs + col) = s4;
+                    e.cs = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                }
                 if (Epi::kRowSum && ((cc & 1) || cc == cc_end - 1)) {
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {

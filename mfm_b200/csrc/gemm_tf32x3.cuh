@@ -52,6 +52,8 @@ template <class E> __device__ __forceinline__ auto epi_publish_bound(const E& e,
     if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (threadIdx.x & 31) == 0 && e.bound_out) *e.bound_out = e.out_bound();
 }
 template <class E> __device__ __forceinline__ void epi_publish_bound(const E&, long) {}
+template <class E, class = void> struct epi_has_colsum { static constexpr bool value = false; };
+template <class E> struct epi_has_colsum<E, decltype((void)E::kColSum)> { static constexpr bool value = E::kColSum; };
 template <class E> __device__ __forceinline__ void epi_publish_amax(const E& e, float vmax) {
     float* slot = epi_amax_slot(e, 0);
     if (slot != nullptr) amax_publish_warp(slot, vmax);
@@ -298,9 +300,13 @@ __device__ __forceinline__ float act_fwd(int act, float v, float& dv) {
 // ACT = false: relu / no activation and sign-of-the-output gates only (the default configuration: nothing of the general
 // activations' code - transcendental functions, derivative stores, multiplicative gates - reaches the kernels' epilogues, which
 // sit at the register cap); ACT = true: every activation of act_fwd.
-template <bool ACT>
+// CS = true: the functor also accumulates per-thread column sums of what it stores (`cs`); the scaled-fp16 kernel reduces them
+// over each 32-row block and writes one partial row per block to `colsum_part` (deterministic; bias gradients without a pass
+// over the tensor).
+template <bool ACT, bool CS = false>
 struct EpiStdT {
     static constexpr bool kRowSum = false;
+    static constexpr bool kColSum = CS;
     float* C; long long ldc;
     const float* bias;               // [N] or null
     const float* mask; long long ldm; // out = mask[row/mask_div,col] > 0 ? out : 0  (relu' gate) or null
@@ -312,6 +318,8 @@ struct EpiStdT {
     mutable float vmax = 0.0f;         // per-thread running maximum of what this copy of the functor stored
     float* dact = nullptr; long long lddact = 0;   // optional: act'(pre-activation) is written here (activations other than relu)
     int mask_mul = 0;                  // 1: out *= mask (the mask operand holds activation derivatives) instead of the > 0 gate
+    float* colsum_part = nullptr; long long ldcs = 0;      // CS: [ceil(M / 32)][ldcs] partial column sums
+    mutable float4 cs = {0.0f, 0.0f, 0.0f, 0.0f};
     __device__ __forceinline__ void at_z(int z) { C += (long long)z * c_zstride; }
     struct Aux { float bias, add, mask; };
     __device__ __forceinline__ Aux load(int row, int col) const {
@@ -370,6 +378,7 @@ struct EpiStdT {
         }
         st4(C + (long long)row * ldc + col, v);
         vmax = amax4(vmax, v);
+        if constexpr (CS) { cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w; }
         return 0.0f;
     }
 };
@@ -413,9 +422,10 @@ __host__ __device__ __forceinline__ uint32_t h16_scale_exp_(float amax) {     //
     se = se < 2 ? 2 : (se > 252 ? 252 : se);
     return (uint32_t)se;
 }
-template <bool ACT>
+template <bool ACT, bool CS = false>
 struct EpiStdST {
     static constexpr bool kRowSum = false;
+    static constexpr bool kColSum = CS;
     float* C; long long ldc;
     const float* bias; const float* mask; long long ldm; const float* add; long long ldadd; int relu; int mask_div;
     float* Cs;                         // split16 copy of C (leading dimension ldc)
@@ -431,6 +441,8 @@ struct EpiStdST {
     mutable float vmax = 0.0f;
     float* dact = nullptr; long long lddact = 0;   // as EpiStd: activation derivative output / multiplicative mask
     int mask_mul = 0;
+    float* colsum_part = nullptr; long long ldcs = 0;      // as EpiStdT
+    mutable float4 cs = {0.0f, 0.0f, 0.0f, 0.0f};
     __device__ __forceinline__ void at_z(int) {}
     __device__ __forceinline__ float out_bound() const {
         float a = in_bound;
@@ -503,6 +515,7 @@ struct EpiStdST {
         }
         st4(C + (long long)row * ldc + col, v);
         vmax = amax4(vmax, v);
+        if constexpr (CS) { cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w; }
         // columns col..col+3 of the 16-group: hi parts at byte 2 (col % 16), lo parts 32 bytes further
         uint2 hp, lp;
         split_pair(v.x * c.scale, v.y * c.scale, hp.x, lp.x);

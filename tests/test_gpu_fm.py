@@ -150,7 +150,12 @@ def test_fm_two_part_backward_is_identical(cuda, lib, setups, name):
                                              _lib.ptr(g2), _lib.ptr(ws), ws.numel(), part, _lib.stream()))
         if part == 1:
             assert torch.equal(g2[split:], grads[split:]) and torch.equal(l2, loss)
-            assert (g2[:split] == 0).all()
+            # the head is untouched so far, except the biases of Dense_3 and Dense_1: their gradients are column sums of
+            # signals part 1 produces (and reduces inside the producing epilogue when that runs on the tensor cores)
+            head = g2[:split].clone()
+            for l in (1, 3):
+                head[st.P.b_off[l]:st.P.b_off[l] + st.P.hidden] = 0
+            assert (head == 0).all()
     assert torch.equal(g2, grads)
 
 
