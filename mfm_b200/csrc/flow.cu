@@ -1007,7 +1007,7 @@ static int ode_solve(const mfm_field_t& F, const mfm_target_t& T, const mfm_ode_
         small::Args A;
         A.F = F; A.T = T; A.n = n; A.hutch = z != nullptr ? 1 : 0; A.n_seg = TS.n_seg;
         for (int k = 0; k < 16; ++k) A.target[k] = k < TS.n_seg ? TS.target[k] : 0.0f;
-        A.rtol = O.rtol; A.atol = O.atol; A.mxstep = O.mxstep; A.sgn = sgn; A.y0 = y0; A.z = z; A.y1 = y1; A.ldj = ldj; A.counters = S.counters;
+        A.rtol = O.rtol; A.atol = O.atol; A.mxstep = O.mxstep; A.sgn = sgn; A.y0 = y0; A.z = z; A.y1 = y1; A.ldj = ldj; A.counters = S.counters; A.wt = B.wt;
         static bool configured = false;
         if (!configured) {
             MFM_CUDA_CHECK(cudaFuncSetAttribute(small::ode_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, small::SMEM_BYTES));

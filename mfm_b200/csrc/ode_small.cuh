@@ -8,8 +8,9 @@
 // the lock-step multi-kernel driver (flow.cu::ode_solve), which stays the path for large ensembles and wide fields.
 // The ODE state, the seven stage slopes and every activation of the 8-layer MLP live in shared memory; the weights
 // (462 KB for d = 2: more than one SM's shared memory) are streamed from L2 as mma.sync B fragments with a
-// four-k-step register prefetch.  Dense layers: 3xTF32 on mma.sync.m16n8k8 with the partial sums flushed to fp32 registers
-// every 32 k (the arithmetic of gemm_tf32x3.cuh); the 8 warps split a layer's output columns, 16 (two n-tiles) each.
+// 128-k register prefetch.  Dense layers: 3xTF32 on mma.sync.m16n8k8 with the partial sums flushed to fp32 registers
+// every 32 k (the arithmetic of gemm_tf32x3.cuh); the 16 warps split a layer's output columns, one n-tile of 8 each; the A
+// operand is split into tf32 hi / lo planes once per layer.
 // Forward-mode tangents (one Hutchinson probe, or the d basis tangents of the exact trace) reuse the same row tile, one
 // pass per tangent.  Eligibility: H in {64, 128}, d <= 16, 2F <= 256, relu / tanh / elu (their derivatives follow from the
 // stored outputs), the warp-per-chain targets (mixture, phi-four, Gaussian).
@@ -22,7 +23,7 @@ namespace mfm {
 namespace small {
 
 constexpr int CH = 16;                  // chains per CTA = rows of one m16 MMA tile
-constexpr int NWARP = 8, NTHR = NWARP * 32;
+constexpr int NWARP = 16, NTHR = NWARP * 32;     // one n-tile of 8 output columns per warp (N = 128)
 constexpr int DP = 16;                  // padded state dimension (d <= 16)
 constexpr int LDH = 132;                // pitch of [16][<=128] buffers: pitch % 32 == 4 -> conflict-free A-fragment reads
 constexpr int LDC = 260;                // pitch of [16][<=256] buffers
@@ -31,11 +32,13 @@ struct Args {
     mfm_field_t F; mfm_target_t T;
     int n, hutch, n_seg; float target[16]; float rtol, atol; int mxstep; float sgn;
     const float* y0; const float* z; float* y1; float* ldj; int* counters;
+    const float* wt;      // the dense kernels transposed (FieldBufs::wt: layer i at wt + F.w_off[i], [out][in])
 };
 
 // shared-memory carve-up (floats)
 struct Smem {
     float* big;      // [16][LDC]: Fourier features, later the two tangent buffers ta | tb ([16][LDH] each)
+    uint32_t *ahi, *alo;   // [16][LDC] each: the tf32 hi / lo parts of the current layer's A operand (split once, read by all warps)
     float *h0, *h2, *h5, *h6, *zw2;      // [16][LDH]
     float* cat;      // [16][LDC] = [s_x | s_t]
     float *xi, *gt, *y7, *gc, *hx, *zs, *yx, *outx;   // [16][DP]
@@ -46,12 +49,13 @@ struct Smem {
     int *seg, *icount, *ntry;                          // [16]
 };
 constexpr int BIG = (CH * LDC > 2 * CH * LDH) ? CH * LDC : 2 * CH * LDH;     // Fourier features [16][LDC], later ta | tb
-constexpr int SMEM_FLOATS = BIG + CH * LDC + 5 * CH * LDH + 8 * CH * DP + 7 * CH * DP + 7 * CH + 7 * CH + NWARP * 5 * DP + 3 * CH;
+constexpr int SMEM_FLOATS = BIG + 3 * CH * LDC + 5 * CH * LDH + 8 * CH * DP + 7 * CH * DP + 7 * CH + 7 * CH + NWARP * 5 * DP + 3 * CH;
 constexpr int SMEM_BYTES = SMEM_FLOATS * 4 + 64;
 
 __device__ __forceinline__ Smem carve(float* p) {
     Smem s;
     s.big = p; p += BIG;
+    s.ahi = reinterpret_cast<uint32_t*>(p); p += CH * LDC; s.alo = reinterpret_cast<uint32_t*>(p); p += CH * LDC;
     s.cat = p; p += CH * LDC;
     s.h0 = p; p += CH * LDH; s.h2 = p; p += CH * LDH; s.h5 = p; p += CH * LDH; s.h6 = p; p += CH * LDH; s.zw2 = p; p += CH * LDH;
     s.xi = p; p += CH * DP; s.gt = p; p += CH * DP; s.y7 = p; p += CH * DP; s.gc = p; p += CH * DP; s.hx = p; p += CH * DP;
@@ -71,82 +75,106 @@ __device__ __forceinline__ float dact_from_output(int act, float h) {
     return h > 0.0f ? 1.0f : h + 1.0f;
 }
 
+// hi = the operand's own bits (the tensor core ignores the 13 low mantissa bits of a tf32 operand: hi = trunc(x), measured in
+// round 1), lo = rn_tf32(x - trunc(x)): one conversion per value instead of two
+__device__ __forceinline__ void split_raw(float x, uint32_t& hi, uint32_t& lo) {
+    hi = __float_as_uint(x);
+    lo = f2tf32(x - __uint_as_float(hi & 0xFFFFE000u));
+}
+
 // out[16][N] = f(A[16][K] W[K][N] + bias):  f = activation (mode 0, act_code as gemm_tf32x3.cuh) or a gate by the derivative
-// read off `gate` (mode 1: forward-mode tangent through that layer).  A, out, gate in shared memory, W row-major in global.
-// Warp w computes n-tiles w and w + 8 (N = 128) / w (N = 64); K % 128 == 0 or K == 64.  3xTF32, partial sums flushed every 32 k.
-// The B fragments of 128 k-values (64 registers) are requested in ONE batch: a layer costs one L2 round trip per 128 k, not
-// one per k-step - the kernel is bound by that latency, there is only one CTA of 8 warps per 16 chains.
+// read off `gate` (mode 1: forward-mode tangent through that layer).  A, out, gate in shared memory; WT = the kernel TRANSPOSED
+// ([N][ldwt], k contiguous: the copy field_prepare_weights builds for the tensor-core GEMMs).
+// Block-wide (contains barriers).  The A operand is split into its tf32 hi / lo parts ONCE, cooperatively, into the ahi / alo
+// planes (every warp needs the whole A tile: splitting in each warp tripled the instruction count of the k-loop); warp w then
+// computes n-tile w, w + 16, ...  3xTF32 with the cross terms in their own accumulator (two independent MMA chains), partial
+// sums flushed every 32 k.
+// k is PERMUTED inside every block of 16: the contraction index is summed over, so any permutation applied to both operands is
+// exact, and with thread t holding k = 4t .. 4t + 3 of a block (b0, b1 of two consecutive k-steps) its B fragments are ONE
+// 16-byte load from the transposed kernel per 16 k instead of four scattered 4-byte loads; the planes are written in the
+// matching order (position (v >> 1) * 8 + (v & 1) * 4 + u for k = 4u + v), from which ldmatrix delivers the A fragments.
+// The fragments of the first 128 k are requested BEFORE the split pass and its barrier, and every register is refilled with the
+// next batch's value right after its last use, so the L2 round trips overlap the arithmetic.
+// Not inlined: eleven inlined copies of the two instantiations made the kernel 38 k instructions and the loop starved on
+// instruction fetch (stall_no_inst was the top stall reason in the ncu capture).
 template <int KN>       // k-steps of 8 per batch: 16 (K % 128 == 0) or 8 (K == 64)
-__device__ __forceinline__ void mma_layer_t(const float* __restrict__ As, int lda, int K, const float* __restrict__ W, int ldw, int N,
-                                            const float* __restrict__ bias, int mode, int act, const float* gate, int ldg,
-                                            float* out, int ldo) {
+__device__ __noinline__ void mma_layer_t(const float* __restrict__ As, int lda, int K, const float* __restrict__ WT, int ldwt, int N,
+                                         const float* __restrict__ bias, int mode, int act, const float* gate, int ldg,
+                                         float* out, int ldo, uint32_t* ahi, uint32_t* alo) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int n_tiles = N >> 3;
-    for (int nt0 = warp; nt0 < n_tiles; nt0 += 2 * NWARP) {
-        const int nt1 = nt0 + NWARP;
-        const bool two = nt1 < n_tiles;
-        const int na = nt0 * 8 + g, nb = (two ? nt1 : nt0) * 8 + g;
-        float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-        for (int kb = 0; kb < K; kb += KN * 8) {
-            float bv[KN][2][2];                            // [k-step][n-tile][b0, b1]
+    float4 bq[KN / 2];                                     // [16-k block]: k = 4t .. 4t + 3 of column nt * 8 + g
+    if (warp < n_tiles) {
+        const float4* w = reinterpret_cast<const float4*>(WT + (long long)(warp * 8 + g) * ldwt) + t;
 #pragma unroll
-            for (int ks = 0; ks < KN; ++ks) {
-                const float* w0 = W + (long long)(kb + ks * 8 + t) * ldw;
-                const float* w1 = w0 + 4ll * ldw;
-                bv[ks][0][0] = __ldg(w0 + na); bv[ks][0][1] = __ldg(w1 + na);
-                bv[ks][1][0] = __ldg(w0 + nb); bv[ks][1][1] = __ldg(w1 + nb);
-            }
+        for (int j = 0; j < KN / 2; ++j) bq[j] = __ldg(w + 4 * j);
+    }
+    const int lgK4 = 29 - __clz(K);                        // log2(K / 4); K is a power of two (eligible())
+    for (int o = threadIdx.x; o < CH * (K >> 2); o += NTHR) {
+        // four consecutive k = 4u .. 4u + 3 of one row: positions base + u + {0, 4, 8, 12} of the permuted planes
+        const int r = o >> lgK4, k4 = (o & ((K >> 2) - 1)) << 2;
+        const float4 v = *reinterpret_cast<const float4*>(As + r * lda + k4);
+        const int base = r * LDC + (k4 & ~15) + ((k4 >> 2) & 3);
+        uint32_t h, l;
+        split_raw(v.x, h, l); ahi[base] = h; alo[base] = l;
+        split_raw(v.y, h, l); ahi[base + 4] = h; alo[base + 4] = l;
+        split_raw(v.z, h, l); ahi[base + 8] = h; alo[base + 8] = l;
+        split_raw(v.w, h, l); ahi[base + 12] = h; alo[base + 12] = l;
+    }
+    __syncthreads();
+    // A fragments by ldmatrix: an m16 x k8 tf32 tile is four 8 x 8 b16 matrices (rows 0-7 | 8-15) x (k 0-3 | 4-7); lane l supplies
+    // the row address of matrix l / 8, and receives exactly the m16n8k8 fragment elements a0..a3
+    const uint32_t frag_off = (uint32_t)((((lane & 7) + ((lane >> 3) & 1) * 8) * LDC + (lane >> 4) * 4) * 4);
+    const uint32_t hi_base = (uint32_t)__cvta_generic_to_shared(ahi) + frag_off, lo_base = (uint32_t)__cvta_generic_to_shared(alo) + frag_off;
+    for (int nt = warp; nt < n_tiles; nt += NWARP) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+        for (int kb = 0; kb < K; kb += KN * 8) {
+            // what the registers are refilled with: the next batch of this n-tile, else the first batch of the warp's next n-tile
+            const bool more_k = kb + KN * 8 < K, more = more_k || nt + NWARP < n_tiles;
+            const float4* wn = reinterpret_cast<const float4*>(WT + (long long)((more_k ? nt : nt + NWARP) * 8 + g) * ldwt + (more_k ? kb + KN * 8 : 0)) + t;
 #pragma unroll
             for (int kq = 0; kq < KN / 4; ++kq) {
-                float part[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+                float pm[4] = {0.f, 0.f, 0.f, 0.f}, px[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) {
                     const int ks = kq * 4 + kk;
-                    const int k0 = kb + ks * 8;
-                    uint32_t ah[4], al[4];
-                    split_tf32(As[g * lda + k0 + t], ah[0], al[0]); split_tf32(As[(g + 8) * lda + k0 + t], ah[1], al[1]);
-                    split_tf32(As[g * lda + k0 + t + 4], ah[2], al[2]); split_tf32(As[(g + 8) * lda + k0 + t + 4], ah[3], al[3]);
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        if (j == 1 && !two) break;
-                        uint32_t bh[2], bl[2];
-                        split_tf32(bv[ks][j][0], bh[0], bl[0]); split_tf32(bv[ks][j][1], bh[1], bl[1]);
-                        mma_tf32(part[j], al, bh); mma_tf32(part[j], ah, bl); mma_tf32(part[j], ah, bh);
-                    }
+                    const uint32_t ko = (uint32_t)(kb + ks * 8) * 4u;
+                    uint32_t ah[4], al[4], bh[2], bl[2];
+                    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(ah[0]), "=r"(ah[1]), "=r"(ah[2]), "=r"(ah[3]) : "r"(hi_base + ko));
+                    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(al[0]), "=r"(al[1]), "=r"(al[2]), "=r"(al[3]) : "r"(lo_base + ko));
+                    const float4 q = bq[ks >> 1];
+                    split_raw((ks & 1) ? q.z : q.x, bh[0], bl[0]); split_raw((ks & 1) ? q.w : q.y, bh[1], bl[1]);
+                    if ((ks & 1) && more) bq[ks >> 1] = __ldg(wn + 4 * (ks >> 1));
+                    mma_tf32(px, al, bh); mma_tf32(pm, ah, bh); mma_tf32(px, ah, bl);
                 }
 #pragma unroll
-                for (int j = 0; j < 2; ++j)
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) acc[j][e] += part[j][e];
+                for (int e = 0; e < 4; ++e) acc[e] += pm[e] + px[e];
             }
         }
+        const int c0 = nt * 8 + 2 * t;
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            if (j == 1 && !two) break;
-            const int c0 = (j == 0 ? nt0 : nt1) * 8 + 2 * t;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int r = g + (e >> 1) * 8, c = c0 + (e & 1);
-                float v = acc[j][e] + (bias ? __ldg(bias + c) : 0.0f);
-                if (mode == 0) { float dv; v = act_fwd(act + 1, v, dv); }
-                else v *= dact_from_output(act, gate[r * ldg + c]);
-                out[r * ldo + c] = v;
-            }
+        for (int e = 0; e < 4; ++e) {
+            const int r = g + (e >> 1) * 8, c = c0 + (e & 1);
+            float v = acc[e] + (bias ? __ldg(bias + c) : 0.0f);
+            if (mode == 0) { float dv; v = act_fwd(act + 1, v, dv); }
+            else v *= dact_from_output(act, gate[r * ldg + c]);
+            out[r * ldo + c] = v;
         }
     }
+    __syncthreads();        // the planes are rewritten by the next layer; out is complete
 }
 
-__device__ __forceinline__ void mma_layer(const float* __restrict__ As, int lda, int K, const float* __restrict__ W, int ldw, int N,
-                                          const float* __restrict__ bias, int mode, int act, const float* gate, int ldg,
-                                          float* out, int ldo) {
-    if (K % 128 == 0) mma_layer_t<16>(As, lda, K, W, ldw, N, bias, mode, act, gate, ldg, out, ldo);
-    else mma_layer_t<8>(As, lda, K, W, ldw, N, bias, mode, act, gate, ldg, out, ldo);
-}
+#define MMA_LAYER(As, lda, K, W, ldw, N, bias, mode, act, gate, ldg, out, ldo)                                        \
+    do {                                                                                                               \
+        if ((K) % 128 == 0) mma_layer_t<16>(As, lda, K, W, ldw, N, bias, mode, act, gate, ldg, out, ldo, S.ahi, S.alo); \
+        else mma_layer_t<8>(As, lda, K, W, ldw, N, bias, mode, act, gate, ldg, out, ldo, S.ahi, S.alo);                \
+    } while (0)
 
 // out[16][n_out] = A[16][K] W[K][n_out] + bias for tiny n_out (<= 16; the heads Dense_4 / Dense_7): 8 lanes per output, each a
 // strided eighth of the K products, then a shuffle reduction (a thread per output would be a chain of K dependent loads)
-__device__ __forceinline__ void head_layer(const float* As, int lda, int K, const float* __restrict__ W, int n_out, const float* __restrict__ bias,
+__device__ __noinline__ void head_layer(const float* As, int lda, int K, const float* __restrict__ W, int n_out, const float* __restrict__ bias,
                                            float* out) {
     const int sub = threadIdx.x & 7;
     for (int o0 = 0; o0 < CH * n_out; o0 += NTHR / 8) {
@@ -162,7 +190,8 @@ __device__ __forceinline__ void head_layer(const float* As, int lda, int K, cons
 
 // v = sgn * field(xi, tf) and negdiv = -sgn * div for the CTA's 16 chains.  xi [16][DP], tf [16] in shared memory; results to
 // vout [16][DP] and S.negdiv.  Block-wide: every thread calls it.
-__device__ void field_tile(const Args& A, const Smem& S, const float* xi, float* vout, bool want_div) {
+// (one copy of this code: inlined at its eight call sites the kernel was 43 k instructions and starved on instruction fetch)
+__device__ __noinline__ void field_tile(const Args& A, const Smem& S, const float* xi, float* vout, bool want_div) {
     const mfm_field_t& F = A.F;
     const int d = F.dim, H = F.hidden, Fd = F.fourier_dim, act = F.act;
     const float* P = F.params;
@@ -203,16 +232,12 @@ __device__ void field_tile(const Args& A, const Smem& S, const float* xi, float*
         }
     }
     __syncthreads();
-    mma_layer(S.big, LDC, 2 * Fd, P + F.w_off[0], H, H, P + F.b_off[0], 0, act, nullptr, 0, S.h0, LDH);          // Dense_0
-    mma_layer(S.h2, LDH, H, P + F.w_off[3], H, H, P + F.b_off[3], 0, act, nullptr, 0, S.cat, LDC);                // Dense_3 -> s_x
-    __syncthreads();
-    mma_layer(S.h0, LDH, H, P + F.w_off[1], H, H, P + F.b_off[1], 0, act, nullptr, 0, S.cat + H, LDC);            // Dense_1 -> s_t
-    __syncthreads();
+    MMA_LAYER(S.big, LDC, 2 * Fd, A.wt + F.w_off[0], 2 * Fd, H, P + F.b_off[0], 0, act, nullptr, 0, S.h0, LDH);          // Dense_0
+    MMA_LAYER(S.h2, LDH, H, A.wt + F.w_off[3], H, H, P + F.b_off[3], 0, act, nullptr, 0, S.cat, LDC);                // Dense_3 -> s_x
+    MMA_LAYER(S.h0, LDH, H, A.wt + F.w_off[1], H, H, P + F.b_off[1], 0, act, nullptr, 0, S.cat + H, LDC);            // Dense_1 -> s_t
     head_layer(S.cat + H, LDC, H, P + F.w_off[4], d, P + F.b_off[4], S.gt);                                       // Dense_4 -> nn_t
-    mma_layer(S.cat, LDC, 2 * H, P + F.w_off[5], H, H, P + F.b_off[5], 0, act, nullptr, 0, S.h5, LDH);            // Dense_5
-    __syncthreads();
-    mma_layer(S.h5, LDH, H, P + F.w_off[6], H, H, P + F.b_off[6], 0, act, nullptr, 0, S.h6, LDH);                 // Dense_6
-    __syncthreads();
+    MMA_LAYER(S.cat, LDC, 2 * H, A.wt + F.w_off[5], 2 * H, H, P + F.b_off[5], 0, act, nullptr, 0, S.h5, LDH);            // Dense_5
+    MMA_LAYER(S.h5, LDH, H, A.wt + F.w_off[6], H, H, P + F.b_off[6], 0, act, nullptr, 0, S.h6, LDH);                 // Dense_6
     head_layer(S.h6, LDH, H, P + F.w_off[7], d, P + F.b_off[7], S.y7);                                            // Dense_7 -> nn_xt
     __syncthreads();
     for (int o = threadIdx.x; o < CH * d; o += NTHR) {
@@ -233,12 +258,9 @@ __device__ void field_tile(const Args& A, const Smem& S, const float* xi, float*
             ta[r * LDH + c] = tin * dact_from_output(act, S.h2[r * LDH + c]);
         }
         __syncthreads();
-        mma_layer(ta, LDH, H, P + F.w_off[3], H, H, nullptr, 1, act, S.cat, LDC, tb, LDH);
-        __syncthreads();
-        mma_layer(tb, LDH, H, P + F.w_off[5], H, H, nullptr, 1, act, S.h5, LDH, ta, LDH);
-        __syncthreads();
-        mma_layer(ta, LDH, H, P + F.w_off[6], H, H, nullptr, 1, act, S.h6, LDH, tb, LDH);
-        __syncthreads();
+        MMA_LAYER(ta, LDH, H, A.wt + F.w_off[3], H, H, nullptr, 1, act, S.cat, LDC, tb, LDH);
+        MMA_LAYER(tb, LDH, H, A.wt + F.w_off[5], 2 * H, H, nullptr, 1, act, S.h5, LDH, ta, LDH);
+        MMA_LAYER(ta, LDH, H, A.wt + F.w_off[6], H, H, nullptr, 1, act, S.h6, LDH, tb, LDH);
         head_layer(tb, LDH, H, P + F.w_off[7], d, nullptr, S.y7);
         __syncthreads();
         if (threadIdx.x < CH) {
@@ -335,6 +357,7 @@ __global__ void __launch_bounds__(NTHR, 1) ode_small_kernel(const Args A) {
     for (long long it = 0; it < max_iter; ++it) {
         const int active = (tid < CH && S.seg[tid] < A.n_seg) ? 1 : 0;
         if (!__syncthreads_or(active)) break;
+#pragma unroll 1
         for (int sg = 1; sg <= 6; ++sg) {
             // stage input xi = y + dt * sum_j beta[sg-1][j] k_j ; field time t + alpha dt   (ode_stage_kernel)
             for (int o = tid; o < CH * d; o += NTHR) {
@@ -435,8 +458,7 @@ __global__ void __launch_bounds__(NTHR, 1) ode_small_kernel(const Args A) {
 inline bool eligible(const mfm_field_t& F, const mfm_target_t& T, int n) {
     const bool target_ok = T.kind == MFM_TARGET_GMM || T.kind == MFM_TARGET_PHI4 || T.kind == MFM_TARGET_GAUSS;
     const bool act_ok = F.act == MFM_ACT_RELU || F.act == MFM_ACT_TANH || F.act == MFM_ACT_ELU;
-    return target_ok && act_ok && n > 0 && F.dim <= DP && (F.hidden == 64 || F.hidden == 128) && F.fourier_dim % 16 == 0 &&
-           2 * F.fourier_dim <= 256 && !(T.kind == MFM_TARGET_GMM && F.dim != 2);
+    return target_ok && act_ok && n > 0 && F.dim <= DP && (F.hidden == 64 || F.hidden == 128) && (F.fourier_dim == 32 || F.fourier_dim == 64 || F.fourier_dim == 128) && !(T.kind == MFM_TARGET_GMM && F.dim != 2);
 }
 
 }  // namespace small
