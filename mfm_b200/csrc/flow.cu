@@ -148,6 +148,29 @@ __global__ void transpose_kernel(int rows, int cols, const float* __restrict__ i
     }
 }
 
+// the same for all eight dense kernels in ONE launch (they are transposed once per ABI call; eight launches of a few
+// microseconds each were a fixed cost that weighed 2 % of an FM update at 8 192 chains and 10 % at the small reference shapes)
+struct TransposeAll { int in[8], out[8], tile0[9], tx[8]; long long w_off[8]; };
+__global__ void transpose_all_kernel(TransposeAll D, const float* __restrict__ params, float* __restrict__ wt) {
+    __shared__ float tile[32][33];
+    int l = 0;
+#pragma unroll
+    for (int i = 1; i < 8; ++i) if ((int)blockIdx.x >= D.tile0[i]) l = i;
+    const int tidx = blockIdx.x - D.tile0[l];
+    const int rows = D.in[l], cols = D.out[l];
+    const int c0 = (tidx % D.tx[l]) * 32, r0 = (tidx / D.tx[l]) * 32;
+    const float* in = params + D.w_off[l]; float* out = wt + D.w_off[l];
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        const int r = r0 + j, c = c0 + threadIdx.x;
+        tile[j][threadIdx.x] = (r < rows && c < cols) ? in[(long long)r * cols + c] : 0.0f;
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        const int c = c0 + j, r = r0 + threadIdx.x;
+        if (r < rows && c < cols) out[(long long)c * rows + r] = tile[threadIdx.x][j];
+    }
+}
+
 // operator norms of the dense kernels for the output bounds of the split-writing epilogue (EpiStdS): per layer the largest
 // absolute column sum (forward product x W), the largest absolute row sum (backward-data product d W^T) and max |bias|.
 // One warp per matrix row, coalesced: row sums of W [in][out] give the row norm, row sums of its transpose (wt, [out][in],
@@ -205,6 +228,21 @@ __global__ void presplit_h16_kernel(const float4* __restrict__ src, uint4* __res
     dst[4 * g] = make_uint4(hp[0], hp[1], hp[2], hp[3]); dst[4 * g + 1] = make_uint4(hp[4], hp[5], hp[6], hp[7]);
     dst[4 * g + 2] = make_uint4(lp[0], lp[1], lp[2], lp[3]); dst[4 * g + 3] = make_uint4(lp[4], lp[5], lp[6], lp[7]);
 }
+// both weight mirrors (W^T and W) in one launch: blockIdx.y picks the pair
+__global__ void presplit_h16_pair_kernel(const float4* __restrict__ src0, uint4* __restrict__ dst0, const float4* __restrict__ src1, uint4* __restrict__ dst1,
+                                         long long n16, const float* __restrict__ amax) {
+    const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (g >= n16) return;
+    const float4* src = blockIdx.y ? src1 : src0; uint4* dst = blockIdx.y ? dst1 : dst0;
+    const float sc = tc2h::h16_scale(*amax);
+    float4 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = __ldg(src + 4 * g + j);
+    uint32_t hp[8], lp[8];
+    tc2h::split16(v, sc, hp, lp);
+    dst[4 * g] = make_uint4(hp[0], hp[1], hp[2], hp[3]); dst[4 * g + 1] = make_uint4(hp[4], hp[5], hp[6], hp[7]);
+    dst[4 * g + 2] = make_uint4(lp[0], lp[1], lp[2], lp[3]); dst[4 * g + 3] = make_uint4(lp[4], lp[5], lp[6], lp[7]);
+}
 int presplit_weights(const float* src, float* dst, long long n_floats, const float* amax, cudaStream_t st) {
     if (tc2h::gemm_h16() && amax != nullptr && n_floats % 16 == 0) {
         presplit_h16_kernel<<<ceil_div(n_floats / 16, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(src), reinterpret_cast<uint4*>(dst), n_floats / 16, amax);
@@ -232,9 +270,14 @@ static bool mirror_range(const mfm_field_t& F, const FieldBufs& B, bool& h16, lo
 
 int field_prepare_weights(const mfm_field_t& F, FieldBufs& B, cudaStream_t st) {
     tc2p::clear_cross(); tc2h::clear_mirrors_h16();
-    for (int i = 0; i < 8; ++i) {
-        int in, out; layer_dims(F, i, in, out);
-        transpose_kernel<<<dim3(ceil_div(out, 32), ceil_div(in, 32)), dim3(32, 8), 0, st>>>(in, out, F.params + F.w_off[i], B.wt + F.w_off[i]);
+    {
+        TransposeAll D; D.tile0[0] = 0;
+        for (int i = 0; i < 8; ++i) {
+            layer_dims(F, i, D.in[i], D.out[i]); D.w_off[i] = F.w_off[i];
+            D.tx[i] = ceil_div(D.out[i], 32);
+            D.tile0[i + 1] = D.tile0[i] + D.tx[i] * ceil_div(D.in[i], 32);
+        }
+        transpose_all_kernel<<<D.tile0[8], dim3(32, 8), 0, st>>>(D, F.params, B.wt);
         MFM_LAUNCH_CHECK();
     }
     if (B.amax) {
@@ -249,8 +292,15 @@ int field_prepare_weights(const mfm_field_t& F, FieldBufs& B, cudaStream_t st) {
     bool h16 = false; long long lo = 0, hi = 0;
     if (mirror_range(F, B, h16, lo, hi)) {
         int rc;
-        if ((rc = presplit_weights(B.wt + lo, B.wx + lo, hi - lo, h16 ? B.amax + AM_W : nullptr, st))) return rc;
-        if ((rc = presplit_weights(F.params + lo, B.wxo + lo, hi - lo, h16 ? B.amax + AM_W : nullptr, st))) return rc;
+        if (h16 && (hi - lo) % 16 == 0) {
+            presplit_h16_pair_kernel<<<dim3(ceil_div((hi - lo) / 16, 256), 2), 256, 0, st>>>(reinterpret_cast<const float4*>(B.wt + lo), reinterpret_cast<uint4*>(B.wx + lo),
+                                                                                              reinterpret_cast<const float4*>(F.params + lo), reinterpret_cast<uint4*>(B.wxo + lo),
+                                                                                              (hi - lo) / 16, B.amax + AM_W);
+            MFM_LAUNCH_CHECK();
+        } else {
+            if ((rc = presplit_weights(B.wt + lo, B.wx + lo, hi - lo, h16 ? B.amax + AM_W : nullptr, st))) return rc;
+            if ((rc = presplit_weights(F.params + lo, B.wxo + lo, hi - lo, h16 ? B.amax + AM_W : nullptr, st))) return rc;
+        }
         field_register_mirrors(F, B);
     }
     return MFM_OK;

@@ -145,6 +145,24 @@ __global__ void colsum_final_kernel(int cols, int slabs, const float* __restrict
     out[col] = t;
 }
 
+// column sums of the [nb, cols] per-32-row partials the backward-data epilogues leave (nb <= a few thousand): 32 columns per
+// block, 8 row groups, fixed order - one launch instead of the partial + final pair
+__global__ void __launch_bounds__(256) colsum_blocks_kernel(int nb, int cols, const float* __restrict__ part, float* __restrict__ out) {
+    __shared__ float sm[8][33];
+    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    const int col = blockIdx.x * 32 + cx;
+    float s = 0.0f;
+    if (col < cols) for (int r = ry; r < nb; r += 8) s += part[(long long)r * cols + col];
+    sm[ry][cx] = s;
+    __syncthreads();
+    if (ry == 0 && col < cols) {
+        float t = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += sm[k][cx];
+        out[col] = t;
+    }
+}
+
 // out[i] = sum_z partial[z*stride + i]
 __global__ void splitk_reduce_kernel(long long count, int splits, long long stride, const float* __restrict__ partial,
                                      float* __restrict__ out) {
@@ -174,13 +192,32 @@ static int wgrad(int n, int in, int out, const float* A, long long lda, const fl
     int max_splits = n / 512;
     if (max_splits > 64) max_splits = 64;
     while (max_splits > 1 && (size_t)max_splits * in * out > splitbuf_floats) --max_splits;
-    int splits = 1; double best = 0.0;
-    for (int sp = 1; sp <= max_splits; ++sp) {
-        const long long ctas = tiles * sp;
-        const double eff = (double)ctas / (double)(((ctas + slots - 1) / slots) * slots);
-        if (eff > best + 1e-9) { best = eff; splits = sp; }
-        if (eff >= 0.92) { splits = sp; break; }
+    int splits = 1;
+    static const int forced = getenv("MFM_WGRAD_SPLITS") ? atoi(getenv("MFM_WGRAD_SPLITS")) : 0;     // tuning aid
+    if (path == 2) {
+        // CTA-pair kernels (one 256 x 256 tile per pair and launch wave): pick the split that minimises a small cost model -
+        // waves x (fixed prologue + epilogue of a tile + its share of the k-loop) + the pass that adds the partial tiles.  Filling
+        // the waves alone (the rule below) over-splits short batches: at 8 192 chains 9 slices of a 1024 x 1024 layer are two waves
+        // of 15-stage tiles whose un-overlapped epilogues and 37 MB of partials cost more than the k-loop itself.
+        const double t_fixed = 10.0, t_stage = h16w ? 1.3 : 2.4;                 // us: per tile; per 64 chains of one tile's k-loop
+        const double red_us_per_mb = 0.4;                                        // the partials are written once and read once
+        double best_t = 1e30;
+        for (int sp = 1; sp <= max_splits; ++sp) {
+            const long long waves = (tiles * sp + slots - 1) / slots;
+            const double stages = (double)((n + sp - 1) / sp + 63) / 64.0;
+            const double t = (double)waves * (t_fixed + stages * t_stage) + (sp > 1 ? (double)(sp + 1) * (double)in * out * 4e-6 * red_us_per_mb : 0.0);
+            if (t < best_t - 1e-9) { best_t = t; splits = sp; }
+        }
+    } else {
+        double best = 0.0;
+        for (int sp = 1; sp <= max_splits; ++sp) {
+            const long long ctas = tiles * sp;
+            const double eff = (double)ctas / (double)(((ctas + slots - 1) / slots) * slots);
+            if (eff > best + 1e-9) { best = eff; splits = sp; }
+            if (eff >= 0.92) { splits = sp; break; }
+        }
     }
+    if (forced > 0) splits = forced < max_splits ? forced : (max_splits > 0 ? max_splits : 1);
     if (splits <= 1) {
         EpiStd e{dW, (long long)out, nullptr, nullptr, 0, nullptr, 0, 1.0f, 0};
         if (h16w) MFM_CUDA_CHECK((tc2w::launch(p16, e, ws.a_src, ws.g_src, st)));
@@ -331,10 +368,15 @@ static int fm_forward_backward(const mfm_field_t& F, const mfm_target_t& T, int 
     // ... or from the per-32-row partials a backward-data epilogue left in M.cspart (cs == true), else from the tensor itself
     auto bias_grad_cs = [&](bool cs, const float* a, long long lda, int cols, float* out) -> int {
         if (!cs) return bias_grad(a, lda, cols, out);
-        const int nb = (n + 31) / 32, slabs = nb >= 8 * COLSUM_SLABS ? COLSUM_SLABS : 1;
-        colsum_partial_kernel<<<dim3(ceil_div(cols, 32), slabs), 256, 0, st>>>(nb, cols, M.cspart, cols, M.colpart);
+        const int nb = (n + 31) / 32;
+        if (nb <= 8 * COLSUM_SLABS) {           // few partial rows: one launch
+            colsum_blocks_kernel<<<ceil_div(cols, 32), 256, 0, st>>>(nb, cols, M.cspart, out);
+            MFM_LAUNCH_CHECK();
+            return MFM_OK;
+        }
+        colsum_partial_kernel<<<dim3(ceil_div(cols, 32), COLSUM_SLABS), 256, 0, st>>>(nb, cols, M.cspart, cols, M.colpart);
         MFM_LAUNCH_CHECK();
-        colsum_final_kernel<<<ceil_div(cols, 256), 256, 0, st>>>(cols, slabs, M.colpart, out);
+        colsum_final_kernel<<<ceil_div(cols, 256), 256, 0, st>>>(cols, COLSUM_SLABS, M.colpart, out);
         MFM_LAUNCH_CHECK();
         return MFM_OK;
     };
