@@ -147,12 +147,12 @@ __global__ void colsum_final_kernel(int cols, int slabs, const float* __restrict
 
 // column sums of the [nb, cols] per-32-row partials the backward-data epilogues leave (nb <= a few thousand): 32 columns per
 // block, 8 row groups, fixed order - one launch instead of the partial + final pair
-__global__ void __launch_bounds__(256) colsum_blocks_kernel(int nb, int cols, const float* __restrict__ part, float* __restrict__ out) {
+__global__ void __launch_bounds__(256) colsum_blocks_kernel(int nb, int cols, const float* __restrict__ part, long long ldp, float* __restrict__ out) {
     __shared__ float sm[8][33];
     const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
     const int col = blockIdx.x * 32 + cx;
     float s = 0.0f;
-    if (col < cols) for (int r = ry; r < nb; r += 8) s += part[(long long)r * cols + col];
+    if (col < cols) for (int r = ry; r < nb; r += 8) s += part[(long long)r * ldp + col];
     sm[ry][cx] = s;
     __syncthreads();
     if (ry == 0 && col < cols) {
@@ -358,7 +358,12 @@ static int fm_forward_backward(const mfm_field_t& F, const mfm_target_t& T, int 
         }
     }
     auto bias_grad = [&](const float* a, long long lda, int cols, float* out) -> int {
-        const int slabs = n >= 8 * COLSUM_SLABS ? COLSUM_SLABS : 1;
+        if (n < 8 * COLSUM_SLABS) {             // few rows: one launch
+            colsum_blocks_kernel<<<ceil_div(cols, 32), 256, 0, st>>>(n, cols, a, lda, out);
+            MFM_LAUNCH_CHECK();
+            return MFM_OK;
+        }
+        const int slabs = COLSUM_SLABS;
         colsum_partial_kernel<<<dim3(ceil_div(cols, 32), slabs), 256, 0, st>>>(n, cols, a, lda, M.colpart);
         MFM_LAUNCH_CHECK();
         colsum_final_kernel<<<ceil_div(cols, 256), 256, 0, st>>>(cols, slabs, M.colpart, out);
@@ -370,7 +375,7 @@ static int fm_forward_backward(const mfm_field_t& F, const mfm_target_t& T, int 
         if (!cs) return bias_grad(a, lda, cols, out);
         const int nb = (n + 31) / 32;
         if (nb <= 8 * COLSUM_SLABS) {           // few partial rows: one launch
-            colsum_blocks_kernel<<<ceil_div(cols, 32), 256, 0, st>>>(nb, cols, M.cspart, out);
+            colsum_blocks_kernel<<<ceil_div(cols, 32), 256, 0, st>>>(nb, cols, M.cspart, cols, out);
             MFM_LAUNCH_CHECK();
             return MFM_OK;
         }

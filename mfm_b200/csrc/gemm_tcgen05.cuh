@@ -310,6 +310,9 @@ template <bool A_KMAJOR, bool B_NMAJOR>
 inline bool eligible(const GemmShape& p) {
     if (encode_fn() == nullptr) return false;
     if (p.M < 128 || p.N < 64 || p.K < 32) return false;                          // tiny problems: warp-level path
+    // ... and small ones: a single 128-row tile of a 128 x 128 x 256 layer took 51 us on this kernel (one CTA: TMEM allocation,
+    // barrier set-up and a 2-stage pipeline for 8 k-blocks) against 13 us on the warp-level kernel (profiles/r02 4-mode launch list)
+    if ((long long)p.M * p.N * p.K < (1ll << 25)) return false;
     if ((reinterpret_cast<uintptr_t>(p.A) & 15) || (reinterpret_cast<uintptr_t>(p.B) & 15)) return false;
     if (p.lda % 4 || p.ldb % 4) return false;
     if (!A_KMAJOR && (p.M % 32)) return false;
