@@ -473,8 +473,9 @@ bool field_bufs_take(FieldBufs& B, Workspace& w, const mfm_field_t& F, int n, bo
     if (T && T->kind == MFM_TARGET_PINES_WHITE) { B.tscratch = w.take<float>(N * d); w.take<float>(N * d); w.take<float>(N * d); w.take<float>(N * d); }
     // fewer than 256 rows in every dense layer (tangent rows of the exact divergence included): nothing reaches the CTA-pair
     // tcgen05 kernel, so the per-call weight preparation for it (maximum, operator norms, two mirrors) and the maxima
-    // bookkeeping are skipped altogether - at the small reference shapes they cost more than the layers themselves
-    if (N * (hutch ? 1 : d) < 256) {
+    // bookkeeping are skipped altogether - at the small reference shapes they cost more than the layers themselves; the same for
+    // narrow networks (hidden < 512: memory-bound layers, see h16_min_hidden)
+    if (N * (hutch ? 1 : d) < 256 || (int)H < tc2h::h16_min_hidden()) {
         B.amax = nullptr; B.wx = B.wxo = nullptr;
         B.ff_s = B.h0_s = B.cat_s = B.h2_s = B.h5_s = B.h6_s = B.ta_s = B.tb_s = nullptr;
     }

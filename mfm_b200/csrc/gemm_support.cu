@@ -160,6 +160,11 @@ extern "C" void mfm_set_gemm_cross_bf16(int v) { mfm::tc2p::g_cross_bf16 = v ? 1
 extern "C" void mfm_set_gemm_streamk(int v) { mfm::tc2p::g_streamk = v ? 1 : 0; }
 extern "C" void mfm_set_gemm_h16(int v) { mfm::tc2h::g_h16 = v < 0 ? 0 : (v > 2 ? 1 : v); }
 extern "C" int mfm_gemm_h16_enabled(void) { return mfm::tc2h::gemm_h16(); }
+// narrowest hidden width for which the MLP runs on the scaled-fp16 path (maxima, operator norms, mirrors, pre-split copies): below
+// it the layers are memory- / latency-bound and the extra copies cost more than the faster arithmetic gains (phi-four, H = 128:
+// 1.40 M chain-steps/s without, 1.24 M with).  Tests force 0 to cover the hand-over logic at small widths.
+namespace mfm { namespace tc2h { static int g_min_hidden = 512; int h16_min_hidden() { return g_min_hidden; } } }
+extern "C" void mfm_debug_set_h16_min_hidden(int h) { mfm::tc2h::g_min_hidden = h < 0 ? 512 : h; }
 extern "C" void mfm_debug_set_h16_groups(int g) { mfm::tc2h::g_groups = (g == 1 || g == 4) ? g : 2; }   // tuning aid, not in the ABI header
 extern "C" void mfm_gemm_register_mirror(const float* base, long long n_floats, const float* mirror) {
     if (!(base && mirror && n_floats > 0)) { mfm::tc2p::clear_cross(); mfm::tc2h::clear_mirrors_h16(); return; }

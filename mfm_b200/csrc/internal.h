@@ -83,6 +83,7 @@ void clear_mirrors_h16();
 cudaError_t launch_absmax(const float* x, long long ld, int rows, int cols, const int* n_rows_dev, float* out, cudaStream_t st);
 float* amax_scratch_for(cudaStream_t st);
 int split_groups();
+int h16_min_hidden();
 }
 int gemm_backend();
 int rng_x64();             // 1: float64-layout draws (jax_enable_x64), rounded to float32 (rng.cu)

@@ -66,11 +66,19 @@ def test_field_and_divergence(cuda, setups, name):
 
 
 @pytest.mark.parametrize("name,n", [("4-mode", 333), ("gmm16", 333), ("gmm16", 512), ("phi-four", 300)])
-def test_field_and_divergence_tensor_core_rows(cuda, setups, name, n):
+def test_field_and_divergence_tensor_core_rows(cuda, lib, setups, name, n):
     """>= 256 rows: the dense layers run on the tcgen05 kernel and hand their outputs over pre-split (d = 2: max |x| is not
     tracked, Dense_2 writes no copy and Dense_3 must split h2 itself; d = 16: Dense_2 runs on mma.sync and writes the copy from
     its scalar epilogue; 333 / 300 rows: a partial last tile)."""
     s = setups[name]
+    lib.mfm_debug_set_h16_min_hidden(0)          # (H = 128 here: by default narrow networks stay off the scaled-fp16 path)
+    try:
+        _field_rows_check(cuda, s, name, n)
+    finally:
+        lib.mfm_debug_set_h16_min_hidden(-1)
+
+
+def _field_rows_check(cuda, s, name, n):
     x = _positions(s, n, seed=3)
     t = np.linspace(0.0, 1.0, n)
     z = np.random.default_rng(6).standard_normal(x.shape) if s.hutch else None

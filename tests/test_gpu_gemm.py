@@ -265,9 +265,11 @@ def test_gemm_h16(cuda, lib, M, N, K, a_scale, b_scale):
             outs[name] = got
     finally:
         lib.mfm_gemm_register_mirror(None, 0, None)
-    # the same parts reach the tensor core whichever way they were made
-    assert np.array_equal(outs["mirror, tracked max"], outs["mirror, reduced max"])
-    assert np.array_equal(outs["mirror, tracked max"], outs["kernel-split B, reduced max"])
+    # the same parts reach the tensor core whichever way they were made (narrow layers without a tracked maximum are not worth
+    # the reduction pass and run on the tf32 + bf16-cross kernel instead: only the tolerance above applies to them)
+    if N * K >= 512 * 512:
+        assert np.array_equal(outs["mirror, tracked max"], outs["mirror, reduced max"])
+        assert np.array_equal(outs["mirror, tracked max"], outs["kernel-split B, reduced max"])
 
 def test_gemm_strided_views(cuda, lib):
     """ld > logical width (writing into a column block of a concatenated buffer)."""
