@@ -318,6 +318,26 @@ static bool fm_take(FmBufs& M, Workspace& w, const mfm_field_t& F, int n, const 
 #define GW_(i) (grads + F.w_off[i])
 #define GB_(i) (grads + F.b_off[i])
 
+// Second stream for the weight gradients.  dW_l needs only the layer's input and the back-propagated signal G_l, nothing downstream
+// needs dW_l: issued on their own stream they fill the SM pairs a backward-data GEMM's last, partial wave of tiles leaves idle
+// (at 8 192 chains a 1024-wide layer is 128 tiles on 74 pairs) and vice versa.  Same kernels, same arithmetic, same results;
+// each weight gradient waits for everything issued on the main stream before it, the call joins the streams before it returns.
+// Off while the main stream is being captured into a graph and for short batches (MFM_FM_STREAMS=0|1 overrides).
+struct FmAux { cudaStream_t s = nullptr; cudaEvent_t fork[12] = {}; cudaEvent_t join = nullptr; bool ok = false; };
+static FmAux* fm_aux() {
+    static FmAux aux[16];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+    FmAux& a = aux[dev];
+    if (!a.ok) {
+        if (cudaStreamCreateWithFlags(&a.s, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        for (int i = 0; i < 12; ++i) if (cudaEventCreateWithFlags(&a.fork[i], cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        if (cudaEventCreateWithFlags(&a.join, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        a.ok = true;
+    }
+    return &a;
+}
+
 // part 0: everything; part 1: forward, loss and the gradients of layers 7..4 (the tail [w_off[4], n_params) of
 // the flat buffer); part 2: the gradients of layers 3..0 (the head) from the activations part 1 left in
 // the workspace.  The split lets the host all-reduce the tail while part 2 runs.
@@ -405,18 +425,44 @@ static int fm_forward_backward(const mfm_field_t& F, const mfm_target_t& T, int 
     auto WS_ = [&](bool on, const float* a_s, const float* a_src, const float* g_s, const float* g_src) {
         WgradSplit w; if (on) { w.a_s = a_s; w.a_src = a_src; w.g_s = g_s; w.g_src = g_src; } return w;
     };
+    // weight gradients on the second stream (see FmAux)
+    static const int streams_env = getenv("MFM_FM_STREAMS") ? atoi(getenv("MFM_FM_STREAMS")) : -1;
+    FmAux* aux = nullptr;
+    {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        const bool capturing = cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone;
+        if (!capturing && (streams_env > 0 || (streams_env < 0 && n >= 1024))) aux = fm_aux();
+    }
+    cudaStream_t sw = aux ? aux->s : st;
+    int n_fork = 0;
+    auto fork_w = [&]() -> int {          // the next weight gradient may start once everything issued on st so far has finished
+        if (!aux) return MFM_OK;
+        cudaEvent_t e = aux->fork[n_fork++ % 12];
+        MFM_CUDA_CHECK(cudaEventRecord(e, st));
+        MFM_CUDA_CHECK(cudaStreamWaitEvent(sw, e, 0));
+        return MFM_OK;
+    };
+    auto join_w = [&]() -> int {          // ... and the caller's stream continues only after the last one
+        if (!aux) return MFM_OK;
+        MFM_CUDA_CHECK(cudaEventRecord(aux->join, sw));
+        MFM_CUDA_CHECK(cudaStreamWaitEvent(st, aux->join, 0));
+        return MFM_OK;
+    };
     if (part != 2) {
     // layer 7 (nn_xt head): y = h6 W7 + b7
-    if ((rc = wgrad(n, H, d, B.h6, H, M.delta, d, GW_(7), sb, sbf, st, WS_(wspd, B.h6_s, BD(AM_H6), M.delta_s, slot(AM_DELTA))))) return rc;
+    if ((rc = fork_w())) return rc;
+    if ((rc = wgrad(n, H, d, B.h6, H, M.delta, d, GW_(7), sb, sbf, sw, WS_(wspd, B.h6_s, BD(AM_H6), M.delta_s, slot(AM_DELTA))))) return rc;
     if ((rc = bias_grad(M.delta, d, d, GB_(7)))) return rc;
     if ((rc = dgrad(n, H, d, M.delta, d, W_(7), M.d6, H, g_h6, H, nullptr, 0, st, G_(slot(AM_DELTA), nullptr, nullptr, slot(AM_D6), M.d6_s, AM_D6, 7, nullptr), M.cspart, &cs6))) return rc;
     if ((rc = bias_grad_cs(cs6, M.d6, H, H, GB_(6)))) return rc;        // bias gradients: column sums of the signal just written
     // layer 6
-    if ((rc = wgrad(n, H, H, B.h5, H, M.d6, H, GW_(6), sb, sbf, st, WS_(wsp, B.h5_s, BD(AM_H5), M.d6_s, BD(AM_D6))))) return rc;
+    if ((rc = fork_w())) return rc;
+    if ((rc = wgrad(n, H, H, B.h5, H, M.d6, H, GW_(6), sb, sbf, sw, WS_(wsp, B.h5_s, BD(AM_H5), M.d6_s, BD(AM_D6))))) return rc;
     if ((rc = dgrad(n, H, H, M.d6, H, W_(6), M.d5, H, g_h5, H, nullptr, 0, st, G_(slot(AM_D6), M.d6_s, BD(AM_D6), slot(AM_D5), M.d5_s, AM_D5, 6, nullptr), M.cspart, &cs5))) return rc;
     if ((rc = bias_grad_cs(cs5, M.d5, H, H, GB_(5)))) return rc;
     // layer 5 (joint, input cat = [s_x | s_t])
-    if ((rc = wgrad(n, 2 * H, H, B.cat, 2 * H, M.d5, H, GW_(5), sb, sbf, st, WS_(wsp, B.cat_s, BD(AM_SX), M.d5_s, BD(AM_D5))))) return rc;
+    if ((rc = fork_w())) return rc;
+    if ((rc = wgrad(n, 2 * H, H, B.cat, 2 * H, M.d5, H, GW_(5), sb, sbf, sw, WS_(wsp, B.cat_s, BD(AM_SX), M.d5_s, BD(AM_D5))))) return rc;
     // d s_x = (d5 W5[:H]^T) * relu'(s_x)
     if ((rc = dgrad(n, H, H, M.d5, H, W_(5), M.dcat, 2 * H, g_cat, 2 * H, nullptr, 0, st, G_(slot(AM_D5), M.d5_s, BD(AM_D5), slot(AM_DCX), M.dcat_s, AM_DCX, 5, nullptr), M.cspart, &csx))) return rc;
     if ((rc = bias_grad_cs(csx, M.dcat, 2 * H, H, GB_(3)))) return rc;  // (layer 3's bias; its slot lies in the head of the flat buffer, which nobody reads before part 2 ends)
@@ -424,27 +470,32 @@ static int fm_forward_backward(const mfm_field_t& F, const mfm_target_t& T, int 
     if ((rc = dgrad(n, H, H, M.d5, H, W_(5) + (long long)H * H, M.dcat + H, 2 * H, nullptr, 0, nullptr, 0, st,
                     G_(slot(AM_D5), M.d5_s, BD(AM_D5), nullptr, M.dcat_s + H, AM_DCT0, 5, nullptr)))) return rc;
     // layer 4 (nn_t head): g_t = s_t W4 + b4, dL/dg_t = delta * clip(grad logprob)
-    if ((rc = wgrad(n, H, d, B.cat + H, 2 * H, M.dgt, d, GW_(4), sb, sbf, st, WS_(wspd, B.cat_s + H, BD(AM_ST), M.dgt_s, slot(AM_DGT))))) return rc;
+    if ((rc = fork_w())) return rc;
+    if ((rc = wgrad(n, H, d, B.cat + H, 2 * H, M.dgt, d, GW_(4), sb, sbf, sw, WS_(wspd, B.cat_s + H, BD(AM_ST), M.dgt_s, slot(AM_DGT))))) return rc;
     if ((rc = bias_grad(M.dgt, d, d, GB_(4)))) return rc;
     // d s_t = (dgt W4^T + joint part) * relu'(s_t)   (in place)
     if ((rc = dgrad(n, H, d, M.dgt, d, W_(4), M.dcat + H, 2 * H, g_cat + H, 2 * H, M.dcat + H, 2 * H, st,
                     G_(slot(AM_DGT), nullptr, nullptr, slot(AM_DCT), M.dcat_s + H, AM_DCT, 4, sp ? BD(AM_DCT0) : nullptr), M.cspart, &cst))) return rc;
     if ((rc = bias_grad_cs(cst, M.dcat + H, 2 * H, H, GB_(1)))) return rc;
     }
-    if (part == 1) return MFM_OK;
+    if (part == 1) return join_w();
     // layer 3 (x branch)
-    if ((rc = wgrad(n, H, H, B.h2, H, M.dcat, 2 * H, GW_(3), sb, sbf, st, WS_(wsp && xa_src, B.h2_s, BD(AM_H2), M.dcat_s, BD(AM_DCX))))) return rc;
+    if ((rc = fork_w())) return rc;
+    if ((rc = wgrad(n, H, H, B.h2, H, M.dcat, 2 * H, GW_(3), sb, sbf, sw, WS_(wsp && xa_src, B.h2_s, BD(AM_H2), M.dcat_s, BD(AM_DCX))))) return rc;
     if ((rc = dgrad(n, H, H, M.dcat, 2 * H, W_(3), M.d2, H, g_h2, H, nullptr, 0, st, G_(slot(AM_DCX), M.dcat_s, BD(AM_DCX), slot(AM_D2), wsp ? M.d2_s : nullptr, AM_D2, 3, nullptr), M.cspart, &cs2))) return rc;
     if ((rc = bias_grad_cs(cs2, M.d2, H, H, GB_(2)))) return rc;
     // layer 2
-    if ((rc = wgrad(n, d, H, M.xt, d, M.d2, H, GW_(2), sb, sbf, st, WS_(wspd && xa_src, M.xt_s, xa_src, M.d2_s, BD(AM_D2))))) return rc;
+    if ((rc = fork_w())) return rc;
+    if ((rc = wgrad(n, d, H, M.xt, d, M.d2, H, GW_(2), sb, sbf, sw, WS_(wspd && xa_src, M.xt_s, xa_src, M.d2_s, BD(AM_D2))))) return rc;
     // layer 1 (time branch)
-    if ((rc = wgrad(n, H, H, B.h0, H, M.dcat + H, 2 * H, GW_(1), sb, sbf, st, WS_(wsp, B.h0_s, BD(AM_H0), M.dcat_s + H, BD(AM_DCT))))) return rc;
+    if ((rc = fork_w())) return rc;
+    if ((rc = wgrad(n, H, H, B.h0, H, M.dcat + H, 2 * H, GW_(1), sb, sbf, sw, WS_(wsp, B.h0_s, BD(AM_H0), M.dcat_s + H, BD(AM_DCT))))) return rc;
     if ((rc = dgrad(n, H, H, M.dcat + H, 2 * H, W_(1), M.d0, H, g_h0, H, nullptr, 0, st, G_(slot(AM_DCT), M.dcat_s + H, BD(AM_DCT), slot(AM_D0), wsp ? M.d0_s : nullptr, AM_D0, 1, nullptr), M.cspart, &cs0))) return rc;
     if ((rc = bias_grad_cs(cs0, M.d0, H, H, GB_(0)))) return rc;
     // layer 0
-    if ((rc = wgrad(n, 2 * Fd, H, B.ff, 2 * Fd, M.d0, H, GW_(0), sb, sbf, st, WS_(wsp, B.ff_s, BD(AM_FF), M.d0_s, BD(AM_D0))))) return rc;
-    return MFM_OK;
+    if ((rc = fork_w())) return rc;
+    if ((rc = wgrad(n, 2 * Fd, H, B.ff, 2 * Fd, M.d0, H, GW_(0), sb, sbf, sw, WS_(wsp, B.ff_s, BD(AM_FF), M.d0_s, BD(AM_D0))))) return rc;
+    return join_w();
 }
 
 // ---------------------------------------------------------------------------------------------
