@@ -106,6 +106,69 @@ __device__ __forceinline__ float xla_erfinv_f32(float x) {
     return fabsf(x) == 1.0f ? x * INFINITY : r;
 }
 
+// ---- the same normal, cheaper: correctly rounded logf from a 16-entry table ------------------------------------------------
+// The double-precision log above is ~40 % of the cost of a normal draw, and the two kernels that draw one or two normals per
+// state element (pines_propose_kernel, fm_batch_kernel) are ALU-bound on it.  log_rn_f32 computes log(z) for a float32 z in
+// double with glibc-logf's range reduction (z = 2^k z', z' in [0.699, 1.398), 16 sub-intervals with centre c_i, r = z' / c_i - 1,
+// |r| < 0.03; the interval around 1 has c = 1 so that small logarithms keep their relative accuracy) and a degree-9 series for
+// log1p(r): error < 2^-46 relative, 12 FP64 operations instead of ~35.  A Ziv test makes the result EXACTLY the rounding of
+// the true logarithm: if y (1 - 2^-44) and y (1 + 2^-44) round to different floats (probability 2^-19) the generic path
+// runs instead.  mfm_debug_normal_fast_check compares the two paths over the whole 32-bit input range (tests/test_gpu_rng.py).
+// {1 / c_i, log c_i}: generated with 50-digit arithmetic (scripts in DESIGN.md section 5), hex floats are exact
+static __constant__ double2 c_log16[16] = {
+    {0x1.661ec79f8f3bep+0, -0x1.57bf7808caadep-2}, {0x1.571ed4aaf883dp+0, -0x1.2bef0a7c06ddbp-2}, {0x1.49539f0f010b0p+0, -0x1.01eae7f513a67p-2},
+    {0x1.3c995b0b80385p+0, -0x1.b31d8a68224e9p-3}, {0x1.30d190c8864a5p+0, -0x1.6574f0ac07758p-3}, {0x1.25e227b0b8ea0p+0, -0x1.1aa2bc79c8100p-3},
+    {0x1.1bb4a4a1a343fp+0, -0x1.a4e76ce8c0e5ep-4}, {0x1.12358f08ae5bap+0, -0x1.1973c5a611cccp-4}, {0x1.0953f419900a7p+0, -0x1.252f438e10c1ep-5},
+    {0x1.0000000000000p+0, 0x0.0p+0},              {0x1.e573ae5c66190p-1, 0x1.b42db8ba5c447p-5},  {0x1.ca4b31f026aa0p-1, 0x1.c5e53aa362eb4p-4},
+    {0x1.b2036576afce6p-1, 0x1.526e57720db08p-3},  {0x1.9c2d163a1aa2dp-1, 0x1.bc2860d224770p-3},  {0x1.886e6037841edp-1, 0x1.1058bc8a07ee1p-2},
+    {0x1.767dcf5534862p-1, 0x1.4043057b6ee09p-2}};
+// copy the table to shared memory (divergent indices into constant memory serialise); block-wide, blockDim.x >= 16
+__device__ __forceinline__ void log_tab_load(double2* s) {
+    if (threadIdx.x < 16) s[threadIdx.x] = c_log16[threadIdx.x];
+    __syncthreads();
+}
+__device__ __forceinline__ float log_rn_f32(float z, const double2* __restrict__ tab) {
+    if (!(z > 1e-30f && z < 1e30f)) return (float)log((double)z);
+    const uint32_t ix = __float_as_uint(z);
+    const uint32_t tmp = ix - 0x3f330000u;
+    const int i = (int)((tmp >> 19) & 15u);
+    const int k = (int)tmp >> 23;
+    const uint32_t iz = ix - (tmp & 0xff800000u);
+    const double2 T = tab[i];
+    const double r = fma((double)__uint_as_float(iz), T.x, -1.0);
+    double p = 1.0 / 9.0;
+    p = fma(p, r, -1.0 / 8.0); p = fma(p, r, 1.0 / 7.0); p = fma(p, r, -1.0 / 6.0); p = fma(p, r, 1.0 / 5.0);
+    p = fma(p, r, -1.0 / 4.0); p = fma(p, r, 1.0 / 3.0); p = fma(p, r, -0.5);
+    const double y = fma((double)k, 0x1.62e42fefa39efp-1, T.y) + fma(r * r, p, r);
+    const float a = (float)(y * (1.0 - 0x1p-44)), b = (float)(y * (1.0 + 0x1p-44));
+    return a == b ? a : (float)log((double)z);
+}
+__device__ __forceinline__ float xla_log1p_f32_t(float t, const double2* tab) {
+    if (fabsf(t) < 1e-4f) return __fmul_rn(__fadd_rn(__fmul_rn(-0.5f, t), 1.0f), t);
+    return log_rn_f32(__fadd_rn(1.0f, t), tab);
+}
+__device__ __forceinline__ float xla_erfinv_tail_f32(float x, float w) {      // the polynomial part of xla_erfinv_f32
+    const bool lt = w < 5.0f;
+    w = lt ? __fadd_rn(w, -2.5f) : __fadd_rn(__fsqrt_rn(w), -3.0f);
+    float p = lt ? 2.81022636e-08f : -0.000200214257f;
+    p = __fadd_rn(lt ? 3.43273939e-07f : 0.000100950558f, __fmul_rn(p, w));
+    p = __fadd_rn(lt ? -3.5233877e-06f : 0.00134934322f, __fmul_rn(p, w));
+    p = __fadd_rn(lt ? -4.39150654e-06f : -0.00367342844f, __fmul_rn(p, w));
+    p = __fadd_rn(lt ? 0.00021858087f : 0.00573950773f, __fmul_rn(p, w));
+    p = __fadd_rn(lt ? -0.00125372503f : -0.0076224613f, __fmul_rn(p, w));
+    p = __fadd_rn(lt ? -0.00417768164f : 0.00943887047f, __fmul_rn(p, w));
+    p = __fadd_rn(lt ? 0.246640727f : 1.00167406f, __fmul_rn(p, w));
+    p = __fadd_rn(lt ? 1.50140941f : 2.83297682f, __fmul_rn(p, w));
+    const float r = __fmul_rn(p, x);
+    return fabsf(x) == 1.0f ? x * INFINITY : r;
+}
+__device__ __forceinline__ float bits_to_normal_t(uint32_t bits, const double2* tab) {
+    const float lo = -0.99999994f;
+    const float u = fmaxf(lo, __fadd_rn(__fmul_rn(bits_to_unit_float(bits), 2.0f), lo));
+    const float w = -xla_log1p_f32_t(-__fmul_rn(u, u), tab);
+    return __fmul_rn(1.41421354f, xla_erfinv_tail_f32(u, w));
+}
+
 // jax.random.normal float32 from 32 random bits:
 // u = max(lo, f*(1-lo)+lo) with lo = nextafter(-1,0); (1-lo) rounds to 2.0f in f32.
 __device__ __forceinline__ float bits_to_normal(uint32_t bits) {
@@ -137,6 +200,9 @@ __device__ __forceinline__ float bits64_to_normal(uint32_t hi, uint32_t lo) {
     const double lo_ = -0x1.fffffffffffffp-1;
     const double u = fmax(lo_, bits64_to_unit_double(hi, lo) * 2.0 + lo_);
     return (float)(0x1.6a09e667f3bcdp+0 * erfinv(u));
+}
+__device__ __forceinline__ float rng_normal_at_t(uint32_t k0, uint32_t k1, uint32_t i, uint32_t n, const double2* tab) {   // float32 draws
+    return bits_to_normal_t(threefry_stream_word(k0, k1, i, n), tab);
 }
 __device__ __forceinline__ float rng_normal_at(uint32_t k0, uint32_t k1, uint32_t i, uint32_t n, int x64) {
     if (!x64) return bits_to_normal(threefry_stream_word(k0, k1, i, n));

@@ -34,7 +34,7 @@ __device__ __forceinline__ float scalar_uniform(u32x2 key, int x64) {
 
 // Writes the proposal into xs (smem) and returns sum((x' - x - h g)^2) (warp-reduced).
 __device__ __forceinline__ float langevin_propose(u32x2 key, int d, float h, float sq2h, const float* __restrict__ x,
-                                                  const float* __restrict__ g, float* xs, int lane, int x64) {
+                                                  const float* __restrict__ g, float* xs, int lane, int x64, const double2* ltab) {
     const uint32_t half = ((uint32_t)d + 1u) >> 1;
     float sq = 0.0f;
     for (uint32_t b = lane; b < half; b += 32) {
@@ -46,7 +46,7 @@ __device__ __forceinline__ float langevin_propose(u32x2 key, int d, float h, flo
             if (has_hi) n_hi = rng_normal_at(key.a, key.b, hi, (uint32_t)d, 1);
         } else {
             const u32x2 o = threefry2x32(key.a, key.b, b, has_hi ? hi : 0u);
-            n_lo = bits_to_normal(o.a); n_hi = bits_to_normal(o.b);
+            n_lo = bits_to_normal_t(o.a, ltab); n_hi = bits_to_normal_t(o.b, ltab);
         }
         {
             const float xv = x[b], gv = g[b];
@@ -110,6 +110,8 @@ __global__ void __launch_bounds__(MALA_WARPS * 32)
 mala_small_kernel(mfm_target_t T, const uint32_t* __restrict__ rng_key, int n, int chain_offset, int n_total, float h,
                   float sq2h, float quarter, MalaIO io, int x64) {
     extern __shared__ float sm[];
+    __shared__ double2 ltab[16];
+    log_tab_load(ltab);                        // (before any warp leaves: contains a barrier)
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int c = blockIdx.x * MALA_WARPS + w;
     if (c >= n) return;
@@ -117,7 +119,7 @@ mala_small_kernel(mfm_target_t T, const uint32_t* __restrict__ rng_key, int n, i
     float* xs = sm + w * 2 * d;
     float* gs = xs + d;
     const ChainKeys ck = derive_chain_keys(rng_key, chain_offset + c, n_total);
-    const float sq_new = langevin_propose(ck.integrator, d, h, sq2h, io.x + (long long)c * d, io.g + (long long)c * d, xs, lane, x64);
+    const float sq_new = langevin_propose(ck.integrator, d, h, sq2h, io.x + (long long)c * d, io.g + (long long)c * d, xs, lane, x64, ltab);
     __syncwarp();
     const float ll = small_target_loglik_grad(T, xs, gs, lane);
     __syncwarp();
@@ -132,13 +134,15 @@ pines_propose_kernel(mfm_target_t T, const uint32_t* __restrict__ rng_key, int n
                      float h, float sq2h, const float* __restrict__ x, const float* __restrict__ g,
                      float* __restrict__ xprop, float* __restrict__ lik, float* __restrict__ sq_new_out,
                      float* __restrict__ u_out, float* __restrict__ xprop_amax, int x64) {
+    __shared__ double2 ltab[16];
+    log_tab_load(ltab);                        // (before any warp leaves: contains a barrier)
     const int lane = threadIdx.x & 31;
     const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= n) return;
     const int d = T.dim;
     const ChainKeys ck = derive_chain_keys(rng_key, chain_offset + c, n_total);
     float* xp = xprop + (long long)c * d;
-    const float sq = langevin_propose(ck.integrator, d, h, sq2h, x + (long long)c * d, g + (long long)c * d, xp, lane, x64);
+    const float sq = langevin_propose(ck.integrator, d, h, sq2h, x + (long long)c * d, g + (long long)c * d, xp, lane, x64, ltab);
     __syncwarp();
     float s = 0.0f, vm = 0.0f;
     for (int i = lane; i < d; i += 32) {

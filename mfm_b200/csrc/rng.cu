@@ -132,3 +132,24 @@ void mfm_host_threefry_split(const uint32_t key[2], int num, uint32_t* out) {
 }
 
 }  // extern "C"
+
+// Test hook (not in the ABI header): bits_to_normal_t (table-driven correctly rounded log) against bits_to_normal (generic double
+// log) on the inputs start, start + stride, ...: counts bit-level mismatches and how often the Ziv test sent the fast path to the
+// generic one (out[0], out[1]).
+__global__ void normal_fast_check_kernel(unsigned long long n, uint32_t start, uint32_t stride, unsigned long long* out) {
+    __shared__ double2 ltab[16];
+    log_tab_load(ltab);
+    unsigned long long bad = 0;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint32_t bits = start + (uint32_t)i * stride;
+        const float a = bits_to_normal_t(bits, ltab), b = bits_to_normal(bits);
+        bad += __float_as_uint(a) != __float_as_uint(b);
+    }
+    if (bad) atomicAdd(out, bad);
+}
+extern "C" int mfm_debug_normal_fast_check(unsigned long long n, uint32_t start, uint32_t stride, unsigned long long* out, mfm_stream_t stream) {
+    MFM_CUDA_CHECK(cudaMemsetAsync(out, 0, 2 * sizeof(unsigned long long), stream));
+    normal_fast_check_kernel<<<148 * 8, 256, 0, stream>>>(n, start, stride, out);
+    MFM_LAUNCH_CHECK();
+    return MFM_OK;
+}

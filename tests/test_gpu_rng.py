@@ -1,9 +1,10 @@
-"""CUDA threefry / uniform / normal vs the oracle: bits and uniforms bit-exact, normals <= 4 ulp
-(erf_inv goes through log1pf/sqrtf whose last-bit behaviour differs between libm and CUDA)."""
+"""CUDA threefry / uniform / normal vs the oracle: bits, uniforms and normals bit-exact (erf_inv restated operation for operation,
+the logarithm correctly rounded on both sides)."""
 import numpy as np
 import pytest
 import torch
 
+from mfm_b200 import _lib
 from oracle import threefry as tf
 from tests.helpers import key_dev, ulp_diff_f32
 
@@ -53,6 +54,22 @@ def test_normal_is_bit_exact(cuda, lib, n):
     exp = tf.normal(k, (n,))
     assert got.tobytes() == exp.tobytes(), int(ulp_diff_f32(got, exp).max())
     assert np.isfinite(got).all()
+
+
+def test_table_driven_log_gives_the_same_normals(cuda, lib):
+    """The hot kernels (pines_propose_kernel, fm_batch_kernel, mala_small_kernel) take the logarithm inside erf_inv from a
+    16-entry table + degree-9 series with a Ziv rounding test (csrc/common.cuh::log_rn_f32) instead of the generic double log:
+    the resulting normal must be the same float for EVERY 32-bit input (2^32 inputs in 16 interleaved sweeps of 2^28)."""
+    import ctypes
+    fn = lib.mfm_debug_normal_fast_check
+    fn.restype = ctypes.c_int
+    fn.argtypes = [ctypes.c_ulonglong, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p]
+    out = torch.zeros(2, dtype=torch.int64, device=cuda)
+    total = 0
+    for start in range(16):
+        _lib.check(fn(1 << 28, start, 16, out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        total += int(out[0].item())
+    assert total == 0, total
 
 
 @pytest.mark.parametrize("n", [1, 2, 3, 64, 1601, 100000])
