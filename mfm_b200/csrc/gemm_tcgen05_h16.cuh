@@ -542,8 +542,10 @@ cudaError_t launch_absmax(const float* x, long long ld, int rows, int cols, cons
 template <class Epi>
 inline bool eligible(const GemmShape& p, const Epi& epi) {
     // operands nobody tracked a maximum for cost one reduction pass: only worth it for layers that are tensor-bound
-    const bool tracked = p.a_amax != nullptr || p.a_bound > 0.0f || (p.a_split != nullptr && p.a_scale_src != nullptr);
-    if (!tracked && (long long)p.N * p.K < 512ll * 512ll) return false;
+    const float* bam = nullptr;
+    const bool a_tracked = p.a_amax != nullptr || p.a_bound > 0.0f || (p.a_split != nullptr && p.a_scale_src != nullptr);
+    const bool b_ready = p.b_mirror != nullptr || lookup_mirror_h16(p.B, &bam) != nullptr;      // else B needs its own reduction + in-kernel split
+    if (!(a_tracked && b_ready) && (long long)p.N * p.K < 512ll * 512ll) return false;
     return tc2p::eligible<true, false>(p, epi) && p.k_split == 0 && p.K % 16 == 0 && p.lda % 16 == 0 && p.ldb % 16 == 0 &&
            ((reinterpret_cast<uintptr_t>(p.A) | reinterpret_cast<uintptr_t>(p.B)) & 63) == 0;
 }

@@ -264,14 +264,15 @@ def test_pipelined_update_is_identical(cuda, lib):
         assert torch.equal(a, b)
 
 
-@pytest.mark.parametrize("name", ["phi-four", "4-mode"])
+@pytest.mark.parametrize("name", ["phi-four", "4-mode", "phi-four-1024"])
 def test_graph_replayed_iterations_are_identical(cuda, lib, name):
     """HotLoop(graph=True) replays the MALA + FM-update iteration from a CUDA graph (latency-bound reference shapes):
     same kernels on the same buffers => bit-identical chains, parameters and losses, flow-MH iterations (eager) included."""
     from types import SimpleNamespace
     from mfm_b200 import distributions as Dm, exe_flow_matching as E, random as mr
     from oracle import targets as OT
-    d, n, m, step = (64, 96, 3, 1e-4) if name == "phi-four" else (2, 128, 3, 0.2)
+    # (phi-four-1024: the reference's own chain count - tensor-core rows, narrow network: captured while no weight mirror exists)
+    d, n, m, step = {"phi-four": (64, 96, 3, 1e-4), "phi-four-1024": (64, 1024, 3, 1e-4), "4-mode": (2, 128, 3, 0.2)}[name]
     H, F = 128, 128
     args = SimpleNamespace(hutchs=False, num_importance_samples=0, mcmc_per_flow_steps=m, step_size=step, ref_dist="stdgauss",
                            cond_flow=True, ot_cond_flow=False, sigma=1e-4, adam_beta1=0.9, adam_beta2=0.999, adam_epsilon=1e-8,
@@ -285,7 +286,7 @@ def test_graph_replayed_iterations_are_identical(cuda, lib, name):
     x0 = torch.from_numpy(rng.uniform(-1, 1, (n, d)).astype(np.float32)).to(cuda)
     out = []
     for graph in (False, True):
-        if name == "phi-four":
+        if name.startswith("phi-four"):
             dist = Dm.PhiFour(d, device=cuda)
         else:
             t4 = OT.four_mode()
