@@ -118,7 +118,10 @@ void mfm_set_gemm_streamk(int enable);
  * K a multiple of 16: each operand is scaled by a per-tensor power of two (max |x| -> [2^14, 2^15)) and split into two fp16 parts,
  * the product is hi.hi' + hi.lo' + lo.hi' in three kind::f16 MMAs per 16 k-values; operand rounding 2^-22.  The maxima are exact:
  * every producer of a GEMM operand folds max |value| into a device slot, operands nobody tracked get one reduction pass.
- * 0 = fall back to tf32 hi*hi + bf16 cross terms.  Environment variable MFM_GEMM_H16=0|1. */
+ * Layers hand their results over pre-split (the epilogue writes the consumer's operand format next to the fp32 tensor) and the
+ * weight gradients read the same copies as MN-major tiles (csrc/gemm_tcgen05_wgrad16.cuh).  Used by the MLP entry points when the
+ * network is at least 512 wide and the batch has at least 256 rows; narrower / shorter problems keep the kernels below.
+ * 0 = fall back to tf32 hi*hi + bf16 cross terms everywhere.  Environment variable MFM_GEMM_H16=0|1. */
 void mfm_set_gemm_h16(int enable);
 int mfm_gemm_h16_enabled(void);
 /* one-line description of the arithmetic the dense layers currently use (bench.py quotes it) */
@@ -253,7 +256,10 @@ int mfm_fm_loss_grad(const mfm_field_t* f, const mfm_target_t* t, const uint32_t
 /* The same computation in two calls so that the multi-GPU host can overlap the gradient all-reduce with the
  * backward pass: part 1 = batch, forward, loss and the gradients of Dense_7..Dense_4, i.e. grads[w_off[4] .. n_params);
  * part 2 = the gradients of Dense_3..Dense_0, grads[0 .. w_off[4]), from the activations part 1 left in `ws` (same
- * arguments, same workspace, nothing else may use `ws` in between); part 0 = both (== mfm_fm_loss_grad). */
+ * arguments, same workspace, nothing else may use `ws` in between); part 0 = both (== mfm_fm_loss_grad).
+ * Part 1 also writes the BIAS gradients of Dense_3 and Dense_1 (they are column sums of signals it produces); both lie in
+ * grads[0 .. w_off[4]), which nothing reads before part 2 has returned.  The weight gradients run on a second, internal stream
+ * and are joined to `stream` before each call returns (not while `stream` is being captured into a CUDA graph). */
 int mfm_fm_loss_grad_part(const mfm_field_t* f, const mfm_target_t* t, const uint32_t* rng_key, int n, int chain_offset,
                           int n_total, float sigma, const float* positions, float* loss_out, float* grads, void* ws,
                           size_t ws_bytes, int part, mfm_stream_t stream);
