@@ -48,7 +48,10 @@ def _check(name, ot, dd, cuda, n, beta, per_chain, steps=3, rng_dtype=np.float32
         p_d = info_d.acceptance_rate.cpu().numpy(); p_o = info_o.acceptance_rate
         acc_d = info_d.is_accepted.cpu().numpy(); acc_o = info_o.is_accepted
         # decisions may only differ inside the tolerance band around the threshold
-        band = np.abs(p_o - dbg["u"]) < 1e-4 * np.maximum(1.0, np.abs(dbg["delta"]))
+        # (1e-5 - north_star's figure - where float32 can deliver it: the log-densities of the mixtures are O(10); for phi-four and
+        # pines |l| ~ 2e3, whose float32 ulp alone is 1.2e-4)
+        fac = 1e-5 if np.abs(st_in.logdensity).max() < 100.0 else 1e-4
+        band = np.abs(p_o - dbg["u"]) < fac * np.maximum(1.0, np.abs(dbg["delta"]))
         assert ((acc_d == acc_o) | band).all(), (name, it)
         n_flip += int((acc_d != acc_o).sum())
         ok = np.isfinite(dbg["delta"])
