@@ -15,7 +15,8 @@
  *     elements; MFM_ODE_GRAPH=0|1 forces either way) the loop is a CUDA-graph WHILE node and the call is asynchronous like all
  *     others; for large ones the host polls a device counter once per iteration, i.e. the call synchronises `stream`.
  *   - arithmetic type: float32 everywhere; dense contractions emulate fp32 products on the tensor cores (operands split
- *     into two 16-bit parts, three fp16 passes - or 3xTF32 for weight gradients - with fp32 accumulation): fp32-accurate results.
+ *     into two 16-bit parts, three fp16 passes - the weight gradients too; 3xTF32 for narrow / unaligned layers - with fp32 accumulation):
+ *     fp32-accurate results.
  */
 #ifndef MFM_B200_H
 #define MFM_B200_H

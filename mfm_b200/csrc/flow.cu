@@ -508,7 +508,7 @@ static constexpr float NORMAL_BOUND = 8.0f;
 // out_v[n,d] = sgn * v(x, tfield);  out_l[n] = -sgn * div v   (z != null: Hutchinson; else exact)
 int field_eval(const mfm_field_t& F, const mfm_target_t& T, int n, const float* x, const float* tfield,
                const float* z, float sgn, float* out_v, float* out_l, FieldBufs& B, cudaStream_t st,
-               const int* nr, const int* row_map, const float* x_amax) {
+               const int* nr, const int* row_map, const float* x_amax, const float* x_split) {
     const float* zw2_amax = (tc2h::gemm_h16() && B.amax && z) ? B.amax + AM_ZW2 : nullptr;   // written by field_prepare_probe
     const int d = F.dim, H = F.hidden, Fd = F.fourier_dim;
     int rc;
@@ -553,7 +553,8 @@ int field_eval(const mfm_field_t& F, const mfm_target_t& T, int n, const float* 
     if ((rc = dense(n, 2 * Fd, H, B.ff, 2 * Fd, WT_(0), 2 * Fd, B_(0), act, B.h0, H, nullptr, 0, 1, st, nr,
                     D_(OUT_(IN_(A_(nullptr, nullptr, 1.0f, slot(AM_H0)), B.ff_s, BD(AM_FF)), B.h0_s, AM_H0, 0, true), B.dh0, H)))) return rc;      // |cos|, |sin| <= 1
     if ((rc = dense(n, d, H, x, d, WT_(2), d, B_(2), act, B.h2, H, nullptr, 0, 1, st, nr,
-                    D_(OUT_(A_(x_amax, nullptr, 0, slot(AM_H2)), B.h2_s, AM_H2, 2, true), B.dh2, H)))) return rc;
+                    D_(OUT_((x_split && x_amax) ? IN_(A_(x_amax, nullptr, 0, slot(AM_H2)), x_split, x_amax) : A_(x_amax, nullptr, 0, slot(AM_H2)),
+                            B.h2_s, AM_H2, 2, true), B.dh2, H)))) return rc;
     {   // s_t and s_x: one scale for both halves of cat
         DenseAmax mt = OUT_(IN_(A_(slot(AM_H0), nullptr, 0, slot(AM_ST)), B.h0_s, BD(AM_H0)), B.cat_s + H, AM_ST, 1, true);
         // (h2's copy exists only when Dense_2 knew max |x|: dense() needs an input maximum to bound its output)
@@ -572,7 +573,7 @@ int field_eval(const mfm_field_t& F, const mfm_target_t& T, int n, const float* 
     mfm_target_t T1 = T; T1.beta = 1.0f;
     const bool want_div = out_l != nullptr;
     if ((rc = target_field_terms(T1, n, x, z, B.zkinv, F.grad_clip, B.gc, (want_div && z) ? B.hx : nullptr,
-                                 (want_div && !z) ? B.hx : nullptr, nr, st, x_amax, B.tscratch))) return rc;
+                                 (want_div && !z) ? B.hx : nullptr, nr, st, x_amax, B.tscratch, sp ? x_split : nullptr))) return rc;
     {
         GemmShape p{n, d, H, B.h6, (long long)H, WT_(7), (long long)H, nr};
         p.a_amax = slot(AM_H6);

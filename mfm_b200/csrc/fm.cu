@@ -364,7 +364,11 @@ static int fm_forward_backward(const mfm_field_t& F, const mfm_target_t& T, int 
     if (part != 2) {
         MFM_CUDA_CHECK(cudaMemsetAsync(grads, 0, (size_t)F.n_params * sizeof(float), st));
         if ((rc = field_prepare_weights(F, B, st))) return rc;
-        if ((rc = field_eval(F, T, n, M.xt, M.times, nullptr, 1.0f, M.v, nullptr, B, st, nullptr, nullptr, xt_amax))) return rc;
+        // x_t leaves the batch kernel with its exact maximum: its split16 copy (the weight gradient of Dense_2 needs it anyway) is
+        // made first, so that the two GEMMs that read x_t - Dense_2 and the pines K^-1 product - load it pre-split too
+        const bool xt_pre = wspd && xt_amax != nullptr;
+        if (xt_pre && (rc = presplit_weights(M.xt, M.xt_s, (long long)n * d, xt_amax, st))) return rc;
+        if ((rc = field_eval(F, T, n, M.xt, M.times, nullptr, 1.0f, M.v, nullptr, B, st, nullptr, nullptr, xt_amax, xt_pre ? M.xt_s : nullptr))) return rc;
         const long long tot = (long long)n * d;
         const int lb = (int)((tot + 255) / 256 < FM_LOSS_BLOCKS ? (tot + 255) / 256 : FM_LOSS_BLOCKS);
         fm_loss_delta_kernel<<<lb, 256, 0, st>>>(tot, M.v, M.target, B.gc, M.delta, M.dgt, M.blockpart, slot(AM_DELTA), slot(AM_DGT));
@@ -374,7 +378,7 @@ static int fm_forward_backward(const mfm_field_t& F, const mfm_target_t& T, int 
         // split16 copies of the [n, d] operands of the weight gradients of layers 2, 7 and 4 (their maxima are exact only now:
         // one element-wise pass each, 8 B per element)
         if (wspd) {
-            if ((rc = presplit_weights(M.xt, M.xt_s, tot, xa_src, st))) return rc;
+            if (!xt_pre && (rc = presplit_weights(M.xt, M.xt_s, tot, xa_src, st))) return rc;
             if ((rc = presplit_weights(M.delta, M.delta_s, tot, slot(AM_DELTA), st))) return rc;
             if ((rc = presplit_weights(M.dgt, M.dgt_s, tot, slot(AM_DGT), st))) return rc;
         }

@@ -40,7 +40,7 @@ int target_value_and_grad(const mfm_target_t& T, int n, const float* x, float* l
 // outputs: gc = clip(grad), hvc = 1[|grad|<clip] * (H z), hdc = 1[|grad|<clip] * diag(H)  (hvc/hdc optional)
 int target_field_terms(const mfm_target_t& T, int n, const float* x, const float* z, const float* zkinv, float clip,
                        float* gc, float* hvc, float* hdc, const int* n_rows_dev, cudaStream_t st, const float* x_amax = nullptr,
-                       float* scratch = nullptr);
+                       float* scratch = nullptr, const float* x_split = nullptr);
 
 // ---- vector field (flow.cu) -------------------------------------------------------------------
 // Slots of the per-workspace pool of tensor maxima (FieldBufs::amax, 64 floats): max |value| of every tensor that is the A
@@ -122,6 +122,7 @@ int dense(int n, int in, int out, const float* A, long long lda, const float* WT
 // x_amax (optional): device slot with max |x| (null: one reduction pass inside the first GEMM that reads x).
 int field_eval(const mfm_field_t& F, const mfm_target_t& T, int n, const float* x, const float* tfield,
                const float* z, float sgn, float* out_v, float* out_l, FieldBufs& B, cudaStream_t st,
-               const int* n_rows_dev = nullptr, const int* row_map = nullptr, const float* x_amax = nullptr);
+               const int* n_rows_dev = nullptr, const int* row_map = nullptr, const float* x_amax = nullptr,
+               const float* x_split = nullptr);    // x_split: split16 copy of x scaled from *x_amax (the FM batch's), or null
 
 }  // namespace mfm

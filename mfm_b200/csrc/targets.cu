@@ -319,7 +319,8 @@ int target_value_and_grad(const mfm_target_t& T, int n, const float* x, float* l
 }
 
 int target_field_terms(const mfm_target_t& T, int n, const float* x, const float* z, const float* zkinv, float clip,
-                       float* gc, float* hvc, float* hdc, const int* n_rows_dev, cudaStream_t st, const float* x_amax, float* scratch) {
+                       float* gc, float* hvc, float* hdc, const int* n_rows_dev, cudaStream_t st, const float* x_amax, float* scratch,
+                       const float* x_split) {
     if (n <= 0) return MFM_OK;
     if (T.kind == MFM_TARGET_PINES_WHITE) {
         // scratch: 4 x [n, d] (f, r / g_lin, q / s, h_lin).  Rows beyond a device-side active count are computed too (harmless).
@@ -340,6 +341,7 @@ int target_field_terms(const mfm_target_t& T, int n, const float* x, const float
     if (T.kind == MFM_TARGET_PINES) {
         GemmShape p{n, T.dim, T.dim, x, (long long)T.dim, T.kinv, (long long)T.dim, n_rows_dev};
         p.a_amax = x_amax; kinv_mirror(T, p);
+        if (x_split && x_amax) { p.a_split = x_split; p.a_scale_src = x_amax; }      // the caller's pre-split copy of x
         EpiPinesField e{x, (long long)T.dim, T.counts, T.kinv_mu, T.kinv_diag, z, zkinv, T.poisson_a, clip, gc, hvc, hdc, (long long)T.dim};
         MFM_CUDA_CHECK((launch_gemm<true, false>(p, e, st)   /* K^-1 is symmetric: read it as the K-major operand */));
         return MFM_OK;
