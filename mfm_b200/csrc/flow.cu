@@ -47,6 +47,7 @@ struct EpiFieldV {
     static constexpr bool kRowSum = false;
     float* V; long long ldv; const float* bias; const float* gt; const float* gc; long long ld; float sgn;
     const int* row_map;      // optional: compact row -> chain index of the output
+    float* amax_out = nullptr; mutable float vmax = 0.0f;      // optional: max |v| (the FM pass bounds its loss gradient with it)
     struct Aux { float bias, gt, gc; int orow; };
     __device__ __forceinline__ Aux load(int row, int col) const {
         const long long o = (long long)row * ld + col;
@@ -55,7 +56,8 @@ struct EpiFieldV {
         return a;
     }
     __device__ __forceinline__ float apply(int, int col, float acc, const Aux& a) const {
-        V[(long long)a.orow * ldv + col] = sgn * (acc + a.bias + a.gt * a.gc);
+        const float v = sgn * (acc + a.bias + a.gt * a.gc);
+        V[(long long)a.orow * ldv + col] = v; vmax = fmaxf(vmax, fabsf(v));
         return 0.0f;
     }
     __device__ __forceinline__ float operator()(int row, int col, float acc) const { return apply(row, col, acc, load(row, col)); }
@@ -75,6 +77,7 @@ struct EpiFieldV {
         v.x = sgn * (acc.x + c.bias.x + r.gt.x * r.gc.x); v.y = sgn * (acc.y + c.bias.y + r.gt.y * r.gc.y);
         v.z = sgn * (acc.z + c.bias.z + r.gt.z * r.gc.z); v.w = sgn * (acc.w + c.bias.w + r.gt.w * r.gc.w);
         st4(V + (long long)r.orow * ldv + col, v);
+        vmax = amax4(vmax, v);
         return 0.0f;
     }
 };
@@ -579,6 +582,7 @@ int field_eval(const mfm_field_t& F, const mfm_target_t& T, int n, const float* 
         p.a_amax = slot(AM_H6);
         if (sp) { p.a_split = B.h6_s; p.a_scale_src = BD(AM_H6); }
         EpiFieldV e{out_v, (long long)d, B_(7), B.gt, B.gc, (long long)d, sgn, row_map};
+        e.amax_out = am ? B.v_amax : nullptr;
         MFM_CUDA_CHECK((launch_gemm<true, false>(p, e, st)));
     }
     if (!want_div) return MFM_OK;

@@ -24,7 +24,7 @@ fm_batch_kernel(const uint32_t* __restrict__ rng_key, int n, int chain_offset, i
     const int lane = threadIdx.x & 31;
     const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= n) return;                                                    // whole warps leave together
-    float vm = 0.0f;
+    float vm = 0.0f, tm = 0.0f;
     const uint32_t gc = (uint32_t)(chain_offset + c);
     // key_time, key_ref, key_gauss, key_ot = split(rng_key, 4)
     const u32x2 k_time = threefry_split_key(rng_key[0], rng_key[1], 0u, 4u);
@@ -53,11 +53,15 @@ fm_batch_kernel(const uint32_t* __restrict__ rng_key, int n, int chain_offset, i
             // sigma*eps + t*x + (1-t)*x0, left to right (:167)
             const float xtv = __fadd_rn(__fadd_rn(__fmul_rn(sigma, eps), __fmul_rn(t, xv)), __fmul_rn(omt, x0));
             xt[idx] = xtv; vm = fmaxf(vm, fabsf(xtv));
-            target[idx] = xv - x0;                                         // :168
+            const float tg = xv - x0;                                      // :168
+            target[idx] = tg; tm = fmaxf(tm, fabsf(tg));
         }
     }
     if (lane == 0) times[c] = t;
-    if (xt_amax) amax_publish_warp(xt_amax, vm);                           // x_t is the A operand of Dense_2 / the K^-1 GEMM
+    if (xt_amax) {
+        amax_publish_warp(xt_amax, vm);                                    // x_t is the A operand of Dense_2 / the K^-1 GEMM
+        amax_publish_warp(xt_amax + (AM_TGT - AM_X), tm);                  // (xt_amax is slot AM_X of the pool) bounds the loss gradient
+    }
 }
 
 // Non-conditional variant, flow_fn (exe_flow_matching.py:139-147, --cond_flow off):
@@ -106,6 +110,43 @@ fm_loss_delta_kernel(long long total, const float* __restrict__ v, const float* 
         m0 = fmaxf(m0, fabsf(dl)); m1 = fmaxf(m1, fabsf(dg));
     }
     if (delta_amax) { amax_publish_warp(delta_amax, m0); amax_publish_warp(dgt_amax, m1); }   // both are GEMM operands of the backward pass
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) block_partial[blockIdx.x] = s;
+}
+
+// The same, four elements per thread, ALSO writing delta and dgt in the split16 layout of the scaled-fp16 GEMMs (they are the
+// A operands of two backward-data layers and the G operands of two weight gradients).  Their scales must be known before the
+// first element is written: |delta| <= 2 (max |v| + max |target|) with both maxima exact (tracked by EpiFieldV and the batch
+// kernel), |dgt| <= |delta| * clip (gc is clipped to [-clip, clip]).  The bounds go to bound_out[0 / 1] for the consumers.
+__global__ void __launch_bounds__(256)
+fm_loss_delta_split_kernel(long long total4, const float4* __restrict__ v, const float4* __restrict__ target, const float4* __restrict__ gc,
+                           float4* __restrict__ delta, float4* __restrict__ dgt, float* __restrict__ block_partial,
+                           float* __restrict__ delta_amax, float* __restrict__ dgt_amax, const float* __restrict__ v_amax,
+                           const float* __restrict__ tgt_amax, float clip, float* __restrict__ delta_s, float* __restrict__ dgt_s,
+                           float* __restrict__ bound_delta, float* __restrict__ bound_dgt) {
+    __shared__ float red[32];
+    const float bd = 2.0f * (*v_amax + *tgt_amax), bg = bd * clip;
+    const float sd = __uint_as_float(h16_scale_exp_(bd) << 23), sg = __uint_as_float(h16_scale_exp_(bg) << 23);
+    if (blockIdx.x == 0 && threadIdx.x == 0) { *bound_delta = bd; *bound_dgt = bg; }
+    float s = 0.0f, m0 = 0.0f, m1 = 0.0f;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 a = v[i], b = target[i], g = __ldg(gc + i);
+        const float4 df = make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w);
+        s += df.x * df.x; s += df.y * df.y; s += df.z * df.z; s += df.w * df.w;        // (same order as the scalar kernel's grid-stride sum is NOT required: the partials differ anyway)
+        const float4 dl = make_float4(2.0f * df.x, 2.0f * df.y, 2.0f * df.z, 2.0f * df.w);
+        const float4 dg = make_float4(dl.x * g.x, dl.y * g.y, dl.z * g.z, dl.w * g.w);
+        delta[i] = dl; dgt[i] = dg;
+        m0 = amax4(m0, dl); m1 = amax4(m1, dg);
+        const long long e = 4 * i;                                                      // first of the four elements
+        uint2 hp, lp;
+        split_pair(dl.x * sd, dl.y * sd, hp.x, lp.x); split_pair(dl.z * sd, dl.w * sd, hp.y, lp.y);
+        char* p = reinterpret_cast<char*>(delta_s + (e & ~15ll)) + 2 * (e & 15);
+        *reinterpret_cast<uint2*>(p) = hp; *reinterpret_cast<uint2*>(p + 32) = lp;
+        split_pair(dg.x * sg, dg.y * sg, hp.x, lp.x); split_pair(dg.z * sg, dg.w * sg, hp.y, lp.y);
+        p = reinterpret_cast<char*>(dgt_s + (e & ~15ll)) + 2 * (e & 15);
+        *reinterpret_cast<uint2*>(p) = hp; *reinterpret_cast<uint2*>(p + 32) = lp;
+    }
+    if (delta_amax) { amax_publish_warp(delta_amax, m0); amax_publish_warp(dgt_amax, m1); }
     s = block_sum(s, red);
     if (threadIdx.x == 0) block_partial[blockIdx.x] = s;
 }
@@ -345,7 +386,7 @@ static FmAux* fm_aux() {
 // the workspace.  The split lets the host all-reduce the tail while part 2 runs.
 // xt_amax: slot holding max |x_t| when the batch kernel tracked it (null: field_eval reduces it).
 static int fm_forward_backward(const mfm_field_t& F, const mfm_target_t& T, int n, FmBufs& M, float* loss_out,
-                               float* grads, cudaStream_t st, int part, const float* xt_amax = nullptr) {
+                               float* grads, cudaStream_t st, int part, const float* xt_amax = nullptr, bool tgt_tracked = false) {
     const int d = F.dim, H = F.hidden, Fd = F.fourier_dim;
     FieldBufs& B = M.B;
     int rc;
@@ -359,6 +400,13 @@ static int fm_forward_backward(const mfm_field_t& F, const mfm_target_t& T, int 
     const bool wsp = !no_wsplit && !no_split && am != nullptr && M.d6_s != nullptr && B.h0_s != nullptr && H % 16 == 0 && (2 * Fd) % 16 == 0 && n >= 256 &&
                      ((reinterpret_cast<uintptr_t>(B.h0_s) | reinterpret_cast<uintptr_t>(B.cat_s)) & 63) == 0;
     const bool wspd = wsp && d % 16 == 0;      // the [n, d] operands have copies too
+    // the loss kernel writes delta / dgt pre-split itself when it can bound them beforehand (tracked maxima of v and of the
+    // targets, a clipped score): no separate passes, and the two backward-data layers that read them load the copies
+    static const bool no_fused_loss = getenv("MFM_FM_NOFUSEDLOSS") != nullptr;
+    const bool fused_loss = !no_fused_loss && wspd && tgt_tracked && xt_amax != nullptr && F.grad_clip > 0.0f;
+    // scale sources of the delta / dgt copies: their bounds (fused) or their exact maxima (separate passes)
+    const float* delta_src = fused_loss ? am + AM_BOUND + AM_DELTA : slot(AM_DELTA);
+    const float* dgt_src = fused_loss ? am + AM_BOUND + AM_DGT : slot(AM_DGT);
     // max |x_t|: the batch kernel's slot, or the one field_eval reduces into when d is a multiple of 16 (else untracked: no h2 copy)
     const float* xa_src = xt_amax ? xt_amax : (d % 16 == 0 ? slot(AM_X) : nullptr);
     if (part != 2) {
@@ -368,10 +416,18 @@ static int fm_forward_backward(const mfm_field_t& F, const mfm_target_t& T, int 
         // made first, so that the two GEMMs that read x_t - Dense_2 and the pines K^-1 product - load it pre-split too
         const bool xt_pre = wspd && xt_amax != nullptr;
         if (xt_pre && (rc = presplit_weights(M.xt, M.xt_s, (long long)n * d, xt_amax, st))) return rc;
+        B.v_amax = fused_loss ? slot(AM_V) : nullptr;
         if ((rc = field_eval(F, T, n, M.xt, M.times, nullptr, 1.0f, M.v, nullptr, B, st, nullptr, nullptr, xt_amax, xt_pre ? M.xt_s : nullptr))) return rc;
+        B.v_amax = nullptr;
         const long long tot = (long long)n * d;
         const int lb = (int)((tot + 255) / 256 < FM_LOSS_BLOCKS ? (tot + 255) / 256 : FM_LOSS_BLOCKS);
-        fm_loss_delta_kernel<<<lb, 256, 0, st>>>(tot, M.v, M.target, B.gc, M.delta, M.dgt, M.blockpart, slot(AM_DELTA), slot(AM_DGT));
+        if (fused_loss)
+            fm_loss_delta_split_kernel<<<lb, 256, 0, st>>>(tot / 4, reinterpret_cast<const float4*>(M.v), reinterpret_cast<const float4*>(M.target),
+                                                           reinterpret_cast<const float4*>(B.gc), reinterpret_cast<float4*>(M.delta), reinterpret_cast<float4*>(M.dgt),
+                                                           M.blockpart, slot(AM_DELTA), slot(AM_DGT), slot(AM_V), slot(AM_TGT), F.grad_clip,
+                                                           M.delta_s, M.dgt_s, am + AM_BOUND + AM_DELTA, am + AM_BOUND + AM_DGT);
+        else
+            fm_loss_delta_kernel<<<lb, 256, 0, st>>>(tot, M.v, M.target, B.gc, M.delta, M.dgt, M.blockpart, slot(AM_DELTA), slot(AM_DGT));
         MFM_LAUNCH_CHECK();
         final_sum_kernel<<<1, 256, 0, st>>>(lb, M.blockpart, loss_out);
         MFM_LAUNCH_CHECK();
@@ -379,8 +435,10 @@ static int fm_forward_backward(const mfm_field_t& F, const mfm_target_t& T, int 
         // one element-wise pass each, 8 B per element)
         if (wspd) {
             if (!xt_pre && (rc = presplit_weights(M.xt, M.xt_s, tot, xa_src, st))) return rc;
-            if ((rc = presplit_weights(M.delta, M.delta_s, tot, slot(AM_DELTA), st))) return rc;
-            if ((rc = presplit_weights(M.dgt, M.dgt_s, tot, slot(AM_DGT), st))) return rc;
+            if (!fused_loss) {
+                if ((rc = presplit_weights(M.delta, M.delta_s, tot, slot(AM_DELTA), st))) return rc;
+                if ((rc = presplit_weights(M.dgt, M.dgt_s, tot, slot(AM_DGT), st))) return rc;
+            }
         }
     }
     auto bias_grad = [&](const float* a, long long lda, int cols, float* out) -> int {
@@ -457,9 +515,9 @@ static int fm_forward_backward(const mfm_field_t& F, const mfm_target_t& T, int 
     if (part != 2) {
     // layer 7 (nn_xt head): y = h6 W7 + b7
     if ((rc = fork_w())) return rc;
-    if ((rc = wgrad(n, H, d, B.h6, H, M.delta, d, GW_(7), sb, sbf, sw, WS_(wspd, B.h6_s, BD(AM_H6), M.delta_s, slot(AM_DELTA))))) return rc;
+    if ((rc = wgrad(n, H, d, B.h6, H, M.delta, d, GW_(7), sb, sbf, sw, WS_(wspd, B.h6_s, BD(AM_H6), M.delta_s, delta_src)))) return rc;
     if ((rc = bias_grad(M.delta, d, d, GB_(7)))) return rc;
-    if ((rc = dgrad(n, H, d, M.delta, d, W_(7), M.d6, H, g_h6, H, nullptr, 0, st, G_(slot(AM_DELTA), nullptr, nullptr, slot(AM_D6), M.d6_s, AM_D6, 7, nullptr), M.cspart, &cs6))) return rc;
+    if ((rc = dgrad(n, H, d, M.delta, d, W_(7), M.d6, H, g_h6, H, nullptr, 0, st, G_(slot(AM_DELTA), fused_loss ? M.delta_s : nullptr, delta_src, slot(AM_D6), M.d6_s, AM_D6, 7, nullptr), M.cspart, &cs6))) return rc;
     if ((rc = bias_grad_cs(cs6, M.d6, H, H, GB_(6)))) return rc;        // bias gradients: column sums of the signal just written
     // layer 6
     if ((rc = fork_w())) return rc;
@@ -477,11 +535,11 @@ static int fm_forward_backward(const mfm_field_t& F, const mfm_target_t& T, int 
                     G_(slot(AM_D5), M.d5_s, BD(AM_D5), nullptr, M.dcat_s + H, AM_DCT0, 5, nullptr)))) return rc;
     // layer 4 (nn_t head): g_t = s_t W4 + b4, dL/dg_t = delta * clip(grad logprob)
     if ((rc = fork_w())) return rc;
-    if ((rc = wgrad(n, H, d, B.cat + H, 2 * H, M.dgt, d, GW_(4), sb, sbf, sw, WS_(wspd, B.cat_s + H, BD(AM_ST), M.dgt_s, slot(AM_DGT))))) return rc;
+    if ((rc = wgrad(n, H, d, B.cat + H, 2 * H, M.dgt, d, GW_(4), sb, sbf, sw, WS_(wspd, B.cat_s + H, BD(AM_ST), M.dgt_s, dgt_src)))) return rc;
     if ((rc = bias_grad(M.dgt, d, d, GB_(4)))) return rc;
     // d s_t = (dgt W4^T + joint part) * relu'(s_t)   (in place)
     if ((rc = dgrad(n, H, d, M.dgt, d, W_(4), M.dcat + H, 2 * H, g_cat + H, 2 * H, M.dcat + H, 2 * H, st,
-                    G_(slot(AM_DGT), nullptr, nullptr, slot(AM_DCT), M.dcat_s + H, AM_DCT, 4, sp ? BD(AM_DCT0) : nullptr), M.cspart, &cst))) return rc;
+                    G_(slot(AM_DGT), fused_loss ? M.dgt_s : nullptr, dgt_src, slot(AM_DCT), M.dcat_s + H, AM_DCT, 4, sp ? BD(AM_DCT0) : nullptr), M.cspart, &cst))) return rc;
     if ((rc = bias_grad_cs(cst, M.dcat + H, 2 * H, H, GB_(1)))) return rc;
     }
     if (part == 1) return join_w();
@@ -607,7 +665,7 @@ int mfm_fm_loss_grad_part(const mfm_field_t* f, const mfm_target_t* t, const uin
                                                              positions, M.times, M.xt, M.target, xt_amax, rng_x64());
         MFM_LAUNCH_CHECK();
     }
-    return fm_forward_backward(*f, *t, n, M, loss_out, grads, stream, part, xt_amax);
+    return fm_forward_backward(*f, *t, n, M, loss_out, grads, stream, part, xt_amax, xt_amax != nullptr);   // fm_batch_kernel tracks max |target| too
 }
 
 int mfm_fm_loss_grad_uncond(const mfm_field_t* f, const mfm_target_t* t, const uint32_t* rng_key, int n, int chain_offset,

@@ -52,6 +52,8 @@ enum AmaxSlot {
     AM_W = 16,           // max |parameter| of the flat MLP buffer (one scale for both weight mirrors)
     AM_X,                // the field's input x (FM batch x_t, ODE stage input)
     AM_DELTA, AM_DGT, AM_D6, AM_D5, AM_DCX, AM_DCT0, AM_DCT, AM_D2, AM_D0, AM_ZW2,
+    AM_V,                // the field's output v (FM forward: bounds the loss gradient before it is written)
+    AM_TGT,              // the FM regression targets x - x0
     AM_WNORM_COL = 32,   // [8] per dense layer: max over outputs of sum_in |W[in][out]|  (bounds the forward product)
     AM_WNORM_ROW = 40,   // [8] per dense layer: max over inputs of sum_out |W[in][out]|   (bounds the backward-data product)
     AM_BIAS = 48,        // [8] per dense layer: max |bias|
@@ -71,6 +73,7 @@ struct FieldBufs {
     // derivative is read off the sign of the output): what the backward pass and the tangents multiply by
     float *dh0, *dh2, *dcat, *dh5, *dh6;
     float* tscratch;        // 4 x [n, d]: the whitened pines target's field terms (four GEMMs against the Cholesky factor)
+    float* v_amax = nullptr;   // optional slot receiving max |v| of the next field evaluation (set by the FM pass)
 };
 namespace tc2p {
 void register_cross(const float* base, size_t n_floats, const float* mirror);
