@@ -171,6 +171,41 @@ class IndepGaussian(Target):
         return dt.type(self.mean) + dt.type(self.std) * tf.vmap_normal(keys, self.dim, dtype)
 
 
+class PhiFourBase(Target):
+    """distributions.py:168-226, prior_type='coupled' (the default; ref_dists['phifour'], exe_flow_matching.py:53): the Gaussian
+    N(0, P^-1) with the tridiagonal precision P = beta (diag(2 c + 1 / c) - c (sub + super diagonal)), c = alpha dim - the
+    quadratic part of the phi-four action.  sample_model = chol_cov @ normal(key, (dim,)) with chol_cov = (L^-1)^T, L the lower
+    Cholesky factor of P.  ('coupled_pbc' cannot be constructed in the reference: it assigns into jnp arrays and divides dim to a
+    float.)  Oracle only: the device path supports diagonal reference distributions."""
+
+    def __init__(self, dim, alpha=0.1, beta=20.0):
+        self.dim = dim
+        c = alpha * dim
+        prec = np.eye(dim) * (3 * c + 1 / c)
+        ones = np.ones((dim, dim))
+        prec -= c * np.triu(np.triu(ones, k=-1).T, k=-1)          # as coded: a tridiagonal band of ones (main diagonal included)
+        self.prec = beta * prec
+        sign, logabs = np.linalg.slogdet(self.prec)
+        self.prior_log_det = -sign * logabs                       # = log det of the covariance
+        L = np.linalg.cholesky(self.prec)
+        import scipy.linalg
+        self.chol_cov = scipy.linalg.solve_triangular(L, np.eye(dim), lower=True).T
+
+    def loglik(self, x):
+        dt = x.dtype
+        P = self.prec.astype(dt)
+        q = np.einsum("ni,ij,nj->n", x, P, x)
+        return -dt.type(0.5) * q - dt.type(0.5) * dt.type(self.dim * np.log(2 * np.pi) + self.prior_log_det)
+
+    def grad_loglik(self, x):
+        return -(x @ self.prec.astype(x.dtype))                   # P is symmetric
+
+    def sample(self, keys, dtype=np.float32):
+        """vmap(sample_model)(keys)."""
+        z = tf.vmap_normal(keys, self.dim, dtype)
+        return z @ self.chol_cov.astype(np.dtype(dtype)).T
+
+
 class PhiFour(Target):
     """distributions.py:114-165, Dirichlet b.c. with value 0, no tilt."""
 

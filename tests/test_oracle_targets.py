@@ -147,3 +147,28 @@ def test_whitened_pines_oracle_by_finite_differences():
     assert abs(t.hdiag(e)[0, 7] - ((t.grad(e[:1] + h * ej) - t.grad(e[:1] - h * ej)) / (2 * h))[0, 7]) < 1e-6
     f = e @ t.L.T + t.mu
     assert np.allclose(t.logprob(e) - u.logprob(f), t.half_log_det, rtol=0, atol=1e-8)
+
+
+def test_phi_four_base_reference_distribution():
+    """PhiFourBase (distributions.py:168-226, 'coupled'): the Gaussian whose precision is the quadratic part of the phi-four
+    action - checked against the action itself, against scipy's multivariate normal, and the sampler against its covariance."""
+    d = 12
+    ref = OT.PhiFourBase(d, 0.1, 20.0)
+    c = 0.1 * d
+    P = 20.0 * (np.diag(np.full(d, 2 * c + 1 / c)) - c * (np.eye(d, k=1) + np.eye(d, k=-1)))
+    assert np.allclose(ref.prec, P)
+    # the quadratic part of PhiFour's energy (Dirichlet boundary, value 0): c/2 sum (x_{i+1} - x_i)^2 with zero padding + x^2 / (2 c)
+    x = np.random.default_rng(0).standard_normal((5, d))
+    xp = np.pad(x, ((0, 0), (1, 1)))
+    quad = 20.0 * (0.5 * c * (np.diff(xp, axis=1) ** 2).sum(1) + (x ** 2).sum(1) / (2 * c))
+    assert np.allclose(0.5 * np.einsum("ni,ij,nj->n", x, ref.prec, x), quad)
+    mvn = scipy.stats.multivariate_normal(np.zeros(d), np.linalg.inv(P))
+    assert np.allclose(ref.loglik(x), mvn.logpdf(x), rtol=1e-12, atol=1e-10)
+    eps = 1e-6
+    g_fd = np.stack([(ref.loglik(x + eps * np.eye(d)[i]) - ref.loglik(x - eps * np.eye(d)[i])) / (2 * eps) for i in range(d)], 1)
+    assert np.allclose(ref.grad_loglik(x), g_fd, rtol=1e-6, atol=1e-6)
+    assert np.allclose(ref.chol_cov @ ref.chol_cov.T, np.linalg.inv(P))
+    keys = tf.split(tf.PRNGKey(3), 4)
+    s = ref.sample(keys, np.float64)
+    z = tf.vmap_normal(keys, d, np.float64)
+    assert np.allclose(s, z @ ref.chol_cov.T)                  # sample_model(key) = chol_cov @ normal(key, (d,)), row by row
